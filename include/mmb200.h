@@ -1,0 +1,150 @@
+/*
+ * mmb200.h — C ABI of libmmb200.so: batched material-point updates on NVIDIA B200 (sm_100a).
+ *
+ * One call = one pass of `material_response` over N independent material (quadrature) points.
+ * The reference (kimauth/MaterialModels.jl) has NO batched entry point and NO FFI: its boundary is
+ * the Julia generic
+ *     material_response(m, strain, state, Δt; cache, options) -> (stress, tangent, new_state)
+ * (reference src/MaterialModels.jl:41-52), called once per point by the FE assembler.  Each
+ * function below replaces the loop over points around one method of that generic; the reference
+ * method it replaces is cited next to it.  INTEGRATION.md shows the Julia `ccall` stubs.
+ *
+ * Conventions (identical to Tensors.jl storage, so Julia arrays reinterpret zero-copy):
+ *   SymmetricTensor{2,3}: 6 doubles  (11,21,31,22,32,33)
+ *   Tensor{2,3}         : 9 doubles  column-major (11,21,31,12,22,32,13,23,33)
+ *   SymmetricTensor{4,3}: 36 doubles, index I + 6*J, I<->(ij), J<->(kl) in the pair order above
+ *   Tensor{1,dim}       : dim doubles, LAST component = normal separation (XuNeedleman)
+ * Layout of every per-point array with `nc` components:
+ *   MM_LAYOUT_SOA: a[c*N + i]   (component-major; the fast path — fully coalesced)
+ *   MM_LAYOUT_AOS: a[i*nc + c]  (== reinterpret(Float64, ::Vector{SymmetricTensor{2,3,Float64,6}}))
+ * State packing: Plastic  [εᵖ(6), κ, α(6), μ]            = 14 doubles (src/Plastic.jl:41-46 field order)
+ *                Crystal  [σ(6), κ(S), α(S), μ(S)], S=12 = 42 doubles (CrystalViscoPlastic.jl:52-57)
+ *
+ * All array pointers of the mm_* entry points are DEVICE pointers owned by the caller; nothing is
+ * allocated on the hot path; `stream` is a cudaStream_t (NULL = default stream); calls are
+ * asynchronous with respect to the host.  The mmh_* entry points take HOST pointers and run the
+ * same kernels through a pipelined H2D -> kernel -> D2H chunk loop (blocking).
+ * Return value: 0 ok, <0 error (see mm_last_error()).  Non-convergence of a local Newton solve is
+ * never an abort: it is counted in *n_fail and flagged per point; the host mirror raises the
+ * reference's error text ("Material model not converged. Could not find material state.",
+ * src/Plastic.jl:157, CrystalViscoPlastic.jl:92) when the count is non-zero.
+ */
+#ifndef MMB200_H
+#define MMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM_LAYOUT_SOA 0
+#define MM_LAYOUT_AOS 1
+
+#define MM_NSLIP 12 /* FCC 4x3 and BCC 6x2 both give 12 systems (slipsystems.jl:9-35) */
+
+#define MM_OK 0
+#define MM_ERR_ARG (-1)
+#define MM_ERR_CUDA (-2)
+#define MM_ERR_NOGPU (-3)
+
+/* hyperelastic models (mm_hyper `model`) */
+#define MM_NEOHOOK 0  /* src/FiniteStrain/neohook.jl:35-43  */
+#define MM_YEOH 1     /* src/FiniteStrain/yeoh.jl:37-54     */
+#define MM_STVENANT 2 /* src/FiniteStrain/stvenant.jl:36-48 */
+/* strain measure handed to mm_hyper (`strain_kind`) */
+#define MM_STRAIN_C 0 /* RightCauchyGreen C, 6 comps (native, neohook.jl:35)                       */
+#define MM_STRAIN_F 1 /* DeformationGradient F, 9 comps; C = tdot(F) = FᵀF (src/traits.jl:35-38) */
+/* crystal structures (slipsystems.jl:3-4) */
+#define MM_FCC 0
+#define MM_BCC 1
+
+/* per-point flag bits written by mm_plastic */
+#define MM_FLAG_PLASTIC 0x01 /* Φ_trial > 0: the Newton branch was taken (Plastic.jl:134)   */
+#define MM_FLAG_FAILED 0x80  /* local Newton did not converge (Plastic.jl:157)              */
+/* mm_crystal `active` is a bit mask: bit i set <=> Φ_i > 0 at the solution; bit 15 = failed */
+#define MM_ACTIVE_FAILED 0x8000
+
+typedef struct MMLinearElastic { double E, nu; } MMLinearElastic;                 /* LinearElastic.jl:10-19 */
+typedef struct MMPlastic { double E, nu, sigma_y, H, r, kappa_inf, alpha_inf; } MMPlastic; /* Plastic.jl:15-36 */
+typedef struct MMHyper { double lambda, mu, c2, c3; } MMHyper;                   /* neohook.jl:10-13, yeoh.jl:11-16 */
+typedef struct MMXuNeedleman { double Phi_n, Phi_t, delta_n, delta_t, Delta_n_star; } MMXuNeedleman; /* XuNeedleman.jl:22-28 */
+typedef struct MMCrystal {                                                        /* CrystalViscoPlastic.jl:18-45 */
+    double E, nu, tau_y, H_iso, H_kin, q, alpha_inf, t_star, sigma_c, m;
+    int32_t nslip;  /* must be MM_NSLIP */
+    int32_t pad_;
+    double MS[MM_NSLIP][9];        /* m_i ⊗ s_i, Tensor{2,3} column-major (:42)                    */
+    double H[MM_NSLIP][MM_NSLIP];  /* H[i][j] = Julia H[i+1,j+1] = H_iso (q + (1-q) δ_ij)   (:41)  */
+} MMCrystal;
+/* Newton options.  Plastic: NLsolve `ftol` on max|F| and `iterations` (defaults 1e-8 / 1000).
+ * Crystal: `solve(...; tol, max_iter)` on ||r||_2, strict < (nonlinear_solver.jl:52; 1e-8 / 100). */
+typedef struct MMNewtonOpts { double tol; int32_t max_iter; int32_t pad_; } MMNewtonOpts;
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* mm_version(void);
+const char* mm_last_error(void);
+int mm_device_count(void);
+
+/* ---- host-side parameter helpers (run once per material, like the Julia constructors) ------ */
+/* elastic_tangent_3D(E, ν) — src/LinearElastic.jl:27-35 */
+int mm_elastic_tangent_3d(double E, double nu, double* out36);
+/* slipsystems(FCC()/BCC(), RodriguesParam(x,y,z)) — slipsystems.jl:37-53; planes/dirs: [12][3] */
+int mm_slipsystems(int structure, const double rodrigues[3], double* planes, double* dirs);
+/* CrystalViscoPlastic(...) constructor — fills nslip, MS and H from the scalars already in *p (:38-45) */
+int mm_crystal_setup(MMCrystal* p, const double* planes, const double* dirs);
+/* XuNeedleman(; σₘₐₓ, τₘₐₓ, Φₙ, Φₜ, Δₙˢ) — XuNeedleman.jl:30-34 */
+int mm_xu_needleman_setup(double sigma_max, double tau_max, double Phi_n, double Phi_t, double Delta_n_star, MMXuNeedleman* out);
+
+/* ---- the hot path: device-pointer entry points --------------------------------------------- */
+/* material_response(::LinearElastic, ε) — src/LinearElastic.jl:57-60.
+ * eps[6], sig[6]; tan[36] may be NULL (the reference returns the one shared m.Eᵉ; use mm_elastic_tangent_3d). */
+int mm_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig, double* tan_or_null,
+                      int64_t N, int layout, void* stream);
+
+/* material_response(::Plastic, ε, state; cache, options) — src/Plastic.jl:126-160 (+ residuals :162-172,
+ * NLsolve newton at :146-148).  eps[6] TOTAL strain, state_in/out[14] (may alias), sig[6], tan[36] (not
+ * major-symmetric in general; may be NULL), flags/iters (uint8, may be NULL), *n_fail += #non-converged. */
+int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, double* sig, double* tan,
+               double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
+               int64_t N, int layout, void* stream);
+
+/* material_response(::NeoHook/::Yeoh/::StVenant, C) — neohook.jl:35-43, yeoh.jl:37-54, stvenant.jl:36-48, and the
+ * trait route material_response(∂S∂C(), m, DeformationGradient(F), ...) — src/traits.jl:91-130.
+ * strain[6 or 9], S[6] (2nd Piola–Kirchhoff), dSdC[36] (may be NULL). */
+int mm_hyper(int model, const MMHyper* p, const double* strain, int strain_kind, double* S, double* dSdC,
+             int64_t N, int layout, void* stream);
+
+/* material_response(::CrystalViscoPlastic{12}, Δε, state, Δt; options) — CrystalViscoPlastic.jl:64-94
+ * (+ residuals :97-115, get_state_vars :118-132, solve nonlinear_solver.jl:52-62).
+ * deps[6] strain INCREMENT, state_in/out[42] (may alias), sig[6], tan[36], active (uint16 mask), iters (uint8). */
+int mm_crystal(const MMCrystal* p, const double* deps, double dt, const double* state_in, double* sig, double* tan,
+               double* state_out, uint16_t* active, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
+               int64_t N, int layout, void* stream);
+
+/* material_response(::XuNeedleman, Δ::Tensor{1,dim}) — XuNeedleman.jl:75-91.  dim = 2 or 3.
+ * jump[dim], T[dim], dTdD[dim*dim] column-major (symmetric Hessian stored in full, as Tensor{2,dim}). */
+int mm_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, double* dTdD, int dim,
+                    int64_t N, int layout, void* stream);
+
+/* Deterministic synthetic inputs (bench + parity harness): out(i,c) = lo[c] + (hi[c]-lo[c]) * u(i,c),
+ * u(i,c) = (splitmix64(seed + i*nc + c) >> 11) * 2^-53.  lo/hi are HOST arrays of nc doubles. */
+int mm_synth_uniform(double* out, int64_t N, int nc, int layout, uint64_t seed, const double* lo, const double* hi,
+                     void* stream);
+
+/* ---- host-buffer entry points (same arguments, HOST pointers; pinned memory is fastest) ----- */
+void* mmh_alloc_pinned(uint64_t bytes);
+void mmh_free_pinned(void* p);
+int mmh_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig, double* tan_or_null, int64_t N, int layout);
+int mmh_plastic(const MMPlastic* p, const double* eps, const double* state_in, double* sig, double* tan, double* state_out,
+                uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
+int mmh_hyper(int model, const MMHyper* p, const double* strain, int strain_kind, double* S, double* dSdC, int64_t N, int layout);
+int mmh_crystal(const MMCrystal* p, const double* deps, double dt, const double* state_in, double* sig, double* tan,
+                double* state_out, uint16_t* active, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
+int mmh_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, double* dTdD, int dim, int64_t N, int layout);
+/* points per pipeline chunk of the mmh_* calls (default 1<<20); returns the previous value */
+int64_t mmh_set_chunk_points(int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMB200_H */
