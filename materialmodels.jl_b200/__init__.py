@@ -3,4 +3,16 @@
 Importing the package never touches CUDA; the native library (csrc/ -> libmmb200.so) is loaded on
 first use and the load FAILS LOUDLY if it is missing — there is no CPU fallback in the product.
 """
-from . import _abi  # noqa: F401
+from . import _abi, synth  # noqa: F401
+from .materials import (  # noqa: F401
+    AbstractMaterial, AbstractMaterialState, AbstractTangent, BCC, FCC, CrystalViscoPlastic, DeformationGradient,
+    GreenLagrange, LinearElastic, NeoHook, Plastic, RightCauchyGreen, SmallStrain, StVenant, StrainMeasure, XuNeedleman,
+    Yeoh, dPdF, dSdC, dSdE, dsigmadeps, native_tangent_type, slipsystems,
+    xu_needleman_Φₙ, xu_needleman_Φₜ, xu_needleman_σₘₐₓ, xu_needleman_τₘₐₓ,
+)
+from .api import (  # noqa: F401
+    NOT_CONVERGED, CrystalViscoPlasticState, LinearElasticState, NeoHookState, PlasticCache, PlasticState, StVenantState,
+    XuNeedlemanState, YeohState, elastic_tangent_3D, get_cache, initial_material_state, material_response, synth_uniform,
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,397 @@
+"""Batched mirror of the reference's generic API (reference src/MaterialModels.jl:41-81):
+
+    initial_material_state(m, N, ...)                       <- initial_material_state(m)
+    get_cache(m)                                            <- get_cache(m)
+    material_response(m, strain, state, Δt; cache, options) <- material_response(...)  (one call = N points)
+    material_response(dSdC(), m, DeformationGradient(F), state, Δt)   <- src/traits.jl:91-107
+
+Arrays are float64.  `torch` CUDA tensors go straight to the device-pointer entry points (mm_*) on the
+current torch stream; numpy arrays (host) go through the pipelined host-buffer entry points (mmh_*).
+Layout: "soa" = shape (nc, N) [default, fast path], "aos" = shape (N, nc) (== a Julia
+Vector{SymmetricTensor{2,3}} reinterpreted).  Either way the hot path is the CUDA library; if it is
+missing, every call raises (no CPU fallback).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _abi
+from ._lib import check, load
+from .materials import (AbstractMaterialState, AbstractTangent, CrystalViscoPlastic, DeformationGradient, LinearElastic,
+                        Plastic, RightCauchyGreen, StrainMeasure, XuNeedleman, _Hyper, dSdC)
+
+NOT_CONVERGED = "Material model not converged. Could not find material state."   # Plastic.jl:157, CrystalViscoPlastic.jl:92
+
+_LAYOUTS = {"soa": _abi.MM_LAYOUT_SOA, "aos": _abi.MM_LAYOUT_AOS, 0: 0, 1: 1}
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _is_host(a):
+    return isinstance(a, np.ndarray)
+
+
+def _shape(nc, N, layout):
+    return (nc, N) if _LAYOUTS[layout] == _abi.MM_LAYOUT_SOA else (N, nc)
+
+
+def _npoints(a, nc, layout):
+    shp = tuple(a.shape)
+    if _LAYOUTS[layout] == _abi.MM_LAYOUT_SOA:
+        if len(shp) != 2 or shp[0] != nc:
+            raise ValueError("expected shape (%d, N) for layout 'soa', got %s" % (nc, shp))
+        return shp[1]
+    if len(shp) != 2 or shp[1] != nc:
+        raise ValueError("expected shape (N, %d) for layout 'aos', got %s" % (nc, shp))
+    return shp[0]
+
+
+def _prep(a, like=None):
+    """contiguous float64, on host (numpy) or device (torch)"""
+    if _is_host(a):
+        return np.ascontiguousarray(a, dtype=np.float64)
+    torch = _torch()
+    if not a.is_cuda:
+        raise ValueError("torch tensors must live on a CUDA device (pass numpy arrays for host data)")
+    if a.dtype != torch.float64:
+        raise ValueError("float64 required")
+    return a.contiguous()
+
+
+def _empty(shape, like, dtype=None):
+    if _is_host(like):
+        return np.empty(shape, dtype=dtype or np.float64)
+    torch = _torch()
+    return torch.empty(shape, dtype=dtype or torch.float64, device=like.device)
+
+
+def _zeros(shape, like, dtype=None):
+    if _is_host(like):
+        return np.zeros(shape, dtype=dtype or np.float64)
+    torch = _torch()
+    return torch.zeros(shape, dtype=dtype or torch.float64, device=like.device)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_host(a):
+        return a.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(a.data_ptr())
+
+
+def _stream(like):
+    torch = _torch()
+    return ctypes.c_void_p(torch.cuda.current_stream(like.device).cuda_stream)
+
+
+class _DeviceGuard:
+    def __init__(self, like):
+        self.like = like
+        self.ctx = None
+
+    def __enter__(self):
+        if not _is_host(self.like):
+            self.ctx = _torch().cuda.device(self.like.device)
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+# --------------------------------------------------------------------------------------------
+# states
+class LinearElasticState(AbstractMaterialState):
+    pass
+
+
+class NeoHookState(AbstractMaterialState):
+    pass
+
+
+class YeohState(AbstractMaterialState):
+    pass
+
+
+class StVenantState(AbstractMaterialState):
+    pass
+
+
+class XuNeedlemanState(AbstractMaterialState):
+    pass
+
+
+class _ArrayState(AbstractMaterialState):
+    NC = 0
+
+    def __init__(self, data, layout="soa"):
+        self.data = data
+        self.layout = layout
+        self.N = _npoints(data, self.NC, layout)
+        self.n_fail = None      # device/host counter of the call that produced this state (None for initial states)
+        self.flags = None
+        self.iters = None
+
+    def _comp(self, lo, hi):
+        return self.data[lo:hi] if _LAYOUTS[self.layout] == 0 else self.data[:, lo:hi]
+
+
+class PlasticState(_ArrayState):
+    """[εᵖ(6), κ, α(6), μ] per point — reference src/Plastic.jl:41-46."""
+    NC = 14
+    εᵖ = property(lambda s: s._comp(0, 6))
+    κ = property(lambda s: s._comp(6, 7))
+    α = property(lambda s: s._comp(7, 13))
+    μ = property(lambda s: s._comp(13, 14))
+
+
+class CrystalViscoPlasticState(_ArrayState):
+    """[σ(6), κ(12), α(12), μ(12)] per point — reference CrystalViscoPlastic.jl:52-57."""
+    NC = 42
+    σ = property(lambda s: s._comp(0, 6))
+    κ = property(lambda s: s._comp(6, 18))
+    α = property(lambda s: s._comp(18, 30))
+    μ = property(lambda s: s._comp(30, 42))
+
+
+def initial_material_state(m, N=None, device="cuda", layout="soa"):
+    """Zero-initialised state for N points (reference: initial_material_state(m), one point).
+    device="cpu" gives a numpy-backed state for the host-buffer path."""
+    if isinstance(m, LinearElastic):
+        return LinearElasticState()
+    if isinstance(m, XuNeedleman):
+        return XuNeedlemanState()
+    if isinstance(m, _Hyper):
+        return {0: NeoHookState, 1: YeohState, 2: StVenantState}[m.MODEL]()
+    cls = PlasticState if isinstance(m, Plastic) else CrystalViscoPlasticState if isinstance(m, CrystalViscoPlastic) else None
+    if cls is None:
+        raise TypeError("unknown material %r" % (m,))
+    if N is None:
+        raise TypeError("initial_material_state(%s, N): number of points required" % type(m).__name__)
+    if str(device) == "cpu":
+        data = np.zeros(_shape(cls.NC, N, layout))
+    else:
+        torch = _torch()
+        data = torch.zeros(_shape(cls.NC, N, layout), dtype=torch.float64, device=device)
+    return cls(data, layout)
+
+
+class PlasticCache:
+    """Placeholder kept for API compatibility: the reference's cache holds NLsolve scratch
+    (src/Plastic.jl:51-63); the GPU path keeps the whole local solve in registers."""
+
+
+def get_cache(m):
+    return PlasticCache() if isinstance(m, Plastic) else None     # reference src/MaterialModels.jl:71-73
+
+
+def elastic_tangent_3D(E, ν):
+    out = np.zeros(36)
+    check(load().mm_elastic_tangent_3d(float(E), float(ν), _ptr(out)), "mm_elastic_tangent_3d")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+def _newton_opts(m, options):
+    if isinstance(m, Plastic):
+        tol, max_iter = 1e-8, 1000        # NLsolve defaults (ftol, iterations)
+        if options:
+            p = options.get("nlsolve_params", options.get(":nlsolve_params", {})) or {}
+            method = p.get("method", "newton")
+            if method not in ("newton", ":newton"):
+                raise NotImplementedError("only NLsolve method=:newton is implemented on the GPU path")
+            tol = float(p.get("ftol", tol))
+            max_iter = int(p.get("iterations", max_iter))
+    else:
+        tol, max_iter = 1e-8, 100         # solve(...; max_iter=100, tol=1e-8), nonlinear_solver.jl:52
+        if options:
+            opt = options._asdict() if hasattr(options, "_asdict") else dict(options)
+            tol = float(opt.get("tol", tol))
+            max_iter = int(opt.get("max_iter", max_iter))
+    return _abi.MMNewtonOpts(tol, max_iter, 0)
+
+
+def _finish_fail(nfail, like, options):
+    if options and (options.get("defer_check") if isinstance(options, dict) else False):
+        return
+    n = int(nfail[0]) if _is_host(like) else int(nfail.item())
+    if n != 0:
+        raise RuntimeError(NOT_CONVERGED)
+
+
+def _response_linear_elastic(m, ε, state, layout, want_tangent):
+    ε = _prep(ε)
+    N = _npoints(ε, 6, layout)
+    σ = _empty(_shape(6, N, layout), ε)
+    tan = _empty(_shape(36, N, layout), ε) if want_tangent else None
+    lib = load()
+    with _DeviceGuard(ε):
+        if _is_host(ε):
+            rc = lib.mmh_linear_elastic(ctypes.byref(m._c), _ptr(ε), _ptr(σ), _ptr(tan), N, _LAYOUTS[layout])
+        else:
+            rc = lib.mm_linear_elastic(ctypes.byref(m._c), _ptr(ε), _ptr(σ), _ptr(tan), N, _LAYOUTS[layout], _stream(ε))
+    check(rc, "mm_linear_elastic")
+    return σ, (tan if want_tangent else m.Eᵉ), state
+
+
+def _response_plastic(m, ε, state, options, want_tangent):
+    layout = state.layout
+    ε = _prep(ε)
+    N = _npoints(ε, 6, layout)
+    if N != state.N:
+        raise ValueError("strain has %d points, state has %d" % (N, state.N))
+    sin = _prep(state.data)
+    σ = _empty(_shape(6, N, layout), ε)
+    tan = _empty(_shape(36, N, layout), ε) if want_tangent else None
+    sout = _empty(_shape(14, N, layout), ε)
+    host = _is_host(ε)
+    flags = _empty((N,), ε, np.uint8 if host else _torch().uint8)
+    iters = _empty((N,), ε, np.uint8 if host else _torch().uint8)
+    nfail = _zeros((1,), ε, np.int32 if host else _torch().int32)
+    o = _newton_opts(m, options)
+    lib = load()
+    with _DeviceGuard(ε):
+        if host:
+            rc = lib.mmh_plastic(ctypes.byref(m._c), _ptr(ε), _ptr(sin), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(flags), _ptr(iters),
+                                 _ptr(nfail), ctypes.byref(o), N, _LAYOUTS[layout])
+        else:
+            rc = lib.mm_plastic(ctypes.byref(m._c), _ptr(ε), _ptr(sin), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(flags), _ptr(iters),
+                                _ptr(nfail), ctypes.byref(o), N, _LAYOUTS[layout], _stream(ε))
+    check(rc, "mm_plastic")
+    new = PlasticState(sout, layout)
+    new.flags, new.iters, new.n_fail = flags, iters, nfail
+    _finish_fail(nfail, ε, options)
+    return σ, tan, new
+
+
+def _response_crystal(m, Δε, state, Δt, options, want_tangent):
+    layout = state.layout
+    Δε = _prep(Δε)
+    N = _npoints(Δε, 6, layout)
+    if N != state.N:
+        raise ValueError("strain has %d points, state has %d" % (N, state.N))
+    sin = _prep(state.data)
+    σ = _empty(_shape(6, N, layout), Δε)
+    tan = _empty(_shape(36, N, layout), Δε) if want_tangent else None
+    sout = _empty(_shape(42, N, layout), Δε)
+    host = _is_host(Δε)
+    active = _empty((N,), Δε, np.uint16 if host else _torch().int16)
+    iters = _empty((N,), Δε, np.uint8 if host else _torch().uint8)
+    nfail = _zeros((1,), Δε, np.int32 if host else _torch().int32)
+    o = _newton_opts(m, options)
+    lib = load()
+    with _DeviceGuard(Δε):
+        if host:
+            rc = lib.mmh_crystal(ctypes.byref(m._c), _ptr(Δε), float(Δt), _ptr(sin), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(active),
+                                 _ptr(iters), _ptr(nfail), ctypes.byref(o), N, _LAYOUTS[layout])
+        else:
+            rc = lib.mm_crystal(ctypes.byref(m._c), _ptr(Δε), float(Δt), _ptr(sin), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(active),
+                                _ptr(iters), _ptr(nfail), ctypes.byref(o), N, _LAYOUTS[layout], _stream(Δε))
+    check(rc, "mm_crystal")
+    new = CrystalViscoPlasticState(sout, layout)
+    new.flags, new.iters, new.n_fail = active, iters, nfail
+    _finish_fail(nfail, Δε, options)
+    return σ, tan, new
+
+
+def _response_hyper(m, strain, kind, state, layout, want_tangent):
+    strain = _prep(strain)
+    nin = 9 if kind == _abi.MM_STRAIN_F else 6
+    N = _npoints(strain, nin, layout)
+    S = _empty(_shape(6, N, layout), strain)
+    tan = _empty(_shape(36, N, layout), strain) if want_tangent else None
+    lib = load()
+    with _DeviceGuard(strain):
+        if _is_host(strain):
+            rc = lib.mmh_hyper(m.MODEL, ctypes.byref(m._c), _ptr(strain), kind, _ptr(S), _ptr(tan), N, _LAYOUTS[layout])
+        else:
+            rc = lib.mm_hyper(m.MODEL, ctypes.byref(m._c), _ptr(strain), kind, _ptr(S), _ptr(tan), N, _LAYOUTS[layout], _stream(strain))
+    check(rc, "mm_hyper")
+    return S, tan, state
+
+
+def _response_xu(m, Δ, state, layout, want_tangent):
+    Δ = _prep(Δ)
+    dim = Δ.shape[0] if _LAYOUTS[layout] == 0 else Δ.shape[1]
+    if dim not in (2, 3):
+        raise ValueError("XuNeedleman: jump must have 2 or 3 components")
+    N = _npoints(Δ, dim, layout)
+    T = _empty(_shape(dim, N, layout), Δ)
+    H = _empty(_shape(dim * dim, N, layout), Δ) if want_tangent else None
+    lib = load()
+    with _DeviceGuard(Δ):
+        if _is_host(Δ):
+            rc = lib.mmh_xu_needleman(ctypes.byref(m._c), _ptr(Δ), _ptr(T), _ptr(H), dim, N, _LAYOUTS[layout])
+        else:
+            rc = lib.mm_xu_needleman(ctypes.byref(m._c), _ptr(Δ), _ptr(T), _ptr(H), dim, N, _LAYOUTS[layout], _stream(Δ))
+    check(rc, "mm_xu_needleman")
+    return T, H, state
+
+
+def material_response(*args, cache=None, options=None, layout="soa", tangent=True):
+    """material_response(m, strain, state=None, Δt=None, cache=None, options=None)
+    material_response(dSdC(), m, DeformationGradient(F) | RightCauchyGreen(C), state=None, Δt=0.0)
+
+    Returns (stress, tangent, new_state) for all N points of `strain`.
+    `layout` applies to stateless models (stateful ones use their state's layout);
+    `tangent=False` skips the 36-component tangent output (returns None in its place)."""
+    args = list(args)
+    if args and isinstance(args[0], AbstractTangent):                       # src/traits.jl:91-107
+        out_tangent = args.pop(0)
+        m = args.pop(0)
+        strain = args.pop(0)
+        state = args.pop(0) if args else None
+        if not isinstance(strain, StrainMeasure):
+            raise TypeError("trait form expects a StrainMeasure (DeformationGradient / RightCauchyGreen)")
+        if not isinstance(m, _Hyper):
+            raise NotImplementedError("trait route is implemented for NeoHook / Yeoh / StVenant")
+        if not isinstance(out_tangent, dSdC):
+            raise NotImplementedError("%s output: not on the B200 path yet (SURVEY §8(f) 'next')" % type(out_tangent).__name__)
+        if isinstance(strain, DeformationGradient):
+            kind = _abi.MM_STRAIN_F
+        elif isinstance(strain, RightCauchyGreen):
+            kind = _abi.MM_STRAIN_C
+        else:                                                                # traits.jl:120
+            raise RuntimeError("%s is not the native strain measure for %s:" % (type(strain).__name__, type(m).__name__))
+        return _response_hyper(m, strain.value, kind, state if state is not None else initial_material_state(m), layout, tangent)
+
+    m = args.pop(0)
+    strain = args.pop(0)
+    state = args.pop(0) if args else None
+    Δt = args.pop(0) if args else None
+    if args:                                   # XuNeedleman takes cache, options positionally (XuNeedleman.jl:75-76)
+        cache = args.pop(0)
+    if args:
+        options = args.pop(0)
+    if isinstance(m, LinearElastic):
+        return _response_linear_elastic(m, strain, state if state is not None else LinearElasticState(), layout, tangent)
+    if isinstance(m, Plastic):
+        if state is None:
+            raise TypeError("material_response(::Plastic, ε, state): state required")
+        return _response_plastic(m, strain, state, options, tangent)
+    if isinstance(m, CrystalViscoPlastic):
+        if state is None:
+            raise TypeError("material_response(::CrystalViscoPlastic, Δε, state): state required")
+        return _response_crystal(m, strain, state, 1.0 if Δt is None else Δt, options, tangent)
+    if isinstance(m, _Hyper):
+        return _response_hyper(m, strain, _abi.MM_STRAIN_C, state if state is not None else initial_material_state(m), layout, tangent)
+    if isinstance(m, XuNeedleman):
+        return _response_xu(m, strain, state if state is not None else XuNeedlemanState(), layout, tangent)
+    raise TypeError("material_response: unsupported material %r" % (m,))
+
+
+def synth_uniform(N, nc, seed, lo, hi, layout="soa", device="cuda"):
+    """Device-side deterministic inputs (bit-identical to synth.host_uniform)."""
+    torch = _torch()
+    out = torch.empty(_shape(nc, N, layout), dtype=torch.float64, device=device)
+    lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, dtype=np.float64), (nc,)))
+    hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, dtype=np.float64), (nc,)))
+    with _DeviceGuard(out):
+        rc = load().mm_synth_uniform(_ptr(out), N, nc, _LAYOUTS[layout], int(seed), _ptr(lo), _ptr(hi), _stream(out))
+    check(rc, "mm_synth_uniform")
+    return out

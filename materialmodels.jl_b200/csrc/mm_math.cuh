@@ -1,0 +1,378 @@
+// Per-point constitutive updates (FP64), written once as accessor-templated inline functions.
+// The CUDA kernels (mm_kernels.cuh) instantiate them with coalesced-SoA or smem-staged-AoS
+// accessors; tests/hosttwin instantiates the same source with a host accessor to check the
+// algebra on a CPU box (a debugging aid of the test-suite only — the shipped library exports no
+// CPU compute path).
+//
+// Storage orders follow Tensors.jl (see include/mmb200.h): symmetric 2nd order = (11,21,31,22,32,33),
+// full 2nd order = column-major 9, minor-symmetric 4th order = I + 6 J.
+//
+// Accessor concept:   double acc.template in<A>(c)            read component c of input array A
+//                     void   acc.template out<A>(c, v)        write component c of output array A
+//                     bool   acc.template has_out<A>()        output array A requested (non-NULL)
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MM_HD __host__ __device__ __forceinline__
+#else
+#define MM_HD inline
+#endif
+
+namespace mm {
+
+// ---- small symmetric-tensor helpers on double[6] = (11,21,31,22,32,33) ---------------------------
+MM_HD double ddot6(const double* a, const double* b) {
+    return a[0] * b[0] + a[3] * b[3] + a[5] * b[5] + 2.0 * (a[1] * b[1] + a[2] * b[2] + a[4] * b[4]);
+}
+MM_HD double tr6(const double* a) { return a[0] + a[3] + a[5]; }
+MM_HD void dev6(const double* a, double* d) {
+    const double m = tr6(a) / 3.0;
+    d[0] = a[0] - m; d[1] = a[1]; d[2] = a[2]; d[3] = a[3] - m; d[4] = a[4]; d[5] = a[5] - m;
+}
+MM_HD bool is_diag_slot(int c) { return c == 0 || c == 3 || c == 5; }
+
+// isotropic stiffness entry Eᵉ[I,J] (raw components) — reference src/LinearElastic.jl:27-35
+MM_HD double iso_entry(int I, int J, double lam, double G) {
+    const bool dI = is_diag_slot(I), dJ = is_diag_slot(J);
+    if (dI && dJ) return (I == J) ? (lam + 2.0 * G) : lam;
+    return (I == J) ? G : 0.0;
+}
+// deviatoric symmetric projector entry I_dev[I,J] (raw components)
+MM_HD double idev_entry(int I, int J) {
+    const bool dI = is_diag_slot(I), dJ = is_diag_slot(J);
+    if (dI && dJ) return (I == J) ? (2.0 / 3.0) : (-1.0 / 3.0);
+    return (I == J) ? 0.5 : 0.0;
+}
+
+// =================================================================================================
+// LinearElastic — reference src/LinearElastic.jl:57-60:  σ = Eᵉ ⊡ ε, tangent = Eᵉ
+// in<0> = ε(6);  out<0> = σ(6), out<1> = tangent(36, optional)
+// =================================================================================================
+struct ElasticK { double lam, G; };
+MM_HD ElasticK make_elastic_k(double E, double nu) {
+    ElasticK k;
+    k.lam = E * nu / ((1 + nu) * (1 - 2 * nu));
+    k.G = E / (2 * (1 + nu));
+    return k;
+}
+template <class Acc> MM_HD void elastic_tangent_out(const ElasticK& k, Acc& acc) {
+#pragma unroll
+    for (int J = 0; J < 6; ++J)
+#pragma unroll
+        for (int I = 0; I < 6; ++I) acc.template out<1>(I + 6 * J, iso_entry(I, J, k.lam, k.G));
+}
+template <class Acc> MM_HD void linear_elastic_point(const ElasticK& k, Acc& acc) {
+    double e[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c);
+    const double ltr = k.lam * tr6(e);
+    const double G2 = 2.0 * k.G;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc.template out<0>(c, is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c]));
+    if (acc.template has_out<1>()) elastic_tangent_out(k, acc);
+}
+
+// =================================================================================================
+// Plastic — reference src/Plastic.jl:126-172.
+// in<0> = ε(6) total strain, in<1> = state [εᵖ(6), κ, α(6), μ];
+// out<0> = σ(6), out<1> = ∂σ∂ε(36, optional), out<2> = new state(14)
+//
+// The reference solves the 14-unknown system R(σ,κ,α,μ) = 0 with NLsolve's plain Newton and a dense
+// ForwardDiff Jacobian, then takes the tangent from the top-left 6x6 of inv(J).  Here the SAME Newton
+// iterates are produced by a closed-form solve of J dx = -R: with s = dev(σ-α), n = s/|s|, ν̂ = √(3/2) n,
+// every block of J is a combination of the identity, the deviatoric projector and n⊗n (Eᵉ:N = 2G N for
+// deviatoric N), so the step splits into a volumetric part, the component along n, the deviatoric part
+// orthogonal to n and two scalar equations (derivation in DESIGN.md §4.2).  Same algebra, ~150 flops per
+// iteration instead of a 14x14 LU, no matrix in registers.
+// =================================================================================================
+struct PlasticK {
+    double lam, G;                  // Lamé constants of Eᵉ
+    double sigma_y, H_kappa, H_alpha, kappa_inf, c2;   // c2 = 3/(2 α_∞)
+    double tol; int max_iter;
+};
+MM_HD PlasticK make_plastic_k(double E, double nu, double sigma_y, double H, double r, double kappa_inf, double alpha_inf, double tol, int max_iter) {
+    PlasticK k;
+    k.lam = E * nu / ((1 + nu) * (1 - 2 * nu));
+    k.G = E / (2 * (1 + nu));
+    k.sigma_y = sigma_y;
+    k.H_kappa = -r * H;                     // Plastic.jl:31
+    k.H_alpha = -2.0 / 3.0 * (1 - r) * H;   // Plastic.jl:32
+    k.kappa_inf = kappa_inf;
+    k.c2 = 3.0 / (2 * alpha_inf);
+    k.tol = tol; k.max_iter = max_iter;
+    return k;
+}
+
+// returns flag bits (MM_FLAG_PLASTIC=1, MM_FLAG_FAILED=0x80); *iters = number of Newton updates
+template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* iters_out) {
+    const double c1 = 1.2247448713915890491;   // sqrt(3/2)
+    const double r2 = 1.4142135623730950488;   // sqrt(2) (Mandel scaling of the shear residuals)
+    const double G2 = 2.0 * k.G;
+    double ep[6], st[6], al_n[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ep[c] = acc.template in<1>(c);
+    const double kap_n = acc.template in<1>(6);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) al_n[c] = acc.template in<1>(7 + c);
+    const double mu_n = acc.template in<1>(13);
+    {   // σ_trial = Eᵉ ⊡ (ε − εᵖ)                                                        Plastic.jl:131
+        double e[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c) - ep[c];
+        const double ltr = k.lam * tr6(e);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) st[c] = is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c]);
+    }
+    double d6[6], s[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) d6[c] = st[c] - al_n[c];
+    dev6(d6, s);
+    double rho = sqrt(ddot6(s, s));
+    const double Phi = c1 * rho - k.sigma_y - kap_n;                                   // Plastic.jl:132
+    if (Phi <= 0.0) {                                                                  // Plastic.jl:134-135
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc.template out<0>(c, st[c]);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc.template out<2>(c, ep[c]);
+        acc.template out<2>(6, kap_n);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc.template out<2>(7 + c, al_n[c]);
+        acc.template out<2>(13, mu_n);
+        if (acc.template has_out<1>()) { ElasticK ek; ek.lam = k.lam; ek.G = k.G; elastic_tangent_out(ek, acc); }
+        *iters_out = 0;
+        return 0;
+    }
+    // ---- Newton on x = (σ, κ, α, μ), x0 = (σ_trial, κₙ, αₙ, μₙ)                       Plastic.jl:142-148
+    double sg[6], al[6], kap = kap_n, mu = mu_n;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { sg[c] = st[c]; al[c] = al_n[c]; }
+    int iters = 0, flag = 1;
+    double n[6], w[6], inv_rho, i1psi, theta, eta, ikk, gk, n_gt;
+    for (;;) {
+        // residuals at x                                                               Plastic.jl:162-172
+#pragma unroll
+        for (int c = 0; c < 6; ++c) d6[c] = sg[c] - al[c];
+        dev6(d6, s);
+        rho = sqrt(ddot6(s, s));
+        inv_rho = 1.0 / rho;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) n[c] = s[c] * inv_rho;
+        dev6(al, w);
+        const double kr = -1.0 + kap / k.kappa_inf;
+        double Rs[6], Ra[6];
+        const double gm = G2 * mu * c1, hm = mu * k.H_alpha;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            Rs[c] = (sg[c] - st[c]) + gm * n[c];
+            Ra[c] = (al[c] - al_n[c]) - hm * (k.c2 * w[c] - c1 * n[c]);
+        }
+        const double Rk = (kap - kap_n) - mu * k.H_kappa * kr;
+        const double Rm = c1 * rho - k.sigma_y - kap;
+        // NLsolve convergence test: max|F| <= ftol on the MANDEL vector (shear entries carry sqrt(2))
+        double fmaxabs = fmax(fabs(Rk), fabs(Rm));
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const double f = is_diag_slot(c) ? 1.0 : r2;
+            fmaxabs = fmax(fmaxabs, fmax(fabs(Rs[c] * f), fabs(Ra[c] * f)));
+        }
+        // quantities shared by the step and by the tangent
+        const double beta = c1 * inv_rho;
+        const double psi = hm * k.c2;
+        i1psi = 1.0 / (1.0 - psi);
+        theta = gm * inv_rho;                       // 2G μ β
+        const double phi = hm * beta;
+        eta = theta - phi * i1psi;
+        gk = -k.H_kappa * kr;
+        ikk = 1.0 / (1.0 - mu * k.H_kappa / k.kappa_inf);
+        double gt[6], ha[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            ha[c] = k.H_alpha * (c1 * n[c] - k.c2 * w[c]);
+            gt[c] = G2 * c1 * n[c] - ha[c] * i1psi;
+        }
+        n_gt = ddot6(n, gt);
+        if (fmaxabs <= k.tol) break;                                  // f_converged
+        if (!(fmaxabs == fmaxabs) || iters >= k.max_iter) { flag |= 0x80; break; }
+        // ---- closed-form Newton step
+        const double trRs = tr6(Rs) / 3.0, trRa = tr6(Ra) / 3.0;
+        double rt[6], ra[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const double dl = is_diag_slot(c) ? 1.0 : 0.0;
+            ra[c] = Ra[c] - trRa * dl;
+            rt[c] = -(Rs[c] - trRs * dl) + ra[c] * i1psi;
+        }
+        const double n_rt = ddot6(n, rt);
+        const double dmu = (c1 * n_rt + Rm + Rk * ikk) / (c1 * n_gt - gk * ikk);
+        const double dkap = (-Rk - gk * dmu) * ikk;
+        const double ny = n_rt - n_gt * dmu;
+        const double i1eta = 1.0 / (1.0 + eta);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const double dl = is_diag_slot(c) ? 1.0 : 0.0;
+            const double Pd = ((rt[c] - gt[c] * dmu) - ny * n[c]) * i1eta;
+            sg[c] += -Rs[c] - theta * Pd - G2 * c1 * n[c] * dmu;
+            al[c] += (-ra[c] - phi * Pd - ha[c] * dmu) * i1psi - trRa * dl;
+        }
+        kap += dkap;
+        mu += dmu;
+        ++iters;
+    }
+    // ---- outputs at the converged iterate                                            Plastic.jl:150-155
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc.template out<0>(c, sg[c]);
+    const double mnu = mu * c1;    // εᵖ = εᵖₙ + μ ν̂,  ν̂ = (3/(2√(3/2)|s|)) s = √(3/2) n
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc.template out<2>(c, ep[c] + mnu * n[c]);
+    acc.template out<2>(6, kap);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc.template out<2>(7 + c, al[c]);
+    acc.template out<2>(13, mu);
+    if (acc.template has_out<1>()) {
+        // ∂σ∂ε = (J⁻¹)_σσ ⊡ Eᵉ = Eᵉ − 2Gξ I_dev + u ⊗ n                                  Plastic.jl:152-154
+        const double xi = theta / (1.0 + eta);
+        const double omega = k.H_alpha * k.c2 * i1psi;
+        const double cD = c1 / (c1 * n_gt - gk * ikk);
+        const double nw = ddot6(n, w);
+        double u[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) u[c] = G2 * (xi * n[c] + cD * (xi * omega * (w[c] - nw * n[c]) - G2 * c1 * n[c]));
+        const double gxi = G2 * xi;
+#pragma unroll
+        for (int J = 0; J < 6; ++J)
+#pragma unroll
+            for (int I = 0; I < 6; ++I)
+                acc.template out<1>(I + 6 * J, iso_entry(I, J, k.lam, k.G) - gxi * idev_entry(I, J) + u[I] * n[J]);
+    }
+    *iters_out = iters;
+    return flag;
+}
+
+// =================================================================================================
+// Hyperelasticity — reference src/FiniteStrain/{neohook.jl:35-43, yeoh.jl:37-54, stvenant.jl:36-48};
+// from F via C = tdot(F) = FᵀF (src/traits.jl:35-38, :91-130).
+// in<0> = C(6) or F(9);  out<0> = S(6), out<1> = ∂S∂C(36, optional)
+// All three models have the form  S = a I + b C⁻¹ + g C,
+//   ∂S∂C = p I⊗I + q sym(C⁻¹ ⊗̄ C⁻¹) + r C⁻¹⊗C⁻¹   (StVenant: the same with C⁻¹ := I)
+// Yeoh: the reference inverts the 9x9 matrix of otimesu(-C, C) numerically (yeoh.jl:44); analytically
+// inv(-C ⊗̄ C) = -C⁻¹ ⊗̄ C⁻¹, which is what is evaluated here.
+// =================================================================================================
+struct HyperK { double lambda, mu, c2, c3; };
+template <int MODEL, int KIND, class Acc> MM_HD void hyper_point(const HyperK& k, Acc& acc) {
+    double C[6];
+    if (KIND == 1) {   // F (column-major 9) -> C = FᵀF
+        double F[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) F[c] = acc.template in<0>(c);
+        C[0] = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+        C[1] = F[3] * F[0] + F[4] * F[1] + F[5] * F[2];
+        C[2] = F[6] * F[0] + F[7] * F[1] + F[8] * F[2];
+        C[3] = F[3] * F[3] + F[4] * F[4] + F[5] * F[5];
+        C[4] = F[6] * F[3] + F[7] * F[4] + F[8] * F[5];
+        C[5] = F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) C[c] = acc.template in<0>(c);
+    }
+    double A[6];          // C⁻¹ (or I for StVenant)
+    double a, b, g, p, q, r;
+    if (MODEL == 2) {     // StVenant: S = λ/2 (tr C − 3) I + μ (C − I);  ∂S∂C = ½λ I⊗I + μ I_sym
+        A[0] = 1.0; A[1] = 0.0; A[2] = 0.0; A[3] = 1.0; A[4] = 0.0; A[5] = 1.0;
+        a = k.lambda / 2 * (tr6(C) - 3.0) - k.mu; b = 0.0; g = k.mu;
+        p = 0.5 * k.lambda; q = k.mu; r = 0.0;
+    } else {
+        // C = [c0 c1 c2; c1 c3 c4; c2 c4 c5];  adjugate / det
+        const double m00 = C[3] * C[5] - C[4] * C[4];
+        const double m01 = C[2] * C[4] - C[1] * C[5];
+        const double m02 = C[1] * C[4] - C[2] * C[3];
+        const double det = C[0] * m00 + C[1] * m01 + C[2] * m02;
+        const double idet = 1.0 / det;
+        A[0] = m00 * idet; A[1] = m01 * idet; A[2] = m02 * idet;
+        A[3] = (C[0] * C[5] - C[2] * C[2]) * idet;
+        A[4] = (C[1] * C[2] - C[0] * C[4]) * idet;
+        A[5] = (C[0] * C[3] - C[1] * C[1]) * idet;
+        const double lnJ = log(sqrt(det));
+        g = 0.0;
+        if (MODEL == 0) {   // NeoHook: S = μ (I − C⁻¹) + λ ln J C⁻¹
+            a = k.mu; b = k.lambda * lnJ - k.mu;
+            p = 0.0; q = k.mu - k.lambda * lnJ; r = 0.5 * k.lambda;
+        } else {            // Yeoh
+            const double i3 = tr6(C) - 3.0;
+            a = k.mu + 4.0 * k.c2 * i3 + 6.0 * k.c3 * (i3 * i3); b = k.lambda * lnJ - k.mu;
+            p = 4.0 * k.c2 + 12.0 * k.c3 * i3; q = k.mu - k.lambda * lnJ; r = 0.5 * k.lambda;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        double v = b * A[c] + g * C[c];
+        if (is_diag_slot(c)) v += a;
+        acc.template out<0>(c, v);
+    }
+    if (acc.template has_out<1>()) {
+        // full 3x3 view of A for the ⊗̄ product
+        const int SI[6] = {0, 1, 2, 1, 2, 2}, SJ[6] = {0, 0, 0, 1, 1, 2};
+        const int SIDX[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+        for (int J = 0; J < 6; ++J)
+#pragma unroll
+            for (int I = 0; I < 6; ++I) {
+                const int i = SI[I], j = SJ[I], kk = SI[J], l = SJ[J];
+                const double sym_u = 0.5 * (A[SIDX[i][kk]] * A[SIDX[j][l]] + A[SIDX[i][l]] * A[SIDX[j][kk]]);
+                double v = q * sym_u + r * (A[I] * A[J]);
+                if (i == j && kk == l) v += p;
+                acc.template out<1>(I + 6 * J, v);
+            }
+    }
+}
+
+// =================================================================================================
+// XuNeedleman — reference src/CohesiveMaterials/XuNeedleman.jl:75-91.  T = ∂Φ/∂Δ, dTdΔ = ∂²Φ/∂Δ²
+// of the potential at :86 (the reference differentiates it with nested duals; closed forms here).
+// in<0> = Δ(dim), last component normal;  out<0> = T(dim), out<1> = dTdΔ(dim², column-major, optional)
+// =================================================================================================
+struct XuK { double Phi_n, delta_n, delta_t, q, r; };
+MM_HD XuK make_xu_k(double Phi_n, double Phi_t, double delta_n, double delta_t, double Delta_n_star) {
+    XuK k; k.Phi_n = Phi_n; k.delta_n = delta_n; k.delta_t = delta_t;
+    k.q = Phi_t / Phi_n;              // :83
+    k.r = Delta_n_star / delta_n;     // :84
+    return k;
+}
+template <int DIM, class Acc> MM_HD void xu_point(const XuK& k, Acc& acc) {
+    double D[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) D[c] = acc.template in<0>(c);
+    const double a = D[DIM - 1] / k.delta_n;
+    double t2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < DIM - 1; ++c) t2 += D[c] * D[c];
+    const double idt2 = 1.0 / (k.delta_t * k.delta_t);
+    const double E1 = exp(-a), E2 = exp(-t2 * idt2);
+    const double A0 = (1 - k.q) / (k.r - 1), B0 = (k.r - k.q) / (k.r - 1);
+    const double f = (1 - k.r + a) * A0, gq = k.q + B0 * a;
+    const double pe = k.Phi_n * E1;
+    // gradient
+    const double Tn = pe / k.delta_n * ((A0 - f) + (gq - B0) * E2);
+    const double ct = 2.0 * pe * gq * E2 * idt2;     // T_t = ct Δ_t
+#pragma unroll
+    for (int c = 0; c < DIM - 1; ++c) acc.template out<0>(c, ct * D[c]);
+    acc.template out<0>(DIM - 1, Tn);
+    if (acc.template has_out<1>()) {
+        const double Hnn = pe / (k.delta_n * k.delta_n) * ((f - 2.0 * A0) + (2.0 * B0 - gq) * E2);
+        const double cnt = -2.0 * pe / k.delta_n * (gq - B0) * E2 * idt2;   // H_nt = cnt Δ_t
+#pragma unroll
+        for (int j = 0; j < DIM - 1; ++j) {
+#pragma unroll
+            for (int i = 0; i < DIM - 1; ++i) {
+                const double v = ct * ((i == j ? 1.0 : 0.0) - 2.0 * D[i] * D[j] * idt2);
+                acc.template out<1>(i + DIM * j, v);
+            }
+            acc.template out<1>((DIM - 1) + DIM * j, cnt * D[j]);
+            acc.template out<1>(j + DIM * (DIM - 1), cnt * D[j]);
+        }
+        acc.template out<1>((DIM - 1) + DIM * (DIM - 1), Hnn);
+    }
+}
+
+}  // namespace mm

@@ -1,0 +1,137 @@
+// Device-pointer entry points of the streaming (HBM-bound) models: LinearElastic, Plastic (J2),
+// NeoHook / Yeoh / StVenant, XuNeedleman, plus the synthetic-input generator.
+#include <cuda_runtime.h>
+#include "../../include/mmb200.h"
+#include "mm_kernels.cuh"
+
+namespace mm {
+
+// ---- Ops ----------------------------------------------------------------------------------------
+struct ElasticOp {
+    static constexpr int NIN = 1, NOUT = 2;
+    __host__ __device__ static constexpr int in_nc(int) { return 6; }
+    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : 36; }
+    ElasticK k;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t) const { linear_elastic_point(k, acc); }
+};
+
+struct PlasticOp {
+    static constexpr int NIN = 2, NOUT = 3;
+    __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? 6 : 14; }
+    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : (a == 1 ? 36 : 14); }
+    PlasticK k;
+    uint8_t* flags;
+    uint8_t* iters;
+    int32_t* n_fail;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i) const {
+        int it = 0;
+        const int flag = plastic_point(k, acc, &it);
+        if (flags) flags[i] = (uint8_t)flag;
+        if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if ((flag & MM_FLAG_FAILED) && n_fail) atomicAdd(n_fail, 1);
+    }
+};
+
+template <int MODEL, int KIND> struct HyperOp {
+    static constexpr int NIN = 1, NOUT = 2;
+    __host__ __device__ static constexpr int in_nc(int) { return KIND == 1 ? 9 : 6; }
+    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : 36; }
+    HyperK k;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t) const { hyper_point<MODEL, KIND>(k, acc); }
+};
+
+template <int DIM> struct XuOp {
+    static constexpr int NIN = 1, NOUT = 2;
+    __host__ __device__ static constexpr int in_nc(int) { return DIM; }
+    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? DIM : DIM * DIM; }
+    XuK k;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t) const { xu_point<DIM>(k, acc); }
+};
+
+// ---- synthetic inputs ---------------------------------------------------------------------------
+struct SynthParams { double lo[48], hi[48]; };
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) synth_kernel(double* out, int64_t N, int nc, int layout, uint64_t seed, const SynthParams sp) {
+    const int64_t total = N * nc;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+        int64_t i; int c;
+        if (layout == MM_LAYOUT_SOA) { c = (int)(e / N); i = e - (int64_t)c * N; }
+        else                         { i = e / nc; c = (int)(e - i * nc); }
+        const uint64_t h = splitmix64(seed + (uint64_t)i * (uint64_t)nc + (uint64_t)c);
+        const double u = __ull2double_rn(h >> 11) * (1.0 / 9007199254740992.0);
+        // no FMA contraction: bit-identical to the host generator used by the parity harness
+        out[e] = __dadd_rn(sp.lo[c], __dmul_rn(__dsub_rn(sp.hi[c], sp.lo[c]), u));
+    }
+}
+
+template <int MODEL> int launch_hyper(const HyperK& k, const double* strain, int strain_kind, double* S, double* dSdC, int64_t N, int layout, cudaStream_t st) {
+    Ptrs<1, 2> p;
+    p.in[0] = strain; p.out[0] = S; p.out[1] = dSdC;
+    if (strain_kind == MM_STRAIN_F) { HyperOp<MODEL, 1> op; op.k = k; return launch_points<HyperOp<MODEL, 1>, 256>(op, p, N, layout, st, "mm_hyper"); }
+    HyperOp<MODEL, 0> op; op.k = k;
+    return launch_points<HyperOp<MODEL, 0>, 256>(op, p, N, layout, st, "mm_hyper");
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" {
+
+int mm_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig, double* tan_or_null, int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!eps || !sig))) return set_error(MM_ERR_ARG, "mm_linear_elastic: bad argument");
+    ElasticOp op; op.k = make_elastic_k(p->E, p->nu);
+    Ptrs<1, 2> ptrs; ptrs.in[0] = eps; ptrs.out[0] = sig; ptrs.out[1] = tan_or_null;
+    return launch_points<ElasticOp, 256>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_linear_elastic");
+}
+
+int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, double* sig, double* tan, double* state_out,
+               uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!eps || !state_in || !sig || !state_out))) return set_error(MM_ERR_ARG, "mm_plastic: bad argument");
+    PlasticOp op;
+    op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
+    op.flags = flags; op.iters = iters; op.n_fail = n_fail;
+    Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = state_out;
+    return launch_points<PlasticOp, 128>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
+}
+
+int mm_hyper(int model, const MMHyper* p, const double* strain, int strain_kind, double* S, double* dSdC, int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!strain || !S))) return set_error(MM_ERR_ARG, "mm_hyper: bad argument");
+    if (strain_kind != MM_STRAIN_C && strain_kind != MM_STRAIN_F) return set_error(MM_ERR_ARG, "mm_hyper: unknown strain_kind %d", strain_kind);
+    HyperK k; k.lambda = p->lambda; k.mu = p->mu; k.c2 = p->c2; k.c3 = p->c3;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (model) {
+        case MM_NEOHOOK: return launch_hyper<0>(k, strain, strain_kind, S, dSdC, N, layout, st);
+        case MM_YEOH: return launch_hyper<1>(k, strain, strain_kind, S, dSdC, N, layout, st);
+        case MM_STVENANT: return launch_hyper<2>(k, strain, strain_kind, S, dSdC, N, layout, st);
+    }
+    return set_error(MM_ERR_ARG, "mm_hyper: unknown model %d", model);
+}
+
+int mm_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, double* dTdD, int dim, int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!jump || !T))) return set_error(MM_ERR_ARG, "mm_xu_needleman: bad argument");
+    const XuK k = make_xu_k(p->Phi_n, p->Phi_t, p->delta_n, p->delta_t, p->Delta_n_star);
+    Ptrs<1, 2> ptrs; ptrs.in[0] = jump; ptrs.out[0] = T; ptrs.out[1] = dTdD;
+    if (dim == 3) { XuOp<3> op; op.k = k; return launch_points<XuOp<3>, 256>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
+    if (dim == 2) { XuOp<2> op; op.k = k; return launch_points<XuOp<2>, 256>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
+    return set_error(MM_ERR_ARG, "mm_xu_needleman: dim must be 2 or 3 (got %d)", dim);
+}
+
+int mm_synth_uniform(double* out, int64_t N, int nc, int layout, uint64_t seed, const double* lo, const double* hi, void* stream) {
+    if (!out || !lo || !hi || N < 0 || nc < 1 || nc > 48) return set_error(MM_ERR_ARG, "mm_synth_uniform: bad argument");
+    if (N == 0) return MM_OK;
+    SynthParams sp;
+    for (int c = 0; c < nc; ++c) { sp.lo[c] = lo[c]; sp.hi[c] = hi[c]; }
+    int64_t blocks = (N * nc + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    synth_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, N, nc, layout, seed, sp);
+    return check_launch("mm_synth_uniform");
+}
+
+}  // extern "C"

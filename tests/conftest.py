@@ -1,0 +1,46 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.dirname(os.path.abspath(__file__))):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with `pytest -m gpu` under gpurun)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle as O
+
+    O.lib()
+    return O
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import json
+
+    with open(os.path.join(ROOT, "tests", "golden", "reference_golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def mm():
+    import materialmodels_jl_b200 as mm
+
+    return mm
+
+
+@pytest.fixture(scope="session")
+def cuda_lib(mm):
+    """The native library on a GPU box; fails (does not skip) if it is missing or sees no device."""
+    import materialmodels_jl_b200._lib as L
+
+    lib = L.load()
+    assert lib.mm_device_count() >= 1, "no CUDA device visible"
+    return lib

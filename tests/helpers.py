@@ -1,0 +1,102 @@
+"""Shared test utilities: error metrics, material set-ups, the golden load paths."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import materialmodels_jl_b200._abi as abi
+import materialmodels_jl_b200.synth as sy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# FP64 parity tolerance stated by BASELINE.json north_star: 1e-12 relative.
+RTOL = 1e-12
+
+
+def rel_err(a, b, axis=0):
+    """Per-point norm-wise relative error ||a-b|| / max(||a||,||b||) — the metric of Julia's `≈`
+    that the reference's own tests use (test/test_utils.jl:27-29). Arrays are SoA (nc, N)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    num = np.linalg.norm(a - b, axis=axis)
+    den = np.maximum(np.linalg.norm(a, axis=axis), np.linalg.norm(b, axis=axis))
+    den = np.where(den == 0, 1.0, den)
+    return num / den
+
+
+def scaled_err(a, b, scale, axis=0):
+    """Per-point ||a-b|| / scale, for quantities whose own norm can be ~0 (state increments)."""
+    return np.linalg.norm(np.asarray(a) - np.asarray(b), axis=axis) / scale
+
+
+def soa(a, layout):
+    """view any layout as SoA (nc, N)"""
+    return a if layout == 0 else np.ascontiguousarray(a.T)
+
+
+def plastic_c():
+    p = sy.PLASTIC_PARAMS
+    return abi.MMPlastic(p["E"], p["nu"], p["sigma_y"], p["H"], p["r"], p["kappa_inf"], p["alpha_inf"])
+
+
+def crystal_c(O, q=None, rodrigues=None, structure=0):
+    c = dict(sy.CRYSTAL_PARAMS)
+    if q is not None:
+        c["q"] = q
+    pl, di = O.slipsystems(structure, rodrigues or sy.CRYSTAL_RODRIGUES)
+    return O.crystal_params(c["E"], c["nu"], c["tau_y"], c["H_iso"], c["H_kin"], c["q"], c["alpha_inf"], c["t_star"], c["sigma_c"], c["m"], pl, di)
+
+
+def xu_c(O):
+    x = sy.XU_PARAMS
+    return O.xu_params(x["sigma_max"], x["tau_max"], x["sigma_max"] * np.e * x["delta_n"], x["tau_max"] * np.sqrt(0.5 * np.e) * x["delta_t"], x["Delta_n_star"])
+
+
+def plastic_golden_loading():
+    """get_Plastic_loading() — reference test/test_plastic.jl:33-42"""
+    s1 = np.linspace(0.0, 0.005, 5)
+    s2 = np.linspace(0.005, 0.001, 5)
+    s3 = np.linspace(0.001, 0.007, 5)
+    xs = list(s1[1:]) + list(s2[1:]) + list(s3[1:])
+    return [np.array([x, x / 10, 0.0, 0.0, 0.0, 0.0]) for x in xs]
+
+
+def crystal_golden_loading():
+    """get_visco_plastic_loading() — reference test/test_crystal_visco_plastic.jl:32-42"""
+    s1 = np.linspace(0.0, 0.01, 5)
+    return [np.array([s1[i] - s1[i - 1], (s1[i] - s1[i - 1]) / 10, 0.0, 0.0, 0.0, 0.0]) for i in range(1, 5)]
+
+
+def linear_elastic_golden_loading():
+    """get_LinearElastic_loading() — reference test/test_linear_elastic.jl:37-40"""
+    return [np.array([x, x / 10, 0.0, 0.0, 0.0, 0.0]) for x in np.linspace(0.0, 0.02, 2)]
+
+
+def plastic_state_scales(eps, sig):
+    """Natural scales for the Plastic state error: εᵖ and μ against the strain magnitude, κ and α against
+    the stress magnitude (a barely-yielding point has |state| ~ 1e-9 obtained from a cancelling yield
+    function, so an error relative to its own norm is ill-posed)."""
+    e = np.linalg.norm(eps, axis=0)
+    s = np.linalg.norm(sig, axis=0)
+    return np.where(e == 0, 1.0, e), np.where(s == 0, 1.0, s)
+
+
+_twin = None
+
+
+def hosttwin():
+    """g++ build of the kernels' per-point math with a host accessor (tests/hosttwin/hosttwin.cpp)."""
+    global _twin
+    if _twin is None:
+        d = os.path.join(ROOT, "tests", "hosttwin")
+        so = os.path.join(d, "libhosttwin.so")
+        srcs = [os.path.join(d, "hosttwin.cpp")] + [os.path.join(ROOT, "materialmodels.jl_b200", "csrc", f) for f in ("mm_math.cuh", "mm_crystal_math.cuh")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, srcs[0]])
+        _twin = C.CDLL(so)
+    return _twin
+
+
+def P(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)

@@ -1,0 +1,60 @@
+// TEST-ONLY: instantiates the kernels' per-point math (csrc/mm_math.cuh, mm_crystal_math.cuh) with a
+// host accessor so the algebra can be compared with the oracle on a CPU-only box.  Never shipped,
+// never loaded by the product; the GPU parity tests (-m gpu) are the real gate.
+#include <cstdint>
+#include <cstring>
+#include "../../include/mmb200.h"
+#include "../../materialmodels.jl_b200/csrc/mm_math.cuh"
+#include "../../materialmodels.jl_b200/csrc/mm_crystal_math.cuh"
+
+namespace {
+template <int NIN, int NOUT> struct HostAcc {   // SoA host arrays
+    const double* inp[NIN]; double* outp[NOUT]; int64_t N, i;
+    template <int A> double in(int c) const { return inp[A][(int64_t)c * N + i]; }
+    template <int A> void out(int c, double v) const { outp[A][(int64_t)c * N + i] = v; }
+    template <int A> bool has_out() const { return outp[A] != nullptr; }
+};
+}
+
+extern "C" {
+int twin_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig, double* tan, int64_t N) {
+    mm::ElasticK k = mm::make_elastic_k(p->E, p->nu);
+    for (int64_t i = 0; i < N; ++i) { HostAcc<1, 2> a{{eps}, {sig, tan}, N, i}; mm::linear_elastic_point(k, a); }
+    return 0;
+}
+int twin_plastic(const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags, uint8_t* iters,
+                 double tol, int max_iter, int64_t N) {
+    mm::PlasticK k = mm::make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, tol, max_iter);
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<2, 3> a{{eps, sin}, {sig, tan, sout}, N, i};
+        int it = 0; int f = mm::plastic_point(k, a, &it);
+        flags[i] = (uint8_t)f; iters[i] = (uint8_t)it;
+    }
+    return 0;
+}
+int twin_hyper(int model, const MMHyper* p, const double* strain, int kind, double* S, double* T, int64_t N) {
+    mm::HyperK k{p->lambda, p->mu, p->c2, p->c3};
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<1, 2> a{{strain}, {S, T}, N, i};
+        if (kind == 1) { if (model == 0) mm::hyper_point<0, 1>(k, a); else if (model == 1) mm::hyper_point<1, 1>(k, a); else mm::hyper_point<2, 1>(k, a); }
+        else           { if (model == 0) mm::hyper_point<0, 0>(k, a); else if (model == 1) mm::hyper_point<1, 0>(k, a); else mm::hyper_point<2, 0>(k, a); }
+    }
+    return 0;
+}
+int twin_xu(const MMXuNeedleman* p, const double* jump, double* T, double* H, int dim, int64_t N) {
+    mm::XuK k = mm::make_xu_k(p->Phi_n, p->Phi_t, p->delta_n, p->delta_t, p->Delta_n_star);
+    for (int64_t i = 0; i < N; ++i) { HostAcc<1, 2> a{{jump}, {T, H}, N, i}; if (dim == 3) mm::xu_point<3>(k, a); else mm::xu_point<2>(k, a); }
+    return 0;
+}
+int twin_crystal(const MMCrystal* p, const double* deps, double dt, const double* sin, double* sig, double* tan, double* sout, uint16_t* active,
+                 uint8_t* iters, double tol, int max_iter, int64_t N) {
+    mm::CrystalK k;
+    mm::make_crystal_k(k, p->E, p->nu, p->tau_y, p->H_kin, p->alpha_inf, p->t_star, p->sigma_c, p->m, p->MS, p->H, dt, tol, max_iter);
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<2, 3> a{{deps, sin}, {sig, tan, sout}, N, i};
+        int it = 0; unsigned m = mm::crystal_point(k, a, &it);
+        active[i] = (uint16_t)m; iters[i] = (uint8_t)it;
+    }
+    return 0;
+}
+}

@@ -1,0 +1,80 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/mmb200.h declares;
+the host-side parameter helpers (no GPU involved) agree with the oracle's."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+import helpers as H
+import materialmodels_jl_b200._abi as abi
+import materialmodels_jl_b200._lib as L
+
+
+def declared_symbols():
+    hdr = open(os.path.join(H.ROOT, "include", "mmb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(mmh?_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    names = declared_symbols()
+    assert len(names) >= 20
+    lib = C.CDLL(L.SO_PATH)
+    for n in names:
+        assert hasattr(lib, n), "libmmb200.so does not export %s" % n
+    # the ctypes mirror covers exactly the declared set
+    assert sorted(abi.SIGNATURES) == names
+
+
+def test_struct_sizes_match_header():
+    assert C.sizeof(abi.MMLinearElastic) == 16 and C.sizeof(abi.MMPlastic) == 56 and C.sizeof(abi.MMHyper) == 32
+    assert C.sizeof(abi.MMXuNeedleman) == 40 and C.sizeof(abi.MMNewtonOpts) == 16
+    assert C.sizeof(abi.MMCrystal) == 80 + 8 + 12 * 9 * 8 + 12 * 12 * 8
+
+
+def test_version_and_no_device_is_reported_not_fatal():
+    lib = L.load()
+    assert b"sm_100a" in lib.mm_version()
+    assert lib.mm_device_count() >= 0
+
+
+def test_bad_arguments_return_error_codes():
+    lib = L.load()
+    p = abi.MMLinearElastic(200e3, 0.3)
+    assert lib.mm_linear_elastic(C.byref(p), None, None, None, 10, 0, None) == abi.MM_ERR_ARG
+    assert b"bad argument" in lib.mm_last_error()
+    assert lib.mm_linear_elastic(C.byref(p), None, None, None, 0, 0, None) == 0          # empty batch is a no-op
+    x = abi.MMXuNeedleman(1, 1, 1, 1, 2)
+    buf = (C.c_double * 8)()
+    assert lib.mm_xu_needleman(C.byref(x), buf, buf, buf, 4, 0, 0, None) == abi.MM_ERR_ARG  # dim must be 2 or 3
+    c = abi.MMCrystal()
+    c.nslip = 7
+    assert lib.mm_crystal(C.byref(c), buf, 1.0, buf, buf, buf, buf, None, None, None, None, 1, 0, None) == abi.MM_ERR_ARG
+
+
+def test_elastic_tangent_helper_matches_oracle(oracle, mm):
+    assert np.array_equal(mm.elastic_tangent_3D(200e3, 0.3), oracle.elastic_tangent_3d(200e3, 0.3))
+
+
+def test_slipsystems_and_crystal_setup_match_oracle(oracle, mm):
+    for structure, code in ((mm.FCC(), 0), (mm.BCC(), 1)):
+        ss = mm.slipsystems(structure, (-0.665267, 0.0203875, 1.08633))
+        pl, di = oracle.slipsystems(code, (-0.665267, 0.0203875, 1.08633))
+        assert np.allclose(np.array([s[0] for s in ss]), pl, rtol=0, atol=2e-16)
+        assert np.allclose(np.array([s[1] for s in ss]), di, rtol=0, atol=2e-16)
+        m = mm.CrystalViscoPlastic(slipsystems=ss, **mm.synth.CRYSTAL_PARAMS)
+        ref = H.crystal_c(oracle, structure=code)
+        assert np.allclose(np.array(m._c.MS), np.array(ref.MS), rtol=0, atol=3e-16)
+        assert np.array_equal(np.array(m._c.H), np.array(ref.H))
+
+
+def test_xu_setup_matches_reference_formulas(mm):
+    Φn = mm.xu_needleman_Φₙ(400.0, 0.002)
+    Φt = mm.xu_needleman_Φₜ(200.0, 0.002)
+    assert np.isclose(mm.xu_needleman_σₘₐₓ(Φn, 0.002), 400.0) and np.isclose(mm.xu_needleman_τₘₐₓ(Φt, 0.002), 200.0)
+    m = mm.XuNeedleman(σₘₐₓ=400.0, τₘₐₓ=200.0, Φₙ=Φn, Φₜ=Φt, Δₙˢ=0.01)
+    out = abi.MMXuNeedleman()
+    assert L.load().mm_xu_needleman_setup(400.0, 200.0, Φn, Φt, 0.01, C.byref(out)) == 0
+    assert np.isclose(out.delta_n, 0.002) and np.isclose(out.delta_t, 0.002)
+    assert out.delta_n == m.δₙ and out.delta_t == m.δₜ

@@ -1,0 +1,158 @@
+"""Full BASELINE.json sizes on the GPU: the oracle cannot finish 10^8 points in seconds, so parity at
+scale is shown through (i) an oracle check on a strided sample of the very same run, (ii) bit-exact
+agreement between the big launch and an independent small launch over a random sub-range (catches any
+64-bit indexing slip: 36 x 10^8 doubles > 2^32 elements), and (iii) size-independent properties of the
+model (yield consistency, untouched elastic state, tangent symmetries, zero-jump traction)."""
+import numpy as np
+import pytest
+
+import helpers as H
+import materialmodels_jl_b200._abi as abi
+import materialmodels_jl_b200.synth as sy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch(cuda_lib):
+    import torch
+
+    return torch
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def sample_idx(N, n=20000):
+    step = max(N // n, 1)
+    return np.arange(0, N, step, dtype=np.int64)[:n]
+
+
+def test_plastic_1e8(mm, torch, oracle):
+    """BASELINE.json configs[1]: J2 plastic, 10^8 points, mixed elastic/plastic, step B from a non-virgin state."""
+    N = 10**8
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    ncA, loA, hiA, seedA = sy.c2_strain(0)
+    ncB, loB, hiB, seedB = sy.c2_strain(1)
+    st0 = mm.initial_material_state(m, N)
+    epsA = mm.synth_uniform(N, ncA, seedA, loA, hiA)
+    _, _, stA = mm.material_response(m, epsA, st0, tangent=False)
+    del st0, epsA
+    epsB = mm.synth_uniform(N, ncB, seedB, loB, hiB)
+    sig, tan, stB = mm.material_response(m, epsB, stA)
+    assert int(stB.n_fail.item()) == 0
+    frac = stB.flags.float().mean().item()
+    assert 0.4 < frac < 0.6                                                # mixed load (~50 % plastic)
+    # (i) oracle on a strided sample of the same run (A then B)
+    idx = sample_idx(N)
+    tidx = torch.from_numpy(idx).cuda()
+    eA = sy.host_uniform(len(idx), ncA, seedA, loA, hiA, idx=idx)
+    eB = sy.host_uniform(len(idx), ncB, seedB, loB, hiB, idx=idx)
+    assert np.array_equal(eB, host(epsB[:, tidx]))
+    p = H.plastic_c()
+    rA = oracle.plastic(p, eA, np.zeros((14, len(idx))))
+    rB = oracle.plastic(p, eB, rA["state"])
+    assert np.array_equal(host(stB.flags[tidx]), rB["flags"]) and np.array_equal(host(stB.iters[tidx]), rB["iters"])
+    assert H.rel_err(host(sig[:, tidx]), rB["sig"]).max() < H.RTOL
+    assert H.rel_err(host(tan[:, tidx]), rB["tan"]).max() < H.RTOL
+    es, ss = H.plastic_state_scales(eB, rB["sig"])
+    sB = host(stB.data[:, tidx])
+    assert H.scaled_err(sB[0:6], rB["state"][0:6], es).max() < H.RTOL
+    assert H.scaled_err(sB[6:13], rB["state"][6:13], ss).max() < H.RTOL
+    assert H.scaled_err(sB[13:14], rB["state"][13:14], es).max() < H.RTOL
+    # (ii) sub-range relaunch is bit-identical (upper end of the index range: offsets beyond 2^32 elements)
+    i0, n = N - 1234567, 1000003
+    sl = slice(i0, i0 + n)
+    st_sub = mm.PlasticState(stA.data[:, sl].contiguous())
+    s2, t2, n2 = mm.material_response(m, epsB[:, sl].contiguous(), st_sub)
+    assert torch.equal(s2, sig[:, sl]) and torch.equal(t2, tan[:, sl]) and torch.equal(n2.data, stB.data[:, sl])
+    # (iii) properties
+    pl = stB.flags == 1
+    d = sig - stB.data[7:13]
+    tr3 = (d[0] + d[3] + d[5]) / 3
+    vm = torch.sqrt(1.5 * ((d[0] - tr3) ** 2 + (d[3] - tr3) ** 2 + (d[5] - tr3) ** 2 + 2 * (d[1] ** 2 + d[2] ** 2 + d[4] ** 2)))
+    Phi = vm - m.σ_y - stB.data[6]
+    assert Phi[pl].abs().max().item() <= 1e-8                              # converged plastic points sit on the yield surface (R_μ, ftol 1e-8)
+    assert Phi[~pl].max().item() <= 0.0                                    # elastic points are inside or on it
+    assert torch.equal(stB.data[:, ~pl], stA.data[:, ~pl])                 # Plastic.jl:135: state returned unchanged
+    Ee = torch.from_numpy(mm.elastic_tangent_3D(m.E, m.ν)).cuda()
+    assert torch.equal(tan[:, ~pl], Ee[:, None].expand(36, int((~pl).sum().item())))
+    assert (stB.data[13][pl] > 0).all()                                    # plastic multiplier positive
+
+
+def test_hyper_1e8(mm, torch, oracle):
+    """BASELINE.json configs[2]: NeoHook and Yeoh from random F, 10^8 points."""
+    N = 10**8
+    nc, lo, hi, seed = sy.c3_defgrad()
+    F = mm.synth_uniform(N, nc, seed, lo, hi)
+    idx = sample_idx(N)
+    tidx = torch.from_numpy(idx).cuda()
+    Fh = sy.host_uniform(len(idx), nc, seed, lo, hi, idx=idx)
+    for name, model, prm in (("NeoHook", abi.MM_NEOHOOK, sy.NEOHOOK_PARAMS), ("Yeoh", abi.MM_YEOH, sy.YEOH_PARAMS)):
+        m = getattr(mm, name)(λ=prm["lambda_"], μ=prm["mu"], c2=prm["c2"], c3=prm["c3"])
+        S, T, _ = mm.material_response(mm.dSdC(), m, mm.DeformationGradient(F))
+        S_ref, T_ref = oracle.hyper(model, abi.MMHyper(**prm), Fh, abi.MM_STRAIN_F)
+        assert H.rel_err(host(S[:, tidx]), S_ref).max() < H.RTOL
+        assert H.rel_err(host(T[:, tidx]), T_ref).max() < H.RTOL
+        i0, n = N - 7654321, 500009
+        S2, T2, _ = mm.material_response(mm.dSdC(), m, mm.DeformationGradient(F[:, i0:i0 + n].contiguous()))
+        assert torch.equal(S2, S[:, i0:i0 + n]) and torch.equal(T2, T[:, i0:i0 + n])
+        # hyperelastic tangent has major symmetry: T[I,J] == T[J,I]
+        T4 = T.view(6, 6, N)
+        for I in range(6):
+            for J in range(I):
+                assert ((T4[I, J] - T4[J, I]).abs() <= 1e-13 * (T4[I, J].abs() + T4[J, I].abs()) + 1e-300).all()
+        del S, T, T4, S2, T2
+
+
+def test_xu_1e8(mm, torch, oracle):
+    """BASELINE.json configs[4]: XuNeedleman 3D, 10^8 interface points, opening and closing jumps."""
+    N = 10**8
+    x = sy.XU_PARAMS
+    m = mm.XuNeedleman(σₘₐₓ=x["sigma_max"], τₘₐₓ=x["tau_max"], Φₙ=mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]),
+                       Φₜ=mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), Δₙˢ=x["Delta_n_star"])
+    nc, lo, hi, seed = sy.c5_jump()
+    D = mm.synth_uniform(N, nc, seed, lo, hi)
+    T, Hh, _ = mm.material_response(m, D)
+    idx = sample_idx(N)
+    tidx = torch.from_numpy(idx).cuda()
+    Dh = sy.host_uniform(len(idx), nc, seed, lo, hi, idx=idx)
+    T_ref, H_ref = oracle.xu_needleman(H.xu_c(oracle), Dh)
+    assert H.rel_err(host(T[:, tidx]), T_ref).max() < H.RTOL and H.rel_err(host(Hh[:, tidx]), H_ref).max() < H.RTOL
+    assert (D[2] < 0).any() and (D[2] > 0).any()                           # loading and unloading (closing) jumps
+    assert torch.equal(Hh[1], Hh[3]) and torch.equal(Hh[2], Hh[6]) and torch.equal(Hh[5], Hh[7])   # symmetric Hessian
+    i0, n = N - 999, 999
+    T2, H2, _ = mm.material_response(m, D[:, i0:].contiguous())
+    assert torch.equal(T2, T[:, i0:]) and torch.equal(H2, Hh[:, i0:])
+    # reversibility (XuNeedleman.jl:5): the law is stateless — same jump, same traction
+    T3, _, _ = mm.material_response(m, D, tangent=False)
+    assert torch.equal(T3, T)
+
+
+def test_linear_elastic_1e6_and_crystal_1e6(mm, torch, oracle):
+    """configs[0] (10^6 LinearElastic, CPU-runnable in full) and a 10^6 slice of configs[3] (crystal)."""
+    N = 10**6
+    nc, lo, hi, seed = sy.c1_strain()
+    eps = sy.host_uniform(N, nc, seed, lo, hi)
+    s_ref, _ = oracle.linear_elastic(200e3, 0.3, eps, want_tangent=False)
+    s, t, _ = mm.material_response(mm.LinearElastic(E=200e3, ν=0.3), torch.from_numpy(eps).cuda())
+    assert H.rel_err(host(s), s_ref).max() < H.RTOL
+    # linearity: σ(2ε) == 2σ(ε) exactly in binary floating point
+    s2, _, _ = mm.material_response(mm.LinearElastic(E=200e3, ν=0.3), torch.from_numpy(2 * eps).cuda(), tangent=False)
+    assert torch.equal(s2, 2 * s)
+    ss = mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES)
+    cm = mm.CrystalViscoPlastic(slipsystems=ss, **sy.CRYSTAL_PARAMS)
+    nc, lo, hi, seed = sy.c4_strain_increment(0)
+    de = mm.synth_uniform(N, nc, seed, lo, hi)
+    sig, tan, st = mm.material_response(cm, de, mm.initial_material_state(cm, N), 1.0)
+    idx = sample_idx(N, 5000)
+    tidx = torch.from_numpy(idx).cuda()
+    r = oracle.crystal(H.crystal_c(oracle), sy.host_uniform(len(idx), nc, seed, lo, hi, idx=idx), np.zeros((42, len(idx))))
+    assert np.array_equal(host(st.flags[tidx]).view(np.uint16), r["active"]) and np.array_equal(host(st.iters[tidx]), r["iters"])
+    assert H.rel_err(host(sig[:, tidx]), r["sig"]).max() < H.RTOL and H.rel_err(host(tan[:, tidx]), r["tan"]).max() < H.RTOL
+    assert H.rel_err(host(st.data[:, tidx]), r["state"]).max() < H.RTOL
+    el = st.flags == 0                                                      # no active system: tangent is exactly Eᵉ, μ stays 0
+    Ee = torch.from_numpy(mm.elastic_tangent_3D(cm.E, cm.ν)).cuda()
+    assert torch.equal(tan[:, el], Ee[:, None].expand(36, int(el.sum().item())))
+    assert (st.data[30:42][:, el] == 0).all()

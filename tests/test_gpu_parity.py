@@ -1,0 +1,356 @@
+"""GPU parity: the CUDA path (through the C ABI, via the host mirror) against the oracle on the same
+seeded inputs, against the reference's golden vectors, and — at BASELINE.json's full sizes — through
+size-independent properties plus an oracle check on a strided sample.
+
+Bars (BASELINE.json north_star): yield / active-slip decisions and Newton iteration counts exact;
+σ, dσdε, state within 1e-12 relative (FP64).  "Relative" is the norm-wise per-point metric of Julia's
+`≈` (what the reference's own tests use); the Plastic state is scaled by its conjugate total quantity
+(see helpers.plastic_state_scales).
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+import materialmodels_jl_b200._abi as abi
+import materialmodels_jl_b200.synth as sy
+
+pytestmark = pytest.mark.gpu
+
+LAYOUTS = [("soa", 0), ("aos", 1)]
+
+
+@pytest.fixture(scope="module")
+def torch(cuda_lib):
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def to_layout(a_soa, lay):
+    return a_soa if lay == 0 else np.ascontiguousarray(a_soa.T)
+
+
+def as_soa(a, lay):
+    return a if lay == 0 else np.ascontiguousarray(a.T)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_device_generator_bit_identical(mm, torch):
+    for lname, lay in LAYOUTS:
+        for nc, lo, hi, seed in (sy.c1_strain(), sy.c2_strain(1), sy.c3_defgrad(), sy.c4_strain_increment(0), sy.c5_jump()):
+            d = host(mm.synth_uniform(100003, nc, seed, lo, hi, layout=lname))
+            h = sy.host_uniform(100003, nc, seed, lo, hi, layout=lay)
+            assert np.array_equal(d, h)
+
+
+@pytest.mark.parametrize("lname,lay", LAYOUTS)
+@pytest.mark.parametrize("N", [1, 255, 256, 257, 100003])
+def test_linear_elastic(mm, torch, oracle, lname, lay, N):
+    m = mm.LinearElastic(E=200e3, ν=0.3)
+    nc, lo, hi, seed = sy.c1_strain()
+    eps = sy.host_uniform(N, nc, seed, lo, hi, layout=lay)
+    s_ref, t_ref = oracle.linear_elastic(200e3, 0.3, eps, layout=lay)
+    s, t, st = mm.material_response(m, dev(torch, eps), layout=lname)
+    assert H.rel_err(as_soa(host(s), lay), as_soa(s_ref, lay)).max() < H.RTOL
+    assert np.array_equal(host(t), t_ref)                                  # tangent == Eᵉ exactly (test_linear_elastic.jl:18)
+    s2, t2, _ = mm.material_response(m, dev(torch, eps), layout=lname, tangent=False)
+    assert np.array_equal(host(s2), host(s)) and np.array_equal(t2, oracle.elastic_tangent_3d(200e3, 0.3))
+
+
+def test_empty_batches(mm, torch):
+    m = mm.LinearElastic(E=200e3, ν=0.3)
+    s, t, _ = mm.material_response(m, torch.zeros((6, 0), dtype=torch.float64, device="cuda"))
+    assert s.shape == (6, 0)
+    p = mm.Plastic(**sy.PLASTIC_PARAMS)
+    st = mm.initial_material_state(p, 0)
+    s, t, st2 = mm.material_response(p, torch.zeros((6, 0), dtype=torch.float64, device="cuda"), st)
+    assert s.shape == (6, 0) and st2.data.shape == (14, 0)
+
+
+def test_linear_elastic_golden(mm, torch, golden):
+    m = mm.LinearElastic(E=200e3, ν=0.3)
+    g = golden["LinearElastic1"]
+    for k, eps in enumerate(H.linear_elastic_golden_loading()):
+        s, t, _ = mm.material_response(m, dev(torch, eps.reshape(6, 1)))
+        assert np.allclose(host(s)[:, 0], g["stresses"][k], rtol=1e-15, atol=0)
+        assert np.array_equal(host(t)[:, 0], np.array(g["tangents"][k]))
+
+
+# ---------------------------------------------------------------------------------------------
+def check_plastic(r, s, t, new, eps_soa, lay):
+    sig, tan, so = as_soa(host(s), lay), as_soa(host(t), lay), as_soa(host(new.data), lay)
+    rs, rt, rst = as_soa(r["sig"], lay), as_soa(r["tan"], lay), as_soa(r["state"], lay)
+    assert np.array_equal(host(new.flags), r["flags"]), "yield flags differ"
+    assert np.array_equal(host(new.iters), r["iters"]), "Newton iteration counts differ"
+    assert H.rel_err(sig, rs).max() < H.RTOL
+    assert H.rel_err(tan, rt).max() < H.RTOL
+    es, ss = H.plastic_state_scales(eps_soa, rs)
+    assert H.scaled_err(so[0:6], rst[0:6], es).max() < H.RTOL
+    assert H.scaled_err(so[13:14], rst[13:14], es).max() < H.RTOL
+    assert H.scaled_err(so[6:13], rst[6:13], ss).max() < H.RTOL
+
+
+@pytest.mark.parametrize("lname,lay", LAYOUTS)
+def test_plastic_parity_three_steps(mm, torch, oracle, lname, lay):
+    N = 200003
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    p = H.plastic_c()
+    st = mm.initial_material_state(m, N, layout=lname)
+    st_ref = np.zeros((14, N) if lay == 0 else (N, 14))
+    for step in range(3):
+        nc, lo, hi, seed = sy.c2_strain(step)
+        eps = sy.host_uniform(N, nc, seed, lo, hi, layout=lay)
+        r = oracle.plastic(p, eps, st_ref, layout=lay)
+        assert r["n_fail"] == 0 and 0.3 < r["flags"].mean() < 0.7
+        s, t, new = mm.material_response(m, dev(torch, eps), st, cache=mm.get_cache(m))
+        check_plastic(r, s, t, new, as_soa(eps, lay), lay)
+        el = r["flags"] == 0
+        assert np.array_equal(as_soa(host(new.data), lay)[:, el], as_soa(host(st.data), lay)[:, el])   # Plastic.jl:135
+        st, st_ref = new, r["state"]
+
+
+def test_plastic_golden_path(mm, torch, golden):
+    """Plastic1.jld2 through the CUDA path (test_plastic.jl:33-49), 37 identical points per step."""
+    g = golden["Plastic1"]
+    m = mm.Plastic(E=200e3, ν=0.3, σ_y=200.0, H=50.0, r=0.5, κ_inf=13.0, α_inf=13.0)
+    n = 37
+    st = mm.initial_material_state(m, n)
+    iters = []
+    for k, eps in enumerate(H.plastic_golden_loading()):
+        s, t, st = mm.material_response(m, dev(torch, np.repeat(eps.reshape(6, 1), n, axis=1)), st)
+        s, t = host(s), host(t)
+        assert np.all(s == s[:, :1]) and np.all(t == t[:, :1])            # deterministic across threads
+        assert H.rel_err(s[:, :1], np.array(g["stresses"][k]).reshape(6, 1))[0] < 5e-15
+        assert H.rel_err(t[:, :1], np.array(g["tangents"][k]).reshape(36, 1))[0] < 5e-15
+        iters.append(int(host(st.iters)[0]))
+    assert iters == [0, 2, 2, 1, 0, 0, 2, 2, 0, 2, 2, 1]
+
+
+def test_plastic_without_tangent_and_in_place_state(mm, torch, cuda_lib):
+    import ctypes as C
+
+    N = 50001
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    nc, lo, hi, seed = sy.c2_strain(0)
+    eps = mm.synth_uniform(N, nc, seed, lo, hi)
+    st0 = mm.initial_material_state(m, N)
+    s, t, st1 = mm.material_response(m, eps, st0)
+    s2, t2, st1b = mm.material_response(m, eps, st0, tangent=False)
+    assert t2 is None and torch.equal(s, s2) and torch.equal(st1.data, st1b.data)
+    # state_in may alias state_out (include/mmb200.h)
+    buf = st0.data.clone()
+    sig = torch.empty_like(s)
+    rc = cuda_lib.mm_plastic(C.byref(m._c), C.c_void_p(eps.data_ptr()), C.c_void_p(buf.data_ptr()), C.c_void_p(sig.data_ptr()), None,
+                             C.c_void_p(buf.data_ptr()), None, None, None, None, N, 0, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(buf, st1.data) and torch.equal(sig, s)
+
+
+def test_plastic_nonconvergence_is_flagged_and_raises(mm, torch, oracle):
+    N = 5000
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    nc, lo, hi, seed = sy.c2_strain(0)
+    eps = sy.host_uniform(N, nc, seed, lo, hi)
+    opts = {"nlsolve_params": {"iterations": 1}}                          # one Newton update is not enough from the trial state
+    r = oracle.plastic(H.plastic_c(), eps, np.zeros((14, N)), max_iter=1)
+    assert r["n_fail"] > 0
+    with pytest.raises(RuntimeError, match="Material model not converged"):   # Plastic.jl:157
+        mm.material_response(m, dev(torch, eps), mm.initial_material_state(m, N), options=opts)
+    o2 = dict(opts, defer_check=True)
+    s, t, new = mm.material_response(m, dev(torch, eps), mm.initial_material_state(m, N), options=o2)
+    assert int(new.n_fail.item()) == r["n_fail"]
+    assert np.array_equal(host(new.flags), r["flags"])
+
+
+# ---------------------------------------------------------------------------------------------
+HYPER = [("NeoHook", abi.MM_NEOHOOK, sy.NEOHOOK_PARAMS), ("Yeoh", abi.MM_YEOH, sy.YEOH_PARAMS), ("StVenant", abi.MM_STVENANT, sy.NEOHOOK_PARAMS),
+         ("NeoHook", abi.MM_NEOHOOK, dict(lambda_=115384.6, mu=76923.1, c2=0.0, c3=0.0))]
+
+
+@pytest.mark.parametrize("lname,lay", LAYOUTS)
+@pytest.mark.parametrize("name,model,prm", HYPER)
+def test_hyper_from_F_and_C(mm, torch, oracle, lname, lay, name, model, prm):
+    N = 100003
+    m = getattr(mm, name)(λ=prm["lambda_"], μ=prm["mu"], c2=prm["c2"], c3=prm["c3"])
+    nc, lo, hi, seed = sy.c3_defgrad()
+    F = sy.host_uniform(N, nc, seed, lo, hi, layout=lay)
+    S_ref, T_ref = oracle.hyper(model, abi.MMHyper(**prm), F, abi.MM_STRAIN_F, layout=lay)
+    S, T, _ = mm.material_response(mm.dSdC(), m, mm.DeformationGradient(dev(torch, F)), None, 0.0, layout=lname)   # traits.jl:91-107
+    assert H.rel_err(as_soa(host(S), lay), as_soa(S_ref, lay)).max() < H.RTOL
+    assert H.rel_err(as_soa(host(T), lay), as_soa(T_ref, lay)).max() < H.RTOL
+    # native call with C (neohook.jl:35) gives the same as the F route
+    Fs = as_soa(F, lay)
+    C6 = np.stack([(Fs[0 + 3 * a] * Fs[0 + 3 * b] + Fs[1 + 3 * a] * Fs[1 + 3 * b] + Fs[2 + 3 * a] * Fs[2 + 3 * b]) for a, b in ((0, 0), (1, 0), (2, 0), (1, 1), (2, 1), (2, 2))])
+    S2, T2, _ = mm.material_response(m, dev(torch, to_layout(C6, lay)), layout=lname)
+    assert H.rel_err(as_soa(host(S2), lay), as_soa(S_ref, lay)).max() < 1e-11
+    assert H.rel_err(as_soa(host(T2), lay), as_soa(T_ref, lay)).max() < 1e-11
+    # S = 2 dΨ/dC, dSdC = 2 d²Ψ/dC² at a few points (test_neohook.jl:13-16), via the oracle's nested duals
+    for j in (0, N // 2, N - 1):
+        _, S_ad, T_ad = oracle.hyper_ad(model, abi.MMHyper(**prm), np.ascontiguousarray(C6[:, j]))
+        assert H.rel_err(as_soa(host(S), lay)[:, j:j + 1], S_ad.reshape(6, 1))[0] < 1e-10
+        assert H.rel_err(as_soa(host(T), lay)[:, j:j + 1], T_ad.reshape(36, 1))[0] < 1e-10
+
+
+@pytest.mark.parametrize("lname,lay", LAYOUTS)
+@pytest.mark.parametrize("dim", [3, 2])
+def test_xu_needleman(mm, torch, oracle, lname, lay, dim):
+    N = 100003
+    x = sy.XU_PARAMS
+    m = mm.XuNeedleman(σₘₐₓ=x["sigma_max"], τₘₐₓ=x["tau_max"], Φₙ=mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]),
+                       Φₜ=mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), Δₙˢ=x["Delta_n_star"])
+    nc, lo, hi, seed = sy.c5_jump()
+    D = sy.host_uniform(N, nc, seed, lo, hi)
+    if dim == 2:
+        D = np.ascontiguousarray(D[1:])
+    D = to_layout(D, lay)
+    T_ref, H_ref = oracle.xu_needleman(H.xu_c(oracle), D, dim=dim, layout=lay)
+    T, Hh, _ = mm.material_response(m, dev(torch, D), layout=lname)
+    assert H.rel_err(as_soa(host(T), lay), as_soa(T_ref, lay)).max() < H.RTOL
+    assert H.rel_err(as_soa(host(Hh), lay), as_soa(H_ref, lay)).max() < H.RTOL
+    # KATs of test_xu_needleman.jl:15-28 through the CUDA path
+    kat = np.zeros((dim, 2))
+    kat[dim - 1, 0] = 0.002
+    kat[0, 1] = np.sqrt(2) * 0.002 / 2
+    Tk, _, _ = mm.material_response(m, dev(torch, to_layout(kat, lay)), layout=lname)
+    Tk = as_soa(host(Tk), lay)
+    assert np.isclose(Tk[dim - 1, 0], 400.0) and np.isclose(Tk[0, 1], 200.0)
+
+
+# ---------------------------------------------------------------------------------------------
+def make_crystal(mm, q=0.0, structure=None):
+    prm = dict(sy.CRYSTAL_PARAMS)
+    prm["q"] = q
+    ss = mm.slipsystems(structure or mm.FCC(), sy.CRYSTAL_RODRIGUES)
+    return mm.CrystalViscoPlastic(slipsystems=ss, **prm)
+
+
+@pytest.mark.parametrize("lname,lay", LAYOUTS)
+def test_crystal_parity_two_steps(mm, torch, oracle, lname, lay):
+    N = 20011
+    m = make_crystal(mm)
+    cp = H.crystal_c(oracle)
+    st = mm.initial_material_state(m, N, layout=lname)
+    st_ref = np.zeros((42, N) if lay == 0 else (N, 42))
+    for step in range(2):
+        nc, lo, hi, seed = sy.c4_strain_increment(step)
+        de = sy.host_uniform(N, nc, seed, lo, hi, layout=lay)
+        r = oracle.crystal(cp, de, st_ref, layout=lay)
+        assert r["n_fail"] == 0
+        s, t, new = mm.material_response(m, dev(torch, de), st, 1.0)
+        assert np.array_equal(host(new.flags).view(np.uint16), r["active"]), "active-slip masks differ"
+        assert np.array_equal(host(new.iters), r["iters"]), "Newton iteration counts differ"
+        assert H.rel_err(as_soa(host(s), lay), as_soa(r["sig"], lay)).max() < H.RTOL
+        assert H.rel_err(as_soa(host(t), lay), as_soa(r["tan"], lay)).max() < H.RTOL
+        assert H.rel_err(as_soa(host(new.data), lay), as_soa(r["state"], lay)).max() < H.RTOL
+        st, st_ref = new, r["state"]
+
+
+def test_crystal_golden_path(mm, torch, golden):
+    g = golden["CrystalViscoPlastic1"]
+    m = make_crystal(mm)
+    n = 5
+    st = mm.initial_material_state(m, n)
+    tol_s = [1e-15, 1e-15, 5e-14, 5e-11]
+    tol_t = [1e-15, 1e-15, 1e-13, 3e-10]
+    iters = []
+    for k, de in enumerate(H.crystal_golden_loading()):
+        s, t, st = mm.material_response(m, dev(torch, np.repeat(de.reshape(6, 1), n, axis=1)), st)   # Δt defaults to 1.0
+        assert H.rel_err(host(s)[:, :1], np.array(g["stresses"][k]).reshape(6, 1))[0] < tol_s[k]
+        assert H.rel_err(host(t)[:, :1], np.array(g["tangents"][k]).reshape(36, 1))[0] < tol_t[k]
+        iters.append(int(host(st.iters)[0]))
+    assert iters == [0, 0, 19, 12]
+
+
+def test_crystal_cross_hardening_bcc_and_failures(mm, torch, oracle):
+    """q != 0 (full H matrix) on the reference's BCC table; a few points exceed max_iter = 100 — they must
+    be flagged exactly like the oracle's, and the host mirror must raise the reference's error."""
+    N = 4000
+    m = make_crystal(mm, q=0.4, structure=mm.BCC())
+    cp = H.crystal_c(oracle, q=0.4, structure=1)
+    st = mm.initial_material_state(m, N)
+    st_ref = np.zeros((42, N))
+    nfail_total = 0
+    for step in range(2):
+        nc, lo, hi, seed = sy.c4_strain_increment(step)
+        de = sy.host_uniform(N, nc, seed, lo, hi)
+        r = oracle.crystal(cp, de, st_ref)
+        s, t, new = mm.material_response(m, dev(torch, de), st, 1.0, options={"defer_check": True})
+        ok = (r["active"] & abi.MM_ACTIVE_FAILED) == 0
+        assert int(new.n_fail.item()) == r["n_fail"] == int((~ok).sum())
+        assert np.array_equal(host(new.flags).view(np.uint16), r["active"])
+        assert np.array_equal(host(new.iters), r["iters"])
+        assert H.rel_err(host(s)[:, ok], r["sig"][:, ok]).max() < H.RTOL
+        assert H.rel_err(host(t)[:, ok], r["tan"][:, ok]).max() < H.RTOL
+        assert H.rel_err(host(new.data)[:, ok], r["state"][:, ok]).max() < H.RTOL
+        if r["n_fail"]:
+            with pytest.raises(RuntimeError, match="Material model not converged"):
+                mm.material_response(m, dev(torch, de), st, 1.0)
+        nfail_total += r["n_fail"]
+        st_ref = np.where(ok[None, :], r["state"], st_ref)
+        st = mm.CrystalViscoPlasticState(dev(torch, st_ref), "soa")
+    assert nfail_total > 0
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lname,lay", LAYOUTS)
+def test_host_buffer_entry_points_match_device_path(mm, torch, lname, lay):
+    """mmh_* (host pointers, pipelined chunks incl. a ragged last chunk) == mm_* bit for bit."""
+    import materialmodels_jl_b200._lib as L
+
+    lib = L.load()
+    old = lib.mmh_set_chunk_points(1000)
+    try:
+        N = 3507
+        m = mm.Plastic(**sy.PLASTIC_PARAMS)
+        nc, lo, hi, seed = sy.c2_strain(0)
+        eps = sy.host_uniform(N, nc, seed, lo, hi, layout=lay)
+        sd, td, nd = mm.material_response(m, dev(torch, eps), mm.initial_material_state(m, N, layout=lname))
+        sh, th, nh = mm.material_response(m, eps, mm.initial_material_state(m, N, device="cpu", layout=lname))
+        assert isinstance(sh, np.ndarray)
+        assert np.array_equal(sh, host(sd)) and np.array_equal(th, host(td)) and np.array_equal(nh.data, host(nd.data))
+        assert np.array_equal(nh.flags, host(nd.flags)) and np.array_equal(nh.iters, host(nd.iters))
+        # second step with non-trivial state
+        nc, lo, hi, seed = sy.c2_strain(1)
+        eps = sy.host_uniform(N, nc, seed, lo, hi, layout=lay)
+        sd, td, nd2 = mm.material_response(m, dev(torch, eps), nd)
+        sh, th, nh2 = mm.material_response(m, eps, nh)
+        assert np.array_equal(sh, host(sd)) and np.array_equal(th, host(td)) and np.array_equal(nh2.data, host(nd2.data))
+        # the stateless models
+        nc, lo, hi, seed = sy.c3_defgrad()
+        F = sy.host_uniform(N, nc, seed, lo, hi, layout=lay)
+        y = mm.Yeoh(λ=1.0, μ=1.0, c2=-1.0, c3=1.0)
+        Sd, Td, _ = mm.material_response(mm.dSdC(), y, mm.DeformationGradient(dev(torch, F)), layout=lname)
+        Sh, Th, _ = mm.material_response(mm.dSdC(), y, mm.DeformationGradient(F), layout=lname)
+        assert np.array_equal(Sh, host(Sd)) and np.array_equal(Th, host(Td))
+        le = mm.LinearElastic(E=200e3, ν=0.3)
+        e6 = sy.host_uniform(N, 6, 1, -1e-3, 1e-3, layout=lay)
+        a, b, _ = mm.material_response(le, e6, layout=lname)
+        c, d, _ = mm.material_response(le, dev(torch, e6), layout=lname)
+        assert np.array_equal(a, host(c)) and np.array_equal(b, host(d))
+        x = sy.XU_PARAMS
+        xm = mm.XuNeedleman(σₘₐₓ=x["sigma_max"], τₘₐₓ=x["tau_max"], Φₙ=mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]),
+                            Φₜ=mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), Δₙˢ=x["Delta_n_star"])
+        nc, lo, hi, seed = sy.c5_jump()
+        D = sy.host_uniform(N, nc, seed, lo, hi, layout=lay)
+        a, b, _ = mm.material_response(xm, D, layout=lname)
+        c, d, _ = mm.material_response(xm, dev(torch, D), layout=lname)
+        assert np.array_equal(a, host(c)) and np.array_equal(b, host(d))
+        cm = make_crystal(mm)
+        nc, lo, hi, seed = sy.c4_strain_increment(0)
+        de = sy.host_uniform(N, nc, seed, lo, hi, layout=lay)
+        a, b, sa = mm.material_response(cm, de, mm.initial_material_state(cm, N, device="cpu", layout=lname))
+        c, d, sc = mm.material_response(cm, dev(torch, de), mm.initial_material_state(cm, N, layout=lname))
+        assert np.array_equal(a, host(c)) and np.array_equal(b, host(d)) and np.array_equal(sa.data, host(sc.data))
+        assert np.array_equal(sa.flags, host(sc.flags).view(np.uint16))
+    finally:
+        lib.mmh_set_chunk_points(old)
