@@ -1,0 +1,294 @@
+#!/usr/bin/env python3
+"""bench.py — material-point updates/s for BASELINE.json configs[1]: J2 `Plastic` (radial-return predictor +
+14-unknown local Newton, isotropic + kinematic hardening), 3D, 10^8 points per GPU, ~50 % of the points
+plastic, timed on step B (non-virgin state produced by step A).  One "step" = one pass of
+material_response over the whole batch: (σ, ∂σ∂ε, new state) for every point.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the oracle port on the host cores, rank 0 only)
+
+Prints ONE JSON line (rank 0).  `value`   : whole-job updates/s, inputs resident in HBM, CUDA-event timed.
+                                `e2e`     : the same metric through the public API with pinned HOST buffers
+                                            (mmh_plastic: H2D + kernel + D2H every step), a 2·10^7-point slice.
+                                `roofline`: algorithmic 608 B/point ÷ mean kernel time vs the measured HBM peak.
+                                `cpu_baseline`: the oracle (C++/OpenMP port of the reference algorithm) on a
+                                            bounded sample, rank 0 at N=1 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "material-point updates/sec (sigma + dsigma/deps + state), J2 plastic 3D"
+UNIT = "updates/s"
+BYTES_PER_POINT = 608          # eps 48 + state 112 in; sigma 48 + tangent 288 + state 112 out
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes read+written per launch of the dominant kernel, from the committed ncu capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "plastic_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk = float(f[0])
+                smax = float(f[1])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:    # timed region shorter than the sampling period: use every sample we have
+            sm = [float(l.split(",")[0]) for _, l in self.rows if l and l.split(",")[0].strip().replace(".", "").isdigit()]
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_run(points, steps=1, warmup=0):
+    """The oracle's mmo_plastic (dense 14x14 ForwardDiff-style Jacobian + LU Newton, as the reference does)
+    on all host cores; step A untimed to build the state, step B timed."""
+    import numpy as np
+
+    import oracle as O
+    from materialmodels_jl_b200 import _abi, synth as sy
+
+    p = _abi.MMPlastic(*[sy.PLASTIC_PARAMS[k] for k in ("E", "nu", "sigma_y", "H", "r", "kappa_inf", "alpha_inf")])
+    ncA, loA, hiA, seedA = sy.c2_strain(0)
+    ncB, loB, hiB, seedB = sy.c2_strain(1)
+    eA = O.synth_uniform(points, ncA, seedA, loA, hiA)
+    eB = O.synth_uniform(points, ncB, seedB, loB, hiB)
+    stA = O.plastic(p, eA, np.zeros((14, points)))["state"]
+    for _ in range(warmup):
+        O.plastic(p, eB, stA)
+    t0 = time.perf_counter()
+    frac = 0.0
+    for _ in range(steps):
+        r = O.plastic(p, eB, stA)
+        frac = float(r["flags"].mean())
+    dt = time.perf_counter() - t0
+    return points * steps / dt, O.num_threads(), dt, frac
+
+
+def run_reference(args):
+    """--impl reference: Julia is not installed here and the reference has no C/C++ sources to compile, so the
+    reference arm is the oracle port (oracle/, kind "port") on all host cores; each step is a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    pts = args.ref_points
+    if pts <= 0:   # size the per-step sample so that the whole run takes ~75 s whatever K is
+        rate, _, _, _ = cpu_baseline_run(100000)
+        pts = int(min(max(rate * 75.0 / (args.steps + min(args.warmup, 1) + 1), 50000), 4 * 10**6))
+    value, cores, dt, frac = cpu_baseline_run(pts, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Plastic J2, 1e8 points/GPU, ~50% plastic, step B (BASELINE.json configs[1])", "sample_points_per_step": pts,
+                   "plastic_fraction": frac},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d-point slice of the same synthetic workload per step, oracle mmo_plastic, OpenMP over all host cores" % pts},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=10**8, help="points per GPU (BASELINE.json configs[1]: 1e8)")
+    ap.add_argument("--e2e-points", type=int, default=2 * 10**7)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-points", type=int, default=4 * 10**6)
+    ap.add_argument("--ref-points", type=int, default=0, help="points per step of --impl reference (0 = sized for a ~75 s run)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+
+    import materialmodels_jl_b200 as mm
+    from materialmodels_jl_b200 import sharding, synth as sy
+
+    rank, world, local = sharding.init_process_group()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    N = args.points
+    lo_pt, _ = sharding.shard_range(N * world, rank, world)     # this rank's slice of the global point index range
+
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    ncA, loA, hiA, seedA = sy.c2_strain(0)
+    ncB, loB, hiB, seedB = sy.c2_strain(1)
+    # the generator indexes points globally: seed + (i0 + i)*nc + c  ==  (seed + i0*nc) + i*nc + c
+    epsA = mm.synth_uniform(N, ncA, seedA + lo_pt * ncA, loA, hiA, device=dev)
+    _, _, stA = mm.material_response(m, epsA, mm.initial_material_state(m, N, device=dev), tangent=False)
+    del epsA
+    epsB = mm.synth_uniform(N, ncB, seedB + lo_pt * ncB, loB, hiB, device=dev)
+    out = {"stress": torch.empty((6, N), dtype=torch.float64, device=dev), "tangent": torch.empty((36, N), dtype=torch.float64, device=dev),
+           "state": torch.empty((14, N), dtype=torch.float64, device=dev), "flags": torch.empty((N,), dtype=torch.uint8, device=dev),
+           "iters": torch.empty((N,), dtype=torch.uint8, device=dev)}
+    opts = {"defer_check": True}      # the convergence counter is read once after the timed region, not per step
+
+    def step():
+        return mm.material_response(m, epsB, stA, options=opts, out=out)
+
+    for _ in range(args.warmup):
+        _, _, stB = step()
+    torch.cuda.synchronize()
+    n_fail = int(stB.n_fail.item())
+    frac = float(stB.flags.float().mean().item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sharding.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    for k in range(args.steps):
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    sharding.barrier()
+    total_ms = ev[0][0].elapsed_time(ev[-1][1])
+    kern_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    total_ms_max = sharding.allreduce_max(total_ms, device=dev)
+    n_fail = sharding.allreduce_sum(n_fail, device=dev)           # the only "collective" of the path: a tiny control-plane sum
+    value = world * N * args.steps / (total_ms_max * 1e-3)
+    mean_kernel_ms = sum(kern_ms) / len(kern_ms)
+
+    # ---- e2e: public API, pinned host buffers, H2D + kernel + D2H inside the timed region --------------
+    e2e = None
+    if not args.no_e2e:
+        Ne = min(args.e2e_points, N)
+        del out
+        torch.cuda.empty_cache()
+        h_eps = mm.PinnedArray((6, Ne))
+        h_st = mm.PinnedArray((14, Ne))
+        h_out = {"stress": mm.PinnedArray((6, Ne)), "tangent": mm.PinnedArray((36, Ne)), "state": mm.PinnedArray((14, Ne)),
+                 "flags": mm.PinnedArray((Ne,), np.uint8), "iters": mm.PinnedArray((Ne,), np.uint8)}
+        h_eps.array[...] = epsB[:, :Ne].cpu().numpy()
+        h_st.array[...] = stA.data[:, :Ne].cpu().numpy()
+        st_host = mm.PlasticState(h_st.array)
+        outs = {k: v.array for k, v in h_out.items()}
+        mm.material_response(m, h_eps.array, st_host, out=outs)            # warm-up (workspace allocation)
+        sharding.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            _, _, sth = mm.material_response(m, h_eps.array, st_host, out=outs)   # raises if any point failed (reads n_fail)
+        dt = time.perf_counter() - t0
+        dt = sharding.allreduce_max(dt, device=dev)
+        same = bool(np.array_equal(outs["stress"], stB_slice_host(stB, mm, m, epsB, stA, Ne)))
+        chunks = -(-Ne // (1 << 20))
+        e2e = {"value": world * Ne * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 160 * Ne, "d2h_bytes_per_step": 450 * Ne + 4,
+               "points_per_step_per_gpu": Ne, "steps": args.e2e_steps, "api": "material_response(m, numpy eps, PlasticState(numpy)) -> mmh_plastic",
+               "kernel_launches_per_step": chunks, "matches_device_path": same,
+               "timing": "host clock around the blocking call (last op is a stream sync), max over ranks"}
+        for v in [h_eps, h_st] + list(h_out.values()):
+            v.free()
+
+    if rank != 0:
+        return 0
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_POINT * N / (mean_kernel_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Plastic J2 (E=200e3, nu=0.3, sigma_y=200, H=50, r=0.5, kappa_inf=alpha_inf=13), %d points/GPU, step B from a non-virgin state (BASELINE.json configs[1])" % N,
+                   "points_per_gpu": N, "layout": "soa", "plastic_fraction": frac, "n_not_converged": n_fail,
+                   "l2": "inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (160 * N / 1e9), "parallelism": "contiguous point shards, no data-path collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                     "kernel": "mm::soa_kernel<mm::PlasticOp,128>", "bytes_per_point": BYTES_PER_POINT, "points_per_launch": N, "kernel_ms_mean": mean_kernel_ms,
+                     "kernel_ms_min": kern_ms[0], "kernel_ms_max": kern_ms[-1], "peak_source": peak_src,
+                     "traffic_source": (traffic or {}).get("source")},
+        "clocks": clocks, "gpu_launches": args.steps,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        v, cores, dt, fr = cpu_baseline_run(args.cpu_points)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d-point slice of the same workload (step B), oracle mmo_plastic, %.1f s" % (args.cpu_points, dt)}
+    print(json.dumps(line))
+    return 0
+
+
+def stB_slice_host(stB, mm, m, epsB, stA, Ne):
+    """stress of the first Ne points from the device-resident path, for the e2e == device-path check"""
+    s, _, _ = mm.material_response(m, epsB[:, :Ne].contiguous(), mm.PlasticState(stA.data[:, :Ne].contiguous()), tangent=False)
+    return s.cpu().numpy()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

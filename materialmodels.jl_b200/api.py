@@ -239,19 +239,33 @@ def _response_linear_elastic(m, ε, state, layout, want_tangent):
     return σ, (tan if want_tangent else m.Eᵉ), state
 
 
-def _response_plastic(m, ε, state, options, want_tangent):
+def _out(out, key, shape, like, dtype=None):
+    """caller-provided output buffer (e.g. pinned host memory) or a fresh allocation"""
+    if out is not None and out.get(key) is not None:
+        a = out[key]
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError("out[%r] has shape %s, expected %s" % (key, tuple(a.shape), tuple(shape)))
+        if _is_host(like) != _is_host(a):
+            raise ValueError("out[%r] must live where the inputs live" % key)
+        if _is_host(a) and not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("out[%r] must be C-contiguous" % key)
+        return a
+    return _empty(shape, like, dtype)
+
+
+def _response_plastic(m, ε, state, options, want_tangent, out=None):
     layout = state.layout
     ε = _prep(ε)
     N = _npoints(ε, 6, layout)
     if N != state.N:
         raise ValueError("strain has %d points, state has %d" % (N, state.N))
     sin = _prep(state.data)
-    σ = _empty(_shape(6, N, layout), ε)
-    tan = _empty(_shape(36, N, layout), ε) if want_tangent else None
-    sout = _empty(_shape(14, N, layout), ε)
     host = _is_host(ε)
-    flags = _empty((N,), ε, np.uint8 if host else _torch().uint8)
-    iters = _empty((N,), ε, np.uint8 if host else _torch().uint8)
+    σ = _out(out, "stress", _shape(6, N, layout), ε)
+    tan = _out(out, "tangent", _shape(36, N, layout), ε) if want_tangent else None
+    sout = _out(out, "state", _shape(14, N, layout), ε)
+    flags = _out(out, "flags", (N,), ε, np.uint8 if host else _torch().uint8)
+    iters = _out(out, "iters", (N,), ε, np.uint8 if host else _torch().uint8)
     nfail = _zeros((1,), ε, np.int32 if host else _torch().int32)
     o = _newton_opts(m, options)
     lib = load()
@@ -333,13 +347,14 @@ def _response_xu(m, Δ, state, layout, want_tangent):
     return T, H, state
 
 
-def material_response(*args, cache=None, options=None, layout="soa", tangent=True):
+def material_response(*args, cache=None, options=None, layout="soa", tangent=True, out=None):
     """material_response(m, strain, state=None, Δt=None, cache=None, options=None)
     material_response(dSdC(), m, DeformationGradient(F) | RightCauchyGreen(C), state=None, Δt=0.0)
 
     Returns (stress, tangent, new_state) for all N points of `strain`.
     `layout` applies to stateless models (stateful ones use their state's layout);
-    `tangent=False` skips the 36-component tangent output (returns None in its place)."""
+    `tangent=False` skips the 36-component tangent output (returns None in its place);
+    `out` (Plastic) = dict of preallocated output buffers: stress, tangent, state, flags, iters."""
     args = list(args)
     if args and isinstance(args[0], AbstractTangent):                       # src/traits.jl:91-107
         out_tangent = args.pop(0)
@@ -373,7 +388,7 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
     if isinstance(m, Plastic):
         if state is None:
             raise TypeError("material_response(::Plastic, ε, state): state required")
-        return _response_plastic(m, strain, state, options, tangent)
+        return _response_plastic(m, strain, state, options, tangent, out)
     if isinstance(m, CrystalViscoPlastic):
         if state is None:
             raise TypeError("material_response(::CrystalViscoPlastic, Δε, state): state required")
@@ -395,3 +410,28 @@ def synth_uniform(N, nc, seed, lo, hi, layout="soa", device="cuda"):
         rc = load().mm_synth_uniform(_ptr(out), N, nc, _LAYOUTS[layout], int(seed), _ptr(lo), _ptr(hi), _stream(out))
     check(rc, "mm_synth_uniform")
     return out
+
+
+class PinnedArray:
+    """float64/uint8 numpy array backed by page-locked host memory (mmh_alloc_pinned): what a host-resident
+    caller should hand to the numpy path so the H2D/D2H copies run at PCIe speed and truly asynchronously."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = load().mmh_alloc_pinned(max(self.nbytes, 1))
+        if not self._ptr:
+            raise MemoryError("mmh_alloc_pinned(%d) failed" % self.nbytes)
+        buf = (ctypes.c_char * max(self.nbytes, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            load().mmh_free_pinned(ctypes.c_void_p(self._ptr))
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

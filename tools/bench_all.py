@@ -1,0 +1,131 @@
+#!/usr/bin/env python3
+"""Kernel timings for all five BASELINE.json configs (development aid; bench.py is the contract line).
+Prints one JSON object per kernel: ms (median/min over reps), algorithmic GB/s, fraction of the measured HBM peak."""
+import argparse, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import materialmodels_jl_b200 as mm
+from materialmodels_jl_b200 import synth as sy
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timeit(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def report(name, N, bpp, med, mn, extra=None):
+    gbs = bpp * N / (med * 1e-3) / 1e9
+    d = {"kernel": name, "N": N, "ms_median": round(med, 4), "ms_min": round(mn, 4), "B_per_pt": bpp, "GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak(), 3),
+         "updates_per_s": N / (med * 1e-3)}
+    if extra:
+        d.update(extra)
+    print(json.dumps(d), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--scale", type=float, default=1.0)
+    a = ap.parse_args()
+    want = lambda k: (not a.only) or any(w in k for w in a.only.split(","))
+    S = a.scale
+    if want("elastic"):
+        m = mm.LinearElastic(E=200e3, ν=0.3)
+        for N in (10**6, int(1e8 * S)):
+            nc, lo, hi, seed = sy.c1_strain()
+            eps = mm.synth_uniform(N, nc, seed, lo, hi)
+            sig = torch.empty_like(eps)
+            med, mn = timeit(lambda: mm.material_response(m, eps, tangent=False), a.reps)
+            report("linear_elastic sigma-only soa", N, 96, med, mn)
+            med, mn = timeit(lambda: mm.material_response(m, eps), a.reps)
+            report("linear_elastic +tangent soa", N, 384, med, mn)
+            del eps, sig
+    if want("plastic"):
+        N = int(1e8 * S)
+        m = mm.Plastic(**sy.PLASTIC_PARAMS)
+        for lname in ("soa", "aos"):
+            ncA, loA, hiA, seedA = sy.c2_strain(0)
+            ncB, loB, hiB, seedB = sy.c2_strain(1)
+            eA = mm.synth_uniform(N, ncA, seedA, loA, hiA, layout=lname)
+            _, _, stA = mm.material_response(m, eA, mm.initial_material_state(m, N, layout=lname), tangent=False)
+            del eA
+            eB = mm.synth_uniform(N, ncB, seedB, loB, hiB, layout=lname)
+            shp = lambda nc: (nc, N) if lname == "soa" else (N, nc)
+            out = {"stress": torch.empty(shp(6), dtype=torch.float64, device="cuda"), "tangent": torch.empty(shp(36), dtype=torch.float64, device="cuda"),
+                   "state": torch.empty(shp(14), dtype=torch.float64, device="cuda"), "flags": torch.empty((N,), dtype=torch.uint8, device="cuda"),
+                   "iters": torch.empty((N,), dtype=torch.uint8, device="cuda")}
+            med, mn = timeit(lambda: mm.material_response(m, eB, stA, options={"defer_check": True}, out=out), a.reps)
+            frac = out["flags"].float().mean().item()
+            report("plastic stepB " + lname, N, 608, med, mn, {"plastic_fraction": round(frac, 4)})
+            if lname == "soa":
+                z = mm.initial_material_state(m, N)
+                e0 = mm.synth_uniform(N, 6, 1, -1e-4, 1e-4)
+                med, mn = timeit(lambda: mm.material_response(m, e0, z, options={"defer_check": True}, out=out), a.reps)
+                report("plastic all-elastic soa", N, 608, med, mn)
+                e1 = mm.synth_uniform(N, 6, 2, 2e-3, 4e-3)
+                e1[3:] = -e1[3:]
+                med, mn = timeit(lambda: mm.material_response(m, e1, z, options={"defer_check": True}, out=out), a.reps)
+                report("plastic all-plastic soa", N, 608, med, mn, {"plastic_fraction": out["flags"].float().mean().item()})
+                del z, e0, e1
+            del eB, stA, out
+            torch.cuda.empty_cache()
+    if want("hyper"):
+        N = int(1e8 * S)
+        nc, lo, hi, seed = sy.c3_defgrad()
+        for lname in ("soa", "aos"):
+            F = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
+            for name, prm in (("NeoHook", sy.NEOHOOK_PARAMS), ("Yeoh", sy.YEOH_PARAMS), ("StVenant", sy.NEOHOOK_PARAMS)):
+                m = getattr(mm, name)(λ=prm["lambda_"], μ=prm["mu"], c2=prm["c2"], c3=prm["c3"])
+                med, mn = timeit(lambda: mm.material_response(mm.dSdC(), m, mm.DeformationGradient(F), layout=lname), a.reps)
+                report("%s from F %s" % (name, lname), N, 408, med, mn)
+            del F
+            torch.cuda.empty_cache()
+    if want("xu"):
+        N = int(1e8 * S)
+        x = sy.XU_PARAMS
+        m = mm.XuNeedleman(σₘₐₓ=x["sigma_max"], τₘₐₓ=x["tau_max"], Φₙ=mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]),
+                           Φₜ=mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), Δₙˢ=x["Delta_n_star"])
+        nc, lo, hi, seed = sy.c5_jump()
+        for lname in ("soa", "aos"):
+            D = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
+            med, mn = timeit(lambda: mm.material_response(m, D, layout=lname), a.reps)
+            report("xu_needleman 3D " + lname, N, 120, med, mn)
+            del D
+    if want("crystal"):
+        N = int(1e7 * S)
+        ss = mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES)
+        m = mm.CrystalViscoPlastic(slipsystems=ss, **sy.CRYSTAL_PARAMS)
+        for lname in ("soa",):
+            nc, lo, hi, seed = sy.c4_strain_increment(0)
+            dA = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
+            z = mm.initial_material_state(m, N, layout=lname)
+            med, mn = timeit(lambda: mm.material_response(m, dA, z, 1.0, options={"defer_check": True}), max(a.reps // 3, 2), warm=1)
+            _, _, stA = mm.material_response(m, dA, z, 1.0)
+            report("crystal stepA " + lname, N, 1056, med, mn, {"mean_iters": stA.iters.float().mean().item(), "frac_active": (stA.flags != 0).float().mean().item()})
+            nc, lo, hi, seed = sy.c4_strain_increment(1)
+            dB = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
+            med, mn = timeit(lambda: mm.material_response(m, dB, stA, 1.0, options={"defer_check": True}), max(a.reps // 3, 2), warm=1)
+            _, _, stB = mm.material_response(m, dB, stA, 1.0, options={"defer_check": True})
+            report("crystal stepB " + lname, N, 1056, med, mn, {"mean_iters": stB.iters.float().mean().item(), "frac_active": (stB.flags != 0).float().mean().item(),
+                                                                 "n_fail": int(stB.n_fail.item())})
+
+
+if __name__ == "__main__":
+    main()
