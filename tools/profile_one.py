@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""Tiny driver for ncu captures: runs a few launches of ONE kernel at a size ncu can replay quickly.
+usage: profile_one.py {plastic|plastic_aos|crystal|neohook|xu|elastic} [points]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import materialmodels_jl_b200 as mm
+from materialmodels_jl_b200 import synth as sy
+
+which = sys.argv[1] if len(sys.argv) > 1 else "plastic"
+N = int(float(sys.argv[2])) if len(sys.argv) > 2 else 10**7
+reps = 3
+if which.startswith("plastic"):
+    lname = "aos" if which.endswith("aos") else "soa"
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    nc, lo, hi, seed = sy.c2_strain(0)
+    eA = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
+    _, _, stA = mm.material_response(m, eA, mm.initial_material_state(m, N, layout=lname), tangent=False)
+    nc, lo, hi, seed = sy.c2_strain(1)
+    eB = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
+    for _ in range(reps):
+        s, t, st = mm.material_response(m, eB, stA, options={"defer_check": True})
+elif which == "crystal":
+    ss = mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES)
+    m = mm.CrystalViscoPlastic(slipsystems=ss, **sy.CRYSTAL_PARAMS)
+    nc, lo, hi, seed = sy.c4_strain_increment(0)
+    dA = mm.synth_uniform(N, nc, seed, lo, hi)
+    _, _, stA = mm.material_response(m, dA, mm.initial_material_state(m, N), 1.0)
+    nc, lo, hi, seed = sy.c4_strain_increment(1)
+    dB = mm.synth_uniform(N, nc, seed, lo, hi)
+    for _ in range(reps):
+        mm.material_response(m, dB, stA, 1.0, options={"defer_check": True})
+elif which == "neohook":
+    nc, lo, hi, seed = sy.c3_defgrad()
+    F = mm.synth_uniform(N, nc, seed, lo, hi)
+    m = mm.NeoHook(λ=1.0, μ=1.0)
+    for _ in range(reps):
+        mm.material_response(mm.dSdC(), m, mm.DeformationGradient(F))
+elif which == "xu":
+    x = sy.XU_PARAMS
+    m = mm.XuNeedleman(σₘₐₓ=x["sigma_max"], τₘₐₓ=x["tau_max"], Φₙ=mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]),
+                       Φₜ=mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), Δₙˢ=x["Delta_n_star"])
+    nc, lo, hi, seed = sy.c5_jump()
+    D = mm.synth_uniform(N, nc, seed, lo, hi)
+    for _ in range(reps):
+        mm.material_response(m, D)
+elif which == "elastic":
+    nc, lo, hi, seed = sy.c1_strain()
+    e = mm.synth_uniform(N, nc, seed, lo, hi)
+    m = mm.LinearElastic(E=200e3, ν=0.3)
+    for _ in range(reps):
+        mm.material_response(m, e)
+torch.cuda.synchronize()
+print("done", which, N)
