@@ -34,6 +34,7 @@ def stale():
 
 
 def build(force=False, verbose=False, extra=()):
+    extra = list(extra) + os.environ.get("MM_NVCC_EXTRA", "").split()      # e.g. -DMM_PLASTIC_MINBLOCKS=3 for tuning sweeps
     if not force and not stale():
         return SO
     objs = []

@@ -32,8 +32,10 @@ template <int NIN, int NOUT> struct SoaAcc {
     template <int A> __device__ __forceinline__ bool has_out() const { return p.out[A] != nullptr; }
 };
 
+template <class Op> struct MinBlocks { static constexpr int value = 1; };   // per-Op occupancy target (register cap)
+
 template <class Op, int BS>
-__global__ void __launch_bounds__(BS) soa_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N) {
+__global__ void __launch_bounds__(BS, MinBlocks<Op>::value) soa_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N) {
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     if (i >= N) return;
     SoaAcc<Op::NIN, Op::NOUT> acc(p, N, i);

@@ -27,8 +27,49 @@ MM_HD double ddot6(const double* a, const double* b) {
     return a[0] * b[0] + a[3] * b[3] + a[5] * b[5] + 2.0 * (a[1] * b[1] + a[2] * b[2] + a[4] * b[4]);
 }
 MM_HD double tr6(const double* a) { return a[0] + a[3] + a[5]; }
+
+// Reciprocal / reciprocal square root for well-scaled positive normal arguments, <= ~1 ulp, WITHOUT the IEEE
+// slow-path scaffolding nvcc emits around `1.0/x` and `sqrt` (sub-normal / inf handling: a BSSY/CALL/BSYNC region
+// plus ~10 integer instructions each; ncu showed 56 % of the J2 kernel's issued instructions were not FP64 math).
+// MUFU.RCP64H / MUFU.RSQ64H seed (~2^-20) + Newton steps in DFMA.  Host build: plain division / sqrt.
+MM_HD double fast_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    if (!(fabs(x) >= 1e-290 && fabs(x) <= 1e290)) return 1.0 / x;      // sub-normal / huge / NaN: IEEE path (never on sane data)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+// returns 1/sqrt(x); *root = sqrt(x)
+MM_HD double fast_rsqrt(double x, double* root) {
+#if defined(__CUDA_ARCH__)
+    if (!(x >= 1e-290 && x <= 1e290)) { const double r = sqrt(x); *root = r; return 1.0 / r; }   // 0, sub-normal, huge, NaN
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);        // ½(1 − x y²)
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    *root = x * y;
+    return y;
+#else
+    const double r = sqrt(x);
+    *root = r;
+    return 1.0 / r;
+#endif
+}
+
 MM_HD void dev6(const double* a, double* d) {
-    const double m = tr6(a) / 3.0;
+    const double m = tr6(a) * (1.0 / 3.0);
     d[0] = a[0] - m; d[1] = a[1]; d[2] = a[2]; d[3] = a[3] - m; d[4] = a[4]; d[5] = a[5] - m;
 }
 MM_HD bool is_diag_slot(int c) { return c == 0 || c == 3 || c == 5; }
@@ -90,6 +131,7 @@ template <class Acc> MM_HD void linear_elastic_point(const ElasticK& k, Acc& acc
 struct PlasticK {
     double lam, G;                  // Lamé constants of Eᵉ
     double sigma_y, H_kappa, H_alpha, kappa_inf, c2;   // c2 = 3/(2 α_∞)
+    double ikinf, hk_ikinf;         // 1/κ_∞, H_κ/κ_∞
     double tol; int max_iter;
 };
 MM_HD PlasticK make_plastic_k(double E, double nu, double sigma_y, double H, double r, double kappa_inf, double alpha_inf, double tol, int max_iter) {
@@ -100,6 +142,8 @@ MM_HD PlasticK make_plastic_k(double E, double nu, double sigma_y, double H, dou
     k.H_kappa = -r * H;                     // Plastic.jl:31
     k.H_alpha = -2.0 / 3.0 * (1 - r) * H;   // Plastic.jl:32
     k.kappa_inf = kappa_inf;
+    k.ikinf = 1.0 / kappa_inf;
+    k.hk_ikinf = k.H_kappa / kappa_inf;
     k.c2 = 3.0 / (2 * alpha_inf);
     k.tol = tol; k.max_iter = max_iter;
     return k;
@@ -134,7 +178,8 @@ template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* i
 #pragma unroll
     for (int c = 0; c < 6; ++c) d6[c] = st[c] - al_n[c];
     dev6(d6, s);
-    double rho = sqrt(ddot6(s, s));
+    double rho, inv_rho;
+    inv_rho = fast_rsqrt(ddot6(s, s), &rho);
     const double Phi = c1 * rho - k.sigma_y - kap_n;                                   // Plastic.jl:132
     // result registers, pre-set to the elastic answer (σ_trial, Eᵉ, state unchanged)     Plastic.jl:134-135
     double sg[6], al[6], n[6], u[6], kap = kap_n, mu = mu_n, gxi = 0.0;
@@ -144,18 +189,19 @@ template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* i
     if (Phi > 0.0) {
         // ---- Newton on x = (σ, κ, α, μ), x0 = (σ_trial, κₙ, αₙ, μₙ)                   Plastic.jl:142-148
         flag = 1;
-        double w[6], inv_rho, i1psi, theta, eta, ikk, gk, n_gt;
+        double w[6], i1psi, theta, i1eta, iden, ikk, gk;
         for (;;) {
             // residuals at x                                                           Plastic.jl:162-172
+            if (iters > 0) {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) d6[c] = sg[c] - al[c];
-            dev6(d6, s);
-            rho = sqrt(ddot6(s, s));
-            inv_rho = 1.0 / rho;
+                for (int c = 0; c < 6; ++c) d6[c] = sg[c] - al[c];
+                dev6(d6, s);
+                inv_rho = fast_rsqrt(ddot6(s, s), &rho);
+            }
 #pragma unroll
             for (int c = 0; c < 6; ++c) n[c] = s[c] * inv_rho;
             dev6(al, w);
-            const double kr = -1.0 + kap / k.kappa_inf;
+            const double kr = kap * k.ikinf - 1.0;
             double Rs[6], Ra[6];
             const double gm = G2 * mu * c1, hm = mu * k.H_alpha;
 #pragma unroll
@@ -166,32 +212,38 @@ template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* i
             const double Rk = (kap - kap_n) - mu * k.H_kappa * kr;
             const double Rm = c1 * rho - k.sigma_y - kap;
             // NLsolve convergence test: max|F| <= ftol on the MANDEL vector (shear entries carry sqrt(2))
-            double fmaxabs = fmax(fabs(Rk), fabs(Rm));
+            bool conv = (fabs(Rk) <= k.tol) & (fabs(Rm) <= k.tol);
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
-                const double f = is_diag_slot(c) ? 1.0 : r2;
-                fmaxabs = fmax(fmaxabs, fmax(fabs(Rs[c] * f), fabs(Ra[c] * f)));
+                const double t = is_diag_slot(c) ? k.tol : k.tol * (1.0 / r2);
+                conv = conv & (fabs(Rs[c]) <= t) & (fabs(Ra[c]) <= t);
             }
-            // quantities shared by the step and by the tangent
+            // quantities shared by the step and by the tangent (two reciprocals serve four quotients)
             const double beta = c1 * inv_rho;
-            const double psi = hm * k.c2;
-            i1psi = 1.0 / (1.0 - psi);
-            theta = gm * inv_rho;                       // 2G μ β
+            const double a1 = 1.0 - hm * k.c2;                 // 1 − ψ
+            const double a2 = 1.0 - mu * k.hk_ikinf;           // k_κ
+            const double ia = fast_rcp(a1 * a2);
+            i1psi = a2 * ia;
+            ikk = a1 * ia;
+            theta = gm * inv_rho;                              // 2G μ β
             const double phi = hm * beta;
-            eta = theta - phi * i1psi;
+            const double eta1 = 1.0 + (theta - phi * i1psi);   // 1 + η
             gk = -k.H_kappa * kr;
-            ikk = 1.0 / (1.0 - mu * k.H_kappa / k.kappa_inf);
             double gt[6], ha[6];
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
                 ha[c] = k.H_alpha * (c1 * n[c] - k.c2 * w[c]);
                 gt[c] = G2 * c1 * n[c] - ha[c] * i1psi;
             }
-            n_gt = ddot6(n, gt);
-            if (fmaxabs <= k.tol) break;                                  // f_converged
-            if (!(fmaxabs == fmaxabs) || iters >= k.max_iter) { flag |= 0x80; break; }
+            const double n_gt = ddot6(n, gt);
+            const double den = c1 * n_gt - gk * ikk;
+            const double ib = fast_rcp(den * eta1);
+            i1eta = den * ib;
+            iden = eta1 * ib;
+            if (conv) break;                                              // f_converged
+            if (iters >= k.max_iter) { flag |= 0x80; break; }
             // ---- closed-form Newton step
-            const double trRs = tr6(Rs) / 3.0, trRa = tr6(Ra) / 3.0;
+            const double trRs = tr6(Rs) * (1.0 / 3.0), trRa = tr6(Ra) * (1.0 / 3.0);
             double rt[6], ra[6];
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
@@ -200,10 +252,9 @@ template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* i
                 rt[c] = -(Rs[c] - trRs * dl) + ra[c] * i1psi;
             }
             const double n_rt = ddot6(n, rt);
-            const double dmu = (c1 * n_rt + Rm + Rk * ikk) / (c1 * n_gt - gk * ikk);
+            const double dmu = (c1 * n_rt + Rm + Rk * ikk) * iden;
             const double dkap = (-Rk - gk * dmu) * ikk;
             const double ny = n_rt - n_gt * dmu;
-            const double i1eta = 1.0 / (1.0 + eta);
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
                 const double dl = is_diag_slot(c) ? 1.0 : 0.0;
@@ -220,9 +271,9 @@ template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* i
 #pragma unroll
         for (int c = 0; c < 6; ++c) ep[c] += mnu * n[c];
         // ∂σ∂ε = (J⁻¹)_σσ ⊡ Eᵉ = Eᵉ − 2Gξ I_dev + u ⊗ n                                  Plastic.jl:152-154
-        const double xi = theta / (1.0 + eta);
+        const double xi = theta * i1eta;
         const double omega = k.H_alpha * k.c2 * i1psi;
-        const double cD = c1 / (c1 * n_gt - gk * ikk);
+        const double cD = c1 * iden;
         const double nw = ddot6(n, w);
 #pragma unroll
         for (int c = 0; c < 6; ++c) u[c] = G2 * (xi * n[c] + cD * (xi * omega * (w[c] - nw * n[c]) - G2 * c1 * n[c]));

@@ -32,6 +32,11 @@ struct PlasticOp {
     }
 };
 
+#ifndef MM_PLASTIC_MINBLOCKS
+#define MM_PLASTIC_MINBLOCKS 3
+#endif
+template <> struct MinBlocks<PlasticOp> { static constexpr int value = MM_PLASTIC_MINBLOCKS; };   // 128 threads x 3 blocks/SM -> <= 168 regs: measured best of {1,3,4,5} (tools/sweep_plastic.sh)
+
 template <int MODEL, int KIND> struct HyperOp {
     static constexpr int NIN = 1, NOUT = 2;
     __host__ __device__ static constexpr int in_nc(int) { return KIND == 1 ? 9 : 6; }
