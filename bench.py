@@ -268,10 +268,11 @@ def main():
         "config": {"workload": "Plastic J2 (E=200e3, nu=0.3, sigma_y=200, H=50, r=0.5, kappa_inf=alpha_inf=13), %d points/GPU, step B from a non-virgin state (BASELINE.json configs[1])" % N,
                    "points_per_gpu": N, "layout": "soa", "plastic_fraction": frac, "n_not_converged": n_fail,
                    "l2": "inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (160 * N / 1e9), "parallelism": "contiguous point shards, no data-path collective"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ((traffic or {}).get("dram_bytes_per_point") or 0) * N or None,
                      "kernel": "mm::soa_kernel<mm::PlasticOp,128>", "bytes_per_point": BYTES_PER_POINT, "points_per_launch": N, "kernel_ms_mean": mean_kernel_ms,
                      "kernel_ms_min": kern_ms[0], "kernel_ms_max": kern_ms[-1], "peak_source": peak_src,
-                     "traffic_source": (traffic or {}).get("source")},
+                     "traffic_source": ("ncu --set full dram__bytes_read+write = %.1f B/point on a %.0e-point capture (%s), scaled to this launch's point count"
+                                        % (traffic["dram_bytes_per_point"], traffic["points_in_capture"], traffic["source"])) if traffic else None},
         "clocks": clocks, "gpu_launches": args.steps,
     }
     if e2e:
