@@ -1,0 +1,118 @@
+# MaterialModelsB200.jl — the binding a MaterialModels.jl maintainer would add: batched methods of the
+# EXISTING generics (`material_response`, `initial_material_state`, `get_cache`) that `ccall` libmmb200.so.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build container has no Julia. It is kept literal and thin so that
+# it can be checked by reading against include/mmb200.h.  Arrays are CUDA.jl `CuArray`s (device pointers) or
+# plain `Array`s (host pointers -> the pipelined mmh_* entry points).  AoS layout is what
+# `reinterpret(Float64, ::Vector{SymmetricTensor{2,3,Float64,6}})` gives, so existing assembler arrays pass
+# through unchanged; SoA (`(nc, N)` stored component-major, i.e. an `N x nc` Julia matrix) is the fast path.
+module MaterialModelsB200
+
+using MaterialModels, Tensors, CUDA
+import MaterialModels: material_response, initial_material_state, get_cache
+
+const libmmb200 = get(ENV, "LIBMMB200", "libmmb200.so")
+const MM_LAYOUT_SOA, MM_LAYOUT_AOS = Cint(0), Cint(1)
+
+struct MMPlastic;  E::Cdouble; nu::Cdouble; sigma_y::Cdouble; H::Cdouble; r::Cdouble; kappa_inf::Cdouble; alpha_inf::Cdouble; end
+struct MMLinearElastic; E::Cdouble; nu::Cdouble; end
+struct MMHyper; lambda::Cdouble; mu::Cdouble; c2::Cdouble; c3::Cdouble; end
+struct MMXuNeedleman; Phi_n::Cdouble; Phi_t::Cdouble; delta_n::Cdouble; delta_t::Cdouble; Delta_n_star::Cdouble; end
+struct MMNewtonOpts; tol::Cdouble; max_iter::Int32; pad::Int32; end
+MMPlastic(m::Plastic) = MMPlastic(m.E, m.ν, m.σ_y, m.H, m.r, m.κ_∞, m.α_∞)
+
+check(rc, what) = rc == 0 || error("$what failed: " * unsafe_string(ccall((:mm_last_error, libmmb200), Cstring, ())))
+
+# batched state: N points of PlasticState, AoS = Vector{PlasticState{3,Float64,6}} uploaded as-is (14 doubles/point)
+struct BatchedPlasticState{A<:AbstractMatrix{Float64}} <: AbstractMaterialState
+    data::A          # AoS: 14 x N (column = one PlasticState);  SoA: N x 14
+    layout::Cint
+end
+initial_material_state(m::Plastic, N::Integer; layout = MM_LAYOUT_AOS) =
+    BatchedPlasticState(layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, 14, N) : CUDA.zeros(Float64, N, 14), layout)
+get_cache(::Plastic, ::Val{:gpu}) = nothing      # the GPU path keeps the local solve in registers
+
+"""
+    material_response(m::Plastic, ε::CuMatrix{Float64}, state::BatchedPlasticState, Δt=nothing; cache, options)
+
+N points at once; same return convention as `src/Plastic.jl:126-160`: `(σ, ∂σ∂ε, new_state)`.
+Raises the reference's error if any local Newton solve did not converge.
+"""
+function material_response(m::Plastic, ε::CuMatrix{Float64}, state::BatchedPlasticState, Δt = nothing;
+                           cache = nothing, options::Dict{Symbol,Any} = Dict{Symbol,Any}())
+    aos = state.layout == MM_LAYOUT_AOS
+    N = aos ? size(ε, 2) : size(ε, 1)
+    σ   = similar(ε)
+    tan = aos ? CUDA.zeros(Float64, 36, N) : CUDA.zeros(Float64, N, 36)
+    new = similar(state.data)
+    flags = CUDA.zeros(UInt8, N); iters = CUDA.zeros(UInt8, N); nfail = CUDA.zeros(Int32, 1)
+    p = get(options, :nlsolve_params, Dict{Symbol,Any}())
+    opts = Ref(MMNewtonOpts(get(p, :ftol, 1e-8), get(p, :iterations, 1000), 0))
+    rc = ccall((:mm_plastic, libmmb200), Cint,
+               (Ref{MMPlastic}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble},
+                CuPtr{UInt8}, CuPtr{UInt8}, CuPtr{Int32}, Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
+               Ref(MMPlastic(m)), ε, state.data, σ, tan, new, flags, iters, nfail, opts, N, state.layout,
+               CUDA.stream().handle)
+    check(rc, "mm_plastic")
+    Array(nfail)[1] == 0 || error("Material model not converged. Could not find material state.")   # Plastic.jl:157
+    return σ, tan, BatchedPlasticState(new, state.layout)
+end
+
+# host arrays (e.g. reinterpret(Float64, ::Vector{SymmetricTensor{2,3,Float64,6}}) reshaped to 6 x N): pipelined mmh_* path
+function material_response(m::Plastic, ε::Matrix{Float64}, state::Matrix{Float64}, Δt = nothing; layout = MM_LAYOUT_AOS, kwargs...)
+    N = layout == MM_LAYOUT_AOS ? size(ε, 2) : size(ε, 1)
+    σ = similar(ε); tan = layout == MM_LAYOUT_AOS ? zeros(36, N) : zeros(N, 36); new = similar(state)
+    flags = zeros(UInt8, N); iters = zeros(UInt8, N); nfail = Ref{Int32}(0)
+    rc = ccall((:mmh_plastic, libmmb200), Cint,
+               (Ref{MMPlastic}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{UInt8}, Ptr{UInt8},
+                Ref{Int32}, Ptr{Cvoid}, Int64, Cint),
+               Ref(MMPlastic(m)), ε, state, σ, tan, new, flags, iters, nfail, C_NULL, N, layout)
+    check(rc, "mmh_plastic")
+    nfail[] == 0 || error("Material model not converged. Could not find material state.")
+    return σ, tan, new
+end
+
+# LinearElastic (src/LinearElastic.jl:57-60): the tangent is the one shared m.Eᵉ, exactly as the reference returns it
+function material_response(m::LinearElastic, ε::CuMatrix{Float64}, state = initial_material_state(m), Δt = nothing;
+                           layout = MM_LAYOUT_AOS, cache = nothing, options = nothing)
+    N = layout == MM_LAYOUT_AOS ? size(ε, 2) : size(ε, 1)
+    σ = similar(ε)
+    check(ccall((:mm_linear_elastic, libmmb200), Cint,
+                (Ref{MMLinearElastic}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, Int64, Cint, Ptr{Cvoid}),
+                Ref(MMLinearElastic(m.E, m.ν)), ε, σ, CU_NULL, N, layout, CUDA.stream().handle), "mm_linear_elastic")
+    return σ, m.Eᵉ, state
+end
+
+# NeoHook / Yeoh / StVenant through the trait route (src/traits.jl:91-107): F (9 x N) -> S (6 x N), ∂S∂C (36 x N)
+_model(::NeoHook) = Cint(0); _model(::Yeoh) = Cint(1); _model(::StVenant) = Cint(2)
+_hyper(m::NeoHook) = MMHyper(m.λ, m.μ, 0.0, 0.0); _hyper(m::StVenant) = MMHyper(m.λ, m.μ, 0.0, 0.0)
+_hyper(m::Yeoh) = MMHyper(m.λ, m.μ, m.c₂, m.c₃)
+function material_response(::MaterialModels.∂S∂C, m::Union{NeoHook,Yeoh,StVenant}, F::DeformationGradient{<:CuMatrix{Float64}},
+                           state, Δt::Float64 = 0.0; layout = MM_LAYOUT_AOS, cache = nothing, options = nothing)
+    N = layout == MM_LAYOUT_AOS ? size(F.value, 2) : size(F.value, 1)
+    S = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, 6, N) : CUDA.zeros(Float64, N, 6)
+    T = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, 36, N) : CUDA.zeros(Float64, N, 36)
+    check(ccall((:mm_hyper, libmmb200), Cint,
+                (Cint, Ref{MMHyper}, CuPtr{Cdouble}, Cint, CuPtr{Cdouble}, CuPtr{Cdouble}, Int64, Cint, Ptr{Cvoid}),
+                _model(m), Ref(_hyper(m)), F.value, Cint(1), S, T, N, layout, CUDA.stream().handle), "mm_hyper")
+    return S, T, state
+end
+
+# XuNeedleman (XuNeedleman.jl:75-91): Δ (dim x N), cache/options positional as in the reference
+function material_response(m::XuNeedleman, Δ::CuMatrix{Float64}, state = XuNeedlemanState(), Δt = nothing, cache = nothing, options = nothing;
+                           layout = MM_LAYOUT_AOS)
+    dim = layout == MM_LAYOUT_AOS ? size(Δ, 1) : size(Δ, 2)
+    N = layout == MM_LAYOUT_AOS ? size(Δ, 2) : size(Δ, 1)
+    T = similar(Δ)
+    dTdΔ = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, dim * dim, N) : CUDA.zeros(Float64, N, dim * dim)
+    check(ccall((:mm_xu_needleman, libmmb200), Cint,
+                (Ref{MMXuNeedleman}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, Cint, Int64, Cint, Ptr{Cvoid}),
+                Ref(MMXuNeedleman(m.Φₙ, m.Φₜ, m.δₙ, m.δₜ, m.Δₙˢ)), Δ, T, dTdΔ, dim, N, layout, CUDA.stream().handle), "mm_xu_needleman")
+    return T, dTdΔ, state
+end
+
+# CrystalViscoPlastic{12} (CrystalViscoPlastic.jl:64-94): the MMCrystal struct (scalars, nslip, MS[12][9], H[12][12]) is
+# filled from `m.MS` and `m.H` directly (same memory order: MS[i] column-major Tensor{2,3}; H[i][j] = m.H[i,j]).
+# mm_crystal(p, Δε, Δt, state_in, σ, tan, state_out, active, iters, n_fail, opts, N, layout, stream) — see INTEGRATION.md.
+
+end # module
