@@ -25,6 +25,12 @@ struct CrystalK {
     double EM[12][6];                 // Eᵉ:MS_i, symmetric storage
     double Gm[12][12];                // Gm[i][j] = (Eᵉ:MS_j):MS_i
     double H[12][12];                 // H[j][i] = Julia H[j+1,i+1]
+    // structured fast path (crystal_point_fast): H = a_h I + b_h 11ᵀ as the reference constructor builds it (:41)
+    double a_h, b_h;
+    double Cmp[6][6];                 // (Eᵉ)⁻¹ as a 6x6 on storage components (raw inverse of Ee[I][J])
+    double isc, dtm_sc, hk_ai;        // 1/σ_c, Δt m/σ_c, H_kin/α_∞
+    int h_struct;                     // 1 if H has the form above (else only the general path applies)
+    int m_int;                        // m if it is an integer in [2,64] (x^(m-1) by multiplications), else 0 (pow)
 };
 
 // host-side table build (once per material)
@@ -51,6 +57,22 @@ inline void make_crystal_k(CrystalK& k, double E, double nu, double tau_y, doubl
             k.Gm[i][j] = g;
             k.H[i][j] = H[i][j];
         }
+    const double hd = H[0][0], ho = H[0][1];
+    k.h_struct = 1;
+    for (int i = 0; i < 12; ++i)
+        for (int j = 0; j < 12; ++j)
+            if (H[i][j] != ((i == j) ? hd : ho)) k.h_struct = 0;
+    k.b_h = ho; k.a_h = hd - ho;
+    {   // inverse of the raw 6x6 [λ 11ᵀ + 2G I on the normal block, G on the shear diagonal]
+        const double i2G = 1.0 / (2.0 * k.G), f = k.lam / (3.0 * k.lam + 2.0 * k.G);
+        for (int a = 0; a < 6; ++a)
+            for (int b = 0; b < 6; ++b) {
+                const bool da = (a == 0 || a == 3 || a == 5), db = (b == 0 || b == 3 || b == 5);
+                k.Cmp[a][b] = (da && db) ? i2G * ((a == b ? 1.0 : 0.0) - f) : ((a == b) ? 1.0 / k.G : 0.0);
+            }
+    }
+    k.isc = 1.0 / sigma_c; k.dtm_sc = dt * m / sigma_c; k.hk_ai = H_kin / alpha_inf;
+    k.m_int = (m >= 2.0 && m <= 64.0 && m == (double)(int)m) ? (int)m : 0;
 }
 
 // LU with partial pivoting on a 12x12 row-major matrix held in (thread-)local memory
@@ -185,6 +207,285 @@ template <class Acc> MM_HD unsigned crystal_point(const CrystalK& k, Acc& acc, i
 #pragma unroll
         for (int c = 0; c < 36; ++c) acc.template out<1>(c, tan[c]);
     }
+    *iters_out = iters;
+    return mask;
+}
+
+// =================================================================================================
+// Register-resident fast path.  Same Newton iterates as crystal_point (and as the reference), but the
+// step J δ = r is solved through the structure of J instead of a 12x12 LU:
+//     J = D − p̂ 1ᵀ − A Bᵀ ,   D_ii = −(t* + p_i (sgn_i α'_i + a_h)),  p̂ = b_h p   (cross hardening, rank 1)
+//     A_i: = c_i Pw[i][:]  (c_i = p_i sgn_i),   B_j: = s_j EM[j][:] = s_j Eᵉ Pw[j][:]   (elastic coupling, rank 6)
+// Woodbury:  (D − A Bᵀ)⁻¹ v = D⁻¹v + D⁻¹A K⁻¹ Bᵀ D⁻¹ v,  K = I₆ − Bᵀ D⁻¹ A = I₆ + Eᵉ S,  S = Σ_i w_i Pw_i Pw_iᵀ,
+//            w_i = −s_i c_i / D_ii  (≥ 0 while the reduced stress keeps the sign of its trial value).
+// K itself is non-symmetric (unpivoted LU of it loses 4-5 digits on the reference's non-traceless BCC systems —
+// measured); multiplying K z = Bᵀ D⁻¹ v by the compliance (Eᵉ)⁻¹ gives the SYMMETRIC POSITIVE DEFINITE system
+//            ((Eᵉ)⁻¹ + S) z = Σ_i s_i (D⁻¹v)_i Pw_i
+// which an unpivoted LDLᵀ solves stably; a non-positive pivot (possible only when some w_i < 0) or a D_ii too close
+// to zero sets *fallback and the caller re-runs the point through the general pivoted path.
+// Sherman–Morrison adds the rank-1 cross-hardening term.  The only matrix is the 6x6 symmetric M (21 doubles) — it and
+// the iterate live in registers with static indexing; the per-system vectors (κₙ, αₙ, c, D⁻¹r, 1/D) sit in the
+// thread's shared-memory scratch column.  Requires k.h_struct.
+// Scratch slots: [0,12) κₙ  [12,24) αₙ  [24,36) c  [36,48) D⁻¹r  [48,60) 1/D
+// =================================================================================================
+#define MM_CRYSTAL_SCRATCH 60
+
+MM_HD double powi_(double b, int n) {      // b^n, n >= 0, by squaring (n is warp-uniform)
+    double r = 1.0;
+    while (n) { if (n & 1) r *= b; b *= b; n >>= 1; }
+    return r;
+}
+
+// in-place LDLᵀ of a symmetric 6x6 (lower triangle of a row-major array in registers), no pivoting.
+// On exit: strict lower triangle = L, diagonal = 1/d_k.  false if a pivot is not safely positive.
+MM_HD bool ldl6_factor(double* M) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double d = M[k * 6 + k];
+        ok = ok & (d > 1e-200) & (d < 1e200);
+        const double id = fast_rcp(d);
+        M[k * 6 + k] = id;
+        double col[6];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) col[i] = M[i * 6 + k];          // unscaled column k
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            const double l = col[i] * id;
+            M[i * 6 + k] = l;
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j) M[i * 6 + j] -= l * col[j];
+        }
+    }
+    return ok;
+}
+MM_HD void ldl6_solve(const double* M, double* b) {
+#pragma unroll
+    for (int i = 1; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) b[i] -= M[i * 6 + j] * b[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) b[i] *= M[i * 6 + i];
+#pragma unroll
+    for (int i = 4; i >= 0; --i)
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) b[i] -= M[j * 6 + i] * b[j];
+}
+
+template <bool HASQ, class Acc, class Scr>
+MM_HD unsigned crystal_point_fast(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
+    const double G2 = 2.0 * k.G;
+    double st[6];
+    {   // σ_trial = σₙ + Eᵉ ⊡ Δε                                                           :119
+        double e[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c);
+        const double ltr = k.lam * tr6(e);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) st[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c]));
+    }
+    double x[12];
+    unsigned spos = 0, sneg = 0;       // frozen trial signs s_i (:120-121)
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const double kn = acc.template in<1>(6 + i), an = acc.template in<1>(18 + i);
+        x[i] = acc.template in<1>(30 + i);
+        scr(i) = kn; scr(12 + i) = an;
+        double tau = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) tau += st[c] * k.Pw[i][c];
+        const double d = tau - an;
+        if (d > 0.0) spos |= (1u << i);
+        if (d < 0.0) sneg |= (1u << i);
+    }
+#define MM_S(i) (((spos >> (i)) & 1u) ? 1.0 : (((sneg >> (i)) & 1u) ? -1.0 : 0.0))
+    double K[36], sig[6], z[6], yr[6], yp[6];
+    unsigned mask = 0;
+    int iters = 0;
+    bool converged = false, bad = false;
+    for (int it = 1;; ++it) {
+        double sumx = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sig[c] = st[c];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const double f = x[j] * MM_S(j);
+            if (HASQ) sumx += x[j];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) sig[c] -= f * k.EM[j][c];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) K[a * 6 + b] = k.Cmp[a][b];          // M = (Eᵉ)⁻¹ + S, lower triangle
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { yr[c] = 0.0; yp[c] = 0.0; }
+        double nrm2 = 0.0;
+        mask = 0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const double si = MM_S(i);
+            double kap = scr(i) + k.a_h * x[i];
+            if (HASQ) kap += k.b_h * sumx;
+            const double iden = fast_rcp(1.0 + k.hk_ai * x[i]);
+            const double al = (scr(12 + i) + k.H_kin * x[i] * si) * iden;
+            double tau = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) tau += sig[c] * k.Pw[i][c];
+            const double red = tau - al;
+            const double sgn = (red > 0.0) ? 1.0 : ((red < 0.0) ? -1.0 : 0.0);
+            const double Phi = fabs(red) - k.tau_y - kap;                                  // :110
+            double Ri = -k.t_star * x[i], p = 0.0;
+            if (Phi > 0.0) {
+                const double xx = Phi * k.isc;
+                const double pw1 = k.m_int ? powi_(xx, k.m_int - 1) : pow(xx, k.m - 1.0);
+                Ri = k.dt * (pw1 * xx) - k.t_star * x[i];                                   // :111
+                p = k.dtm_sc * pw1;
+                mask |= (1u << i);
+            }
+            nrm2 += Ri * Ri;
+            const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
+            // D_ii = −dD.  The Woodbury split needs D safely invertible: dD >= t*/4 (it is >= t* unless an ACTIVE system's
+            // reduced stress has flipped sign against its trial value while a_h < H_kin); otherwise -> pivoted general path.
+            const double dD = k.t_star + p * (sgn * dal + k.a_h);
+            bad = bad | !(dD >= 0.25 * k.t_star);
+            const double invD = -fast_rcp(dD);
+            const double ci = p * sgn;
+            const double rD = Ri * invD;
+            scr(24 + i) = ci; scr(36 + i) = rD; scr(48 + i) = invD;
+            if (p != 0.0) {                      // inactive systems contribute nothing to S
+                const double w = -si * ci * invD;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    const double wa = w * k.Pw[i][a];
+#pragma unroll
+                    for (int b = 0; b <= a; ++b) K[a * 6 + b] += wa * k.Pw[i][b];
+                }
+            }
+            const double srD = si * rD;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) yr[c] += srD * k.Pw[i][c];
+            if (HASQ) {
+                const double spD = si * (k.b_h * p * invD);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) yp[c] += spD * k.Pw[i][c];
+            }
+        }
+        iters = it - 1;
+        if (it > k.max_iter) break;                                                      // nonlinear_solver.jl:61
+        if (sqrt(nrm2) < k.tol) { converged = true; break; }                             // nonlinear_solver.jl:56
+        if (bad) break;
+        if (!ldl6_factor(K)) { bad = true; break; }
+        ldl6_solve(K, yr);
+        double su = 0.0, sv = 0.0;
+        if (HASQ) {
+            ldl6_solve(K, yp);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const double ci = scr(24 + i), invD = scr(48 + i);
+                double du = 0.0, dv = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; dv += k.Pw[i][c] * yp[c]; }
+                su += scr(36 + i) + invD * ci * du;
+                sv += k.b_h * fabs(ci) * invD + invD * ci * dv;
+            }
+        }
+        const double fac = HASQ ? su * fast_rcp(1.0 - sv) : 0.0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const double ci = scr(24 + i), invD = scr(48 + i);
+            double du = 0.0, dv = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; if (HASQ) dv += k.Pw[i][c] * yp[c]; }
+            double d = scr(36 + i) + invD * ci * du;
+            if (HASQ) d += (k.b_h * fabs(ci) * invD + invD * ci * dv) * fac;
+            x[i] -= d;                                                                   // nonlinear_solver.jl:59
+        }
+        iters = it;
+    }
+    if (bad) { *fallback = true; *iters_out = 0; return 0; }       // (also when the guard trips on the converged pass: the tangent needs D⁻¹)
+    if (!converged) mask |= 0x8000u;
+    // outputs                                                                            :77, :90
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { acc.template out<0>(c, sig[c]); acc.template out<2>(c, sig[c]); }
+    {
+        double sumx = 0.0;
+        if (HASQ) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) sumx += x[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            double kap = scr(i) + k.a_h * x[i];
+            if (HASQ) kap += k.b_h * sumx;
+            const double al = (scr(12 + i) + k.H_kin * x[i] * MM_S(i)) * fast_rcp(1.0 + k.hk_ai * x[i]);
+            acc.template out<2>(6 + i, kap); acc.template out<2>(18 + i, al); acc.template out<2>(30 + i, x[i]);
+        }
+    }
+    if (acc.template has_out<1>()) {
+        const bool want = ((mask & 0x0FFFu) != 0) && converged;
+        bool okf = true;
+        double vq[12], svq = 0.0;       // HASQ only: v = (D − ABᵀ)⁻¹ p̂
+        if (want) {
+            okf = ldl6_factor(K);
+            if (HASQ) {
+                ldl6_solve(K, yp);
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    const double ci = scr(24 + i), invD = scr(48 + i);
+                    double dv = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) dv += k.Pw[i][c] * yp[c];
+                    vq[i] = k.b_h * fabs(ci) * invD + invD * ci * dv;
+                    svq += vq[i];
+                }
+            }
+        }
+        if (!okf) { *fallback = true; *iters_out = 0; return 0; }
+        const double ifq = HASQ ? fast_rcp(1.0 - svq) : 0.0;
+#pragma unroll 1
+        for (int Jc = 0; Jc < 6; ++Jc) {                                                 // :79-89, one tangent column at a time
+            double col[6];
+#pragma unroll
+            for (int Ic = 0; Ic < 6; ++Ic) col[Ic] = iso_entry(Ic, Jc, k.lam, k.G);
+            if (want) {
+                // right-hand side ∂R/∂ε column: c_j EM[j][Jc];  Z = J⁻¹ rhs
+#pragma unroll
+                for (int c = 0; c < 6; ++c) z[c] = 0.0;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    const double rD = scr(24 + j) * k.EM[j][Jc] * scr(48 + j);
+                    scr(36 + j) = rD;
+                    const double srD = MM_S(j) * rD;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) z[c] += srD * k.Pw[j][c];
+                }
+                ldl6_solve(K, z);
+                double sz = 0.0;
+                double Z[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    double du = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) du += k.Pw[i][c] * z[c];
+                    Z[i] = scr(36 + i) + scr(48 + i) * scr(24 + i) * du;
+                    sz += Z[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    double Zi = Z[i];
+                    if (HASQ) Zi += vq[i] * (sz * ifq);
+                    const double ci = scr(24 + i);
+                    const double sgnZ = (ci > 0.0) ? Zi : ((ci < 0.0) ? -Zi : 0.0);      // sgn_i Z_i (sgn_i = sign c_i on active systems)
+#pragma unroll
+                    for (int Ic = 0; Ic < 6; ++Ic) col[Ic] += k.EM[i][Ic] * sgnZ;
+                }
+            }
+#pragma unroll
+            for (int Ic = 0; Ic < 6; ++Ic) acc.template out<1>(Ic + 6 * Jc, col[Ic]);
+        }
+    }
+#undef MM_S
     *iters_out = iters;
     return mask;
 }

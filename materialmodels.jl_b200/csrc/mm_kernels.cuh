@@ -34,19 +34,29 @@ template <int NIN, int NOUT> struct SoaAcc {
 
 template <class Op> struct MinBlocks { static constexpr int value = 1; };   // per-Op occupancy target (register cap)
 
+// Per-thread scratch in shared memory, laid out [slot][thread] (thread-minor => bank-conflict free).
+// Ops declare how many doubles they need in Op::SCRATCH (0 for the streaming models).
+struct Scratch {
+    double* base;     // already offset by the thread index
+    int stride;       // threads per block
+    __device__ __forceinline__ double& operator()(int j) const { return base[j * stride]; }
+};
+
 template <class Op, int BS>
 __global__ void __launch_bounds__(BS, MinBlocks<Op>::value) soa_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N) {
+    extern __shared__ double sm_scratch[];
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     if (i >= N) return;
     SoaAcc<Op::NIN, Op::NOUT> acc(p, N, i);
-    op.point(acc, i);
+    Scratch scr{sm_scratch + threadIdx.x, BS};
+    op.point(acc, i, scr);
 }
 
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int pad_odd(int nc) { return nc | 1; }
 template <class Op> __host__ __device__ constexpr int aos_in_off(int a) { return a == 0 ? 0 : aos_in_off<Op>(a - 1) + pad_odd(Op::in_nc(a - 1)); }
 template <class Op> __host__ __device__ constexpr int aos_out_off(int a) { return a == 0 ? aos_in_off<Op>(Op::NIN) : aos_out_off<Op>(a - 1) + pad_odd(Op::out_nc(a - 1)); }
-template <class Op> __host__ __device__ constexpr int aos_doubles_per_point() { return aos_out_off<Op>(Op::NOUT); }
+template <class Op> __host__ __device__ constexpr int aos_doubles_per_point() { return aos_out_off<Op>(Op::NOUT) + Op::SCRATCH; }
 
 template <class Op, int BS> struct AosAcc {
     double* sm;
@@ -95,7 +105,8 @@ __global__ void __launch_bounds__(BS) aos_kernel(const Op op, const Ptrs<Op::NIN
         __syncthreads();
         if ((int)threadIdx.x < npts) {
             AosAcc<Op, BS> acc(sm, p, (int)threadIdx.x);
-            op.point(acc, i0 + threadIdx.x);
+            Scratch scr{sm + aos_out_off<Op>(Op::NOUT) * BS + threadIdx.x, BS};
+            op.point(acc, i0 + threadIdx.x, scr);
         }
         __syncthreads();
         TileIO<Op, BS, 0>::store_all(sm, p, i0, npts);
@@ -114,7 +125,14 @@ int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int
     if (layout == 0) {
         const int64_t blocks = (N + BS - 1) / BS;
         if (blocks > 2147483647LL) return set_error(-1, "%s: N too large for one launch", what);
-        soa_kernel<Op, BS><<<(unsigned)blocks, BS, 0, stream>>>(op, p, N);
+        constexpr size_t scratch = (size_t)Op::SCRATCH * BS * sizeof(double);
+        static bool soa_configured = false;
+        if (!soa_configured && scratch > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(soa_kernel<Op, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch);
+            if (e != cudaSuccess) return set_error(-2, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+            soa_configured = true;
+        }
+        soa_kernel<Op, BS><<<(unsigned)blocks, BS, scratch, stream>>>(op, p, N);
     } else if (layout == 1) {
         constexpr size_t smem = (size_t)aos_doubles_per_point<Op>() * BS * sizeof(double);
         static bool configured = false;

@@ -8,22 +8,22 @@ namespace mm {
 
 // ---- Ops ----------------------------------------------------------------------------------------
 struct ElasticOp {
-    static constexpr int NIN = 1, NOUT = 2;
+    static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int) { return 6; }
     __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : 36; }
     ElasticK k;
-    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t) const { linear_elastic_point(k, acc); }
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { linear_elastic_point(k, acc); }
 };
 
 struct PlasticOp {
-    static constexpr int NIN = 2, NOUT = 3;
+    static constexpr int NIN = 2, NOUT = 3, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? 6 : 14; }
     __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : (a == 1 ? 36 : 14); }
     PlasticK k;
     uint8_t* flags;
     uint8_t* iters;
     int32_t* n_fail;
-    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i) const {
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
         int it = 0;
         const int flag = plastic_point(k, acc, &it);
         if (flags) flags[i] = (uint8_t)flag;
@@ -38,19 +38,19 @@ struct PlasticOp {
 template <> struct MinBlocks<PlasticOp> { static constexpr int value = MM_PLASTIC_MINBLOCKS; };   // 128 threads x 3 blocks/SM -> <= 168 regs: measured best of {1,3,4,5} (tools/sweep_plastic.sh)
 
 template <int MODEL, int KIND> struct HyperOp {
-    static constexpr int NIN = 1, NOUT = 2;
+    static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int) { return KIND == 1 ? 9 : 6; }
     __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : 36; }
     HyperK k;
-    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t) const { hyper_point<MODEL, KIND>(k, acc); }
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { hyper_point<MODEL, KIND>(k, acc); }
 };
 
 template <int DIM> struct XuOp {
-    static constexpr int NIN = 1, NOUT = 2;
+    static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int) { return DIM; }
     __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? DIM : DIM * DIM; }
     XuK k;
-    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t) const { xu_point<DIM>(k, acc); }
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { xu_point<DIM>(k, acc); }
 };
 
 // ---- synthetic inputs ---------------------------------------------------------------------------

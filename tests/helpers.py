@@ -100,3 +100,40 @@ def hosttwin():
 
 def P(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+CHAOTIC_ITERS = 40
+# The reference's BCC table pairs plane (-1,0,-1) with two directions that do not lie in it (slipsystems.jl:25,31);
+# those two 'systems' make some converged Jacobians ill-conditioned, and the tangent J⁻¹-solve of two correct FP64
+# implementations then differs by cond(J)·eps (observed up to 2e-11 with the pivoted LU on BOTH sides). FCC keeps 1e-12.
+BCC_TAN_TOL = 1e-9
+
+
+def crystal_compare(r, active, iters, sig, tan, state, nfail_gpu=None, tan_tol=RTOL):
+    """Compare a crystal-plasticity result (SoA numpy arrays) with the oracle's `r`.
+
+    The reference's Newton (`solve`, no line search) on the stiff (Φ/σ_c)^m law is chaotic for a small fraction of
+    inputs: trajectories of > CHAOTIC_ITERS iterations (or that never converge — the reference raises an error for
+    those) amplify rounding differences, so two correct FP64 implementations can disagree there on the iteration
+    count, on whether the solve converged at all, and — when they converge to different roots — on the values.
+    Everywhere else the bar is the north-star one: active masks and iteration counts EXACT, values within 1e-12.
+    Returns the number of chaotic points (reported by the callers)."""
+    import materialmodels_jl_b200._abi as abi
+
+    active = np.asarray(active).view(np.uint16)
+    failed_o = (r["active"] & abi.MM_ACTIVE_FAILED) != 0
+    chaotic = failed_o | (r["iters"] >= CHAOTIC_ITERS)
+    ok = ~chaotic
+    assert chaotic.mean() < 0.02, "too many chaotic points for this workload: %g" % chaotic.mean()
+    assert np.array_equal(active[ok], r["active"][ok]), "active-slip masks differ on regular points"
+    assert np.array_equal(np.asarray(iters)[ok], r["iters"][ok]), "Newton iteration counts differ on regular points"
+    assert rel_err(sig[:, ok], r["sig"][:, ok]).max() < RTOL
+    assert rel_err(tan[:, ok], r["tan"][:, ok]).max() < tan_tol
+    assert rel_err(state[:, ok], r["state"][:, ok]).max() < RTOL
+    # on chaotic points both sides must at least agree that the point is hard: GPU failures only occur there
+    failed_g = (active & abi.MM_ACTIVE_FAILED) != 0
+    assert not np.any(failed_g & ok), "GPU reports non-convergence on a regular point"
+    assert not np.any(active & 0x4000), "fix-up marker leaked into the output"
+    if nfail_gpu is not None:
+        assert nfail_gpu == int(failed_g.sum())
+    return int(chaotic.sum())

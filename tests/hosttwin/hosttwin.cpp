@@ -46,6 +46,28 @@ int twin_xu(const MMXuNeedleman* p, const double* jump, double* T, double* H, in
     for (int64_t i = 0; i < N; ++i) { HostAcc<1, 2> a{{jump}, {T, H}, N, i}; if (dim == 3) mm::xu_point<3>(k, a); else mm::xu_point<2>(k, a); }
     return 0;
 }
+struct HostScratch { double v[MM_CRYSTAL_SCRATCH]; double& operator()(int j) { return v[j]; } };
+
+// mode 0: general pivoted path; mode 1: structured fast path (falls back like the kernel does)
+int twin_crystal_mode(const MMCrystal* p, const double* deps, double dt, const double* sin, double* sig, double* tan, double* sout, uint16_t* active,
+                      uint8_t* iters, double tol, int max_iter, int64_t N, int mode, int64_t* n_fallback) {
+    mm::CrystalK k;
+    mm::make_crystal_k(k, p->E, p->nu, p->tau_y, p->H_kin, p->alpha_inf, p->t_star, p->sigma_c, p->m, p->MS, p->H, dt, tol, max_iter);
+    int64_t nfb = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<2, 3> a{{deps, sin}, {sig, tan, sout}, N, i};
+        int it = 0; unsigned m;
+        if (mode == 0 || !k.h_struct) m = mm::crystal_point(k, a, &it);
+        else {
+            HostScratch scr; bool fb = false;
+            m = (k.b_h != 0.0) ? mm::crystal_point_fast<true>(k, a, scr, &it, &fb) : mm::crystal_point_fast<false>(k, a, scr, &it, &fb);
+            if (fb) { ++nfb; m = mm::crystal_point(k, a, &it); }
+        }
+        active[i] = (uint16_t)m; iters[i] = (uint8_t)it;
+    }
+    if (n_fallback) *n_fallback = nfb;
+    return 0;
+}
 int twin_crystal(const MMCrystal* p, const double* deps, double dt, const double* sin, double* sig, double* tan, double* sout, uint16_t* active,
                  uint8_t* iters, double tol, int max_iter, int64_t N) {
     mm::CrystalK k;

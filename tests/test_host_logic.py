@@ -137,24 +137,28 @@ def test_twin_streaming_models_match_oracle(oracle):
 
 
 def test_twin_crystal_matches_oracle(oracle):
+    """Both crystal paths of the kernels (general pivoted 12x12; structured SPD/Woodbury with fix-up) on the host
+    against the oracle: FCC and the reference's BCC table, without and with cross hardening, three steps."""
     tw = H.hosttwin()
     N = 4000
-    for q, structure in ((0.0, 0), (0.4, 1)):
+    n_fallback_total = 0
+    for q, structure in ((0.0, 0), (0.4, 1), (0.3, 0), (0.0, 1)):
         cp = H.crystal_c(oracle, q=q, structure=structure)
         st = np.zeros((42, N))
-        for step in range(2):
+        for step in range(3):
             nc, lo, hi, seed = sy.c4_strain_increment(step)
             de = sy.host_uniform(N, nc, seed, lo, hi)
             r = oracle.crystal(cp, de, st)
-            sig, tan, so = np.zeros((6, N)), np.zeros((36, N)), np.zeros((42, N))
-            ac, it = np.zeros(N, np.uint16), np.zeros(N, np.uint8)
-            tw.twin_crystal(C.byref(cp), H.P(de), C.c_double(1.0), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(ac), H.P(it), C.c_double(1e-8), 100, C.c_int64(N))
-            # cross-hardening + the reference's BCC table make a few points exceed max_iter = 100: the reference
-            # would raise (CrystalViscoPlastic.jl:92); here they must be flagged identically by both sides
+            for mode in (0, 1):
+                sig, tan, so = np.zeros((6, N)), np.zeros((36, N)), np.zeros((42, N))
+                ac, it = np.zeros(N, np.uint16), np.zeros(N, np.uint8)
+                nfb = C.c_int64(0)
+                tw.twin_crystal_mode(C.byref(cp), H.P(de), C.c_double(1.0), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(ac), H.P(it),
+                                     C.c_double(1e-8), 100, C.c_int64(N), mode, C.byref(nfb))
+                H.crystal_compare(r, ac, it, sig, tan, so, tan_tol=H.BCC_TAN_TOL if structure == 1 else H.RTOL)
+                n_fallback_total += nfb.value
+                if q == 0.0 and structure == 0 and step < 2:
+                    assert nfb.value == 0          # the benchmark configuration never needs the fix-up pass
             ok = (r["active"] & abi.MM_ACTIVE_FAILED) == 0
-            assert r["n_fail"] == int((~ok).sum()) and (q != 0.0 or r["n_fail"] == 0)
-            assert np.array_equal(ac, r["active"])                          # active-slip decisions (and failures) exact
-            assert np.array_equal(it, r["iters"])                           # Newton counts exact
-            assert H.rel_err(sig[:, ok], r["sig"][:, ok]).max() < H.RTOL and H.rel_err(tan[:, ok], r["tan"][:, ok]).max() < H.RTOL
-            assert H.rel_err(so[:, ok], r["state"][:, ok]).max() < H.RTOL
             st = np.where(ok[None, :], r["state"], st)                      # failed points keep their old state
+    assert n_fallback_total > 0                     # ... but the guard does fire on the harder configurations
