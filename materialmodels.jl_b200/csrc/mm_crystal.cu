@@ -69,17 +69,106 @@ __global__ void __launch_bounds__(128) crystal_fixup_kernel(const CrystalK k, co
 #define MM_CRYSTAL_BS 64
 #endif
 #ifndef MM_CRYSTAL_MINBLOCKS
-#define MM_CRYSTAL_MINBLOCKS 4
+#define MM_CRYSTAL_MINBLOCKS 5
+#endif
+#ifndef MM_CRYSTAL_THRESH
+#define MM_CRYSTAL_THRESH 8
 #endif
 template <> struct MinBlocks<CrystalOp<1>> { static constexpr int value = MM_CRYSTAL_MINBLOCKS; };
 template <> struct MinBlocks<CrystalOp<2>> { static constexpr int value = MM_CRYSTAL_MINBLOCKS; };
 
+// ---------------------------------------------------------------------------------------------------------
+// Lane-persistent kernel.  Newton iteration counts differ wildly between neighbouring points (0 for an elastic
+// point, 5-30 for a plastic one), so with one point per thread a warp idles most of its lanes while the slowest
+// solve finishes (ncu: 12.4 of 32 threads active per instruction).  Here each WARP owns a contiguous chunk of
+// points; a lane whose point is finished is refilled with the next point of the chunk, and the (expensive, uniform)
+// tangent + store phase runs only when at least MM_CRYSTAL_THRESH lanes are waiting for it — warp-level voting
+// (__ballot_sync) decides every phase.  All per-point vectors live in the lane's shared-memory scratch column.
+// ---------------------------------------------------------------------------------------------------------
+template <bool HASQ, int LAYOUT, int BS>
+__global__ void __launch_bounds__(BS, MM_CRYSTAL_MINBLOCKS)
+crystal_persistent_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint8_t* iters, int32_t* n_fail, const int64_t N, const int chunk) {
+    extern __shared__ double sm_scratch[];
+    const Scratch scr{sm_scratch + threadIdx.x, BS};
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_id = (int64_t)blockIdx.x * (BS / 32) + (threadIdx.x >> 5);
+    int64_t next = warp_id * chunk;
+    const int64_t end = (next + chunk < N) ? (next + chunk) : N;
+    CrystalLane L;
+    bool has_work = false, finished = false;
+    int64_t my = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !has_work);
+        if (idle != 0u && next < end) {                       // refill idle lanes with the next points of the chunk
+            if (!has_work) {
+                const int64_t cand = next + __popc(idle & ((1u << lane) - 1u));
+                if (cand < end) {
+                    my = cand;
+                    DirectAcc<LAYOUT> acc(p, N, my);
+                    crystal_init(k, acc, scr, L);
+                    has_work = true; finished = false;
+                }
+            }
+            next += __popc(idle);
+        }
+        const unsigned working = __ballot_sync(FULL, has_work);
+        if (working == 0u) break;
+        if (has_work && !finished) finished = crystal_iterate<HASQ>(k, scr, L);
+        const unsigned fin = __ballot_sync(FULL, has_work && finished);
+        const unsigned iterating = working & ~fin;
+        if (fin != 0u && (__popc(fin) >= MM_CRYSTAL_THRESH || iterating == 0u)) {
+            if (has_work && finished) {
+                DirectAcc<LAYOUT> acc(p, N, my);
+                bool fallback = false;
+                unsigned mask = crystal_finalize<HASQ>(k, acc, scr, L, &fallback);
+                if (fallback) mask = MM_ACTIVE_NEEDS_GENERAL;
+                active[my] = (uint16_t)mask;
+                if (iters) iters[my] = (uint8_t)(fallback ? 0 : (L.iters > 255 ? 255 : L.iters));
+                if ((mask & MM_ACTIVE_FAILED) && n_fail) atomicAdd(n_fail, 1);
+                has_work = false; finished = false;
+            }
+        }
+    }
+}
+
+template <bool HASQ, int LAYOUT>
+int launch_crystal_persistent(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
+    constexpr int BS = MM_CRYSTAL_BS;
+    constexpr size_t smem = (size_t)MM_CRYSTAL_SCRATCH * BS * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(crystal_persistent_kernel<HASQ, LAYOUT, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_crystal: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    // chunk of points per warp: large enough to refill many times, small enough for >= ~8 waves of warps on the chip
+    const int64_t resident_warps = (int64_t)sm_count() * MM_CRYSTAL_MINBLOCKS * (BS / 32);
+    int64_t chunk = N / (resident_warps * 8);
+    if (chunk > 1024) chunk = 1024;
+    if (chunk < 64) chunk = 64;
+    chunk = (chunk + 31) / 32 * 32;
+    const int64_t warps = (N + chunk - 1) / chunk;
+    const int64_t blocks = (warps + (BS / 32) - 1) / (BS / 32);
+    crystal_persistent_kernel<HASQ, LAYOUT, BS><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, n_fail, N, (int)chunk);
+    return check_launch("mm_crystal");
+}
+
 template <int MODE>
 int launch_crystal(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
-    CrystalOp<MODE> op;
-    op.k = k; op.active = active; op.iters = iters; op.n_fail = n_fail;
-    int rc = launch_points<CrystalOp<MODE>, (MODE == 0) ? 64 : MM_CRYSTAL_BS>(op, ptrs, N, layout, st, "mm_crystal");
-    if (rc || MODE == 0 || N == 0) return rc;
+    if (N == 0) return MM_OK;
+    int rc;
+    const char* pers = getenv("MM_CRYSTAL_PERSISTENT");      // A/B switch: "0" = one point per thread through the generic wrappers
+    if (MODE != 0 && !(pers && pers[0] == '0')) {
+        if (layout == 0)      rc = launch_crystal_persistent<MODE == 2, 0>(k, active, iters, n_fail, ptrs, N, st);
+        else if (layout == 1) rc = launch_crystal_persistent<MODE == 2, 1>(k, active, iters, n_fail, ptrs, N, st);
+        else return set_error(MM_ERR_ARG, "mm_crystal: unknown layout %d", layout);
+    } else {
+        CrystalOp<MODE> op;
+        op.k = k; op.active = active; op.iters = iters; op.n_fail = n_fail;
+        rc = launch_points<CrystalOp<MODE>, 64>(op, ptrs, N, layout, st, "mm_crystal");
+    }
+    if (rc || MODE == 0) return rc;
     const int64_t blocks = (N + 127) / 128;
     if (layout == 0) crystal_fixup_kernel<0><<<(unsigned)blocks, 128, 0, st>>>(k, ptrs, active, iters, n_fail, N);
     else             crystal_fixup_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(k, ptrs, active, iters, n_fail, N);

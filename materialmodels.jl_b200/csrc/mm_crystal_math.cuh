@@ -272,8 +272,28 @@ MM_HD void ldl6_solve(const double* M, double* b) {
         for (int j = i + 1; j < 6; ++j) b[i] -= M[j * 6 + i] * b[j];
 }
 
-template <bool HASQ, class Acc, class Scr>
-MM_HD unsigned crystal_point_fast(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
+// ---- the structured path in three phases, so that a persistent warp can interleave points (mm_crystal.cu) ----
+// Per-lane state: everything indexed by slip system lives in the scratch column (run-time indexed, rolled loops =>
+// small code, no instruction-cache thrash); registers hold only the 6x6 M, σ and a few scalars.
+// Scratch slots: [0,12) κₙ [12,24) αₙ [24,36) c=p·sgn [36,48) D⁻¹r [48,60) 1/D [60,72) x=μ [72,78) σ_trial
+#undef MM_CRYSTAL_SCRATCH
+#define MM_CRYSTAL_SCRATCH 78
+
+struct CrystalLane {
+    double K[36];          // lower triangle of M = (Eᵉ)⁻¹ + S at the last evaluation (kept for the tangent)
+    double sig[6];         // σ at the last evaluation
+    double yp[6];          // Σ s_i (D⁻¹p̂)_i Pw_i at the last evaluation (cross hardening only)
+    unsigned spos, sneg;   // frozen trial signs
+    unsigned mask;         // active mask at the last evaluation
+    int it;                // loop index of nonlinear_solver.jl:53 (1-based) of the NEXT evaluation
+    int iters;             // number of x updates done
+    bool converged, bad;
+};
+
+MM_HD double crystal_sign(const CrystalLane& L, int i) { return ((L.spos >> i) & 1u) ? 1.0 : (((L.sneg >> i) & 1u) ? -1.0 : 0.0); }
+
+template <class Acc, class Scr>
+MM_HD void crystal_init(const CrystalK& k, Acc& acc, Scr& scr, CrystalLane& L) {
     const double G2 = 2.0 * k.G;
     double st[6];
     {   // σ_trial = σₙ + Eᵉ ⊡ Δε                                                           :119
@@ -282,200 +302,223 @@ MM_HD unsigned crystal_point_fast(const CrystalK& k, Acc& acc, Scr& scr, int* it
         for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c);
         const double ltr = k.lam * tr6(e);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) st[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c]));
+        for (int c = 0; c < 6; ++c) { st[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c])); scr(72 + c) = st[c]; }
     }
-    double x[12];
-    unsigned spos = 0, sneg = 0;       // frozen trial signs s_i (:120-121)
+    L.spos = 0; L.sneg = 0;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < 12; ++i) {                                                      // :120-121
         const double kn = acc.template in<1>(6 + i), an = acc.template in<1>(18 + i);
-        x[i] = acc.template in<1>(30 + i);
-        scr(i) = kn; scr(12 + i) = an;
+        scr(i) = kn; scr(12 + i) = an; scr(60 + i) = acc.template in<1>(30 + i);
         double tau = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) tau += st[c] * k.Pw[i][c];
         const double d = tau - an;
-        if (d > 0.0) spos |= (1u << i);
-        if (d < 0.0) sneg |= (1u << i);
+        if (d > 0.0) L.spos |= (1u << i);
+        if (d < 0.0) L.sneg |= (1u << i);
     }
-#define MM_S(i) (((spos >> (i)) & 1u) ? 1.0 : (((sneg >> (i)) & 1u) ? -1.0 : 0.0))
-    double K[36], sig[6], z[6], yr[6], yp[6];
+    L.mask = 0; L.it = 1; L.iters = 0; L.converged = false; L.bad = false;
+}
+
+// one pass of the `solve` loop body (nonlinear_solver.jl:53-60): evaluate r and J at x, test, update x.
+// returns true when the point is finished (converged, out of iterations, or needs the general path).
+template <bool HASQ, class Scr>
+MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
+    double sumx = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) L.sig[c] = scr(72 + c);
+#pragma unroll 1
+    for (int j = 0; j < 12; ++j) {                                                      // σ = σ_trial − Σ x_j s_j Eᵉ:MS_j   :131
+        const double xj = scr(60 + j);
+        const double f = xj * crystal_sign(L, j);
+        if (HASQ) sumx += xj;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) L.sig[c] -= f * k.EM[j][c];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) L.K[a * 6 + b] = k.Cmp[a][b];
+    double yr[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { yr[c] = 0.0; L.yp[c] = 0.0; }
+    double nrm2 = 0.0;
     unsigned mask = 0;
-    int iters = 0;
-    bool converged = false, bad = false;
-    for (int it = 1;; ++it) {
-        double sumx = 0.0;
+    bool bad = false;
+#pragma unroll 1
+    for (int i = 0; i < 12; ++i) {
+        double pw[6];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) sig[c] = st[c];
+        for (int c = 0; c < 6; ++c) pw[c] = k.Pw[i][c];
+        const double si = crystal_sign(L, i), xi = scr(60 + i);
+        double kap = scr(i) + k.a_h * xi;                                               // :127 with H = a I + b 11ᵀ
+        if (HASQ) kap += k.b_h * sumx;
+        const double iden = fast_rcp(1.0 + k.hk_ai * xi);
+        const double al = (scr(12 + i) + k.H_kin * xi * si) * iden;                     // :128
+        double tau = 0.0;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-            const double f = x[j] * MM_S(j);
-            if (HASQ) sumx += x[j];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) sig[c] -= f * k.EM[j][c];
+        for (int c = 0; c < 6; ++c) tau += L.sig[c] * pw[c];
+        const double red = tau - al;
+        const double sgn = (red > 0.0) ? 1.0 : ((red < 0.0) ? -1.0 : 0.0);
+        const double Phi = fabs(red) - k.tau_y - kap;                                    // :110
+        double Ri = -k.t_star * xi, p = 0.0;
+        if (Phi > 0.0) {                                                                // ⟨Φ⟩ = (Φ+|Φ|)/2
+            const double xx = Phi * k.isc;
+            const double pw1 = k.m_int ? powi_(xx, k.m_int - 1) : pow(xx, k.m - 1.0);
+            Ri = k.dt * (pw1 * xx) - k.t_star * xi;                                     // :111
+            p = k.dtm_sc * pw1;
+            mask |= (1u << i);
         }
+        nrm2 += Ri * Ri;
+        const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
+        // D_ii = −dD.  The Woodbury split needs D safely invertible: dD >= t*/4 (it is >= t* unless an ACTIVE system's
+        // reduced stress has flipped sign against its trial value while a_h < H_kin); otherwise -> pivoted general path.
+        const double dD = k.t_star + p * (sgn * dal + k.a_h);
+        bad = bad | !(dD >= 0.25 * k.t_star);
+        const double invD = -fast_rcp(dD);
+        const double ci = p * sgn;
+        const double rD = Ri * invD;
+        scr(24 + i) = ci; scr(36 + i) = rD; scr(48 + i) = invD;
+        if (p != 0.0) {                      // inactive systems contribute nothing to S
+            const double w = -si * ci * invD;
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
+            for (int a = 0; a < 6; ++a) {
+                const double wa = w * pw[a];
 #pragma unroll
-            for (int b = 0; b <= a; ++b) K[a * 6 + b] = k.Cmp[a][b];          // M = (Eᵉ)⁻¹ + S, lower triangle
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { yr[c] = 0.0; yp[c] = 0.0; }
-        double nrm2 = 0.0;
-        mask = 0;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            const double si = MM_S(i);
-            double kap = scr(i) + k.a_h * x[i];
-            if (HASQ) kap += k.b_h * sumx;
-            const double iden = fast_rcp(1.0 + k.hk_ai * x[i]);
-            const double al = (scr(12 + i) + k.H_kin * x[i] * si) * iden;
-            double tau = 0.0;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) tau += sig[c] * k.Pw[i][c];
-            const double red = tau - al;
-            const double sgn = (red > 0.0) ? 1.0 : ((red < 0.0) ? -1.0 : 0.0);
-            const double Phi = fabs(red) - k.tau_y - kap;                                  // :110
-            double Ri = -k.t_star * x[i], p = 0.0;
-            if (Phi > 0.0) {
-                const double xx = Phi * k.isc;
-                const double pw1 = k.m_int ? powi_(xx, k.m_int - 1) : pow(xx, k.m - 1.0);
-                Ri = k.dt * (pw1 * xx) - k.t_star * x[i];                                   // :111
-                p = k.dtm_sc * pw1;
-                mask |= (1u << i);
-            }
-            nrm2 += Ri * Ri;
-            const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
-            // D_ii = −dD.  The Woodbury split needs D safely invertible: dD >= t*/4 (it is >= t* unless an ACTIVE system's
-            // reduced stress has flipped sign against its trial value while a_h < H_kin); otherwise -> pivoted general path.
-            const double dD = k.t_star + p * (sgn * dal + k.a_h);
-            bad = bad | !(dD >= 0.25 * k.t_star);
-            const double invD = -fast_rcp(dD);
-            const double ci = p * sgn;
-            const double rD = Ri * invD;
-            scr(24 + i) = ci; scr(36 + i) = rD; scr(48 + i) = invD;
-            if (p != 0.0) {                      // inactive systems contribute nothing to S
-                const double w = -si * ci * invD;
-#pragma unroll
-                for (int a = 0; a < 6; ++a) {
-                    const double wa = w * k.Pw[i][a];
-#pragma unroll
-                    for (int b = 0; b <= a; ++b) K[a * 6 + b] += wa * k.Pw[i][b];
-                }
-            }
-            const double srD = si * rD;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) yr[c] += srD * k.Pw[i][c];
-            if (HASQ) {
-                const double spD = si * (k.b_h * p * invD);
-#pragma unroll
-                for (int c = 0; c < 6; ++c) yp[c] += spD * k.Pw[i][c];
+                for (int b = 0; b <= a; ++b) L.K[a * 6 + b] += wa * pw[b];
             }
         }
-        iters = it - 1;
-        if (it > k.max_iter) break;                                                      // nonlinear_solver.jl:61
-        if (sqrt(nrm2) < k.tol) { converged = true; break; }                             // nonlinear_solver.jl:56
-        if (bad) break;
-        if (!ldl6_factor(K)) { bad = true; break; }
-        ldl6_solve(K, yr);
-        double su = 0.0, sv = 0.0;
+        const double srD = si * rD;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) yr[c] += srD * pw[c];
         if (HASQ) {
-            ldl6_solve(K, yp);
+            const double spD = si * (k.b_h * p * invD);
 #pragma unroll
-            for (int i = 0; i < 12; ++i) {
-                const double ci = scr(24 + i), invD = scr(48 + i);
-                double du = 0.0, dv = 0.0;
-#pragma unroll
-                for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; dv += k.Pw[i][c] * yp[c]; }
-                su += scr(36 + i) + invD * ci * du;
-                sv += k.b_h * fabs(ci) * invD + invD * ci * dv;
-            }
+            for (int c = 0; c < 6; ++c) L.yp[c] += spD * pw[c];
         }
-        const double fac = HASQ ? su * fast_rcp(1.0 - sv) : 0.0;
+    }
+    L.mask = mask;
+    L.iters = L.it - 1;
+    if (L.it > k.max_iter) return true;                                                  // nonlinear_solver.jl:61 (returns nothing)
+    if (sqrt(nrm2) < k.tol) { L.converged = true; return true; }                         // nonlinear_solver.jl:56
+    if (bad) { L.bad = true; return true; }
+    // x -= J \ r                                                                        nonlinear_solver.jl:59
+    double M[36];
 #pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) M[a * 6 + b] = L.K[a * 6 + b];
+    if (!ldl6_factor(M)) { L.bad = true; return true; }
+    ldl6_solve(M, yr);
+    double fac = 0.0;
+    double ypl[6];
+    if (HASQ) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) ypl[c] = L.yp[c];
+        ldl6_solve(M, ypl);
+        double su = 0.0, sv = 0.0;
+#pragma unroll 1
         for (int i = 0; i < 12; ++i) {
             const double ci = scr(24 + i), invD = scr(48 + i);
             double du = 0.0, dv = 0.0;
 #pragma unroll
-            for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; if (HASQ) dv += k.Pw[i][c] * yp[c]; }
-            double d = scr(36 + i) + invD * ci * du;
-            if (HASQ) d += (k.b_h * fabs(ci) * invD + invD * ci * dv) * fac;
-            x[i] -= d;                                                                   // nonlinear_solver.jl:59
+            for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; dv += k.Pw[i][c] * ypl[c]; }
+            su += scr(36 + i) + invD * ci * du;
+            sv += k.b_h * fabs(ci) * invD + invD * ci * dv;
         }
-        iters = it;
+        fac = su * fast_rcp(1.0 - sv);
     }
-    if (bad) { *fallback = true; *iters_out = 0; return 0; }       // (also when the guard trips on the converged pass: the tangent needs D⁻¹)
-    if (!converged) mask |= 0x8000u;
-    // outputs                                                                            :77, :90
+#pragma unroll 1
+    for (int i = 0; i < 12; ++i) {
+        const double ci = scr(24 + i), invD = scr(48 + i);
+        double du = 0.0, dv = 0.0;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { acc.template out<0>(c, sig[c]); acc.template out<2>(c, sig[c]); }
-    {
-        double sumx = 0.0;
-        if (HASQ) {
+        for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; if (HASQ) dv += k.Pw[i][c] * ypl[c]; }
+        double d = scr(36 + i) + invD * ci * du;
+        if (HASQ) d += (k.b_h * fabs(ci) * invD + invD * ci * dv) * fac;
+        scr(60 + i) -= d;
+    }
+    L.iters = L.it;
+    L.it += 1;
+    return false;
+}
+
+// outputs of a finished point (:77-90).  Returns the mask (bit 15 = not converged) or *fallback = true.
+template <bool HASQ, class Acc, class Scr>
+MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLane& L, bool* fallback) {
+    if (L.bad) { *fallback = true; return 0; }
+    unsigned mask = L.mask;
+    if (!L.converged) mask |= 0x8000u;
 #pragma unroll
-            for (int j = 0; j < 12; ++j) sumx += x[j];
-        }
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            double kap = scr(i) + k.a_h * x[i];
-            if (HASQ) kap += k.b_h * sumx;
-            const double al = (scr(12 + i) + k.H_kin * x[i] * MM_S(i)) * fast_rcp(1.0 + k.hk_ai * x[i]);
-            acc.template out<2>(6 + i, kap); acc.template out<2>(18 + i, al); acc.template out<2>(30 + i, x[i]);
-        }
+    for (int c = 0; c < 6; ++c) { acc.template out<0>(c, L.sig[c]); acc.template out<2>(c, L.sig[c]); }
+    double sumx = 0.0;
+    if (HASQ) {
+#pragma unroll 1
+        for (int j = 0; j < 12; ++j) sumx += scr(60 + j);
+    }
+#pragma unroll 1
+    for (int i = 0; i < 12; ++i) {
+        const double xi = scr(60 + i);
+        double kap = scr(i) + k.a_h * xi;
+        if (HASQ) kap += k.b_h * sumx;
+        const double al = (scr(12 + i) + k.H_kin * xi * crystal_sign(L, i)) * fast_rcp(1.0 + k.hk_ai * xi);
+        acc.template out<2>(6 + i, kap); acc.template out<2>(18 + i, al); acc.template out<2>(30 + i, xi);
     }
     if (acc.template has_out<1>()) {
-        const bool want = ((mask & 0x0FFFu) != 0) && converged;
-        bool okf = true;
-        double vq[12], svq = 0.0;       // HASQ only: v = (D − ABᵀ)⁻¹ p̂
+        const bool want = ((mask & 0x0FFFu) != 0) && L.converged;
+        double svq = 0.0;
         if (want) {
-            okf = ldl6_factor(K);
-            if (HASQ) {
-                ldl6_solve(K, yp);
-#pragma unroll
+            if (!ldl6_factor(L.K)) { *fallback = true; return 0; }
+            if (HASQ) {            // v = (D − ABᵀ)⁻¹ p̂, kept in scratch [36,48) is taken by the columns -> recomputed per use via yp
+                ldl6_solve(L.K, L.yp);
+#pragma unroll 1
                 for (int i = 0; i < 12; ++i) {
                     const double ci = scr(24 + i), invD = scr(48 + i);
                     double dv = 0.0;
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) dv += k.Pw[i][c] * yp[c];
-                    vq[i] = k.b_h * fabs(ci) * invD + invD * ci * dv;
-                    svq += vq[i];
+                    for (int c = 0; c < 6; ++c) dv += k.Pw[i][c] * L.yp[c];
+                    svq += k.b_h * fabs(ci) * invD + invD * ci * dv;
                 }
             }
         }
-        if (!okf) { *fallback = true; *iters_out = 0; return 0; }
         const double ifq = HASQ ? fast_rcp(1.0 - svq) : 0.0;
 #pragma unroll 1
-        for (int Jc = 0; Jc < 6; ++Jc) {                                                 // :79-89, one tangent column at a time
+        for (int Jc = 0; Jc < 6; ++Jc) {                                                 // one tangent column at a time
             double col[6];
 #pragma unroll
             for (int Ic = 0; Ic < 6; ++Ic) col[Ic] = iso_entry(Ic, Jc, k.lam, k.G);
             if (want) {
                 // right-hand side ∂R/∂ε column: c_j EM[j][Jc];  Z = J⁻¹ rhs
-#pragma unroll
-                for (int c = 0; c < 6; ++c) z[c] = 0.0;
-#pragma unroll
+                double z[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
                 for (int j = 0; j < 12; ++j) {
                     const double rD = scr(24 + j) * k.EM[j][Jc] * scr(48 + j);
                     scr(36 + j) = rD;
-                    const double srD = MM_S(j) * rD;
+                    const double srD = crystal_sign(L, j) * rD;
 #pragma unroll
                     for (int c = 0; c < 6; ++c) z[c] += srD * k.Pw[j][c];
                 }
-                ldl6_solve(K, z);
+                ldl6_solve(L.K, z);
                 double sz = 0.0;
-                double Z[12];
-#pragma unroll
+#pragma unroll 1
                 for (int i = 0; i < 12; ++i) {
                     double du = 0.0;
 #pragma unroll
                     for (int c = 0; c < 6; ++c) du += k.Pw[i][c] * z[c];
-                    Z[i] = scr(36 + i) + scr(48 + i) * scr(24 + i) * du;
-                    sz += Z[i];
+                    const double Zi = scr(36 + i) + scr(48 + i) * scr(24 + i) * du;
+                    scr(36 + i) = Zi;
+                    sz += Zi;
                 }
-#pragma unroll
+                const double qf = HASQ ? sz * ifq : 0.0;
+#pragma unroll 1
                 for (int i = 0; i < 12; ++i) {
-                    double Zi = Z[i];
-                    if (HASQ) Zi += vq[i] * (sz * ifq);
                     const double ci = scr(24 + i);
+                    double Zi = scr(36 + i);
+                    if (HASQ) {
+                        double dv = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) dv += k.Pw[i][c] * L.yp[c];
+                        Zi += (k.b_h * fabs(ci) * scr(48 + i) + scr(48 + i) * ci * dv) * qf;
+                    }
                     const double sgnZ = (ci > 0.0) ? Zi : ((ci < 0.0) ? -Zi : 0.0);      // sgn_i Z_i (sgn_i = sign c_i on active systems)
 #pragma unroll
                     for (int Ic = 0; Ic < 6; ++Ic) col[Ic] += k.EM[i][Ic] * sgnZ;
@@ -485,8 +528,17 @@ MM_HD unsigned crystal_point_fast(const CrystalK& k, Acc& acc, Scr& scr, int* it
             for (int Ic = 0; Ic < 6; ++Ic) acc.template out<1>(Ic + 6 * Jc, col[Ic]);
         }
     }
-#undef MM_S
-    *iters_out = iters;
+    return mask;
+}
+
+// one point start to finish (host twin, and the non-persistent wrapper)
+template <bool HASQ, class Acc, class Scr>
+MM_HD unsigned crystal_point_fast(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
+    CrystalLane L;
+    crystal_init(k, acc, scr, L);
+    while (!crystal_iterate<HASQ>(k, scr, L)) {}
+    const unsigned mask = crystal_finalize<HASQ>(k, acc, scr, L, fallback);
+    *iters_out = *fallback ? 0 : L.iters;
     return mask;
 }
 
