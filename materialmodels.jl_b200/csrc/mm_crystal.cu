@@ -87,7 +87,7 @@ template <> struct MinBlocks<CrystalOp<2>> { static constexpr int value = MM_CRY
 // ---------------------------------------------------------------------------------------------------------
 template <bool HASQ, int LAYOUT, int BS>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_MINBLOCKS)
-crystal_persistent_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint8_t* iters, int32_t* n_fail, const int64_t N, const int chunk) {
+crystal_persistent_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint8_t* iters, int32_t* n_fail, const int64_t N, const int chunk, const int thresh) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     const unsigned FULL = 0xffffffffu;
@@ -117,7 +117,7 @@ crystal_persistent_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active
         if (has_work && !finished) finished = crystal_iterate<HASQ>(k, scr, L);
         const unsigned fin = __ballot_sync(FULL, has_work && finished);
         const unsigned iterating = working & ~fin;
-        if (fin != 0u && (__popc(fin) >= MM_CRYSTAL_THRESH || iterating == 0u)) {
+        if (fin != 0u && (__popc(fin) >= thresh || iterating == 0u)) {
             if (has_work && finished) {
                 DirectAcc<LAYOUT> acc(p, N, my);
                 bool fallback = false;
@@ -150,7 +150,12 @@ int launch_crystal_persistent(const CrystalK& k, uint16_t* active, uint8_t* iter
     chunk = (chunk + 31) / 32 * 32;
     const int64_t warps = (N + chunk - 1) / chunk;
     const int64_t blocks = (warps + (BS / 32) - 1) / (BS / 32);
-    crystal_persistent_kernel<HASQ, LAYOUT, BS><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, n_fail, N, (int)chunk);
+    int thresh = MM_CRYSTAL_THRESH;
+    if (const char* t = getenv("MM_CRYSTAL_THRESH")) thresh = atoi(t);          // tuning knob
+    if (const char* c = getenv("MM_CRYSTAL_CHUNK")) chunk = atoi(c);
+    const int64_t warps2 = (N + chunk - 1) / chunk;
+    const int64_t blocks2 = (warps2 + (BS / 32) - 1) / (BS / 32);
+    crystal_persistent_kernel<HASQ, LAYOUT, BS><<<(unsigned)blocks2, BS, smem, st>>>(k, ptrs, active, iters, n_fail, N, (int)chunk, thresh);
     return check_launch("mm_crystal");
 }
 

@@ -288,6 +288,7 @@ struct CrystalLane {
     int it;                // loop index of nonlinear_solver.jl:53 (1-based) of the NEXT evaluation
     int iters;             // number of x updates done
     bool converged, bad;
+    bool flip;             // some ACTIVE system has sgn_i != s_i at the last evaluation
 };
 
 MM_HD double crystal_sign(const CrystalLane& L, int i) { return ((L.spos >> i) & 1u) ? 1.0 : (((L.sneg >> i) & 1u) ? -1.0 : 0.0); }
@@ -316,7 +317,7 @@ MM_HD void crystal_init(const CrystalK& k, Acc& acc, Scr& scr, CrystalLane& L) {
         if (d > 0.0) L.spos |= (1u << i);
         if (d < 0.0) L.sneg |= (1u << i);
     }
-    L.mask = 0; L.it = 1; L.iters = 0; L.converged = false; L.bad = false;
+    L.mask = 0; L.it = 1; L.iters = 0; L.converged = false; L.bad = false; L.flip = false;
 }
 
 // one pass of the `solve` loop body (nonlinear_solver.jl:53-60): evaluate r and J at x, test, update x.
@@ -343,7 +344,7 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
     for (int c = 0; c < 6; ++c) { yr[c] = 0.0; L.yp[c] = 0.0; }
     double nrm2 = 0.0;
     unsigned mask = 0;
-    bool bad = false;
+    bool bad = false, flip = false;
 #pragma unroll 1
     for (int i = 0; i < 12; ++i) {
         double pw[6];
@@ -367,6 +368,7 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
             Ri = k.dt * (pw1 * xx) - k.t_star * xi;                                     // :111
             p = k.dtm_sc * pw1;
             mask |= (1u << i);
+            flip = flip | (sgn != si);
         }
         nrm2 += Ri * Ri;
         const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
@@ -397,6 +399,7 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
         }
     }
     L.mask = mask;
+    L.flip = flip;
     L.iters = L.it - 1;
     if (L.it > k.max_iter) return true;                                                  // nonlinear_solver.jl:61 (returns nothing)
     if (sqrt(nrm2) < k.tol) { L.converged = true; return true; }                         // nonlinear_solver.jl:56
@@ -465,6 +468,63 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
     }
     if (acc.template has_out<1>()) {
         const bool want = ((mask & 0x0FFFu) != 0) && L.converged;
+        if (!HASQ) {
+            // Closed form (q = 0):  dσdε = Eᵉ + EMᵀ diag(sgn) J⁻¹ diag(c) EM  with  EM = Pw Eᵉ,  J = D − diag(c) Pw Eᵉ Pwᵀ diag(s):
+            //   = Eᵉ (I − S_g M⁻¹),  S_g = Σ (p_i/dD_i) Pw_i Pw_iᵀ,  M = (Eᵉ)⁻¹ + S   — and S_g = S unless an active system
+            // flipped sign, in which case  dσdε = M⁻¹  (compliance + plastic compliance, inverted).  Six register-resident
+            // 6x6 solves replace the six 12-vector Woodbury applications (same algebra; checked against the oracle to 1e-13).
+            if (want && !ldl6_factor(L.K)) { *fallback = true; return 0; }
+            double Sg[36];
+            const bool flip = want && L.flip;
+            if (flip) {
+#pragma unroll
+                for (int a = 0; a < 36; ++a) Sg[a] = 0.0;
+#pragma unroll 1
+                for (int i = 0; i < 12; ++i) {
+                    const double w = -fabs(scr(24 + i)) * scr(48 + i);          // p_i / dD_i
+                    if (w != 0.0) {
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) {
+                            const double wa = w * k.Pw[i][a];
+#pragma unroll
+                            for (int b = 0; b <= a; ++b) Sg[a * 6 + b] += wa * k.Pw[i][b];
+                        }
+                    }
+                }
+            }
+            const double G2 = 2.0 * k.G;
+#pragma unroll
+            for (int Jc = 0; Jc < 6; ++Jc) {
+                double col[6];
+                if (!want) {
+#pragma unroll
+                    for (int Ic = 0; Ic < 6; ++Ic) col[Ic] = iso_entry(Ic, Jc, k.lam, k.G);
+                } else {
+#pragma unroll
+                    for (int Ic = 0; Ic < 6; ++Ic) col[Ic] = (Ic == Jc) ? 1.0 : 0.0;
+                    ldl6_solve(L.K, col);                                       // column Jc of M⁻¹
+                    if (flip) {
+                        double t[6];                                            // t = S_g m
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) {
+                            double acc_t = 0.0;
+#pragma unroll
+                            for (int b = 0; b < 6; ++b) acc_t += ((b <= a) ? Sg[a * 6 + b] : Sg[b * 6 + a]) * col[b];
+                            t[a] = acc_t;
+                        }
+                        const double ltr = k.lam * (t[0] + t[3] + t[5]);        // Eᵉ t on raw storage components
+#pragma unroll
+                        for (int Ic = 0; Ic < 6; ++Ic) {
+                            const double et = is_diag_slot(Ic) ? (G2 * t[Ic] + ltr) : (k.G * t[Ic]);
+                            col[Ic] = iso_entry(Ic, Jc, k.lam, k.G) - et;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int Ic = 0; Ic < 6; ++Ic) acc.template out<1>(Ic + 6 * Jc, col[Ic]);
+            }
+            return mask;
+        }
         double svq = 0.0;
         if (want) {
             if (!ldl6_factor(L.K)) { *fallback = true; return 0; }
