@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(128) crystal_fixup_kernel(const CrystalK k, co
 #ifndef MM_CRYSTAL_THRESH
 #define MM_CRYSTAL_THRESH 8
 #endif
-template <> struct MinBlocks<CrystalOp<1>> { static constexpr int value = MM_CRYSTAL_MINBLOCKS; };
-template <> struct MinBlocks<CrystalOp<2>> { static constexpr int value = MM_CRYSTAL_MINBLOCKS; };
+template <> struct MinBlocks<CrystalOp<1>> { static constexpr int value = MM_CRYSTAL_MINBLOCKS, block = 64; };
+template <> struct MinBlocks<CrystalOp<2>> { static constexpr int value = MM_CRYSTAL_MINBLOCKS, block = 64; };
 
 // ---------------------------------------------------------------------------------------------------------
 // Lane-persistent kernel.  Newton iteration counts differ wildly between neighbouring points (0 for an elastic

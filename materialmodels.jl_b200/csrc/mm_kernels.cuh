@@ -6,13 +6,14 @@
 // and is launched through one of two wrappers:
 //   * soa_kernel — MM_LAYOUT_SOA, a[c*N + i]: thread <-> point, every load/store of a component is a
 //     fully coalesced 256 B/warp streaming access (ld.global.cs / st.global.cs: data is touched once).
-//   * aos_kernel — MM_LAYOUT_AOS, a[i*nc + c]: the block stages a tile of BS points per array through
-//     shared memory with contiguous coalesced copies; per-thread accesses hit an odd-padded stride
-//     (nc|1 doubles) so they are bank-conflict free.
+//   * aos_bulk_kernel — MM_LAYOUT_AOS, a[i*nc + c]: a tile of BS points of an array is one contiguous run in
+//     global memory; it is staged through dense shared-memory images by 1-D TMA bulk copies (cp.async.bulk +
+//     mbarrier in, bulk_group out) driven by one elected thread — no per-element copy instructions.
 // Both paths run the same math (mm_math.cuh).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "mm_math.cuh"
 
 namespace mm {
@@ -32,7 +33,7 @@ template <int NIN, int NOUT> struct SoaAcc {
     template <int A> __device__ __forceinline__ bool has_out() const { return p.out[A] != nullptr; }
 };
 
-template <class Op> struct MinBlocks { static constexpr int value = 1; };   // per-Op occupancy target (register cap)
+template <class Op> struct MinBlocks { static constexpr int value = 1, block = 32; };   // per-Op occupancy target (register cap): `value` blocks of `block` threads
 
 // Per-thread scratch in shared memory, laid out [slot][thread] (thread-minor => bank-conflict free).
 // Ops declare how many doubles they need in Op::SCRATCH (0 for the streaming models).
@@ -53,63 +54,133 @@ __global__ void __launch_bounds__(BS, MinBlocks<Op>::value) soa_kernel(const Op 
 }
 
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int pad_odd(int nc) { return nc | 1; }
-template <class Op> __host__ __device__ constexpr int aos_in_off(int a) { return a == 0 ? 0 : aos_in_off<Op>(a - 1) + pad_odd(Op::in_nc(a - 1)); }
-template <class Op> __host__ __device__ constexpr int aos_out_off(int a) { return a == 0 ? aos_in_off<Op>(Op::NIN) : aos_out_off<Op>(a - 1) + pad_odd(Op::out_nc(a - 1)); }
-template <class Op> __host__ __device__ constexpr int aos_doubles_per_point() { return aos_out_off<Op>(Op::NOUT) + Op::SCRATCH; }
+// AoS path (MM_LAYOUT_AOS): the copy engine moves whole tiles.  A tile of BS points of array A is one
+// contiguous run of BS*nc doubles in global memory, so it is fetched with ONE 1-D bulk async copy (TMA,
+// cp.async.bulk ... mbarrier::complete_tx) into a dense shared-memory image, and the outputs leave through bulk
+// shared->global copies (bulk_group).  No per-element copy instructions, no address arithmetic; one elected thread
+// drives the copies, the rest of the block waits on the mbarrier phase.  The next tile's loads are issued together
+// with this tile's stores, so they overlap the store drain.  Bulk copies need 16-byte aligned bases and full tiles;
+// the one ragged tile (or every tile, if a base is unaligned) uses element-wise copies inside the same kernel.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <class Op, int BS> struct AosAcc {
+// dense tile images: inputs [A][pt][c], then outputs [A][pt][c] (no aliasing: strides differ)
+template <class Op> __host__ __device__ constexpr int dense_in_off(int a) { return a == 0 ? 0 : dense_in_off<Op>(a - 1) + Op::in_nc(a - 1); }
+template <class Op> __host__ __device__ constexpr int dense_out_off(int a) { return a == 0 ? dense_in_off<Op>(Op::NIN) : dense_out_off<Op>(a - 1) + Op::out_nc(a - 1); }
+template <class Op> __host__ __device__ constexpr int dense_doubles_per_point() { return dense_out_off<Op>(Op::NOUT) + Op::SCRATCH; }
+
+template <class Op, int BS> struct DenseAcc {
     double* sm;
     const Ptrs<Op::NIN, Op::NOUT>& p;
     int t;
-    __device__ __forceinline__ AosAcc(double* sm_, const Ptrs<Op::NIN, Op::NOUT>& p_, int t_) : sm(sm_), p(p_), t(t_) {}
-    template <int A> __device__ __forceinline__ double in(int c) const { return sm[aos_in_off<Op>(A) * BS + t * pad_odd(Op::in_nc(A)) + c]; }
-    template <int A> __device__ __forceinline__ void out(int c, double v) const { sm[aos_out_off<Op>(A) * BS + t * pad_odd(Op::out_nc(A)) + c] = v; }
+    __device__ __forceinline__ DenseAcc(double* sm_, const Ptrs<Op::NIN, Op::NOUT>& p_, int t_) : sm(sm_), p(p_), t(t_) {}
+    template <int A> __device__ __forceinline__ double in(int c) const { return sm[dense_in_off<Op>(A) * BS + t * Op::in_nc(A) + c]; }
+    template <int A> __device__ __forceinline__ void out(int c, double v) const { sm[dense_out_off<Op>(A) * BS + t * Op::out_nc(A) + c] = v; }
     template <int A> __device__ __forceinline__ bool has_out() const { return p.out[A] != nullptr; }
 };
-
-template <int NC, int BS> __device__ __forceinline__ void tile_in(double* sm, const double* g, int npts) {
-    constexpr int NCP = pad_odd(NC);
-    const int n = npts * NC;
-    for (int e = threadIdx.x; e < n; e += BS) {
-        const int pt = e / NC, c = e - pt * NC;
-        sm[pt * NCP + c] = __ldcs(g + e);
+template <class Op, int BS, int A> struct BulkIO {
+    static __device__ __forceinline__ uint32_t in_bytes() {
+        uint32_t b = (uint32_t)(BS * Op::in_nc(A) * sizeof(double));
+        if constexpr (A + 1 < Op::NIN) b += BulkIO<Op, BS, A + 1>::in_bytes();
+        return b;
     }
-}
-template <int NC, int BS> __device__ __forceinline__ void tile_out(const double* sm, double* g, int npts) {
-    constexpr int NCP = pad_odd(NC);
-    const int n = npts * NC;
-    for (int e = threadIdx.x; e < n; e += BS) {
-        const int pt = e / NC, c = e - pt * NC;
-        __stcs(g + e, sm[pt * NCP + c]);
+    static __device__ __forceinline__ void load_all(double* sm, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, uint64_t* bar) {
+        bulk_g2s(sm + dense_in_off<Op>(A) * BS, p.in[A] + i0 * Op::in_nc(A), (uint32_t)(BS * Op::in_nc(A) * sizeof(double)), bar);
+        if constexpr (A + 1 < Op::NIN) BulkIO<Op, BS, A + 1>::load_all(sm, p, i0, bar);
     }
-}
-template <class Op, int BS, int A> struct TileIO {
-    static __device__ __forceinline__ void load_all(double* sm, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, int npts) {
-        tile_in<Op::in_nc(A), BS>(sm + aos_in_off<Op>(A) * BS, p.in[A] + i0 * Op::in_nc(A), npts);
-        if constexpr (A + 1 < Op::NIN) TileIO<Op, BS, A + 1>::load_all(sm, p, i0, npts);
-    }
-    static __device__ __forceinline__ void store_all(const double* sm, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, int npts) {
-        if (p.out[A] != nullptr) tile_out<Op::out_nc(A), BS>(sm + aos_out_off<Op>(A) * BS, p.out[A] + i0 * Op::out_nc(A), npts);
-        if constexpr (A + 1 < Op::NOUT) TileIO<Op, BS, A + 1>::store_all(sm, p, i0, npts);
+    static __device__ __forceinline__ void store_all(double* sm, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0) {
+        if (p.out[A] != nullptr) bulk_s2g(p.out[A] + i0 * Op::out_nc(A), sm + dense_out_off<Op>(A) * BS, (uint32_t)(BS * Op::out_nc(A) * sizeof(double)));
+        if constexpr (A + 1 < Op::NOUT) BulkIO<Op, BS, A + 1>::store_all(sm, p, i0);
     }
 };
 
-template <class Op, int BS>
-__global__ void __launch_bounds__(BS) aos_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N, const int64_t ntiles) {
-    extern __shared__ double sm[];
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t i0 = tile * BS;
-        const int npts = (int)((N - i0 < BS) ? (N - i0) : BS);
-        TileIO<Op, BS, 0>::load_all(sm, p, i0, npts);
-        __syncthreads();
-        if ((int)threadIdx.x < npts) {
-            AosAcc<Op, BS> acc(sm, p, (int)threadIdx.x);
-            Scratch scr{sm + aos_out_off<Op>(Op::NOUT) * BS + threadIdx.x, BS};
-            op.point(acc, i0 + threadIdx.x, scr);
+template <class Op, int BS, int A> struct DenseTailIO {     // element-wise copies for the one ragged tile (npts < BS)
+    static __device__ __forceinline__ void load_all(double* sm, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, int npts) {
+        const double* g = p.in[A] + i0 * Op::in_nc(A);
+        for (int e = threadIdx.x; e < npts * Op::in_nc(A); e += BS) sm[dense_in_off<Op>(A) * BS + e] = __ldcs(g + e);
+        if constexpr (A + 1 < Op::NIN) DenseTailIO<Op, BS, A + 1>::load_all(sm, p, i0, npts);
+    }
+    static __device__ __forceinline__ void store_all(const double* sm, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, int npts) {
+        if (p.out[A] != nullptr) {
+            double* g = p.out[A] + i0 * Op::out_nc(A);
+            for (int e = threadIdx.x; e < npts * Op::out_nc(A); e += BS) __stcs(g + e, sm[dense_out_off<Op>(A) * BS + e]);
         }
-        __syncthreads();
-        TileIO<Op, BS, 0>::store_all(sm, p, i0, npts);
+        if constexpr (A + 1 < Op::NOUT) DenseTailIO<Op, BS, A + 1>::store_all(sm, p, i0, npts);
+    }
+};
+
+// `bulk` = 0 sends every tile through the element-wise copies (arrays whose base is not 16-byte aligned); the
+// compute code is the same instantiation either way, so results do not depend on how a batch is tiled or chunked.
+template <class Op, int BS>
+__global__ void __launch_bounds__(BS, (MinBlocks<Op>::value * MinBlocks<Op>::block + BS - 1) / BS)
+aos_bulk_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N, const int64_t ntiles, const int bulk) {
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm_raw);
+    double* sm = reinterpret_cast<double*>(sm_raw + 16);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    int64_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    const int64_t nfull = bulk ? N / BS : 0;          // tiles [0, nfull) are full and go through the copy engine
+    if (threadIdx.x == 0 && tile < nfull) {
+        mbar_expect_tx(bar, BulkIO<Op, BS, 0>::in_bytes());
+        BulkIO<Op, BS, 0>::load_all(sm, p, tile * BS, bar);
+    }
+    uint32_t parity = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        const bool full = tile < nfull;
+        const int npts = (int)((N - tile * BS < BS) ? (N - tile * BS) : BS);
+        if (full) {
+            mbar_wait(bar, parity);                   // this tile's inputs have landed
+            parity ^= 1u;
+        } else {
+            DenseTailIO<Op, BS, 0>::load_all(sm, p, tile * BS, npts);
+            __syncthreads();
+        }
+        if ((int)threadIdx.x < npts) {
+            DenseAcc<Op, BS> acc(sm, p, (int)threadIdx.x);
+            Scratch scr{sm + dense_out_off<Op>(Op::NOUT) * BS + threadIdx.x, BS};
+            op.point(acc, tile * BS + threadIdx.x, scr);
+        }
+        fence_async_smem();                           // generic-proxy writes -> visible to the copy engine
+        __syncthreads();                              // all outputs written, all inputs consumed
+        if (full) {
+            if (threadIdx.x == 0) {
+                BulkIO<Op, BS, 0>::store_all(sm, p, tile * BS);
+                bulk_commit();
+                const int64_t nxt = tile + gridDim.x;
+                if (nxt < nfull) {                    // next tile's loads overlap this tile's store drain
+                    mbar_expect_tx(bar, BulkIO<Op, BS, 0>::in_bytes());
+                    BulkIO<Op, BS, 0>::load_all(sm, p, nxt * BS, bar);
+                }
+                bulk_wait_read0();                    // output image may be overwritten again
+            }
+        } else {
+            DenseTailIO<Op, BS, 0>::store_all(sm, p, tile * BS, npts);
+        }
         __syncthreads();
     }
 }
@@ -119,34 +190,39 @@ int set_error(int code, const char* fmt, ...);   // mm_api.cu
 int check_launch(const char* what);              // mm_api.cu
 int sm_count();                                  // mm_api.cu
 
-template <class Op, int BS>
+template <class Op, int BS_SOA, int BS_AOS = BS_SOA>
 int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int layout, cudaStream_t stream, const char* what) {
     if (N == 0) return 0;
     if (layout == 0) {
-        const int64_t blocks = (N + BS - 1) / BS;
+        const int64_t blocks = (N + BS_SOA - 1) / BS_SOA;
         if (blocks > 2147483647LL) return set_error(-1, "%s: N too large for one launch", what);
-        constexpr size_t scratch = (size_t)Op::SCRATCH * BS * sizeof(double);
+        constexpr size_t scratch = (size_t)Op::SCRATCH * BS_SOA * sizeof(double);
         static bool soa_configured = false;
         if (!soa_configured && scratch > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(soa_kernel<Op, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch);
+            cudaError_t e = cudaFuncSetAttribute(soa_kernel<Op, BS_SOA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch);
             if (e != cudaSuccess) return set_error(-2, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
             soa_configured = true;
         }
-        soa_kernel<Op, BS><<<(unsigned)blocks, BS, scratch, stream>>>(op, p, N);
+        soa_kernel<Op, BS_SOA><<<(unsigned)blocks, BS_SOA, scratch, stream>>>(op, p, N);
     } else if (layout == 1) {
-        constexpr size_t smem = (size_t)aos_doubles_per_point<Op>() * BS * sizeof(double);
-        static bool configured = false;
-        if (!configured) {
-            if (smem > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(aos_kernel<Op, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return set_error(-2, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-            }
-            configured = true;
+        // one kernel for every AoS batch: full tiles through the copy engine (TMA bulk copies) when all array bases are
+        // 16-byte aligned, the ragged last tile (or everything, if unaligned) through element-wise copies
+        bool aligned = true;
+        for (int a = 0; a < Op::NIN; ++a) aligned = aligned && ((reinterpret_cast<uintptr_t>(p.in[a]) & 15u) == 0);
+        for (int a = 0; a < Op::NOUT; ++a) aligned = aligned && ((reinterpret_cast<uintptr_t>(p.out[a]) & 15u) == 0);
+        static int use_bulk = -1;
+        if (use_bulk < 0) { const char* e = getenv("MM_AOS_BULK"); use_bulk = (e && e[0] == '0') ? 0 : 1; }
+        constexpr size_t smem_b = 16 + (size_t)dense_doubles_per_point<Op>() * BS_AOS * sizeof(double);
+        static bool configured_b = false;
+        if (!configured_b) {
+            cudaError_t e = cudaFuncSetAttribute(aos_bulk_kernel<Op, BS_AOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+            if (e != cudaSuccess) return set_error(-2, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+            configured_b = true;
         }
-        const int64_t ntiles = (N + BS - 1) / BS;
-        int64_t blocks = (int64_t)sm_count() * 8;
+        const int64_t ntiles = (N + BS_AOS - 1) / BS_AOS;
+        int64_t blocks = (int64_t)sm_count() * 16;          // grid-stride over tiles; 16 CTAs/SM covers any residency
         if (blocks > ntiles) blocks = ntiles;
-        aos_kernel<Op, BS><<<(unsigned)blocks, BS, smem, stream>>>(op, p, N, ntiles);
+        aos_bulk_kernel<Op, BS_AOS><<<(unsigned)blocks, BS_AOS, smem_b, stream>>>(op, p, N, ntiles, (aligned && use_bulk) ? 1 : 0);
     } else {
         return set_error(-1, "%s: unknown layout %d", what, layout);
     }

@@ -32,10 +32,16 @@ struct PlasticOp {
     }
 };
 
+#ifndef MM_PLASTIC_AOS_BS
+#define MM_PLASTIC_AOS_BS 64
+#endif
+#ifndef MM_STREAM_AOS_BS
+#define MM_STREAM_AOS_BS 128
+#endif
 #ifndef MM_PLASTIC_MINBLOCKS
 #define MM_PLASTIC_MINBLOCKS 3
 #endif
-template <> struct MinBlocks<PlasticOp> { static constexpr int value = MM_PLASTIC_MINBLOCKS; };   // 128 threads x 3 blocks/SM -> <= 168 regs: measured best of {1,3,4,5} (tools/sweep_plastic.sh)
+template <> struct MinBlocks<PlasticOp> { static constexpr int value = MM_PLASTIC_MINBLOCKS, block = 128; };   // 128 threads x 3 blocks/SM -> <= 168 regs: measured best of {1,3,4,5} (tools/sweep_plastic.sh)
 
 template <int MODEL, int KIND> struct HyperOp {
     static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;
@@ -77,9 +83,9 @@ __global__ void __launch_bounds__(256) synth_kernel(double* out, int64_t N, int 
 template <int MODEL> int launch_hyper(const HyperK& k, const double* strain, int strain_kind, double* S, double* dSdC, int64_t N, int layout, cudaStream_t st) {
     Ptrs<1, 2> p;
     p.in[0] = strain; p.out[0] = S; p.out[1] = dSdC;
-    if (strain_kind == MM_STRAIN_F) { HyperOp<MODEL, 1> op; op.k = k; return launch_points<HyperOp<MODEL, 1>, 256>(op, p, N, layout, st, "mm_hyper"); }
+    if (strain_kind == MM_STRAIN_F) { HyperOp<MODEL, 1> op; op.k = k; return launch_points<HyperOp<MODEL, 1>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper"); }
     HyperOp<MODEL, 0> op; op.k = k;
-    return launch_points<HyperOp<MODEL, 0>, 256>(op, p, N, layout, st, "mm_hyper");
+    return launch_points<HyperOp<MODEL, 0>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper");
 }
 
 }  // namespace mm
@@ -92,7 +98,7 @@ int mm_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig, 
     if (!p || N < 0 || (N > 0 && (!eps || !sig))) return set_error(MM_ERR_ARG, "mm_linear_elastic: bad argument");
     ElasticOp op; op.k = make_elastic_k(p->E, p->nu);
     Ptrs<1, 2> ptrs; ptrs.in[0] = eps; ptrs.out[0] = sig; ptrs.out[1] = tan_or_null;
-    return launch_points<ElasticOp, 256>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_linear_elastic");
+    return launch_points<ElasticOp, 256, MM_STREAM_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_linear_elastic");
 }
 
 int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, double* sig, double* tan, double* state_out,
@@ -102,7 +108,7 @@ int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, do
     op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
     op.flags = flags; op.iters = iters; op.n_fail = n_fail;
     Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = state_out;
-    return launch_points<PlasticOp, 128>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
+    return launch_points<PlasticOp, 128, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
 }
 
 int mm_hyper(int model, const MMHyper* p, const double* strain, int strain_kind, double* S, double* dSdC, int64_t N, int layout, void* stream) {
@@ -122,8 +128,8 @@ int mm_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, doubl
     if (!p || N < 0 || (N > 0 && (!jump || !T))) return set_error(MM_ERR_ARG, "mm_xu_needleman: bad argument");
     const XuK k = make_xu_k(p->Phi_n, p->Phi_t, p->delta_n, p->delta_t, p->Delta_n_star);
     Ptrs<1, 2> ptrs; ptrs.in[0] = jump; ptrs.out[0] = T; ptrs.out[1] = dTdD;
-    if (dim == 3) { XuOp<3> op; op.k = k; return launch_points<XuOp<3>, 256>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
-    if (dim == 2) { XuOp<2> op; op.k = k; return launch_points<XuOp<2>, 256>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
+    if (dim == 3) { XuOp<3> op; op.k = k; return launch_points<XuOp<3>, 256, MM_STREAM_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
+    if (dim == 2) { XuOp<2> op; op.k = k; return launch_points<XuOp<2>, 256, MM_STREAM_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
     return set_error(MM_ERR_ARG, "mm_xu_needleman: dim must be 2 or 3 (got %d)", dim);
 }
 
