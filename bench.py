@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--ref-points", type=int, default=0, help="points per step of --impl reference (0 = sized for a ~75 s run)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the informational timings of the other BASELINE configs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -231,7 +232,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         Ne = min(args.e2e_points, N)
-        del out
+        out = None
         torch.cuda.empty_cache()
         h_eps = mm.PinnedArray((6, Ne))
         h_st = mm.PinnedArray((14, Ne))
@@ -257,6 +258,12 @@ def main():
         for v in [h_eps, h_st] + list(h_out.values()):
             v.free()
 
+    out = None
+    if world > 1:
+        sharding.barrier()
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
     if rank != 0:
         return 0
     peak, peak_src = measured_peak()
@@ -277,12 +284,100 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if world == 1 and not args.no_extra:
+        del epsB, stA, stB
+        torch.cuda.empty_cache()
+        line["other_configs"] = other_configs(mm, torch, dev, peak)
     if world == 1 and not args.no_cpu:
         v, cores, dt, fr = cpu_baseline_run(args.cpu_points)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d-point slice of the same workload (step B), oracle mmo_plastic, %.1f s" % (args.cpu_points, dt)}
     print(json.dumps(line))
     return 0
+
+
+def _time_kernel(torch, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def fp64_peak_tflops():
+    """measured DFMA peak (tools/fp64_peak.cu), the denominator for the FP64-bound crystal model"""
+    exe = os.path.join(ROOT, "tools", "fp64_peak")
+    try:
+        if not os.path.exists(exe):
+            subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", exe, exe + ".cu"],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return json.loads(subprocess.check_output([exe], text=True, timeout=60).strip().splitlines()[-1])["fp64_fma_tflops"]
+    except Exception:
+        return None
+
+
+def other_configs(mm, torch, dev, peak):
+    """Kernel-only timings of BASELINE.json configs[0], [2], [3], [4] at their stated sizes (the headline stays configs[1]).
+    Informational: same CUDA-event timing, inputs resident, median of 5; each entry names its algorithmic bytes/point."""
+    from materialmodels_jl_b200 import synth as sy
+
+    out = {}
+
+    def rec(name, N, bpp, ms, **kw):
+        gbs = bpp * N / (ms * 1e-3) / 1e9
+        out[name] = dict(points=N, ms=round(ms, 4), updates_per_s=N / (ms * 1e-3), bytes_per_point=bpp, GBps=round(gbs, 1), frac_of_hbm_peak=round(gbs / peak, 3), **kw)
+
+    try:
+        m = mm.LinearElastic(E=200e3, ν=0.3)
+        nc, lo, hi, seed = sy.c1_strain()
+        for N in (10**6, 10**8):
+            eps = mm.synth_uniform(N, nc, seed, lo, hi, device=dev)
+            rec("c0_linear_elastic_sigma_only_%.0e" % N, N, 96, _time_kernel(torch, lambda: mm.material_response(m, eps, tangent=False)))
+            del eps
+        N = 10**8
+        nc, lo, hi, seed = sy.c3_defgrad()
+        F = mm.synth_uniform(N, nc, seed, lo, hi, device=dev)
+        for name, prm in (("NeoHook", sy.NEOHOOK_PARAMS), ("Yeoh", sy.YEOH_PARAMS)):
+            hm = getattr(mm, name)(λ=prm["lambda_"], μ=prm["mu"], c2=prm["c2"], c3=prm["c3"])
+            rec("c2_%s_from_F" % name.lower(), N, 408, _time_kernel(torch, lambda: mm.material_response(mm.dSdC(), hm, mm.DeformationGradient(F))))
+        del F
+        torch.cuda.empty_cache()
+        x = sy.XU_PARAMS
+        xm = mm.XuNeedleman(σₘₐₓ=x["sigma_max"], τₘₐₓ=x["tau_max"], Φₙ=mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]),
+                            Φₜ=mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), Δₙˢ=x["Delta_n_star"])
+        nc, lo, hi, seed = sy.c5_jump()
+        D = mm.synth_uniform(N, nc, seed, lo, hi, device=dev)
+        rec("c4_xu_needleman_3d", N, 120, _time_kernel(torch, lambda: mm.material_response(xm, D)))
+        del D
+        torch.cuda.empty_cache()
+        N = 10**7
+        cm = mm.CrystalViscoPlastic(slipsystems=mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES), **sy.CRYSTAL_PARAMS)
+        nc, lo, hi, seed = sy.c4_strain_increment(0)
+        dA = mm.synth_uniform(N, nc, seed, lo, hi, device=dev)
+        _, _, stA = mm.material_response(cm, dA, mm.initial_material_state(cm, N, device=dev), 1.0)
+        nc, lo, hi, seed = sy.c4_strain_increment(1)
+        dB = mm.synth_uniform(N, nc, seed, lo, hi, device=dev)
+        ms = _time_kernel(torch, lambda: mm.material_response(cm, dB, stA, 1.0, options={"defer_check": True}), reps=3, warm=1)
+        _, _, stB = mm.material_response(cm, dB, stA, 1.0, options={"defer_check": True})
+        it = stB.iters.float()
+        # flops of the REFERENCE algorithm per point (dense 12x12): per Newton update LU 1152 + solves 288 + Jacobian/residual 1392;
+        # final evaluation 1392; tangent (inv(J), dR/dε, 12 outer products) 6100  -> DESIGN.md §4.5
+        ref_flops = float((it * 2832.0 + 1392.0 + 6100.0).sum().item())
+        f64 = fp64_peak_tflops()
+        rec("c3_crystal_fcc12_stepB", N, 1056, ms, mean_newton_updates=float(it.mean().item()), frac_points_with_active_slip=float((stB.flags != 0).float().mean().item()),
+            n_not_converged=int(stB.n_fail.item()), reference_algorithm_tflops=round(ref_flops / (ms * 1e-3) / 1e12, 2), fp64_fma_peak_tflops_measured=f64,
+            bound="fp64 / latency (not HBM): see profiles/r01_crystal_persistent_ncu_full.txt")
+    except Exception as e:       # informational block must never cost the headline line
+        out["error"] = repr(e)
+    return out
 
 
 def stB_slice_host(stB, mm, m, epsB, stA, Ne):
