@@ -29,6 +29,7 @@ struct CrystalK {
     double a_h, b_h;
     double Cmp[6][6];                 // (Eᵉ)⁻¹ as a 6x6 on storage components (raw inverse of Ee[I][J])
     double isc, dtm_sc, hk_ai;        // 1/σ_c, Δt m/σ_c, H_kin/α_∞
+    double mits, tol2_lo, tol2_hi;    // −1/t*, tol²(1 ∓ 8 eps)
     int h_struct;                     // 1 if H has the form above (else only the general path applies)
     int m_int;                        // m if it is an integer in [2,64] (x^(m-1) by multiplications), else 0 (pow)
 };
@@ -72,6 +73,7 @@ inline void make_crystal_k(CrystalK& k, double E, double nu, double tau_y, doubl
             }
     }
     k.isc = 1.0 / sigma_c; k.dtm_sc = dt * m / sigma_c; k.hk_ai = H_kin / alpha_inf;
+    k.mits = -1.0 / t_star; k.tol2_lo = tol * tol * (1.0 - 1.8e-15); k.tol2_hi = tol * tol * (1.0 + 1.8e-15);
     k.m_int = (m >= 2.0 && m <= 64.0 && m == (double)(int)m) ? (int)m : 0;
 }
 
@@ -361,7 +363,7 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
         const double red = tau - al;
         const double sgn = (red > 0.0) ? 1.0 : ((red < 0.0) ? -1.0 : 0.0);
         const double Phi = fabs(red) - k.tau_y - kap;                                    // :110
-        double Ri = -k.t_star * xi, p = 0.0;
+        double Ri = -k.t_star * xi, p = 0.0, invD = k.mits;                            // inactive: D_ii = −t*
         if (Phi > 0.0) {                                                                // ⟨Φ⟩ = (Φ+|Φ|)/2
             const double xx = Phi * k.isc;
             const double pw1 = k.m_int ? powi_(xx, k.m_int - 1) : pow(xx, k.m - 1.0);
@@ -369,14 +371,14 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
             p = k.dtm_sc * pw1;
             mask |= (1u << i);
             flip = flip | (sgn != si);
+            const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
+            // D_ii = −dD.  The Woodbury split needs D safely invertible: dD >= t*/4 (it is >= t* unless an ACTIVE system's
+            // reduced stress has flipped sign against its trial value while a_h < H_kin); otherwise -> pivoted general path.
+            const double dD = k.t_star + p * (sgn * dal + k.a_h);
+            bad = bad | !(dD >= 0.25 * k.t_star);
+            invD = -fast_rcp(dD);
         }
         nrm2 += Ri * Ri;
-        const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
-        // D_ii = −dD.  The Woodbury split needs D safely invertible: dD >= t*/4 (it is >= t* unless an ACTIVE system's
-        // reduced stress has flipped sign against its trial value while a_h < H_kin); otherwise -> pivoted general path.
-        const double dD = k.t_star + p * (sgn * dal + k.a_h);
-        bad = bad | !(dD >= 0.25 * k.t_star);
-        const double invD = -fast_rcp(dD);
         const double ci = p * sgn;
         const double rD = Ri * invD;
         scr(24 + i) = ci; scr(36 + i) = rD; scr(48 + i) = invD;
@@ -392,7 +394,7 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
         const double srD = si * rD;
 #pragma unroll
         for (int c = 0; c < 6; ++c) yr[c] += srD * pw[c];
-        if (HASQ) {
+        if (HASQ && p != 0.0) {
             const double spD = si * (k.b_h * p * invD);
 #pragma unroll
             for (int c = 0; c < 6; ++c) L.yp[c] += spD * pw[c];
@@ -402,7 +404,8 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
     L.flip = flip;
     L.iters = L.it - 1;
     if (L.it > k.max_iter) return true;                                                  // nonlinear_solver.jl:61 (returns nothing)
-    if (sqrt(nrm2) < k.tol) { L.converged = true; return true; }                         // nonlinear_solver.jl:56
+    // norm(r) < tol  (nonlinear_solver.jl:56); the square root is only taken inside a rounding-width band around tol²
+    if (nrm2 < k.tol2_lo || (nrm2 <= k.tol2_hi && sqrt(nrm2) < k.tol)) { L.converged = true; return true; }
     if (bad) { L.bad = true; return true; }
     // x -= J \ r                                                                        nonlinear_solver.jl:59
     double M[36];
@@ -432,12 +435,16 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
     }
 #pragma unroll 1
     for (int i = 0; i < 12; ++i) {
-        const double ci = scr(24 + i), invD = scr(48 + i);
-        double du = 0.0, dv = 0.0;
+        const double ci = scr(24 + i);
+        double d = scr(36 + i);                       // (D⁻¹r)_i ; the Woodbury correction only touches systems with c_i != 0
+        if (ci != 0.0) {
+            const double invD = scr(48 + i);
+            double du = 0.0, dv = 0.0;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; if (HASQ) dv += k.Pw[i][c] * ypl[c]; }
-        double d = scr(36 + i) + invD * ci * du;
-        if (HASQ) d += (k.b_h * fabs(ci) * invD + invD * ci * dv) * fac;
+            for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; if (HASQ) dv += k.Pw[i][c] * ypl[c]; }
+            d += invD * ci * du;
+            if (HASQ) d += (k.b_h * fabs(ci) * invD + invD * ci * dv) * fac;
+        }
         scr(60 + i) -= d;
     }
     L.iters = L.it;
