@@ -126,6 +126,28 @@ int mm_crystal(const MMCrystal* p, const double* deps, double dt, const double* 
 int mm_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, double* dTdD, int dim,
                     int64_t N, int layout, void* stream);
 
+/* ---- dimension wrappers — reference src/wrappers.jl ----------------------------------
+ * material_response(dim::AbstractDim, m, Δε_dim, state, Δt; cache, options): strain-restricted kinds pad the strain with
+ * zeros and cut the 3D result down (wrappers.jl:29-41); stress-restricted kinds iterate the out-of-plane strains until
+ * the out-of-plane stresses vanish (options :plane_stress_tol = 1e-8 on the Mandel 2-norm, :plane_stress_max_iter = 10)
+ * and return the Schur-complement tangent (wrappers.jl:45-79).  Reduced storage = Tensors.jl SymmetricTensor{2,d}/{4,d}:
+ * nc = mm_wrap_ncomp(kind) = 1, 3 (11,21,22), or 6; tangent nc*nc with index I + nc*J.  MM_DIM_SHELL_STRESS keeps the
+ * full 3D storage with zero 33-rows/columns (wrappers.jl:131-146).
+ * flags (Plastic): MM_FLAG_PLASTIC / MM_FLAG_FAILED of the LAST inner evaluation, MM_FLAG_WRAPPER_FAILED when the outer
+ * Newton did not converge ("Not converged. Could not find plane stress state.", wrappers.jl:78). */
+#define MM_DIM_UNIAXIAL_STRAIN 1 /* UniaxialStrain{1}  wrappers.jl:4  */
+#define MM_DIM_PLANE_STRAIN 2    /* PlaneStrain{2}     wrappers.jl:6  */
+#define MM_DIM_UNIAXIAL_STRESS 3 /* UniaxialStress{1}  wrappers.jl:5  */
+#define MM_DIM_PLANE_STRESS 4    /* PlaneStress{2}     wrappers.jl:7  */
+#define MM_DIM_SHELL_STRESS 5    /* ShellStress{3}     wrappers.jl:8  */
+#define MM_FLAG_WRAPPER_FAILED 0x40
+int mm_wrap_ncomp(int dim_kind);
+int mm_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const double* eps_red, double* sig_red, double* tan_red,
+                              uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
+int mm_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red,
+                       double* state_out, uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
+                       const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
+
 /* Deterministic synthetic inputs (bench + parity harness): out(i,c) = lo[c] + (hi[c]-lo[c]) * u(i,c),
  * u(i,c) = (splitmix64(seed + i*nc + c) >> 11) * 2^-53.  lo/hi are HOST arrays of nc doubles. */
 int mm_synth_uniform(double* out, int64_t N, int nc, int layout, uint64_t seed, const double* lo, const double* hi,

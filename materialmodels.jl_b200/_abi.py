@@ -12,6 +12,8 @@ MM_FCC, MM_BCC = 0, 1
 MM_FLAG_PLASTIC = 0x01
 MM_FLAG_FAILED = 0x80
 MM_ACTIVE_FAILED = 0x8000
+MM_FLAG_WRAPPER_FAILED = 0x40
+MM_DIM_UNIAXIAL_STRAIN, MM_DIM_PLANE_STRAIN, MM_DIM_UNIAXIAL_STRESS, MM_DIM_PLANE_STRESS, MM_DIM_SHELL_STRESS = 1, 2, 3, 4, 5
 
 
 class MMLinearElastic(C.Structure):
@@ -59,6 +61,10 @@ SIGNATURES = {
     "mm_hyper": (C.c_int, [C.c_int, C.POINTER(MMHyper), _P, C.c_int, _P, _P, _I64, C.c_int, _P]),
     "mm_crystal": (C.c_int, [C.POINTER(MMCrystal), _P, C.c_double, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int, _P]),
     "mm_xu_needleman": (C.c_int, [C.POINTER(MMXuNeedleman), _P, _P, _P, C.c_int, _I64, C.c_int, _P]),
+    "mm_wrap_ncomp": (C.c_int, [C.c_int]),
+    "mm_wrapped_linear_elastic": (C.c_int, [C.c_int, C.POINTER(MMLinearElastic), _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int, _P]),
+    "mm_wrapped_plastic": (C.c_int, [C.c_int, C.POINTER(MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), C.POINTER(MMNewtonOpts),
+                                     _I64, C.c_int, _P]),
     "mm_synth_uniform": (C.c_int, [_P, _I64, C.c_int, C.c_int, C.c_uint64, _P, _P, _P]),
     "mmh_alloc_pinned": (_P, [C.c_uint64]),
     "mmh_free_pinned": (None, [_P]),

@@ -17,10 +17,11 @@ import numpy as np
 
 from . import _abi
 from ._lib import check, load
-from .materials import (AbstractMaterialState, AbstractTangent, CrystalViscoPlastic, DeformationGradient, LinearElastic,
+from .materials import (AbstractDim, AbstractMaterialState, AbstractTangent, CrystalViscoPlastic, DeformationGradient, LinearElastic,
                         Plastic, RightCauchyGreen, StrainMeasure, XuNeedleman, _Hyper, dSdC)
 
 NOT_CONVERGED = "Material model not converged. Could not find material state."   # Plastic.jl:157, CrystalViscoPlastic.jl:92
+PLANE_STRESS_NOT_CONVERGED = "Not converged. Could not find plane stress state."    # wrappers.jl:78
 
 _LAYOUTS = {"soa": _abi.MM_LAYOUT_SOA, "aos": _abi.MM_LAYOUT_AOS, 0: 0, 1: 1}
 
@@ -347,6 +348,61 @@ def _response_xu(m, Δ, state, layout, want_tangent):
     return T, H, state
 
 
+def _response_wrapped(dim, m, Δε, state, options, layout, want_tangent):
+    """material_response(dim::AbstractDim, m, Δε, state, Δt; cache, options) — reference src/wrappers.jl:29-79
+    (device arrays only; LinearElastic and Plastic)."""
+    kind = dim.KIND
+    nc = load().mm_wrap_ncomp(kind)
+    wtol, wmax = 1e-8, 10                                            # wrappers.jl:55-56
+    if options:
+        wtol = float(options.get("plane_stress_tol", options.get(":plane_stress_tol", wtol)))
+        wmax = int(options.get("plane_stress_max_iter", options.get(":plane_stress_max_iter", wmax)))
+    w = _abi.MMNewtonOpts(wtol, wmax, 0)
+    if isinstance(m, Plastic):
+        layout = state.layout
+    Δε = _prep(Δε)
+    if _is_host(Δε):
+        raise NotImplementedError("dimension wrappers: device (torch CUDA) arrays only")
+    N = _npoints(Δε, nc, layout)
+    torch = _torch()
+    σ = _empty(_shape(nc, N, layout), Δε)
+    tan = _empty(_shape(nc * nc, N, layout), Δε) if want_tangent else None
+    oit = _empty((N,), Δε, torch.uint8)
+    nfail = _zeros((1,), Δε, torch.int32)
+    lib = load()
+    defer = bool(options and options.get("defer_check"))
+    with _DeviceGuard(Δε):
+        if isinstance(m, LinearElastic):
+            rc = lib.mm_wrapped_linear_elastic(kind, ctypes.byref(m._c), _ptr(Δε), _ptr(σ), _ptr(tan), _ptr(oit), _ptr(nfail), ctypes.byref(w),
+                                               N, _LAYOUTS[layout], _stream(Δε))
+            check(rc, "mm_wrapped_linear_elastic")
+            new = state if state is not None else LinearElasticState()
+            flags = None
+        elif isinstance(m, Plastic):
+            if state is None or N != state.N:
+                raise ValueError("material_response(dim, ::Plastic, Δε, state): state with %d points required" % N)
+            sin = _prep(state.data)
+            sout = _empty(_shape(14, N, layout), Δε)
+            flags = _empty((N,), Δε, torch.uint8)
+            iters = _empty((N,), Δε, torch.uint8)
+            o = _newton_opts(m, options)
+            rc = lib.mm_wrapped_plastic(kind, ctypes.byref(m._c), _ptr(Δε), _ptr(sin), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(flags), _ptr(iters),
+                                        _ptr(oit), _ptr(nfail), ctypes.byref(o), ctypes.byref(w), N, _LAYOUTS[layout], _stream(Δε))
+            check(rc, "mm_wrapped_plastic")
+            new = PlasticState(sout, layout)
+            new.flags, new.iters, new.n_fail = flags, iters, nfail
+        else:
+            raise NotImplementedError("dimension wrappers are implemented for LinearElastic and Plastic")
+    if hasattr(new, "__dict__"):
+        new.outer_iters = oit
+        new.n_fail = nfail
+    if not defer and int(nfail.item()) != 0:
+        if flags is None or bool((flags & _abi.MM_FLAG_WRAPPER_FAILED).any().item()):
+            raise RuntimeError(PLANE_STRESS_NOT_CONVERGED)
+        raise RuntimeError(NOT_CONVERGED)
+    return σ, tan, new
+
+
 def material_response(*args, cache=None, options=None, layout="soa", tangent=True, out=None):
     """material_response(m, strain, state=None, Δt=None, cache=None, options=None)
     material_response(dSdC(), m, DeformationGradient(F) | RightCauchyGreen(C), state=None, Δt=0.0)
@@ -356,6 +412,12 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
     `tangent=False` skips the 36-component tangent output (returns None in its place);
     `out` (Plastic) = dict of preallocated output buffers: stress, tangent, state, flags, iters."""
     args = list(args)
+    if args and isinstance(args[0], AbstractDim):                            # src/wrappers.jl:29-79
+        dim = args.pop(0)
+        m = args.pop(0)
+        strain = args.pop(0)
+        state = args.pop(0) if args else None
+        return _response_wrapped(dim, m, strain, state, options, layout, tangent)
     if args and isinstance(args[0], AbstractTangent):                       # src/traits.jl:91-107
         out_tangent = args.pop(0)
         m = args.pop(0)

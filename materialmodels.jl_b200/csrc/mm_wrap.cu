@@ -1,0 +1,109 @@
+// Device-pointer entry points of the dimension wrappers (reference src/wrappers.jl) around LinearElastic and Plastic.
+#include <cuda_runtime.h>
+#include "../../include/mmb200.h"
+#include "mm_kernels.cuh"
+#include "mm_wrap_math.cuh"
+
+namespace mm {
+
+template <int KIND> struct WrappedElasticOp {
+    static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;
+    __host__ __device__ static constexpr int in_nc(int) { return wrap_nc(KIND); }
+    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? wrap_nc(KIND) : wrap_nc(KIND) * wrap_nc(KIND); }
+    ElasticK k;
+    double tol; int max_iter;
+    uint8_t* outer_iters;
+    int32_t* n_fail;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
+        int oit = 0, iit = 0;
+        const ElasticK kk = k;
+        const int flag = wrapped_point<KIND, 0>([&](RegIO<0>& io, int*) { linear_elastic_point(kk, io); return 0; }, acc, tol, max_iter, &oit, &iit);
+        if (outer_iters) outer_iters[i] = (uint8_t)oit;
+        if (flag && n_fail) atomicAdd(n_fail, 1);
+    }
+};
+
+template <int KIND> struct WrappedPlasticOp {
+    static constexpr int NIN = 2, NOUT = 3, SCRATCH = 0;
+    __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? wrap_nc(KIND) : 14; }
+    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? wrap_nc(KIND) : (a == 1 ? wrap_nc(KIND) * wrap_nc(KIND) : 14); }
+    PlasticK k;
+    double tol; int max_iter;
+    uint8_t* flags;
+    uint8_t* iters;
+    uint8_t* outer_iters;
+    int32_t* n_fail;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
+        int oit = 0, iit = 0;
+        const PlasticK kk = k;
+        const int flag = wrapped_point<KIND, 14>([&](RegIO<14>& io, int* it) { return plastic_point(kk, io, it); }, acc, tol, max_iter, &oit, &iit);
+        if (flags) flags[i] = (uint8_t)flag;
+        if (iters) iters[i] = (uint8_t)(iit > 255 ? 255 : iit);
+        if (outer_iters) outer_iters[i] = (uint8_t)oit;
+        if ((flag & 0xC0) && n_fail) atomicAdd(n_fail, 1);
+    }
+};
+template <int KIND> struct MinBlocks<WrappedPlasticOp<KIND>> { static constexpr int value = 2, block = 128; };
+
+template <int KIND>
+int launch_wrapped_elastic(const MMLinearElastic* p, const double* eps, double* sig, double* tan, uint8_t* oit, int32_t* n_fail, const MMNewtonOpts* w,
+                           int64_t N, int layout, cudaStream_t st) {
+    WrappedElasticOp<KIND> op;
+    op.k = make_elastic_k(p->E, p->nu); op.tol = w ? w->tol : 1e-8; op.max_iter = w ? w->max_iter : 10; op.outer_iters = oit; op.n_fail = n_fail;
+    Ptrs<1, 2> ptrs; ptrs.in[0] = eps; ptrs.out[0] = sig; ptrs.out[1] = tan;
+    return launch_points<WrappedElasticOp<KIND>, 256, 128>(op, ptrs, N, layout, st, "mm_wrapped_linear_elastic");
+}
+template <int KIND>
+int launch_wrapped_plastic(const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags, uint8_t* iters,
+                           uint8_t* oit, int32_t* n_fail, const MMNewtonOpts* o, const MMNewtonOpts* w, int64_t N, int layout, cudaStream_t st) {
+    WrappedPlasticOp<KIND> op;
+    op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, o ? o->tol : 1e-8, o ? o->max_iter : 1000);
+    op.tol = w ? w->tol : 1e-8; op.max_iter = w ? w->max_iter : 10;
+    op.flags = flags; op.iters = iters; op.outer_iters = oit; op.n_fail = n_fail;
+    Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = sin; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = sout;
+    return launch_points<WrappedPlasticOp<KIND>, 128, 64>(op, ptrs, N, layout, st, "mm_wrapped_plastic");
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" {
+
+int mm_wrap_ncomp(int dim_kind) {
+    if (dim_kind < MM_DIM_UNIAXIAL_STRAIN || dim_kind > MM_DIM_SHELL_STRESS) return set_error(MM_ERR_ARG, "mm_wrap_ncomp: unknown dim_kind %d", dim_kind);
+    return wrap_nc(dim_kind);
+}
+
+int mm_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const double* eps_red, double* sig_red, double* tan_red, uint8_t* outer_iters,
+                              int32_t* n_fail, const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!eps_red || !sig_red))) return set_error(MM_ERR_ARG, "mm_wrapped_linear_elastic: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dim_kind) {
+        case MM_DIM_UNIAXIAL_STRAIN: return launch_wrapped_elastic<WRAP_UNIAXIAL_STRAIN>(p, eps_red, sig_red, tan_red, outer_iters, n_fail, wrapper_opts, N, layout, st);
+        case MM_DIM_PLANE_STRAIN: return launch_wrapped_elastic<WRAP_PLANE_STRAIN>(p, eps_red, sig_red, tan_red, outer_iters, n_fail, wrapper_opts, N, layout, st);
+        case MM_DIM_UNIAXIAL_STRESS: return launch_wrapped_elastic<WRAP_UNIAXIAL_STRESS>(p, eps_red, sig_red, tan_red, outer_iters, n_fail, wrapper_opts, N, layout, st);
+        case MM_DIM_PLANE_STRESS: return launch_wrapped_elastic<WRAP_PLANE_STRESS>(p, eps_red, sig_red, tan_red, outer_iters, n_fail, wrapper_opts, N, layout, st);
+        case MM_DIM_SHELL_STRESS: return launch_wrapped_elastic<WRAP_SHELL_STRESS>(p, eps_red, sig_red, tan_red, outer_iters, n_fail, wrapper_opts, N, layout, st);
+    }
+    return set_error(MM_ERR_ARG, "mm_wrapped_linear_elastic: unknown dim_kind %d", dim_kind);
+}
+
+int mm_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red, double* state_out,
+                       uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts, const MMNewtonOpts* wrapper_opts,
+                       int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!eps_red || !state_in || !sig_red || !state_out))) return set_error(MM_ERR_ARG, "mm_wrapped_plastic: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+#define MM_WP(K) return launch_wrapped_plastic<K>(p, eps_red, state_in, sig_red, tan_red, state_out, flags, iters, outer_iters, n_fail, opts, wrapper_opts, N, layout, st)
+    switch (dim_kind) {
+        case MM_DIM_UNIAXIAL_STRAIN: MM_WP(WRAP_UNIAXIAL_STRAIN);
+        case MM_DIM_PLANE_STRAIN: MM_WP(WRAP_PLANE_STRAIN);
+        case MM_DIM_UNIAXIAL_STRESS: MM_WP(WRAP_UNIAXIAL_STRESS);
+        case MM_DIM_PLANE_STRESS: MM_WP(WRAP_PLANE_STRESS);
+        case MM_DIM_SHELL_STRESS: MM_WP(WRAP_SHELL_STRESS);
+    }
+#undef MM_WP
+    return set_error(MM_ERR_ARG, "mm_wrapped_plastic: unknown dim_kind %d", dim_kind);
+}
+
+}  // extern "C"

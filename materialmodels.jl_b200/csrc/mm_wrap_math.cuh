@@ -1,0 +1,180 @@
+// Dimension wrappers — reference src/wrappers.jl:1-162, fused around the 3D point functions of mm_math.cuh.
+//   strain-restricted (UniaxialStrain{1}, PlaneStrain{2}): pad the strain with zeros, one 3D evaluation, cut σ and ∂σ∂ε
+//   down to dimension d (:29-41);
+//   stress-restricted (UniaxialStress{1}, PlaneStress{2}, ShellStress{3}): outer Newton on the out-of-plane strain
+//   components until the out-of-plane stresses vanish (2-norm of their Mandel vector < tol, default 1e-8, max_iter 10),
+//   tangent = Schur complement of the Mandel 6x6 (:45-79).
+// The inner model runs on a REGISTER accessor (RegIO): its σ, ∂σ∂ε and new state never leave the thread between outer
+// iterations; only the reduced quantities are stored.  Reduced storage = Tensors.jl SymmetricTensor{2,d}/{4,d}:
+// d = 1: (11);  d = 2: (11,21,22), 9 = I + 3J;  ShellStress keeps the full 3D storage with zero 33-rows/columns (:131-146).
+#pragma once
+#include "mm_math.cuh"
+
+namespace mm {
+
+enum { WRAP_UNIAXIAL_STRAIN = 1, WRAP_PLANE_STRAIN = 2, WRAP_UNIAXIAL_STRESS = 3, WRAP_PLANE_STRESS = 4, WRAP_SHELL_STRESS = 5 };
+
+MM_HD constexpr int wrap_dim(int kind) { return (kind == WRAP_UNIAXIAL_STRAIN || kind == WRAP_UNIAXIAL_STRESS) ? 1 : ((kind == WRAP_SHELL_STRESS) ? 3 : 2); }
+MM_HD constexpr int wrap_nc(int kind) { return wrap_dim(kind) * (wrap_dim(kind) + 1) / 2; }
+// 3D storage slot (11,21,31,22,32,33) of reduced storage slot r
+MM_HD constexpr int wrap_slot(int d, int r) { return d == 1 ? 0 : (d == 2 ? (r == 0 ? 0 : (r == 1 ? 1 : 3)) : r); }
+// 3D storage slot of Mandel position [11,22,33,23,13,12]
+MM_HD constexpr int slot_of_mandel(int m) { return m == 0 ? 0 : (m == 1 ? 3 : (m == 2 ? 5 : (m == 3 ? 4 : (m == 4 ? 2 : 1)))); }
+// Mandel index sets of the restricted-stress kinds (wrappers.jl:149-162, 0-based)
+MM_HD constexpr int wrap_nzero(int kind) { return kind == WRAP_PLANE_STRESS ? 3 : (kind == WRAP_UNIAXIAL_STRESS ? 5 : 1); }
+MM_HD constexpr int wrap_zero(int kind, int a) { return kind == WRAP_PLANE_STRESS ? 2 + a : (kind == WRAP_UNIAXIAL_STRESS ? 1 + a : 2); }
+MM_HD constexpr int wrap_nz(int kind, int a) {
+    return kind == WRAP_PLANE_STRESS ? (a == 0 ? 0 : (a == 1 ? 1 : 5)) : (kind == WRAP_UNIAXIAL_STRESS ? 0 : (a < 2 ? a : a + 1));
+}
+// reduced storage slot of the a-th non-zero Mandel position
+MM_HD constexpr int wrap_red_of_nz(int kind, int a) {
+    return kind == WRAP_PLANE_STRESS ? (a == 0 ? 0 : (a == 1 ? 2 : 1)) : (kind == WRAP_UNIAXIAL_STRESS ? 0 : slot_of_mandel(wrap_nz(kind, a)));
+}
+MM_HD constexpr double mandel_f(int m) { return m < 3 ? 1.0 : 1.4142135623730950488; }
+
+// register-resident accessor for one inner 3D evaluation (NS = number of state doubles of the inner model)
+template <int NS> struct RegIO {
+    double eps[6];
+    double st_in[NS > 0 ? NS : 1];
+    double sig[6], tan[36];
+    double st_out[NS > 0 ? NS : 1];
+    template <int A> MM_HD double in(int c) const { return A == 0 ? eps[c] : st_in[c]; }
+    template <int A> MM_HD void out(int c, double v) { if (A == 0) sig[c] = v; else if (A == 1) tan[c] = v; else st_out[c] = v; }
+    template <int A> MM_HD bool has_out() const { return true; }
+};
+
+// solve A X = B in place (A: n x n row-major, B: n x m row-major) by Gaussian elimination with partial pivoting;
+// everything statically indexed so it stays in registers.  false on a zero pivot.
+template <int n, int m> MM_HD bool small_solve(double* A, double* B) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+#pragma unroll
+        for (int i = k + 1; i < n; ++i) {            // bring the largest |A[i][k]| to row k
+            if (fabs(A[i * n + k]) > fabs(A[k * n + k])) {
+#pragma unroll
+                for (int j = k; j < n; ++j) { const double t = A[k * n + j]; A[k * n + j] = A[i * n + j]; A[i * n + j] = t; }
+#pragma unroll
+                for (int j = 0; j < m; ++j) { const double t = B[k * m + j]; B[k * m + j] = B[i * m + j]; B[i * m + j] = t; }
+            }
+        }
+        const double pv = A[k * n + k];
+        ok = ok & (pv != 0.0);
+        const double ip = 1.0 / pv;
+#pragma unroll
+        for (int i = k + 1; i < n; ++i) {
+            const double l = A[i * n + k] * ip;
+#pragma unroll
+            for (int j = k + 1; j < n; ++j) A[i * n + j] -= l * A[k * n + j];
+#pragma unroll
+            for (int j = 0; j < m; ++j) B[i * m + j] -= l * B[k * m + j];
+        }
+    }
+#pragma unroll
+    for (int k = n - 1; k >= 0; --k) {
+        const double ip = 1.0 / A[k * n + k];
+#pragma unroll
+        for (int j = 0; j < m; ++j) {
+            double s = B[k * m + j];
+#pragma unroll
+            for (int i = k + 1; i < n; ++i) s -= A[k * n + i] * B[i * m + j];
+            B[k * m + j] = s * ip;
+        }
+    }
+    return ok;
+}
+
+// status bits returned: 0x80 inner model failed, 0x40 outer Newton not converged ("Could not find plane stress state")
+// inner(io, &inner_iters) -> inner flag bits (0x80 = failed).  acc: in<0> reduced strain, in<1> state (NS > 0),
+// out<0> reduced stress, out<1> reduced tangent (optional), out<2> new state (NS > 0).
+template <int KIND, int NS, class Inner, class Acc>
+MM_HD int wrapped_point(Inner&& inner, Acc& acc, double tol, int max_iter, int* outer_iters, int* inner_iters) {
+    constexpr int d = wrap_dim(KIND), nc = wrap_nc(KIND);
+    RegIO<NS> io;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) io.eps[c] = 0.0;
+#pragma unroll
+    for (int r = 0; r < nc; ++r) io.eps[wrap_slot(d, r)] = acc.template in<0>(r);               // increase_dim (:24-27)
+#pragma unroll
+    for (int c = 0; c < NS; ++c) io.st_in[c] = acc.template in<1>(c);
+    int flag = 0, oit = 0;
+    if (KIND == WRAP_UNIAXIAL_STRAIN || KIND == WRAP_PLANE_STRAIN) {                              // :29-41
+        flag = inner(io, inner_iters);
+#pragma unroll
+        for (int r = 0; r < nc; ++r) acc.template out<0>(r, io.sig[wrap_slot(d, r)]);
+        if (acc.template has_out<1>()) {
+#pragma unroll
+            for (int b = 0; b < nc; ++b)
+#pragma unroll
+                for (int a = 0; a < nc; ++a) acc.template out<1>(a + nc * b, io.tan[wrap_slot(d, a) + 6 * wrap_slot(d, b)]);
+        }
+    } else {
+        constexpr int nzero = wrap_nzero(KIND), nnz = 6 - nzero;
+        bool done = false;
+        for (int it = 1; it <= max_iter && !done; ++it) {                                         // :60-77
+            flag = inner(io, inner_iters);
+            if (flag & 0x80) break;
+            oit = it - 1;
+            double sm[nzero], nrm2 = 0.0, Jzz[nzero * nzero];
+#pragma unroll
+            for (int a = 0; a < nzero; ++a) {
+                sm[a] = io.sig[slot_of_mandel(wrap_zero(KIND, a))] * mandel_f(wrap_zero(KIND, a));
+                nrm2 += sm[a] * sm[a];
+#pragma unroll
+                for (int b = 0; b < nzero; ++b)
+                    Jzz[a * nzero + b] = io.tan[slot_of_mandel(wrap_zero(KIND, a)) + 6 * slot_of_mandel(wrap_zero(KIND, b))] *
+                                         (mandel_f(wrap_zero(KIND, a)) * mandel_f(wrap_zero(KIND, b)));
+            }
+            if (sqrt(nrm2) < tol) {                                                               // :63-70 Schur complement
+                double X[nzero * nnz];                                                            // inv(M_zz) M_z,nz
+#pragma unroll
+                for (int a = 0; a < nzero; ++a)
+#pragma unroll
+                    for (int b = 0; b < nnz; ++b)
+                        X[a * nnz + b] = io.tan[slot_of_mandel(wrap_zero(KIND, a)) + 6 * slot_of_mandel(wrap_nz(KIND, b))] *
+                                         (mandel_f(wrap_zero(KIND, a)) * mandel_f(wrap_nz(KIND, b)));
+                if (!small_solve<nzero, nnz>(Jzz, X)) flag |= 0x40;
+#pragma unroll
+                for (int r = 0; r < nc; ++r) acc.template out<0>(r, io.sig[wrap_slot(d, r)]);
+                if (acc.template has_out<1>()) {
+                    if (KIND == WRAP_SHELL_STRESS) {
+#pragma unroll
+                        for (int c = 0; c < 36; ++c) if (c % 6 == 5 || c / 6 == 5) acc.template out<1>(c, 0.0);   // zero 33-row/column
+                    }
+#pragma unroll
+                    for (int a = 0; a < nnz; ++a)
+#pragma unroll
+                        for (int b = 0; b < nnz; ++b) {
+                            const double fa = mandel_f(wrap_nz(KIND, a)), fb = mandel_f(wrap_nz(KIND, b));
+                            double v = io.tan[slot_of_mandel(wrap_nz(KIND, a)) + 6 * slot_of_mandel(wrap_nz(KIND, b))] * (fa * fb);
+#pragma unroll
+                            for (int p = 0; p < nzero; ++p)
+                                v -= io.tan[slot_of_mandel(wrap_nz(KIND, a)) + 6 * slot_of_mandel(wrap_zero(KIND, p))] * (fa * mandel_f(wrap_zero(KIND, p))) * X[p * nnz + b];
+                            acc.template out<1>(wrap_red_of_nz(KIND, a) + nc * wrap_red_of_nz(KIND, b), v / (fa * fb));
+                        }
+                }
+                done = true;
+            } else {                                                                              // :72-76 Δε_3D += frommandel(−inv(J) σ)
+                if (!small_solve<nzero, 1>(Jzz, sm)) { flag |= 0x40; break; }
+#pragma unroll
+                for (int a = 0; a < nzero; ++a) io.eps[slot_of_mandel(wrap_zero(KIND, a))] -= sm[a] / mandel_f(wrap_zero(KIND, a));
+                oit = it;
+            }
+        }
+        if (!done && !(flag & 0x80)) flag |= 0x40;                                                // :78
+        if (!done) {                                                                              // failed: still define the outputs
+#pragma unroll
+            for (int r = 0; r < nc; ++r) acc.template out<0>(r, io.sig[wrap_slot(d, r)]);
+            if (acc.template has_out<1>()) {
+#pragma unroll
+                for (int c = 0; c < nc * nc; ++c) acc.template out<1>(c, 0.0);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NS; ++c) acc.template out<2>(c, io.st_out[c]);
+    *outer_iters = oit;
+    return flag;
+}
+
+}  // namespace mm

@@ -182,6 +182,33 @@ class XuNeedleman(AbstractMaterial):
 
 
 # --------------------------------------------------------------------------------------------
+# dimension wrappers (reference src/wrappers.jl:1-15)
+class AbstractDim:
+    KIND = 0
+    DIM = 3
+
+
+class UniaxialStrain(AbstractDim):
+    KIND, DIM = _abi.MM_DIM_UNIAXIAL_STRAIN, 1
+
+
+class UniaxialStress(AbstractDim):
+    KIND, DIM = _abi.MM_DIM_UNIAXIAL_STRESS, 1
+
+
+class PlaneStrain(AbstractDim):
+    KIND, DIM = _abi.MM_DIM_PLANE_STRAIN, 2
+
+
+class PlaneStress(AbstractDim):
+    KIND, DIM = _abi.MM_DIM_PLANE_STRESS, 2
+
+
+class ShellStress(AbstractDim):
+    KIND, DIM = _abi.MM_DIM_SHELL_STRESS, 3
+
+
+# --------------------------------------------------------------------------------------------
 # strain measures and tangent tags (reference src/traits.jl:1-26)
 class StrainMeasure:
     def __init__(self, value):

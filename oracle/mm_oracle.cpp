@@ -225,4 +225,69 @@ int mmo_synth_uniform(double* out, int64_t N, int nc, int layout, uint64_t seed,
     return 0;
 }
 
+// ---- dimension wrappers (reference src/wrappers.jl) ------------------------------------------------------------
+int mmo_wrapped_linear_elastic(int kind, const MMLinearElastic* p, const double* eps_red, double* sig_red, double* tan_red,
+                               uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* wopts, int64_t N, int layout) {
+    LinearElasticM m = make_linear_elastic(p->E, p->nu);
+    const int nc = wrap_ncomp(kind);
+    double tol = wopts ? wopts->tol : 1e-8; int max_iter = wopts ? wopts->max_iter : 10;
+    View ve = V(eps_red, N, nc, layout), vs = V(sig_red, N, nc, layout), vt = V(tan_red, N, nc * nc, layout);
+    int64_t fails = 0;
+#pragma omp parallel for schedule(static) reduction(+ : fails)
+    for (int64_t i = 0; i < N; ++i) {
+        double e[6], s[6], t[36]; int oit = 0;
+        for (int c = 0; c < nc; ++c) e[c] = ve.at(i, c);
+        auto inner = [&](const Sym2<double>& eps3, Sym2<double>& sig, Sym4<double>& tan) { material_response(m, eps3, sig, tan); return 0; };
+        int st = wrapped_response(kind, inner, e, tol, max_iter, s, t, oit);
+        if (st) ++fails;
+        for (int c = 0; c < nc; ++c) vs.at(i, c) = s[c];
+        if (tan_red) for (int c = 0; c < nc * nc; ++c) vt.at(i, c) = t[c];
+        if (outer_iters) outer_iters[i] = (uint8_t)oit;
+    }
+    if (n_fail) *n_fail += (int32_t)fails;
+    return 0;
+}
+
+int mmo_wrapped_plastic(int kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red,
+                        double* state_out, uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail,
+                        const MMNewtonOpts* opts, const MMNewtonOpts* wopts, int64_t N, int layout) {
+    PlasticM m = make_plastic(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf);
+    NewtonOpts o{opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000};
+    const int nc = wrap_ncomp(kind);
+    double tol = wopts ? wopts->tol : 1e-8; int max_iter = wopts ? wopts->max_iter : 10;
+    View ve = V(eps_red, N, nc, layout), vi = V(state_in, N, 14, layout), vs = V(sig_red, N, nc, layout), vt = V(tan_red, N, nc * nc, layout),
+         vo = V(state_out, N, 14, layout);
+    int64_t fails = 0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : fails)
+    for (int64_t i = 0; i < N; ++i) {
+        double e[6], s[6], t[36]; int oit = 0;
+        for (int c = 0; c < 6; ++c) { s[c] = 0; }
+        for (int c = 0; c < 36; ++c) t[c] = 0;
+        for (int c = 0; c < nc; ++c) e[c] = ve.at(i, c);
+        PlasticState st, sn;
+        for (int c = 0; c < 6; ++c) st.ep.a[c] = vi.at(i, c);
+        st.kappa = vi.at(i, 6);
+        for (int c = 0; c < 6; ++c) st.alpha.a[c] = vi.at(i, 7 + c);
+        st.mu = vi.at(i, 13);
+        sn = st;
+        int flag = 0, it = 0;
+        auto inner = [&](const Sym2<double>& eps3, Sym2<double>& sig, Sym4<double>& tan) { return material_response(m, eps3, st, o, sig, tan, sn, flag, it); };
+        int status = wrapped_response(kind, inner, e, tol, max_iter, s, t, oit);
+        if (status == 1) flag |= MM_FLAG_FAILED;
+        if (status == 2) flag |= 0x40;
+        if (status) ++fails;
+        for (int c = 0; c < nc; ++c) vs.at(i, c) = s[c];
+        if (tan_red) for (int c = 0; c < nc * nc; ++c) vt.at(i, c) = t[c];
+        for (int c = 0; c < 6; ++c) vo.at(i, c) = sn.ep.a[c];
+        vo.at(i, 6) = sn.kappa;
+        for (int c = 0; c < 6; ++c) vo.at(i, 7 + c) = sn.alpha.a[c];
+        vo.at(i, 13) = sn.mu;
+        if (flags) flags[i] = (uint8_t)flag;
+        if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if (outer_iters) outer_iters[i] = (uint8_t)oit;
+    }
+    if (n_fail) *n_fail += (int32_t)fails;
+    return 0;
+}
+
 }  // extern "C"

@@ -406,4 +406,105 @@ template <int dim> inline void xu_response(const XuM& m, const double* jump, dou
     for (int b = 0; b < dim; ++b) for (int a = 0; a < dim; ++a) dTdD[a + dim * b] = Phi.d[a].d[b];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dimension wrappers — reference src/wrappers.jl:1-162
+//   strain-restricted (UniaxialStrain{1}, PlaneStrain{2}, Dim{d}): pad the strain with zeros, call the 3D routine,
+//   cut σ and ∂σ∂ε down to dim d                                                                     (:29-41)
+//   stress-restricted (UniaxialStress{1}, PlaneStress{2}, ShellStress{3}): outer Newton on the out-of-plane strain
+//   components until the out-of-plane stresses vanish (tol 1e-8 on the Mandel 2-norm, max_iter 10), tangent by the
+//   Schur complement of the Mandel 6x6                                                                (:45-79)
+// ---------------------------------------------------------------------------------------------
+enum { MMO_UNIAXIAL_STRAIN = 1, MMO_PLANE_STRAIN = 2, MMO_UNIAXIAL_STRESS = 3, MMO_PLANE_STRESS = 4, MMO_SHELL_STRESS = 5 };
+inline int wrap_dim(int kind) { return (kind == MMO_UNIAXIAL_STRAIN || kind == MMO_UNIAXIAL_STRESS) ? 1 : ((kind == MMO_SHELL_STRESS) ? 3 : 2); }
+inline int wrap_ncomp(int kind) { int d = wrap_dim(kind); return d * (d + 1) / 2; }
+// storage slot (in the 3D symmetric storage) of reduced storage slot r of SymmetricTensor{2,d}
+inline int wrap_slot(int d, int r) { static const int m1[1] = {0}, m2[3] = {0, 1, 3}; return d == 1 ? m1[r] : (d == 2 ? m2[r] : r); }
+// 3D storage slot (11,21,31,22,32,33) of Mandel position [11,22,33,23,13,12]
+static const int SLOT_OF_MANDEL[6] = {0, 3, 5, 4, 2, 1};
+
+// generic dense inverse by LU with partial pivoting, n <= 5 (StaticArrays `inv`)
+inline bool small_inverse(int n, const double* A /*col-major n x n*/, double* Ainv) {
+    double LU[25]; int piv[5];
+    for (int i = 0; i < n * n; ++i) LU[i] = A[i];
+    for (int k = 0; k < n; ++k) {
+        int p = k; double amax = std::fabs(LU[k + n * k]);
+        for (int i = k + 1; i < n; ++i) { double v = std::fabs(LU[i + n * k]); if (v > amax) { amax = v; p = i; } }
+        piv[k] = p;
+        if (amax == 0.0) return false;
+        if (p != k) for (int j = 0; j < n; ++j) { double t = LU[k + n * j]; LU[k + n * j] = LU[p + n * j]; LU[p + n * j] = t; }
+        double ip = 1.0 / LU[k + n * k];
+        for (int i = k + 1; i < n; ++i) LU[i + n * k] *= ip;
+        for (int j = k + 1; j < n; ++j) { double akj = LU[k + n * j]; for (int i = k + 1; i < n; ++i) LU[i + n * j] -= LU[i + n * k] * akj; }
+    }
+    for (int j = 0; j < n; ++j) {
+        double e[5]; for (int i = 0; i < n; ++i) e[i] = (i == j) ? 1.0 : 0.0;
+        for (int k = 0; k < n; ++k) { int p = piv[k]; if (p != k) { double t = e[k]; e[k] = e[p]; e[p] = t; } }
+        for (int k = 0; k < n; ++k) for (int i = k + 1; i < n; ++i) e[i] -= LU[i + n * k] * e[k];
+        for (int k = n - 1; k >= 0; --k) { e[k] /= LU[k + n * k]; for (int i = 0; i < k; ++i) e[i] -= LU[i + n * k] * e[k]; }
+        for (int i = 0; i < n; ++i) Ainv[i + n * j] = e[i];
+    }
+    return true;
+}
+
+// Inner: status = inner(eps3d, sig, tan)   (state handling is the caller's: it captures the last temp_state)
+// Outputs: sig_red[nc], tan_red[nc*nc] in the reduced storage of SymmetricTensor{2,d}/{4,d} (ShellStress: full 3D storage
+// with zero 33-rows/columns, wrappers.jl:131-146).  Returns 0 ok, 1 inner failure, 2 outer Newton not converged.
+template <class Inner>
+inline int wrapped_response(int kind, Inner inner, const double* eps_red, double tol, int max_iter, double* sig_red, double* tan_red, int& outer_iters) {
+    const int d = wrap_dim(kind), nc = wrap_ncomp(kind);
+    const double r2 = std::sqrt(2.0);
+    Sym2<double> eps3;
+    for (int r = 0; r < nc; ++r) eps3.a[wrap_slot(d, r)] = eps_red[r];                      // increase_dim (:24-27)
+    Sym2<double> sig; Sym4<double> tan;
+    outer_iters = 0;
+    if (kind == MMO_UNIAXIAL_STRAIN || kind == MMO_PLANE_STRAIN) {                            // :29-41
+        int st = inner(eps3, sig, tan);
+        for (int r = 0; r < nc; ++r) sig_red[r] = sig.a[wrap_slot(d, r)];
+        for (int b = 0; b < nc; ++b) for (int a = 0; a < nc; ++a) tan_red[a + nc * b] = tan.a[wrap_slot(d, a) + 6 * wrap_slot(d, b)];
+        return st ? 1 : 0;
+    }
+    // Mandel index sets (0-based positions in [11,22,33,23,13,12])                        :149-162
+    int zero[5], nz[5], nzero, nnz;
+    if (kind == MMO_PLANE_STRESS)      { nzero = 3; zero[0] = 2; zero[1] = 3; zero[2] = 4; nnz = 3; nz[0] = 0; nz[1] = 1; nz[2] = 5; }
+    else if (kind == MMO_UNIAXIAL_STRESS) { nzero = 5; for (int i = 0; i < 5; ++i) zero[i] = i + 1; nnz = 1; nz[0] = 0; }
+    else                               { nzero = 1; zero[0] = 2; nnz = 5; nz[0] = 0; nz[1] = 1; nz[2] = 3; nz[3] = 4; nz[4] = 5; }
+    auto fm = [&](int m) { return m < 3 ? 1.0 : r2; };
+    for (int it = 1; it <= max_iter; ++it) {                                                // :60-77
+        int st = inner(eps3, sig, tan);
+        if (st) return 1;
+        outer_iters = it - 1;
+        double sm[5], nrm2 = 0;
+        for (int a = 0; a < nzero; ++a) { sm[a] = sig.a[SLOT_OF_MANDEL[zero[a]]] * fm(zero[a]); nrm2 += sm[a] * sm[a]; }
+        double M[36];                                                                        // tomandel(∂σ∂ε)
+        for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) M[a + 6 * b] = tan.a[SLOT_OF_MANDEL[a] + 6 * SLOT_OF_MANDEL[b]] * fm(a) * fm(b);
+        double Jzz[25], Jinv[25];
+        for (int a = 0; a < nzero; ++a) for (int b = 0; b < nzero; ++b) Jzz[a + nzero * b] = M[zero[a] + 6 * zero[b]];
+        if (!small_inverse(nzero, Jzz, Jinv)) return 2;
+        if (std::sqrt(nrm2) < tol) {                                                          // :63-70
+            double mod[25];
+            for (int a = 0; a < nnz; ++a) for (int b = 0; b < nnz; ++b) {
+                double s = M[nz[a] + 6 * nz[b]];
+                for (int p = 0; p < nzero; ++p) for (int q = 0; q < nzero; ++q) s -= M[nz[a] + 6 * zero[p]] * Jinv[p + nzero * q] * M[zero[q] + 6 * nz[b]];
+                mod[a + nnz * b] = s;
+            }
+            for (int r = 0; r < nc; ++r) sig_red[r] = sig.a[wrap_slot(d, r)];
+            for (int i = 0; i < nc * nc; ++i) tan_red[i] = 0.0;
+            for (int a = 0; a < nnz; ++a) for (int b = 0; b < nnz; ++b) {                     // frommandel back to tensor components
+                const int sa = SLOT_OF_MANDEL[nz[a]], sb = SLOT_OF_MANDEL[nz[b]];          // 3D storage slots
+                int ra = -1, rb = -1;
+                for (int r = 0; r < nc; ++r) { if (wrap_slot(d, r) == sa) ra = r; if (wrap_slot(d, r) == sb) rb = r; }
+                tan_red[ra + nc * rb] = mod[a + nnz * b] / (fm(nz[a]) * fm(nz[b]));
+            }
+            return 0;
+        }
+        for (int a = 0; a < nzero; ++a) {                                                     // Δε_3D += frommandel(−inv(J) σ_mandel)
+            double de = 0;
+            for (int b = 0; b < nzero; ++b) de -= Jinv[a + nzero * b] * sm[b];
+            eps3.a[SLOT_OF_MANDEL[zero[a]]] += de / fm(zero[a]);
+        }
+        outer_iters = it;
+    }
+    return 2;                                                                                // "Not converged. Could not find plane stress state." (:78)
+}
+
 }  // namespace mmo

@@ -37,6 +37,9 @@ _SIG = {
     "mmo_solve_scalar_kat": (C.c_int, [C.c_int, C.c_double, _P, _P, _P]),
     "mmo_strain_energy": (C.c_double, [C.c_int, C.POINTER(abi.MMHyper), _P]),
     "mmo_synth_uniform": (C.c_int, [_P, _I64, C.c_int, C.c_int, C.c_uint64, _P, _P]),
+    "mmo_wrapped_linear_elastic": (C.c_int, [C.c_int, C.POINTER(abi.MMLinearElastic), _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
+    "mmo_wrapped_plastic": (C.c_int, [C.c_int, C.POINTER(abi.MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts),
+                                      C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
 }
 
 _lib = None
@@ -190,3 +193,35 @@ def synth_uniform(N, nc, seed, lo, hi, layout=SOA):
     hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, dtype=np.float64), (nc,)))
     lib().mmo_synth_uniform(_ptr(out), N, nc, layout, seed, _ptr(lo), _ptr(hi))
     return out
+
+
+# ---- dimension wrappers (reference src/wrappers.jl) ---------------------------------------------
+UNIAXIAL_STRAIN, PLANE_STRAIN, UNIAXIAL_STRESS, PLANE_STRESS, SHELL_STRESS = 1, 2, 3, 4, 5
+WRAP_NCOMP = {1: 1, 2: 3, 3: 1, 4: 3, 5: 6}
+
+
+def wrapped_linear_elastic(kind, E, nu, eps_red, layout=SOA, tol=1e-8, max_iter=10):
+    nc = WRAP_NCOMP[kind]
+    eps_red, N = _n(eps_red, layout)
+    sig, tan = _alloc(nc, N, layout), _alloc(nc * nc, N, layout)
+    oit, nfail = np.zeros(N, np.uint8), np.zeros(1, np.int32)
+    p = abi.MMLinearElastic(E, nu)
+    w = abi.MMNewtonOpts(tol, max_iter, 0)
+    rc = lib().mmo_wrapped_linear_elastic(kind, C.byref(p), _ptr(eps_red), _ptr(sig), _ptr(tan), _ptr(oit), _ptr(nfail), C.byref(w), N, layout)
+    assert rc == 0
+    return dict(sig=sig, tan=tan, outer_iters=oit, n_fail=int(nfail[0]))
+
+
+def wrapped_plastic(kind, params, eps_red, state, layout=SOA, tol=1e-8, max_iter=1000, wtol=1e-8, wmax_iter=10):
+    nc = WRAP_NCOMP[kind]
+    p = params if isinstance(params, abi.MMPlastic) else abi.MMPlastic(*params)
+    eps_red, N = _n(eps_red, layout)
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    sig, tan, st = _alloc(nc, N, layout), _alloc(nc * nc, N, layout), _alloc(14, N, layout)
+    flags, iters, oit = np.zeros(N, np.uint8), np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+    nfail = np.zeros(1, np.int32)
+    o, w = abi.MMNewtonOpts(tol, max_iter, 0), abi.MMNewtonOpts(wtol, wmax_iter, 0)
+    rc = lib().mmo_wrapped_plastic(kind, C.byref(p), _ptr(eps_red), _ptr(state), _ptr(sig), _ptr(tan), _ptr(st), _ptr(flags), _ptr(iters),
+                                   _ptr(oit), _ptr(nfail), C.byref(o), C.byref(w), N, layout)
+    assert rc == 0
+    return dict(sig=sig, tan=tan, state=st, flags=flags, iters=iters, outer_iters=oit, n_fail=int(nfail[0]))

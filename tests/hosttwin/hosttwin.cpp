@@ -6,6 +6,7 @@
 #include "../../include/mmb200.h"
 #include "../../materialmodels.jl_b200/csrc/mm_math.cuh"
 #include "../../materialmodels.jl_b200/csrc/mm_crystal_math.cuh"
+#include "../../materialmodels.jl_b200/csrc/mm_wrap_math.cuh"
 
 namespace {
 template <int NIN, int NOUT> struct HostAcc {   // SoA host arrays
@@ -79,4 +80,47 @@ int twin_crystal(const MMCrystal* p, const double* deps, double dt, const double
     }
     return 0;
 }
+
+}  // extern "C"
+template <int KIND> static void twin_wrapped_plastic_k(const mm::PlasticK& k, const double* eps, const double* sin, double* sig, double* tan, double* sout,
+                                                       uint8_t* flags, uint8_t* iters, uint8_t* oiters, double wtol, int wmax, int64_t N) {
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<2, 3> a{{eps, sin}, {sig, tan, sout}, N, i};
+        int oit = 0, iit = 0;
+        int f = mm::wrapped_point<KIND, 14>([&](mm::RegIO<14>& io, int* it) { return mm::plastic_point(k, io, it); }, a, wtol, wmax, &oit, &iit);
+        flags[i] = (uint8_t)f; iters[i] = (uint8_t)iit; oiters[i] = (uint8_t)oit;
+    }
+}
+extern "C" int twin_wrapped_plastic(int kind, const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags,
+                         uint8_t* iters, uint8_t* oiters, double tol, int max_iter, double wtol, int wmax, int64_t N) {
+    mm::PlasticK k = mm::make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, tol, max_iter);
+    switch (kind) {
+        case 1: twin_wrapped_plastic_k<1>(k, eps, sin, sig, tan, sout, flags, iters, oiters, wtol, wmax, N); break;
+        case 2: twin_wrapped_plastic_k<2>(k, eps, sin, sig, tan, sout, flags, iters, oiters, wtol, wmax, N); break;
+        case 3: twin_wrapped_plastic_k<3>(k, eps, sin, sig, tan, sout, flags, iters, oiters, wtol, wmax, N); break;
+        case 4: twin_wrapped_plastic_k<4>(k, eps, sin, sig, tan, sout, flags, iters, oiters, wtol, wmax, N); break;
+        case 5: twin_wrapped_plastic_k<5>(k, eps, sin, sig, tan, sout, flags, iters, oiters, wtol, wmax, N); break;
+        default: return -1;
+    }
+    return 0;
+}
+template <int KIND> static void twin_wrapped_elastic_k(const mm::ElasticK& k, const double* eps, double* sig, double* tan, uint8_t* oiters, int64_t N) {
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<1, 2> a{{eps}, {sig, tan}, N, i};
+        int oit = 0, iit = 0;
+        mm::wrapped_point<KIND, 0>([&](mm::RegIO<0>& io, int*) { mm::linear_elastic_point(k, io); return 0; }, a, 1e-8, 10, &oit, &iit);
+        oiters[i] = (uint8_t)oit;
+    }
+}
+extern "C" int twin_wrapped_elastic(int kind, const MMLinearElastic* p, const double* eps, double* sig, double* tan, uint8_t* oiters, int64_t N) {
+    mm::ElasticK k = mm::make_elastic_k(p->E, p->nu);
+    switch (kind) {
+        case 1: twin_wrapped_elastic_k<1>(k, eps, sig, tan, oiters, N); break;
+        case 2: twin_wrapped_elastic_k<2>(k, eps, sig, tan, oiters, N); break;
+        case 3: twin_wrapped_elastic_k<3>(k, eps, sig, tan, oiters, N); break;
+        case 4: twin_wrapped_elastic_k<4>(k, eps, sig, tan, oiters, N); break;
+        case 5: twin_wrapped_elastic_k<5>(k, eps, sig, tan, oiters, N); break;
+        default: return -1;
+    }
+    return 0;
 }

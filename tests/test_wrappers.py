@@ -1,0 +1,158 @@
+"""Dimension wrappers (reference src/wrappers.jl): the oracle against the reference's own tests
+(test/test_wrappers.jl), the kernels' math on the host against the oracle, and the CUDA path against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers as H
+import materialmodels_jl_b200._abi as abi
+import materialmodels_jl_b200.synth as sy
+
+E, NU = 200e3, 0.3
+KINDS = [1, 2, 3, 4, 5]          # UniaxialStrain, PlaneStrain, UniaxialStress, PlaneStress, ShellStress
+NC = {1: 1, 2: 3, 3: 1, 4: 3, 5: 6}
+# strain amplitudes giving a mixed elastic / plastic population per kind
+AMPL = {1: 2.5e-3, 2: 1.0e-3, 3: 2.5e-3, 4: 1.2e-3, 5: 0.8e-3}
+# UniaxialStress: the 1x1 tangent is a Schur complement through a 5x5 block (2.7e5 -> O(1e2..1e5)): cond·eps ~ 1e-11
+TAN_TOL = {1: H.RTOL, 2: H.RTOL, 3: 1e-10, 4: H.RTOL, 5: H.RTOL}
+
+
+# ---- oracle vs the reference's KATs (test_wrappers.jl) ---------------------------------------------
+def test_oracle_wrappers_reference_kats(oracle):
+    rng = np.random.default_rng(11)
+    e = rng.random((1, 5))                                                           # :10-14 UniaxialStress
+    r = oracle.wrapped_linear_elastic(oracle.UNIAXIAL_STRESS, E, NU, e)
+    assert np.allclose(r["tan"][0], E) and np.allclose(r["sig"], E * e) and r["n_fail"] == 0
+    e = rng.random((3, 5))                                                           # :16-21 PlaneStress
+    r = oracle.wrapped_linear_elastic(oracle.PLANE_STRESS, E, NU, e)
+    vo = [0, 2, 1]                                                                   # storage (11,21,22) -> Voigt (11,22,12)
+    ref = E / (1 - NU**2) * np.array([[1, NU, 0], [NU, 1, 0], [0, 0, (1 - NU) / 2]])
+    W = np.array([1.0, 2.0, 1.0])
+    for j in range(5):
+        T = r["tan"][:, j].reshape(3, 3, order="F")
+        assert np.allclose(T[np.ix_(vo, vo)], ref, rtol=1e-12, atol=1e-9)
+        assert np.allclose(r["sig"][:, j], T @ (W * e[:, j]), rtol=1e-12)             # σ ≈ ∂σ∂ε ⊡ Δε
+    e = rng.random((6, 5))                                                           # :23-38 ShellStress
+    r = oracle.wrapped_linear_elastic(oracle.SHELL_STRESS, E, NU, e)
+    a = (1 - NU) / 2
+    ref = E / (1 - NU**2) * np.array([[1, NU, 0, 0, 0, 0], [NU, 1, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0], [0, 0, 0, a, 0, 0], [0, 0, 0, 0, a, 0], [0, 0, 0, 0, 0, a]])
+    vo6 = [0, 3, 5, 4, 2, 1]
+    W6 = np.array([1.0, 2, 2, 1, 2, 1])
+    for j in range(5):
+        T = r["tan"][:, j].reshape(6, 6, order="F")
+        assert np.allclose(T[np.ix_(vo6, vo6)], ref, rtol=1e-12, atol=1e-9)
+        assert abs(r["sig"][5, j]) < 1e-10 * E
+        assert np.allclose(r["sig"][:, j], T @ (W6 * e[:, j]), rtol=1e-11, atol=1e-9)
+    e = rng.random((1, 5))                                                           # :44-50 UniaxialStrain
+    r = oracle.wrapped_linear_elastic(oracle.UNIAXIAL_STRAIN, E, NU, e)
+    e3 = np.zeros((6, 5))
+    e3[0] = e[0]
+    s3, t3 = oracle.linear_elastic(E, NU, e3)
+    assert np.array_equal(r["sig"][0], s3[0]) and np.array_equal(r["tan"][0], t3[0])
+    e = rng.random((3, 5))                                                           # :52-56 PlaneStrain
+    r = oracle.wrapped_linear_elastic(oracle.PLANE_STRAIN, E, NU, e)
+    ref = E / (1 + NU) / (1 - 2 * NU) * np.array([[1 - NU, NU, 0], [NU, 1 - NU, 0], [0, 0, (1 - 2 * NU) / 2]])
+    for j in range(5):
+        T = r["tan"][:, j].reshape(3, 3, order="F")
+        assert np.allclose(T[np.ix_(vo, vo)], ref, rtol=1e-12, atol=1e-9)
+        assert np.allclose(r["sig"][:, j], T @ (W * e[:, j]), rtol=1e-12)
+
+
+def test_oracle_plane_stress_plastic_properties(oracle):
+    """Plastic under PlaneStress / UniaxialStress / ShellStress: the converged 3D stress has vanishing out-of-plane
+    components, the state is the inner model's, and the tangent is consistent with a finite difference of the stress."""
+    p = H.plastic_c()
+    N = 2000
+    for kind in (3, 4, 5):
+        nc = NC[kind]
+        eps = sy.host_uniform(N, nc, 900 + kind, -AMPL[kind], AMPL[kind])
+        r = oracle.wrapped_plastic(kind, p, eps, np.zeros((14, N)))
+        assert r["n_fail"] == 0 and 0.2 < (r["flags"] & 1).mean() < 0.9
+        h = 1e-9
+        for c in range(nc):
+            ep = eps.copy()
+            ep[c] += h
+            rp = oracle.wrapped_plastic(kind, p, ep, np.zeros((14, N)))
+            same = rp["flags"] == r["flags"]
+            fd = (rp["sig"] - r["sig"]) / h
+            col = r["tan"][c * nc:(c + 1) * nc] * (1.0 if c in {1: (0,), 3: (0, 2), 6: (0, 3, 5)}[nc] else 2.0)   # off-diagonal strain slots count twice
+            err = np.linalg.norm(fd[:, same] - col[:, same], axis=0) / np.linalg.norm(col[:, same], axis=0).clip(1.0)
+            assert np.percentile(err, 99) < 2e-3      # FD noise: inner ftol and plane-stress tol are 1e-8 on stresses, h = 1e-9
+
+
+# ---- kernels' math on the host vs the oracle -------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+def test_twin_wrapped_matches_oracle(oracle, kind):
+    tw = H.hosttwin()
+    N = 6000
+    nc = NC[kind]
+    p = H.plastic_c()
+    st = np.zeros((14, N))
+    for step in range(2):
+        eps = sy.host_uniform(N, nc, 777 + kind + 10 * step, -AMPL[kind], AMPL[kind])
+        r = oracle.wrapped_plastic(kind, p, eps, st)
+        sig, tan, so = np.zeros((nc, N)), np.zeros((nc * nc, N)), np.zeros((14, N))
+        fl, it, oi = np.zeros(N, np.uint8), np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+        tw.twin_wrapped_plastic(kind, C.byref(p), H.P(eps), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(fl), H.P(it), H.P(oi),
+                                C.c_double(1e-8), 1000, C.c_double(1e-8), 10, C.c_int64(N))
+        assert r["n_fail"] == 0 and 0.15 < (r["flags"] & 1).mean() < 0.9
+        assert np.array_equal(fl, r["flags"]) and np.array_equal(it, r["iters"]) and np.array_equal(oi, r["outer_iters"])
+        assert H.rel_err(sig, r["sig"]).max() < H.RTOL and H.rel_err(tan, r["tan"]).max() < TAN_TOL[kind]
+        assert np.abs(so - r["state"]).max() < 1e-12 * max(1.0, np.abs(r["state"]).max())
+        st = r["state"]
+    e = sy.host_uniform(500, nc, 5, -1e-3, 1e-3)
+    rr = oracle.wrapped_linear_elastic(kind, E, NU, e)
+    s2, t2, o2 = np.zeros((nc, 500)), np.zeros((nc * nc, 500)), np.zeros(500, np.uint8)
+    tw.twin_wrapped_elastic(kind, C.byref(abi.MMLinearElastic(E, NU)), H.P(e), H.P(s2), H.P(t2), H.P(o2), C.c_int64(500))
+    assert H.rel_err(s2, rr["sig"]).max() < H.RTOL and H.rel_err(t2, rr["tan"]).max() < H.RTOL and np.array_equal(o2, rr["outer_iters"])
+
+
+# ---- CUDA path ------------------------------------------------------------------------------------
+DIMS = {1: "UniaxialStrain", 2: "PlaneStrain", 3: "UniaxialStress", 4: "PlaneStress", 5: "ShellStress"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lname,lay", [("soa", 0), ("aos", 1)])
+@pytest.mark.parametrize("kind", KINDS)
+def test_gpu_wrapped_plastic_and_elastic(mm, cuda_lib, oracle, kind, lname, lay):
+    import torch
+
+    N = 50021
+    nc = NC[kind]
+    dim = getattr(mm, DIMS[kind])()
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    p = H.plastic_c()
+    st = mm.initial_material_state(m, N, layout=lname)
+    st_ref = np.zeros((14, N) if lay == 0 else (N, 14))
+    soa = (lambda a: a) if lay == 0 else (lambda a: np.ascontiguousarray(a.T))
+    for step in range(2):
+        eps = sy.host_uniform(N, nc, 777 + kind + 10 * step, -AMPL[kind], AMPL[kind], layout=lay)
+        r = oracle.wrapped_plastic(kind, p, eps, st_ref, layout=lay)
+        s, t, new = mm.material_response(dim, m, torch.from_numpy(eps).cuda(), st, cache=mm.get_cache(m))
+        assert r["n_fail"] == 0
+        assert np.array_equal(new.flags.cpu().numpy(), r["flags"]), "yield flags differ"
+        assert np.array_equal(new.iters.cpu().numpy(), r["iters"]), "inner Newton counts differ"
+        assert np.array_equal(new.outer_iters.cpu().numpy(), r["outer_iters"]), "outer (plane-stress) iteration counts differ"
+        assert H.rel_err(soa(s.cpu().numpy()), soa(r["sig"])).max() < H.RTOL
+        assert H.rel_err(soa(t.cpu().numpy()), soa(r["tan"])).max() < TAN_TOL[kind]
+        assert np.abs(new.data.cpu().numpy() - r["state"]).max() < 1e-12 * max(1.0, np.abs(r["state"]).max())
+        st, st_ref = new, r["state"]
+    le = mm.LinearElastic(E=E, ν=NU)
+    e = sy.host_uniform(N, nc, 5, -1e-3, 1e-3, layout=lay)
+    rr = oracle.wrapped_linear_elastic(kind, E, NU, e, layout=lay)
+    s, t, _ = mm.material_response(dim, le, torch.from_numpy(e).cuda(), None, layout=lname)
+    assert H.rel_err(soa(s.cpu().numpy()), soa(rr["sig"])).max() < H.RTOL and H.rel_err(soa(t.cpu().numpy()), soa(rr["tan"])).max() < H.RTOL
+
+
+@pytest.mark.gpu
+def test_gpu_plane_stress_failure_raises_reference_error(mm, cuda_lib):
+    import torch
+
+    N = 4000
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    eps = torch.from_numpy(sy.host_uniform(N, 3, 42, -2e-3, 2e-3)).cuda()
+    with pytest.raises(RuntimeError, match="Could not find plane stress state"):       # wrappers.jl:78
+        mm.material_response(mm.PlaneStress(), m, eps, mm.initial_material_state(m, N), options={"plane_stress_max_iter": 1})
+    with pytest.raises(RuntimeError, match="Material model not converged"):             # Plastic.jl:157 (inner)
+        mm.material_response(mm.PlaneStress(), m, eps, mm.initial_material_state(m, N), options={"nlsolve_params": {"iterations": 0}})

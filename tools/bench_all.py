@@ -108,6 +108,21 @@ def main():
             med, mn = timeit(lambda: mm.material_response(m, D, layout=lname), a.reps)
             report("xu_needleman 3D " + lname, N, 120, med, mn)
             del D
+    if want("wrapped"):
+        N = int(1e8 * S)
+        m = mm.Plastic(**sy.PLASTIC_PARAMS)
+        for dim, nc, amp in ((mm.PlaneStress(), 3, 1.2e-3), (mm.UniaxialStress(), 1, 2.5e-3), (mm.ShellStress(), 6, 0.8e-3), (mm.PlaneStrain(), 3, 1.0e-3)):
+            eA = mm.synth_uniform(N, nc, 31, -amp, amp)
+            _, _, stA = mm.material_response(dim, m, eA, mm.initial_material_state(m, N), options={"defer_check": True})
+            eB = mm.synth_uniform(N, nc, 32, -amp, amp)
+            med, mn = timeit(lambda: mm.material_response(dim, m, eB, stA, options={"defer_check": True}), a.reps)
+            _, _, stB = mm.material_response(dim, m, eB, stA, options={"defer_check": True})
+            bpp = 8 * (nc + 14 + nc + nc * nc + 14) + 3
+            report("plastic %s stepB soa" % type(dim).__name__, N, bpp, med, mn,
+                   {"plastic_fraction": round((stB.flags & 1).float().mean().item(), 3), "mean_outer_iters": round(stB.outer_iters.float().mean().item(), 2),
+                    "n_fail": int(stB.n_fail.item())})
+            del eA, eB, stA, stB
+            torch.cuda.empty_cache()
     if want("crystal"):
         N = int(1e7 * S)
         ss = mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES)
