@@ -18,6 +18,13 @@ AMPL = {1: 2.5e-3, 2: 1.0e-3, 3: 2.5e-3, 4: 1.2e-3, 5: 0.8e-3}
 TAN_TOL = {1: H.RTOL, 2: H.RTOL, 3: 1e-10, 4: H.RTOL, 5: H.RTOL}
 
 
+def sig_err(a, b):
+    """stress error against the problem's stress scale: a reduced stress can have a single component that passes through
+    zero (UniaxialStrain / UniaxialStress), where an error relative to its own magnitude is meaningless"""
+    scale = np.maximum(np.linalg.norm(b, axis=0), sy.PLASTIC_PARAMS["sigma_y"])
+    return (np.linalg.norm(a - b, axis=0) / scale).max()
+
+
 # ---- oracle vs the reference's KATs (test_wrappers.jl) ---------------------------------------------
 def test_oracle_wrappers_reference_kats(oracle):
     rng = np.random.default_rng(11)
@@ -98,7 +105,7 @@ def test_twin_wrapped_matches_oracle(oracle, kind):
                                 C.c_double(1e-8), 1000, C.c_double(1e-8), 10, C.c_int64(N))
         assert r["n_fail"] == 0 and 0.15 < (r["flags"] & 1).mean() < 0.9
         assert np.array_equal(fl, r["flags"]) and np.array_equal(it, r["iters"]) and np.array_equal(oi, r["outer_iters"])
-        assert H.rel_err(sig, r["sig"]).max() < H.RTOL and H.rel_err(tan, r["tan"]).max() < TAN_TOL[kind]
+        assert sig_err(sig, r["sig"]) < H.RTOL and H.rel_err(tan, r["tan"]).max() < TAN_TOL[kind]
         assert np.abs(so - r["state"]).max() < 1e-12 * max(1.0, np.abs(r["state"]).max())
         st = r["state"]
     e = sy.host_uniform(500, nc, 5, -1e-3, 1e-3)
@@ -134,7 +141,7 @@ def test_gpu_wrapped_plastic_and_elastic(mm, cuda_lib, oracle, kind, lname, lay)
         assert np.array_equal(new.flags.cpu().numpy(), r["flags"]), "yield flags differ"
         assert np.array_equal(new.iters.cpu().numpy(), r["iters"]), "inner Newton counts differ"
         assert np.array_equal(new.outer_iters.cpu().numpy(), r["outer_iters"]), "outer (plane-stress) iteration counts differ"
-        assert H.rel_err(soa(s.cpu().numpy()), soa(r["sig"])).max() < H.RTOL
+        assert sig_err(soa(s.cpu().numpy()), soa(r["sig"])) < H.RTOL
         assert H.rel_err(soa(t.cpu().numpy()), soa(r["tan"])).max() < TAN_TOL[kind]
         assert np.abs(new.data.cpu().numpy() - r["state"]).max() < 1e-12 * max(1.0, np.abs(r["state"]).max())
         st, st_ref = new, r["state"]
