@@ -55,6 +55,11 @@ extern "C" {
 /* strain measure handed to mm_hyper (`strain_kind`) */
 #define MM_STRAIN_C 0 /* RightCauchyGreen C, 6 comps (native, neohook.jl:35)                       */
 #define MM_STRAIN_F 1 /* DeformationGradient F, 9 comps; C = tdot(F) = FᵀF (src/traits.jl:35-38) */
+#define MM_STRAIN_E 2 /* GreenLagrange E, 6 comps; C = 2E + I (src/traits.jl:43-46)              */
+/* stress / tangent measure returned by mm_hyper_ex (`tangent_kind`), src/traits.jl:14-26, :60-77 */
+#define MM_TANGENT_DSDC 0 /* S (6),  ∂S∂C (36)  — native                                          */
+#define MM_TANGENT_DSDE 1 /* S (6),  ∂S∂E = 2 ∂S∂C (36)                       traits.jl:61-63    */
+#define MM_TANGENT_DPDF 2 /* Pᵀ = S⋅Fᵀ (9, Tensor{2,3}), ∂Pᵀ∂F (81, Tensor{4,3}: i+3j+9k+27l); needs MM_STRAIN_F   traits.jl:67-77 */
 /* crystal structures (slipsystems.jl:3-4) */
 #define MM_FCC 0
 #define MM_BCC 1
@@ -113,6 +118,11 @@ int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, do
  * strain[6 or 9], S[6] (2nd Piola–Kirchhoff), dSdC[36] (may be NULL). */
 int mm_hyper(int model, const MMHyper* p, const double* strain, int strain_kind, double* S, double* dSdC,
              int64_t N, int layout, void* stream);
+
+/* material_response(output_tangent, m, strain::StrainMeasure, state, Δt) — the full trait layer src/traits.jl:91-107
+ * (SURVEY §8(f) rank 2): any strain kind in, any tangent kind out, fused into the hyperelastic kernel. */
+int mm_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent,
+                int64_t N, int layout, void* stream);
 
 /* material_response(::CrystalViscoPlastic{12}, Δε, state, Δt; options) — CrystalViscoPlastic.jl:64-94
  * (+ residuals :97-115, get_state_vars :118-132, solve nonlinear_solver.jl:52-62).

@@ -7,7 +7,8 @@ MM_LAYOUT_AOS = 1
 MM_NSLIP = 12
 MM_OK, MM_ERR_ARG, MM_ERR_CUDA, MM_ERR_NOGPU = 0, -1, -2, -3
 MM_NEOHOOK, MM_YEOH, MM_STVENANT = 0, 1, 2
-MM_STRAIN_C, MM_STRAIN_F = 0, 1
+MM_STRAIN_C, MM_STRAIN_F, MM_STRAIN_E = 0, 1, 2
+MM_TANGENT_DSDC, MM_TANGENT_DSDE, MM_TANGENT_DPDF = 0, 1, 2
 MM_FCC, MM_BCC = 0, 1
 MM_FLAG_PLASTIC = 0x01
 MM_FLAG_FAILED = 0x80
@@ -59,6 +60,7 @@ SIGNATURES = {
     "mm_linear_elastic": (C.c_int, [C.POINTER(MMLinearElastic), _P, _P, _P, _I64, C.c_int, _P]),
     "mm_plastic": (C.c_int, [C.POINTER(MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int, _P]),
     "mm_hyper": (C.c_int, [C.c_int, C.POINTER(MMHyper), _P, C.c_int, _P, _P, _I64, C.c_int, _P]),
+    "mm_hyper_ex": (C.c_int, [C.c_int, C.POINTER(MMHyper), _P, C.c_int, C.c_int, _P, _P, _I64, C.c_int, _P]),
     "mm_crystal": (C.c_int, [C.POINTER(MMCrystal), _P, C.c_double, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int, _P]),
     "mm_xu_needleman": (C.c_int, [C.POINTER(MMXuNeedleman), _P, _P, _P, C.c_int, _I64, C.c_int, _P]),
     "mm_wrap_ncomp": (C.c_int, [C.c_int]),

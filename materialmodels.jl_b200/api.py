@@ -17,8 +17,8 @@ import numpy as np
 
 from . import _abi
 from ._lib import check, load
-from .materials import (AbstractDim, AbstractMaterialState, AbstractTangent, CrystalViscoPlastic, DeformationGradient, LinearElastic,
-                        Plastic, RightCauchyGreen, StrainMeasure, XuNeedleman, _Hyper, dSdC)
+from .materials import (AbstractDim, AbstractMaterialState, AbstractTangent, CrystalViscoPlastic, DeformationGradient, GreenLagrange,
+                        LinearElastic, Plastic, RightCauchyGreen, StrainMeasure, XuNeedleman, _Hyper, dPdF, dSdC, dSdE)
 
 NOT_CONVERGED = "Material model not converged. Could not find material state."   # Plastic.jl:157, CrystalViscoPlastic.jl:92
 PLANE_STRESS_NOT_CONVERGED = "Not converged. Could not find plane stress state."    # wrappers.jl:78
@@ -314,18 +314,21 @@ def _response_crystal(m, Δε, state, Δt, options, want_tangent):
     return σ, tan, new
 
 
-def _response_hyper(m, strain, kind, state, layout, want_tangent):
+def _response_hyper(m, strain, kind, state, layout, want_tangent, tangent_kind=_abi.MM_TANGENT_DSDC):
     strain = _prep(strain)
     nin = 9 if kind == _abi.MM_STRAIN_F else 6
+    ns, nt = (9, 81) if tangent_kind == _abi.MM_TANGENT_DPDF else (6, 36)
     N = _npoints(strain, nin, layout)
-    S = _empty(_shape(6, N, layout), strain)
-    tan = _empty(_shape(36, N, layout), strain) if want_tangent else None
+    S = _empty(_shape(ns, N, layout), strain)
+    tan = _empty(_shape(nt, N, layout), strain) if want_tangent else None
     lib = load()
     with _DeviceGuard(strain):
         if _is_host(strain):
+            if tangent_kind != _abi.MM_TANGENT_DSDC or kind == _abi.MM_STRAIN_E:
+                raise NotImplementedError("host-buffer path: native (S, dSdC) from C or F only; use device arrays for the other trait routes")
             rc = lib.mmh_hyper(m.MODEL, ctypes.byref(m._c), _ptr(strain), kind, _ptr(S), _ptr(tan), N, _LAYOUTS[layout])
         else:
-            rc = lib.mm_hyper(m.MODEL, ctypes.byref(m._c), _ptr(strain), kind, _ptr(S), _ptr(tan), N, _LAYOUTS[layout], _stream(strain))
+            rc = lib.mm_hyper_ex(m.MODEL, ctypes.byref(m._c), _ptr(strain), kind, tangent_kind, _ptr(S), _ptr(tan), N, _LAYOUTS[layout], _stream(strain))
     check(rc, "mm_hyper")
     return S, tan, state
 
@@ -427,15 +430,25 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
             raise TypeError("trait form expects a StrainMeasure (DeformationGradient / RightCauchyGreen)")
         if not isinstance(m, _Hyper):
             raise NotImplementedError("trait route is implemented for NeoHook / Yeoh / StVenant")
-        if not isinstance(out_tangent, dSdC):
-            raise NotImplementedError("%s output: not on the B200 path yet (SURVEY §8(f) 'next')" % type(out_tangent).__name__)
+        if isinstance(out_tangent, dSdC):
+            tk = _abi.MM_TANGENT_DSDC
+        elif isinstance(out_tangent, dSdE):
+            tk = _abi.MM_TANGENT_DSDE
+        elif isinstance(out_tangent, dPdF):
+            tk = _abi.MM_TANGENT_DPDF
+        else:
+            raise NotImplementedError("%s output is not defined for %s" % (type(out_tangent).__name__, type(m).__name__))
         if isinstance(strain, DeformationGradient):
             kind = _abi.MM_STRAIN_F
         elif isinstance(strain, RightCauchyGreen):
             kind = _abi.MM_STRAIN_C
+        elif isinstance(strain, GreenLagrange):
+            kind = _abi.MM_STRAIN_E                                          # traits.jl:43-46
         else:                                                                # traits.jl:120
             raise RuntimeError("%s is not the native strain measure for %s:" % (type(strain).__name__, type(m).__name__))
-        return _response_hyper(m, strain.value, kind, state if state is not None else initial_material_state(m), layout, tangent)
+        if tk == _abi.MM_TANGENT_DPDF and kind != _abi.MM_STRAIN_F:
+            raise TypeError("the dPdF (∂Pᵀ∂F) output needs DeformationGradient(F) as input (traits.jl:67-72)")
+        return _response_hyper(m, strain.value, kind, state if state is not None else initial_material_state(m), layout, tangent, tk)
 
     m = args.pop(0)
     strain = args.pop(0)

@@ -309,10 +309,14 @@ template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* i
 // inv(-C ⊗̄ C) = -C⁻¹ ⊗̄ C⁻¹, which is what is evaluated here.
 // =================================================================================================
 struct HyperK { double lambda, mu, c2, c3; };
-template <int MODEL, int KIND, class Acc> MM_HD void hyper_point(const HyperK& k, Acc& acc) {
+// KIND: 0 = C (RightCauchyGreen), 1 = F (DeformationGradient; C = FᵀF, traits.jl:35-38), 2 = E (GreenLagrange; C = 2E + I, traits.jl:43-46)
+// TAN : 0 = (S, ∂S∂C) native, 1 = (S, ∂S∂E = 2 ∂S∂C) traits.jl:61-63, 2 = (Pᵀ = S⋅Fᵀ, ∂Pᵀ∂F) traits.jl:67-77 (needs KIND = 1):
+//       ∂Pᵀ∂F_ijkl = S_il δ_jk + 2 Σ_n Σ_q F_jn ∂S∂C_inlq F_kq   (the reference's otimesl/otimesu expression, minor symmetry used)
+//       out<0> = Pᵀ(9, column-major), out<1> = ∂Pᵀ∂F(81, i + 3j + 9k + 27l)
+template <int MODEL, int KIND, int TAN, class Acc> MM_HD void hyper_point_ex(const HyperK& k, Acc& acc) {
     double C[6];
+    double F[9];
     if (KIND == 1) {   // F (column-major 9) -> C = FᵀF
-        double F[9];
 #pragma unroll
         for (int c = 0; c < 9; ++c) F[c] = acc.template in<0>(c);
         C[0] = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
@@ -321,6 +325,9 @@ template <int MODEL, int KIND, class Acc> MM_HD void hyper_point(const HyperK& k
         C[3] = F[3] * F[3] + F[4] * F[4] + F[5] * F[5];
         C[4] = F[6] * F[3] + F[7] * F[4] + F[8] * F[5];
         C[5] = F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
+    } else if (KIND == 2) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) C[c] = is_diag_slot(c) ? (2.0 * acc.template in<0>(c) + 1.0) : (2.0 * acc.template in<0>(c));
     } else {
 #pragma unroll
         for (int c = 0; c < 6; ++c) C[c] = acc.template in<0>(c);
@@ -353,28 +360,72 @@ template <int MODEL, int KIND, class Acc> MM_HD void hyper_point(const HyperK& k
             p = 4.0 * k.c2 + 12.0 * k.c3 * i3; q = k.mu - k.lambda * lnJ; r = 0.5 * k.lambda;
         }
     }
+    double S[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-        double v = b * A[c] + g * C[c];
-        if (is_diag_slot(c)) v += a;
-        acc.template out<0>(c, v);
+        S[c] = b * A[c] + g * C[c];
+        if (is_diag_slot(c)) S[c] += a;
     }
-    if (acc.template has_out<1>()) {
-        // full 3x3 view of A for the ⊗̄ product
-        const int SI[6] = {0, 1, 2, 1, 2, 2}, SJ[6] = {0, 0, 0, 1, 1, 2};
-        const int SIDX[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    const int SI[6] = {0, 1, 2, 1, 2, 2}, SJ[6] = {0, 0, 0, 1, 1, 2};
+    const int SIDX[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    if (TAN != 2) {
+        const double tf = (TAN == 1) ? 2.0 : 1.0;
 #pragma unroll
-        for (int J = 0; J < 6; ++J)
+        for (int c = 0; c < 6; ++c) acc.template out<0>(c, S[c]);
+        if (acc.template has_out<1>()) {
 #pragma unroll
-            for (int I = 0; I < 6; ++I) {
-                const int i = SI[I], j = SJ[I], kk = SI[J], l = SJ[J];
-                const double sym_u = 0.5 * (A[SIDX[i][kk]] * A[SIDX[j][l]] + A[SIDX[i][l]] * A[SIDX[j][kk]]);
-                double v = q * sym_u + r * (A[I] * A[J]);
-                if (i == j && kk == l) v += p;
-                acc.template out<1>(I + 6 * J, v);
-            }
+            for (int J = 0; J < 6; ++J)
+#pragma unroll
+                for (int I = 0; I < 6; ++I) {
+                    const int i = SI[I], j = SJ[I], kk = SI[J], l = SJ[J];
+                    const double sym_u = 0.5 * (A[SIDX[i][kk]] * A[SIDX[j][l]] + A[SIDX[i][l]] * A[SIDX[j][kk]]);
+                    double v = q * sym_u + r * (A[I] * A[J]);
+                    if (i == j && kk == l) v += p;
+                    acc.template out<1>(I + 6 * J, tf * v);
+                }
+        }
+    } else {
+        // Pᵀ_ij = Σ_n S_in F_jn
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                acc.template out<0>(i + 3 * j, S[SIDX[i][0]] * F[j] + S[SIDX[i][1]] * F[j + 3] + S[SIDX[i][2]] * F[j + 6]);
+        if (acc.template has_out<1>()) {
+            double D[36];       // ∂S∂C (minor symmetric)
+#pragma unroll
+            for (int J = 0; J < 6; ++J)
+#pragma unroll
+                for (int I = 0; I < 6; ++I) {
+                    const int i = SI[I], j = SJ[I], kk = SI[J], l = SJ[J];
+                    const double sym_u = 0.5 * (A[SIDX[i][kk]] * A[SIDX[j][l]] + A[SIDX[i][l]] * A[SIDX[j][kk]]);
+                    double v = q * sym_u + r * (A[I] * A[J]);
+                    if (i == j && kk == l) v += p;
+                    D[I + 6 * J] = v;
+                }
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    double G[3][3];     // G[n][k] = Σ_q D_(in)(lq) F_kq
+#pragma unroll
+                    for (int n = 0; n < 3; ++n)
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk)
+                            G[n][kk] = D[SIDX[i][n] + 6 * SIDX[l][0]] * F[kk] + D[SIDX[i][n] + 6 * SIDX[l][1]] * F[kk + 3] + D[SIDX[i][n] + 6 * SIDX[l][2]] * F[kk + 6];
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            double v = 2.0 * (F[j] * G[0][kk] + F[j + 3] * G[1][kk] + F[j + 6] * G[2][kk]);
+                            if (j == kk) v += S[SIDX[i][l]];
+                            acc.template out<1>(i + 3 * j + 9 * kk + 27 * l, v);
+                        }
+                }
+        }
     }
 }
+template <int MODEL, int KIND, class Acc> MM_HD void hyper_point(const HyperK& k, Acc& acc) { hyper_point_ex<MODEL, KIND, 0>(k, acc); }
 
 // =================================================================================================
 // XuNeedleman — reference src/CohesiveMaterials/XuNeedleman.jl:75-91.  T = ∂Φ/∂Δ, dTdΔ = ∂²Φ/∂Δ²

@@ -43,12 +43,12 @@ struct PlasticOp {
 #endif
 template <> struct MinBlocks<PlasticOp> { static constexpr int value = MM_PLASTIC_MINBLOCKS, block = 128; };   // 128 threads x 3 blocks/SM -> <= 168 regs: measured best of {1,3,4,5} (tools/sweep_plastic.sh)
 
-template <int MODEL, int KIND> struct HyperOp {
+template <int MODEL, int KIND, int TAN> struct HyperOp {
     static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int) { return KIND == 1 ? 9 : 6; }
-    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : 36; }
+    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? (TAN == 2 ? 9 : 6) : (TAN == 2 ? 81 : 36); }
     HyperK k;
-    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { hyper_point<MODEL, KIND>(k, acc); }
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { hyper_point_ex<MODEL, KIND, TAN>(k, acc); }
 };
 
 template <int DIM> struct XuOp {
@@ -80,12 +80,23 @@ __global__ void __launch_bounds__(256) synth_kernel(double* out, int64_t N, int 
     }
 }
 
-template <int MODEL> int launch_hyper(const HyperK& k, const double* strain, int strain_kind, double* S, double* dSdC, int64_t N, int layout, cudaStream_t st) {
+template <int MODEL, int KIND, int TAN>
+int launch_hyper_mkt(const HyperK& k, const double* strain, double* S, double* T, int64_t N, int layout, cudaStream_t st) {
     Ptrs<1, 2> p;
-    p.in[0] = strain; p.out[0] = S; p.out[1] = dSdC;
-    if (strain_kind == MM_STRAIN_F) { HyperOp<MODEL, 1> op; op.k = k; return launch_points<HyperOp<MODEL, 1>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper"); }
-    HyperOp<MODEL, 0> op; op.k = k;
-    return launch_points<HyperOp<MODEL, 0>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper");
+    p.in[0] = strain; p.out[0] = S; p.out[1] = T;
+    HyperOp<MODEL, KIND, TAN> op; op.k = k;
+    return launch_points<HyperOp<MODEL, KIND, TAN>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper");
+}
+template <int MODEL> int launch_hyper(const HyperK& k, const double* strain, int strain_kind, int tangent_kind, double* S, double* T, int64_t N, int layout, cudaStream_t st) {
+    if (tangent_kind == MM_TANGENT_DPDF) return launch_hyper_mkt<MODEL, 1, 2>(k, strain, S, T, N, layout, st);
+    if (tangent_kind == MM_TANGENT_DSDE) {
+        if (strain_kind == MM_STRAIN_F) return launch_hyper_mkt<MODEL, 1, 1>(k, strain, S, T, N, layout, st);
+        if (strain_kind == MM_STRAIN_E) return launch_hyper_mkt<MODEL, 2, 1>(k, strain, S, T, N, layout, st);
+        return launch_hyper_mkt<MODEL, 0, 1>(k, strain, S, T, N, layout, st);
+    }
+    if (strain_kind == MM_STRAIN_F) return launch_hyper_mkt<MODEL, 1, 0>(k, strain, S, T, N, layout, st);
+    if (strain_kind == MM_STRAIN_E) return launch_hyper_mkt<MODEL, 2, 0>(k, strain, S, T, N, layout, st);
+    return launch_hyper_mkt<MODEL, 0, 0>(k, strain, S, T, N, layout, st);
 }
 
 }  // namespace mm
@@ -111,17 +122,25 @@ int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, do
     return launch_points<PlasticOp, 128, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
 }
 
-int mm_hyper(int model, const MMHyper* p, const double* strain, int strain_kind, double* S, double* dSdC, int64_t N, int layout, void* stream) {
-    if (!p || N < 0 || (N > 0 && (!strain || !S))) return set_error(MM_ERR_ARG, "mm_hyper: bad argument");
-    if (strain_kind != MM_STRAIN_C && strain_kind != MM_STRAIN_F) return set_error(MM_ERR_ARG, "mm_hyper: unknown strain_kind %d", strain_kind);
+int mm_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent,
+                int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!strain || !stress))) return set_error(MM_ERR_ARG, "mm_hyper: bad argument");
+    if (strain_kind != MM_STRAIN_C && strain_kind != MM_STRAIN_F && strain_kind != MM_STRAIN_E) return set_error(MM_ERR_ARG, "mm_hyper: unknown strain_kind %d", strain_kind);
+    if (tangent_kind != MM_TANGENT_DSDC && tangent_kind != MM_TANGENT_DSDE && tangent_kind != MM_TANGENT_DPDF) return set_error(MM_ERR_ARG, "mm_hyper: unknown tangent_kind %d", tangent_kind);
+    if (tangent_kind == MM_TANGENT_DPDF && strain_kind != MM_STRAIN_F)
+        return set_error(MM_ERR_ARG, "mm_hyper: the dPdF tangent needs the deformation gradient as input (src/traits.jl:67-72)");
     HyperK k; k.lambda = p->lambda; k.mu = p->mu; k.c2 = p->c2; k.c3 = p->c3;
     cudaStream_t st = (cudaStream_t)stream;
     switch (model) {
-        case MM_NEOHOOK: return launch_hyper<0>(k, strain, strain_kind, S, dSdC, N, layout, st);
-        case MM_YEOH: return launch_hyper<1>(k, strain, strain_kind, S, dSdC, N, layout, st);
-        case MM_STVENANT: return launch_hyper<2>(k, strain, strain_kind, S, dSdC, N, layout, st);
+        case MM_NEOHOOK: return launch_hyper<0>(k, strain, strain_kind, tangent_kind, stress, tangent, N, layout, st);
+        case MM_YEOH: return launch_hyper<1>(k, strain, strain_kind, tangent_kind, stress, tangent, N, layout, st);
+        case MM_STVENANT: return launch_hyper<2>(k, strain, strain_kind, tangent_kind, stress, tangent, N, layout, st);
     }
     return set_error(MM_ERR_ARG, "mm_hyper: unknown model %d", model);
+}
+
+int mm_hyper(int model, const MMHyper* p, const double* strain, int strain_kind, double* S, double* dSdC, int64_t N, int layout, void* stream) {
+    return mm_hyper_ex(model, p, strain, strain_kind, MM_TANGENT_DSDC, S, dSdC, N, layout, stream);
 }
 
 int mm_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, double* dTdD, int dim, int64_t N, int layout, void* stream) {

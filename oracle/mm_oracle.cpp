@@ -290,4 +290,32 @@ int mmo_wrapped_plastic(int kind, const MMPlastic* p, const double* eps_red, con
     return 0;
 }
 
+// ---- trait layer (reference src/traits.jl:34-107): strain kinds C / F / E, tangent kinds ∂S∂C / ∂S∂E / ∂Pᵀ∂F ----------
+int mmo_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent,
+                 int64_t N, int layout) {
+    HyperM m{p->lambda, p->mu, p->c2, p->c3};
+    if (tangent_kind == MMO_TAN_DPDF && strain_kind != MMO_STRAIN_F) return MM_ERR_ARG;
+    const int nin = strain_kind == MMO_STRAIN_F ? 9 : 6, ns = tangent_kind == MMO_TAN_DPDF ? 9 : 6, nt = tangent_kind == MMO_TAN_DPDF ? 81 : 36;
+    View vi = V(strain, N, nin, layout), vs = V(stress, N, ns, layout), vt = V(tangent, N, nt, layout);
+    int om = model == MM_NEOHOOK ? MMO_NEOHOOK : (model == MM_YEOH ? MMO_YEOH : MMO_STVENANT);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+        double in[9], s[9], t[81];
+        for (int c = 0; c < nin; ++c) in[c] = vi.at(i, c);
+        hyper_response_traits(om, m, in, strain_kind, tangent_kind, s, t);
+        for (int c = 0; c < ns; ++c) vs.at(i, c) = s[c];
+        if (tangent) for (int c = 0; c < nt; ++c) vt.at(i, c) = t[c];
+    }
+    return 0;
+}
+// AD check (NeoHook): Pᵀ and ∂Pᵀ∂F by dual numbers through F -> S(FᵀF)⋅Fᵀ, single point
+int mmo_neohook_dPdF_ad(const MMHyper* p, const double* F9, double* Pt9, double* dP81) {
+    HyperM m{p->lambda, p->mu, p->c2, p->c3};
+    Ten2<double> F, Pt; Ten4<double> dP;
+    for (int c = 0; c < 9; ++c) F.a[c] = F9[c];
+    neohook_dPdF_ad(m, F, Pt, dP);
+    std::memcpy(Pt9, Pt.a, sizeof(Pt.a)); std::memcpy(dP81, dP.a, sizeof(dP.a));
+    return 0;
+}
+
 }  // extern "C"

@@ -507,4 +507,83 @@ inline int wrapped_response(int kind, Inner inner, const double* eps_red, double
     return 2;                                                                                // "Not converged. Could not find plane stress state." (:78)
 }
 
+// ---------------------------------------------------------------------------------------------
+// Trait layer: strain / stress / tangent transformations — reference src/traits.jl:34-77
+// ---------------------------------------------------------------------------------------------
+enum { MMO_TAN_DSDC = 0, MMO_TAN_DSDE = 1, MMO_TAN_DPDF = 2 };
+enum { MMO_STRAIN_C = 0, MMO_STRAIN_F = 1, MMO_STRAIN_E = 2 };
+
+template <class T> inline Ten4<T> full4(const Sym4<T>& A) {
+    Ten4<T> r;
+    for (int l = 0; l < 3; ++l) for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) r(i, j, k, l) = A(i, j, k, l);
+    return r;
+}
+template <class T> inline Ten4<T> dcontract44(const Ten4<T>& A, const Ten4<T>& Bt) {
+    Ten4<T> r;
+    for (int l = 0; l < 3; ++l) for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) {
+        T s(0.0);
+        for (int n = 0; n < 3; ++n) for (int m = 0; m < 3; ++m) s = s + A(i, j, m, n) * Bt(m, n, k, l);
+        r(i, j, k, l) = s;
+    }
+    return r;
+}
+// otimesu / otimesl on general (unsymmetric) second-order tensors
+template <class T> inline Ten4<T> otimesu2(const Ten2<T>& A, const Ten2<T>& Bt) { Ten4<T> r; for (int l = 0; l < 3; ++l) for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) r(i, j, k, l) = A(i, k) * Bt(j, l); return r; }
+template <class T> inline Ten4<T> otimesl2(const Ten2<T>& A, const Ten2<T>& Bt) { Ten4<T> r; for (int l = 0; l < 3; ++l) for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) r(i, j, k, l) = A(i, l) * Bt(j, k); return r; }
+template <class T> inline Ten2<T> full2(const Sym2<T>& A) { Ten2<T> r; for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) r(i, j) = A(i, j); return r; }
+template <class T> inline Ten2<T> transpose2(const Ten2<T>& A) { Ten2<T> r; for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) r(i, j) = A(j, i); return r; }
+
+// transform_stress_tangent(S, dSdC, ∂Pᵀ∂F, F) — traits.jl:67-77:  Pᵀ = S⋅Fᵀ,
+// dPᵀdF = otimesl(S, I) + otimesu(I, F) ⊡ dSdC ⊡ (otimesl(I, Fᵀ) + otimesu(Fᵀ, I))
+inline void to_dPdF(const Sym2<double>& S, const Sym4<double>& dSdC, const Ten2<double>& F, Ten2<double>& Pt, Ten4<double>& dPtdF) {
+    Ten2<double> I; I(0, 0) = 1; I(1, 1) = 1; I(2, 2) = 1;
+    Ten2<double> Sf = full2(S), Ft = transpose2(F);
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += Sf(i, k) * Ft(k, j); Pt(i, j) = s; }
+    Ten4<double> right = otimesl2(I, Ft) + otimesu2(Ft, I);
+    dPtdF = otimesl2(Sf, I) + dcontract44(dcontract44(otimesu2(I, F), full4(dSdC)), right);
+}
+
+// full trait-route response: strain kind -> C (traits.jl:35-51), native routine, output tangent kind (traits.jl:60-77)
+// stress_out: 6 (S) or 9 (Pᵀ);  tangent_out: 36 or 81
+inline bool hyper_response_traits(int model, const HyperM& mp, const double* strain, int strain_kind, int tangent_kind, double* stress_out, double* tangent_out) {
+    Sym2<double> C; Ten2<double> F;
+    if (strain_kind == MMO_STRAIN_F) { for (int c = 0; c < 9; ++c) F.a[c] = strain[c]; C = tdot(F); }
+    else if (strain_kind == MMO_STRAIN_E) { for (int c = 0; c < 6; ++c) C.a[c] = 2 * strain[c]; C(0, 0) += 1; C(1, 1) += 1; C(2, 2) += 1; }   // C = 2E + I (:43-46)
+    else for (int c = 0; c < 6; ++c) C.a[c] = strain[c];
+    Sym2<double> S; Sym4<double> T;
+    bool ok = hyper_response(model, mp, C, S, T);
+    if (tangent_kind == MMO_TAN_DPDF) {
+        Ten2<double> Pt; Ten4<double> dP;
+        to_dPdF(S, T, F, Pt, dP);
+        for (int c = 0; c < 9; ++c) stress_out[c] = Pt.a[c];
+        for (int c = 0; c < 81; ++c) tangent_out[c] = dP.a[c];
+    } else {
+        const double f = (tangent_kind == MMO_TAN_DSDE) ? 2.0 : 1.0;                     // ∂S∂E = 2 ∂S∂C (:61-63)
+        for (int c = 0; c < 6; ++c) stress_out[c] = S.a[c];
+        for (int c = 0; c < 36; ++c) tangent_out[c] = f * T.a[c];
+    }
+    return ok;
+}
+
+// AD cross-check of ∂Pᵀ∂F as in test_straintraits.jl:41-48: gradient of F -> S(FᵀF)⋅Fᵀ with 9 dual partials.
+// Only for the closed-form models (NeoHook, StVenant); the native routine is re-evaluated on duals.
+template <class T> inline void neohook_S(const HyperM& mp, const Sym2<T>& C, Sym2<T>& S) {
+    Sym2<T> invC = inv(C);
+    T lJ = log_(sqrt_(det(C)));
+    Sym2<double> I = identity2<double>();
+    for (int c = 0; c < 6; ++c) S.a[c] = mp.mu * (I.a[c] - invC.a[c]) + (mp.lambda * lJ) * invC.a[c];
+}
+inline void neohook_dPdF_ad(const HyperM& mp, const Ten2<double>& F, Ten2<double>& Pt, Ten4<double>& dP) {
+    typedef Dual<9> D;
+    Ten2<D> Fd; for (int c = 0; c < 9; ++c) { Fd.a[c] = D(F.a[c]); Fd.a[c].d[c] = 1.0; }
+    Sym2<D> C = tdot(Fd), S;
+    neohook_S(mp, C, S);
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) {
+        D s(0.0);
+        for (int k = 0; k < 3; ++k) s = s + S(i, k) * Fd(j, k);
+        Pt(i, j) = s.v;
+        for (int l = 0; l < 3; ++l) for (int k = 0; k < 3; ++k) dP(i, j, k, l) = s.d[k + 3 * l];
+    }
+}
+
 }  // namespace mmo

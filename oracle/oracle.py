@@ -37,6 +37,8 @@ _SIG = {
     "mmo_solve_scalar_kat": (C.c_int, [C.c_int, C.c_double, _P, _P, _P]),
     "mmo_strain_energy": (C.c_double, [C.c_int, C.POINTER(abi.MMHyper), _P]),
     "mmo_synth_uniform": (C.c_int, [_P, _I64, C.c_int, C.c_int, C.c_uint64, _P, _P]),
+    "mmo_hyper_ex": (C.c_int, [C.c_int, C.POINTER(abi.MMHyper), _P, C.c_int, C.c_int, _P, _P, _I64, C.c_int]),
+    "mmo_neohook_dPdF_ad": (C.c_int, [C.POINTER(abi.MMHyper), _P, _P, _P]),
     "mmo_wrapped_linear_elastic": (C.c_int, [C.c_int, C.POINTER(abi.MMLinearElastic), _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
     "mmo_wrapped_plastic": (C.c_int, [C.c_int, C.POINTER(abi.MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts),
                                       C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
@@ -225,3 +227,26 @@ def wrapped_plastic(kind, params, eps_red, state, layout=SOA, tol=1e-8, max_iter
                                    _ptr(oit), _ptr(nfail), C.byref(o), C.byref(w), N, layout)
     assert rc == 0
     return dict(sig=sig, tan=tan, state=st, flags=flags, iters=iters, outer_iters=oit, n_fail=int(nfail[0]))
+
+
+# ---- trait layer (reference src/traits.jl) -------------------------------------------------------
+TAN_DSDC, TAN_DSDE, TAN_DPDF = 0, 1, 2
+STRAIN_C, STRAIN_F, STRAIN_E = 0, 1, 2
+
+
+def hyper_ex(model, params, strain, strain_kind, tangent_kind, layout=SOA):
+    p = params if isinstance(params, abi.MMHyper) else abi.MMHyper(*params)
+    strain, N = _n(strain, layout)
+    ns, nt = (9, 81) if tangent_kind == TAN_DPDF else (6, 36)
+    S, T = _alloc(ns, N, layout), _alloc(nt, N, layout)
+    rc = lib().mmo_hyper_ex(model, C.byref(p), _ptr(strain), strain_kind, tangent_kind, _ptr(S), _ptr(T), N, layout)
+    assert rc == 0
+    return S, T
+
+
+def neohook_dPdF_ad(params, F9):
+    p = params if isinstance(params, abi.MMHyper) else abi.MMHyper(*params)
+    F9 = np.ascontiguousarray(F9, dtype=np.float64)
+    Pt, dP = np.zeros(9), np.zeros(81)
+    lib().mmo_neohook_dPdF_ad(C.byref(p), _ptr(F9), _ptr(Pt), _ptr(dP))
+    return Pt, dP

@@ -124,3 +124,17 @@ extern "C" int twin_wrapped_elastic(int kind, const MMLinearElastic* p, const do
     }
     return 0;
 }
+
+template <int MODEL> static int twin_hyper_ex_m(const mm::HyperK& k, const double* strain, int kind, int tan, double* S, double* T, int64_t N) {
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<1, 2> a{{strain}, {S, T}, N, i};
+        if (tan == 2) mm::hyper_point_ex<MODEL, 1, 2>(k, a);
+        else if (tan == 1) { if (kind == 1) mm::hyper_point_ex<MODEL, 1, 1>(k, a); else if (kind == 2) mm::hyper_point_ex<MODEL, 2, 1>(k, a); else mm::hyper_point_ex<MODEL, 0, 1>(k, a); }
+        else { if (kind == 1) mm::hyper_point_ex<MODEL, 1, 0>(k, a); else if (kind == 2) mm::hyper_point_ex<MODEL, 2, 0>(k, a); else mm::hyper_point_ex<MODEL, 0, 0>(k, a); }
+    }
+    return 0;
+}
+extern "C" int twin_hyper_ex(int model, const MMHyper* p, const double* strain, int kind, int tan, double* S, double* T, int64_t N) {
+    mm::HyperK k{p->lambda, p->mu, p->c2, p->c3};
+    return model == 0 ? twin_hyper_ex_m<0>(k, strain, kind, tan, S, T, N) : (model == 1 ? twin_hyper_ex_m<1>(k, strain, kind, tan, S, T, N) : twin_hyper_ex_m<2>(k, strain, kind, tan, S, T, N));
+}

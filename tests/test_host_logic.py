@@ -61,10 +61,10 @@ def test_api_argument_validation_without_gpu(mm):
         mm.material_response(m, np.zeros((5, 6)), st)                   # wrong layout for this state
     with pytest.raises(TypeError):
         mm.material_response(m, np.zeros((6, 5)))                       # state required
-    with pytest.raises(NotImplementedError):
-        mm.material_response(mm.dPdF(), mm.NeoHook(λ=1.0, μ=1.0), mm.DeformationGradient(np.zeros((9, 1))))
+    with pytest.raises(TypeError, match="needs DeformationGradient"):            # traits.jl:67-72: ∂Pᵀ∂F needs F
+        mm.material_response(mm.dPdF(), mm.NeoHook(λ=1.0, μ=1.0), mm.RightCauchyGreen(np.zeros((6, 1))))
     with pytest.raises(RuntimeError, match="not the native strain measure"):   # traits.jl:120
-        mm.material_response(mm.dSdC(), mm.NeoHook(λ=1.0, μ=1.0), mm.GreenLagrange(np.zeros((6, 1))))
+        mm.material_response(mm.dSdC(), mm.NeoHook(λ=1.0, μ=1.0), mm.SmallStrain(np.zeros((6, 1))))
     with pytest.raises(TypeError):
         mm.initial_material_state(m)                                    # batched API needs N
 

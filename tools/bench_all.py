@@ -97,6 +97,17 @@ def main():
                 report("%s from F %s" % (name, lname), N, 408, med, mn)
             del F
             torch.cuda.empty_cache()
+    if want("traits"):
+        N = int(1e8 * S)
+        nc, lo, hi, seed = sy.c3_defgrad()
+        F = mm.synth_uniform(N, nc, seed, lo, hi)
+        m = mm.NeoHook(λ=1.0, μ=1.0)
+        med, mn = timeit(lambda: mm.material_response(mm.dPdF(), m, mm.DeformationGradient(F)), a.reps)
+        report("NeoHook dPdF from F soa", N, 8 * (9 + 9 + 81), med, mn)
+        med, mn = timeit(lambda: mm.material_response(mm.dSdE(), m, mm.DeformationGradient(F)), a.reps)
+        report("NeoHook dSdE from F soa", N, 408, med, mn)
+        del F
+        torch.cuda.empty_cache()
     if want("xu"):
         N = int(1e8 * S)
         x = sy.XU_PARAMS
