@@ -81,6 +81,7 @@ typedef struct MMCrystal {                                                      
     double MS[MM_NSLIP][9];        /* m_i ⊗ s_i, Tensor{2,3} column-major (:42)                    */
     double H[MM_NSLIP][MM_NSLIP];  /* H[i][j] = Julia H[i+1,j+1] = H_iso (q + (1-q) δ_ij)   (:41)  */
 } MMCrystal;
+typedef struct MMTransverselyIsotropic { double L_perp, L_par, M_par, G_perp, G_par; } MMTransverselyIsotropic; /* transverselyisotropic.jl:19-37 */
 /* Newton options.  Plastic: NLsolve `ftol` on max|F| and `iterations` (defaults 1e-8 / 1000).
  * Crystal: `solve(...; tol, max_iter)` on ||r||_2, strict < (nonlinear_solver.jl:52; 1e-8 / 100). */
 typedef struct MMNewtonOpts { double tol; int32_t max_iter; int32_t pad_; } MMNewtonOpts;
@@ -158,6 +159,19 @@ int mm_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, 
                        double* state_out, uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
                        const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
 
+/* ---- TransverselyIsotropic — reference src/transverselyisotropic.jl -----------------------
+ * TransverselyIsotropic(; E_L, E_T, G_LT, ν_LT, ν_TT) (:39-53) and material_response(m, ε, state) (:92-106): the stiffness is
+ * rebuilt per point from the unit direction a3 held in the state.  eps[6], a3[3] (the state; returned unchanged), sig[6],
+ * tan[36] (may be NULL). */
+int mm_transversely_isotropic_setup(double E_L, double E_T, double G_LT, double nu_LT, double nu_TT, MMTransverselyIsotropic* out);
+int mm_transversely_isotropic(const MMTransverselyIsotropic* p, const double* eps, const double* a3, double* sig, double* tan,
+                              int64_t N, int layout, void* stream);
+
+/* ---- elastic_strain_energy_density — LinearElastic.jl:63, neohook.jl:29-33, yeoh.jl:31-35,
+ * stvenant.jl:28-34, and through any strain measure (traits.jl:133-136).  psi[N] (one double per point, layout-free). */
+int mm_linear_elastic_energy(const MMLinearElastic* p, const double* eps, double* psi, int64_t N, int layout, void* stream);
+int mm_hyper_energy(int model, const MMHyper* p, const double* strain, int strain_kind, double* psi, int64_t N, int layout, void* stream);
+
 /* Deterministic synthetic inputs (bench + parity harness): out(i,c) = lo[c] + (hi[c]-lo[c]) * u(i,c),
  * u(i,c) = (splitmix64(seed + i*nc + c) >> 11) * 2^-53.  lo/hi are HOST arrays of nc doubles. */
 int mm_synth_uniform(double* out, int64_t N, int nc, int layout, uint64_t seed, const double* lo, const double* hi,
@@ -173,6 +187,12 @@ int mmh_hyper(int model, const MMHyper* p, const double* strain, int strain_kind
 int mmh_crystal(const MMCrystal* p, const double* deps, double dt, const double* state_in, double* sig, double* tan,
                 double* state_out, uint16_t* active, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
 int mmh_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, double* dTdD, int dim, int64_t N, int layout);
+int mmh_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent,
+                 int64_t N, int layout);
+int mmh_transversely_isotropic(const MMTransverselyIsotropic* p, const double* eps, const double* a3, double* sig, double* tan,
+                               int64_t N, int layout);
+int mmh_linear_elastic_energy(const MMLinearElastic* p, const double* eps, double* psi, int64_t N, int layout);
+int mmh_hyper_energy(int model, const MMHyper* p, const double* strain, int strain_kind, double* psi, int64_t N, int layout);
 /* points per pipeline chunk of the mmh_* calls (default 1<<20); returns the previous value */
 int64_t mmh_set_chunk_points(int64_t n);
 

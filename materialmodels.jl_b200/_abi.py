@@ -42,6 +42,10 @@ class MMCrystal(C.Structure):
     ]
 
 
+class MMTransverselyIsotropic(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("L_perp", "L_par", "M_par", "G_perp", "G_par")]
+
+
 class MMNewtonOpts(C.Structure):
     _fields_ = [("tol", C.c_double), ("max_iter", C.c_int32), ("pad_", C.c_int32)]
 
@@ -67,7 +71,15 @@ SIGNATURES = {
     "mm_wrapped_linear_elastic": (C.c_int, [C.c_int, C.POINTER(MMLinearElastic), _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int, _P]),
     "mm_wrapped_plastic": (C.c_int, [C.c_int, C.POINTER(MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), C.POINTER(MMNewtonOpts),
                                      _I64, C.c_int, _P]),
+    "mm_transversely_isotropic_setup": (C.c_int, [C.c_double] * 5 + [C.POINTER(MMTransverselyIsotropic)]),
+    "mm_transversely_isotropic": (C.c_int, [C.POINTER(MMTransverselyIsotropic), _P, _P, _P, _P, _I64, C.c_int, _P]),
+    "mm_linear_elastic_energy": (C.c_int, [C.POINTER(MMLinearElastic), _P, _P, _I64, C.c_int, _P]),
+    "mm_hyper_energy": (C.c_int, [C.c_int, C.POINTER(MMHyper), _P, C.c_int, _P, _I64, C.c_int, _P]),
     "mm_synth_uniform": (C.c_int, [_P, _I64, C.c_int, C.c_int, C.c_uint64, _P, _P, _P]),
+    "mmh_hyper_ex": (C.c_int, [C.c_int, C.POINTER(MMHyper), _P, C.c_int, C.c_int, _P, _P, _I64, C.c_int]),
+    "mmh_transversely_isotropic": (C.c_int, [C.POINTER(MMTransverselyIsotropic), _P, _P, _P, _P, _I64, C.c_int]),
+    "mmh_linear_elastic_energy": (C.c_int, [C.POINTER(MMLinearElastic), _P, _P, _I64, C.c_int]),
+    "mmh_hyper_energy": (C.c_int, [C.c_int, C.POINTER(MMHyper), _P, C.c_int, _P, _I64, C.c_int]),
     "mmh_alloc_pinned": (_P, [C.c_uint64]),
     "mmh_free_pinned": (None, [_P]),
     "mmh_linear_elastic": (C.c_int, [C.POINTER(MMLinearElastic), _P, _P, _P, _I64, C.c_int]),

@@ -18,7 +18,8 @@ import numpy as np
 from . import _abi
 from ._lib import check, load
 from .materials import (AbstractDim, AbstractMaterialState, AbstractTangent, CrystalViscoPlastic, DeformationGradient, GreenLagrange,
-                        LinearElastic, Plastic, RightCauchyGreen, StrainMeasure, XuNeedleman, _Hyper, dPdF, dSdC, dSdE)
+                        LinearElastic, Plastic, RightCauchyGreen, SmallStrain, StrainMeasure, TransverselyIsotropic, XuNeedleman, _Hyper,
+                        dPdF, dSdC, dSdE)
 
 NOT_CONVERGED = "Material model not converged. Could not find material state."   # Plastic.jl:157, CrystalViscoPlastic.jl:92
 PLANE_STRESS_NOT_CONVERGED = "Not converged. Could not find plane stress state."    # wrappers.jl:78
@@ -160,9 +161,56 @@ class CrystalViscoPlasticState(_ArrayState):
     μ = property(lambda s: s._comp(30, 42))
 
 
-def initial_material_state(m, N=None, device="cuda", layout="soa"):
-    """Zero-initialised state for N points (reference: initial_material_state(m), one point).
-    device="cpu" gives a numpy-backed state for the host-buffer path."""
+class TransverselyIsotropicState(_ArrayState):
+    """a3(3) per point: unit vector normal to the plane of isotropy — reference src/transverselyisotropic.jl:55-57."""
+    NC = 3
+    a3 = property(lambda s: s.data)
+
+
+def _transviso_state(a3, N, device, layout):
+    """initial_material_state(::TransverselyIsotropic, a3 = (1,0,0)) — reference src/transverselyisotropic.jl:59-64.
+    `a3`: one direction (3,) shared by all N points, or a per-point array of shape (3, N) [soa] / (N, 3) [aos]."""
+    host = str(device) == "cpu"
+    if a3 is None:
+        a3 = (1.0, 0.0, 0.0)
+    if not _is_host(a3) and not isinstance(a3, (tuple, list)):                # torch tensor: per-point directions
+        data = _prep(a3)
+        nrm = data.norm(dim=0 if _LAYOUTS[layout] == 0 else 1)
+        bad = (nrm - 1.0).abs() > 1.4901161193847656e-08 * _torch().maximum(nrm, _torch().ones_like(nrm))
+        if bool(bad.any().item()):
+            raise ValueError("The material direction vector is not a unit vector (norm(a3) = %r)" % float(nrm[bad][0].item()))
+        return TransverselyIsotropicState(data, layout)
+    a = np.asarray(a3, dtype=np.float64)
+    if a.ndim == 1:
+        if a.shape != (3,):
+            raise ValueError("a3 must have 3 components")
+        if N is None:
+            raise TypeError("initial_material_state(::TransverselyIsotropic, a3, N): number of points required")
+        a = np.broadcast_to(a[:, None], (3, N)) if _LAYOUTS[layout] == 0 else np.broadcast_to(a[None, :], (N, 3))
+    a = np.ascontiguousarray(a)
+    nrm = np.linalg.norm(a, axis=0 if _LAYOUTS[layout] == 0 else 1)
+    bad = np.abs(nrm - 1.0) > np.sqrt(np.finfo(np.float64).eps) * np.maximum(nrm, 1.0)     # Julia's isapprox default rtol
+    if bad.any():
+        raise ValueError("The material direction vector is not a unit vector (norm(a3) = %r)" % float(nrm[bad][0]))
+    data = a if host else _torch().from_numpy(a).to(device)
+    return TransverselyIsotropicState(data, layout)
+
+
+def initial_material_state(m, *args, N=None, device="cuda", layout="soa", a3=None):
+    """Zero-initialised state for N points (reference: initial_material_state(m), one point):
+    initial_material_state(m, N).  device="cpu" gives a numpy-backed state for the host-buffer path.
+    TransverselyIsotropic: initial_material_state(m, a3, N) / (m, a3_per_point) / (m, N) [default direction (1,0,0)]."""
+    args = list(args)
+    if isinstance(m, TransverselyIsotropic):
+        if args and not isinstance(args[0], (int, np.integer)):
+            a3 = args.pop(0)
+        if args:
+            N = int(args.pop(0))
+        return _transviso_state(a3, N, device, layout)
+    if args:
+        N = int(args.pop(0))
+    if args:
+        raise TypeError("initial_material_state: too many positional arguments")
     if isinstance(m, LinearElastic):
         return LinearElasticState()
     if isinstance(m, XuNeedleman):
@@ -324,13 +372,73 @@ def _response_hyper(m, strain, kind, state, layout, want_tangent, tangent_kind=_
     lib = load()
     with _DeviceGuard(strain):
         if _is_host(strain):
-            if tangent_kind != _abi.MM_TANGENT_DSDC or kind == _abi.MM_STRAIN_E:
-                raise NotImplementedError("host-buffer path: native (S, dSdC) from C or F only; use device arrays for the other trait routes")
-            rc = lib.mmh_hyper(m.MODEL, ctypes.byref(m._c), _ptr(strain), kind, _ptr(S), _ptr(tan), N, _LAYOUTS[layout])
+            rc = lib.mmh_hyper_ex(m.MODEL, ctypes.byref(m._c), _ptr(strain), kind, tangent_kind, _ptr(S), _ptr(tan), N, _LAYOUTS[layout])
         else:
             rc = lib.mm_hyper_ex(m.MODEL, ctypes.byref(m._c), _ptr(strain), kind, tangent_kind, _ptr(S), _ptr(tan), N, _LAYOUTS[layout], _stream(strain))
     check(rc, "mm_hyper")
     return S, tan, state
+
+
+def _response_transviso(m, ε, state, want_tangent):
+    """material_response(m::TransverselyIsotropic, ε, state) — reference src/transverselyisotropic.jl:92-106."""
+    layout = state.layout
+    ε = _prep(ε)
+    N = _npoints(ε, 6, layout)
+    if N != state.N:
+        raise ValueError("strain has %d points, state has %d" % (N, state.N))
+    a3 = _prep(state.data)
+    if _is_host(ε) != _is_host(a3):
+        raise ValueError("strain and state must live in the same place")
+    σ = _empty(_shape(6, N, layout), ε)
+    tan = _empty(_shape(36, N, layout), ε) if want_tangent else None
+    lib = load()
+    with _DeviceGuard(ε):
+        if _is_host(ε):
+            rc = lib.mmh_transversely_isotropic(ctypes.byref(m._c), _ptr(ε), _ptr(a3), _ptr(σ), _ptr(tan), N, _LAYOUTS[layout])
+        else:
+            rc = lib.mm_transversely_isotropic(ctypes.byref(m._c), _ptr(ε), _ptr(a3), _ptr(σ), _ptr(tan), N, _LAYOUTS[layout], _stream(ε))
+    check(rc, "mm_transversely_isotropic")
+    return σ, tan, state
+
+
+def elastic_strain_energy_density(m, strain, layout="soa"):
+    """elastic_strain_energy_density(m, strain) -> ψ[N] — reference src/LinearElastic.jl:63 (ε), neohook.jl:29-33,
+    yeoh.jl:31-35, stvenant.jl:28-34 (C), and with a StrainMeasure (C / F / E) through src/traits.jl:133-136."""
+    kind = _abi.MM_STRAIN_C
+    if isinstance(strain, StrainMeasure):
+        if isinstance(m, _Hyper):
+            if isinstance(strain, DeformationGradient):
+                kind = _abi.MM_STRAIN_F
+            elif isinstance(strain, GreenLagrange):
+                kind = _abi.MM_STRAIN_E
+            elif not isinstance(strain, RightCauchyGreen):
+                raise RuntimeError("%s is not the native strain measure for %s:" % (type(strain).__name__, type(m).__name__))
+        elif not isinstance(strain, SmallStrain):
+            raise RuntimeError("%s is not the native strain measure for %s:" % (type(strain).__name__, type(m).__name__))
+        strain = strain.value
+    x = _prep(strain)
+    lib = load()
+    if isinstance(m, LinearElastic):
+        N = _npoints(x, 6, layout)
+        ψ = _empty((N,), x)
+        with _DeviceGuard(x):
+            if _is_host(x):
+                rc = lib.mmh_linear_elastic_energy(ctypes.byref(m._c), _ptr(x), _ptr(ψ), N, _LAYOUTS[layout])
+            else:
+                rc = lib.mm_linear_elastic_energy(ctypes.byref(m._c), _ptr(x), _ptr(ψ), N, _LAYOUTS[layout], _stream(x))
+        check(rc, "mm_linear_elastic_energy")
+        return ψ
+    if isinstance(m, _Hyper):
+        N = _npoints(x, 9 if kind == _abi.MM_STRAIN_F else 6, layout)
+        ψ = _empty((N,), x)
+        with _DeviceGuard(x):
+            if _is_host(x):
+                rc = lib.mmh_hyper_energy(m.MODEL, ctypes.byref(m._c), _ptr(x), kind, _ptr(ψ), N, _LAYOUTS[layout])
+            else:
+                rc = lib.mm_hyper_energy(m.MODEL, ctypes.byref(m._c), _ptr(x), kind, _ptr(ψ), N, _LAYOUTS[layout], _stream(x))
+        check(rc, "mm_hyper_energy")
+        return ψ
+    raise TypeError("elastic_strain_energy_density is defined for LinearElastic, NeoHook, Yeoh, StVenant (as in the reference)")
 
 
 def _response_xu(m, Δ, state, layout, want_tangent):
@@ -470,6 +578,10 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
         return _response_crystal(m, strain, state, 1.0 if Δt is None else Δt, options, tangent)
     if isinstance(m, _Hyper):
         return _response_hyper(m, strain, _abi.MM_STRAIN_C, state if state is not None else initial_material_state(m), layout, tangent)
+    if isinstance(m, TransverselyIsotropic):
+        if state is None:
+            raise TypeError("material_response(::TransverselyIsotropic, ε, state): state (material direction) required")
+        return _response_transviso(m, strain, state, tangent)
     if isinstance(m, XuNeedleman):
         return _response_xu(m, strain, state if state is not None else XuNeedlemanState(), layout, tangent)
     raise TypeError("material_response: unsupported material %r" % (m,))

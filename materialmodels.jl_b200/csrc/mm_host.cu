@@ -171,4 +171,37 @@ int mmh_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, doub
     });
 }
 
+int mmh_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent, int64_t N, int layout) {
+    if (!p || N < 0 || (N > 0 && (!strain || !stress))) return set_error(MM_ERR_ARG, "mmh_hyper_ex: bad argument");
+    const bool pf = tangent_kind == MM_TANGENT_DPDF;
+    Arr a[3] = {in_arr(strain, strain_kind == MM_STRAIN_F ? 9 : 6), out_arr(stress, pf ? 9 : 6), out_arr(tangent, pf ? 81 : 36)};
+    return pipeline(a, 3, N, layout, nullptr, [&](int s, int64_t n, cudaStream_t st) {
+        return mm_hyper_ex(model, p, (const double*)a[0].d[s], strain_kind, tangent_kind, (double*)a[1].d[s], (double*)a[2].d[s], n, layout, st);
+    });
+}
+
+int mmh_transversely_isotropic(const MMTransverselyIsotropic* p, const double* eps, const double* a3, double* sig, double* tan, int64_t N, int layout) {
+    if (!p || N < 0 || (N > 0 && (!eps || !a3 || !sig))) return set_error(MM_ERR_ARG, "mmh_transversely_isotropic: bad argument");
+    Arr a[4] = {in_arr(eps, 6), in_arr(a3, 3), out_arr(sig, 6), out_arr(tan, 36)};
+    return pipeline(a, 4, N, layout, nullptr, [&](int s, int64_t n, cudaStream_t st) {
+        return mm_transversely_isotropic(p, (const double*)a[0].d[s], (const double*)a[1].d[s], (double*)a[2].d[s], (double*)a[3].d[s], n, layout, st);
+    });
+}
+
+int mmh_linear_elastic_energy(const MMLinearElastic* p, const double* eps, double* psi, int64_t N, int layout) {
+    if (!p || N < 0 || (N > 0 && (!eps || !psi))) return set_error(MM_ERR_ARG, "mmh_linear_elastic_energy: bad argument");
+    Arr a[2] = {in_arr(eps, 6), out_arr(psi, 1, 8, false)};
+    return pipeline(a, 2, N, layout, nullptr, [&](int s, int64_t n, cudaStream_t st) {
+        return mm_linear_elastic_energy(p, (const double*)a[0].d[s], (double*)a[1].d[s], n, layout, st);
+    });
+}
+
+int mmh_hyper_energy(int model, const MMHyper* p, const double* strain, int strain_kind, double* psi, int64_t N, int layout) {
+    if (!p || N < 0 || (N > 0 && (!strain || !psi))) return set_error(MM_ERR_ARG, "mmh_hyper_energy: bad argument");
+    Arr a[2] = {in_arr(strain, strain_kind == MM_STRAIN_F ? 9 : 6), out_arr(psi, 1, 8, false)};
+    return pipeline(a, 2, N, layout, nullptr, [&](int s, int64_t n, cudaStream_t st) {
+        return mm_hyper_energy(model, p, (const double*)a[0].d[s], strain_kind, (double*)a[1].d[s], n, layout, st);
+    });
+}
+
 }  // extern "C"

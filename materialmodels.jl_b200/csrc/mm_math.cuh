@@ -475,4 +475,88 @@ template <int DIM, class Acc> MM_HD void xu_point(const XuK& k, Acc& acc) {
     }
 }
 
+// =================================================================================================
+// TransverselyIsotropic — reference src/transverselyisotropic.jl:92-106.
+// in<0> = ε(6), in<1> = a3(3) (unit direction, the model's state); out<0> = σ(6), out<1> = E(36, optional)
+//   E = L⊥ I⊗I + 2G⊥ Iˢʸᵐ + (L∥−L⊥)(I⊗A + A⊗I) + (M∥ − 4G∥ + 2G⊥ − 2L∥ + L⊥) A⊗A + 4(G∥−G⊥) 𝔸,   A = a⊗a,
+//   𝔸_ijkl = ¼ (A_ik δ_jl + A_il δ_jk + δ_ik A_jl + δ_il A_jk)
+// =================================================================================================
+struct TransvIsoK { double L_perp, L_par, M_par, G_perp, G_par; };
+template <class Acc> MM_HD void transviso_point(const TransvIsoK& k, Acc& acc) {
+    double e[6], a[3];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a[c] = acc.template in<1>(c);
+    const int SI[6] = {0, 1, 2, 1, 2, 2}, SJ[6] = {0, 0, 0, 1, 1, 2};
+    double A[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) A[c] = a[SI[c]] * a[SJ[c]];
+    const int SIDX[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    const double c3 = k.L_par - k.L_perp, c4 = k.M_par - 4.0 * k.G_par + 2.0 * k.G_perp - 2.0 * k.L_par + k.L_perp, c5 = k.G_par - k.G_perp;
+    double sig[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int J = 0; J < 6; ++J) {
+        const double wJ = is_diag_slot(J) ? e[J] : 2.0 * e[J];      // ⊡ sums both (k,l) and (l,k)
+#pragma unroll
+        for (int I = 0; I < 6; ++I) {
+            const int i = SI[I], j = SJ[I], kk = SI[J], l = SJ[J];
+            const double dij = (i == j), dkl = (kk == l), dik = (i == kk), djl = (j == l), dil = (i == l), djk = (j == kk);
+            const double bbA = A[SIDX[i][kk]] * djl + A[SIDX[i][l]] * djk + dik * A[SIDX[j][l]] + dil * A[SIDX[j][kk]];
+            const double v = k.L_perp * (dij * dkl) + k.G_perp * (dik * djl + dil * djk) + c3 * (dij * A[J] + A[I] * dkl) + c4 * (A[I] * A[J]) + c5 * bbA;
+            sig[I] += v * wJ;
+            if (acc.template has_out<1>()) acc.template out<1>(I + 6 * J, v);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc.template out<0>(c, sig[c]);
+}
+
+// =================================================================================================
+// elastic_strain_energy_density — LinearElastic.jl:63: ½ ε:Eᵉ:ε;
+// neohook.jl:29-33, yeoh.jl:31-35, stvenant.jl:28-34 through any strain measure (traits.jl:133-136).
+// in<0> = strain; out<0> = ψ (1 component)
+// =================================================================================================
+template <class Acc> MM_HD void linear_elastic_energy_point(const ElasticK& k, Acc& acc) {
+    double e[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c);
+    const double tr = tr6(e);
+    acc.template out<0>(0, 0.5 * (k.lam * tr * tr + 2.0 * k.G * ddot6(e, e)));
+}
+template <int MODEL, int KIND, class Acc> MM_HD void hyper_energy_point(const HyperK& k, Acc& acc) {
+    double C[6];
+    if (KIND == 1) {
+        double F[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) F[c] = acc.template in<0>(c);
+        C[0] = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+        C[1] = F[3] * F[0] + F[4] * F[1] + F[5] * F[2];
+        C[2] = F[6] * F[0] + F[7] * F[1] + F[8] * F[2];
+        C[3] = F[3] * F[3] + F[4] * F[4] + F[5] * F[5];
+        C[4] = F[6] * F[3] + F[7] * F[4] + F[8] * F[5];
+        C[5] = F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
+    } else if (KIND == 2) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) C[c] = is_diag_slot(c) ? (2.0 * acc.template in<0>(c) + 1.0) : (2.0 * acc.template in<0>(c));
+    } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) C[c] = acc.template in<0>(c);
+    }
+    double psi;
+    if (MODEL == 2) {      // StVenant: E = (C − I)/2, ψ = ½ λ tr(E)² + μ E:E
+        double E[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) E[c] = 0.5 * (is_diag_slot(c) ? (C[c] - 1.0) : C[c]);
+        const double trE = tr6(E);
+        psi = 0.5 * k.lambda * (trE * trE) + k.mu * ddot6(E, E);
+    } else {
+        const double det = C[0] * (C[3] * C[5] - C[4] * C[4]) + C[1] * (C[2] * C[4] - C[1] * C[5]) + C[2] * (C[1] * C[4] - C[2] * C[3]);
+        const double lJ = log(sqrt(det)), i3 = tr6(C) - 3.0;
+        psi = k.mu / 2 * i3 - k.mu * lJ + k.lambda / 2 * (lJ * lJ);
+        if (MODEL == 1) psi += k.c2 * (i3 * i3) + k.c3 * (i3 * i3 * i3);
+    }
+    acc.template out<0>(0, psi);
+}
+
 }  // namespace mm

@@ -59,6 +59,28 @@ template <int DIM> struct XuOp {
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { xu_point<DIM>(k, acc); }
 };
 
+struct TransvIsoOp {
+    static constexpr int NIN = 2, NOUT = 2, SCRATCH = 0;
+    __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? 6 : 3; }
+    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : 36; }
+    TransvIsoK k;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { transviso_point(k, acc); }
+};
+struct ElasticEnergyOp {
+    static constexpr int NIN = 1, NOUT = 1, SCRATCH = 0;
+    __host__ __device__ static constexpr int in_nc(int) { return 6; }
+    __host__ __device__ static constexpr int out_nc(int) { return 1; }
+    ElasticK k;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { linear_elastic_energy_point(k, acc); }
+};
+template <int MODEL, int KIND> struct HyperEnergyOp {
+    static constexpr int NIN = 1, NOUT = 1, SCRATCH = 0;
+    __host__ __device__ static constexpr int in_nc(int) { return KIND == 1 ? 9 : 6; }
+    __host__ __device__ static constexpr int out_nc(int) { return 1; }
+    HyperK k;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { hyper_energy_point<MODEL, KIND>(k, acc); }
+};
+
 // ---- synthetic inputs ---------------------------------------------------------------------------
 struct SynthParams { double lo[48], hi[48]; };
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -97,6 +119,14 @@ template <int MODEL> int launch_hyper(const HyperK& k, const double* strain, int
     if (strain_kind == MM_STRAIN_F) return launch_hyper_mkt<MODEL, 1, 0>(k, strain, S, T, N, layout, st);
     if (strain_kind == MM_STRAIN_E) return launch_hyper_mkt<MODEL, 2, 0>(k, strain, S, T, N, layout, st);
     return launch_hyper_mkt<MODEL, 0, 0>(k, strain, S, T, N, layout, st);
+}
+
+template <int MODEL> int launch_hyper_energy(const HyperK& k, const double* strain, int strain_kind, double* psi, int64_t N, int layout, cudaStream_t st) {
+    Ptrs<1, 1> p; p.in[0] = strain; p.out[0] = psi;
+    if (strain_kind == MM_STRAIN_F) { HyperEnergyOp<MODEL, 1> op; op.k = k; return launch_points<HyperEnergyOp<MODEL, 1>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper_energy"); }
+    if (strain_kind == MM_STRAIN_E) { HyperEnergyOp<MODEL, 2> op; op.k = k; return launch_points<HyperEnergyOp<MODEL, 2>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper_energy"); }
+    HyperEnergyOp<MODEL, 0> op; op.k = k;
+    return launch_points<HyperEnergyOp<MODEL, 0>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper_energy");
 }
 
 }  // namespace mm
@@ -150,6 +180,44 @@ int mm_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, doubl
     if (dim == 3) { XuOp<3> op; op.k = k; return launch_points<XuOp<3>, 256, MM_STREAM_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
     if (dim == 2) { XuOp<2> op; op.k = k; return launch_points<XuOp<2>, 256, MM_STREAM_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
     return set_error(MM_ERR_ARG, "mm_xu_needleman: dim must be 2 or 3 (got %d)", dim);
+}
+
+int mm_transversely_isotropic_setup(double E_L, double E_T, double G_LT, double nu_LT, double nu_TT, MMTransverselyIsotropic* out) {
+    if (!out) return set_error(MM_ERR_ARG, "mm_transversely_isotropic_setup: null output");
+    const double den = 2 * E_T * nu_LT * nu_LT - E_L + E_L * nu_TT;                     // transverselyisotropic.jl:46-50
+    out->M_par = (E_L * E_L * (nu_TT - 1)) / den;
+    out->L_par = -(E_L * E_T * nu_LT) / den;
+    out->L_perp = -(E_T * (E_T * nu_LT * nu_LT + E_L * nu_TT)) / ((nu_TT + 1) * den);
+    out->G_perp = E_T / (2 * (nu_TT + 1));
+    out->G_par = G_LT;
+    return MM_OK;
+}
+
+int mm_transversely_isotropic(const MMTransverselyIsotropic* p, const double* eps, const double* a3, double* sig, double* tan, int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!eps || !a3 || !sig))) return set_error(MM_ERR_ARG, "mm_transversely_isotropic: bad argument");
+    TransvIsoOp op; op.k.L_perp = p->L_perp; op.k.L_par = p->L_par; op.k.M_par = p->M_par; op.k.G_perp = p->G_perp; op.k.G_par = p->G_par;
+    Ptrs<2, 2> ptrs; ptrs.in[0] = eps; ptrs.in[1] = a3; ptrs.out[0] = sig; ptrs.out[1] = tan;
+    return launch_points<TransvIsoOp, 256, MM_STREAM_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_transversely_isotropic");
+}
+
+int mm_linear_elastic_energy(const MMLinearElastic* p, const double* eps, double* psi, int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!eps || !psi))) return set_error(MM_ERR_ARG, "mm_linear_elastic_energy: bad argument");
+    ElasticEnergyOp op; op.k = make_elastic_k(p->E, p->nu);
+    Ptrs<1, 1> ptrs; ptrs.in[0] = eps; ptrs.out[0] = psi;
+    return launch_points<ElasticEnergyOp, 256, MM_STREAM_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_linear_elastic_energy");
+}
+
+int mm_hyper_energy(int model, const MMHyper* p, const double* strain, int strain_kind, double* psi, int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!strain || !psi))) return set_error(MM_ERR_ARG, "mm_hyper_energy: bad argument");
+    if (strain_kind != MM_STRAIN_C && strain_kind != MM_STRAIN_F && strain_kind != MM_STRAIN_E) return set_error(MM_ERR_ARG, "mm_hyper_energy: unknown strain_kind %d", strain_kind);
+    HyperK k; k.lambda = p->lambda; k.mu = p->mu; k.c2 = p->c2; k.c3 = p->c3;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (model) {
+        case MM_NEOHOOK: return launch_hyper_energy<0>(k, strain, strain_kind, psi, N, layout, st);
+        case MM_YEOH: return launch_hyper_energy<1>(k, strain, strain_kind, psi, N, layout, st);
+        case MM_STVENANT: return launch_hyper_energy<2>(k, strain, strain_kind, psi, N, layout, st);
+    }
+    return set_error(MM_ERR_ARG, "mm_hyper_energy: unknown model %d", model);
 }
 
 int mm_synth_uniform(double* out, int64_t N, int nc, int layout, uint64_t seed, const double* lo, const double* hi, void* stream) {

@@ -98,6 +98,26 @@ class StVenant(_Hyper):
     MODEL = _abi.MM_STVENANT
 
 
+class TransverselyIsotropic(AbstractMaterial):
+    """TransverselyIsotropic(; E_L, E_T, G_LT, ν_LT, ν_TT) or TransverselyIsotropic(L⊥, L₌, M₌, G⊥, G₌)
+    — reference src/transverselyisotropic.jl:19-53.  The material direction lives in the state."""
+
+    def __init__(self, *args, **kw):
+        if args:
+            if len(args) != 5:
+                raise TypeError("TransverselyIsotropic(L⊥, L₌, M₌, G⊥, G₌) takes 5 positional arguments")
+            c = _abi.MMTransverselyIsotropic(*map(float, args))
+        else:
+            from ._lib import check, load
+
+            E_L, E_T, G_LT = _kw(kw, "E_L"), _kw(kw, "E_T"), _kw(kw, "G_LT")
+            ν_LT, ν_TT = _kw(kw, "ν_LT", "nu_LT"), _kw(kw, "ν_TT", "nu_TT")
+            c = _abi.MMTransverselyIsotropic()
+            check(load().mm_transversely_isotropic_setup(E_L, E_T, G_LT, ν_LT, ν_TT, ctypes.byref(c)), "mm_transversely_isotropic_setup")
+        self._c = c
+        self.L_perp, self.L_par, self.M_par, self.G_perp, self.G_par = c.L_perp, c.L_par, c.M_par, c.G_perp, c.G_par
+
+
 class FCC:
     CODE = _abi.MM_FCC
 

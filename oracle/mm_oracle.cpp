@@ -318,4 +318,49 @@ int mmo_neohook_dPdF_ad(const MMHyper* p, const double* F9, double* Pt9, double*
     return 0;
 }
 
+// ---- TransverselyIsotropic + strain energies --------------------------------------
+int mmo_transviso_setup(double E_L, double E_T, double G_LT, double nu_LT, double nu_TT, MMTransverselyIsotropic* out) {
+    TransvIsoM m = make_transviso(E_L, E_T, G_LT, nu_LT, nu_TT);
+    out->L_perp = m.L_perp; out->L_par = m.L_par; out->M_par = m.M_par; out->G_perp = m.G_perp; out->G_par = m.G_par;
+    return 0;
+}
+int mmo_transversely_isotropic(const MMTransverselyIsotropic* p, const double* eps, const double* a3, double* sig, double* tan, int64_t N, int layout) {
+    TransvIsoM m{p->L_perp, p->L_par, p->M_par, p->G_perp, p->G_par};
+    View ve = V(eps, N, 6, layout), va = V(a3, N, 3, layout), vs = V(sig, N, 6, layout), vt = V(tan, N, 36, layout);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+        Sym2<double> e, s; Sym4<double> t; double a[3];
+        for (int c = 0; c < 6; ++c) e.a[c] = ve.at(i, c);
+        for (int c = 0; c < 3; ++c) a[c] = va.at(i, c);
+        material_response(m, e, a, s, t);
+        for (int c = 0; c < 6; ++c) vs.at(i, c) = s.a[c];
+        if (tan) for (int c = 0; c < 36; ++c) vt.at(i, c) = t.a[c];
+    }
+    return 0;
+}
+// elastic_strain_energy_density: model = -1 LinearElastic (p = MMLinearElastic, strain = ε), else hyper model with strain kind C/F/E
+int mmo_strain_energy_batch(int model, const void* params, const double* strain, int strain_kind, double* psi, int64_t N, int layout) {
+    const int nin = (model >= 0 && strain_kind == MMO_STRAIN_F) ? 9 : 6;
+    View vi = V(strain, N, nin, layout);
+    if (model < 0) {
+        const MMLinearElastic* p = (const MMLinearElastic*)params;
+        LinearElasticM m = make_linear_elastic(p->E, p->nu);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < N; ++i) { Sym2<double> e; for (int c = 0; c < 6; ++c) e.a[c] = vi.at(i, c); psi[i] = linear_elastic_energy(m, e); }
+        return 0;
+    }
+    const MMHyper* p = (const MMHyper*)params;
+    HyperM m{p->lambda, p->mu, p->c2, p->c3};
+    int om = model == MM_NEOHOOK ? MMO_NEOHOOK : (model == MM_YEOH ? MMO_YEOH : MMO_STVENANT);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+        Sym2<double> C;
+        if (strain_kind == MMO_STRAIN_F) { Ten2<double> F; for (int c = 0; c < 9; ++c) F.a[c] = vi.at(i, c); C = tdot(F); }
+        else if (strain_kind == MMO_STRAIN_E) { for (int c = 0; c < 6; ++c) C.a[c] = 2 * vi.at(i, c); C(0, 0) += 1; C(1, 1) += 1; C(2, 2) += 1; }
+        else for (int c = 0; c < 6; ++c) C.a[c] = vi.at(i, c);
+        psi[i] = strain_energy<double>(om, m, C);
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -586,4 +586,32 @@ inline void neohook_dPdF_ad(const HyperM& mp, const Ten2<double>& F, Ten2<double
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TransverselyIsotropic — reference src/transverselyisotropic.jl:19-106
+// ---------------------------------------------------------------------------------------------
+struct TransvIsoM { double L_perp, L_par, M_par, G_perp, G_par; };
+inline TransvIsoM make_transviso(double E_L, double E_T, double G_LT, double nu_LT, double nu_TT) {   // :39-53
+    TransvIsoM m;
+    m.M_par = (E_L * E_L * (nu_TT - 1)) / (2 * E_T * nu_LT * nu_LT - E_L + E_L * nu_TT);
+    m.L_par = -(E_L * E_T * nu_LT) / (2 * E_T * nu_LT * nu_LT - E_L + E_L * nu_TT);
+    m.L_perp = -(E_T * (E_T * nu_LT * nu_LT + E_L * nu_TT)) / ((nu_TT + 1) * (2 * E_T * nu_LT * nu_LT - E_L + E_L * nu_TT));
+    m.G_perp = E_T / (2 * (nu_TT + 1));
+    m.G_par = G_LT;
+    return m;
+}
+template <class T> inline Sym4<T> operator+(const Sym4<T>& x, const Sym4<T>& y) { Sym4<T> r; for (int i = 0; i < 36; ++i) r.a[i] = x.a[i] + y.a[i]; return r; }
+template <class T> inline Sym4<T> scale(double s, const Sym4<T>& x) { Sym4<T> r; for (int i = 0; i < 36; ++i) r.a[i] = s * x.a[i]; return r; }
+inline void material_response(const TransvIsoM& m, const Sym2<double>& eps, const double a3[3], Sym2<double>& sig, Sym4<double>& E) {   // :92-106
+    Sym2<double> I = identity2<double>(), A;
+    for (int j = 0; j < 3; ++j) for (int i = j; i < 3; ++i) A(i, j) = 0.5 * (a3[i] * a3[j] + a3[j] * a3[i]);       // symmetric(a3 ⊗ a3)
+    Sym4<double> Isym = scale(0.5, symmetric(otimesu(I, I) + otimesl(I, I)));
+    Sym4<double> IoI = symmetric(otimes(I, I));
+    Sym4<double> AA = scale(0.25, symmetric(otimesu(A, I) + otimesl(A, I) + otimesu(I, A) + otimesl(I, A)));
+    E = scale(m.L_perp, IoI) + scale(2 * m.G_perp, Isym) + scale(m.L_par - m.L_perp, symmetric(otimes(I, A) + otimes(A, I))) +
+        scale(m.M_par - 4 * m.G_par + 2 * m.G_perp - 2 * m.L_par + m.L_perp, symmetric(otimes(A, A))) + scale(4 * (m.G_par - m.G_perp), AA);
+    sig = dcontract(E, eps);
+}
+// LinearElastic energy — reference src/LinearElastic.jl:63
+inline double linear_elastic_energy(const LinearElasticM& m, const Sym2<double>& eps) { return 0.5 * dcontract(eps, dcontract(m.Ee, eps)); }
+
 }  // namespace mmo

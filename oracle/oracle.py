@@ -39,6 +39,9 @@ _SIG = {
     "mmo_synth_uniform": (C.c_int, [_P, _I64, C.c_int, C.c_int, C.c_uint64, _P, _P]),
     "mmo_hyper_ex": (C.c_int, [C.c_int, C.POINTER(abi.MMHyper), _P, C.c_int, C.c_int, _P, _P, _I64, C.c_int]),
     "mmo_neohook_dPdF_ad": (C.c_int, [C.POINTER(abi.MMHyper), _P, _P, _P]),
+    "mmo_transviso_setup": (C.c_int, [C.c_double] * 5 + [C.POINTER(abi.MMTransverselyIsotropic)]),
+    "mmo_transversely_isotropic": (C.c_int, [C.POINTER(abi.MMTransverselyIsotropic), _P, _P, _P, _P, _I64, C.c_int]),
+    "mmo_strain_energy_batch": (C.c_int, [C.c_int, _P, _P, C.c_int, _P, _I64, C.c_int]),
     "mmo_wrapped_linear_elastic": (C.c_int, [C.c_int, C.POINTER(abi.MMLinearElastic), _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
     "mmo_wrapped_plastic": (C.c_int, [C.c_int, C.POINTER(abi.MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts),
                                       C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
@@ -250,3 +253,29 @@ def neohook_dPdF_ad(params, F9):
     Pt, dP = np.zeros(9), np.zeros(81)
     lib().mmo_neohook_dPdF_ad(C.byref(p), _ptr(F9), _ptr(Pt), _ptr(dP))
     return Pt, dP
+
+
+# ---- TransverselyIsotropic and energies ----------------------------------
+def transviso_params(E_L, E_T, G_LT, nu_LT, nu_TT):
+    p = abi.MMTransverselyIsotropic()
+    lib().mmo_transviso_setup(E_L, E_T, G_LT, nu_LT, nu_TT, C.byref(p))
+    return p
+
+
+def transversely_isotropic(p, eps, a3, layout=SOA):
+    eps, N = _n(eps, layout)
+    a3 = np.ascontiguousarray(a3, dtype=np.float64)
+    sig, tan = _alloc(6, N, layout), _alloc(36, N, layout)
+    rc = lib().mmo_transversely_isotropic(C.byref(p), _ptr(eps), _ptr(a3), _ptr(sig), _ptr(tan), N, layout)
+    assert rc == 0
+    return sig, tan
+
+
+def strain_energy_batch(model, params, strain, strain_kind=0, layout=SOA):
+    """model = -1: LinearElastic (params = (E, nu)); else hyper model with strain kind C/F/E"""
+    strain, N = _n(strain, layout)
+    psi = np.zeros(N)
+    p = (abi.MMLinearElastic(*params) if model < 0 else (params if isinstance(params, abi.MMHyper) else abi.MMHyper(*params)))
+    rc = lib().mmo_strain_energy_batch(model, C.byref(p), _ptr(strain), strain_kind, _ptr(psi), N, layout)
+    assert rc == 0
+    return psi

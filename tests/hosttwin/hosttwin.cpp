@@ -138,3 +138,26 @@ extern "C" int twin_hyper_ex(int model, const MMHyper* p, const double* strain, 
     mm::HyperK k{p->lambda, p->mu, p->c2, p->c3};
     return model == 0 ? twin_hyper_ex_m<0>(k, strain, kind, tan, S, T, N) : (model == 1 ? twin_hyper_ex_m<1>(k, strain, kind, tan, S, T, N) : twin_hyper_ex_m<2>(k, strain, kind, tan, S, T, N));
 }
+
+// ---- TransverselyIsotropic and strain energies ----
+extern "C" int twin_transviso(const MMTransverselyIsotropic* p, const double* eps, const double* a3, double* sig, double* tan, int64_t N) {
+    mm::TransvIsoK k{p->L_perp, p->L_par, p->M_par, p->G_perp, p->G_par};
+    for (int64_t i = 0; i < N; ++i) { HostAcc<2, 2> a{{eps, a3}, {sig, tan}, N, i}; mm::transviso_point(k, a); }
+    return 0;
+}
+extern "C" int twin_linear_elastic_energy(const MMLinearElastic* p, const double* eps, double* psi, int64_t N) {
+    mm::ElasticK k = mm::make_elastic_k(p->E, p->nu);
+    for (int64_t i = 0; i < N; ++i) { HostAcc<1, 1> a{{eps}, {psi}, N, i}; mm::linear_elastic_energy_point(k, a); }
+    return 0;
+}
+template <int MODEL> static void twin_hyper_energy_m(const mm::HyperK& k, const double* strain, int kind, double* psi, int64_t N) {
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<1, 1> a{{strain}, {psi}, N, i};
+        if (kind == 1) mm::hyper_energy_point<MODEL, 1>(k, a); else if (kind == 2) mm::hyper_energy_point<MODEL, 2>(k, a); else mm::hyper_energy_point<MODEL, 0>(k, a);
+    }
+}
+extern "C" int twin_hyper_energy(int model, const MMHyper* p, const double* strain, int kind, double* psi, int64_t N) {
+    mm::HyperK k{p->lambda, p->mu, p->c2, p->c3};
+    if (model == 0) twin_hyper_energy_m<0>(k, strain, kind, psi, N); else if (model == 1) twin_hyper_energy_m<1>(k, strain, kind, psi, N); else twin_hyper_energy_m<2>(k, strain, kind, psi, N);
+    return 0;
+}

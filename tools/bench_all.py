@@ -108,6 +108,34 @@ def main():
         report("NeoHook dSdE from F soa", N, 408, med, mn)
         del F
         torch.cuda.empty_cache()
+    if want("transviso"):
+        N = int(1e8 * S)
+        m = mm.TransverselyIsotropic(E_L=100e3, E_T=10e3, G_LT=5e3, ν_LT=0.4, ν_TT=0.3)
+        for lname in ("soa", "aos"):
+            eps = mm.synth_uniform(N, 6, 99, -2e-3, 2e-3, layout=lname)
+            a3 = mm.synth_uniform(N, 3, 100, 0.1, 1.0, layout=lname)
+            a3 /= a3.norm(dim=0 if lname == "soa" else 1, keepdim=True)
+            st = mm.TransverselyIsotropicState(a3.contiguous(), lname)
+            med, mn = timeit(lambda: mm.material_response(m, eps, st), a.reps)
+            report("transversely_isotropic " + lname, N, 8 * (6 + 3 + 6 + 36), med, mn)
+            del eps, a3, st
+            torch.cuda.empty_cache()
+    if want("energy"):
+        N = int(1e8 * S)
+        nc, lo, hi, seed = sy.c3_defgrad()
+        for lname in ("soa", "aos"):
+            F = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
+            for name, prm in (("NeoHook", sy.NEOHOOK_PARAMS), ("Yeoh", sy.YEOH_PARAMS), ("StVenant", sy.NEOHOOK_PARAMS)):
+                m = getattr(mm, name)(λ=prm["lambda_"], μ=prm["mu"], c2=prm["c2"], c3=prm["c3"])
+                med, mn = timeit(lambda: mm.elastic_strain_energy_density(m, mm.DeformationGradient(F), layout=lname), a.reps)
+                report("%s energy from F %s" % (name, lname), N, 80, med, mn)
+            del F
+            eps = mm.synth_uniform(N, 6, 5, -2e-3, 2e-3, layout=lname)
+            le = mm.LinearElastic(E=200e3, ν=0.3)
+            med, mn = timeit(lambda: mm.elastic_strain_energy_density(le, eps, layout=lname), a.reps)
+            report("LinearElastic energy " + lname, N, 56, med, mn)
+            del eps
+            torch.cuda.empty_cache()
     if want("xu"):
         N = int(1e8 * S)
         x = sy.XU_PARAMS
