@@ -69,25 +69,37 @@ __global__ void __launch_bounds__(128) crystal_fixup_kernel(const CrystalK k, co
 #define MM_CRYSTAL_BS 64
 #endif
 #ifndef MM_CRYSTAL_MINBLOCKS
-#define MM_CRYSTAL_MINBLOCKS 5
+#define MM_CRYSTAL_MINBLOCKS 4
 #endif
 #ifndef MM_CRYSTAL_THRESH
-#define MM_CRYSTAL_THRESH 8
+#define MM_CRYSTAL_THRESH 4
 #endif
 template <> struct MinBlocks<CrystalOp<1>> { static constexpr int value = MM_CRYSTAL_MINBLOCKS, block = 64; };
 template <> struct MinBlocks<CrystalOp<2>> { static constexpr int value = MM_CRYSTAL_MINBLOCKS, block = 64; };
 
 // ---------------------------------------------------------------------------------------------------------
-// Lane-persistent kernel.  Newton iteration counts differ wildly between neighbouring points (0 for an elastic
-// point, 5-30 for a plastic one), so with one point per thread a warp idles most of its lanes while the slowest
-// solve finishes (ncu: 12.4 of 32 threads active per instruction).  Here each WARP owns a contiguous chunk of
-// points; a lane whose point is finished is refilled with the next point of the chunk, and the (expensive, uniform)
-// tangent + store phase runs only when at least MM_CRYSTAL_THRESH lanes are waiting for it — warp-level voting
-// (__ballot_sync) decides every phase.  All per-point vectors live in the lane's shared-memory scratch column.
+// Two-kernel structured path.
+// (1) crystal_newton_kernel — lane-persistent Newton.  Iteration counts differ wildly between neighbouring points
+//     (0 for an elastic point, 5-30 for a plastic one), so with one point per thread a warp idles most of its lanes
+//     while the slowest solve finishes.  Here each WARP owns a contiguous chunk of points; a lane whose solve is
+//     finished stores its converged μ (into the μ slots of the state output), its iteration count and a status word,
+//     and is refilled with the next point of the chunk — in batches of >= `thresh` lanes so that the (divergent)
+//     store + refill code runs with many lanes; warp-level voting (__ballot_sync) decides every phase.  All
+//     per-point vectors live in the lane's shared-memory scratch column.
+// (2) crystal_finish_kernel — one thread per point, no divergence between neighbours: re-evaluates at the stored μ
+//     (one extra pass out of ~15) and writes σ, the tangent (six 6x6 solves) and the state.  In the one-kernel version
+//     this phase ran with 5.8 of 32 lanes active and took 16 % of the time (profiles/r01_crystal_v5_ncu_full.txt).
 // ---------------------------------------------------------------------------------------------------------
-template <bool HASQ, int LAYOUT, int BS>
+template <int LAYOUT> struct DirectAccRW : DirectAcc<LAYOUT> {
+    __device__ __forceinline__ DirectAccRW(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_) : DirectAcc<LAYOUT>(p_, N_, i_) {}
+    template <int A> __device__ __forceinline__ double rd_out(int c) const {
+        return LAYOUT == 0 ? this->p.out[A][(int64_t)c * this->N + this->i] : this->p.out[A][this->i * CrystalOp<0>::out_nc(A) + c];
+    }
+};
+
+template <bool HASQ, bool INTPOW, int LAYOUT, int BS>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_MINBLOCKS)
-crystal_persistent_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint8_t* iters, int32_t* n_fail, const int64_t N, const int chunk, const int thresh) {
+crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint8_t* iters, const int64_t N, const int chunk, const int thresh) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     const unsigned FULL = 0xffffffffu;
@@ -114,31 +126,55 @@ crystal_persistent_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active
         }
         const unsigned working = __ballot_sync(FULL, has_work);
         if (working == 0u) break;
-        if (has_work && !finished) finished = crystal_iterate<HASQ>(k, scr, L);
+        if (has_work && !finished) finished = crystal_iterate<HASQ, INTPOW, false>(k, scr, L);
         const unsigned fin = __ballot_sync(FULL, has_work && finished);
         const unsigned iterating = working & ~fin;
-        if (fin != 0u && (__popc(fin) >= thresh || iterating == 0u)) {
+        if (fin != 0u && (__popc(fin) >= thresh || iterating == 0u || next >= end)) {
             if (has_work && finished) {
-                DirectAcc<LAYOUT> acc(p, N, my);
-                bool fallback = false;
-                unsigned mask = crystal_finalize<HASQ>(k, acc, scr, L, &fallback);
-                if (fallback) mask = MM_ACTIVE_NEEDS_GENERAL;
-                active[my] = (uint16_t)mask;
-                if (iters) iters[my] = (uint8_t)(fallback ? 0 : (L.iters > 255 ? 255 : L.iters));
-                if ((mask & MM_ACTIVE_FAILED) && n_fail) atomicAdd(n_fail, 1);
+                if (!L.bad) {
+                    DirectAcc<LAYOUT> acc(p, N, my);
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) acc.template out<2>(30 + i, scr(60 + i));
+                }
+                active[my] = (uint16_t)(L.bad ? MM_ACTIVE_NEEDS_GENERAL : (L.converged ? 0u : MM_ACTIVE_FAILED));
+                if (iters) iters[my] = (uint8_t)(L.bad ? 0 : (L.iters > 255 ? 255 : L.iters));
                 has_work = false; finished = false;
             }
         }
     }
 }
 
-template <bool HASQ, int LAYOUT>
-int launch_crystal_persistent(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
-    constexpr int BS = MM_CRYSTAL_BS;
-    constexpr size_t smem = (size_t)MM_CRYSTAL_SCRATCH * BS * sizeof(double);
+#ifndef MM_CRYSTAL_FINISH_BS
+#define MM_CRYSTAL_FINISH_BS 64
+#endif
+#ifndef MM_CRYSTAL_FINISH_MINBLOCKS
+#define MM_CRYSTAL_FINISH_MINBLOCKS 4
+#endif
+template <bool HASQ, bool INTPOW, int LAYOUT, int BS>
+__global__ void __launch_bounds__(BS, MM_CRYSTAL_FINISH_MINBLOCKS)
+crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, int32_t* n_fail, const int64_t N) {
+    extern __shared__ double sm_scratch[];
+    const Scratch scr{sm_scratch + threadIdx.x, BS};
+    const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
+    if (i >= N) return;
+    const unsigned status = active[i];
+    if (status & MM_ACTIVE_NEEDS_GENERAL) return;                     // left to the fix-up pass
+    DirectAccRW<LAYOUT> acc(p, N, i);
+    bool fallback = false;
+    unsigned mask = crystal_finish_from_x<HASQ, INTPOW>(k, acc, scr, (status & MM_ACTIVE_FAILED) == 0, &fallback);
+    if (fallback) mask = MM_ACTIVE_NEEDS_GENERAL;
+    active[i] = (uint16_t)mask;
+    if ((mask & MM_ACTIVE_FAILED) && n_fail) atomicAdd(n_fail, 1);
+}
+
+template <bool HASQ, bool INTPOW, int LAYOUT>
+int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
+    constexpr int BS = MM_CRYSTAL_BS, FBS = MM_CRYSTAL_FINISH_BS;
+    constexpr size_t smem = (size_t)MM_CRYSTAL_SCRATCH * BS * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(crystal_persistent_kernel<HASQ, LAYOUT, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
         if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_crystal: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
@@ -148,15 +184,22 @@ int launch_crystal_persistent(const CrystalK& k, uint16_t* active, uint8_t* iter
     if (chunk > 1024) chunk = 1024;
     if (chunk < 64) chunk = 64;
     chunk = (chunk + 31) / 32 * 32;
+    int thresh = MM_CRYSTAL_THRESH;
+    if (const char* t = getenv("MM_CRYSTAL_THRESH")) thresh = atoi(t);          // tuning knobs
+    if (const char* c = getenv("MM_CRYSTAL_CHUNK")) chunk = atoi(c);
     const int64_t warps = (N + chunk - 1) / chunk;
     const int64_t blocks = (warps + (BS / 32) - 1) / (BS / 32);
-    int thresh = MM_CRYSTAL_THRESH;
-    if (const char* t = getenv("MM_CRYSTAL_THRESH")) thresh = atoi(t);          // tuning knob
-    if (const char* c = getenv("MM_CRYSTAL_CHUNK")) chunk = atoi(c);
-    const int64_t warps2 = (N + chunk - 1) / chunk;
-    const int64_t blocks2 = (warps2 + (BS / 32) - 1) / (BS / 32);
-    crystal_persistent_kernel<HASQ, LAYOUT, BS><<<(unsigned)blocks2, BS, smem, st>>>(k, ptrs, active, iters, n_fail, N, (int)chunk, thresh);
-    return check_launch("mm_crystal");
+    crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, N, (int)chunk, thresh);
+    int rc = check_launch("mm_crystal (Newton kernel)");
+    if (rc) return rc;
+    crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS><<<(unsigned)((N + FBS - 1) / FBS), FBS, fsmem, st>>>(k, ptrs, active, n_fail, N);
+    return check_launch("mm_crystal (finish kernel)");
+}
+
+template <bool HASQ, int LAYOUT>
+int launch_crystal_persistent(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
+    return k.m_int ? launch_crystal_two_kernel<HASQ, true, LAYOUT>(k, active, iters, n_fail, ptrs, N, st)
+                   : launch_crystal_two_kernel<HASQ, false, LAYOUT>(k, active, iters, n_fail, ptrs, N, st);
 }
 
 template <int MODE>

@@ -237,6 +237,32 @@ MM_HD double powi_(double b, int n) {      // b^n, n >= 0, by squaring (n is war
     while (n) { if (n & 1) r *= b; b *= b; n >>= 1; }
     return r;
 }
+// b^n for 1 <= n < 64 (n warp-uniform): same multiplication sequence as powi_, fixed trip count => straight-line code
+MM_HD double powi6_(double b, int n) {
+    double r = (n & 1) ? b : 1.0;
+#pragma unroll
+    for (int bit = 1; bit < 6; ++bit) {
+        if ((n >> bit) != 0) b *= b;
+        if ((n >> bit) & 1) r *= b;
+    }
+    return r;
+}
+// reciprocal without the range guard of fast_rcp: for arguments that are well scaled whenever the solve is healthy
+// (1 + H_kin μ/α_∞ and the guarded D_ii); on a diverged iterate (0, inf, NaN) it yields inf/NaN like a division would,
+// the residual norm turns NaN and the point ends as "not converged".
+MM_HD double rcp_nc(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
 
 // in-place LDLᵀ of a symmetric 6x6 (lower triangle of a row-major array in registers), no pivoting.
 // On exit: strict lower triangle = L, diagonal = 1/d_k.  false if a pivot is not safely positive.
@@ -322,14 +348,25 @@ MM_HD void crystal_init(const CrystalK& k, Acc& acc, Scr& scr, CrystalLane& L) {
     L.mask = 0; L.it = 1; L.iters = 0; L.converged = false; L.bad = false; L.flip = false;
 }
 
-// one pass of the `solve` loop body (nonlinear_solver.jl:53-60): evaluate r and J at x, test, update x.
-// returns true when the point is finished (converged, out of iterations, or needs the general path).
-template <bool HASQ, class Scr>
-MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
+#ifndef MM_CRYSTAL_UNROLL
+#define MM_CRYSTAL_UNROLL 1
+#endif
+#ifndef MM_CRYSTAL_UNROLL_SMALL
+#define MM_CRYSTAL_UNROLL_SMALL 12
+#endif
+constexpr int kCrystalUnroll = MM_CRYSTAL_UNROLL, kCrystalUnrollSmall = MM_CRYSTAL_UNROLL_SMALL;
+
+// Evaluate r and J at x (the first half of a `solve` pass, nonlinear_solver.jl:54-55): on exit L.sig = σ(x), L.K = M =
+// (Eᵉ)⁻¹ + S (lower triangle), L.yp, L.mask, L.flip are set, the scratch holds c, D⁻¹r, 1/D, and yr = Σ s_i (D⁻¹r)_i Pw_i.
+// INTPOW (integer m: x^(m-1) of :111 by multiplications): branch-free over the slip systems — inactive systems run the
+// same arithmetic with ⟨Φ⟩ = 0 (p = 0, R = −t* μ), identical values, no divergence inside the pass, and the per-system
+// dependency chains (two reciprocals, one power) can overlap.  !INTPOW: general m through pow(), active systems only.
+template <bool HASQ, bool INTPOW, class Scr>
+MM_HD void crystal_evaluate(const CrystalK& k, Scr& scr, CrystalLane& L, double* yr, double* nrm2_out, bool* bad_out) {
     double sumx = 0.0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) L.sig[c] = scr(72 + c);
-#pragma unroll 1
+#pragma unroll kCrystalUnrollSmall
     for (int j = 0; j < 12; ++j) {                                                      // σ = σ_trial − Σ x_j s_j Eᵉ:MS_j   :131
         const double xj = scr(60 + j);
         const double f = xj * crystal_sign(L, j);
@@ -341,13 +378,13 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
     for (int a = 0; a < 6; ++a)
 #pragma unroll
         for (int b = 0; b <= a; ++b) L.K[a * 6 + b] = k.Cmp[a][b];
-    double yr[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) { yr[c] = 0.0; L.yp[c] = 0.0; }
     double nrm2 = 0.0;
     unsigned mask = 0;
     bool bad = false, flip = false;
-#pragma unroll 1
+    const int npow = k.m_int - 1;
+#pragma unroll kCrystalUnroll
     for (int i = 0; i < 12; ++i) {
         double pw[6];
 #pragma unroll
@@ -355,7 +392,7 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
         const double si = crystal_sign(L, i), xi = scr(60 + i);
         double kap = scr(i) + k.a_h * xi;                                               // :127 with H = a I + b 11ᵀ
         if (HASQ) kap += k.b_h * sumx;
-        const double iden = fast_rcp(1.0 + k.hk_ai * xi);
+        const double iden = INTPOW ? rcp_nc(1.0 + k.hk_ai * xi) : fast_rcp(1.0 + k.hk_ai * xi);
         const double al = (scr(12 + i) + k.H_kin * xi * si) * iden;                     // :128
         double tau = 0.0;
 #pragma unroll
@@ -363,26 +400,41 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
         const double red = tau - al;
         const double sgn = (red > 0.0) ? 1.0 : ((red < 0.0) ? -1.0 : 0.0);
         const double Phi = fabs(red) - k.tau_y - kap;                                    // :110
-        double Ri = -k.t_star * xi, p = 0.0, invD = k.mits;                            // inactive: D_ii = −t*
-        if (Phi > 0.0) {                                                                // ⟨Φ⟩ = (Φ+|Φ|)/2
-            const double xx = Phi * k.isc;
-            const double pw1 = k.m_int ? powi_(xx, k.m_int - 1) : pow(xx, k.m - 1.0);
-            Ri = k.dt * (pw1 * xx) - k.t_star * xi;                                     // :111
+        const bool act = Phi > 0.0;                                                     // ⟨Φ⟩ = (Φ+|Φ|)/2
+        double Ri, p, invD;
+        if (INTPOW) {
+            const double xx = act ? Phi * k.isc : 0.0;
+            const double pw1 = powi6_(xx, npow);
+            Ri = k.dt * (pw1 * xx) - k.t_star * xi;                                     // :111  (inactive: 0 − t* μ)
             p = k.dtm_sc * pw1;
-            mask |= (1u << i);
-            flip = flip | (sgn != si);
+            mask |= act ? (1u << i) : 0u;
+            flip = flip | (act & (sgn != si));
             const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
             // D_ii = −dD.  The Woodbury split needs D safely invertible: dD >= t*/4 (it is >= t* unless an ACTIVE system's
             // reduced stress has flipped sign against its trial value while a_h < H_kin); otherwise -> pivoted general path.
             const double dD = k.t_star + p * (sgn * dal + k.a_h);
-            bad = bad | !(dD >= 0.25 * k.t_star);
-            invD = -fast_rcp(dD);
+            bad = bad | (act & !(dD >= 0.25 * k.t_star));
+            invD = act ? -rcp_nc(dD) : k.mits;                                          // inactive: D_ii = −t*
+        } else {
+            Ri = -k.t_star * xi; p = 0.0; invD = k.mits;
+            if (act) {
+                const double xx = Phi * k.isc;
+                const double pw1 = pow(xx, k.m - 1.0);
+                Ri = k.dt * (pw1 * xx) - k.t_star * xi;
+                p = k.dtm_sc * pw1;
+                mask |= (1u << i);
+                flip = flip | (sgn != si);
+                const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
+                const double dD = k.t_star + p * (sgn * dal + k.a_h);
+                bad = bad | !(dD >= 0.25 * k.t_star);
+                invD = -fast_rcp(dD);
+            }
         }
         nrm2 += Ri * Ri;
         const double ci = p * sgn;
         const double rD = Ri * invD;
         scr(24 + i) = ci; scr(36 + i) = rD; scr(48 + i) = invD;
-        if (p != 0.0) {                      // inactive systems contribute nothing to S
+        if (INTPOW || p != 0.0) {                                                       // inactive systems contribute nothing to S
             const double w = -si * ci * invD;
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
@@ -394,7 +446,7 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
         const double srD = si * rD;
 #pragma unroll
         for (int c = 0; c < 6; ++c) yr[c] += srD * pw[c];
-        if (HASQ && p != 0.0) {
+        if (HASQ && (INTPOW || p != 0.0)) {
             const double spD = si * (k.b_h * p * invD);
 #pragma unroll
             for (int c = 0; c < 6; ++c) L.yp[c] += spD * pw[c];
@@ -402,17 +454,32 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
     }
     L.mask = mask;
     L.flip = flip;
+    *nrm2_out = nrm2;
+    *bad_out = bad;
+}
+
+// one pass of the `solve` loop body (nonlinear_solver.jl:53-60): evaluate r and J at x, test, update x.
+// returns true when the point is finished (converged, out of iterations, or needs the general path).
+// KEEPK: leave L.K = M intact for crystal_finalize (one-kernel path / host twin); otherwise M is factored in place.
+template <bool HASQ, bool INTPOW, bool KEEPK, class Scr>
+MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
+    double yr[6], nrm2;
+    bool bad;
+    crystal_evaluate<HASQ, INTPOW>(k, scr, L, yr, &nrm2, &bad);
     L.iters = L.it - 1;
     if (L.it > k.max_iter) return true;                                                  // nonlinear_solver.jl:61 (returns nothing)
     // norm(r) < tol  (nonlinear_solver.jl:56); the square root is only taken inside a rounding-width band around tol²
     if (nrm2 < k.tol2_lo || (nrm2 <= k.tol2_hi && sqrt(nrm2) < k.tol)) { L.converged = true; return true; }
     if (bad) { L.bad = true; return true; }
     // x -= J \ r                                                                        nonlinear_solver.jl:59
-    double M[36];
+    double Mc[KEEPK ? 36 : 1];
+    double* M = KEEPK ? Mc : L.K;
+    if (KEEPK) {
 #pragma unroll
-    for (int a = 0; a < 6; ++a)
+        for (int a = 0; a < 6; ++a)
 #pragma unroll
-        for (int b = 0; b <= a; ++b) M[a * 6 + b] = L.K[a * 6 + b];
+            for (int b = 0; b <= a; ++b) Mc[KEEPK ? (a * 6 + b) : 0] = L.K[a * 6 + b];
+    }
     if (!ldl6_factor(M)) { L.bad = true; return true; }
     ldl6_solve(M, yr);
     double fac = 0.0;
@@ -422,7 +489,7 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
         for (int c = 0; c < 6; ++c) ypl[c] = L.yp[c];
         ldl6_solve(M, ypl);
         double su = 0.0, sv = 0.0;
-#pragma unroll 1
+#pragma unroll kCrystalUnrollSmall
         for (int i = 0; i < 12; ++i) {
             const double ci = scr(24 + i), invD = scr(48 + i);
             double du = 0.0, dv = 0.0;
@@ -433,18 +500,15 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
         }
         fac = su * fast_rcp(1.0 - sv);
     }
-#pragma unroll 1
+#pragma unroll kCrystalUnrollSmall
     for (int i = 0; i < 12; ++i) {
-        const double ci = scr(24 + i);
-        double d = scr(36 + i);                       // (D⁻¹r)_i ; the Woodbury correction only touches systems with c_i != 0
-        if (ci != 0.0) {
-            const double invD = scr(48 + i);
-            double du = 0.0, dv = 0.0;
+        const double ci = scr(24 + i), invD = scr(48 + i);
+        double d = scr(36 + i);                       // (D⁻¹r)_i ; the Woodbury correction vanishes for c_i = 0
+        double du = 0.0, dv = 0.0;
 #pragma unroll
-            for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; if (HASQ) dv += k.Pw[i][c] * ypl[c]; }
-            d += invD * ci * du;
-            if (HASQ) d += (k.b_h * fabs(ci) * invD + invD * ci * dv) * fac;
-        }
+        for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; if (HASQ) dv += k.Pw[i][c] * ypl[c]; }
+        d += invD * ci * du;
+        if (HASQ) d += (k.b_h * fabs(ci) * invD + invD * ci * dv) * fac;
         scr(60 + i) -= d;
     }
     L.iters = L.it;
@@ -599,14 +663,34 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
 }
 
 // one point start to finish (host twin, and the non-persistent wrapper)
-template <bool HASQ, class Acc, class Scr>
-MM_HD unsigned crystal_point_fast(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
+template <bool HASQ, bool INTPOW, class Acc, class Scr>
+MM_HD unsigned crystal_point_fast_t(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
     CrystalLane L;
     crystal_init(k, acc, scr, L);
-    while (!crystal_iterate<HASQ>(k, scr, L)) {}
+    while (!crystal_iterate<HASQ, INTPOW, true>(k, scr, L)) {}
     const unsigned mask = crystal_finalize<HASQ>(k, acc, scr, L, fallback);
     *iters_out = *fallback ? 0 : L.iters;
     return mask;
+}
+template <bool HASQ, class Acc, class Scr>
+MM_HD unsigned crystal_point_fast(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
+    return k.m_int ? crystal_point_fast_t<HASQ, true>(k, acc, scr, iters_out, fallback) : crystal_point_fast_t<HASQ, false>(k, acc, scr, iters_out, fallback);
+}
+
+// Second half of the two-kernel path: the Newton kernel left the converged μ in the state output; re-evaluate there
+// (same code as the last Newton pass, so σ, M, masks are reproduced) and write all outputs — one thread per point,
+// no divergence between neighbouring points.  `acc` must offer rd_out<2>(c) (read back from the state output).
+template <bool HASQ, bool INTPOW, class Acc, class Scr>
+MM_HD unsigned crystal_finish_from_x(const CrystalK& k, Acc& acc, Scr& scr, bool converged, bool* fallback) {
+    CrystalLane L;
+    crystal_init(k, acc, scr, L);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) scr(60 + i) = acc.template rd_out<2>(30 + i);
+    double yr[6], nrm2;
+    bool bad;
+    crystal_evaluate<HASQ, INTPOW>(k, scr, L, yr, &nrm2, &bad);
+    L.converged = converged;
+    return crystal_finalize<HASQ>(k, acc, scr, L, fallback);
 }
 
 }  // namespace mm

@@ -482,29 +482,41 @@ template <int DIM, class Acc> MM_HD void xu_point(const XuK& k, Acc& acc) {
 //   𝔸_ijkl = ¼ (A_ik δ_jl + A_il δ_jk + δ_ik A_jl + δ_il A_jk)
 // =================================================================================================
 struct TransvIsoK { double L_perp, L_par, M_par, G_perp, G_par; };
+MM_HD constexpr int slot_i(int c) { return c < 3 ? c : (c < 5 ? c - 2 : 2); }       // row index of storage slot c: 0,1,2,1,2,2
+MM_HD constexpr int slot_j(int c) { return c < 3 ? 0 : (c < 5 ? 1 : 2); }           // column index:             0,0,0,1,1,2
+MM_HD constexpr int sym_slot(int i, int j) { return i >= j ? (j == 0 ? i : (j == 1 ? i + 2 : 5)) : (i == 0 ? j : (i == 1 ? j + 2 : 5)); }
 template <class Acc> MM_HD void transviso_point(const TransvIsoK& k, Acc& acc) {
     double e[6], a[3];
 #pragma unroll
     for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c);
 #pragma unroll
     for (int c = 0; c < 3; ++c) a[c] = acc.template in<1>(c);
-    const int SI[6] = {0, 1, 2, 1, 2, 2}, SJ[6] = {0, 0, 0, 1, 1, 2};
     double A[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) A[c] = a[SI[c]] * a[SJ[c]];
-    const int SIDX[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    for (int c = 0; c < 6; ++c) A[c] = a[slot_i(c)] * a[slot_j(c)];
     const double c3 = k.L_par - k.L_perp, c4 = k.M_par - 4.0 * k.G_par + 2.0 * k.G_perp - 2.0 * k.L_par + k.L_perp, c5 = k.G_par - k.G_perp;
+    double c3A[6], c5A[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { c3A[c] = c3 * A[c]; c5A[c] = c5 * A[c]; }
     double sig[6] = {0, 0, 0, 0, 0, 0};
+    // the Kronecker deltas are compile-time constants after unrolling: only the surviving terms are emitted
 #pragma unroll
     for (int J = 0; J < 6; ++J) {
         const double wJ = is_diag_slot(J) ? e[J] : 2.0 * e[J];      // ⊡ sums both (k,l) and (l,k)
 #pragma unroll
         for (int I = 0; I < 6; ++I) {
-            const int i = SI[I], j = SJ[I], kk = SI[J], l = SJ[J];
-            const double dij = (i == j), dkl = (kk == l), dik = (i == kk), djl = (j == l), dil = (i == l), djk = (j == kk);
-            const double bbA = A[SIDX[i][kk]] * djl + A[SIDX[i][l]] * djk + dik * A[SIDX[j][l]] + dil * A[SIDX[j][kk]];
-            const double v = k.L_perp * (dij * dkl) + k.G_perp * (dik * djl + dil * djk) + c3 * (dij * A[J] + A[I] * dkl) + c4 * (A[I] * A[J]) + c5 * bbA;
-            sig[I] += v * wJ;
+            const int i = slot_i(I), j = slot_j(I), kk = slot_i(J), l = slot_j(J);
+            double v = (c4 * A[I]) * A[J];
+            if (i == j && kk == l) v += k.L_perp;
+            if (i == kk && j == l) v += k.G_perp;
+            if (i == l && j == kk) v += k.G_perp;
+            if (i == j) v += c3A[J];
+            if (kk == l) v += c3A[I];
+            if (j == l) v += c5A[sym_slot(i, kk)];
+            if (j == kk) v += c5A[sym_slot(i, l)];
+            if (i == kk) v += c5A[sym_slot(j, l)];
+            if (i == l) v += c5A[sym_slot(j, kk)];
+            sig[I] = fma(v, wJ, sig[I]);
             if (acc.template has_out<1>()) acc.template out<1>(I + 6 * J, v);
         }
     }
