@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) crystal_fixup_kernel(const CrystalK k, co
 #define MM_CRYSTAL_BS 64
 #endif
 #ifndef MM_CRYSTAL_MINBLOCKS
-#define MM_CRYSTAL_MINBLOCKS 4
+#define MM_CRYSTAL_MINBLOCKS 6
 #endif
 #ifndef MM_CRYSTAL_THRESH
 #define MM_CRYSTAL_THRESH 4
@@ -134,7 +134,7 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
                 if (!L.bad) {
                     DirectAcc<LAYOUT> acc(p, N, my);
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) acc.template out<2>(30 + i, scr(60 + i));
+                    for (int i = 0; i < 12; ++i) acc.template out<2>(30 + i, scr(XS + i));
                 }
                 active[my] = (uint16_t)(L.bad ? MM_ACTIVE_NEEDS_GENERAL : (L.converged ? 0u : MM_ACTIVE_FAILED));
                 if (iters) iters[my] = (uint8_t)(L.bad ? 0 : (L.iters > 255 ? 255 : L.iters));

@@ -242,8 +242,14 @@ MM_HD double powi6_(double b, int n) {
     double r = (n & 1) ? b : 1.0;
 #pragma unroll
     for (int bit = 1; bit < 6; ++bit) {
+#if defined(__CUDA_ARCH__)
+        // predicated multiplies: n is uniform, so these are @P DMUL (no select pairs, no FP64 pipe time when off)
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p mul.f64 %0, %0, %1;\n\t}" : "+d"(b) : "d"(b), "r"(n >> bit));
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p mul.f64 %0, %0, %1;\n\t}" : "+d"(r) : "d"(b), "r"((n >> bit) & 1));
+#else
         if ((n >> bit) != 0) b *= b;
         if ((n >> bit) & 1) r *= b;
+#endif
     }
     return r;
 }
@@ -303,9 +309,10 @@ MM_HD void ldl6_solve(const double* M, double* b) {
 // ---- the structured path in three phases, so that a persistent warp can interleave points (mm_crystal.cu) ----
 // Per-lane state: everything indexed by slip system lives in the scratch column (run-time indexed, rolled loops =>
 // small code, no instruction-cache thrash); registers hold only the 6x6 M, σ and a few scalars.
-// Scratch slots: [0,12) κₙ [12,24) αₙ [24,36) c=p·sgn [36,48) D⁻¹r [48,60) 1/D [60,72) x=μ [72,78) σ_trial
+// Scratch slots: [0,12) κₙ [12,24) αₙ [24,36) g = c/D = p·sgn/D_ii [36,48) D⁻¹r [48,60) x=μ [60,66) σ_trial
 #undef MM_CRYSTAL_SCRATCH
-#define MM_CRYSTAL_SCRATCH 78
+#define MM_CRYSTAL_SCRATCH 66
+constexpr int XS = 48, SIGT = 60;
 
 struct CrystalLane {
     double K[36];          // lower triangle of M = (Eᵉ)⁻¹ + S at the last evaluation (kept for the tangent)
@@ -331,13 +338,13 @@ MM_HD void crystal_init(const CrystalK& k, Acc& acc, Scr& scr, CrystalLane& L) {
         for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c);
         const double ltr = k.lam * tr6(e);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) { st[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c])); scr(72 + c) = st[c]; }
+        for (int c = 0; c < 6; ++c) { st[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c])); scr(SIGT + c) = st[c]; }
     }
     L.spos = 0; L.sneg = 0;
 #pragma unroll
     for (int i = 0; i < 12; ++i) {                                                      // :120-121
         const double kn = acc.template in<1>(6 + i), an = acc.template in<1>(18 + i);
-        scr(i) = kn; scr(12 + i) = an; scr(60 + i) = acc.template in<1>(30 + i);
+        scr(i) = kn; scr(12 + i) = an; scr(XS + i) = acc.template in<1>(30 + i);
         double tau = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) tau += st[c] * k.Pw[i][c];
@@ -365,10 +372,10 @@ template <bool HASQ, bool INTPOW, class Scr>
 MM_HD void crystal_evaluate(const CrystalK& k, Scr& scr, CrystalLane& L, double* yr, double* nrm2_out, bool* bad_out) {
     double sumx = 0.0;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) L.sig[c] = scr(72 + c);
+    for (int c = 0; c < 6; ++c) L.sig[c] = scr(SIGT + c);
 #pragma unroll kCrystalUnrollSmall
     for (int j = 0; j < 12; ++j) {                                                      // σ = σ_trial − Σ x_j s_j Eᵉ:MS_j   :131
-        const double xj = scr(60 + j);
+        const double xj = scr(XS + j);
         const double f = xj * crystal_sign(L, j);
         if (HASQ) sumx += xj;
 #pragma unroll
@@ -389,7 +396,7 @@ MM_HD void crystal_evaluate(const CrystalK& k, Scr& scr, CrystalLane& L, double*
         double pw[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) pw[c] = k.Pw[i][c];
-        const double si = crystal_sign(L, i), xi = scr(60 + i);
+        const double si = crystal_sign(L, i), xi = scr(XS + i);
         double kap = scr(i) + k.a_h * xi;                                               // :127 with H = a I + b 11ᵀ
         if (HASQ) kap += k.b_h * sumx;
         const double iden = INTPOW ? rcp_nc(1.0 + k.hk_ai * xi) : fast_rcp(1.0 + k.hk_ai * xi);
@@ -433,9 +440,10 @@ MM_HD void crystal_evaluate(const CrystalK& k, Scr& scr, CrystalLane& L, double*
         nrm2 += Ri * Ri;
         const double ci = p * sgn;
         const double rD = Ri * invD;
-        scr(24 + i) = ci; scr(36 + i) = rD; scr(48 + i) = invD;
+        const double g = ci * invD;                                                     // invD < 0 always, so sign(c_i) = −sign(g_i)
+        scr(24 + i) = g; scr(36 + i) = rD;
         if (INTPOW || p != 0.0) {                                                       // inactive systems contribute nothing to S
-            const double w = -si * ci * invD;
+            const double w = -si * g;
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
                 const double wa = w * pw[a];
@@ -468,9 +476,9 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
     crystal_evaluate<HASQ, INTPOW>(k, scr, L, yr, &nrm2, &bad);
     L.iters = L.it - 1;
     if (L.it > k.max_iter) return true;                                                  // nonlinear_solver.jl:61 (returns nothing)
+    if (bad) { L.bad = true; return true; }                                              // D not safely invertible -> general path
     // norm(r) < tol  (nonlinear_solver.jl:56); the square root is only taken inside a rounding-width band around tol²
     if (nrm2 < k.tol2_lo || (nrm2 <= k.tol2_hi && sqrt(nrm2) < k.tol)) { L.converged = true; return true; }
-    if (bad) { L.bad = true; return true; }
     // x -= J \ r                                                                        nonlinear_solver.jl:59
     double Mc[KEEPK ? 36 : 1];
     double* M = KEEPK ? Mc : L.K;
@@ -491,25 +499,25 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
         double su = 0.0, sv = 0.0;
 #pragma unroll kCrystalUnrollSmall
         for (int i = 0; i < 12; ++i) {
-            const double ci = scr(24 + i), invD = scr(48 + i);
+            const double g = scr(24 + i);
             double du = 0.0, dv = 0.0;
 #pragma unroll
             for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; dv += k.Pw[i][c] * ypl[c]; }
-            su += scr(36 + i) + invD * ci * du;
-            sv += k.b_h * fabs(ci) * invD + invD * ci * dv;
+            su += scr(36 + i) + g * du;
+            sv += g * dv - k.b_h * fabs(g);
         }
         fac = su * fast_rcp(1.0 - sv);
     }
 #pragma unroll kCrystalUnrollSmall
     for (int i = 0; i < 12; ++i) {
-        const double ci = scr(24 + i), invD = scr(48 + i);
+        const double g = scr(24 + i);
         double d = scr(36 + i);                       // (D⁻¹r)_i ; the Woodbury correction vanishes for c_i = 0
         double du = 0.0, dv = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) { du += k.Pw[i][c] * yr[c]; if (HASQ) dv += k.Pw[i][c] * ypl[c]; }
-        d += invD * ci * du;
-        if (HASQ) d += (k.b_h * fabs(ci) * invD + invD * ci * dv) * fac;
-        scr(60 + i) -= d;
+        d += g * du;
+        if (HASQ) d += (g * dv - k.b_h * fabs(g)) * fac;
+        scr(XS + i) -= d;
     }
     L.iters = L.it;
     L.it += 1;
@@ -527,11 +535,11 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
     double sumx = 0.0;
     if (HASQ) {
 #pragma unroll 1
-        for (int j = 0; j < 12; ++j) sumx += scr(60 + j);
+        for (int j = 0; j < 12; ++j) sumx += scr(XS + j);
     }
 #pragma unroll 1
     for (int i = 0; i < 12; ++i) {
-        const double xi = scr(60 + i);
+        const double xi = scr(XS + i);
         double kap = scr(i) + k.a_h * xi;
         if (HASQ) kap += k.b_h * sumx;
         const double al = (scr(12 + i) + k.H_kin * xi * crystal_sign(L, i)) * fast_rcp(1.0 + k.hk_ai * xi);
@@ -552,7 +560,7 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
                 for (int a = 0; a < 36; ++a) Sg[a] = 0.0;
 #pragma unroll 1
                 for (int i = 0; i < 12; ++i) {
-                    const double w = -fabs(scr(24 + i)) * scr(48 + i);          // p_i / dD_i
+                    const double w = fabs(scr(24 + i));                         // p_i / dD_i = |c_i / D_ii|
                     if (w != 0.0) {
 #pragma unroll
                         for (int a = 0; a < 6; ++a) {
@@ -603,11 +611,11 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
                 ldl6_solve(L.K, L.yp);
 #pragma unroll 1
                 for (int i = 0; i < 12; ++i) {
-                    const double ci = scr(24 + i), invD = scr(48 + i);
+                    const double g = scr(24 + i);
                     double dv = 0.0;
 #pragma unroll
                     for (int c = 0; c < 6; ++c) dv += k.Pw[i][c] * L.yp[c];
-                    svq += k.b_h * fabs(ci) * invD + invD * ci * dv;
+                    svq += g * dv - k.b_h * fabs(g);
                 }
             }
         }
@@ -622,7 +630,7 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
                 double z[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
                 for (int j = 0; j < 12; ++j) {
-                    const double rD = scr(24 + j) * k.EM[j][Jc] * scr(48 + j);
+                    const double rD = scr(24 + j) * k.EM[j][Jc];
                     scr(36 + j) = rD;
                     const double srD = crystal_sign(L, j) * rD;
 #pragma unroll
@@ -635,22 +643,22 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
                     double du = 0.0;
 #pragma unroll
                     for (int c = 0; c < 6; ++c) du += k.Pw[i][c] * z[c];
-                    const double Zi = scr(36 + i) + scr(48 + i) * scr(24 + i) * du;
+                    const double Zi = scr(36 + i) + scr(24 + i) * du;
                     scr(36 + i) = Zi;
                     sz += Zi;
                 }
                 const double qf = HASQ ? sz * ifq : 0.0;
 #pragma unroll 1
                 for (int i = 0; i < 12; ++i) {
-                    const double ci = scr(24 + i);
+                    const double g = scr(24 + i);
                     double Zi = scr(36 + i);
                     if (HASQ) {
                         double dv = 0.0;
 #pragma unroll
                         for (int c = 0; c < 6; ++c) dv += k.Pw[i][c] * L.yp[c];
-                        Zi += (k.b_h * fabs(ci) * scr(48 + i) + scr(48 + i) * ci * dv) * qf;
+                        Zi += (g * dv - k.b_h * fabs(g)) * qf;
                     }
-                    const double sgnZ = (ci > 0.0) ? Zi : ((ci < 0.0) ? -Zi : 0.0);      // sgn_i Z_i (sgn_i = sign c_i on active systems)
+                    const double sgnZ = (g < 0.0) ? Zi : ((g > 0.0) ? -Zi : 0.0);        // sgn_i Z_i (sgn_i = sign c_i = −sign g_i on active systems)
 #pragma unroll
                     for (int Ic = 0; Ic < 6; ++Ic) col[Ic] += k.EM[i][Ic] * sgnZ;
                 }
@@ -685,10 +693,11 @@ MM_HD unsigned crystal_finish_from_x(const CrystalK& k, Acc& acc, Scr& scr, bool
     CrystalLane L;
     crystal_init(k, acc, scr, L);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) scr(60 + i) = acc.template rd_out<2>(30 + i);
+    for (int i = 0; i < 12; ++i) scr(XS + i) = acc.template rd_out<2>(30 + i);
     double yr[6], nrm2;
     bool bad;
     crystal_evaluate<HASQ, INTPOW>(k, scr, L, yr, &nrm2, &bad);
+    if (bad) { *fallback = true; return 0; }
     L.converged = converged;
     return crystal_finalize<HASQ>(k, acc, scr, L, fallback);
 }
