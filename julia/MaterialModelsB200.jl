@@ -87,7 +87,16 @@ end
 _model(::NeoHook) = Cint(0); _model(::Yeoh) = Cint(1); _model(::StVenant) = Cint(2)
 _hyper(m::NeoHook) = MMHyper(m.λ, m.μ, 0.0, 0.0); _hyper(m::StVenant) = MMHyper(m.λ, m.μ, 0.0, 0.0)
 _hyper(m::Yeoh) = MMHyper(m.λ, m.μ, m.c₂, m.c₃)
-function material_response(::MaterialModels.∂S∂C, m::Union{NeoHook,Yeoh,StVenant}, F::DeformationGradient{<:CuMatrix{Float64}},
+# The reference's strain wrappers are typed on single tensors (`DeformationGradient{T<:Tensor{2}}`, src/traits.jl:2-6), so the
+# batched arrays get a wrapper of their own that carries the measure as a type parameter; the outer constructors keep the
+# reference's spelling: DeformationGradient(F::CuMatrix), RightCauchyGreen(C::CuMatrix), GreenLagrange(E::CuMatrix).
+struct BatchedStrain{K<:MaterialModels.StrainMeasure,A<:AbstractMatrix{Float64}}
+    value::A
+end
+MaterialModels.DeformationGradient(F::AbstractMatrix{Float64}) = BatchedStrain{DeformationGradient,typeof(F)}(F)
+MaterialModels.RightCauchyGreen(C::AbstractMatrix{Float64}) = BatchedStrain{RightCauchyGreen,typeof(C)}(C)
+MaterialModels.GreenLagrange(E::AbstractMatrix{Float64}) = BatchedStrain{GreenLagrange,typeof(E)}(E)
+function material_response(::MaterialModels.∂S∂C, m::Union{NeoHook,Yeoh,StVenant}, F::BatchedStrain{DeformationGradient,<:CuMatrix{Float64}},
                            state, Δt::Float64 = 0.0; layout = MM_LAYOUT_AOS, cache = nothing, options = nothing)
     N = layout == MM_LAYOUT_AOS ? size(F.value, 2) : size(F.value, 1)
     S = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, 6, N) : CUDA.zeros(Float64, N, 6)
@@ -111,8 +120,115 @@ function material_response(m::XuNeedleman, Δ::CuMatrix{Float64}, state = XuNeed
     return T, dTdΔ, state
 end
 
+# Trait routes with another output measure (src/traits.jl:61-77): ∂S∂E (tangent_kind 1) and ∂Pᵀ∂F (tangent_kind 2,
+# Pᵀ 9 x N, ∂Pᵀ∂F 81 x N) through mm_hyper_ex; strain_kind 0 = C, 1 = F, 2 = E.
+_tk(::MaterialModels.∂S∂C) = Cint(0); _tk(::MaterialModels.∂S∂E) = Cint(1); _tk(::MaterialModels.∂Pᵀ∂F) = Cint(2)
+_sk(::BatchedStrain{RightCauchyGreen}) = Cint(0); _sk(::BatchedStrain{DeformationGradient}) = Cint(1); _sk(::BatchedStrain{GreenLagrange}) = Cint(2)
+function material_response(t::Union{MaterialModels.∂S∂E,MaterialModels.∂Pᵀ∂F}, m::Union{NeoHook,Yeoh,StVenant},
+                           strain::BatchedStrain{<:Any,<:CuMatrix{Float64}}, state, Δt::Float64 = 0.0;
+                           layout = MM_LAYOUT_AOS, cache = nothing, options = nothing)
+    N = layout == MM_LAYOUT_AOS ? size(strain.value, 2) : size(strain.value, 1)
+    ns, nt = t isa MaterialModels.∂Pᵀ∂F ? (9, 81) : (6, 36)
+    S = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, ns, N) : CUDA.zeros(Float64, N, ns)
+    T = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, nt, N) : CUDA.zeros(Float64, N, nt)
+    check(ccall((:mm_hyper_ex, libmmb200), Cint,
+                (Cint, Ref{MMHyper}, CuPtr{Cdouble}, Cint, Cint, CuPtr{Cdouble}, CuPtr{Cdouble}, Int64, Cint, Ptr{Cvoid}),
+                _model(m), Ref(_hyper(m)), strain.value, _sk(strain), _tk(t), S, T, N, layout, CUDA.stream().handle), "mm_hyper_ex")
+    return S, T, state
+end
+
+# elastic_strain_energy_density (LinearElastic.jl:63; neohook.jl:29, yeoh.jl:31, stvenant.jl:28; traits.jl:133-136): ψ[N]
+function MaterialModels.elastic_strain_energy_density(m::Union{NeoHook,Yeoh,StVenant}, strain::BatchedStrain{<:Any,<:CuMatrix{Float64}};
+                                                      layout = MM_LAYOUT_AOS)
+    N = layout == MM_LAYOUT_AOS ? size(strain.value, 2) : size(strain.value, 1)
+    ψ = CUDA.zeros(Float64, N)
+    check(ccall((:mm_hyper_energy, libmmb200), Cint, (Cint, Ref{MMHyper}, CuPtr{Cdouble}, Cint, CuPtr{Cdouble}, Int64, Cint, Ptr{Cvoid}),
+                _model(m), Ref(_hyper(m)), strain.value, _sk(strain), ψ, N, layout, CUDA.stream().handle), "mm_hyper_energy")
+    return ψ
+end
+function MaterialModels.elastic_strain_energy_density(m::LinearElastic, ε::CuMatrix{Float64}; layout = MM_LAYOUT_AOS)
+    N = layout == MM_LAYOUT_AOS ? size(ε, 2) : size(ε, 1)
+    ψ = CUDA.zeros(Float64, N)
+    check(ccall((:mm_linear_elastic_energy, libmmb200), Cint, (Ref{MMLinearElastic}, CuPtr{Cdouble}, CuPtr{Cdouble}, Int64, Cint, Ptr{Cvoid}),
+                Ref(MMLinearElastic(m.E, m.ν)), ε, ψ, N, layout, CUDA.stream().handle), "mm_linear_elastic_energy")
+    return ψ
+end
+
+# TransverselyIsotropic (src/transverselyisotropic.jl:92-106): the state is the unit direction a3 per point (3 x N)
+struct MMTransverselyIsotropic; L_perp::Cdouble; L_par::Cdouble; M_par::Cdouble; G_perp::Cdouble; G_par::Cdouble; end
+struct BatchedTransverselyIsotropicState{A<:AbstractMatrix{Float64}} <: AbstractMaterialState
+    a3::A
+    layout::Cint
+end
+function material_response(m::TransverselyIsotropic, ε::CuMatrix{Float64}, state::BatchedTransverselyIsotropicState, Δt = nothing;
+                           cache = nothing, options = nothing)
+    layout = state.layout
+    N = layout == MM_LAYOUT_AOS ? size(ε, 2) : size(ε, 1)
+    σ = similar(ε)
+    E = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, 36, N) : CUDA.zeros(Float64, N, 36)
+    check(ccall((:mm_transversely_isotropic, libmmb200), Cint,
+                (Ref{MMTransverselyIsotropic}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, Int64, Cint, Ptr{Cvoid}),
+                Ref(MMTransverselyIsotropic(m.L⊥, m.L₌, m.M₌, m.G⊥, m.G₌)), ε, state.a3, σ, E, N, layout, CUDA.stream().handle),
+          "mm_transversely_isotropic")
+    return σ, E, state
+end
+
+# Dimension wrappers (src/wrappers.jl:29-79) around Plastic: dim_kind 1 UniaxialStrain, 2 PlaneStrain, 3 UniaxialStress,
+# 4 PlaneStress, 5 ShellStress; reduced arrays have nc = mm_wrap_ncomp(kind) components (1, 3 or 6).
+_dimkind(::UniaxialStrain) = Cint(1); _dimkind(::PlaneStrain) = Cint(2); _dimkind(::UniaxialStress) = Cint(3)
+_dimkind(::PlaneStress) = Cint(4); _dimkind(::ShellStress) = Cint(5)
+function material_response(dim::MaterialModels.AbstractDim, m::Plastic, Δε::CuMatrix{Float64}, state::BatchedPlasticState, Δt = nothing;
+                           cache = nothing, options::Dict{Symbol,Any} = Dict{Symbol,Any}())
+    kind = _dimkind(dim); layout = state.layout
+    nc = Int(ccall((:mm_wrap_ncomp, libmmb200), Cint, (Cint,), kind))
+    N = layout == MM_LAYOUT_AOS ? size(Δε, 2) : size(Δε, 1)
+    σ = similar(Δε)
+    T = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, nc * nc, N) : CUDA.zeros(Float64, N, nc * nc)
+    new = similar(state.data)
+    flags = CUDA.zeros(UInt8, N); iters = CUDA.zeros(UInt8, N); outer = CUDA.zeros(UInt8, N); nfail = CUDA.zeros(Int32, 1)
+    inner = MMNewtonOpts(1e-8, 1000, 0)
+    wrap = MMNewtonOpts(get(options, :plane_stress_tol, 1e-8), get(options, :plane_stress_max_iter, 10), 0)        # wrappers.jl:55-56
+    check(ccall((:mm_wrapped_plastic, libmmb200), Cint,
+                (Cint, Ref{MMPlastic}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt8}, CuPtr{UInt8},
+                 CuPtr{UInt8}, CuPtr{Int32}, Ref{MMNewtonOpts}, Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
+                kind, Ref(MMPlastic(m)), Δε, state.data, σ, T, new, flags, iters, outer, nfail, Ref(inner), Ref(wrap), N, layout,
+                CUDA.stream().handle), "mm_wrapped_plastic")
+    if Array(nfail)[1] != 0
+        any(Array(flags) .& 0x40 .!= 0) && error("Not converged. Could not find plane stress state.")              # wrappers.jl:78
+        error("Material model not converged. Could not find material state.")                                      # Plastic.jl:157
+    end
+    return σ, T, BatchedPlasticState(new, layout)
+end
+
 # CrystalViscoPlastic{12} (CrystalViscoPlastic.jl:64-94): the MMCrystal struct (scalars, nslip, MS[12][9], H[12][12]) is
 # filled from `m.MS` and `m.H` directly (same memory order: MS[i] column-major Tensor{2,3}; H[i][j] = m.H[i,j]).
-# mm_crystal(p, Δε, Δt, state_in, σ, tan, state_out, active, iters, n_fail, opts, N, layout, stream) — see INTEGRATION.md.
+struct MMCrystal
+    E::Cdouble; nu::Cdouble; tau_y::Cdouble; H_iso::Cdouble; H_kin::Cdouble; q::Cdouble; alpha_inf::Cdouble; t_star::Cdouble; sigma_c::Cdouble; m::Cdouble
+    nslip::Int32; pad::Int32
+    MS::NTuple{108,Cdouble}          # MS[i][0:9], i = 0..11
+    H::NTuple{144,Cdouble}           # H[i][j] = m.H[i+1, j+1]
+end
+MMCrystal(m::CrystalViscoPlastic{12}) = MMCrystal(m.E, m.ν, m.τ_y, m.H_iso, m.H_kin, m.q, m.α_∞, m.t_star, m.σ_c, m.m, 12, 0,
+    ntuple(n -> m.MS[(n - 1) ÷ 9 + 1][(n - 1) % 9 + 1], 108), ntuple(n -> m.H[(n - 1) ÷ 12 + 1, (n - 1) % 12 + 1], 144))
+struct BatchedCrystalState{A<:AbstractMatrix{Float64}} <: AbstractMaterialState
+    data::A          # AoS: 42 x N (σ, κ, α, μ);  SoA: N x 42
+    layout::Cint
+end
+function material_response(m::CrystalViscoPlastic{12}, Δε::CuMatrix{Float64}, state::BatchedCrystalState, Δt = 1.0;
+                           cache = nothing, options = NamedTuple())
+    layout = state.layout
+    N = layout == MM_LAYOUT_AOS ? size(Δε, 2) : size(Δε, 1)
+    σ = similar(Δε)
+    T = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, 36, N) : CUDA.zeros(Float64, N, 36)
+    new = similar(state.data)
+    active = CUDA.zeros(UInt16, N); iters = CUDA.zeros(UInt8, N); nfail = CUDA.zeros(Int32, 1)
+    opts = MMNewtonOpts(get(options, :tol, 1e-8), get(options, :max_iter, 100), 0)                                  # nonlinear_solver.jl:52
+    check(ccall((:mm_crystal, libmmb200), Cint,
+                (Ref{MMCrystal}, CuPtr{Cdouble}, Cdouble, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt16}, CuPtr{UInt8},
+                 CuPtr{Int32}, Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
+                Ref(MMCrystal(m)), Δε, Float64(Δt), state.data, σ, T, new, active, iters, nfail, Ref(opts), N, layout, CUDA.stream().handle), "mm_crystal")
+    Array(nfail)[1] == 0 || error("Material model not converged. Could not find material state.")                  # CrystalViscoPlastic.jl:92
+    return σ, T, BatchedCrystalState(new, layout)
+end
 
 end # module
