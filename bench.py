@@ -374,7 +374,7 @@ def other_configs(mm, torch, dev, peak):
         f64 = fp64_peak_tflops()
         rec("c3_crystal_fcc12_stepB", N, 1056, ms, mean_newton_updates=float(it.mean().item()), frac_points_with_active_slip=float((stB.flags != 0).float().mean().item()),
             n_not_converged=int(stB.n_fail.item()), reference_algorithm_tflops=round(ref_flops / (ms * 1e-3) / 1e12, 2), fp64_fma_peak_tflops_measured=f64,
-            bound="fp64 / latency (not HBM): see profiles/r01_crystal_persistent_ncu_full.txt")
+            bound="fp64 / latency (not HBM): see profiles/r01_crystal_two_kernel_ncu_full.txt")
     except Exception as e:       # informational block must never cost the headline line
         out["error"] = repr(e)
     return out
