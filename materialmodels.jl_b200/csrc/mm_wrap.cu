@@ -43,7 +43,10 @@ template <int KIND> struct WrappedPlasticOp {
         if ((flag & 0xC0) && n_fail) atomicAdd(n_fail, 1);
     }
 };
-template <int KIND> struct MinBlocks<WrappedPlasticOp<KIND>> { static constexpr int value = 2, block = 128; };
+#ifndef MM_WRAP_MINBLOCKS
+#define MM_WRAP_MINBLOCKS 3
+#endif
+template <int KIND> struct MinBlocks<WrappedPlasticOp<KIND>> { static constexpr int value = MM_WRAP_MINBLOCKS, block = 128; };
 
 template <int KIND>
 int launch_wrapped_elastic(const MMLinearElastic* p, const double* eps, double* sig, double* tan, uint8_t* oit, int32_t* n_fail, const MMNewtonOpts* w,
