@@ -26,6 +26,8 @@ def init_process_group(backend=None):
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
             if backend == "nccl":
+                # NCCL writes its banner / debug lines to stdout unless told otherwise; the bench's stdout is one JSON line
+                os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mmb200_nccl.%h.%p.log")
                 torch.cuda.set_device(local)
                 dist.init_process_group(backend=backend, device_id=torch.device("cuda", local))
             else:
