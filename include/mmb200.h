@@ -158,6 +158,10 @@ int mm_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const doub
 int mm_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red,
                        double* state_out, uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
                        const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
+/* the same wrappers around TransverselyIsotropic (wrappers.jl is generic in the material); a3[3] per point is the state */
+int mm_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropic* p, const double* eps_red, const double* a3,
+                                      double* sig_red, double* tan_red, uint8_t* outer_iters, int32_t* n_fail,
+                                      const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
 
 /* ---- TransverselyIsotropic — reference src/transverselyisotropic.jl -----------------------
  * TransverselyIsotropic(; E_L, E_T, G_LT, ν_LT, ν_TT) (:39-53) and material_response(m, ε, state) (:92-106): the stiffness is
@@ -187,6 +191,14 @@ int mmh_hyper(int model, const MMHyper* p, const double* strain, int strain_kind
 int mmh_crystal(const MMCrystal* p, const double* deps, double dt, const double* state_in, double* sig, double* tan,
                 double* state_out, uint16_t* active, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
 int mmh_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, double* dTdD, int dim, int64_t N, int layout);
+int mmh_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const double* eps_red, double* sig_red, double* tan_red,
+                               uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* wrapper_opts, int64_t N, int layout);
+int mmh_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red,
+                        double* state_out, uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
+                        const MMNewtonOpts* wrapper_opts, int64_t N, int layout);
+int mmh_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropic* p, const double* eps_red, const double* a3,
+                                       double* sig_red, double* tan_red, uint8_t* outer_iters, int32_t* n_fail,
+                                       const MMNewtonOpts* wrapper_opts, int64_t N, int layout);
 int mmh_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent,
                  int64_t N, int layout);
 int mmh_transversely_isotropic(const MMTransverselyIsotropic* p, const double* eps, const double* a3, double* sig, double* tan,

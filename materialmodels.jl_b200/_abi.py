@@ -71,6 +71,11 @@ SIGNATURES = {
     "mm_wrapped_linear_elastic": (C.c_int, [C.c_int, C.POINTER(MMLinearElastic), _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int, _P]),
     "mm_wrapped_plastic": (C.c_int, [C.c_int, C.POINTER(MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), C.POINTER(MMNewtonOpts),
                                      _I64, C.c_int, _P]),
+    "mm_wrapped_transversely_isotropic": (C.c_int, [C.c_int, C.POINTER(MMTransverselyIsotropic), _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int, _P]),
+    "mmh_wrapped_linear_elastic": (C.c_int, [C.c_int, C.POINTER(MMLinearElastic), _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int]),
+    "mmh_wrapped_plastic": (C.c_int, [C.c_int, C.POINTER(MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), C.POINTER(MMNewtonOpts),
+                                      _I64, C.c_int]),
+    "mmh_wrapped_transversely_isotropic": (C.c_int, [C.c_int, C.POINTER(MMTransverselyIsotropic), _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int]),
     "mm_transversely_isotropic_setup": (C.c_int, [C.c_double] * 5 + [C.POINTER(MMTransverselyIsotropic)]),
     "mm_transversely_isotropic": (C.c_int, [C.POINTER(MMTransverselyIsotropic), _P, _P, _P, _P, _I64, C.c_int, _P]),
     "mm_linear_elastic_energy": (C.c_int, [C.POINTER(MMLinearElastic), _P, _P, _I64, C.c_int, _P]),

@@ -461,54 +461,68 @@ def _response_xu(m, Δ, state, layout, want_tangent):
 
 def _response_wrapped(dim, m, Δε, state, options, layout, want_tangent):
     """material_response(dim::AbstractDim, m, Δε, state, Δt; cache, options) — reference src/wrappers.jl:29-79
-    (device arrays only; LinearElastic and Plastic)."""
+    (LinearElastic, Plastic, TransverselyIsotropic; device arrays -> mm_wrapped_*, numpy arrays -> mmh_wrapped_*)."""
     kind = dim.KIND
-    nc = load().mm_wrap_ncomp(kind)
+    lib = load()
+    nc = lib.mm_wrap_ncomp(kind)
     wtol, wmax = 1e-8, 10                                            # wrappers.jl:55-56
     if options:
         wtol = float(options.get("plane_stress_tol", options.get(":plane_stress_tol", wtol)))
         wmax = int(options.get("plane_stress_max_iter", options.get(":plane_stress_max_iter", wmax)))
     w = _abi.MMNewtonOpts(wtol, wmax, 0)
-    if isinstance(m, Plastic):
+    if isinstance(m, (Plastic, TransverselyIsotropic)):
+        if state is None:
+            raise ValueError("material_response(dim, ::%s, Δε, state): state required" % type(m).__name__)
         layout = state.layout
     Δε = _prep(Δε)
-    if _is_host(Δε):
-        raise NotImplementedError("dimension wrappers: device (torch CUDA) arrays only")
+    host = _is_host(Δε)
     N = _npoints(Δε, nc, layout)
-    torch = _torch()
+    u8 = np.uint8 if host else _torch().uint8
     σ = _empty(_shape(nc, N, layout), Δε)
     tan = _empty(_shape(nc * nc, N, layout), Δε) if want_tangent else None
-    oit = _empty((N,), Δε, torch.uint8)
-    nfail = _zeros((1,), Δε, torch.int32)
-    lib = load()
+    oit = _empty((N,), Δε, u8)
+    nfail = _zeros((1,), Δε, np.int32 if host else _torch().int32)
     defer = bool(options and options.get("defer_check"))
+    lay = _LAYOUTS[layout]
+    tail = () if host else (_stream(Δε),)
+    flags = None
     with _DeviceGuard(Δε):
         if isinstance(m, LinearElastic):
-            rc = lib.mm_wrapped_linear_elastic(kind, ctypes.byref(m._c), _ptr(Δε), _ptr(σ), _ptr(tan), _ptr(oit), _ptr(nfail), ctypes.byref(w),
-                                               N, _LAYOUTS[layout], _stream(Δε))
-            check(rc, "mm_wrapped_linear_elastic")
+            fn = lib.mmh_wrapped_linear_elastic if host else lib.mm_wrapped_linear_elastic
+            check(fn(kind, ctypes.byref(m._c), _ptr(Δε), _ptr(σ), _ptr(tan), _ptr(oit), _ptr(nfail), ctypes.byref(w), N, lay, *tail), "mm_wrapped_linear_elastic")
             new = state if state is not None else LinearElasticState()
-            flags = None
+        elif isinstance(m, TransverselyIsotropic):
+            if N != state.N:
+                raise ValueError("strain has %d points, state has %d" % (N, state.N))
+            a3 = _prep(state.data)
+            if _is_host(a3) != host:
+                raise ValueError("strain and state must live in the same place")
+            fn = lib.mmh_wrapped_transversely_isotropic if host else lib.mm_wrapped_transversely_isotropic
+            check(fn(kind, ctypes.byref(m._c), _ptr(Δε), _ptr(a3), _ptr(σ), _ptr(tan), _ptr(oit), _ptr(nfail), ctypes.byref(w), N, lay, *tail),
+                  "mm_wrapped_transversely_isotropic")
+            new = state
         elif isinstance(m, Plastic):
-            if state is None or N != state.N:
+            if N != state.N:
                 raise ValueError("material_response(dim, ::Plastic, Δε, state): state with %d points required" % N)
             sin = _prep(state.data)
+            if _is_host(sin) != host:
+                raise ValueError("strain and state must live in the same place")
             sout = _empty(_shape(14, N, layout), Δε)
-            flags = _empty((N,), Δε, torch.uint8)
-            iters = _empty((N,), Δε, torch.uint8)
+            flags = _empty((N,), Δε, u8)
+            iters = _empty((N,), Δε, u8)
             o = _newton_opts(m, options)
-            rc = lib.mm_wrapped_plastic(kind, ctypes.byref(m._c), _ptr(Δε), _ptr(sin), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(flags), _ptr(iters),
-                                        _ptr(oit), _ptr(nfail), ctypes.byref(o), ctypes.byref(w), N, _LAYOUTS[layout], _stream(Δε))
-            check(rc, "mm_wrapped_plastic")
+            fn = lib.mmh_wrapped_plastic if host else lib.mm_wrapped_plastic
+            check(fn(kind, ctypes.byref(m._c), _ptr(Δε), _ptr(sin), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(flags), _ptr(iters), _ptr(oit), _ptr(nfail),
+                     ctypes.byref(o), ctypes.byref(w), N, lay, *tail), "mm_wrapped_plastic")
             new = PlasticState(sout, layout)
             new.flags, new.iters, new.n_fail = flags, iters, nfail
         else:
-            raise NotImplementedError("dimension wrappers are implemented for LinearElastic and Plastic")
+            raise NotImplementedError("dimension wrappers are implemented for LinearElastic, Plastic and TransverselyIsotropic")
     if hasattr(new, "__dict__"):
         new.outer_iters = oit
         new.n_fail = nfail
-    if not defer and int(nfail.item()) != 0:
-        if flags is None or bool((flags & _abi.MM_FLAG_WRAPPER_FAILED).any().item()):
+    if not defer and (int(nfail[0]) if host else int(nfail.item())) != 0:
+        if flags is None or bool((flags & _abi.MM_FLAG_WRAPPER_FAILED).any()):
             raise RuntimeError(PLANE_STRESS_NOT_CONVERGED)
         raise RuntimeError(NOT_CONVERGED)
     return σ, tan, new

@@ -171,6 +171,44 @@ int mmh_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, doub
     });
 }
 
+int mmh_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const double* eps_red, double* sig_red, double* tan_red, uint8_t* outer_iters,
+                               int32_t* n_fail, const MMNewtonOpts* wrapper_opts, int64_t N, int layout) {
+    const int nc = mm_wrap_ncomp(dim_kind);
+    if (nc < 0) return nc;
+    if (!p || N < 0 || (N > 0 && (!eps_red || !sig_red))) return set_error(MM_ERR_ARG, "mmh_wrapped_linear_elastic: bad argument");
+    Arr a[4] = {in_arr(eps_red, nc), out_arr(sig_red, nc), out_arr(tan_red, nc * nc), out_arr(outer_iters, 1, 1, false)};
+    return pipeline(a, 4, N, layout, n_fail, [&](int s, int64_t n, cudaStream_t st) {
+        return mm_wrapped_linear_elastic(dim_kind, p, (const double*)a[0].d[s], (double*)a[1].d[s], (double*)a[2].d[s], (uint8_t*)a[3].d[s], g_ws.d_fail,
+                                         wrapper_opts, n, layout, st);
+    });
+}
+
+int mmh_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red, double* state_out,
+                        uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts, const MMNewtonOpts* wrapper_opts,
+                        int64_t N, int layout) {
+    const int nc = mm_wrap_ncomp(dim_kind);
+    if (nc < 0) return nc;
+    if (!p || N < 0 || (N > 0 && (!eps_red || !state_in || !sig_red || !state_out))) return set_error(MM_ERR_ARG, "mmh_wrapped_plastic: bad argument");
+    Arr a[8] = {in_arr(eps_red, nc), in_arr(state_in, 14), out_arr(sig_red, nc), out_arr(tan_red, nc * nc), out_arr(state_out, 14),
+                out_arr(flags, 1, 1, false), out_arr(iters, 1, 1, false), out_arr(outer_iters, 1, 1, false)};
+    return pipeline(a, 8, N, layout, n_fail, [&](int s, int64_t n, cudaStream_t st) {
+        return mm_wrapped_plastic(dim_kind, p, (const double*)a[0].d[s], (const double*)a[1].d[s], (double*)a[2].d[s], (double*)a[3].d[s], (double*)a[4].d[s],
+                                  (uint8_t*)a[5].d[s], (uint8_t*)a[6].d[s], (uint8_t*)a[7].d[s], g_ws.d_fail, opts, wrapper_opts, n, layout, st);
+    });
+}
+
+int mmh_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropic* p, const double* eps_red, const double* a3, double* sig_red,
+                                       double* tan_red, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* wrapper_opts, int64_t N, int layout) {
+    const int nc = mm_wrap_ncomp(dim_kind);
+    if (nc < 0) return nc;
+    if (!p || N < 0 || (N > 0 && (!eps_red || !a3 || !sig_red))) return set_error(MM_ERR_ARG, "mmh_wrapped_transversely_isotropic: bad argument");
+    Arr a[5] = {in_arr(eps_red, nc), in_arr(a3, 3), out_arr(sig_red, nc), out_arr(tan_red, nc * nc), out_arr(outer_iters, 1, 1, false)};
+    return pipeline(a, 5, N, layout, n_fail, [&](int s, int64_t n, cudaStream_t st) {
+        return mm_wrapped_transversely_isotropic(dim_kind, p, (const double*)a[0].d[s], (const double*)a[1].d[s], (double*)a[2].d[s], (double*)a[3].d[s],
+                                                 (uint8_t*)a[4].d[s], g_ws.d_fail, wrapper_opts, n, layout, st);
+    });
+}
+
 int mmh_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent, int64_t N, int layout) {
     if (!p || N < 0 || (N > 0 && (!strain || !stress))) return set_error(MM_ERR_ARG, "mmh_hyper_ex: bad argument");
     const bool pf = tangent_kind == MM_TANGENT_DPDF;

@@ -48,6 +48,41 @@ template <int KIND> struct WrappedPlasticOp {
 #endif
 template <int KIND> struct MinBlocks<WrappedPlasticOp<KIND>> { static constexpr int value = MM_WRAP_MINBLOCKS, block = 128; };
 
+// wrappers.jl is generic in the material; TransverselyIsotropic (the laminate-ply model: ShellStress / PlaneStress use) carries
+// its direction a3 as the (unchanged) state, so the inner model reads it through in<1> and nothing is written to out<2>
+template <class Acc> struct NoStateOut {
+    Acc& a;
+    template <int A> __device__ __forceinline__ double in(int c) const { return a.template in<A>(c); }
+    template <int A> __device__ __forceinline__ void out(int c, double v) { if (A < 2) a.template out<(A < 2 ? A : 0)>(c, v); }
+    template <int A> __device__ __forceinline__ bool has_out() const { return A < 2 ? a.template has_out<(A < 2 ? A : 0)>() : false; }
+};
+template <int KIND> struct WrappedTransvIsoOp {
+    static constexpr int NIN = 2, NOUT = 2, SCRATCH = 0;
+    __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? wrap_nc(KIND) : 3; }
+    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? wrap_nc(KIND) : wrap_nc(KIND) * wrap_nc(KIND); }
+    TransvIsoK k;
+    double tol; int max_iter;
+    uint8_t* outer_iters;
+    int32_t* n_fail;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
+        int oit = 0, iit = 0;
+        const TransvIsoK kk = k;
+        NoStateOut<Acc> na{acc};
+        const int flag = wrapped_point<KIND, 3>([&](RegIO<3>& io, int*) { transviso_point(kk, io); return 0; }, na, tol, max_iter, &oit, &iit);
+        if (outer_iters) outer_iters[i] = (uint8_t)oit;
+        if (flag && n_fail) atomicAdd(n_fail, 1);
+    }
+};
+template <int KIND>
+int launch_wrapped_transviso(const MMTransverselyIsotropic* p, const double* eps, const double* a3, double* sig, double* tan, uint8_t* oit, int32_t* n_fail,
+                             const MMNewtonOpts* w, int64_t N, int layout, cudaStream_t st) {
+    WrappedTransvIsoOp<KIND> op;
+    op.k.L_perp = p->L_perp; op.k.L_par = p->L_par; op.k.M_par = p->M_par; op.k.G_perp = p->G_perp; op.k.G_par = p->G_par;
+    op.tol = w ? w->tol : 1e-8; op.max_iter = w ? w->max_iter : 10; op.outer_iters = oit; op.n_fail = n_fail;
+    Ptrs<2, 2> ptrs; ptrs.in[0] = eps; ptrs.in[1] = a3; ptrs.out[0] = sig; ptrs.out[1] = tan;
+    return launch_points<WrappedTransvIsoOp<KIND>, 128, 128>(op, ptrs, N, layout, st, "mm_wrapped_transversely_isotropic");
+}
+
 template <int KIND>
 int launch_wrapped_elastic(const MMLinearElastic* p, const double* eps, double* sig, double* tan, uint8_t* oit, int32_t* n_fail, const MMNewtonOpts* w,
                            int64_t N, int layout, cudaStream_t st) {
@@ -90,6 +125,22 @@ int mm_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const doub
         case MM_DIM_SHELL_STRESS: return launch_wrapped_elastic<WRAP_SHELL_STRESS>(p, eps_red, sig_red, tan_red, outer_iters, n_fail, wrapper_opts, N, layout, st);
     }
     return set_error(MM_ERR_ARG, "mm_wrapped_linear_elastic: unknown dim_kind %d", dim_kind);
+}
+
+int mm_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropic* p, const double* eps_red, const double* a3, double* sig_red, double* tan_red,
+                                      uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!eps_red || !a3 || !sig_red))) return set_error(MM_ERR_ARG, "mm_wrapped_transversely_isotropic: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+#define MM_WT(K) return launch_wrapped_transviso<K>(p, eps_red, a3, sig_red, tan_red, outer_iters, n_fail, wrapper_opts, N, layout, st)
+    switch (dim_kind) {
+        case MM_DIM_UNIAXIAL_STRAIN: MM_WT(WRAP_UNIAXIAL_STRAIN);
+        case MM_DIM_PLANE_STRAIN: MM_WT(WRAP_PLANE_STRAIN);
+        case MM_DIM_UNIAXIAL_STRESS: MM_WT(WRAP_UNIAXIAL_STRESS);
+        case MM_DIM_PLANE_STRESS: MM_WT(WRAP_PLANE_STRESS);
+        case MM_DIM_SHELL_STRESS: MM_WT(WRAP_SHELL_STRESS);
+    }
+#undef MM_WT
+    return set_error(MM_ERR_ARG, "mm_wrapped_transversely_isotropic: unknown dim_kind %d", dim_kind);
 }
 
 int mm_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red, double* state_out,

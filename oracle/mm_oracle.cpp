@@ -290,6 +290,29 @@ int mmo_wrapped_plastic(int kind, const MMPlastic* p, const double* eps_red, con
     return 0;
 }
 
+int mmo_wrapped_transviso(int kind, const MMTransverselyIsotropic* p, const double* eps_red, const double* a3, double* sig_red, double* tan_red,
+                          uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* wopts, int64_t N, int layout) {
+    TransvIsoM m{p->L_perp, p->L_par, p->M_par, p->G_perp, p->G_par};
+    const int nc = wrap_ncomp(kind);
+    double tol = wopts ? wopts->tol : 1e-8; int max_iter = wopts ? wopts->max_iter : 10;
+    View ve = V(eps_red, N, nc, layout), va = V(a3, N, 3, layout), vs = V(sig_red, N, nc, layout), vt = V(tan_red, N, nc * nc, layout);
+    int64_t fails = 0;
+#pragma omp parallel for schedule(static) reduction(+ : fails)
+    for (int64_t i = 0; i < N; ++i) {
+        double e[6], s[6], t[36], a[3]; int oit = 0;
+        for (int c = 0; c < nc; ++c) e[c] = ve.at(i, c);
+        for (int c = 0; c < 3; ++c) a[c] = va.at(i, c);
+        auto inner = [&](const Sym2<double>& eps3, Sym2<double>& sig, Sym4<double>& tan) { material_response(m, eps3, a, sig, tan); return 0; };
+        int st = wrapped_response(kind, inner, e, tol, max_iter, s, t, oit);
+        if (st) ++fails;
+        for (int c = 0; c < nc; ++c) vs.at(i, c) = s[c];
+        if (tan_red) for (int c = 0; c < nc * nc; ++c) vt.at(i, c) = t[c];
+        if (outer_iters) outer_iters[i] = (uint8_t)oit;
+    }
+    if (n_fail) *n_fail += (int32_t)fails;
+    return 0;
+}
+
 // ---- trait layer (reference src/traits.jl:34-107): strain kinds C / F / E, tangent kinds ∂S∂C / ∂S∂E / ∂Pᵀ∂F ----------
 int mmo_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent,
                  int64_t N, int layout) {

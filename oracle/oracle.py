@@ -39,6 +39,7 @@ _SIG = {
     "mmo_synth_uniform": (C.c_int, [_P, _I64, C.c_int, C.c_int, C.c_uint64, _P, _P]),
     "mmo_hyper_ex": (C.c_int, [C.c_int, C.POINTER(abi.MMHyper), _P, C.c_int, C.c_int, _P, _P, _I64, C.c_int]),
     "mmo_neohook_dPdF_ad": (C.c_int, [C.POINTER(abi.MMHyper), _P, _P, _P]),
+    "mmo_wrapped_transviso": (C.c_int, [C.c_int, C.POINTER(abi.MMTransverselyIsotropic), _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
     "mmo_transviso_setup": (C.c_int, [C.c_double] * 5 + [C.POINTER(abi.MMTransverselyIsotropic)]),
     "mmo_transversely_isotropic": (C.c_int, [C.POINTER(abi.MMTransverselyIsotropic), _P, _P, _P, _P, _I64, C.c_int]),
     "mmo_strain_energy_batch": (C.c_int, [C.c_int, _P, _P, C.c_int, _P, _I64, C.c_int]),
@@ -279,3 +280,15 @@ def strain_energy_batch(model, params, strain, strain_kind=0, layout=SOA):
     rc = lib().mmo_strain_energy_batch(model, C.byref(p), _ptr(strain), strain_kind, _ptr(psi), N, layout)
     assert rc == 0
     return psi
+
+
+def wrapped_transviso(kind, p, eps_red, a3, layout=SOA, tol=1e-8, max_iter=10):
+    nc = WRAP_NCOMP[kind]
+    eps_red, N = _n(eps_red, layout)
+    a3 = np.ascontiguousarray(a3, dtype=np.float64)
+    sig, tan = _alloc(nc, N, layout), _alloc(nc * nc, N, layout)
+    oit, nfail = np.zeros(N, np.uint8), np.zeros(1, np.int32)
+    w = abi.MMNewtonOpts(tol, max_iter, 0)
+    rc = lib().mmo_wrapped_transviso(kind, C.byref(p), _ptr(eps_red), _ptr(a3), _ptr(sig), _ptr(tan), _ptr(oit), _ptr(nfail), C.byref(w), N, layout)
+    assert rc == 0
+    return dict(sig=sig, tan=tan, outer_iters=oit, n_fail=int(nfail[0]))

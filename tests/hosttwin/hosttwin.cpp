@@ -161,3 +161,32 @@ extern "C" int twin_hyper_energy(int model, const MMHyper* p, const double* stra
     if (model == 0) twin_hyper_energy_m<0>(k, strain, kind, psi, N); else if (model == 1) twin_hyper_energy_m<1>(k, strain, kind, psi, N); else twin_hyper_energy_m<2>(k, strain, kind, psi, N);
     return 0;
 }
+
+// ---- dimension wrappers around TransverselyIsotropic ----
+namespace { template <class Acc> struct NoStateOutH {
+    Acc& a;
+    template <int A> double in(int c) const { return a.template in<A>(c); }
+    template <int A> void out(int c, double v) { if (A < 2) a.template out<(A < 2 ? A : 0)>(c, v); }
+    template <int A> bool has_out() const { return A < 2 ? a.template has_out<(A < 2 ? A : 0)>() : false; }
+}; }
+template <int KIND> static void twin_wrapped_transviso_k(const mm::TransvIsoK& k, const double* eps, const double* a3, double* sig, double* tan, uint8_t* oiters, int64_t N) {
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<2, 2> a{{eps, a3}, {sig, tan}, N, i};
+        NoStateOutH<HostAcc<2, 2>> na{a};
+        int oit = 0, iit = 0;
+        mm::wrapped_point<KIND, 3>([&](mm::RegIO<3>& io, int*) { mm::transviso_point(k, io); return 0; }, na, 1e-8, 10, &oit, &iit);
+        oiters[i] = (uint8_t)oit;
+    }
+}
+extern "C" int twin_wrapped_transviso(int kind, const MMTransverselyIsotropic* p, const double* eps, const double* a3, double* sig, double* tan, uint8_t* oiters, int64_t N) {
+    mm::TransvIsoK k{p->L_perp, p->L_par, p->M_par, p->G_perp, p->G_par};
+    switch (kind) {
+        case 1: twin_wrapped_transviso_k<1>(k, eps, a3, sig, tan, oiters, N); break;
+        case 2: twin_wrapped_transviso_k<2>(k, eps, a3, sig, tan, oiters, N); break;
+        case 3: twin_wrapped_transviso_k<3>(k, eps, a3, sig, tan, oiters, N); break;
+        case 4: twin_wrapped_transviso_k<4>(k, eps, a3, sig, tan, oiters, N); break;
+        case 5: twin_wrapped_transviso_k<5>(k, eps, a3, sig, tan, oiters, N); break;
+        default: return -1;
+    }
+    return 0;
+}

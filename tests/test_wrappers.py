@@ -163,3 +163,91 @@ def test_gpu_plane_stress_failure_raises_reference_error(mm, cuda_lib):
         mm.material_response(mm.PlaneStress(), m, eps, mm.initial_material_state(m, N), options={"plane_stress_max_iter": 1})
     with pytest.raises(RuntimeError, match="Material model not converged"):             # Plastic.jl:157 (inner)
         mm.material_response(mm.PlaneStress(), m, eps, mm.initial_material_state(m, N), options={"nlsolve_params": {"iterations": 0}})
+
+
+# ---- wrappers around TransverselyIsotropic (wrappers.jl is generic in the material) and host-buffer forms --------------
+TI = dict(E_L=100e3, E_T=10e3, G_LT=5e3, nu_LT=0.4, nu_TT=0.3)          # test_transversely.jl:4-8
+
+
+def _unit_dirs(N, seed):
+    a = sy.host_uniform(N, 3, seed, [-1.0] * 3, [1.0] * 3)
+    a[:, np.linalg.norm(a, axis=0) < 1e-3] = np.array([[1.0], [0.0], [0.0]])
+    return np.ascontiguousarray(a / np.linalg.norm(a, axis=0))
+
+
+def test_oracle_wrapped_transviso_is_the_schur_complement(oracle):
+    """PlaneStress around a linear model: one outer update, tangent = Schur complement of the 3D stiffness (wrappers.jl:63-70),
+    and the converged 3D strain gives vanishing out-of-plane stresses."""
+    p = oracle.transviso_params(TI["E_L"], TI["E_T"], TI["G_LT"], TI["nu_LT"], TI["nu_TT"])
+    N = 50
+    a3 = _unit_dirs(N, 3)
+    e = sy.host_uniform(N, 3, 4, [-1e-3] * 3, [1e-3] * 3)
+    r = oracle.wrapped_transviso(oracle.PLANE_STRESS, p, e, a3)
+    assert r["n_fail"] == 0 and np.all(r["outer_iters"] == 1)
+    _, E3 = oracle.transversely_isotropic(p, np.zeros((6, N)), a3)
+    slot = {(0, 0): 0, (1, 0): 1, (2, 0): 2, (1, 1): 3, (2, 1): 4, (2, 2): 5}
+    inp, oop = [0, 1, 3], [2, 4, 5]                       # storage slots (11,21,22) in plane; (31,32,33) out of plane
+    w = np.array([1.0, 2.0, 2.0, 1.0, 2.0, 1.0])         # ⊡ weights of the symmetric storage
+    for j in range(N):
+        T = E3[:, j].reshape(6, 6, order="F") * w[None, :]                          # σ_I = Σ_J T[I,J] ε_J on storage components
+        S = T[np.ix_(inp, inp)] - T[np.ix_(inp, oop)] @ np.linalg.solve(T[np.ix_(oop, oop)], T[np.ix_(oop, inp)])
+        assert np.allclose(r["sig"][:, j], S @ e[:, j], rtol=1e-11, atol=1e-12)
+        Tred = r["tan"][:, j].reshape(3, 3, order="F") * np.array([1.0, 2.0, 1.0])[None, :]
+        assert np.allclose(Tred, S, rtol=1e-11, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_twin_wrapped_transviso_matches_oracle(oracle, kind):
+    tw = H.hosttwin()
+    p = oracle.transviso_params(TI["E_L"], TI["E_T"], TI["G_LT"], TI["nu_LT"], TI["nu_TT"])
+    N, nc = 3000, NC[kind]
+    a3 = _unit_dirs(N, 30 + kind)
+    e = sy.host_uniform(N, nc, 40 + kind, [-1e-3] * nc, [1e-3] * nc)
+    r = oracle.wrapped_transviso(kind, p, e, a3)
+    sig, tan, oit = np.zeros((nc, N)), np.zeros((nc * nc, N)), np.zeros(N, np.uint8)
+    assert tw.twin_wrapped_transviso(kind, C.byref(p), H.P(e), H.P(a3), H.P(sig), H.P(tan), H.P(oit), C.c_int64(N)) == 0
+    assert np.array_equal(oit, r["outer_iters"])
+    scale = np.maximum(np.linalg.norm(r["sig"], axis=0), 1e-3 * TI["E_T"])
+    assert (np.linalg.norm(sig - r["sig"], axis=0) / scale).max() < 1e-11
+    assert H.rel_err(tan, r["tan"]).max() < 1e-10        # Schur complements through up to a 5x5 block of a stiffness with E_L/E_T = 10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lname,lay", [("soa", 0), ("aos", 1)])
+@pytest.mark.parametrize("kind", KINDS)
+def test_gpu_wrapped_transviso_and_host_buffer_forms(mm, cuda_lib, oracle, kind, lname, lay):
+    import torch
+
+    N, nc = 30011, NC[kind]
+    dim = getattr(mm, DIMS[kind])()
+    m = mm.TransverselyIsotropic(E_L=TI["E_L"], E_T=TI["E_T"], G_LT=TI["G_LT"], ν_LT=TI["nu_LT"], ν_TT=TI["nu_TT"])
+    p = oracle.transviso_params(TI["E_L"], TI["E_T"], TI["G_LT"], TI["nu_LT"], TI["nu_TT"])
+    soa = (lambda a: a) if lay == 0 else (lambda a: np.ascontiguousarray(a.T))
+    lay_of = soa
+    a3 = _unit_dirs(N, 30 + kind)
+    e = sy.host_uniform(N, nc, 40 + kind, [-1e-3] * nc, [1e-3] * nc)
+    r = oracle.wrapped_transviso(kind, p, e, a3)
+    st = mm.initial_material_state(m, torch.from_numpy(lay_of(a3)).cuda(), layout=lname)
+    s, t, new = mm.material_response(dim, m, torch.from_numpy(lay_of(e)).cuda(), st)
+    assert np.array_equal(new.outer_iters.cpu().numpy(), r["outer_iters"])
+    scale = np.maximum(np.linalg.norm(r["sig"], axis=0), 1e-3 * TI["E_T"])
+    assert (np.linalg.norm(soa(s.cpu().numpy()) - r["sig"], axis=0) / scale).max() < 1e-11
+    assert H.rel_err(soa(t.cpu().numpy()), r["tan"]).max() < 1e-10
+    # host-buffer forms (pipelined chunks, ragged last chunk) == device forms, bit for bit
+    old = cuda_lib.mmh_set_chunk_points(7000)
+    try:
+        sth = mm.initial_material_state(m, lay_of(a3), device="cpu", layout=lname)
+        sh, th, _ = mm.material_response(dim, m, lay_of(e), sth)
+        assert np.array_equal(sh, s.cpu().numpy()) and np.array_equal(th, t.cpu().numpy())
+        pm = mm.Plastic(**sy.PLASTIC_PARAMS)
+        ep = sy.host_uniform(N, nc, 777 + kind, -AMPL[kind], AMPL[kind], layout=lay)
+        sd, td, nd = mm.material_response(dim, pm, torch.from_numpy(ep).cuda(), mm.initial_material_state(pm, N, layout=lname))
+        sh, th, nh = mm.material_response(dim, pm, ep, mm.initial_material_state(pm, N, device="cpu", layout=lname))
+        assert np.array_equal(sh, sd.cpu().numpy()) and np.array_equal(th, td.cpu().numpy()) and np.array_equal(nh.data, nd.data.cpu().numpy())
+        assert np.array_equal(nh.flags, nd.flags.cpu().numpy()) and np.array_equal(nh.outer_iters, nd.outer_iters.cpu().numpy())
+        le = mm.LinearElastic(E=E, ν=NU)
+        sd, td, _ = mm.material_response(dim, le, torch.from_numpy(ep).cuda(), None, layout=lname)
+        sh, th, _ = mm.material_response(dim, le, ep, None, layout=lname)
+        assert np.array_equal(sh, sd.cpu().numpy()) and np.array_equal(th, td.cpu().numpy())
+    finally:
+        cuda_lib.mmh_set_chunk_points(old)
