@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--points", type=int, default=10**8, help="points per GPU (BASELINE.json configs[1]: 1e8)")
     ap.add_argument("--e2e-points", type=int, default=2 * 10**7)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-points", type=int, default=4 * 10**6)
+    ap.add_argument("--cpu-points", type=int, default=16 * 10**6)
     ap.add_argument("--ref-points", type=int, default=0, help="points per step of --impl reference (0 = sized for a ~75 s run)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
