@@ -176,6 +176,20 @@ int mm_transversely_isotropic(const MMTransverselyIsotropic* p, const double* ep
 int mm_linear_elastic_energy(const MMLinearElastic* p, const double* eps, double* psi, int64_t N, int layout, void* stream);
 int mm_hyper_energy(int model, const MMHyper* p, const double* strain, int strain_kind, double* psi, int64_t N, int layout, void* stream);
 
+/* ---- the caller side fused around the update — the quadrature loop of a small-strain solid element,
+ * i.e. what a Ferrite.jl-style assemble_cell! does around the reference's per-point material_response (src/MaterialModels.jl:41-52):
+ *     ε = sym(Σ_a u_a ⊗ ∇N_a);  σ, D, state_new = material_response(m, ε, state);  fe[a] += (σ ⋅ ∇N_a) dΩ
+ * nn nodes and nq quadrature points per cell, supported (nn, nq): (4,1) (4,4) (8,1) (8,8) (10,4).  P = ncell*nq points, point
+ * index = cell*nq + q.  All arrays component-major: per point dNdx[(3a+k)*P + i] (∇N_a in physical coordinates, as CellValues
+ * holds it after reinit!), dOmega[i], state / sig / tan [c*P + i]; per cell ue, fe [(3a+k)*ncell + cell].
+ * sig (6 per point) and tan (36 per point) may be NULL: explicit / matrix-free codes need neither, and leaving the tangent out
+ * removes 288 of the 608 algorithmic bytes per point of the unfused J2 update. */
+int mm_cells_linear_elastic(const MMLinearElastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue,
+                            double* fe, double* sig, double* tan, int64_t ncell, void* stream);
+int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue,
+                     const double* state_in, double* fe, double* sig, double* tan, double* state_out, uint8_t* flags, uint8_t* iters,
+                     int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell, void* stream);
+
 /* Deterministic synthetic inputs (bench + parity harness): out(i,c) = lo[c] + (hi[c]-lo[c]) * u(i,c),
  * u(i,c) = (splitmix64(seed + i*nc + c) >> 11) * 2^-53.  lo/hi are HOST arrays of nc doubles. */
 int mm_synth_uniform(double* out, int64_t N, int nc, int layout, uint64_t seed, const double* lo, const double* hi,

@@ -12,7 +12,7 @@ from .materials import (  # noqa: F401
 )
 from .api import (  # noqa: F401
     NOT_CONVERGED, PLANE_STRESS_NOT_CONVERGED, CrystalViscoPlasticState, PinnedArray, LinearElasticState, NeoHookState, PlasticCache, PlasticState, StVenantState,
-    TransverselyIsotropicState, XuNeedlemanState, YeohState, elastic_strain_energy_density, elastic_tangent_3D, get_cache, initial_material_state, material_response, synth_uniform,
+    TransverselyIsotropicState, XuNeedlemanState, YeohState, cell_internal_forces, elastic_strain_energy_density, elastic_tangent_3D, get_cache, initial_material_state, material_response, synth_uniform,
 )
 
 __version__ = "0.1.0"

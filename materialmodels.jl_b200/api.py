@@ -601,6 +601,55 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
     raise TypeError("material_response: unsupported material %r" % (m,))
 
 
+def cell_internal_forces(m, dNdx, dΩ, ue, state=None, tangent=False, stress=False, options=None):
+    """The caller's quadrature loop fused around material_response (what a Ferrite.jl-style
+    assemble_cell! does around the reference's per-point call, src/MaterialModels.jl:41-52), all cells at once:
+
+        ε = sym(Σ_a u_a ⊗ ∇N_a);   σ, D, state_new = material_response(m, ε, state);   fe[a] += (σ ⋅ ∇N_a) dΩ
+
+    dNdx (3·nn, P): ∇N_a at every quadrature point (physical coordinates), dΩ (P,), ue (3·nn, ncell), P = ncell·nq, point
+    index = cell·nq + q; state: PlasticState over the P points (layout "soa") for Plastic, None for LinearElastic.
+    Returns (fe (3·nn, ncell), new_state, extras) with extras["stress"] (6, P) / extras["tangent"] (36, P) when requested.
+    Device (torch CUDA) arrays only.  Supported (nn, nq): (4,1) (4,4) (8,1) (8,8) (10,4)."""
+    dNdx, dΩ, ue = _prep(dNdx), _prep(dΩ), _prep(ue)
+    if _is_host(dNdx) or _is_host(dΩ) or _is_host(ue):
+        raise NotImplementedError("cell_internal_forces: device (torch CUDA) arrays only")
+    if ue.dim() != 2 or ue.shape[0] % 3 != 0:
+        raise ValueError("ue must have shape (3*nn, ncell)")
+    nn, ncell = ue.shape[0] // 3, ue.shape[1]
+    P = dΩ.shape[0]
+    if ncell == 0 or P % ncell != 0 or tuple(dNdx.shape) != (3 * nn, P):
+        raise ValueError("inconsistent shapes: dNdx %s, dΩ %s, ue %s" % (tuple(dNdx.shape), tuple(dΩ.shape), tuple(ue.shape)))
+    nq = P // ncell
+    torch = _torch()
+    fe = _empty((3 * nn, ncell), ue)
+    σ = _empty((6, P), ue) if stress else None
+    tan = _empty((36, P), ue) if tangent else None
+    lib = load()
+    extras = {"stress": σ, "tangent": tan}
+    with _DeviceGuard(ue):
+        if isinstance(m, LinearElastic):
+            check(lib.mm_cells_linear_elastic(ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(fe), _ptr(σ), _ptr(tan), ncell, _stream(ue)),
+                  "mm_cells_linear_elastic")
+            return fe, (state if state is not None else LinearElasticState()), extras
+        if not isinstance(m, Plastic):
+            raise NotImplementedError("cell_internal_forces is implemented for LinearElastic and Plastic")
+        if state is None or state.N != P or _LAYOUTS[state.layout] != _abi.MM_LAYOUT_SOA:
+            raise ValueError("cell_internal_forces(::Plastic): a 'soa' PlasticState over the %d quadrature points is required" % P)
+        sin = _prep(state.data)
+        sout = _empty((14, P), ue)
+        flags = _empty((P,), ue, torch.uint8)
+        iters = _empty((P,), ue, torch.uint8)
+        nfail = _zeros((1,), ue, torch.int32)
+        o = _newton_opts(m, options)
+        check(lib.mm_cells_plastic(ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(sin), _ptr(fe), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(flags),
+                                   _ptr(iters), _ptr(nfail), ctypes.byref(o), ncell, _stream(ue)), "mm_cells_plastic")
+    new = PlasticState(sout, "soa")
+    new.flags, new.iters, new.n_fail = flags, iters, nfail
+    _finish_fail(nfail, ue, options)
+    return fe, new, extras
+
+
 def synth_uniform(N, nc, seed, lo, hi, layout="soa", device="cuda"):
     """Device-side deterministic inputs (bit-identical to synth.host_uniform)."""
     torch = _torch()

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libmmb200.so")
-SOURCES = ["mm_api.cu", "mm_ops.cu", "mm_crystal.cu", "mm_wrap.cu", "mm_host.cu"]
+SOURCES = ["mm_api.cu", "mm_ops.cu", "mm_crystal.cu", "mm_wrap.cu", "mm_cells.cu", "mm_host.cu"]
 HEADERS = ["mm_math.cuh", "mm_crystal_math.cuh", "mm_wrap_math.cuh", "mm_kernels.cuh", os.path.join("..", "..", "include", "mmb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

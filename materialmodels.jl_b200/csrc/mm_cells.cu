@@ -1,0 +1,181 @@
+// mm_cells_* — SURVEY §8(f) rank 4b, the CALLER side of material_response fused around it: the quadrature loop of a
+// small-strain solid element (what a Ferrite.jl-style `assemble_cell!` does around the reference's per-point call):
+//
+//     for q in 1:nq                                              # caller-owned loop in the reference's world
+//         ε  = function_symmetric_gradient(cv, q, ue)           # ε = sym(Σ_a u_a ⊗ ∇N_a)
+//         σ, D, state_new[q] = material_response(m, ε, state[q]) # <- the reference's hot path (src/MaterialModels.jl:41-52)
+//         fe[a] += (σ ⋅ ∇N_a) dΩ                                # Bᵀσ
+//
+// One thread per quadrature point; the NQ points of a cell sit in NQ adjacent lanes and sum their Bᵀσ contributions through
+// shared memory, so σ never goes to memory and the 36-entry tangent is written only if the caller asks for it
+// (implicit codes), which removes 288 of the 608 algorithmic bytes per point of the unfused J2 update.
+// Arrays (all FP64, component-major like MM_LAYOUT_SOA):
+//   per point  (P = ncell*NQ points, point index = cell*NQ + q):  dNdx[(3a+k)*P + i], dOmega[i], state[c*P + i], sig/tan
+//   per cell   (ncell cells):                                     ue[(3a+k)*ncell + cell], fe[(3a+k)*ncell + cell]
+#include <cuda_runtime.h>
+#include "../../include/mmb200.h"
+#include "mm_kernels.cuh"
+
+namespace mm {
+
+// accessor for the inner 3D model: strain from registers, state straight from / to global memory (coalesced), σ kept in registers
+template <int NS> struct CellAcc {
+    double eps[6], sig[6];
+    const double* st_in; double* st_out; double* tan; double* sig_out;
+    int64_t P, i;
+    template <int A> __device__ __forceinline__ double in(int c) const { return A == 0 ? eps[c] : __ldcs(st_in + (int64_t)c * P + i); }
+    template <int A> __device__ __forceinline__ void out(int c, double v) {
+        if (A == 0) { sig[c] = v; if (sig_out) __stcs(sig_out + (int64_t)c * P + i, v); }
+        else if (A == 1) __stcs(tan + (int64_t)c * P + i, v);
+        else __stcs(st_out + (int64_t)c * P + i, v);
+    }
+    template <int A> __device__ __forceinline__ bool has_out() const { return A == 1 ? tan != nullptr : true; }
+};
+
+struct CellArgs {
+    const double* dNdx; const double* dOmega; const double* ue; const double* state_in;
+    double* fe; double* sig; double* tan; double* state_out;
+    uint8_t* flags; uint8_t* iters; int32_t* n_fail;
+    int64_t ncell;
+};
+
+// MODEL 0: LinearElastic (stateless), 1: Plastic (14 state doubles)
+// NQ == 1: everything in registers.  NQ > 1: ∇N is parked in shared memory across the material update (3·NN doubles per
+// thread would otherwise cost 2·3·NN registers on top of the J2 solve) and the Bᵀσ contributions of the NQ lanes of a cell
+// are summed through a padded shared-memory image: lane q adds up and stores components q, q+NQ, … (3·NN/NQ each) — one
+// STS + 3·NN/NQ·NQ LDS per thread instead of 3·NN·log2(NQ) 64-bit shuffles.
+#ifndef MM_CELLS_MINBLOCKS
+#define MM_CELLS_MINBLOCKS 3
+#endif
+template <int MODEL, int NN, int NQ, int BS>
+__global__ void __launch_bounds__(BS, MM_CELLS_MINBLOCKS) cells_kernel(const ElasticK ke, const PlasticK kp, const CellArgs a) {
+    static_assert(NQ == 1 || NQ == 2 || NQ == 4 || NQ == 8, "quadrature points per cell must be a power of two <= 8");
+    static_assert(BS % 32 == 0 && 32 % NQ == 0, "a cell's points must share a warp");
+    constexpr int NC = 3 * NN;
+    extern __shared__ double sm[];
+    double* sm_dN = sm;                                  // [NC][BS]      (NQ > 1)
+    double* sm_f = sm + (NQ > 1 ? NC * BS : 0);          // [NC][BS + 1]  (NQ > 1), padded: the NQ lanes of a cell read NQ different rows
+    const int64_t P = a.ncell * NQ;
+    const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
+    const unsigned mask = __ballot_sync(0xffffffffu, i < P);   // cells are whole and warp-local: the survivors sync among themselves below
+    if (i >= P) return;
+    const int64_t cell = i / NQ;
+    const int q = (int)(i - cell * NQ);
+    const int t = threadIdx.x;
+    double dN[NQ == 1 ? NC : 1];
+    CellAcc<MODEL == 1 ? 14 : 0> acc;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc.eps[c] = 0.0;
+#pragma unroll
+    for (int n = 0; n < NN; ++n) {
+        double u[3], d[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            d[k] = __ldcs(a.dNdx + (int64_t)(3 * n + k) * P + i);
+            u[k] = __ldg(a.ue + (int64_t)(3 * n + k) * a.ncell + cell);       // shared by the NQ lanes of the cell
+            if (NQ == 1) dN[NQ == 1 ? 3 * n + k : 0] = d[k]; else sm_dN[(3 * n + k) * BS + t] = d[k];
+        }
+        // ε = sym(Σ_a u_a ⊗ ∇N_a), storage (11,21,31,22,32,33)
+        acc.eps[0] += u[0] * d[0];
+        acc.eps[3] += u[1] * d[1];
+        acc.eps[5] += u[2] * d[2];
+        acc.eps[1] += 0.5 * (u[1] * d[0] + u[0] * d[1]);
+        acc.eps[2] += 0.5 * (u[2] * d[0] + u[0] * d[2]);
+        acc.eps[4] += 0.5 * (u[2] * d[1] + u[1] * d[2]);
+    }
+    const double dO = __ldcs(a.dOmega + i);
+    acc.st_in = a.state_in; acc.st_out = a.state_out; acc.tan = a.tan; acc.sig_out = a.sig; acc.P = P; acc.i = i;
+    if (MODEL == 0) {
+        linear_elastic_point(ke, acc);
+    } else {
+        int it = 0;
+        const int flag = plastic_point(kp, acc, &it);
+        if (a.flags) a.flags[i] = (uint8_t)flag;
+        if (a.iters) a.iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if ((flag & MM_FLAG_FAILED) && a.n_fail) atomicAdd(a.n_fail, 1);
+    }
+    // fe[a][k] = Σ_q (σ ⋅ ∇N_a)_k dΩ
+    const double s00 = acc.sig[0] * dO, s10 = acc.sig[1] * dO, s20 = acc.sig[2] * dO, s11 = acc.sig[3] * dO, s21 = acc.sig[4] * dO, s22 = acc.sig[5] * dO;
+#pragma unroll
+    for (int n = 0; n < NN; ++n) {
+        double d[3], f[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[k] = (NQ == 1) ? dN[NQ == 1 ? 3 * n + k : 0] : sm_dN[(3 * n + k) * BS + t];
+        f[0] = s00 * d[0] + s10 * d[1] + s20 * d[2];
+        f[1] = s10 * d[0] + s11 * d[1] + s21 * d[2];
+        f[2] = s20 * d[0] + s21 * d[1] + s22 * d[2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (NQ == 1) __stcs(a.fe + (int64_t)(3 * n + k) * a.ncell + cell, f[k]);
+            else sm_f[(3 * n + k) * (BS + 1) + t] = f[k];
+        }
+    }
+    if (NQ > 1) {
+        __syncwarp(mask);
+        const int t0 = t - q;                              // first lane of this cell
+#pragma unroll
+        for (int c0 = 0; c0 < NC; c0 += NQ) {
+            const int c = c0 + q;
+            if (c < NC) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) v += sm_f[c * (BS + 1) + t0 + j];
+                __stcs(a.fe + (int64_t)c * a.ncell + cell, v);
+            }
+        }
+    }
+}
+
+template <int MODEL, int NN, int NQ>
+int launch_cells(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
+    constexpr int BS = 128;
+    constexpr size_t smem = (NQ > 1) ? (size_t)3 * NN * (2 * BS + 1) * sizeof(double) : 0;
+    const int64_t P = a.ncell * NQ;
+    if (P == 0) return MM_OK;
+    const int64_t blocks = (P + BS - 1) / BS;
+    if (blocks > 2147483647LL) return set_error(MM_ERR_ARG, "mm_cells: too many points for one launch");
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(cells_kernel<MODEL, NN, NQ, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_cells: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    cells_kernel<MODEL, NN, NQ, BS><<<(unsigned)blocks, BS, smem, st>>>(ke, kp, a);
+    return check_launch("mm_cells");
+}
+
+template <int MODEL>
+int dispatch_cells(int nn, int nq, const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
+    if (nn == 4 && nq == 1) return launch_cells<MODEL, 4, 1>(ke, kp, a, st);       // linear tetrahedron, 1-point rule
+    if (nn == 4 && nq == 4) return launch_cells<MODEL, 4, 4>(ke, kp, a, st);       // linear tetrahedron, 4-point rule
+    if (nn == 8 && nq == 8) return launch_cells<MODEL, 8, 8>(ke, kp, a, st);       // trilinear hexahedron, 2x2x2 Gauss
+    if (nn == 8 && nq == 1) return launch_cells<MODEL, 8, 1>(ke, kp, a, st);       // trilinear hexahedron, reduced integration
+    if (nn == 10 && nq == 4) return launch_cells<MODEL, 10, 4>(ke, kp, a, st);     // quadratic tetrahedron, 4-point rule
+    return set_error(MM_ERR_ARG, "mm_cells: unsupported element (nodes %d, quadrature points %d); supported: (4,1) (4,4) (8,1) (8,8) (10,4)", nn, nq);
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" {
+
+int mm_cells_linear_elastic(const MMLinearElastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, double* fe, double* sig,
+                            double* tan, int64_t ncell, void* stream) {
+    if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !fe))) return set_error(MM_ERR_ARG, "mm_cells_linear_elastic: bad argument");
+    CellArgs a{dNdx, dOmega, ue, nullptr, fe, sig, tan, nullptr, nullptr, nullptr, nullptr, ncell};
+    PlasticK kp{};
+    return dispatch_cells<0>(nn, nq, make_elastic_k(p->E, p->nu), kp, a, (cudaStream_t)stream);
+}
+
+int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, const double* state_in, double* fe,
+                     double* sig, double* tan, double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell,
+                     void* stream) {
+    if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !state_in || !fe || !state_out))) return set_error(MM_ERR_ARG, "mm_cells_plastic: bad argument");
+    CellArgs a{dNdx, dOmega, ue, state_in, fe, sig, tan, state_out, flags, iters, n_fail, ncell};
+    ElasticK ke = make_elastic_k(p->E, p->nu);
+    PlasticK kp = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
+    return dispatch_cells<1>(nn, nq, ke, kp, a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

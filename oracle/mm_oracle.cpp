@@ -5,6 +5,7 @@
 // OpenMP over points.  This is the checker for the CUDA path and the CPU baseline that bench.py
 // reports; the product never links or loads it.
 #include <cstdint>
+#include <vector>
 #include <cstring>
 #include <cmath>
 #ifdef _OPENMP
@@ -308,6 +309,61 @@ int mmo_wrapped_transviso(int kind, const MMTransverselyIsotropic* p, const doub
         for (int c = 0; c < nc; ++c) vs.at(i, c) = s[c];
         if (tan_red) for (int c = 0; c < nc * nc; ++c) vt.at(i, c) = t[c];
         if (outer_iters) outer_iters[i] = (uint8_t)oit;
+    }
+    if (n_fail) *n_fail += (int32_t)fails;
+    return 0;
+}
+
+// ---- the caller's quadrature loop around material_response (Ferrite.jl-style assemble_cell!) --------
+//   ε = symmetric(Σ_a u_a ⊗ ∇N_a);  σ, D, state_new = material_response(m, ε, state);  fe[a] += (σ ⋅ ∇N_a) dΩ
+// model: 0 LinearElastic (params = MMLinearElastic), 1 Plastic (params = MMPlastic).  Arrays as include/mmb200.h mm_cells_*.
+int mmo_cells(int model, const void* params, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, const double* state_in,
+              double* fe, double* sig_out, double* tan_out, double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
+              int64_t ncell) {
+    const int64_t P = ncell * nq;
+    LinearElasticM le{}; PlasticM pm{};
+    if (model == 0) { const MMLinearElastic* p = (const MMLinearElastic*)params; le = make_linear_elastic(p->E, p->nu); }
+    else { const MMPlastic* p = (const MMPlastic*)params; pm = make_plastic(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf); }
+    NewtonOpts o{opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000};
+    int64_t fails = 0;
+#pragma omp parallel for schedule(static) reduction(+ : fails)
+    for (int64_t cell = 0; cell < ncell; ++cell) {
+        std::vector<double> f(3 * nn, 0.0);
+        for (int q = 0; q < nq; ++q) {
+            const int64_t i = cell * nq + q;
+            Ten2<double> G;                                                  // ∇u = Σ_a u_a ⊗ ∇N_a
+            for (int a = 0; a < nn; ++a)
+                for (int k = 0; k < 3; ++k)
+                    for (int l = 0; l < 3; ++l) G(k, l) = G(k, l) + ue[(int64_t)(3 * a + k) * ncell + cell] * dNdx[(int64_t)(3 * a + l) * P + i];
+            Sym2<double> eps, sig; Sym4<double> tan;
+            for (int l = 0; l < 3; ++l) for (int k = l; k < 3; ++k) eps(k, l) = 0.5 * (G(k, l) + G(l, k));
+            if (model == 0) material_response(le, eps, sig, tan);
+            else {
+                PlasticState st, sn;
+                for (int c = 0; c < 6; ++c) st.ep.a[c] = state_in[(int64_t)c * P + i];
+                st.kappa = state_in[(int64_t)6 * P + i];
+                for (int c = 0; c < 6; ++c) st.alpha.a[c] = state_in[(int64_t)(7 + c) * P + i];
+                st.mu = state_in[(int64_t)13 * P + i];
+                int flag = 0, it = 0;
+                int status = material_response(pm, eps, st, o, sig, tan, sn, flag, it);
+                if (status) { flag |= MM_FLAG_FAILED; ++fails; }
+                for (int c = 0; c < 6; ++c) state_out[(int64_t)c * P + i] = sn.ep.a[c];
+                state_out[(int64_t)6 * P + i] = sn.kappa;
+                for (int c = 0; c < 6; ++c) state_out[(int64_t)(7 + c) * P + i] = sn.alpha.a[c];
+                state_out[(int64_t)13 * P + i] = sn.mu;
+                if (flags) flags[i] = (uint8_t)flag;
+                if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+            }
+            if (sig_out) for (int c = 0; c < 6; ++c) sig_out[(int64_t)c * P + i] = sig.a[c];
+            if (tan_out) for (int c = 0; c < 36; ++c) tan_out[(int64_t)c * P + i] = tan.a[c];
+            for (int a = 0; a < nn; ++a)
+                for (int k = 0; k < 3; ++k) {
+                    double v = 0;
+                    for (int l = 0; l < 3; ++l) v += sig(k, l) * dNdx[(int64_t)(3 * a + l) * P + i];
+                    f[3 * a + k] += v * dOmega[i];
+                }
+        }
+        for (int c = 0; c < 3 * nn; ++c) fe[(int64_t)c * ncell + cell] = f[c];
     }
     if (n_fail) *n_fail += (int32_t)fails;
     return 0;

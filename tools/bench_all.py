@@ -176,6 +176,38 @@ def main():
             report("LinearElastic energy " + lname, N, 56, med, mn)
             del eps
             torch.cuda.empty_cache()
+    if want("cells"):
+        # the caller's quadrature loop fused around the J2 update.  Geometry is synthetic (timing only): ∇N and u are
+        # uniform random, scaled so that about half the points yield.  Algorithmic bytes per POINT: dNdx 24 nn + dΩ 8 + state 112 in,
+        # state 112 + 2 flag bytes out, per cell ue and fe 24 nn each (divided by nq); + 288 when the tangent is written.
+        m = mm.Plastic(**sy.PLASTIC_PARAMS)
+        for nn, nq in ((4, 1), (8, 8)):
+            P = int(1e8 * S) // nq * nq
+            ncell = P // nq
+            amp, best = 1e-4, (2.0, 1e-4)                      # displacement amplitude giving ~50 % plastic points (calibrated on 2^20 points)
+            Pc = (1 << 20) // nq * nq
+            dNc, dOc = mm.synth_uniform(Pc, 3 * nn, 71, -1.0, 1.0), mm.synth_uniform(Pc, 1, 72, 0.5, 1.5).reshape(Pc)
+            for _ in range(24):
+                _, stc, _ = mm.cell_internal_forces(m, dNc, dOc, mm.synth_uniform(Pc // nq, 3 * nn, 73, -amp, amp), mm.initial_material_state(m, Pc), options={"defer_check": True})
+                fr = (stc.flags & 1).float().mean().item()
+                if abs(fr - 0.5) < best[0]:
+                    best = (abs(fr - 0.5), amp)
+                amp *= 1.12
+            amp = best[1]
+            del dNc, dOc, stc
+            dN = mm.synth_uniform(P, 3 * nn, 71, -1.0, 1.0)
+            dO = mm.synth_uniform(P, 1, 72, 0.5, 1.5).reshape(P)
+            ue = mm.synth_uniform(ncell, 3 * nn, 73, -amp, amp)
+            _, stA, _ = mm.cell_internal_forces(m, dN, dO, ue, mm.initial_material_state(m, P), options={"defer_check": True})
+            ue = mm.synth_uniform(ncell, 3 * nn, 74, -amp, amp)
+            for tan in (False, True):
+                med, mn = timeit(lambda: mm.cell_internal_forces(m, dN, dO, ue, stA, tangent=tan, options={"defer_check": True}), a.reps)
+                _, stB, _ = mm.cell_internal_forces(m, dN, dO, ue, stA, tangent=tan, options={"defer_check": True})
+                bpp = 24 * nn + 8 + 112 + 112 + 2 + 48 * nn / nq + (288 if tan else 0)
+                report("cells J2 nn=%d nq=%d %s" % (nn, nq, "fe+state+tangent" if tan else "fe+state"), P, bpp, med, mn,
+                       {"plastic_fraction": round((stB.flags & 1).float().mean().item(), 3), "n_fail": int(stB.n_fail.item()), "unfused_B_per_pt": 608 + 48 + 24 * nn + 8 + 48 * nn / nq})
+            del dN, dO, ue, stA, stB
+            torch.cuda.empty_cache()
     if want("xu"):
         N = int(1e8 * S)
         x = sy.XU_PARAMS
