@@ -40,9 +40,9 @@ struct CellArgs {
 };
 
 // MODEL 0: LinearElastic (stateless), 1: Plastic (14 state doubles)
-// NQ == 1: everything in registers.  NQ > 1: ∇N is parked in shared memory across the material update (3·NN doubles per
-// thread would otherwise cost 2·3·NN registers on top of the J2 solve) and the Bᵀσ contributions of the NQ lanes of a cell
-// are summed through a padded shared-memory image: lane q adds up and stores components q, q+NQ, … (3·NN/NQ each) — one
+// ∇N is parked in shared memory across the material update (3·NN doubles per thread would otherwise cost 2·3·NN registers on
+// top of the J2 solve: 255 registers and 15.2 ms for the hexahedron, against 168 and 10.7 ms this way); for NQ > 1 the Bᵀσ
+// contributions of the NQ lanes of a cell are summed through a padded shared-memory image: lane q adds up and stores components q, q+NQ, … (3·NN/NQ each) — one
 // STS + 3·NN/NQ·NQ LDS per thread instead of 3·NN·log2(NQ) 64-bit shuffles.
 #ifndef MM_CELLS_MINBLOCKS
 #define MM_CELLS_MINBLOCKS 3
@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(BS, MM_CELLS_MINBLOCKS) cells_kernel(const Ela
     static_assert(BS % 32 == 0 && 32 % NQ == 0, "a cell's points must share a warp");
     constexpr int NC = 3 * NN;
     extern __shared__ double sm[];
-    double* sm_dN = sm;                                  // [NC][BS]      (NQ > 1)
-    double* sm_f = sm + (NQ > 1 ? NC * BS : 0);          // [NC][BS + 1]  (NQ > 1), padded: the NQ lanes of a cell read NQ different rows
+    double* sm_dN = sm;                                  // [NC][BS]
+    double* sm_f = sm + NC * BS;                         // [NC][BS + 1]  (NQ > 1), padded: the NQ lanes of a cell read NQ different rows
     const int64_t P = a.ncell * NQ;
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     const unsigned mask = __ballot_sync(0xffffffffu, i < P);   // cells are whole and warp-local: the survivors sync among themselves below
@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(BS, MM_CELLS_MINBLOCKS) cells_kernel(const Ela
     const int64_t cell = i / NQ;
     const int q = (int)(i - cell * NQ);
     const int t = threadIdx.x;
-    double dN[NQ == 1 ? NC : 1];
     CellAcc<MODEL == 1 ? 14 : 0> acc;
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc.eps[c] = 0.0;
@@ -73,7 +72,7 @@ __global__ void __launch_bounds__(BS, MM_CELLS_MINBLOCKS) cells_kernel(const Ela
         for (int k = 0; k < 3; ++k) {
             d[k] = __ldcs(a.dNdx + (int64_t)(3 * n + k) * P + i);
             u[k] = __ldg(a.ue + (int64_t)(3 * n + k) * a.ncell + cell);       // shared by the NQ lanes of the cell
-            if (NQ == 1) dN[NQ == 1 ? 3 * n + k : 0] = d[k]; else sm_dN[(3 * n + k) * BS + t] = d[k];
+            sm_dN[(3 * n + k) * BS + t] = d[k];
         }
         // ε = sym(Σ_a u_a ⊗ ∇N_a), storage (11,21,31,22,32,33)
         acc.eps[0] += u[0] * d[0];
@@ -100,7 +99,7 @@ __global__ void __launch_bounds__(BS, MM_CELLS_MINBLOCKS) cells_kernel(const Ela
     for (int n = 0; n < NN; ++n) {
         double d[3], f[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) d[k] = (NQ == 1) ? dN[NQ == 1 ? 3 * n + k : 0] : sm_dN[(3 * n + k) * BS + t];
+        for (int k = 0; k < 3; ++k) d[k] = sm_dN[(3 * n + k) * BS + t];
         f[0] = s00 * d[0] + s10 * d[1] + s20 * d[2];
         f[1] = s10 * d[0] + s11 * d[1] + s21 * d[2];
         f[2] = s20 * d[0] + s21 * d[1] + s22 * d[2];
@@ -129,7 +128,7 @@ __global__ void __launch_bounds__(BS, MM_CELLS_MINBLOCKS) cells_kernel(const Ela
 template <int MODEL, int NN, int NQ>
 int launch_cells(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
     constexpr int BS = 128;
-    constexpr size_t smem = (NQ > 1) ? (size_t)3 * NN * (2 * BS + 1) * sizeof(double) : 0;
+    constexpr size_t smem = (size_t)3 * NN * ((NQ > 1) ? (2 * BS + 1) : BS) * sizeof(double);
     const int64_t P = a.ncell * NQ;
     if (P == 0) return MM_OK;
     const int64_t blocks = (P + BS - 1) / BS;
