@@ -200,6 +200,25 @@ function material_response(dim::MaterialModels.AbstractDim, m::Plastic, Δε::Cu
     return σ, T, BatchedPlasticState(new, layout)
 end
 
+# The caller's quadrature loop fused around the update (include/mmb200.h mm_cells_*): what a Ferrite.jl assemble_cell! does
+# around material_response, all cells at once.  dNdx: P x 3nn (shape_gradient(cv, q, a) after reinit!, P = ncell*nq, row = cell*nq + q
+# -> component-major as the C side wants), dΩ: P, ue: ncell x 3nn, state: P x 14 (SoA).  Returns fe (ncell x 3nn) and the new state.
+function cell_internal_forces(m::Plastic, dNdx::CuMatrix{Float64}, dΩ::CuVector{Float64}, ue::CuMatrix{Float64}, state::BatchedPlasticState;
+                              tangent::Bool = false)
+    state.layout == MM_LAYOUT_SOA || error("cell_internal_forces needs the SoA state layout")
+    ncell, nc = size(ue); nn = nc ÷ 3; P = length(dΩ); nq = P ÷ ncell
+    fe = CUDA.zeros(Float64, ncell, nc); new = similar(state.data)
+    D = tangent ? CUDA.zeros(Float64, P, 36) : nothing
+    flags = CUDA.zeros(UInt8, P); iters = CUDA.zeros(UInt8, P); nfail = CUDA.zeros(Int32, 1)
+    check(ccall((:mm_cells_plastic, libmmb200), Cint,
+                (Ref{MMPlastic}, Cint, Cint, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble},
+                 CuPtr{Cdouble}, CuPtr{UInt8}, CuPtr{UInt8}, CuPtr{Int32}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+                Ref(MMPlastic(m)), nn, nq, dNdx, dΩ, ue, state.data, fe, CU_NULL, tangent ? D : CU_NULL, new, flags, iters, nfail, C_NULL, ncell,
+                CUDA.stream().handle), "mm_cells_plastic")
+    Array(nfail)[1] == 0 || error("Material model not converged. Could not find material state.")                  # Plastic.jl:157
+    return fe, BatchedPlasticState(new, MM_LAYOUT_SOA), D
+end
+
 # CrystalViscoPlastic{12} (CrystalViscoPlastic.jl:64-94): the MMCrystal struct (scalars, nslip, MS[12][9], H[12][12]) is
 # filled from `m.MS` and `m.H` directly (same memory order: MS[i] column-major Tensor{2,3}; H[i][j] = m.H[i,j]).
 struct MMCrystal

@@ -131,5 +131,21 @@ def test_no_entry_point_writes_out_of_bounds(mm, cuda_lib, N, lay, shift):
         assert lib.mm_crystal(C.byref(cm._c), I(de), 1.0, I(np.zeros((42, N))), s.ptr, t.ptr, so.ptr, ac.ptr, it.ptr, pn, None, N, lay, None) == 0
         for g, n in ((s, "σ"), (t, "tangent"), (so, "state"), (it, "iters"), (ac, "active")):
             g.check("mm_crystal(q=%g) %s" % (q, n))
+    # fused cell kernels (SoA only): ncell chosen so that P = ncell*nq is ragged against the 128-thread blocks
+    if lay == 0:
+        for nn, nq in ((4, 1), (4, 4), (8, 1), (8, 8), (10, 4)):
+            ncell = max(1, N // nq)
+            P = ncell * nq
+            dN = sy.host_uniform(P, 3 * nn, 71, [-1.0] * (3 * nn), [1.0] * (3 * nn))
+            dO = sy.host_uniform(P, 1, 72, [0.5], [1.5])
+            ue = sy.host_uniform(ncell, 3 * nn, 73, [-4e-4] * (3 * nn), [4e-4] * (3 * nn))
+            fe, s, t, so, fl, it = G(3 * nn * ncell), G(6 * P), G(36 * P), G(14 * P), G(P, u8), G(P, u8)
+            assert lib.mm_cells_plastic(C.byref(pp), nn, nq, I(dN), I(dO), I(ue), I(np.zeros((14, P))), fe.ptr, s.ptr, t.ptr, so.ptr, fl.ptr, it.ptr, pn, None,
+                                        ncell, None) == 0
+            for g, n in ((fe, "fe"), (s, "σ"), (t, "tangent"), (so, "state"), (fl, "flags"), (it, "iters")):
+                g.check("mm_cells_plastic(%d,%d) %s" % (nn, nq, n))
+            fe, s = G(3 * nn * ncell), G(6 * P)
+            assert lib.mm_cells_linear_elastic(C.byref(le), nn, nq, I(dN), I(dO), I(ue), fe.ptr, s.ptr, None, ncell, None) == 0
+            fe.check("mm_cells_linear_elastic fe"), s.check("mm_cells_linear_elastic σ")
     torch.cuda.synchronize()
     assert lib.mm_last_error() is not None
