@@ -183,12 +183,15 @@ int mm_hyper_energy(int model, const MMHyper* p, const double* strain, int strai
  * index = cell*nq + q.  All arrays component-major: per point dNdx[(3a+k)*P + i] (∇N_a in physical coordinates, as CellValues
  * holds it after reinit!), dOmega[i], state / sig / tan [c*P + i]; per cell ue, fe [(3a+k)*ncell + cell].
  * sig (6 per point) and tan (36 per point) may be NULL: explicit / matrix-free codes need neither, and leaving the tangent out
- * removes 288 of the 608 algorithmic bytes per point of the unfused J2 update. */
+ * removes 288 of the 608 algorithmic bytes per point of the unfused J2 update.
+ * ke (may be NULL): the element stiffness ke[3a+i][3b+j] = Σ_q δε_(a,i) ⊡ D ⊡ Δε_(b,j) dΩ, (3nn)² per cell, stored
+ * ke[((3a+i)*3nn + 3b+j)*ncell + cell]; D stays in registers (not major-symmetric for J2 with kinematic hardening, so all
+ * (3nn)² entries are written). */
 int mm_cells_linear_elastic(const MMLinearElastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue,
-                            double* fe, double* sig, double* tan, int64_t ncell, void* stream);
+                            double* fe, double* ke, double* sig, double* tan, int64_t ncell, void* stream);
 int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue,
-                     const double* state_in, double* fe, double* sig, double* tan, double* state_out, uint8_t* flags, uint8_t* iters,
-                     int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell, void* stream);
+                     const double* state_in, double* fe, double* ke, double* sig, double* tan, double* state_out, uint8_t* flags,
+                     uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell, void* stream);
 
 /* Deterministic synthetic inputs (bench + parity harness): out(i,c) = lo[c] + (hi[c]-lo[c]) * u(i,c),
  * u(i,c) = (splitmix64(seed + i*nc + c) >> 11) * 2^-53.  lo/hi are HOST arrays of nc doubles. */

@@ -212,8 +212,8 @@ function cell_internal_forces(m::Plastic, dNdx::CuMatrix{Float64}, dΩ::CuVector
     flags = CUDA.zeros(UInt8, P); iters = CUDA.zeros(UInt8, P); nfail = CUDA.zeros(Int32, 1)
     check(ccall((:mm_cells_plastic, libmmb200), Cint,
                 (Ref{MMPlastic}, Cint, Cint, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble},
-                 CuPtr{Cdouble}, CuPtr{UInt8}, CuPtr{UInt8}, CuPtr{Int32}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
-                Ref(MMPlastic(m)), nn, nq, dNdx, dΩ, ue, state.data, fe, CU_NULL, tangent ? D : CU_NULL, new, flags, iters, nfail, C_NULL, ncell,
+                 CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt8}, CuPtr{UInt8}, CuPtr{Int32}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+                Ref(MMPlastic(m)), nn, nq, dNdx, dΩ, ue, state.data, fe, CU_NULL #= ke: pass a (3nn)² x ncell array for BᵀDB =#, CU_NULL, tangent ? D : CU_NULL, new, flags, iters, nfail, C_NULL, ncell,
                 CUDA.stream().handle), "mm_cells_plastic")
     Array(nfail)[1] == 0 || error("Material model not converged. Could not find material state.")                  # Plastic.jl:157
     return fe, BatchedPlasticState(new, MM_LAYOUT_SOA), D

@@ -601,7 +601,7 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
     raise TypeError("material_response: unsupported material %r" % (m,))
 
 
-def cell_internal_forces(m, dNdx, dΩ, ue, state=None, tangent=False, stress=False, options=None):
+def cell_internal_forces(m, dNdx, dΩ, ue, state=None, tangent=False, stress=False, stiffness=False, options=None):
     """The caller's quadrature loop fused around material_response (what a Ferrite.jl-style
     assemble_cell! does around the reference's per-point call, src/MaterialModels.jl:41-52), all cells at once:
 
@@ -609,7 +609,8 @@ def cell_internal_forces(m, dNdx, dΩ, ue, state=None, tangent=False, stress=Fal
 
     dNdx (3·nn, P): ∇N_a at every quadrature point (physical coordinates), dΩ (P,), ue (3·nn, ncell), P = ncell·nq, point
     index = cell·nq + q; state: PlasticState over the P points (layout "soa") for Plastic, None for LinearElastic.
-    Returns (fe (3·nn, ncell), new_state, extras) with extras["stress"] (6, P) / extras["tangent"] (36, P) when requested.
+    Returns (fe (3·nn, ncell), new_state, extras) with extras["stress"] (6, P) / extras["tangent"] (36, P) when requested and
+    extras["stiffness"] ((3·nn)², ncell): ke[3a+i, 3b+j] = Σ_q δε ⊡ D ⊡ Δε dΩ at row (3a+i)·3nn + 3b+j (stiffness=True).
     Device (torch CUDA) arrays only.  Supported (nn, nq): (4,1) (4,4) (8,1) (8,8) (10,4)."""
     dNdx, dΩ, ue = _prep(dNdx), _prep(dΩ), _prep(ue)
     if _is_host(dNdx) or _is_host(dΩ) or _is_host(ue):
@@ -625,12 +626,13 @@ def cell_internal_forces(m, dNdx, dΩ, ue, state=None, tangent=False, stress=Fal
     fe = _empty((3 * nn, ncell), ue)
     σ = _empty((6, P), ue) if stress else None
     tan = _empty((36, P), ue) if tangent else None
+    ke = _empty((9 * nn * nn, ncell), ue) if stiffness else None
     lib = load()
-    extras = {"stress": σ, "tangent": tan}
+    extras = {"stress": σ, "tangent": tan, "stiffness": ke}
     with _DeviceGuard(ue):
         if isinstance(m, LinearElastic):
-            check(lib.mm_cells_linear_elastic(ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(fe), _ptr(σ), _ptr(tan), ncell, _stream(ue)),
-                  "mm_cells_linear_elastic")
+            check(lib.mm_cells_linear_elastic(ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(fe), _ptr(ke), _ptr(σ), _ptr(tan), ncell,
+                                              _stream(ue)), "mm_cells_linear_elastic")
             return fe, (state if state is not None else LinearElasticState()), extras
         if not isinstance(m, Plastic):
             raise NotImplementedError("cell_internal_forces is implemented for LinearElastic and Plastic")
@@ -642,7 +644,7 @@ def cell_internal_forces(m, dNdx, dΩ, ue, state=None, tangent=False, stress=Fal
         iters = _empty((P,), ue, torch.uint8)
         nfail = _zeros((1,), ue, torch.int32)
         o = _newton_opts(m, options)
-        check(lib.mm_cells_plastic(ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(sin), _ptr(fe), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(flags),
+        check(lib.mm_cells_plastic(ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(sin), _ptr(fe), _ptr(ke), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(flags),
                                    _ptr(iters), _ptr(nfail), ctypes.byref(o), ncell, _stream(ue)), "mm_cells_plastic")
     new = PlasticState(sout, "soa")
     new.flags, new.iters, new.n_fail = flags, iters, nfail

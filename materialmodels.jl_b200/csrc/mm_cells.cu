@@ -5,6 +5,7 @@
 //         ε  = function_symmetric_gradient(cv, q, ue)           # ε = sym(Σ_a u_a ⊗ ∇N_a)
 //         σ, D, state_new[q] = material_response(m, ε, state[q]) # <- the reference's hot path (src/MaterialModels.jl:41-52)
 //         fe[a] += (σ ⋅ ∇N_a) dΩ                                # Bᵀσ
+//         ke[a,b] += δε_a ⊡ D ⊡ Δε_b dΩ                         # BᵀDB  (optional)
 //
 // One thread per quadrature point; the NQ points of a cell sit in NQ adjacent lanes and sum their Bᵀσ contributions through
 // shared memory, so σ never goes to memory and the 36-entry tangent is written only if the caller asks for it
@@ -19,22 +20,24 @@
 namespace mm {
 
 // accessor for the inner 3D model: strain from registers, state straight from / to global memory (coalesced), σ kept in registers
-template <int NS> struct CellAcc {
+// KEEP_D: the 36-entry tangent also stays in registers (for the element stiffness BᵀDB)
+template <bool KEEP_D> struct CellAcc {
     double eps[6], sig[6];
+    double D[KEEP_D ? 36 : 1];
     const double* st_in; double* st_out; double* tan; double* sig_out;
     int64_t P, i;
     template <int A> __device__ __forceinline__ double in(int c) const { return A == 0 ? eps[c] : __ldcs(st_in + (int64_t)c * P + i); }
     template <int A> __device__ __forceinline__ void out(int c, double v) {
         if (A == 0) { sig[c] = v; if (sig_out) __stcs(sig_out + (int64_t)c * P + i, v); }
-        else if (A == 1) __stcs(tan + (int64_t)c * P + i, v);
+        else if (A == 1) { if (KEEP_D) D[KEEP_D ? c : 0] = v; if (tan) __stcs(tan + (int64_t)c * P + i, v); }
         else __stcs(st_out + (int64_t)c * P + i, v);
     }
-    template <int A> __device__ __forceinline__ bool has_out() const { return A == 1 ? tan != nullptr : true; }
+    template <int A> __device__ __forceinline__ bool has_out() const { return A == 1 ? (KEEP_D || tan != nullptr) : true; }
 };
 
 struct CellArgs {
     const double* dNdx; const double* dOmega; const double* ue; const double* state_in;
-    double* fe; double* sig; double* tan; double* state_out;
+    double* fe; double* ke; double* sig; double* tan; double* state_out;
     uint8_t* flags; uint8_t* iters; int32_t* n_fail;
     int64_t ncell;
 };
@@ -47,14 +50,14 @@ struct CellArgs {
 #ifndef MM_CELLS_MINBLOCKS
 #define MM_CELLS_MINBLOCKS 3
 #endif
-template <int MODEL, int NN, int NQ, int BS>
-__global__ void __launch_bounds__(BS, MM_CELLS_MINBLOCKS) cells_kernel(const ElasticK ke, const PlasticK kp, const CellArgs a) {
+template <int MODEL, int NN, int NQ, int BS, bool WITH_KE>
+__global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_kernel(const ElasticK ke, const PlasticK kp, const CellArgs a) {
     static_assert(NQ == 1 || NQ == 2 || NQ == 4 || NQ == 8, "quadrature points per cell must be a power of two <= 8");
     static_assert(BS % 32 == 0 && 32 % NQ == 0, "a cell's points must share a warp");
     constexpr int NC = 3 * NN;
     extern __shared__ double sm[];
     double* sm_dN = sm;                                  // [NC][BS]
-    double* sm_f = sm + NC * BS;                         // [NC][BS + 1]  (NQ > 1), padded: the NQ lanes of a cell read NQ different rows
+    double* sm_f = sm + NC * BS;                         // [NC][BS + 1] (fe) / [3 NC][BS + 1] (one block row of ke), NQ > 1; padded: the NQ lanes of a cell read NQ different rows
     const int64_t P = a.ncell * NQ;
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     const unsigned mask = __ballot_sync(0xffffffffu, i < P);   // cells are whole and warp-local: the survivors sync among themselves below
@@ -62,7 +65,7 @@ __global__ void __launch_bounds__(BS, MM_CELLS_MINBLOCKS) cells_kernel(const Ela
     const int64_t cell = i / NQ;
     const int q = (int)(i - cell * NQ);
     const int t = threadIdx.x;
-    CellAcc<MODEL == 1 ? 14 : 0> acc;
+    CellAcc<WITH_KE> acc;
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc.eps[c] = 0.0;
 #pragma unroll
@@ -109,9 +112,9 @@ __global__ void __launch_bounds__(BS, MM_CELLS_MINBLOCKS) cells_kernel(const Ela
             else sm_f[(3 * n + k) * (BS + 1) + t] = f[k];
         }
     }
+    const int t0 = t - q;                                  // first lane of this cell
     if (NQ > 1) {
         __syncwarp(mask);
-        const int t0 = t - q;                              // first lane of this cell
 #pragma unroll
         for (int c0 = 0; c0 < NC; c0 += NQ) {
             const int c = c0 + q;
@@ -123,24 +126,70 @@ __global__ void __launch_bounds__(BS, MM_CELLS_MINBLOCKS) cells_kernel(const Ela
             }
         }
     }
+    if (WITH_KE) {
+        // ke[3a+i][3b+j] = Σ_q Σ_nl ∇N_a[n] D_(in)(jl) ∇N_b[l] dΩ   (δε_i ⊡ D ⊡ Δε_j with the minor symmetries of D), one block row
+        // (fixed a: 3 x NC values) at a time: T_a[i][J] = Σ_n ∇N_a[n] D[(in), J], then block[i][j] = Σ_l T_a[i][(jl)] ∇N_b[l].
+        // Stored component-major over cells: ke[((3a+i)*NC + 3b+j)*ncell + cell].
+#pragma unroll 1
+        for (int na = 0; na < NN; ++na) {
+            double da[3], T[3][6];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) da[k] = sm_dN[(3 * na + k) * BS + t] * dO;
+#pragma unroll
+            for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                for (int J = 0; J < 6; ++J)
+                    T[ii][J] = da[0] * acc.D[WITH_KE ? sym_slot(ii, 0) + 6 * J : 0] + da[1] * acc.D[WITH_KE ? sym_slot(ii, 1) + 6 * J : 0] +
+                               da[2] * acc.D[WITH_KE ? sym_slot(ii, 2) + 6 * J : 0];
+            if (NQ > 1) __syncwarp(mask);                  // the previous block row has been read
+#pragma unroll 1
+            for (int nb = 0; nb < NN; ++nb) {
+                double db[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) db[k] = sm_dN[(3 * nb + k) * BS + t];
+#pragma unroll
+                for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 3; ++jj) {
+                        const double v = T[ii][sym_slot(jj, 0)] * db[0] + T[ii][sym_slot(jj, 1)] * db[1] + T[ii][sym_slot(jj, 2)] * db[2];
+                        if (NQ == 1) __stcs(a.ke + ((int64_t)(3 * na + ii) * NC + (3 * nb + jj)) * a.ncell + cell, v);
+                        else sm_f[(ii * NC + 3 * nb + jj) * (BS + 1) + t] = v;
+                    }
+            }
+            if (NQ > 1) {
+                __syncwarp(mask);
+#pragma unroll 1
+                for (int c = q; c < 3 * NC; c += NQ) {     // c = ii*NC + (3 nb + jj)
+                    double v = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NQ; ++j) v += sm_f[c * (BS + 1) + t0 + j];
+                    __stcs(a.ke + ((int64_t)(3 * na) * NC + c) * a.ncell + cell, v);
+                }
+            }
+        }
+    }
 }
 
-template <int MODEL, int NN, int NQ>
-int launch_cells(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
+template <int MODEL, int NN, int NQ, bool WITH_KE>
+int launch_cells_k(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
     constexpr int BS = 128;
-    constexpr size_t smem = (size_t)3 * NN * ((NQ > 1) ? (2 * BS + 1) : BS) * sizeof(double);
+    constexpr size_t smem = (size_t)3 * NN * (BS + ((NQ > 1) ? (WITH_KE ? 3 : 1) * (BS + 1) : 0)) * sizeof(double);
     const int64_t P = a.ncell * NQ;
     if (P == 0) return MM_OK;
     const int64_t blocks = (P + BS - 1) / BS;
     if (blocks > 2147483647LL) return set_error(MM_ERR_ARG, "mm_cells: too many points for one launch");
     static bool configured = false;
     if (!configured && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(cells_kernel<MODEL, NN, NQ, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(cells_kernel<MODEL, NN, NQ, BS, WITH_KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_cells: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    cells_kernel<MODEL, NN, NQ, BS><<<(unsigned)blocks, BS, smem, st>>>(ke, kp, a);
+    cells_kernel<MODEL, NN, NQ, BS, WITH_KE><<<(unsigned)blocks, BS, smem, st>>>(ke, kp, a);
     return check_launch("mm_cells");
+}
+template <int MODEL, int NN, int NQ>
+int launch_cells(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
+    return a.ke ? launch_cells_k<MODEL, NN, NQ, true>(ke, kp, a, st) : launch_cells_k<MODEL, NN, NQ, false>(ke, kp, a, st);
 }
 
 template <int MODEL>
@@ -159,19 +208,19 @@ using namespace mm;
 
 extern "C" {
 
-int mm_cells_linear_elastic(const MMLinearElastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, double* fe, double* sig,
-                            double* tan, int64_t ncell, void* stream) {
+int mm_cells_linear_elastic(const MMLinearElastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, double* fe, double* ke_out,
+                            double* sig, double* tan, int64_t ncell, void* stream) {
     if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !fe))) return set_error(MM_ERR_ARG, "mm_cells_linear_elastic: bad argument");
-    CellArgs a{dNdx, dOmega, ue, nullptr, fe, sig, tan, nullptr, nullptr, nullptr, nullptr, ncell};
+    CellArgs a{dNdx, dOmega, ue, nullptr, fe, ke_out, sig, tan, nullptr, nullptr, nullptr, nullptr, ncell};
     PlasticK kp{};
     return dispatch_cells<0>(nn, nq, make_elastic_k(p->E, p->nu), kp, a, (cudaStream_t)stream);
 }
 
 int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, const double* state_in, double* fe,
-                     double* sig, double* tan, double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell,
+                     double* ke_out, double* sig, double* tan, double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell,
                      void* stream) {
     if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !state_in || !fe || !state_out))) return set_error(MM_ERR_ARG, "mm_cells_plastic: bad argument");
-    CellArgs a{dNdx, dOmega, ue, state_in, fe, sig, tan, state_out, flags, iters, n_fail, ncell};
+    CellArgs a{dNdx, dOmega, ue, state_in, fe, ke_out, sig, tan, state_out, flags, iters, n_fail, ncell};
     ElasticK ke = make_elastic_k(p->E, p->nu);
     PlasticK kp = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
     return dispatch_cells<1>(nn, nq, ke, kp, a, (cudaStream_t)stream);

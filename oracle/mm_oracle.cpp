@@ -318,7 +318,7 @@ int mmo_wrapped_transviso(int kind, const MMTransverselyIsotropic* p, const doub
 //   ε = symmetric(Σ_a u_a ⊗ ∇N_a);  σ, D, state_new = material_response(m, ε, state);  fe[a] += (σ ⋅ ∇N_a) dΩ
 // model: 0 LinearElastic (params = MMLinearElastic), 1 Plastic (params = MMPlastic).  Arrays as include/mmb200.h mm_cells_*.
 int mmo_cells(int model, const void* params, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, const double* state_in,
-              double* fe, double* sig_out, double* tan_out, double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
+              double* fe, double* ke, double* sig_out, double* tan_out, double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
               int64_t ncell) {
     const int64_t P = ncell * nq;
     LinearElasticM le{}; PlasticM pm{};
@@ -328,7 +328,7 @@ int mmo_cells(int model, const void* params, int nn, int nq, const double* dNdx,
     int64_t fails = 0;
 #pragma omp parallel for schedule(static) reduction(+ : fails)
     for (int64_t cell = 0; cell < ncell; ++cell) {
-        std::vector<double> f(3 * nn, 0.0);
+        std::vector<double> f(3 * nn, 0.0), K(ke ? 9 * nn * nn : 0, 0.0);
         for (int q = 0; q < nq; ++q) {
             const int64_t i = cell * nq + q;
             Ten2<double> G;                                                  // ∇u = Σ_a u_a ⊗ ∇N_a
@@ -362,8 +362,20 @@ int mmo_cells(int model, const void* params, int nn, int nq, const double* dNdx,
                     for (int l = 0; l < 3; ++l) v += sig(k, l) * dNdx[(int64_t)(3 * a + l) * P + i];
                     f[3 * a + k] += v * dOmega[i];
                 }
+            if (ke)                                                          // ke[i,j] += δε_i ⊡ D ⊡ Δε_j dΩ, δε = symmetric(e_k ⊗ ∇N_a)
+                for (int a = 0; a < nn; ++a) for (int k = 0; k < 3; ++k) {
+                    Sym2<double> de;
+                    for (int l = 0; l < 3; ++l) { de(k, l) = 0; }
+                    for (int l = 0; l < 3; ++l) de(k, l) = de(k, l) + 0.5 * dNdx[(int64_t)(3 * a + l) * P + i] * (k == l ? 2.0 : 1.0);
+                    for (int b = 0; b < nn; ++b) for (int m2 = 0; m2 < 3; ++m2) {
+                        Sym2<double> De;
+                        for (int l = 0; l < 3; ++l) De(m2, l) = De(m2, l) + 0.5 * dNdx[(int64_t)(3 * b + l) * P + i] * (m2 == l ? 2.0 : 1.0);
+                        K[(3 * a + k) * 3 * nn + 3 * b + m2] += dcontract(de, dcontract(tan, De)) * dOmega[i];
+                    }
+                }
         }
         for (int c = 0; c < 3 * nn; ++c) fe[(int64_t)c * ncell + cell] = f[c];
+        if (ke) for (int c = 0; c < 9 * nn * nn; ++c) ke[(int64_t)c * ncell + cell] = K[c];
     }
     if (n_fail) *n_fail += (int32_t)fails;
     return 0;

@@ -40,7 +40,7 @@ _SIG = {
     "mmo_hyper_ex": (C.c_int, [C.c_int, C.POINTER(abi.MMHyper), _P, C.c_int, C.c_int, _P, _P, _I64, C.c_int]),
     "mmo_neohook_dPdF_ad": (C.c_int, [C.POINTER(abi.MMHyper), _P, _P, _P]),
     "mmo_wrapped_transviso": (C.c_int, [C.c_int, C.POINTER(abi.MMTransverselyIsotropic), _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
-    "mmo_cells": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64]),
+    "mmo_cells": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64]),
     "mmo_transviso_setup": (C.c_int, [C.c_double] * 5 + [C.POINTER(abi.MMTransverselyIsotropic)]),
     "mmo_transversely_isotropic": (C.c_int, [C.POINTER(abi.MMTransverselyIsotropic), _P, _P, _P, _P, _I64, C.c_int]),
     "mmo_strain_energy_batch": (C.c_int, [C.c_int, _P, _P, C.c_int, _P, _I64, C.c_int]),
@@ -295,7 +295,7 @@ def wrapped_transviso(kind, p, eps_red, a3, layout=SOA, tol=1e-8, max_iter=10):
     return dict(sig=sig, tan=tan, outer_iters=oit, n_fail=int(nfail[0]))
 
 
-def cells(model, params, nn, nq, dNdx, dOmega, ue, state=None, want_tangent=True, tol=1e-8, max_iter=1000):
+def cells(model, params, nn, nq, dNdx, dOmega, ue, state=None, want_tangent=True, want_stiffness=False, tol=1e-8, max_iter=1000):
     """the caller's quadrature loop around material_response.  model 0: LinearElastic (E, nu); 1: Plastic.
     dNdx (3nn, P), dOmega (P,), ue (3nn, ncell), state (14, P) with P = ncell*nq."""
     dNdx = np.ascontiguousarray(dNdx, dtype=np.float64); dOmega = np.ascontiguousarray(dOmega, dtype=np.float64); ue = np.ascontiguousarray(ue, dtype=np.float64)
@@ -303,6 +303,7 @@ def cells(model, params, nn, nq, dNdx, dOmega, ue, state=None, want_tangent=True
     assert dNdx.shape == (3 * nn, P) and dOmega.shape == (P,) and ue.shape == (3 * nn, ncell)
     fe, sig = np.zeros((3 * nn, ncell)), np.zeros((6, P))
     tan = np.zeros((36, P)) if want_tangent else None
+    ke = np.zeros((9 * nn * nn, ncell)) if want_stiffness else None
     if model == 0:
         p = abi.MMLinearElastic(*params)
         st_in = st_out = flags = iters = None
@@ -312,7 +313,7 @@ def cells(model, params, nn, nq, dNdx, dOmega, ue, state=None, want_tangent=True
         flags, iters = np.zeros(P, np.uint8), np.zeros(P, np.uint8)
     nfail = np.zeros(1, np.int32)
     o = abi.MMNewtonOpts(tol, max_iter, 0)
-    rc = lib().mmo_cells(model, C.byref(p), nn, nq, _ptr(dNdx), _ptr(dOmega), _ptr(ue), _ptr(st_in), _ptr(fe), _ptr(sig), _ptr(tan), _ptr(st_out),
+    rc = lib().mmo_cells(model, C.byref(p), nn, nq, _ptr(dNdx), _ptr(dOmega), _ptr(ue), _ptr(st_in), _ptr(fe), _ptr(ke), _ptr(sig), _ptr(tan), _ptr(st_out),
                          _ptr(flags), _ptr(iters), _ptr(nfail), C.byref(o), ncell)
     assert rc == 0
-    return dict(fe=fe, sig=sig, tan=tan, state=st_out, flags=flags, iters=iters, n_fail=int(nfail[0]))
+    return dict(fe=fe, ke=ke, sig=sig, tan=tan, state=st_out, flags=flags, iters=iters, n_fail=int(nfail[0]))

@@ -94,6 +94,9 @@ def test_oracle_cell_loop_finite_element_identities(oracle, kind):
             D[i, j, k, l] = D[j, i, k, l] = D[i, j, l, k] = D[j, i, l, k] = D36[I + 6 * J]
     K = np.einsum("cqaj,ijkl,cqbl,cq->caibk", dNdx, D, dNdx, dO)
     assert np.allclose(fe_of(r, ncell, nn), np.einsum("caibk,cbk->cai", K, U), rtol=1e-11, atol=1e-12 * E)
+    rk = oracle.cells(0, (E, NU), nn, nq, d, o, u, want_stiffness=True)                # the oracle's ke[i,j] += δε_i ⊡ D ⊡ Δε_j dΩ loop
+    Ko = ke_of(rk, ncell, nn)
+    assert np.allclose(Ko, K.reshape(ncell, 3 * nn, 3 * nn), rtol=1e-12, atol=1e-12 * E) and np.allclose(Ko, Ko.transpose(0, 2, 1), rtol=1e-12, atol=1e-12 * E)
     # (iv) per point the loop calls the (pinned) point-wise update: Plastic through the cell loop == Plastic on the same strains
     p = H.plastic_c()
     U = AMP[kind] * (2 * rng.random((ncell, nn, 3)) - 1)
@@ -110,10 +113,22 @@ def test_oracle_cell_loop_finite_element_identities(oracle, kind):
         s[:, i, j] = s[:, j, i] = rc["sig"][I]
     f_ref = np.einsum("cqkl,cqal,cq->cak", s.reshape(ncell, nq, 3, 3), dNdx, dO)
     assert np.allclose(fe_of(rc, ncell, nn), f_ref, rtol=1e-12, atol=1e-12)
+    # (v) consistent element stiffness with the (non-major-symmetric) J2 tangent of every point
+    rk = oracle.cells(1, p, nn, nq, d, o, u, np.zeros((14, P)), want_stiffness=True)
+    Dq = np.zeros((P, 3, 3, 3, 3))
+    for I, (i, j) in enumerate(SLOTS):
+        for J, (k, l) in enumerate(SLOTS):
+            Dq[:, i, j, k, l] = Dq[:, j, i, k, l] = Dq[:, i, j, l, k] = Dq[:, j, i, l, k] = rc["tan"][I + 6 * J]
+    Kp = np.einsum("cqaj,cqijkl,cqbl,cq->caibk", dNdx, Dq.reshape(ncell, nq, 3, 3, 3, 3), dNdx, dO).reshape(ncell, 3 * nn, 3 * nn)
+    assert np.allclose(ke_of(rk, ncell, nn), Kp, rtol=1e-11, atol=1e-12 * E)
 
 
 def fe_of(r, ncell, nn):
     return r["fe"].T.reshape(ncell, nn, 3)
+
+
+def ke_of(r, ncell, nn):
+    return r["ke"].T.reshape(ncell, 3 * nn, 3 * nn)
 
 
 @pytest.mark.gpu
@@ -141,6 +156,13 @@ def test_gpu_cell_loop_matches_oracle(mm, cuda_lib, oracle, kind, ncell):
         fscale = np.abs(r["fe"]).max()
         assert np.abs(fe.cpu().numpy() - r["fe"]).max() < H.RTOL * fscale
         assert np.abs(new.data.cpu().numpy() - r["state"]).max() < 1e-12 * max(1.0, np.abs(r["state"]).max())
+        # element stiffness BᵀDB (D stays in registers)
+        rk = oracle.cells(1, p, nn, nq, d, o, u, st_ref, want_stiffness=True)
+        fe3, new3, ex3 = mm.cell_internal_forces(m, dev(d), dev(o), dev(u), st, stiffness=True)
+        kscale = np.abs(rk["ke"]).max(axis=0)
+        assert (np.abs(ex3["stiffness"].cpu().numpy() - rk["ke"]).max(axis=0) / kscale).max() < H.RTOL
+        assert np.abs(fe3.cpu().numpy() - r["fe"]).max() < H.RTOL * fscale                      # (another kernel instantiation: not bitwise)
+        assert np.abs(new3.data.cpu().numpy() - r["state"]).max() < 1e-12 * max(1.0, np.abs(r["state"]).max()) and torch.equal(new3.flags, new.flags)
         # the lean call (no σ, no tangent written) gives the same forces and state bit for bit
         fe2, new2, ex2 = mm.cell_internal_forces(m, dev(d), dev(o), dev(u), st)
         assert ex2["stress"] is None and ex2["tangent"] is None
@@ -150,6 +172,9 @@ def test_gpu_cell_loop_matches_oracle(mm, cuda_lib, oracle, kind, ncell):
     r = oracle.cells(0, (E, NU), nn, nq, d, o, u)
     fe, _, ex = mm.cell_internal_forces(le, dev(d), dev(o), dev(u), stress=True)
     assert np.abs(fe.cpu().numpy() - r["fe"]).max() < H.RTOL * np.abs(r["fe"]).max() and H.rel_err(ex["stress"].cpu().numpy(), r["sig"]).max() < H.RTOL
+    _, _, exk = mm.cell_internal_forces(le, dev(d), dev(o), dev(u), stiffness=True)
+    Kg = exk["stiffness"].cpu().numpy().T.reshape(ncell, 3 * nn, 3 * nn)
+    assert np.allclose(np.einsum("crs,cs->cr", Kg, u.T), fe.cpu().numpy().T, rtol=1e-10, atol=1e-10 * np.abs(r["fe"]).max())   # fe = Kₑ uₑ
     # equilibrium identity through the CUDA path: the nodal forces of every cell sum to zero
     f = fe.cpu().numpy().T.reshape(ncell, nn, 3)
     assert np.abs(f.sum(axis=1)).max() < 1e-10 * np.abs(f).max()

@@ -139,13 +139,13 @@ def test_no_entry_point_writes_out_of_bounds(mm, cuda_lib, N, lay, shift):
             dN = sy.host_uniform(P, 3 * nn, 71, [-1.0] * (3 * nn), [1.0] * (3 * nn))
             dO = sy.host_uniform(P, 1, 72, [0.5], [1.5])
             ue = sy.host_uniform(ncell, 3 * nn, 73, [-4e-4] * (3 * nn), [4e-4] * (3 * nn))
-            fe, s, t, so, fl, it = G(3 * nn * ncell), G(6 * P), G(36 * P), G(14 * P), G(P, u8), G(P, u8)
-            assert lib.mm_cells_plastic(C.byref(pp), nn, nq, I(dN), I(dO), I(ue), I(np.zeros((14, P))), fe.ptr, s.ptr, t.ptr, so.ptr, fl.ptr, it.ptr, pn, None,
-                                        ncell, None) == 0
-            for g, n in ((fe, "fe"), (s, "σ"), (t, "tangent"), (so, "state"), (fl, "flags"), (it, "iters")):
+            fe, kk, s, t, so, fl, it = G(3 * nn * ncell), G(9 * nn * nn * ncell), G(6 * P), G(36 * P), G(14 * P), G(P, u8), G(P, u8)
+            assert lib.mm_cells_plastic(C.byref(pp), nn, nq, I(dN), I(dO), I(ue), I(np.zeros((14, P))), fe.ptr, kk.ptr, s.ptr, t.ptr, so.ptr, fl.ptr, it.ptr, pn,
+                                        None, ncell, None) == 0
+            for g, n in ((fe, "fe"), (kk, "ke"), (s, "σ"), (t, "tangent"), (so, "state"), (fl, "flags"), (it, "iters")):
                 g.check("mm_cells_plastic(%d,%d) %s" % (nn, nq, n))
             fe, s = G(3 * nn * ncell), G(6 * P)
-            assert lib.mm_cells_linear_elastic(C.byref(le), nn, nq, I(dN), I(dO), I(ue), fe.ptr, s.ptr, None, ncell, None) == 0
+            assert lib.mm_cells_linear_elastic(C.byref(le), nn, nq, I(dN), I(dO), I(ue), fe.ptr, None, s.ptr, None, ncell, None) == 0
             fe.check("mm_cells_linear_elastic fe"), s.check("mm_cells_linear_elastic σ")
     torch.cuda.synchronize()
     assert lib.mm_last_error() is not None

@@ -206,7 +206,17 @@ def main():
                 bpp = 24 * nn + 8 + 112 + 112 + 2 + 48 * nn / nq + (288 if tan else 0)
                 report("cells J2 nn=%d nq=%d %s" % (nn, nq, "fe+state+tangent" if tan else "fe+state"), P, bpp, med, mn,
                        {"plastic_fraction": round((stB.flags & 1).float().mean().item(), 3), "n_fail": int(stB.n_fail.item()), "unfused_B_per_pt": 608 + 48 + 24 * nn + 8 + 48 * nn / nq})
-            del dN, dO, ue, stA, stB
+            # element stiffness BᵀDB as well (D stays in registers): + 8 (3nn)²/nq bytes per point; fewer points so that ke fits
+            Pk = min(P, int(2e7 * S) // nq * nq if nq == 1 else P)
+            nck = Pk // nq
+            ke_bytes = 8 * 9 * nn * nn / nq
+            sub = lambda x, n: x[..., :n].contiguous()
+            dNk, dOk, uek, stk = sub(dN, Pk), dO[:Pk].contiguous(), sub(ue, nck), mm.PlasticState(sub(stA.data, Pk))
+            med, mn = timeit(lambda: mm.cell_internal_forces(m, dNk, dOk, uek, stk, stiffness=True, options={"defer_check": True}), a.reps)
+            flop = 2 * (nn * 54 + nn * nn * 27)
+            report("cells J2 nn=%d nq=%d fe+state+ke" % (nn, nq), Pk, 24 * nn + 8 + 112 + 112 + 2 + 48 * nn / nq + ke_bytes, med, mn,
+                   {"ke_flop_per_pt": flop, "ke_TFLOPs": round(flop * Pk / (med * 1e-3) / 1e12, 2)})
+            del dN, dO, ue, stA, stB, dNk, dOk, uek, stk
             torch.cuda.empty_cache()
     if want("xu"):
         N = int(1e8 * S)
