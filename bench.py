@@ -125,6 +125,49 @@ def cpu_baseline_run(points, steps=1, warmup=0):
     return points * steps / dt, O.num_threads(), dt, frac
 
 
+def cpu_baseline_other_configs(n=200000):
+    """cpu_baseline leg for the other BASELINE.json configs: the oracle (reference algorithm, all host cores) on an n-point sample
+    of each config's synthetic inputs -> updates/s, so every GPU kernel figure in `other_configs` has its CPU figure beside it."""
+    import numpy as np
+
+    import oracle as O
+    from materialmodels_jl_b200 import _abi, synth as sy
+
+    def rate(fn):
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        reps = max(1, min(20, int(1.0 / max(dt, 1e-6))))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return n * reps / (time.perf_counter() - t0)
+
+    out = {"threads": O.num_threads(), "sample_points": n}
+    nc, lo, hi, seed = sy.c1_strain()
+    e = sy.host_uniform(n, nc, seed, lo, hi)
+    out["c0_linear_elastic_sigma_only"] = rate(lambda: O.linear_elastic(200e3, 0.3, e, want_tangent=False))
+    nc, lo, hi, seed = sy.c3_defgrad()
+    F = sy.host_uniform(n, nc, seed, lo, hi)
+    out["c2_neohook_from_F"] = rate(lambda: O.hyper(_abi.MM_NEOHOOK, _abi.MMHyper(**sy.NEOHOOK_PARAMS), F, 1))
+    out["c2_yeoh_from_F"] = rate(lambda: O.hyper(_abi.MM_YEOH, _abi.MMHyper(**sy.YEOH_PARAMS), F, 1))
+    x = sy.XU_PARAMS
+    xp = O.xu_params(x["sigma_max"], x["tau_max"], x["sigma_max"] * np.e * x["delta_n"], x["tau_max"] * np.sqrt(0.5 * np.e) * x["delta_t"], x["Delta_n_star"])
+    nc, lo, hi, seed = sy.c5_jump()
+    D = sy.host_uniform(n, nc, seed, lo, hi)
+    out["c4_xu_needleman_3d"] = rate(lambda: O.xu_needleman(xp, D, 3))
+    c = sy.CRYSTAL_PARAMS
+    pl, di = O.slipsystems(0, sy.CRYSTAL_RODRIGUES)
+    cp = O.crystal_params(c["E"], c["nu"], c["tau_y"], c["H_iso"], c["H_kin"], c["q"], c["alpha_inf"], c["t_star"], c["sigma_c"], c["m"], pl, di)
+    nc, lo, hi, seed = sy.c4_strain_increment(0)
+    sA = O.crystal(cp, sy.host_uniform(n, nc, seed, lo, hi), np.zeros((42, n)))["state"]
+    nc, lo, hi, seed = sy.c4_strain_increment(1)
+    dB = sy.host_uniform(n, nc, seed, lo, hi)
+    out["c3_crystal_fcc12_stepB"] = rate(lambda: O.crystal(cp, dB, sA))
+    return out
+
+
 def run_reference(args):
     """--impl reference: Julia is not installed here and the reference has no C/C++ sources to compile, so the
     reference arm is the oracle port (oracle/, kind "port") on all host cores; each step is a bounded sample."""
@@ -292,6 +335,17 @@ def main():
         v, cores, dt, fr = cpu_baseline_run(args.cpu_points)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d-point slice of the same workload (step B), oracle mmo_plastic, %.1f s" % (args.cpu_points, dt)}
+        if "other_configs" in line and "error" not in line["other_configs"]:
+            try:
+                cpu = cpu_baseline_other_configs()
+                for k, v in line["other_configs"].items():
+                    key = k if k in cpu else (k.rsplit("_1e", 1)[0] if k.rsplit("_1e", 1)[0] in cpu else None)
+                    if key:
+                        v["cpu_oracle_updates_per_s"] = cpu[key]
+                        v["gpu_over_cpu"] = round(v["updates_per_s"] / cpu[key], 1)
+                line["cpu_baseline"]["other_configs_sample"] = "%d points per config, %d threads" % (cpu["sample_points"], cpu["threads"])
+            except Exception as e:
+                line["cpu_baseline"]["other_configs_error"] = repr(e)
     print(json.dumps(line))
     return 0
 

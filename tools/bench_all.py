@@ -29,32 +29,12 @@ def timeit(fn, reps, warm=3):
     return ts[len(ts) // 2], ts[0]
 
 
-CPU = {"on": False, "n": 200000}
-
-
-def cpu_rate(fn):
-    """updates/s of the oracle (C++/OpenMP restatement of the reference algorithm, all host cores) on a bounded sample;
-    only the tools/ and bench.py baseline legs may execute oracle/ (it is never on the product path)"""
-    import time
-    fn()
-    t0 = time.perf_counter(); fn(); dt = time.perf_counter() - t0
-    reps = max(1, min(20, int(1.0 / max(dt, 1e-6))))
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        fn()
-    return CPU["n"] * reps / (time.perf_counter() - t0)
-
-
-def report(name, N, bpp, med, mn, extra=None, cpu=None):
+def report(name, N, bpp, med, mn, extra=None):
     gbs = bpp * N / (med * 1e-3) / 1e9
     d = {"kernel": name, "N": N, "ms_median": round(med, 4), "ms_min": round(mn, 4), "B_per_pt": bpp, "GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak(), 3),
          "updates_per_s": N / (med * 1e-3)}
     if extra:
         d.update(extra)
-    if CPU["on"] and cpu is not None:
-        import oracle as O
-        r = cpu_rate(cpu)
-        d.update({"cpu_oracle_updates_per_s": r, "cpu_threads": O.num_threads(), "cpu_sample_points": CPU["n"], "gpu_over_cpu": round(N / (med * 1e-3) / r, 1)})
     print(json.dumps(d), flush=True)
 
 
@@ -63,15 +43,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--cpu", action="store_true", help="also time the oracle (reference algorithm, all host cores) on a 2e5-point sample of the same inputs")
     a = ap.parse_args()
-    CPU["on"] = a.cpu
-    if a.cpu:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import numpy as np
-        import oracle as O
-        from materialmodels_jl_b200 import _abi as abi
-    n = CPU["n"]
     want = lambda k: (not a.only) or any(w in k for w in a.only.split(","))
     S = a.scale
     if want("elastic"):
@@ -81,10 +53,9 @@ def main():
             eps = mm.synth_uniform(N, nc, seed, lo, hi)
             sig = torch.empty_like(eps)
             med, mn = timeit(lambda: mm.material_response(m, eps, tangent=False), a.reps)
-            he = sy.host_uniform(n, nc, seed, lo, hi) if a.cpu else None
-            report("linear_elastic sigma-only soa", N, 96, med, mn, cpu=(lambda: O.linear_elastic(200e3, 0.3, he, want_tangent=False)) if a.cpu else None)
+            report("linear_elastic sigma-only soa", N, 96, med, mn)
             med, mn = timeit(lambda: mm.material_response(m, eps), a.reps)
-            report("linear_elastic +tangent soa", N, 384, med, mn, cpu=(lambda: O.linear_elastic(200e3, 0.3, he)) if a.cpu else None)
+            report("linear_elastic +tangent soa", N, 384, med, mn)
             del eps, sig
     if want("plastic"):
         N = int(1e8 * S)
@@ -102,13 +73,7 @@ def main():
                    "iters": torch.empty((N,), dtype=torch.uint8, device="cuda")}
             med, mn = timeit(lambda: mm.material_response(m, eB, stA, options={"defer_check": True}, out=out), a.reps)
             frac = out["flags"].float().mean().item()
-            cpu = None
-            if a.cpu and lname == "soa":
-                pp = abi.MMPlastic(*[sy.PLASTIC_PARAMS[k] for k in ("E", "nu", "sigma_y", "H", "r", "kappa_inf", "alpha_inf")])
-                hA = O.plastic(pp, sy.host_uniform(n, ncA, seedA, loA, hiA), np.zeros((14, n)))["state"]
-                hB = sy.host_uniform(n, ncB, seedB, loB, hiB)
-                cpu = lambda: O.plastic(pp, hB, hA)
-            report("plastic stepB " + lname, N, 608, med, mn, {"plastic_fraction": round(frac, 4)}, cpu=cpu)
+            report("plastic stepB " + lname, N, 608, med, mn, {"plastic_fraction": round(frac, 4)})
             if lname == "soa":
                 z = mm.initial_material_state(m, N)
                 e0 = mm.synth_uniform(N, 6, 1, -1e-4, 1e-4)
@@ -129,12 +94,7 @@ def main():
             for name, prm in (("NeoHook", sy.NEOHOOK_PARAMS), ("Yeoh", sy.YEOH_PARAMS), ("StVenant", sy.NEOHOOK_PARAMS)):
                 m = getattr(mm, name)(λ=prm["lambda_"], μ=prm["mu"], c2=prm["c2"], c3=prm["c3"])
                 med, mn = timeit(lambda: mm.material_response(mm.dSdC(), m, mm.DeformationGradient(F), layout=lname), a.reps)
-                cpu = None
-                if a.cpu and lname == "soa":
-                    hF = sy.host_uniform(n, nc, seed, lo, hi)
-                    hp = abi.MMHyper(**prm)
-                    cpu = (lambda mdl=m.MODEL, hp=hp: O.hyper(mdl, hp, hF, 1))
-                report("%s from F %s" % (name, lname), N, 408, med, mn, cpu=cpu)
+                report("%s from F %s" % (name, lname), N, 408, med, mn)
             del F
             torch.cuda.empty_cache()
     if want("traits"):
@@ -227,12 +187,7 @@ def main():
         for lname in ("soa", "aos"):
             D = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
             med, mn = timeit(lambda: mm.material_response(m, D, layout=lname), a.reps)
-            cpu = None
-            if a.cpu and lname == "soa":
-                hD = sy.host_uniform(n, nc, seed, lo, hi)
-                xp = O.xu_params(x["sigma_max"], x["tau_max"], mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]), mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), x["Delta_n_star"])
-                cpu = lambda: O.xu_needleman(xp, hD, 3)
-            report("xu_needleman 3D " + lname, N, 120, med, mn, cpu=cpu)
+            report("xu_needleman 3D " + lname, N, 120, med, mn)
             del D
     if want("wrapped"):
         N = int(1e8 * S)
@@ -264,17 +219,8 @@ def main():
             dB = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
             med, mn = timeit(lambda: mm.material_response(m, dB, stA, 1.0, options={"defer_check": True}), max(a.reps // 3, 2), warm=1)
             _, _, stB = mm.material_response(m, dB, stA, 1.0, options={"defer_check": True})
-            cpu = None
-            if a.cpu:
-                pl, di = O.slipsystems(0, sy.CRYSTAL_RODRIGUES)
-                c = sy.CRYSTAL_PARAMS
-                cp = O.crystal_params(c["E"], c["nu"], c["tau_y"], c["H_iso"], c["H_kin"], c["q"], c["alpha_inf"], c["t_star"], c["sigma_c"], c["m"], pl, di)
-                nA = sy.c4_strain_increment(0)
-                hA = O.crystal(cp, sy.host_uniform(n, nA[0], nA[3], nA[1], nA[2]), np.zeros((42, n)))["state"]
-                hB = sy.host_uniform(n, nc, seed, lo, hi)
-                cpu = lambda: O.crystal(cp, hB, hA)
             report("crystal stepB " + lname, N, 1056, med, mn, {"mean_iters": stB.iters.float().mean().item(), "frac_active": (stB.flags != 0).float().mean().item(),
-                                                                 "n_fail": int(stB.n_fail.item())}, cpu=cpu)
+                                                                 "n_fail": int(stB.n_fail.item())})
 
 
 if __name__ == "__main__":
