@@ -47,6 +47,9 @@ struct CellArgs {
 // top of the J2 solve: 255 registers and 15.2 ms for the hexahedron, against 168 and 10.7 ms this way); for NQ > 1 the Bᵀσ
 // contributions of the NQ lanes of a cell are summed through a padded shared-memory image: lane q adds up and stores components q, q+NQ, … (3·NN/NQ each) — one
 // STS + 3·NN/NQ·NQ LDS per thread instead of 3·NN·log2(NQ) 64-bit shuffles.
+#ifndef MM_CELLS_KE_UNROLL
+#define MM_CELLS_KE_UNROLL 1
+#endif
 #ifndef MM_CELLS_MINBLOCKS
 #define MM_CELLS_MINBLOCKS 3
 #endif
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_ke
     constexpr int NC = 3 * NN;
     extern __shared__ double sm[];
     double* sm_dN = sm;                                  // [NC][BS]
-    double* sm_f = sm + NC * BS;                         // [NC][BS + 1] (fe) / [3 NC][BS + 1] (one block row of ke), NQ > 1; padded: the NQ lanes of a cell read NQ different rows
+    double* sm_f = sm + NC * BS;                         // NQ > 1: [NC][BS + 1] fe image (padded: the NQ lanes of a cell read NQ different rows); the [BS][38] tangent image follows
     const int64_t P = a.ncell * NQ;
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     const unsigned mask = __ballot_sync(0xffffffffu, i < P);   // cells are whole and warp-local: the survivors sync among themselves below
@@ -127,43 +130,88 @@ __global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_ke
         }
     }
     if (WITH_KE) {
-        // ke[3a+i][3b+j] = Σ_q Σ_nl ∇N_a[n] D_(in)(jl) ∇N_b[l] dΩ   (δε_i ⊡ D ⊡ Δε_j with the minor symmetries of D), one block row
-        // (fixed a: 3 x NC values) at a time: T_a[i][J] = Σ_n ∇N_a[n] D[(in), J], then block[i][j] = Σ_l T_a[i][(jl)] ∇N_b[l].
+        // ke[3a+i][3b+j] = Σ_q Σ_nl ∇N_a[n] D_(in)(jl) ∇N_b[l] dΩ   (δε_i ⊡ D ⊡ Δε_j with the minor symmetries of D):
+        // T_a[i][J] = Σ_n ∇N_a[n] D[(in), J] (54 FMA), then block[i][j] = Σ_l T_a[i][(jl)] ∇N_b[l] (27 FMA per node pair).
         // Stored component-major over cells: ke[((3a+i)*NC + 3b+j)*ncell + cell].
+        if (NQ == 1) {                                     // thread = cell: block rows straight to global memory
 #pragma unroll 1
-        for (int na = 0; na < NN; ++na) {
-            double da[3], T[3][6];
+            for (int na = 0; na < NN; ++na) {
+                double da[3], T[3][6];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) da[k] = sm_dN[(3 * na + k) * BS + t] * dO;
-#pragma unroll
-            for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-                for (int J = 0; J < 6; ++J)
-                    T[ii][J] = da[0] * acc.D[WITH_KE ? sym_slot(ii, 0) + 6 * J : 0] + da[1] * acc.D[WITH_KE ? sym_slot(ii, 1) + 6 * J : 0] +
-                               da[2] * acc.D[WITH_KE ? sym_slot(ii, 2) + 6 * J : 0];
-            if (NQ > 1) __syncwarp(mask);                  // the previous block row has been read
-#pragma unroll 1
-            for (int nb = 0; nb < NN; ++nb) {
-                double db[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) db[k] = sm_dN[(3 * nb + k) * BS + t];
+                for (int k = 0; k < 3; ++k) da[k] = sm_dN[(3 * na + k) * BS + t] * dO;
 #pragma unroll
                 for (int ii = 0; ii < 3; ++ii)
 #pragma unroll
-                    for (int jj = 0; jj < 3; ++jj) {
-                        const double v = T[ii][sym_slot(jj, 0)] * db[0] + T[ii][sym_slot(jj, 1)] * db[1] + T[ii][sym_slot(jj, 2)] * db[2];
-                        if (NQ == 1) __stcs(a.ke + ((int64_t)(3 * na + ii) * NC + (3 * nb + jj)) * a.ncell + cell, v);
-                        else sm_f[(ii * NC + 3 * nb + jj) * (BS + 1) + t] = v;
-                    }
-            }
-            if (NQ > 1) {
-                __syncwarp(mask);
+                    for (int J = 0; J < 6; ++J)
+                        T[ii][J] = da[0] * acc.D[WITH_KE ? sym_slot(ii, 0) + 6 * J : 0] + da[1] * acc.D[WITH_KE ? sym_slot(ii, 1) + 6 * J : 0] +
+                                   da[2] * acc.D[WITH_KE ? sym_slot(ii, 2) + 6 * J : 0];
 #pragma unroll 1
-                for (int c = q; c < 3 * NC; c += NQ) {     // c = ii*NC + (3 nb + jj)
-                    double v = 0.0;
+                for (int nb = 0; nb < NN; ++nb) {
+                    double db[3];
 #pragma unroll
-                    for (int j = 0; j < NQ; ++j) v += sm_f[c * (BS + 1) + t0 + j];
-                    __stcs(a.ke + ((int64_t)(3 * na) * NC + c) * a.ncell + cell, v);
+                    for (int k = 0; k < 3; ++k) db[k] = sm_dN[(3 * nb + k) * BS + t];
+#pragma unroll
+                    for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                        for (int jj = 0; jj < 3; ++jj)
+                            __stcs(a.ke + ((int64_t)(3 * na + ii) * NC + (3 * nb + jj)) * a.ncell + cell,
+                                   T[ii][sym_slot(jj, 0)] * db[0] + T[ii][sym_slot(jj, 1)] * db[1] + T[ii][sym_slot(jj, 2)] * db[2]);
+                }
+            }
+        } else {
+            // NQ lanes per cell: lane q owns the block rows of nodes a = q, q+NQ, … and accumulates them over the cell's NQ points in
+            // registers — no cross-lane reduction.  Every point parks its tangent and dΩ in shared memory ([thread][38], read back as
+            // broadcast 128-bit loads by the NQ lanes of the cell); ∇N is already there.  Columns in chunks of <= 8 nodes (72 accumulators).
+            constexpr int PD = 38, CH = (NN < 8) ? NN : 8, MM_CELLS_KE_UNROLL_V = MM_CELLS_KE_UNROLL;
+            double* sm_D = sm_f + ((NC * (BS + 1) + 1) & ~1);   // its own region (the fe image is column-per-thread, this one row-per-thread:
+                                                                // sharing the buffer would need a block-wide barrier); rounded up to 16 bytes
+#pragma unroll
+            for (int c = 0; c < 36; c += 2) *reinterpret_cast<double2*>(sm_D + t * PD + c) = make_double2(acc.D[WITH_KE ? c : 0], acc.D[WITH_KE ? c + 1 : 0]);
+            sm_D[t * PD + 36] = dO;
+            __syncwarp(mask);
+#pragma unroll 1
+            for (int na = q; na < NN; na += NQ) {
+#pragma unroll
+                for (int b0 = 0; b0 < NN; b0 += CH) {
+                    double K[3][3 * CH];
+#pragma unroll
+                    for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                        for (int c = 0; c < 3 * CH; ++c) K[ii][c] = 0.0;
+#pragma unroll MM_CELLS_KE_UNROLL_V
+                    for (int pq = 0; pq < NQ; ++pq) {
+                        const double* Dp = sm_D + (t0 + pq) * PD;
+                        const double w = Dp[36];
+                        double da[3], T[3][6];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) da[k] = sm_dN[(3 * na + k) * BS + t0 + pq] * w;
+#pragma unroll
+                        for (int J = 0; J < 6; ++J) {
+                            const double2 d01 = *reinterpret_cast<const double2*>(Dp + 6 * J), d23 = *reinterpret_cast<const double2*>(Dp + 6 * J + 2),
+                                          d45 = *reinterpret_cast<const double2*>(Dp + 6 * J + 4);
+                            const double Dc[6] = {d01.x, d01.y, d23.x, d23.y, d45.x, d45.y};          // D[I + 6J], I = 0..5
+#pragma unroll
+                            for (int ii = 0; ii < 3; ++ii) T[ii][J] = da[0] * Dc[sym_slot(ii, 0)] + da[1] * Dc[sym_slot(ii, 1)] + da[2] * Dc[sym_slot(ii, 2)];
+                        }
+#pragma unroll
+                        for (int nb = 0; nb < CH; ++nb) {
+                            if (b0 + nb < NN) {
+                                double db[3];
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) db[k] = sm_dN[(3 * (b0 + nb) + k) * BS + t0 + pq];
+#pragma unroll
+                                for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                                    for (int jj = 0; jj < 3; ++jj)
+                                        K[ii][3 * nb + jj] += T[ii][sym_slot(jj, 0)] * db[0] + T[ii][sym_slot(jj, 1)] * db[1] + T[ii][sym_slot(jj, 2)] * db[2];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                        for (int c = 0; c < 3 * CH; ++c)
+                            if (3 * b0 + c < NC) __stcs(a.ke + ((int64_t)(3 * na + ii) * NC + (3 * b0 + c)) * a.ncell + cell, K[ii][c]);
                 }
             }
         }
@@ -173,7 +221,8 @@ __global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_ke
 template <int MODEL, int NN, int NQ, bool WITH_KE>
 int launch_cells_k(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
     constexpr int BS = 128;
-    constexpr size_t smem = (size_t)3 * NN * (BS + ((NQ > 1) ? (WITH_KE ? 3 : 1) * (BS + 1) : 0)) * sizeof(double);
+    constexpr size_t fe_img = (NQ > 1) ? (size_t)3 * NN * (BS + 1) : 0, d_img = (NQ > 1 && WITH_KE) ? (size_t)38 * BS + 2 : 0;
+    constexpr size_t smem = ((size_t)3 * NN * BS + fe_img + d_img) * sizeof(double);
     const int64_t P = a.ncell * NQ;
     if (P == 0) return MM_OK;
     const int64_t blocks = (P + BS - 1) / BS;
