@@ -45,6 +45,25 @@ elif which == "xu":
     D = mm.synth_uniform(N, nc, seed, lo, hi)
     for _ in range(reps):
         mm.material_response(m, D)
+elif which in ("cells_tet4", "cells_hex8"):
+    nn, nq = (4, 1) if which.endswith("tet4") else (8, 8)
+    P = N // nq * nq
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    amp = 7e-4 if nq == 1 else 3.6e-4
+    dN = mm.synth_uniform(P, 3 * nn, 71, -1.0, 1.0)
+    dO = mm.synth_uniform(P, 1, 72, 0.5, 1.5).reshape(P)
+    _, stA, _ = mm.cell_internal_forces(m, dN, dO, mm.synth_uniform(P // nq, 3 * nn, 73, -amp, amp), mm.initial_material_state(m, P), options={"defer_check": True})
+    ue = mm.synth_uniform(P // nq, 3 * nn, 74, -amp, amp)
+    for _ in range(reps):
+        mm.cell_internal_forces(m, dN, dO, ue, stA, options={"defer_check": True})
+elif which == "transviso":
+    m = mm.TransverselyIsotropic(E_L=100e3, E_T=10e3, G_LT=5e3, ν_LT=0.4, ν_TT=0.3)
+    eps = mm.synth_uniform(N, 6, 99, -2e-3, 2e-3)
+    a3 = mm.synth_uniform(N, 3, 100, 0.1, 1.0)
+    a3 /= a3.norm(dim=0, keepdim=True)
+    st = mm.TransverselyIsotropicState(a3.contiguous(), "soa")
+    for _ in range(reps):
+        mm.material_response(m, eps, st)
 elif which == "elastic":
     nc, lo, hi, seed = sy.c1_strain()
     e = mm.synth_uniform(N, nc, seed, lo, hi)
