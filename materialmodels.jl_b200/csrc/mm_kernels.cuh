@@ -92,13 +92,15 @@ template <class Op> __host__ __device__ constexpr int dense_in_off(int a) { retu
 template <class Op> __host__ __device__ constexpr int dense_out_off(int a) { return a == 0 ? dense_in_off<Op>(Op::NIN) : dense_out_off<Op>(a - 1) + Op::out_nc(a - 1); }
 template <class Op> __host__ __device__ constexpr int dense_doubles_per_point() { return dense_out_off<Op>(Op::NOUT) + Op::SCRATCH; }
 
+template <class Op> __host__ __device__ constexpr int dense_out_rel(int a) { return dense_out_off<Op>(a) - dense_in_off<Op>(Op::NIN); }   // offset inside the output image
 template <class Op, int BS> struct DenseAcc {
-    double* sm;
+    const double* sm_in;      // input image  [A][pt][c]
+    double* sm_out;           // output image [A][pt][c]
     const Ptrs<Op::NIN, Op::NOUT>& p;
     int t;
-    __device__ __forceinline__ DenseAcc(double* sm_, const Ptrs<Op::NIN, Op::NOUT>& p_, int t_) : sm(sm_), p(p_), t(t_) {}
-    template <int A> __device__ __forceinline__ double in(int c) const { return sm[dense_in_off<Op>(A) * BS + t * Op::in_nc(A) + c]; }
-    template <int A> __device__ __forceinline__ void out(int c, double v) const { sm[dense_out_off<Op>(A) * BS + t * Op::out_nc(A) + c] = v; }
+    __device__ __forceinline__ DenseAcc(const double* in_, double* out_, const Ptrs<Op::NIN, Op::NOUT>& p_, int t_) : sm_in(in_), sm_out(out_), p(p_), t(t_) {}
+    template <int A> __device__ __forceinline__ double in(int c) const { return sm_in[dense_in_off<Op>(A) * BS + t * Op::in_nc(A) + c]; }
+    template <int A> __device__ __forceinline__ void out(int c, double v) const { sm_out[dense_out_rel<Op>(A) * BS + t * Op::out_nc(A) + c] = v; }
     template <int A> __device__ __forceinline__ bool has_out() const { return p.out[A] != nullptr; }
 };
 template <class Op, int BS, int A> struct BulkIO {
@@ -107,79 +109,95 @@ template <class Op, int BS, int A> struct BulkIO {
         if constexpr (A + 1 < Op::NIN) b += BulkIO<Op, BS, A + 1>::in_bytes();
         return b;
     }
-    static __device__ __forceinline__ void load_all(double* sm, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, uint64_t* bar) {
-        bulk_g2s(sm + dense_in_off<Op>(A) * BS, p.in[A] + i0 * Op::in_nc(A), (uint32_t)(BS * Op::in_nc(A) * sizeof(double)), bar);
-        if constexpr (A + 1 < Op::NIN) BulkIO<Op, BS, A + 1>::load_all(sm, p, i0, bar);
+    static __device__ __forceinline__ void load_all(double* sm_in, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, uint64_t* bar) {
+        bulk_g2s(sm_in + dense_in_off<Op>(A) * BS, p.in[A] + i0 * Op::in_nc(A), (uint32_t)(BS * Op::in_nc(A) * sizeof(double)), bar);
+        if constexpr (A + 1 < Op::NIN) BulkIO<Op, BS, A + 1>::load_all(sm_in, p, i0, bar);
     }
-    static __device__ __forceinline__ void store_all(double* sm, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0) {
-        if (p.out[A] != nullptr) bulk_s2g(p.out[A] + i0 * Op::out_nc(A), sm + dense_out_off<Op>(A) * BS, (uint32_t)(BS * Op::out_nc(A) * sizeof(double)));
-        if constexpr (A + 1 < Op::NOUT) BulkIO<Op, BS, A + 1>::store_all(sm, p, i0);
+    static __device__ __forceinline__ void store_all(double* sm_out, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0) {
+        if (p.out[A] != nullptr) bulk_s2g(p.out[A] + i0 * Op::out_nc(A), sm_out + dense_out_rel<Op>(A) * BS, (uint32_t)(BS * Op::out_nc(A) * sizeof(double)));
+        if constexpr (A + 1 < Op::NOUT) BulkIO<Op, BS, A + 1>::store_all(sm_out, p, i0);
     }
 };
 
 template <class Op, int BS, int A> struct DenseTailIO {     // element-wise copies for the one ragged tile (npts < BS)
-    static __device__ __forceinline__ void load_all(double* sm, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, int npts) {
+    static __device__ __forceinline__ void load_all(double* sm_in, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, int npts) {
         const double* g = p.in[A] + i0 * Op::in_nc(A);
-        for (int e = threadIdx.x; e < npts * Op::in_nc(A); e += BS) sm[dense_in_off<Op>(A) * BS + e] = __ldcs(g + e);
-        if constexpr (A + 1 < Op::NIN) DenseTailIO<Op, BS, A + 1>::load_all(sm, p, i0, npts);
+        for (int e = threadIdx.x; e < npts * Op::in_nc(A); e += BS) sm_in[dense_in_off<Op>(A) * BS + e] = __ldcs(g + e);
+        if constexpr (A + 1 < Op::NIN) DenseTailIO<Op, BS, A + 1>::load_all(sm_in, p, i0, npts);
     }
-    static __device__ __forceinline__ void store_all(const double* sm, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, int npts) {
+    static __device__ __forceinline__ void store_all(const double* sm_out, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, int npts) {
         if (p.out[A] != nullptr) {
             double* g = p.out[A] + i0 * Op::out_nc(A);
-            for (int e = threadIdx.x; e < npts * Op::out_nc(A); e += BS) __stcs(g + e, sm[dense_out_off<Op>(A) * BS + e]);
+            for (int e = threadIdx.x; e < npts * Op::out_nc(A); e += BS) __stcs(g + e, sm_out[dense_out_rel<Op>(A) * BS + e]);
         }
-        if constexpr (A + 1 < Op::NOUT) DenseTailIO<Op, BS, A + 1>::store_all(sm, p, i0, npts);
+        if constexpr (A + 1 < Op::NOUT) DenseTailIO<Op, BS, A + 1>::store_all(sm_out, p, i0, npts);
     }
 };
 
 // `bulk` = 0 sends every tile through the element-wise copies (arrays whose base is not 16-byte aligned); the
 // compute code is the same instantiation either way, so results do not depend on how a batch is tiled or chunked.
+// NBUF input images: with 2, the loads of the NEXT tile are issued before this tile is computed (their DRAM latency hides behind
+// the math instead of being exposed after every tile); with 1 they are issued together with this tile's stores.
+#ifndef MM_AOS_NBUF
+#define MM_AOS_NBUF 2
+#endif
+template <class Op, int BS> __host__ __device__ constexpr size_t aos_smem_bytes() {
+    return 16 + (size_t)(MM_AOS_NBUF * dense_in_off<Op>(Op::NIN) + dense_out_rel<Op>(Op::NOUT) + Op::SCRATCH) * BS * sizeof(double);
+}
 template <class Op, int BS>
 __global__ void __launch_bounds__(BS, (MinBlocks<Op>::value * MinBlocks<Op>::block + BS - 1) / BS)
 aos_bulk_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N, const int64_t ntiles, const int bulk) {
+    constexpr int NB = MM_AOS_NBUF, IN_D = dense_in_off<Op>(Op::NIN) * BS, OUT_D = dense_out_rel<Op>(Op::NOUT) * BS;
     extern __shared__ __align__(128) unsigned char sm_raw[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm_raw);
-    double* sm = reinterpret_cast<double*>(sm_raw + 16);
-    if (threadIdx.x == 0) mbar_init(bar, 1);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm_raw);               // NB barriers (<= 2) in the first 16 bytes
+    double* sm_in = reinterpret_cast<double*>(sm_raw + 16);            // NB input images
+    double* sm_out = sm_in + NB * IN_D;
+    double* sm_scr = sm_out + OUT_D;
+    if (threadIdx.x == 0) { for (int b = 0; b < NB; ++b) mbar_init(bar + b, 1); }
     __syncthreads();
     int64_t tile = blockIdx.x;
     if (tile >= ntiles) return;
     const int64_t nfull = bulk ? N / BS : 0;          // tiles [0, nfull) are full and go through the copy engine
     if (threadIdx.x == 0 && tile < nfull) {
         mbar_expect_tx(bar, BulkIO<Op, BS, 0>::in_bytes());
-        BulkIO<Op, BS, 0>::load_all(sm, p, tile * BS, bar);
+        BulkIO<Op, BS, 0>::load_all(sm_in, p, tile * BS, bar);
     }
-    uint32_t parity = 0;
-    for (; tile < ntiles; tile += gridDim.x) {
+    uint32_t k = 0;                                    // tiles processed by this CTA
+    for (; tile < ntiles; tile += gridDim.x, ++k) {
         const bool full = tile < nfull;
         const int npts = (int)((N - tile * BS < BS) ? (N - tile * BS) : BS);
+        const int buf = (NB == 2) ? (int)(k & 1u) : 0;
+        double* in_img = sm_in + buf * IN_D;
+        const int64_t nxt = tile + gridDim.x;
+        if (NB == 2 && threadIdx.x == 0 && nxt < nfull) {             // image buf^1 was consumed one iteration ago (barrier at its end)
+            mbar_expect_tx(bar + (buf ^ 1), BulkIO<Op, BS, 0>::in_bytes());
+            BulkIO<Op, BS, 0>::load_all(sm_in + (buf ^ 1) * IN_D, p, nxt * BS, bar + (buf ^ 1));
+        }
         if (full) {
-            mbar_wait(bar, parity);                   // this tile's inputs have landed
-            parity ^= 1u;
+            mbar_wait(bar + buf, (NB == 2) ? ((k >> 1) & 1u) : (k & 1u));   // this tile's inputs have landed
         } else {
-            DenseTailIO<Op, BS, 0>::load_all(sm, p, tile * BS, npts);
+            DenseTailIO<Op, BS, 0>::load_all(in_img, p, tile * BS, npts);
             __syncthreads();
         }
         if ((int)threadIdx.x < npts) {
-            DenseAcc<Op, BS> acc(sm, p, (int)threadIdx.x);
-            Scratch scr{sm + dense_out_off<Op>(Op::NOUT) * BS + threadIdx.x, BS};
+            DenseAcc<Op, BS> acc(in_img, sm_out, p, (int)threadIdx.x);
+            Scratch scr{sm_scr + threadIdx.x, BS};
             op.point(acc, tile * BS + threadIdx.x, scr);
         }
         fence_async_smem();                           // generic-proxy writes -> visible to the copy engine
         __syncthreads();                              // all outputs written, all inputs consumed
         if (full) {
             if (threadIdx.x == 0) {
-                BulkIO<Op, BS, 0>::store_all(sm, p, tile * BS);
+                BulkIO<Op, BS, 0>::store_all(sm_out, p, tile * BS);
                 bulk_commit();
-                const int64_t nxt = tile + gridDim.x;
-                if (nxt < nfull) {                    // next tile's loads overlap this tile's store drain
+                if (NB == 1 && nxt < nfull) {         // single image: next tile's loads overlap this tile's store drain
                     mbar_expect_tx(bar, BulkIO<Op, BS, 0>::in_bytes());
-                    BulkIO<Op, BS, 0>::load_all(sm, p, nxt * BS, bar);
+                    BulkIO<Op, BS, 0>::load_all(sm_in, p, nxt * BS, bar);
                 }
                 bulk_wait_read0();                    // output image may be overwritten again
             }
         } else {
-            DenseTailIO<Op, BS, 0>::store_all(sm, p, tile * BS, npts);
+            DenseTailIO<Op, BS, 0>::store_all(sm_out, p, tile * BS, npts);
         }
         __syncthreads();
     }
@@ -212,7 +230,7 @@ int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int
         for (int a = 0; a < Op::NOUT; ++a) aligned = aligned && ((reinterpret_cast<uintptr_t>(p.out[a]) & 15u) == 0);
         static int use_bulk = -1;
         if (use_bulk < 0) { const char* e = getenv("MM_AOS_BULK"); use_bulk = (e && e[0] == '0') ? 0 : 1; }
-        constexpr size_t smem_b = 16 + (size_t)dense_doubles_per_point<Op>() * BS_AOS * sizeof(double);
+        constexpr size_t smem_b = aos_smem_bytes<Op, BS_AOS>();
         static bool configured_b = false;
         if (!configured_b) {
             cudaError_t e = cudaFuncSetAttribute(aos_bulk_kernel<Op, BS_AOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
