@@ -100,6 +100,34 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must not inherit that)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter) is sent
+    to stderr, and the line goes to the saved descriptor"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _REAL_STDOUT
+
+
+def emit(line):
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def cpu_baseline_run(points, steps=1, warmup=0):
     """The oracle's mmo_plastic (dense 14x14 ForwardDiff-style Jacobian + LU Newton, as the reference does)
     on all host cores; step A untimed to build the state, step B timed."""
@@ -108,6 +136,7 @@ def cpu_baseline_run(points, steps=1, warmup=0):
     import oracle as O
     from materialmodels_jl_b200 import _abi, synth as sy
 
+    O.set_threads(host_threads())
     p = _abi.MMPlastic(*[sy.PLASTIC_PARAMS[k] for k in ("E", "nu", "sigma_y", "H", "r", "kappa_inf", "alpha_inf")])
     ncA, loA, hiA, seedA = sy.c2_strain(0)
     ncB, loB, hiB, seedB = sy.c2_strain(1)
@@ -132,6 +161,8 @@ def cpu_baseline_other_configs(n=200000):
 
     import oracle as O
     from materialmodels_jl_b200 import _abi, synth as sy
+
+    O.set_threads(host_threads())
 
     def rate(fn):
         fn()
@@ -189,7 +220,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -208,6 +239,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the informational timings of the other BASELINE configs")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -346,7 +378,7 @@ def main():
                 line["cpu_baseline"]["other_configs_sample"] = "%d points per config, %d threads" % (cpu["sample_points"], cpu["threads"])
             except Exception as e:
                 line["cpu_baseline"]["other_configs_error"] = repr(e)
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
