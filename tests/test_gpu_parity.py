@@ -74,6 +74,26 @@ def test_empty_batches(mm, torch):
     st = mm.initial_material_state(p, 0)
     s, t, st2 = mm.material_response(p, torch.zeros((6, 0), dtype=torch.float64, device="cuda"), st)
     assert s.shape == (6, 0) and st2.data.shape == (14, 0)
+    z = lambda nc: torch.zeros((nc, 0), dtype=torch.float64, device="cuda")
+    # every other entry point accepts an empty batch too (N = 0 is a no-op, never a launch with a zero grid)
+    s, t, _ = mm.material_response(mm.dPdF(), mm.NeoHook(λ=1.0, μ=1.0), mm.DeformationGradient(z(9)))
+    assert s.shape == (9, 0) and t.shape == (81, 0)
+    assert mm.elastic_strain_energy_density(mm.Yeoh(λ=1.0, μ=1.0, c2=-1.0, c3=1.0), mm.GreenLagrange(z(6))).shape == (0,)
+    x = sy.XU_PARAMS
+    xm = mm.XuNeedleman(σₘₐₓ=x["sigma_max"], τₘₐₓ=x["tau_max"], Φₙ=mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]),
+                        Φₜ=mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), Δₙˢ=x["Delta_n_star"])
+    assert mm.material_response(xm, z(3))[1].shape == (9, 0)
+    s, t, _ = mm.material_response(mm.PlaneStress(), p, z(3), mm.initial_material_state(p, 0))
+    assert s.shape == (3, 0) and t.shape == (9, 0)
+    ti = mm.TransverselyIsotropic(E_L=100e3, E_T=10e3, G_LT=5e3, ν_LT=0.4, ν_TT=0.3)
+    s, t, _ = mm.material_response(ti, z(6), mm.TransverselyIsotropicState(z(3), "soa"))
+    assert s.shape == (6, 0)
+    cm = make_crystal(mm)
+    s, t, cs = mm.material_response(cm, z(6), mm.initial_material_state(cm, 0), 1.0)
+    assert s.shape == (6, 0) and cs.data.shape == (42, 0)
+    for lay in ("soa", "aos"):
+        e = torch.zeros((6, 0) if lay == "soa" else (0, 6), dtype=torch.float64, device="cuda")
+        assert mm.material_response(m, e, layout=lay)[0].numel() == 0
 
 
 def test_linear_elastic_golden(mm, torch, golden):

@@ -67,6 +67,9 @@ def main():
     print(json.dumps(info), flush=True)
     if rank == 0:
         os.system("nvidia-smi topo -m 2>&1 | head -20; lscpu | grep -i -E 'numa|socket|model name' ; cat /sys/fs/cgroup/cpuset.cpus.effective 2>/dev/null")
+    if os.environ.get("PROBE_CHUNK"):
+        import materialmodels_jl_b200._lib as L
+        L.load().mmh_set_chunk_points(int(float(os.environ["PROBE_CHUNK"])))
     m = mm.Plastic(**sy.PLASTIC_PARAMS)
     nc, lo, hi, seed = sy.c2_strain(0)
     eps = sy.host_uniform(Ne, nc, seed, lo, hi)
@@ -96,7 +99,7 @@ def main():
         dt = time.perf_counter() - t0
         dtm = sharding.allreduce_max(dt, device=dev)
         if rank == 0:
-            print(json.dumps({"policy": policy, "note": note, "world": world, "updates_per_s": world * Ne * 3 / dtm, "GBps_total": world * Ne * 3 * 610 / dtm / 1e9}), flush=True)
+            print(json.dumps({"policy": policy, "note": note, "chunk": os.environ.get("PROBE_CHUNK", "default"), "world": world, "updates_per_s": world * Ne * 3 / dtm, "GBps_total": world * Ne * 3 * 610 / dtm / 1e9}), flush=True)
         for v in [h_eps, h_st] + list(h_out.values()):
             v.free()
         set_mempolicy(MPOL_DEFAULT, [])
