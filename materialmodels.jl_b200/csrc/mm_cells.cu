@@ -227,12 +227,8 @@ int launch_cells_k(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cu
     if (P == 0) return MM_OK;
     const int64_t blocks = (P + BS - 1) / BS;
     if (blocks > 2147483647LL) return set_error(MM_ERR_ARG, "mm_cells: too many points for one launch");
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(cells_kernel<MODEL, NN, NQ, BS, WITH_KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_cells: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    if (int rc = ensure_smem(optin, cells_kernel<MODEL, NN, NQ, BS, WITH_KE>, smem, "mm_cells")) return rc;
     cells_kernel<MODEL, NN, NQ, BS, WITH_KE><<<(unsigned)blocks, BS, smem, st>>>(ke, kp, a);
     return check_launch("mm_cells");
 }

@@ -171,13 +171,9 @@ template <bool HASQ, bool INTPOW, int LAYOUT>
 int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
     constexpr int BS = MM_CRYSTAL_BS, FBS = MM_CRYSTAL_FINISH_BS;
     constexpr size_t smem = (size_t)MM_CRYSTAL_SCRATCH * BS * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-        if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_crystal: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
-    }
+    static SmemOptIn optin_newton, optin_finish;
+    if (int rc = ensure_smem(optin_newton, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS>, smem, "mm_crystal")) return rc;
+    if (int rc = ensure_smem(optin_finish, crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS>, fsmem, "mm_crystal")) return rc;
     // chunk of points per warp: large enough to refill many times, small enough for >= ~8 waves of warps on the chip
     const int64_t resident_warps = (int64_t)sm_count() * MM_CRYSTAL_MINBLOCKS * (BS / 32);
     int64_t chunk = N / (resident_warps * 8);

@@ -208,6 +208,20 @@ int set_error(int code, const char* fmt, ...);   // mm_api.cu
 int check_launch(const char* what);              // mm_api.cu
 int sm_count();                                  // mm_api.cu
 
+// opt-in to > 48 KB of dynamic shared memory: a per-function, PER-DEVICE attribute, so it is remembered per device
+// (`done` is one static table per kernel instantiation) — a process that drives several GPUs stays correct
+struct SmemOptIn { bool done[64] = {}; };
+template <class K> int ensure_smem(SmemOptIn& st, K kernel, size_t bytes, const char* what) {
+    if (bytes <= 48 * 1024) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;
+    if (st.done[dev] && dev != 63) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return set_error(-2, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    st.done[dev] = true;
+    return 0;
+}
+
 template <class Op, int BS_SOA, int BS_AOS = BS_SOA>
 int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int layout, cudaStream_t stream, const char* what) {
     if (N == 0) return 0;
@@ -215,12 +229,8 @@ int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int
         const int64_t blocks = (N + BS_SOA - 1) / BS_SOA;
         if (blocks > 2147483647LL) return set_error(-1, "%s: N too large for one launch", what);
         constexpr size_t scratch = (size_t)Op::SCRATCH * BS_SOA * sizeof(double);
-        static bool soa_configured = false;
-        if (!soa_configured && scratch > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(soa_kernel<Op, BS_SOA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scratch);
-            if (e != cudaSuccess) return set_error(-2, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-            soa_configured = true;
-        }
+        static SmemOptIn soa_optin;
+        if (int rc = ensure_smem(soa_optin, soa_kernel<Op, BS_SOA>, scratch, what)) return rc;
         soa_kernel<Op, BS_SOA><<<(unsigned)blocks, BS_SOA, scratch, stream>>>(op, p, N);
     } else if (layout == 1) {
         // one kernel for every AoS batch: full tiles through the copy engine (TMA bulk copies) when all array bases are
@@ -231,12 +241,8 @@ int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int
         static int use_bulk = -1;
         if (use_bulk < 0) { const char* e = getenv("MM_AOS_BULK"); use_bulk = (e && e[0] == '0') ? 0 : 1; }
         constexpr size_t smem_b = aos_smem_bytes<Op, BS_AOS>();
-        static bool configured_b = false;
-        if (!configured_b) {
-            cudaError_t e = cudaFuncSetAttribute(aos_bulk_kernel<Op, BS_AOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-            if (e != cudaSuccess) return set_error(-2, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-            configured_b = true;
-        }
+        static SmemOptIn aos_optin;
+        if (int rc = ensure_smem(aos_optin, aos_bulk_kernel<Op, BS_AOS>, smem_b, what)) return rc;
         const int64_t ntiles = (N + BS_AOS - 1) / BS_AOS;
         int64_t blocks = (int64_t)sm_count() * 16;          // grid-stride over tiles; 16 CTAs/SM covers any residency
         if (blocks > ntiles) blocks = ntiles;

@@ -208,7 +208,7 @@ def main():
         N = int(1e7 * S)
         ss = mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES)
         m = mm.CrystalViscoPlastic(slipsystems=ss, **sy.CRYSTAL_PARAMS)
-        for lname in ("soa",):
+        for lname in ("soa", "aos"):
             nc, lo, hi, seed = sy.c4_strain_increment(0)
             dA = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
             z = mm.initial_material_state(m, N, layout=lname)
