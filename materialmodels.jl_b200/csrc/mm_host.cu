@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "../../include/mmb200.h"
 
 namespace mm {
@@ -29,9 +30,15 @@ struct Workspace {
     cudaStream_t streams[NSLOT] = {nullptr, nullptr, nullptr};
     int32_t* d_fail = nullptr;
     bool init = false;
-} g_ws;
+};
+Workspace g_ws_dev[64];             // one workspace (streams, staging buffer, counter) per device the process has used
+int g_cur = 0;
+#define g_ws g_ws_dev[g_cur]
 
 int ensure(size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_error(MM_ERR_NOGPU, "mmh: no CUDA device");
+    g_cur = (dev >= 0 && dev < 64) ? dev : 0;
     if (!g_ws.init) {
         for (int s = 0; s < NSLOT; ++s)
             if (cudaStreamCreateWithFlags(&g_ws.streams[s], cudaStreamNonBlocking) != cudaSuccess) return set_error(MM_ERR_CUDA, "mmh: cudaStreamCreate failed");
@@ -71,6 +78,8 @@ int copy_chunk(const Arr& a, int slot, int64_t N, int64_t i0, int64_t n, int lay
 template <class Launch>
 int pipeline(Arr* arrs, int narr, int64_t N, int layout, int32_t* n_fail, Launch launch) {
     if (N == 0) return MM_OK;
+    static std::mutex mu;                               // the staging workspace is shared: host threads take turns
+    std::lock_guard<std::mutex> lock(mu);
     const int64_t chunk = (N < g_chunk) ? N : g_chunk;
     size_t per_slot = 0;
     for (int a = 0; a < narr; ++a) if (arrs[a].h_in || arrs[a].h_out) per_slot += align256((size_t)chunk * arrs[a].nc * arrs[a].elem);
