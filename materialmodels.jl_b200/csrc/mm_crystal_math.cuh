@@ -156,6 +156,7 @@ template <class Acc> MM_HD unsigned crystal_point(const CrystalK& k, Acc& acc, i
             const double Phi = fabs(red) - k.tau_y - kap[i];                            // :110
             double Ri = -k.t_star * x[i];
             p[i] = 0.0;
+            if (!(Phi <= 0.0) && !(Phi > 0.0)) Ri = Phi;                                // NaN Φ: ⟨Φ⟩ = (Φ+|Φ|)/2 is NaN in the reference, so is R
             if (Phi > 0.0) {                                                            // ⟨Φ⟩ = (Φ+|Φ|)/2
                 const double xx = Phi / k.sigma_c;
                 const double pw1 = pow(xx, k.m - 1.0);
@@ -176,6 +177,7 @@ template <class Acc> MM_HD unsigned crystal_point(const CrystalK& k, Acc& acc, i
         }
         iters = it - 1;
         if (it > k.max_iter) break;                                                      // nonlinear_solver.jl:61 (returns nothing)
+        if (!(nrm2 == nrm2)) break;                                                      // NaN residual can never pass :56 — the reference runs out of iterations
         if (sqrt(nrm2) < k.tol) { converged = true; break; }                             // nonlinear_solver.jl:56
         if (!lu12_factor(J, piv)) break;
         lu12_solve(J, piv, r);
@@ -410,7 +412,7 @@ MM_HD void crystal_evaluate(const CrystalK& k, Scr& scr, CrystalLane& L, double*
         const bool act = Phi > 0.0;                                                     // ⟨Φ⟩ = (Φ+|Φ|)/2
         double Ri, p, invD;
         if (INTPOW) {
-            const double xx = act ? Phi * k.isc : 0.0;
+            const double xx = act ? Phi * k.isc : Phi * 0.0;                            // ∓0 when inactive; a NaN Φ stays NaN (⟨Φ⟩ = (Φ+|Φ|)/2 in the reference)
             const double pw1 = powi6_(xx, npow);
             Ri = k.dt * (pw1 * xx) - k.t_star * xi;                                     // :111  (inactive: 0 − t* μ)
             p = k.dtm_sc * pw1;
@@ -424,6 +426,7 @@ MM_HD void crystal_evaluate(const CrystalK& k, Scr& scr, CrystalLane& L, double*
             invD = act ? -rcp_nc(dD) : k.mits;                                          // inactive: D_ii = −t*
         } else {
             Ri = -k.t_star * xi; p = 0.0; invD = k.mits;
+            if (!act && !(Phi <= 0.0)) Ri = Phi;                                        // NaN Φ
             if (act) {
                 const double xx = Phi * k.isc;
                 const double pw1 = pow(xx, k.m - 1.0);
@@ -476,6 +479,7 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
     crystal_evaluate<HASQ, INTPOW>(k, scr, L, yr, &nrm2, &bad);
     L.iters = L.it - 1;
     if (L.it > k.max_iter) return true;                                                  // nonlinear_solver.jl:61 (returns nothing)
+    if (!(nrm2 == nrm2)) return true;                                                    // NaN residual (NaN input): can never pass :56 -> not converged
     if (bad) { L.bad = true; return true; }                                              // D not safely invertible -> general path
     // norm(r) < tol  (nonlinear_solver.jl:56); the square root is only taken inside a rounding-width band around tol²
     if (nrm2 < k.tol2_lo || (nrm2 <= k.tol2_hi && sqrt(nrm2) < k.tol)) { L.converged = true; return true; }

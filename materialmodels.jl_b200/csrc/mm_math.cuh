@@ -186,7 +186,7 @@ template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* i
 #pragma unroll
     for (int c = 0; c < 6; ++c) { sg[c] = st[c]; al[c] = al_n[c]; n[c] = 0.0; u[c] = 0.0; }
     int iters = 0, flag = 0;
-    if (Phi > 0.0) {
+    if (!(Phi <= 0.0)) {                                                                // Plastic.jl:134 `if Φ <= 0` (a NaN Φ takes the Newton branch, as in the reference)
         // ---- Newton on x = (σ, κ, α, μ), x0 = (σ_trial, κₙ, αₙ, μₙ)                   Plastic.jl:142-148
         flag = 1;
         double w[6], i1psi, theta, i1eta, iden, ikk, gk;
@@ -241,7 +241,8 @@ template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* i
             i1eta = den * ib;
             iden = eta1 * ib;
             if (conv) break;                                              // f_converged
-            if (iters >= k.max_iter) { flag |= 0x80; break; }
+            // out of iterations, or a non-finite residual (NaN/Inf input: NLsolve raises on it; here the point is flagged as failed)
+            if (iters >= k.max_iter || !(fabs(Rm) < 1.7e308)) { flag |= 0x80; break; }
             // ---- closed-form Newton step
             const double trRs = tr6(Rs) * (1.0 / 3.0), trRa = tr6(Ra) * (1.0 / 3.0);
             double rt[6], ra[6];

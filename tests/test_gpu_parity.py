@@ -395,3 +395,44 @@ def test_host_buffer_entry_points_match_device_path(mm, torch, lname, lay):
         assert np.array_equal(sa.flags, host(sc.flags).view(np.uint16))
     finally:
         lib.mmh_set_chunk_points(old)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_nan_inputs_terminate_are_flagged_and_do_not_leak(mm, torch):
+    """A NaN strain can never satisfy a convergence test: the local Newton loops must still terminate (iteration caps), the point
+    must be flagged as failed and counted, and its neighbours must be untouched."""
+    N = 4096
+    bad = torch.tensor([3, 77, 1000, 4095], device="cuda")
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    nc, lo, hi, seed = sy.c2_strain(0)
+    eps = mm.synth_uniform(N, nc, seed, lo, hi)
+    s0, t0, n0 = mm.material_response(m, eps, mm.initial_material_state(m, N))
+    e2 = eps.clone()
+    e2[0, bad] = float("nan")
+    with pytest.raises(RuntimeError, match="Material model not converged"):
+        mm.material_response(m, e2, mm.initial_material_state(m, N), options={"nlsolve_params": {"iterations": 50}})
+    s, t, new = mm.material_response(m, e2, mm.initial_material_state(m, N), options={"nlsolve_params": {"iterations": 50}, "defer_check": True})
+    assert int(new.n_fail.item()) == 4 and bool(((new.flags[bad] & abi.MM_FLAG_FAILED) != 0).all())
+    ok = torch.ones(N, dtype=torch.bool, device="cuda")
+    ok[bad] = False
+    assert torch.equal(s[:, ok], s0[:, ok]) and torch.equal(t[:, ok], t0[:, ok]) and torch.equal(new.data[:, ok], n0.data[:, ok])
+    assert int((new.flags[ok] & abi.MM_FLAG_FAILED).sum().item()) == 0
+    # crystal plasticity (two-kernel structured path): same guarantees
+    cm = make_crystal(mm)
+    nc, lo, hi, seed = sy.c4_strain_increment(0)
+    de = mm.synth_uniform(N, nc, seed, lo, hi)
+    c0 = mm.material_response(cm, de, mm.initial_material_state(cm, N), 1.0)
+    d2 = de.clone()
+    d2[2, bad] = float("nan")
+    sg, tg, cs = mm.material_response(cm, d2, mm.initial_material_state(cm, N), 1.0, options={"defer_check": True})
+    fl = cs.flags.view(torch.int16).to(torch.int32) & 0xFFFF
+    assert int(cs.n_fail.item()) == 4 and bool(((fl[bad] & abi.MM_ACTIVE_FAILED) != 0).all()) and int((fl[ok] & abi.MM_ACTIVE_FAILED).sum().item()) == 0
+    assert torch.equal(sg[:, ok], c0[0][:, ok]) and torch.equal(cs.data[:, ok], c0[2].data[:, ok])
+    # plane-stress wrapper around J2
+    e3 = mm.synth_uniform(N, 3, 31, -1.2e-3, 1.2e-3)
+    w0 = mm.material_response(mm.PlaneStress(), m, e3, mm.initial_material_state(m, N))
+    e3b = e3.clone()
+    e3b[1, bad] = float("nan")
+    ws, wt, wn = mm.material_response(mm.PlaneStress(), m, e3b, mm.initial_material_state(m, N), options={"nlsolve_params": {"iterations": 50}, "defer_check": True})
+    assert int(wn.n_fail.item()) == 4 and bool(((wn.flags[bad] & (abi.MM_FLAG_FAILED | abi.MM_FLAG_WRAPPER_FAILED)) != 0).all())
+    assert torch.equal(ws[:, ok], w0[0][:, ok]) and torch.equal(wn.data[:, ok], w0[2].data[:, ok])
