@@ -534,6 +534,10 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
     if (L.bad) { *fallback = true; return 0; }
     unsigned mask = L.mask;
     if (!L.converged) mask |= 0x8000u;
+    // the tangent's SPD factorisation first: if it fails the point goes to the general path and NOTHING may have been written yet
+    // (state_out may alias state_in, and the general path restarts from the old state)
+    const bool want_tan = acc.template has_out<1>() && ((mask & 0x0FFFu) != 0) && L.converged;
+    if (want_tan && !ldl6_factor(L.K)) { *fallback = true; return 0; }
 #pragma unroll
     for (int c = 0; c < 6; ++c) { acc.template out<0>(c, L.sig[c]); acc.template out<2>(c, L.sig[c]); }
     double sumx = 0.0;
@@ -556,7 +560,6 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
             //   = Eᵉ (I − S_g M⁻¹),  S_g = Σ (p_i/dD_i) Pw_i Pw_iᵀ,  M = (Eᵉ)⁻¹ + S   — and S_g = S unless an active system
             // flipped sign, in which case  dσdε = M⁻¹  (compliance + plastic compliance, inverted).  Six register-resident
             // 6x6 solves replace the six 12-vector Woodbury applications (same algebra; checked against the oracle to 1e-13).
-            if (want && !ldl6_factor(L.K)) { *fallback = true; return 0; }
             double Sg[36];
             const bool flip = want && L.flip;
             if (flip) {
@@ -610,7 +613,6 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
         }
         double svq = 0.0;
         if (want) {
-            if (!ldl6_factor(L.K)) { *fallback = true; return 0; }
             if (HASQ) {            // v = (D − ABᵀ)⁻¹ p̂, kept in scratch [36,48) is taken by the columns -> recomputed per use via yp
                 ldl6_solve(L.K, L.yp);
 #pragma unroll 1

@@ -436,3 +436,31 @@ def test_nan_inputs_terminate_are_flagged_and_do_not_leak(mm, torch):
     ws, wt, wn = mm.material_response(mm.PlaneStress(), m, e3b, mm.initial_material_state(m, N), options={"nlsolve_params": {"iterations": 50}, "defer_check": True})
     assert int(wn.n_fail.item()) == 4 and bool(((wn.flags[bad] & (abi.MM_FLAG_FAILED | abi.MM_FLAG_WRAPPER_FAILED)) != 0).all())
     assert torch.equal(ws[:, ok], w0[0][:, ok]) and torch.equal(wn.data[:, ok], w0[2].data[:, ok])
+
+
+@pytest.mark.parametrize("q,structure", [(0.0, None), (0.3, None), (0.0, "bcc")])
+def test_crystal_in_place_state_update(mm, torch, cuda_lib, q, structure):
+    """state_out == state_in (include/mmb200.h): the two-kernel path parks μ in the state output between its kernels and hands flagged
+    points to a fix-up pass that restarts from the OLD state — an in-place call must still give the out-of-place result bit for bit
+    (BCC / cross-hardening runs include fix-up points)."""
+    import ctypes as C
+
+    N = 20011
+    m = make_crystal(mm, q=q, structure=mm.BCC() if structure == "bcc" else None)
+    st = mm.initial_material_state(m, N)
+    for step in (0, 1):
+        nc, lo, hi, seed = sy.c4_strain_increment(step)
+        de = mm.synth_uniform(N, nc, seed, lo, hi)
+        s_ref, t_ref, new = mm.material_response(m, de, st, 1.0, options={"defer_check": True})
+        inplace = st.data.clone()
+        sig, tan = torch.empty_like(s_ref), torch.empty_like(t_ref)
+        act = torch.empty(N, dtype=torch.int16, device="cuda")
+        it = torch.empty(N, dtype=torch.uint8, device="cuda")
+        nf = torch.zeros(1, dtype=torch.int32, device="cuda")
+        P = lambda a: C.c_void_p(a.data_ptr())
+        rc = cuda_lib.mm_crystal(C.byref(m._c), P(de), 1.0, P(inplace), P(sig), P(tan), P(inplace), P(act), P(it), P(nf), None, N, 0, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert torch.equal(inplace, new.data) and torch.equal(sig, s_ref) and torch.equal(tan, t_ref)
+        assert torch.equal(act, new.flags) and torch.equal(it, new.iters) and int(nf.item()) == int(new.n_fail.item())
+        st = new
