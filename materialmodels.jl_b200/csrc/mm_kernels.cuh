@@ -44,7 +44,7 @@ struct Scratch {
 };
 
 template <class Op, int BS>
-__global__ void __launch_bounds__(BS, MinBlocks<Op>::value) soa_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N) {
+__global__ void __launch_bounds__(BS, (MinBlocks<Op>::value * MinBlocks<Op>::block + BS - 1) / BS) soa_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N) {
     extern __shared__ double sm_scratch[];
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     if (i >= N) return;

@@ -32,6 +32,9 @@ struct PlasticOp {
     }
 };
 
+#ifndef MM_PLASTIC_SOA_BS
+#define MM_PLASTIC_SOA_BS 128
+#endif
 #ifndef MM_PLASTIC_AOS_BS
 #define MM_PLASTIC_AOS_BS 64
 #endif
@@ -149,7 +152,7 @@ int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, do
     op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
     op.flags = flags; op.iters = iters; op.n_fail = n_fail;
     Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = state_out;
-    return launch_points<PlasticOp, 128, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
+    return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
 }
 
 int mm_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent,
