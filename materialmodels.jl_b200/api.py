@@ -611,7 +611,8 @@ def cell_internal_forces(m, dNdx, dΩ, ue, state=None, tangent=False, stress=Fal
     index = cell·nq + q; state: PlasticState over the P points (layout "soa") for Plastic, None for LinearElastic.
     Returns (fe (3·nn, ncell), new_state, extras) with extras["stress"] (6, P) / extras["tangent"] (36, P) when requested and
     extras["stiffness"] ((3·nn)², ncell): ke[3a+i, 3b+j] = Σ_q δε ⊡ D ⊡ Δε dΩ at row (3a+i)·3nn + 3b+j (stiffness=True).
-    Device (torch CUDA) arrays only.  Supported (nn, nq): (4,1) (4,4) (8,1) (8,8) (10,4)."""
+    NeoHook / Yeoh / StVenant: total-Lagrangian form, F = I + Σ_a u_a ⊗ ∇N_a, fe[a] = Σ (P⋅∇N_a) dΩ, extras["stress"] = Pᵀ (9, P),
+    extras["tangent"] = ∂Pᵀ∂F (81, P).  Device (torch CUDA) arrays only.  Supported (nn, nq): (4,1) (4,4) (8,1) (8,8) (10,4)."""
     dNdx, dΩ, ue = _prep(dNdx), _prep(dΩ), _prep(ue)
     if _is_host(dNdx) or _is_host(dΩ) or _is_host(ue):
         raise NotImplementedError("cell_internal_forces: device (torch CUDA) arrays only")
@@ -634,8 +635,16 @@ def cell_internal_forces(m, dNdx, dΩ, ue, state=None, tangent=False, stress=Fal
             check(lib.mm_cells_linear_elastic(ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(fe), _ptr(ke), _ptr(σ), _ptr(tan), ncell,
                                               _stream(ue)), "mm_cells_linear_elastic")
             return fe, (state if state is not None else LinearElasticState()), extras
+        if isinstance(m, _Hyper):                       # total Lagrangian: F = I + Σ u ⊗ ∇N, stress = Pᵀ (9), tangent = ∂Pᵀ∂F (81)
+            if stiffness:
+                raise NotImplementedError("cell_internal_forces(::%s): element stiffness not implemented (ask for tangent=True and assemble from ∂Pᵀ∂F)" % type(m).__name__)
+            Pt = _empty((9, P), ue) if stress else None
+            dP = _empty((81, P), ue) if tangent else None
+            check(lib.mm_cells_hyper(m.MODEL, ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(fe), _ptr(Pt), _ptr(dP), ncell, _stream(ue)),
+                  "mm_cells_hyper")
+            return fe, (state if state is not None else initial_material_state(m)), {"stress": Pt, "tangent": dP, "stiffness": None}
         if not isinstance(m, Plastic):
-            raise NotImplementedError("cell_internal_forces is implemented for LinearElastic and Plastic")
+            raise NotImplementedError("cell_internal_forces is implemented for LinearElastic, Plastic, NeoHook, Yeoh, StVenant")
         if state is None or state.N != P or _LAYOUTS[state.layout] != _abi.MM_LAYOUT_SOA:
             raise ValueError("cell_internal_forces(::Plastic): a 'soa' PlasticState over the %d quadrature points is required" % P)
         sin = _prep(state.data)

@@ -35,6 +35,19 @@ template <bool KEEP_D> struct CellAcc {
     template <int A> __device__ __forceinline__ bool has_out() const { return A == 1 ? (KEEP_D || tan != nullptr) : true; }
 };
 
+// finite strain: F in registers, Pᵀ kept in registers (and optionally stored), ∂Pᵀ∂F straight to global memory on request
+struct HyperCellAcc {
+    double F[9], Pt[9];
+    double* pt_out; double* dP_out;
+    int64_t P, i;
+    template <int A> __device__ __forceinline__ double in(int c) const { return F[c]; }
+    template <int A> __device__ __forceinline__ void out(int c, double v) {
+        if (A == 0) { Pt[c] = v; if (pt_out) __stcs(pt_out + (int64_t)c * P + i, v); }
+        else __stcs(dP_out + (int64_t)c * P + i, v);
+    }
+    template <int A> __device__ __forceinline__ bool has_out() const { return A == 1 ? dP_out != nullptr : true; }
+};
+
 struct CellArgs {
     const double* dNdx; const double* dOmega; const double* ue; const double* state_in;
     double* fe; double* ke; double* sig; double* tan; double* state_out;
@@ -237,6 +250,98 @@ int launch_cells(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cuda
     return a.ke ? launch_cells_k<MODEL, NN, NQ, true>(ke, kp, a, st) : launch_cells_k<MODEL, NN, NQ, false>(ke, kp, a, st);
 }
 
+// Total-Lagrangian counterpart: F = I + Σ_a u_a ⊗ ∇N_a (∇N w.r.t. the reference configuration), (Pᵀ, ∂Pᵀ∂F) from the hyperelastic
+// model through the trait route of src/traits.jl:67-77, fe[a][i] = Σ_j P_ij ∇N_a[j] dΩ.  Same thread/lane mapping and shared-memory
+// reduction as cells_kernel.
+struct HyperCellArgs {
+    const double* dNdx; const double* dOmega; const double* ue;
+    double* fe; double* Pt; double* dPdF;
+    int64_t ncell;
+};
+template <int HMODEL, int NN, int NQ, int BS>
+__global__ void __launch_bounds__(BS, 3) hyper_cells_kernel(const HyperK k, const HyperCellArgs a) {
+    static_assert(NQ == 1 || NQ == 2 || NQ == 4 || NQ == 8, "quadrature points per cell must be a power of two <= 8");
+    constexpr int NC = 3 * NN;
+    extern __shared__ double sm[];
+    double* sm_dN = sm;
+    double* sm_f = sm + NC * BS;
+    const int64_t P = a.ncell * NQ;
+    const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
+    const unsigned mask = __ballot_sync(0xffffffffu, i < P);
+    if (i >= P) return;
+    const int64_t cell = i / NQ;
+    const int q = (int)(i - cell * NQ);
+    const int t = threadIdx.x;
+    HyperCellAcc acc;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) acc.F[c] = (c == 0 || c == 4 || c == 8) ? 1.0 : 0.0;
+#pragma unroll
+    for (int n = 0; n < NN; ++n) {
+        double u[3], d[3];
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+            d[kk] = __ldcs(a.dNdx + (int64_t)(3 * n + kk) * P + i);
+            u[kk] = __ldg(a.ue + (int64_t)(3 * n + kk) * a.ncell + cell);
+            sm_dN[(3 * n + kk) * BS + t] = d[kk];
+        }
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj)
+#pragma unroll
+            for (int ii = 0; ii < 3; ++ii) acc.F[ii + 3 * jj] += u[ii] * d[jj];             // F_ij += u_a[i] ∇N_a[j]
+    }
+    const double dO = __ldcs(a.dOmega + i);
+    acc.pt_out = a.Pt; acc.dP_out = a.dPdF; acc.P = P; acc.i = i;
+    hyper_point_ex<HMODEL, 1, 2>(k, acc);
+#pragma unroll
+    for (int n = 0; n < NN; ++n) {
+        double d[3];
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) d[kk] = sm_dN[(3 * n + kk) * BS + t] * dO;
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii) {
+            const double f = acc.Pt[0 + 3 * ii] * d[0] + acc.Pt[1 + 3 * ii] * d[1] + acc.Pt[2 + 3 * ii] * d[2];   // P_ij = Pᵀ_ji = Pt[j + 3 i]
+            if (NQ == 1) __stcs(a.fe + (int64_t)(3 * n + ii) * a.ncell + cell, f);
+            else sm_f[(3 * n + ii) * (BS + 1) + t] = f;
+        }
+    }
+    if (NQ > 1) {
+        __syncwarp(mask);
+        const int t0 = t - q;
+#pragma unroll
+        for (int c0 = 0; c0 < NC; c0 += NQ) {
+            const int c = c0 + q;
+            if (c < NC) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) v += sm_f[c * (BS + 1) + t0 + j];
+                __stcs(a.fe + (int64_t)c * a.ncell + cell, v);
+            }
+        }
+    }
+}
+template <int HMODEL, int NN, int NQ>
+int launch_hyper_cells(const HyperK& k, const HyperCellArgs& a, cudaStream_t st) {
+    constexpr int BS = 128;
+    constexpr size_t smem = (size_t)3 * NN * ((NQ > 1) ? (2 * BS + 1) : BS) * sizeof(double);
+    const int64_t P = a.ncell * NQ;
+    if (P == 0) return MM_OK;
+    const int64_t blocks = (P + BS - 1) / BS;
+    if (blocks > 2147483647LL) return set_error(MM_ERR_ARG, "mm_cells_hyper: too many points for one launch");
+    static SmemOptIn optin;
+    if (int rc = ensure_smem(optin, hyper_cells_kernel<HMODEL, NN, NQ, BS>, smem, "mm_cells_hyper")) return rc;
+    hyper_cells_kernel<HMODEL, NN, NQ, BS><<<(unsigned)blocks, BS, smem, st>>>(k, a);
+    return check_launch("mm_cells_hyper");
+}
+template <int HMODEL>
+int dispatch_hyper_cells(int nn, int nq, const HyperK& k, const HyperCellArgs& a, cudaStream_t st) {
+    if (nn == 4 && nq == 1) return launch_hyper_cells<HMODEL, 4, 1>(k, a, st);
+    if (nn == 4 && nq == 4) return launch_hyper_cells<HMODEL, 4, 4>(k, a, st);
+    if (nn == 8 && nq == 8) return launch_hyper_cells<HMODEL, 8, 8>(k, a, st);
+    if (nn == 8 && nq == 1) return launch_hyper_cells<HMODEL, 8, 1>(k, a, st);
+    if (nn == 10 && nq == 4) return launch_hyper_cells<HMODEL, 10, 4>(k, a, st);
+    return set_error(MM_ERR_ARG, "mm_cells_hyper: unsupported element (nodes %d, quadrature points %d); supported: (4,1) (4,4) (8,1) (8,8) (10,4)", nn, nq);
+}
+
 template <int MODEL>
 int dispatch_cells(int nn, int nq, const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
     if (nn == 4 && nq == 1) return launch_cells<MODEL, 4, 1>(ke, kp, a, st);       // linear tetrahedron, 1-point rule
@@ -269,6 +374,19 @@ int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, con
     ElasticK ke = make_elastic_k(p->E, p->nu);
     PlasticK kp = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
     return dispatch_cells<1>(nn, nq, ke, kp, a, (cudaStream_t)stream);
+}
+
+int mm_cells_hyper(int model, const MMHyper* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, double* fe, double* Pt,
+                   double* dPdF, int64_t ncell, void* stream) {
+    if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !fe))) return set_error(MM_ERR_ARG, "mm_cells_hyper: bad argument");
+    HyperK k; k.lambda = p->lambda; k.mu = p->mu; k.c2 = p->c2; k.c3 = p->c3;
+    HyperCellArgs a{dNdx, dOmega, ue, fe, Pt, dPdF, ncell};
+    switch (model) {
+        case MM_NEOHOOK: return dispatch_hyper_cells<0>(nn, nq, k, a, (cudaStream_t)stream);
+        case MM_YEOH: return dispatch_hyper_cells<1>(nn, nq, k, a, (cudaStream_t)stream);
+        case MM_STVENANT: return dispatch_hyper_cells<2>(nn, nq, k, a, (cudaStream_t)stream);
+    }
+    return set_error(MM_ERR_ARG, "mm_cells_hyper: unknown model %d", model);
 }
 
 }  // extern "C"

@@ -381,6 +381,37 @@ int mmo_cells(int model, const void* params, int nn, int nq, const double* dNdx,
     return 0;
 }
 
+// total-Lagrangian cell loop: F = I + Σ_a u_a ⊗ ∇N_a; (Pᵀ, ∂Pᵀ∂F) = material_response(∂Pᵀ∂F(), m, DeformationGradient(F)) (traits.jl:67-107);
+// fe[a][i] += (P ⋅ ∇N_a)_i dΩ with P = (Pᵀ)ᵀ
+int mmo_cells_hyper(int model, const MMHyper* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, double* fe, double* Pt_out,
+                    double* dP_out, int64_t ncell) {
+    const int64_t P = ncell * nq;
+    HyperM m{p->lambda, p->mu, p->c2, p->c3};
+    int om = model == MM_NEOHOOK ? MMO_NEOHOOK : (model == MM_YEOH ? MMO_YEOH : MMO_STVENANT);
+#pragma omp parallel for schedule(static)
+    for (int64_t cell = 0; cell < ncell; ++cell) {
+        std::vector<double> f(3 * nn, 0.0);
+        for (int q = 0; q < nq; ++q) {
+            const int64_t i = cell * nq + q;
+            double F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Pt[9], dP[81];
+            for (int a = 0; a < nn; ++a)
+                for (int k = 0; k < 3; ++k)
+                    for (int l = 0; l < 3; ++l) F[k + 3 * l] += ue[(int64_t)(3 * a + k) * ncell + cell] * dNdx[(int64_t)(3 * a + l) * P + i];
+            hyper_response_traits(om, m, F, MMO_STRAIN_F, MMO_TAN_DPDF, Pt, dP);
+            if (Pt_out) for (int c = 0; c < 9; ++c) Pt_out[(int64_t)c * P + i] = Pt[c];
+            if (dP_out) for (int c = 0; c < 81; ++c) dP_out[(int64_t)c * P + i] = dP[c];
+            for (int a = 0; a < nn; ++a)
+                for (int k = 0; k < 3; ++k) {
+                    double v = 0;
+                    for (int l = 0; l < 3; ++l) v += Pt[l + 3 * k] * dNdx[(int64_t)(3 * a + l) * P + i];     // P_kl = Pᵀ_lk
+                    f[3 * a + k] += v * dOmega[i];
+                }
+        }
+        for (int c = 0; c < 3 * nn; ++c) fe[(int64_t)c * ncell + cell] = f[c];
+    }
+    return 0;
+}
+
 // ---- trait layer (reference src/traits.jl:34-107): strain kinds C / F / E, tangent kinds ∂S∂C / ∂S∂E / ∂Pᵀ∂F ----------
 int mmo_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent,
                  int64_t N, int layout) {

@@ -41,6 +41,7 @@ _SIG = {
     "mmo_neohook_dPdF_ad": (C.c_int, [C.POINTER(abi.MMHyper), _P, _P, _P]),
     "mmo_wrapped_transviso": (C.c_int, [C.c_int, C.POINTER(abi.MMTransverselyIsotropic), _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
     "mmo_cells": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64]),
+    "mmo_cells_hyper": (C.c_int, [C.c_int, C.POINTER(abi.MMHyper), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _I64]),
     "mmo_transviso_setup": (C.c_int, [C.c_double] * 5 + [C.POINTER(abi.MMTransverselyIsotropic)]),
     "mmo_transversely_isotropic": (C.c_int, [C.POINTER(abi.MMTransverselyIsotropic), _P, _P, _P, _P, _I64, C.c_int]),
     "mmo_strain_energy_batch": (C.c_int, [C.c_int, _P, _P, C.c_int, _P, _I64, C.c_int]),
@@ -317,3 +318,16 @@ def cells(model, params, nn, nq, dNdx, dOmega, ue, state=None, want_tangent=True
                          _ptr(flags), _ptr(iters), _ptr(nfail), C.byref(o), ncell)
     assert rc == 0
     return dict(fe=fe, ke=ke, sig=sig, tan=tan, state=st_out, flags=flags, iters=iters, n_fail=int(nfail[0]))
+
+
+def cells_hyper(model, params, nn, nq, dNdx, dOmega, ue, want_tangent=True):
+    """total-Lagrangian cell loop for NeoHook / Yeoh / StVenant: F = I + Σ u ⊗ ∇N, (Pᵀ, ∂Pᵀ∂F), fe = Σ P⋅∇N dΩ"""
+    dNdx = np.ascontiguousarray(dNdx, dtype=np.float64); dOmega = np.ascontiguousarray(dOmega, dtype=np.float64); ue = np.ascontiguousarray(ue, dtype=np.float64)
+    ncell = ue.shape[1]; P = ncell * nq
+    assert dNdx.shape == (3 * nn, P) and dOmega.shape == (P,) and ue.shape == (3 * nn, ncell)
+    p = params if isinstance(params, abi.MMHyper) else abi.MMHyper(*params)
+    fe, Pt = np.zeros((3 * nn, ncell)), np.zeros((9, P))
+    dP = np.zeros((81, P)) if want_tangent else None
+    rc = lib().mmo_cells_hyper(model, C.byref(p), nn, nq, _ptr(dNdx), _ptr(dOmega), _ptr(ue), _ptr(fe), _ptr(Pt), _ptr(dP), ncell)
+    assert rc == 0
+    return dict(fe=fe, Pt=Pt, dPdF=dP)

@@ -180,3 +180,71 @@ def test_gpu_cell_loop_matches_oracle(mm, cuda_lib, oracle, kind, ncell):
     assert np.abs(f.sum(axis=1)).max() < 1e-10 * np.abs(f).max()
     with pytest.raises(RuntimeError, match="unsupported element"):
         mm.cell_internal_forces(le, dev(np.zeros((9, 6))), dev(np.ones(6)), dev(np.zeros((9, 2))))
+
+
+# ---- total-Lagrangian cells: NeoHook / Yeoh / StVenant --------------------------------------------------------------------------
+import materialmodels_jl_b200._abi as abi  # noqa: E402
+
+HYPER = [("NeoHook", abi.MM_NEOHOOK, sy.NEOHOOK_PARAMS), ("Yeoh", abi.MM_YEOH, sy.YEOH_PARAMS), ("StVenant", abi.MM_STVENANT, sy.NEOHOOK_PARAMS)]
+
+
+def _F_of(U, dNdx):
+    ncell, nq = dNdx.shape[:2]
+    return np.eye(3)[None, None] + np.einsum("cak,cqal->cqkl", U, dNdx)
+
+
+@pytest.mark.parametrize("name,model,prm", HYPER)
+@pytest.mark.parametrize("kind", ["tet4", "hex8"])
+def test_oracle_hyper_cells_energy_consistency_and_objectivity(oracle, kind, name, model, prm):
+    """fe = ∂W/∂u with W = Σ_q ψ(F_q) dΩ (the energy of src/FiniteStrain/*.jl:28-35), by central differences of the oracle's energy;
+    a rigid rotation of the cell gives F = R, C = I, no stress, no force."""
+    ncell = 6
+    X, nn, nq, (dNdx, dO) = random_cells(kind, ncell, 15)
+    rng = np.random.default_rng(16)
+    hp = abi.MMHyper(**prm)
+    U = 0.05 * (2 * rng.random((ncell, nn, 3)) - 1)
+    d, o, u = pack(dNdx, dO, U)
+    r = oracle.cells_hyper(model, hp, nn, nq, d, o, u)
+
+    def W(Uv):
+        F = _F_of(Uv, dNdx).reshape(ncell * nq, 3, 3)
+        F9 = np.ascontiguousarray(F.transpose(2, 1, 0).reshape(9, -1))          # column-major per point: index i + 3j
+        return (oracle.strain_energy_batch(model, hp, F9, oracle.STRAIN_F) * dO.reshape(-1)).reshape(ncell, nq).sum(axis=1)
+
+    h = 1e-6
+    fd = np.zeros((ncell, nn, 3))
+    for a in range(nn):
+        for k in range(3):
+            Up, Um = U.copy(), U.copy()
+            Up[:, a, k] += h
+            Um[:, a, k] -= h
+            fd[:, a, k] = (W(Up) - W(Um)) / (2 * h)
+    assert np.allclose(fe_of(r, ncell, nn), fd, rtol=2e-7, atol=1e-8 * np.abs(fd).max())
+    # objectivity: u = (R − I) x + t
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    U = X @ (R - np.eye(3)).T + np.array([0.3, -0.2, 0.1])
+    d, o, u = pack(dNdx, dO, U)
+    r = oracle.cells_hyper(model, hp, nn, nq, d, o, u)
+    assert np.abs(r["Pt"]).max() < 1e-12 and np.abs(r["fe"]).max() < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,model,prm", HYPER)
+@pytest.mark.parametrize("kind,ncell", [("tet4", 20011), ("hex8", 5003)])
+def test_gpu_hyper_cells_match_oracle(mm, cuda_lib, oracle, kind, ncell, name, model, prm):
+    import torch
+
+    X, nn, nq, (dNdx, dO) = random_cells(kind, ncell, 17)
+    rng = np.random.default_rng(18)
+    U = 0.05 * (2 * rng.random((ncell, nn, 3)) - 1)
+    d, o, u = pack(dNdx, dO, U)
+    hp = abi.MMHyper(**prm)
+    r = oracle.cells_hyper(model, hp, nn, nq, d, o, u)
+    m = getattr(mm, name)(λ=prm["lambda_"], μ=prm["mu"], c2=prm["c2"], c3=prm["c3"])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    fe, _, ex = mm.cell_internal_forces(m, dev(d), dev(o), dev(u), tangent=True, stress=True)
+    assert H.rel_err(ex["stress"].cpu().numpy(), r["Pt"]).max() < H.RTOL and H.rel_err(ex["tangent"].cpu().numpy(), r["dPdF"]).max() < H.RTOL
+    assert np.abs(fe.cpu().numpy() - r["fe"]).max() < H.RTOL * np.abs(r["fe"]).max()
+    fe2, _, ex2 = mm.cell_internal_forces(m, dev(d), dev(o), dev(u))            # lean call: nothing but fe leaves the kernel
+    assert ex2["stress"] is None and ex2["tangent"] is None and torch.equal(fe2, fe)

@@ -178,6 +178,19 @@ def main():
                    {"ke_flop_per_pt": flop, "ke_TFLOPs": round(flop * Pk / (med * 1e-3) / 1e12, 2)})
             del dN, dO, ue, stA, stB, dNk, dOk, uek, stk
             torch.cuda.empty_cache()
+    if want("hypercells"):
+        hm = mm.NeoHook(λ=1.0, μ=1.0)
+        for nn, nq in ((4, 1), (8, 8)):
+            P = int(1e8 * S) // nq * nq
+            ncell = P // nq
+            dN = mm.synth_uniform(P, 3 * nn, 71, -1.0, 1.0)
+            dO = mm.synth_uniform(P, 1, 72, 0.5, 1.5).reshape(P)
+            ue = mm.synth_uniform(ncell, 3 * nn, 74, -0.03, 0.03)
+            for tan in (False, True):
+                med, mn = timeit(lambda: mm.cell_internal_forces(hm, dN, dO, ue, tangent=tan), a.reps)
+                report("cells NeoHook nn=%d nq=%d %s" % (nn, nq, "fe+dPdF" if tan else "fe"), P, 24 * nn + 8 + 48 * nn / nq + (648 if tan else 0), med, mn)
+            del dN, dO, ue
+            torch.cuda.empty_cache()
     if want("xu"):
         N = int(1e8 * S)
         x = sy.XU_PARAMS

@@ -45,7 +45,7 @@ elif which == "xu":
     D = mm.synth_uniform(N, nc, seed, lo, hi)
     for _ in range(reps):
         mm.material_response(m, D)
-elif which in ("cells_tet4", "cells_hex8"):
+elif which in ("cells_tet4", "cells_hex8", "cells_hex8_ke"):
     nn, nq = (4, 1) if which.endswith("tet4") else (8, 8)
     P = N // nq * nq
     m = mm.Plastic(**sy.PLASTIC_PARAMS)
@@ -55,7 +55,7 @@ elif which in ("cells_tet4", "cells_hex8"):
     _, stA, _ = mm.cell_internal_forces(m, dN, dO, mm.synth_uniform(P // nq, 3 * nn, 73, -amp, amp), mm.initial_material_state(m, P), options={"defer_check": True})
     ue = mm.synth_uniform(P // nq, 3 * nn, 74, -amp, amp)
     for _ in range(reps):
-        mm.cell_internal_forces(m, dN, dO, ue, stA, options={"defer_check": True})
+        mm.cell_internal_forces(m, dN, dO, ue, stA, stiffness=which.endswith("_ke"), options={"defer_check": True})
 elif which == "transviso":
     m = mm.TransverselyIsotropic(E_L=100e3, E_T=10e3, G_LT=5e3, ν_LT=0.4, ν_TT=0.3)
     eps = mm.synth_uniform(N, 6, 99, -2e-3, 2e-3)
