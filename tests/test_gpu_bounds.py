@@ -144,6 +144,10 @@ def test_no_entry_point_writes_out_of_bounds(mm, cuda_lib, N, lay, shift):
                                         None, ncell, None) == 0
             for g, n in ((fe, "fe"), (kk, "ke"), (s, "σ"), (t, "tangent"), (so, "state"), (fl, "flags"), (it, "iters")):
                 g.check("mm_cells_plastic(%d,%d) %s" % (nn, nq, n))
+            fe, pt, dp = G(3 * nn * ncell), G(9 * P), G(81 * P)
+            u2 = sy.host_uniform(ncell, 3 * nn, 75, [-0.03] * (3 * nn), [0.03] * (3 * nn))
+            assert lib.mm_cells_hyper(abi.MM_YEOH, C.byref(hp), nn, nq, I(dN), I(dO), I(u2), fe.ptr, pt.ptr, dp.ptr, ncell, None) == 0
+            fe.check("mm_cells_hyper fe"), pt.check("mm_cells_hyper Pt"), dp.check("mm_cells_hyper dPdF")
             fe, s = G(3 * nn * ncell), G(6 * P)
             assert lib.mm_cells_linear_elastic(C.byref(le), nn, nq, I(dN), I(dO), I(ue), fe.ptr, None, s.ptr, None, ncell, None) == 0
             fe.check("mm_cells_linear_elastic fe"), s.check("mm_cells_linear_elastic σ")
