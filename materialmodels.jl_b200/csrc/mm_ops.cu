@@ -105,12 +105,19 @@ __global__ void __launch_bounds__(256) synth_kernel(double* out, int64_t N, int 
     }
 }
 
+// the 81-entry ∂Pᵀ∂F route needs ~250 registers unconstrained (one 256-thread block per SM, 8 warps: 0.84 of the HBM peak);
+// capped at 168 (3 x 128 threads per SM) it streams like the others
+#ifndef MM_DPDF_MINBLOCKS
+#define MM_DPDF_MINBLOCKS 3
+#endif
+template <int MODEL, int KIND> struct MinBlocks<HyperOp<MODEL, KIND, 2>> { static constexpr int value = MM_DPDF_MINBLOCKS, block = 128; };
+
 template <int MODEL, int KIND, int TAN>
 int launch_hyper_mkt(const HyperK& k, const double* strain, double* S, double* T, int64_t N, int layout, cudaStream_t st) {
     Ptrs<1, 2> p;
     p.in[0] = strain; p.out[0] = S; p.out[1] = T;
     HyperOp<MODEL, KIND, TAN> op; op.k = k;
-    return launch_points<HyperOp<MODEL, KIND, TAN>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper");
+    return launch_points<HyperOp<MODEL, KIND, TAN>, (TAN == 2 ? 128 : 256), (TAN == 2 ? 64 : MM_STREAM_AOS_BS)>(op, p, N, layout, st, "mm_hyper");
 }
 template <int MODEL> int launch_hyper(const HyperK& k, const double* strain, int strain_kind, int tangent_kind, double* S, double* T, int64_t N, int layout, cudaStream_t st) {
     if (tangent_kind == MM_TANGENT_DPDF) return launch_hyper_mkt<MODEL, 1, 2>(k, strain, S, T, N, layout, st);

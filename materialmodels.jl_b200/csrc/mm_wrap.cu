@@ -73,6 +73,10 @@ template <int KIND> struct WrappedTransvIsoOp {
         if (flag && n_fail) atomicAdd(n_fail, 1);
     }
 };
+#ifndef MM_WRAPTI_MINBLOCKS
+#define MM_WRAPTI_MINBLOCKS 4
+#endif
+template <int KIND> struct MinBlocks<WrappedTransvIsoOp<KIND>> { static constexpr int value = MM_WRAPTI_MINBLOCKS, block = 128; };
 template <int KIND>
 int launch_wrapped_transviso(const MMTransverselyIsotropic* p, const double* eps, const double* a3, double* sig, double* tan, uint8_t* oit, int32_t* n_fail,
                              const MMNewtonOpts* w, int64_t N, int layout, cudaStream_t st) {

@@ -217,6 +217,19 @@ def main():
                     "n_fail": int(stB.n_fail.item())})
             del eA, eB, stA, stB
             torch.cuda.empty_cache()
+    if want("wrapti"):
+        N = int(1e8 * S)
+        m = mm.TransverselyIsotropic(E_L=100e3, E_T=10e3, G_LT=5e3, ν_LT=0.4, ν_TT=0.3)
+        a3 = mm.synth_uniform(N, 3, 100, 0.1, 1.0)
+        a3 /= a3.norm(dim=0, keepdim=True)
+        st = mm.TransverselyIsotropicState(a3.contiguous(), "soa")
+        for dim, nc in ((mm.PlaneStress(), 3), (mm.ShellStress(), 6)):
+            e = mm.synth_uniform(N, nc, 41, -1e-3, 1e-3)
+            med, mn = timeit(lambda: mm.material_response(dim, m, e, st, options={"defer_check": True}), a.reps)
+            report("transversely_isotropic %s soa" % type(dim).__name__, N, 8 * (nc + 3 + nc + nc * nc) + 1, med, mn)
+            del e
+        del a3, st
+        torch.cuda.empty_cache()
     if want("crystal"):
         N = int(1e7 * S)
         ss = mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES)
