@@ -230,6 +230,23 @@ def main():
             del e
         del a3, st
         torch.cuda.empty_cache()
+    if want("xtalvariants"):
+        # crystal plasticity off the headline configuration: BCC table (the reference's, with two non-slip 'systems' -> fix-up points)
+        # and cross hardening q != 0 (Sherman-Morrison path)
+        N = int(1e7 * S)
+        for tag, structure, q in (("FCC q=0.3", mm.FCC(), 0.3), ("BCC q=0", mm.BCC(), 0.0), ("BCC q=0.3", mm.BCC(), 0.3)):
+            prm = dict(sy.CRYSTAL_PARAMS); prm["q"] = q
+            m = mm.CrystalViscoPlastic(slipsystems=mm.slipsystems(structure, sy.CRYSTAL_RODRIGUES), **prm)
+            nc, lo, hi, seed = sy.c4_strain_increment(0)
+            dA = mm.synth_uniform(N, nc, seed, lo, hi)
+            _, _, stA = mm.material_response(m, dA, mm.initial_material_state(m, N), 1.0, options={"defer_check": True})
+            nc, lo, hi, seed = sy.c4_strain_increment(1)
+            dB = mm.synth_uniform(N, nc, seed, lo, hi)
+            med, mn = timeit(lambda: mm.material_response(m, dB, stA, 1.0, options={"defer_check": True}), max(a.reps // 3, 2), warm=1)
+            _, _, stB = mm.material_response(m, dB, stA, 1.0, options={"defer_check": True})
+            report("crystal stepB " + tag, N, 1056, med, mn, {"mean_iters": stB.iters.float().mean().item(), "n_fail": int(stB.n_fail.item())})
+            del dA, dB, stA, stB
+            torch.cuda.empty_cache()
     if want("crystal"):
         N = int(1e7 * S)
         ss = mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES)
