@@ -7,31 +7,24 @@
 
 namespace mm {
 
-// MODE 0: general path (any H; 12x12 pivoted LU in thread-local memory).
-// MODE 1 / 2: register-resident structured path for H = a I + b 11ᵀ without / with the cross-hardening term
-// (b = H_iso q).  A point whose SPD factorisation or D-guard fails is only MARKED (bit 14 of its mask); a second,
-// tiny launch (crystal_fixup_kernel) re-runs exactly those points through the general pivoted path, so the main
-// kernel carries no fallback code (registers) and a rare fallback does not stall its warp.
+// General path (any H; 12x12 pivoted LU in thread-local memory): one thread per point through the generic wrappers.
+// Structured path (H = a I + b 11ᵀ, what the reference constructor builds): the two kernels below.  A point whose SPD
+// factorisation or D-guard fails there is only MARKED (bit 14 of its mask); a third launch (crystal_fixup_kernel) re-runs
+// exactly those points through the general pivoted solve, so the main kernels carry no fallback code (registers) and a rare
+// fallback does not stall its warp.
 #define MM_ACTIVE_NEEDS_GENERAL 0x4000u
 
-template <int MODE> struct CrystalOp {
-    static constexpr int NIN = 2, NOUT = 3, SCRATCH = (MODE == 0) ? 0 : MM_CRYSTAL_SCRATCH;
+struct CrystalGeneralOp {
+    static constexpr int NIN = 2, NOUT = 3, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? 6 : 42; }
     __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : (a == 1 ? 36 : 42); }
     CrystalK k;
-    uint16_t* active;     // never NULL for MODE 1/2 (mm_crystal substitutes a temporary)
+    uint16_t* active;
     uint8_t* iters;
     int32_t* n_fail;
-    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch& scr) const {
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
         int it = 0;
-        unsigned mask;
-        if (MODE == 0) {
-            mask = crystal_point(k, acc, &it);
-        } else {
-            bool fallback = false;
-            mask = crystal_point_fast<MODE == 2>(k, acc, scr, &it, &fallback);
-            if (fallback) mask = MM_ACTIVE_NEEDS_GENERAL;
-        }
+        const unsigned mask = crystal_point(k, acc, &it);
         if (active) active[i] = (uint16_t)mask;
         if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
         if ((mask & MM_ACTIVE_FAILED) && n_fail) atomicAdd(n_fail, 1);
@@ -44,10 +37,10 @@ template <int LAYOUT> struct DirectAcc {
     int64_t N, i;
     __device__ __forceinline__ DirectAcc(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_) : p(p_), N(N_), i(i_) {}
     template <int A> __device__ __forceinline__ double in(int c) const {
-        return LAYOUT == 0 ? p.in[A][(int64_t)c * N + i] : p.in[A][i * CrystalOp<0>::in_nc(A) + c];
+        return LAYOUT == 0 ? p.in[A][(int64_t)c * N + i] : p.in[A][i * CrystalGeneralOp::in_nc(A) + c];
     }
     template <int A> __device__ __forceinline__ void out(int c, double v) const {
-        if (LAYOUT == 0) p.out[A][(int64_t)c * N + i] = v; else p.out[A][i * CrystalOp<0>::out_nc(A) + c] = v;
+        if (LAYOUT == 0) p.out[A][(int64_t)c * N + i] = v; else p.out[A][i * CrystalGeneralOp::out_nc(A) + c] = v;
     }
     template <int A> __device__ __forceinline__ bool has_out() const { return p.out[A] != nullptr; }
 };
@@ -90,8 +83,6 @@ __global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const Crysta
 #ifndef MM_CRYSTAL_THRESH
 #define MM_CRYSTAL_THRESH 4
 #endif
-template <> struct MinBlocks<CrystalOp<1>> { static constexpr int value = MM_CRYSTAL_MINBLOCKS, block = 64; };
-template <> struct MinBlocks<CrystalOp<2>> { static constexpr int value = MM_CRYSTAL_MINBLOCKS, block = 64; };
 
 // ---------------------------------------------------------------------------------------------------------
 // Two-kernel structured path.
@@ -109,7 +100,7 @@ template <> struct MinBlocks<CrystalOp<2>> { static constexpr int value = MM_CRY
 template <int LAYOUT> struct DirectAccRW : DirectAcc<LAYOUT> {
     __device__ __forceinline__ DirectAccRW(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_) : DirectAcc<LAYOUT>(p_, N_, i_) {}
     template <int A> __device__ __forceinline__ double rd_out(int c) const {
-        return LAYOUT == 0 ? this->p.out[A][(int64_t)c * this->N + this->i] : this->p.out[A][this->i * CrystalOp<0>::out_nc(A) + c];
+        return LAYOUT == 0 ? this->p.out[A][(int64_t)c * this->N + this->i] : this->p.out[A][this->i * CrystalGeneralOp::out_nc(A) + c];
     }
 };
 
@@ -214,21 +205,21 @@ int launch_crystal_persistent(const CrystalK& k, uint16_t* active, uint8_t* iter
                    : launch_crystal_two_kernel<HASQ, false, LAYOUT>(k, active, iters, n_fail, ptrs, N, st);
 }
 
-template <int MODE>
-int launch_crystal(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
+int launch_crystal_general(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
+    if (N == 0) return MM_OK;
+    CrystalGeneralOp op;
+    op.k = k; op.active = active; op.iters = iters; op.n_fail = n_fail;
+    return launch_points<CrystalGeneralOp, 64>(op, ptrs, N, layout, st, "mm_crystal");
+}
+
+template <bool HASQ>
+int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
     if (N == 0) return MM_OK;
     int rc;
-    const char* pers = getenv("MM_CRYSTAL_PERSISTENT");      // A/B switch: "0" = one point per thread through the generic wrappers
-    if (MODE != 0 && !(pers && pers[0] == '0')) {
-        if (layout == 0)      rc = launch_crystal_persistent<MODE == 2, 0>(k, active, iters, n_fail, ptrs, N, st);
-        else if (layout == 1) rc = launch_crystal_persistent<MODE == 2, 1>(k, active, iters, n_fail, ptrs, N, st);
-        else return set_error(MM_ERR_ARG, "mm_crystal: unknown layout %d", layout);
-    } else {
-        CrystalOp<MODE> op;
-        op.k = k; op.active = active; op.iters = iters; op.n_fail = n_fail;
-        rc = launch_points<CrystalOp<MODE>, 64>(op, ptrs, N, layout, st, "mm_crystal");
-    }
-    if (rc || MODE == 0) return rc;
+    if (layout == 0)      rc = launch_crystal_persistent<HASQ, 0>(k, active, iters, n_fail, ptrs, N, st);
+    else if (layout == 1) rc = launch_crystal_persistent<HASQ, 1>(k, active, iters, n_fail, ptrs, N, st);
+    else return set_error(MM_ERR_ARG, "mm_crystal: unknown layout %d", layout);
+    if (rc) return rc;
     const int64_t blocks = (N + MM_FIXUP_RANGE - 1) / MM_FIXUP_RANGE;
     if (layout == 0) crystal_fixup_kernel<0><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N);
     else             crystal_fixup_kernel<1><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N);
@@ -250,7 +241,7 @@ extern "C" int mm_crystal(const MMCrystal* p, const double* deps, double dt, con
     Ptrs<2, 3> ptrs; ptrs.in[0] = deps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = state_out;
     cudaStream_t st = (cudaStream_t)stream;
     const char* force = getenv("MM_CRYSTAL_FORCE_GENERAL");      // debugging / A-B timing switch
-    if (!k.h_struct || (force && force[0] == '1')) return launch_crystal<0>(k, active, iters, n_fail, ptrs, N, layout, st);
+    if (!k.h_struct || (force && force[0] == '1')) return launch_crystal_general(k, active, iters, n_fail, ptrs, N, layout, st);
     // the structured path needs a per-point flag array for its fix-up pass; callers normally pass `active`,
     // otherwise a stream-ordered temporary is used (the only allocation this library ever makes on a compute call)
     uint16_t* flags = active;
@@ -258,8 +249,8 @@ extern "C" int mm_crystal(const MMCrystal* p, const double* deps, double dt, con
         cudaError_t e = cudaMallocAsync((void**)&flags, (size_t)N * sizeof(uint16_t), st);
         if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_crystal: cudaMallocAsync: %s", cudaGetErrorString(e));
     }
-    const int rc = (k.b_h != 0.0) ? launch_crystal<2>(k, flags, iters, n_fail, ptrs, N, layout, st)
-                                  : launch_crystal<1>(k, flags, iters, n_fail, ptrs, N, layout, st);
+    const int rc = (k.b_h != 0.0) ? launch_crystal_structured<true>(k, flags, iters, n_fail, ptrs, N, layout, st)
+                                  : launch_crystal_structured<false>(k, flags, iters, n_fail, ptrs, N, layout, st);
     if (!active && flags) cudaFreeAsync(flags, st);
     return rc;
 }
