@@ -13,6 +13,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with `pytest -m gpu` under gpurun)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built artefacts (they are git-ignored): build libmmb200.so (nvcc cross-compiles without a GPU) before
+    the first test needs it.  No-op when the library is up to date; on a box without nvcc the prebuilt library is used as it is."""
+    import importlib.util
+    import shutil
+
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        return
+    spec = importlib.util.spec_from_file_location("_mm_build", os.path.join(ROOT, "materialmodels.jl_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.build()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     import oracle as O
