@@ -15,10 +15,12 @@ def pytest_configure(config):
 
 def pytest_sessionstart(session):
     """A fresh checkout has no built artefacts (they are git-ignored): build libmmb200.so (nvcc cross-compiles without a GPU) before
-    the first test needs it.  No-op when the library is up to date; on a box without nvcc the prebuilt library is used as it is."""
+    the first test needs it.  Only when the library is MISSING — a present one is used as it is (file times do not survive every copy)."""
     import importlib.util
     import shutil
 
+    if os.path.exists(os.path.join(ROOT, "materialmodels.jl_b200", "libmmb200.so")):
+        return
     if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
         return
     spec = importlib.util.spec_from_file_location("_mm_build", os.path.join(ROOT, "materialmodels.jl_b200", "build.py"))
