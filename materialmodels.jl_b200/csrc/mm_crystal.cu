@@ -15,16 +15,16 @@ namespace mm {
 #define MM_ACTIVE_NEEDS_GENERAL 0x4000u
 
 struct CrystalGeneralOp {
-    static constexpr int NIN = 2, NOUT = 3, SCRATCH = 0;
+    static constexpr int NIN = 2, NOUT = 3, SCRATCH = 144;     // the 12x12 Jacobian of each thread in its shared-memory scratch column
     __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? 6 : 42; }
     __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : (a == 1 ? 36 : 42); }
     CrystalK k;
     uint16_t* active;
     uint8_t* iters;
     int32_t* n_fail;
-    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch& scr) const {
         int it = 0;
-        const unsigned mask = crystal_point(k, acc, &it);
+        const unsigned mask = crystal_point(k, acc, &it, scr.base, scr.stride);
         if (active) active[i] = (uint16_t)mask;
         if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
         if ((mask & MM_ACTIVE_FAILED) && n_fail) atomicAdd(n_fail, 1);
@@ -49,28 +49,51 @@ template <int LAYOUT> struct DirectAcc {
 // lie would leave 31 of 32 lanes idle through a 12x12 pivoted-LU Newton solve (measured: BCC 415 ms per 1e7 points against 25 ms for
 // FCC).  Each block scans a contiguous range of the flag array, compacts the flagged indices into shared memory, and then works the
 // list off with full lanes.
-#define MM_FIXUP_BS 64
-#define MM_FIXUP_RANGE 8192
+#define MM_FIXUP_BS 32
+#define MM_FIXUP_RANGE 4096
 template <int LAYOUT>
-__global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint8_t* iters, int32_t* n_fail, const int64_t N) {
-    __shared__ int list[MM_FIXUP_RANGE];
-    __shared__ int count;
-    if (threadIdx.x == 0) count = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * MM_FIXUP_RANGE;
-    const int n = (int)((N - base < MM_FIXUP_RANGE) ? (N - base) : MM_FIXUP_RANGE);
-    for (int j = threadIdx.x; j < n; j += MM_FIXUP_BS)
-        if (active[base + j] & MM_ACTIVE_NEEDS_GENERAL) list[atomicAdd(&count, 1)] = j;
-    __syncthreads();
-    const int m = count;
-    for (int e = threadIdx.x; e < m; e += MM_FIXUP_BS) {
-        const int64_t i = base + list[e];
-        DirectAcc<LAYOUT> acc(p, N, i);
-        int it = 0;
-        const unsigned mask = crystal_point(k, acc, &it);
-        active[i] = (uint16_t)mask;
-        if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
-        if ((mask & MM_ACTIVE_FAILED) && n_fail) atomicAdd(n_fail, 1);
+__global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint8_t* iters, int32_t* n_fail, const int64_t N,
+                                                                    const int64_t nranges) {
+    __shared__ uint16_t list[MM_FIXUP_RANGE];
+    __shared__ int count, next;
+    __shared__ double Jsm[144 * MM_FIXUP_BS];                             // every thread's 12x12 Jacobian: column t of a [144][BS] image
+    for (int64_t r = blockIdx.x; r < nranges; r += gridDim.x) {           // persistent blocks: few resident threads keep the per-thread
+        __syncthreads();                                                  // solver state (2.4 KB of local memory each) inside L1
+        if (threadIdx.x == 0) { count = 0; next = 0; }
+        __syncthreads();
+        const int64_t base = r * MM_FIXUP_RANGE;
+        const int n = (int)((N - base < MM_FIXUP_RANGE) ? (N - base) : MM_FIXUP_RANGE);
+        for (int j = threadIdx.x; j < n; j += MM_FIXUP_BS)
+            if (active[base + j] & MM_ACTIVE_NEEDS_GENERAL) list[atomicAdd(&count, 1)] = (uint16_t)j;
+        __syncthreads();
+        const int m = count;
+        if (m == 0) continue;
+        // lanes take list entries one at a time and advance ONE Newton pass per trip, so a lane whose solve ends (converged after a few
+        // passes) moves on to the next point while its neighbours keep iterating: a non-converging point no longer holds 31 others for
+        // max_iter passes
+        CrystalGen S;
+        bool has = false;
+        int64_t i = 0;
+        for (;;) {
+            if (!has) {
+                const int e = atomicAdd(&next, 1);
+                if (e < m) {
+                    i = base + list[e];
+                    DirectAcc<LAYOUT> acc(p, N, i);
+                    crystal_gen_init(k, acc, S, Jsm + threadIdx.x, MM_FIXUP_BS);
+                    has = true;
+                }
+            }
+            if (!__any_sync(0xffffffffu, has)) break;
+            if (has && crystal_gen_pass(k, S)) {
+                DirectAcc<LAYOUT> acc(p, N, i);
+                const unsigned mask = crystal_gen_finalize(k, acc, S);
+                active[i] = (uint16_t)mask;
+                if (iters) iters[i] = (uint8_t)(S.iters > 255 ? 255 : S.iters);
+                if ((mask & MM_ACTIVE_FAILED) && n_fail) atomicAdd(n_fail, 1);
+                has = false;
+            }
+        }
     }
 }
 
@@ -220,9 +243,13 @@ int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint8_t* iter
     else if (layout == 1) rc = launch_crystal_persistent<HASQ, 1>(k, active, iters, n_fail, ptrs, N, st);
     else return set_error(MM_ERR_ARG, "mm_crystal: unknown layout %d", layout);
     if (rc) return rc;
-    const int64_t blocks = (N + MM_FIXUP_RANGE - 1) / MM_FIXUP_RANGE;
-    if (layout == 0) crystal_fixup_kernel<0><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N);
-    else             crystal_fixup_kernel<1><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N);
+    const int64_t nranges = (N + MM_FIXUP_RANGE - 1) / MM_FIXUP_RANGE;
+    int per_sm = 5;
+    if (const char* e = getenv("MM_FIXUP_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;      // tuning knob
+    int64_t blocks = (int64_t)sm_count() * per_sm;
+    if (blocks > nranges) blocks = nranges;
+    if (layout == 0) crystal_fixup_kernel<0><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges);
+    else             crystal_fixup_kernel<1><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges);
     return check_launch("mm_crystal (fix-up pass)");
 }
 

@@ -77,133 +77,154 @@ inline void make_crystal_k(CrystalK& k, double E, double nu, double tau_y, doubl
     k.m_int = (m >= 2.0 && m <= 64.0 && m == (double)(int)m) ? (int)m : 0;
 }
 
-// LU with partial pivoting on a 12x12 row-major matrix held in (thread-)local memory
-MM_HD bool lu12_factor(double* A, int* piv) {
+// LU with partial pivoting on a 12x12 row-major matrix; element e lives at A[e * st] (st = 1: thread-local array; st = threads per
+// block: the thread's column of a shared-memory image — the 144-entry matrix is what makes the general path slow when it sits in
+// local memory, ~1 700 accesses per Newton pass at L2 latency once the per-thread stacks overflow L1)
+MM_HD bool lu12_factor(double* A, int* piv, int st = 1) {
     for (int k = 0; k < 12; ++k) {
-        int p = k; double amax = fabs(A[k * 12 + k]);
-        for (int i = k + 1; i < 12; ++i) { const double v = fabs(A[i * 12 + k]); if (v > amax) { amax = v; p = i; } }
+        int p = k; double amax = fabs(A[(k * 12 + k) * st]);
+        for (int i = k + 1; i < 12; ++i) { const double v = fabs(A[(i * 12 + k) * st]); if (v > amax) { amax = v; p = i; } }
         piv[k] = p;
         if (amax == 0.0) return false;
-        if (p != k) for (int j = 0; j < 12; ++j) { const double t = A[k * 12 + j]; A[k * 12 + j] = A[p * 12 + j]; A[p * 12 + j] = t; }
-        const double ip = 1.0 / A[k * 12 + k];
+        if (p != k) for (int j = 0; j < 12; ++j) { const double t = A[(k * 12 + j) * st]; A[(k * 12 + j) * st] = A[(p * 12 + j) * st]; A[(p * 12 + j) * st] = t; }
+        const double ip = 1.0 / A[(k * 12 + k) * st];
         for (int i = k + 1; i < 12; ++i) {
-            const double l = A[i * 12 + k] * ip;
-            A[i * 12 + k] = l;
-            for (int j = k + 1; j < 12; ++j) A[i * 12 + j] -= l * A[k * 12 + j];
+            const double l = A[(i * 12 + k) * st] * ip;
+            A[(i * 12 + k) * st] = l;
+            for (int j = k + 1; j < 12; ++j) A[(i * 12 + j) * st] -= l * A[(k * 12 + j) * st];
         }
     }
     return true;
 }
-MM_HD void lu12_solve(const double* LU, const int* piv, double* b) {
+MM_HD void lu12_solve(const double* LU, const int* piv, double* b, int st = 1) {
     for (int k = 0; k < 12; ++k) { const int p = piv[k]; if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; } }
-    for (int i = 1; i < 12; ++i) { double s = b[i]; for (int j = 0; j < i; ++j) s -= LU[i * 12 + j] * b[j]; b[i] = s; }
-    for (int i = 11; i >= 0; --i) { double s = b[i]; for (int j = i + 1; j < 12; ++j) s -= LU[i * 12 + j] * b[j]; b[i] = s / LU[i * 12 + i]; }
+    for (int i = 1; i < 12; ++i) { double s = b[i]; for (int j = 0; j < i; ++j) s -= LU[(i * 12 + j) * st] * b[j]; b[i] = s; }
+    for (int i = 11; i >= 0; --i) { double s = b[i]; for (int j = i + 1; j < 12; ++j) s -= LU[(i * 12 + j) * st] * b[j]; b[i] = s / LU[(i * 12 + i) * st]; }
 }
 
-// returns the active mask (bit i <=> Φ_i > 0 at the solution; bit 15 = not converged); *iters_out = number of x updates
-template <class Acc> MM_HD unsigned crystal_point(const CrystalK& k, Acc& acc, int* iters_out) {
+// General path in resumable form (init / one `solve` pass / finalize), so that a kernel can interleave points lane by lane
+// (the fix-up pass of mm_crystal.cu refills a lane as soon as its solve ends; with one monolithic solve per thread a single
+// non-converging point holds its whole warp for max_iter passes).  crystal_point below is init + passes + finalize.
+struct CrystalGen {
+    double st[6], kap_n[12], al_n[12], x[12], sg[12];      // inputs of the solve and the iterate
+    double sig[6], kap[12], al[12], p[12], sgn[12];        // state variables at the last evaluation
+    double* J;                                             // Jacobian at the last evaluation (factored in place by the update): element e at J[e * Js]
+    int Js;
+    unsigned mask;
+    int it, iters;
+    bool converged;
+};
+
+template <class Acc> MM_HD void crystal_gen_init(const CrystalK& k, Acc& acc, CrystalGen& S, double* J, int Js) {
     const double G2 = 2.0 * k.G;
-    double st[6];
+    S.J = J; S.Js = Js;
     {   // σ_trial = σₙ + Eᵉ ⊡ Δε                                                           :119
         double e[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c);
         const double ltr = k.lam * tr6(e);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) st[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c]));
+        for (int c = 0; c < 6; ++c) S.st[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c]));
     }
-    double kap_n[12], al_n[12], x[12], sg[12];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) { kap_n[i] = acc.template in<1>(6 + i); al_n[i] = acc.template in<1>(18 + i); x[i] = acc.template in<1>(30 + i); }
+    for (int i = 0; i < 12; ++i) { S.kap_n[i] = acc.template in<1>(6 + i); S.al_n[i] = acc.template in<1>(18 + i); S.x[i] = acc.template in<1>(30 + i); }
 #pragma unroll
     for (int i = 0; i < 12; ++i) {                                                      // :120-121
         double tau = 0.0;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) tau += st[c] * k.Pw[i][c];
-        const double d = tau - al_n[i];
-        sg[i] = (d > 0.0) ? 1.0 : ((d < 0.0) ? -1.0 : 0.0);
+        for (int c = 0; c < 6; ++c) tau += S.st[c] * k.Pw[i][c];
+        const double d = tau - S.al_n[i];
+        S.sg[i] = (d > 0.0) ? 1.0 : ((d < 0.0) ? -1.0 : 0.0);
     }
-    double J[144], sig[6], kap[12], al[12], p[12], sgn[12];
-    int piv[12];
-    unsigned mask = 0;
-    int iters = 0;
-    bool converged = false;
-    for (int it = 1;; ++it) {   // pass max_iter+1 only re-evaluates the state at the last iterate of a failed solve
-        // state variables at x                                                            :118-132
+    S.mask = 0; S.it = 1; S.iters = 0; S.converged = false;
+}
+
+// one pass of the `solve` loop (nonlinear_solver.jl:53-60): evaluate r and J at x, test, update.  true = finished.
+// (pass max_iter+1 only re-evaluates the state at the last iterate of a failed solve)
+MM_HD bool crystal_gen_pass(const CrystalK& k, CrystalGen& S) {
+    // state variables at x                                                            :118-132
 #pragma unroll
-        for (int c = 0; c < 6; ++c) sig[c] = st[c];
+    for (int c = 0; c < 6; ++c) S.sig[c] = S.st[c];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        const double f = S.x[j] * S.sg[j];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) S.sig[c] -= f * k.EM[j][c];
+    }
+    double r[12], nrm2 = 0.0;
+    unsigned mask = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        double kp = 0.0;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) kp += k.H[j][i] * S.x[j];
+        S.kap[i] = S.kap_n[i] + kp;
+        const double den = 1.0 + k.H_kin * S.x[i] / k.alpha_inf;
+        S.al[i] = (S.al_n[i] + k.H_kin * S.x[i] * S.sg[i]) / den;
+        double tau = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) tau += S.sig[c] * k.Pw[i][c];
+        const double red = tau - S.al[i];
+        S.sgn[i] = (red > 0.0) ? 1.0 : ((red < 0.0) ? -1.0 : 0.0);
+        const double Phi = fabs(red) - k.tau_y - S.kap[i];                              // :110
+        double Ri = -k.t_star * S.x[i];
+        S.p[i] = 0.0;
+        if (!(Phi <= 0.0) && !(Phi > 0.0)) Ri = Phi;                                    // NaN Φ: ⟨Φ⟩ = (Φ+|Φ|)/2 is NaN in the reference, so is R
+        if (Phi > 0.0) {                                                                // ⟨Φ⟩ = (Φ+|Φ|)/2
+            const double xx = Phi / k.sigma_c;
+            const double pw1 = pow(xx, k.m - 1.0);
+            Ri = k.dt * (pw1 * xx) - k.t_star * S.x[i];                                 // :111
+            S.p[i] = k.dt * k.m / k.sigma_c * pw1;
+            mask |= (1u << i);
+        }
+        r[i] = Ri;
+        nrm2 += Ri * Ri;
+        const double dal = (k.H_kin * S.sg[i] - S.al[i] * k.H_kin / k.alpha_inf) / den;
+        // Jacobian row i
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
-            const double f = x[j] * sg[j];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) sig[c] -= f * k.EM[j][c];
+            double v = S.p[i] * (S.sgn[i] * (-S.sg[j] * k.Gm[i][j]) - k.H[j][i]);
+            if (j == i) v += -S.p[i] * S.sgn[i] * dal - k.t_star;
+            S.J[(i * 12 + j) * S.Js] = v;
         }
-        double r[12], nrm2 = 0.0;
-        mask = 0;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            double kp = 0.0;
-#pragma unroll
-            for (int j = 0; j < 12; ++j) kp += k.H[j][i] * x[j];
-            kap[i] = kap_n[i] + kp;
-            const double den = 1.0 + k.H_kin * x[i] / k.alpha_inf;
-            al[i] = (al_n[i] + k.H_kin * x[i] * sg[i]) / den;
-            double tau = 0.0;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) tau += sig[c] * k.Pw[i][c];
-            const double red = tau - al[i];
-            sgn[i] = (red > 0.0) ? 1.0 : ((red < 0.0) ? -1.0 : 0.0);
-            const double Phi = fabs(red) - k.tau_y - kap[i];                            // :110
-            double Ri = -k.t_star * x[i];
-            p[i] = 0.0;
-            if (!(Phi <= 0.0) && !(Phi > 0.0)) Ri = Phi;                                // NaN Φ: ⟨Φ⟩ = (Φ+|Φ|)/2 is NaN in the reference, so is R
-            if (Phi > 0.0) {                                                            // ⟨Φ⟩ = (Φ+|Φ|)/2
-                const double xx = Phi / k.sigma_c;
-                const double pw1 = pow(xx, k.m - 1.0);
-                Ri = k.dt * (pw1 * xx) - k.t_star * x[i];                               // :111
-                p[i] = k.dt * k.m / k.sigma_c * pw1;
-                mask |= (1u << i);
-            }
-            r[i] = Ri;
-            nrm2 += Ri * Ri;
-            const double dal = (k.H_kin * sg[i] - al[i] * k.H_kin / k.alpha_inf) / den;
-            // Jacobian row i
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                double v = p[i] * (sgn[i] * (-sg[j] * k.Gm[i][j]) - k.H[j][i]);
-                if (j == i) v += -p[i] * sgn[i] * dal - k.t_star;
-                J[i * 12 + j] = v;
-            }
-        }
-        iters = it - 1;
-        if (it > k.max_iter) break;                                                      // nonlinear_solver.jl:61 (returns nothing)
-        if (!(nrm2 == nrm2)) break;                                                      // NaN residual can never pass :56 — the reference runs out of iterations
-        if (sqrt(nrm2) < k.tol) { converged = true; break; }                             // nonlinear_solver.jl:56
-        if (!lu12_factor(J, piv)) break;
-        lu12_solve(J, piv, r);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) x[i] -= r[i];                                      // nonlinear_solver.jl:59
-        iters = it;
     }
-    if (!converged) mask |= 0x8000u;
-    // outputs                                                                            :77, :90
+    S.mask = mask;
+    S.iters = S.it - 1;
+    if (S.it > k.max_iter) return true;                                                  // nonlinear_solver.jl:61 (returns nothing)
+    if (!(nrm2 == nrm2)) return true;                                                    // NaN residual can never pass :56 — the reference runs out of iterations
+    if (sqrt(nrm2) < k.tol) { S.converged = true; return true; }                         // nonlinear_solver.jl:56
+    int piv[12];
+    if (!lu12_factor(S.J, piv, S.Js)) return true;
+    lu12_solve(S.J, piv, r, S.Js);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { acc.template out<0>(c, sig[c]); acc.template out<2>(c, sig[c]); }
+    for (int i = 0; i < 12; ++i) S.x[i] -= r[i];                                        // nonlinear_solver.jl:59
+    S.iters = S.it;
+    S.it += 1;
+    return false;
+}
+
+// outputs (:77, :90) and the tangent (:79-89); returns the active mask (bit i <=> Φ_i > 0 at the solution; bit 15 = not converged)
+template <class Acc> MM_HD unsigned crystal_gen_finalize(const CrystalK& k, Acc& acc, CrystalGen& S) {
+    unsigned mask = S.mask;
+    if (!S.converged) mask |= 0x8000u;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) { acc.template out<2>(6 + i, kap[i]); acc.template out<2>(18 + i, al[i]); acc.template out<2>(30 + i, x[i]); }
+    for (int c = 0; c < 6; ++c) { acc.template out<0>(c, S.sig[c]); acc.template out<2>(c, S.sig[c]); }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { acc.template out<2>(6 + i, S.kap[i]); acc.template out<2>(18 + i, S.al[i]); acc.template out<2>(30 + i, S.x[i]); }
     if (acc.template has_out<1>()) {
         double tan[36];
+        int piv[12];
 #pragma unroll
         for (int Jc = 0; Jc < 6; ++Jc)
 #pragma unroll
             for (int Ic = 0; Ic < 6; ++Ic) tan[Ic + 6 * Jc] = iso_entry(Ic, Jc, k.lam, k.G);
-        if ((mask & 0x0FFFu) != 0 && converged && lu12_factor(J, piv)) {                 // :79-89
+        if ((mask & 0x0FFFu) != 0 && S.converged && lu12_factor(S.J, piv, S.Js)) {       // :79-89
             for (int Jc = 0; Jc < 6; ++Jc) {
                 double z[12];
-                for (int j = 0; j < 12; ++j) z[j] = p[j] * sgn[j] * k.EM[j][Jc];
-                lu12_solve(J, piv, z);
+                for (int j = 0; j < 12; ++j) z[j] = S.p[j] * S.sgn[j] * k.EM[j][Jc];
+                lu12_solve(S.J, piv, z, S.Js);
                 for (int i = 0; i < 12; ++i) {
-                    const double zi = sgn[i] * z[i];
+                    const double zi = S.sgn[i] * z[i];
                     for (int Ic = 0; Ic < 6; ++Ic) tan[Ic + 6 * Jc] += k.EM[i][Ic] * zi;
                 }
             }
@@ -211,8 +232,18 @@ template <class Acc> MM_HD unsigned crystal_point(const CrystalK& k, Acc& acc, i
 #pragma unroll
         for (int c = 0; c < 36; ++c) acc.template out<1>(c, tan[c]);
     }
-    *iters_out = iters;
     return mask;
+}
+
+// returns the active mask (bit i <=> Φ_i > 0 at the solution; bit 15 = not converged); *iters_out = number of x updates
+// J / Js: where the 144-entry Jacobian lives (NULL: a thread-local array)
+template <class Acc> MM_HD unsigned crystal_point(const CrystalK& k, Acc& acc, int* iters_out, double* J = nullptr, int Js = 1) {
+    CrystalGen S;
+    double Jloc[144];
+    crystal_gen_init(k, acc, S, J ? J : Jloc, J ? Js : 1);
+    while (!crystal_gen_pass(k, S)) {}
+    *iters_out = S.iters;
+    return crystal_gen_finalize(k, acc, S);
 }
 
 // =================================================================================================
