@@ -79,6 +79,23 @@ def test_plastic_1e8(mm, torch, oracle):
     Ee = torch.from_numpy(mm.elastic_tangent_3D(m.E, m.ν)).cuda()
     assert torch.equal(tan[:, ~pl], Ee[:, None].expand(36, int((~pl).sum().item())))
     assert (stB.data[13][pl] > 0).all()                                    # plastic multiplier positive
+    del d, tr3, vm, Phi
+    # (iv) yield decisions against an independent FP64 evaluation of the trial yield function (torch ops), and the size of the band in
+    # which two correct FP64 evaluations of Φ could disagree on its sign (|Φ| < 1e-9 σ_y)
+    lam, G = m.E * m.ν / ((1 + m.ν) * (1 - 2 * m.ν)), m.E / (2 * (1 + m.ν))
+    e = epsB - stA.data[0:6]
+    ltr = lam * (e[0] + e[3] + e[5])
+    e.mul_(2 * G)
+    e[0] += ltr; e[3] += ltr; e[5] += ltr
+    e -= stA.data[7:13]
+    tr3 = (e[0] + e[3] + e[5]) / 3
+    vm = torch.sqrt(1.5 * ((e[0] - tr3) ** 2 + (e[3] - tr3) ** 2 + (e[5] - tr3) ** 2 + 2 * (e[1] ** 2 + e[2] ** 2 + e[4] ** 2)))
+    Phi_t = vm - m.σ_y - stA.data[6]
+    band = Phi_t.abs() < 1e-9 * m.σ_y
+    n_band = int(band.sum().item())
+    print("points with |Φ_trial| < 1e-9 σ_y: %d of %d" % (n_band, N))
+    assert n_band < 100
+    assert torch.equal(pl[~band], (Phi_t > 0)[~band])
 
 
 def test_hyper_1e8(mm, torch, oracle):
