@@ -193,6 +193,9 @@ int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, con
                      const double* state_in, double* fe, double* ke, double* sig, double* tan, double* state_out, uint8_t* flags,
                      uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell, void* stream);
 
+int mm_cells_transversely_isotropic(const MMTransverselyIsotropic* p, int nn, int nq, const double* dNdx, const double* dOmega,
+                                    const double* ue, const double* a3 /* [3][P] unit directions */, double* fe, double* ke, double* sig,
+                                    double* tan, int64_t ncell, void* stream);
 /* total-Lagrangian counterpart for NeoHook / Yeoh / StVenant: F = I + Σ_a u_a ⊗ ∇N_a (∇N w.r.t. the reference configuration),
  * (Pᵀ, ∂Pᵀ∂F) through the trait route (src/traits.jl:67-77), fe[a][i] = Σ_q Σ_j P_ij ∇N_a[j] dΩ.  Pt (9 per point, i + 3j) and
  * dPdF (81 per point) may be NULL. */

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mm_hyper_energy": (C.c_int, [C.c_int, C.POINTER(MMHyper), _P, C.c_int, _P, _I64, C.c_int, _P]),
     "mm_cells_linear_elastic": (C.c_int, [C.POINTER(MMLinearElastic), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "mm_cells_plastic": (C.c_int, [C.POINTER(MMPlastic), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, _P]),
+    "mm_cells_transversely_isotropic": (C.c_int, [C.POINTER(MMTransverselyIsotropic), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "mm_cells_hyper": (C.c_int, [C.c_int, C.POINTER(MMHyper), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "mm_synth_uniform": (C.c_int, [_P, _I64, C.c_int, C.c_int, C.c_uint64, _P, _P, _P]),
     "mmh_hyper_ex": (C.c_int, [C.c_int, C.POINTER(MMHyper), _P, C.c_int, C.c_int, _P, _P, _I64, C.c_int]),

@@ -635,6 +635,12 @@ def cell_internal_forces(m, dNdx, dΩ, ue, state=None, tangent=False, stress=Fal
             check(lib.mm_cells_linear_elastic(ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(fe), _ptr(ke), _ptr(σ), _ptr(tan), ncell,
                                               _stream(ue)), "mm_cells_linear_elastic")
             return fe, (state if state is not None else LinearElasticState()), extras
+        if isinstance(m, TransverselyIsotropic):
+            if state is None or state.N != P or _LAYOUTS[state.layout] != _abi.MM_LAYOUT_SOA:
+                raise ValueError("cell_internal_forces(::TransverselyIsotropic): a 'soa' TransverselyIsotropicState over the %d quadrature points is required" % P)
+            check(lib.mm_cells_transversely_isotropic(ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(_prep(state.data)), _ptr(fe), _ptr(ke),
+                                                      _ptr(σ), _ptr(tan), ncell, _stream(ue)), "mm_cells_transversely_isotropic")
+            return fe, state, extras
         if isinstance(m, _Hyper):                       # total Lagrangian: F = I + Σ u ⊗ ∇N, stress = Pᵀ (9), tangent = ∂Pᵀ∂F (81)
             if stiffness:
                 raise NotImplementedError("cell_internal_forces(::%s): element stiffness not implemented (ask for tangent=True and assemble from ∂Pᵀ∂F)" % type(m).__name__)

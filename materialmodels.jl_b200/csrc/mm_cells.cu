@@ -55,7 +55,7 @@ struct CellArgs {
     int64_t ncell;
 };
 
-// MODEL 0: LinearElastic (stateless), 1: Plastic (14 state doubles)
+// MODEL 0: LinearElastic (stateless), 1: Plastic (14 state doubles), 2: TransverselyIsotropic (state = direction a3, read-only)
 // ∇N is parked in shared memory across the material update (3·NN doubles per thread would otherwise cost 2·3·NN registers on
 // top of the J2 solve: 255 registers and 15.2 ms for the hexahedron, against 168 and 10.7 ms this way); for NQ > 1 the Bᵀσ
 // contributions of the NQ lanes of a cell are summed through a padded shared-memory image: lane q adds up and stores components q, q+NQ, … (3·NN/NQ each) — one
@@ -67,7 +67,7 @@ struct CellArgs {
 #define MM_CELLS_MINBLOCKS 3
 #endif
 template <int MODEL, int NN, int NQ, int BS, bool WITH_KE>
-__global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_kernel(const ElasticK ke, const PlasticK kp, const CellArgs a) {
+__global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_kernel(const ElasticK ke, const PlasticK kp, const TransvIsoK kt, const CellArgs a) {
     static_assert(NQ == 1 || NQ == 2 || NQ == 4 || NQ == 8, "quadrature points per cell must be a power of two <= 8");
     static_assert(BS % 32 == 0 && 32 % NQ == 0, "a cell's points must share a warp");
     constexpr int NC = 3 * NN;
@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_ke
     acc.st_in = a.state_in; acc.st_out = a.state_out; acc.tan = a.tan; acc.sig_out = a.sig; acc.P = P; acc.i = i;
     if (MODEL == 0) {
         linear_elastic_point(ke, acc);
+    } else if (MODEL == 2) {
+        transviso_point(kt, acc);
     } else {
         int it = 0;
         const int flag = plastic_point(kp, acc, &it);
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_ke
 }
 
 template <int MODEL, int NN, int NQ, bool WITH_KE>
-int launch_cells_k(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
+int launch_cells_k(const ElasticK& ke, const PlasticK& kp, const TransvIsoK& kt, const CellArgs& a, cudaStream_t st) {
     constexpr int BS = 128;
     constexpr size_t fe_img = (NQ > 1) ? (size_t)3 * NN * (BS + 1) : 0, d_img = (NQ > 1 && WITH_KE) ? (size_t)38 * BS + 2 : 0;
     constexpr size_t smem = ((size_t)3 * NN * BS + fe_img + d_img) * sizeof(double);
@@ -242,12 +244,12 @@ int launch_cells_k(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cu
     if (blocks > 2147483647LL) return set_error(MM_ERR_ARG, "mm_cells: too many points for one launch");
     static SmemOptIn optin;
     if (int rc = ensure_smem(optin, cells_kernel<MODEL, NN, NQ, BS, WITH_KE>, smem, "mm_cells")) return rc;
-    cells_kernel<MODEL, NN, NQ, BS, WITH_KE><<<(unsigned)blocks, BS, smem, st>>>(ke, kp, a);
+    cells_kernel<MODEL, NN, NQ, BS, WITH_KE><<<(unsigned)blocks, BS, smem, st>>>(ke, kp, kt, a);
     return check_launch("mm_cells");
 }
 template <int MODEL, int NN, int NQ>
-int launch_cells(const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
-    return a.ke ? launch_cells_k<MODEL, NN, NQ, true>(ke, kp, a, st) : launch_cells_k<MODEL, NN, NQ, false>(ke, kp, a, st);
+int launch_cells(const ElasticK& ke, const PlasticK& kp, const TransvIsoK& kt, const CellArgs& a, cudaStream_t st) {
+    return a.ke ? launch_cells_k<MODEL, NN, NQ, true>(ke, kp, kt, a, st) : launch_cells_k<MODEL, NN, NQ, false>(ke, kp, kt, a, st);
 }
 
 // Total-Lagrangian counterpart: F = I + Σ_a u_a ⊗ ∇N_a (∇N w.r.t. the reference configuration), (Pᵀ, ∂Pᵀ∂F) from the hyperelastic
@@ -343,12 +345,12 @@ int dispatch_hyper_cells(int nn, int nq, const HyperK& k, const HyperCellArgs& a
 }
 
 template <int MODEL>
-int dispatch_cells(int nn, int nq, const ElasticK& ke, const PlasticK& kp, const CellArgs& a, cudaStream_t st) {
-    if (nn == 4 && nq == 1) return launch_cells<MODEL, 4, 1>(ke, kp, a, st);       // linear tetrahedron, 1-point rule
-    if (nn == 4 && nq == 4) return launch_cells<MODEL, 4, 4>(ke, kp, a, st);       // linear tetrahedron, 4-point rule
-    if (nn == 8 && nq == 8) return launch_cells<MODEL, 8, 8>(ke, kp, a, st);       // trilinear hexahedron, 2x2x2 Gauss
-    if (nn == 8 && nq == 1) return launch_cells<MODEL, 8, 1>(ke, kp, a, st);       // trilinear hexahedron, reduced integration
-    if (nn == 10 && nq == 4) return launch_cells<MODEL, 10, 4>(ke, kp, a, st);     // quadratic tetrahedron, 4-point rule
+int dispatch_cells(int nn, int nq, const ElasticK& ke, const PlasticK& kp, const TransvIsoK& kt, const CellArgs& a, cudaStream_t st) {
+    if (nn == 4 && nq == 1) return launch_cells<MODEL, 4, 1>(ke, kp, kt, a, st);       // linear tetrahedron, 1-point rule
+    if (nn == 4 && nq == 4) return launch_cells<MODEL, 4, 4>(ke, kp, kt, a, st);       // linear tetrahedron, 4-point rule
+    if (nn == 8 && nq == 8) return launch_cells<MODEL, 8, 8>(ke, kp, kt, a, st);       // trilinear hexahedron, 2x2x2 Gauss
+    if (nn == 8 && nq == 1) return launch_cells<MODEL, 8, 1>(ke, kp, kt, a, st);       // trilinear hexahedron, reduced integration
+    if (nn == 10 && nq == 4) return launch_cells<MODEL, 10, 4>(ke, kp, kt, a, st);     // quadratic tetrahedron, 4-point rule
     return set_error(MM_ERR_ARG, "mm_cells: unsupported element (nodes %d, quadrature points %d); supported: (4,1) (4,4) (8,1) (8,8) (10,4)", nn, nq);
 }
 
@@ -363,7 +365,8 @@ int mm_cells_linear_elastic(const MMLinearElastic* p, int nn, int nq, const doub
     if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !fe))) return set_error(MM_ERR_ARG, "mm_cells_linear_elastic: bad argument");
     CellArgs a{dNdx, dOmega, ue, nullptr, fe, ke_out, sig, tan, nullptr, nullptr, nullptr, nullptr, ncell};
     PlasticK kp{};
-    return dispatch_cells<0>(nn, nq, make_elastic_k(p->E, p->nu), kp, a, (cudaStream_t)stream);
+    TransvIsoK kt{};
+    return dispatch_cells<0>(nn, nq, make_elastic_k(p->E, p->nu), kp, kt, a, (cudaStream_t)stream);
 }
 
 int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, const double* state_in, double* fe,
@@ -373,7 +376,18 @@ int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, con
     CellArgs a{dNdx, dOmega, ue, state_in, fe, ke_out, sig, tan, state_out, flags, iters, n_fail, ncell};
     ElasticK ke = make_elastic_k(p->E, p->nu);
     PlasticK kp = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
-    return dispatch_cells<1>(nn, nq, ke, kp, a, (cudaStream_t)stream);
+    TransvIsoK kt{};
+    return dispatch_cells<1>(nn, nq, ke, kp, kt, a, (cudaStream_t)stream);
+}
+
+int mm_cells_transversely_isotropic(const MMTransverselyIsotropic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue,
+                                    const double* a3, double* fe, double* ke_out, double* sig, double* tan, int64_t ncell, void* stream) {
+    if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !a3 || !fe))) return set_error(MM_ERR_ARG, "mm_cells_transversely_isotropic: bad argument");
+    CellArgs a{dNdx, dOmega, ue, a3, fe, ke_out, sig, tan, nullptr, nullptr, nullptr, nullptr, ncell};
+    ElasticK ke{};
+    PlasticK kp{};
+    TransvIsoK kt{p->L_perp, p->L_par, p->M_par, p->G_perp, p->G_par};
+    return dispatch_cells<2>(nn, nq, ke, kp, kt, a, (cudaStream_t)stream);
 }
 
 int mm_cells_hyper(int model, const MMHyper* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, double* fe, double* Pt,

@@ -316,13 +316,15 @@ int mmo_wrapped_transviso(int kind, const MMTransverselyIsotropic* p, const doub
 
 // ---- the caller's quadrature loop around material_response (Ferrite.jl-style assemble_cell!) --------
 //   ε = symmetric(Σ_a u_a ⊗ ∇N_a);  σ, D, state_new = material_response(m, ε, state);  fe[a] += (σ ⋅ ∇N_a) dΩ
-// model: 0 LinearElastic (params = MMLinearElastic), 1 Plastic (params = MMPlastic).  Arrays as include/mmb200.h mm_cells_*.
+// model: 0 LinearElastic (params = MMLinearElastic), 1 Plastic (params = MMPlastic), 2 TransverselyIsotropic (params =
+// MMTransverselyIsotropic, state_in = a3[3][P]).  Arrays as include/mmb200.h mm_cells_*.
 int mmo_cells(int model, const void* params, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, const double* state_in,
               double* fe, double* ke, double* sig_out, double* tan_out, double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
               int64_t ncell) {
     const int64_t P = ncell * nq;
-    LinearElasticM le{}; PlasticM pm{};
+    LinearElasticM le{}; PlasticM pm{}; TransvIsoM tm{};
     if (model == 0) { const MMLinearElastic* p = (const MMLinearElastic*)params; le = make_linear_elastic(p->E, p->nu); }
+    else if (model == 2) { const MMTransverselyIsotropic* p = (const MMTransverselyIsotropic*)params; tm = TransvIsoM{p->L_perp, p->L_par, p->M_par, p->G_perp, p->G_par}; }
     else { const MMPlastic* p = (const MMPlastic*)params; pm = make_plastic(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf); }
     NewtonOpts o{opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000};
     int64_t fails = 0;
@@ -338,7 +340,11 @@ int mmo_cells(int model, const void* params, int nn, int nq, const double* dNdx,
             Sym2<double> eps, sig; Sym4<double> tan;
             for (int l = 0; l < 3; ++l) for (int k = l; k < 3; ++k) eps(k, l) = 0.5 * (G(k, l) + G(l, k));
             if (model == 0) material_response(le, eps, sig, tan);
-            else {
+            else if (model == 2) {
+                double a3[3];
+                for (int c = 0; c < 3; ++c) a3[c] = state_in[(int64_t)c * P + i];
+                material_response(tm, eps, a3, sig, tan);
+            } else {
                 PlasticState st, sn;
                 for (int c = 0; c < 6; ++c) st.ep.a[c] = state_in[(int64_t)c * P + i];
                 st.kappa = state_in[(int64_t)6 * P + i];

@@ -308,6 +308,10 @@ def cells(model, params, nn, nq, dNdx, dOmega, ue, state=None, want_tangent=True
     if model == 0:
         p = abi.MMLinearElastic(*params)
         st_in = st_out = flags = iters = None
+    elif model == 2:
+        p = params
+        st_in = np.ascontiguousarray(state, dtype=np.float64)          # a3 (3, P)
+        st_out = flags = iters = None
     else:
         p = params if isinstance(params, abi.MMPlastic) else abi.MMPlastic(*params)
         st_in = np.ascontiguousarray(state, dtype=np.float64); st_out = np.zeros((14, P))

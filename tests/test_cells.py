@@ -248,3 +248,56 @@ def test_gpu_hyper_cells_match_oracle(mm, cuda_lib, oracle, kind, ncell, name, m
     assert np.abs(fe.cpu().numpy() - r["fe"]).max() < H.RTOL * np.abs(r["fe"]).max()
     fe2, _, ex2 = mm.cell_internal_forces(m, dev(d), dev(o), dev(u))            # lean call: nothing but fe leaves the kernel
     assert ex2["stress"] is None and ex2["tangent"] is None and torch.equal(fe2, fe)
+
+
+# ---- TransverselyIsotropic through the cell loop (per-point direction a3) --------------------------------------------------------
+TI = dict(E_L=100e3, E_T=10e3, G_LT=5e3, nu_LT=0.4, nu_TT=0.3)
+
+
+def _ti_dirs(P, seed):
+    a = sy.host_uniform(P, 3, seed, [-1.0] * 3, [1.0] * 3)
+    a[:, np.linalg.norm(a, axis=0) < 1e-3] = np.array([[1.0], [0.0], [0.0]])
+    return np.ascontiguousarray(a / np.linalg.norm(a, axis=0))
+
+
+@pytest.mark.parametrize("kind", ["tet4", "hex8"])
+def test_oracle_transviso_cells(oracle, kind):
+    """per point equal to the point-wise TransverselyIsotropic oracle; fe = Kₑ uₑ with the oracle's own element stiffness"""
+    ncell = 30
+    X, nn, nq, (dNdx, dO) = random_cells(kind, ncell, 25)
+    P = ncell * nq
+    p = oracle.transviso_params(TI["E_L"], TI["E_T"], TI["G_LT"], TI["nu_LT"], TI["nu_TT"])
+    a3 = _ti_dirs(P, 26)
+    U = 1e-3 * (2 * np.random.default_rng(27).random((ncell, nn, 3)) - 1)
+    d, o, u = pack(dNdx, dO, U)
+    r = oracle.cells(2, p, nn, nq, d, o, u, a3, want_stiffness=True)
+    grad = np.einsum("cak,cqal->cqkl", U, dNdx).reshape(P, 3, 3)
+    eps = np.stack([0.5 * (grad[:, i, j] + grad[:, j, i]) for i, j in SLOTS])
+    s_ref, t_ref = oracle.transversely_isotropic(p, eps, a3)
+    assert H.rel_err(r["sig"], s_ref).max() < 1e-13 and H.rel_err(r["tan"], t_ref).max() < 1e-13
+    K = ke_of(r, ncell, nn)
+    assert np.allclose(np.einsum("crs,cs->cr", K, u.T), r["fe"].T, rtol=1e-11, atol=1e-12 * np.abs(r["fe"]).max())
+    assert np.allclose(K, K.transpose(0, 2, 1), rtol=1e-11, atol=1e-9)             # hyperelastic stiffness: major-symmetric
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,ncell", [("tet4", 20011), ("hex8", 5003)])
+def test_gpu_transviso_cells_match_oracle(mm, cuda_lib, oracle, kind, ncell):
+    import torch
+
+    X, nn, nq, (dNdx, dO) = random_cells(kind, ncell, 28)
+    P = ncell * nq
+    p = oracle.transviso_params(TI["E_L"], TI["E_T"], TI["G_LT"], TI["nu_LT"], TI["nu_TT"])
+    m = mm.TransverselyIsotropic(E_L=TI["E_L"], E_T=TI["E_T"], G_LT=TI["G_LT"], ν_LT=TI["nu_LT"], ν_TT=TI["nu_TT"])
+    a3 = _ti_dirs(P, 29)
+    U = 1e-3 * (2 * np.random.default_rng(30).random((ncell, nn, 3)) - 1)
+    d, o, u = pack(dNdx, dO, U)
+    r = oracle.cells(2, p, nn, nq, d, o, u, a3, want_stiffness=True)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    st = mm.initial_material_state(m, dev(a3))
+    fe, st2, ex = mm.cell_internal_forces(m, dev(d), dev(o), dev(u), st, tangent=True, stress=True, stiffness=True)
+    assert st2 is st
+    assert H.rel_err(ex["stress"].cpu().numpy(), r["sig"]).max() < H.RTOL and H.rel_err(ex["tangent"].cpu().numpy(), r["tan"]).max() < H.RTOL
+    assert np.abs(fe.cpu().numpy() - r["fe"]).max() < H.RTOL * np.abs(r["fe"]).max()
+    kscale = np.abs(r["ke"]).max(axis=0)
+    assert (np.abs(ex["stiffness"].cpu().numpy() - r["ke"]).max(axis=0) / kscale).max() < H.RTOL
