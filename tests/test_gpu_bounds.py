@@ -144,6 +144,12 @@ def test_no_entry_point_writes_out_of_bounds(mm, cuda_lib, N, lay, shift):
                                         None, ncell, None) == 0
             for g, n in ((fe, "fe"), (kk, "ke"), (s, "σ"), (t, "tangent"), (so, "state"), (fl, "flags"), (it, "iters")):
                 g.check("mm_cells_plastic(%d,%d) %s" % (nn, nq, n))
+            fe, kk, s, t = G(3 * nn * ncell), G(9 * nn * nn * ncell), G(6 * P), G(36 * P)
+            a3c = sy.host_uniform(P, 3, 101, [0.1] * 3, [1.0] * 3)
+            a3c /= np.linalg.norm(a3c, axis=0)
+            assert lib.mm_cells_transversely_isotropic(C.byref(tp), nn, nq, I(dN), I(dO), I(ue), I(a3c), fe.ptr, kk.ptr, s.ptr, t.ptr, ncell, None) == 0
+            for g, n in ((fe, "fe"), (kk, "ke"), (s, "σ"), (t, "tangent")):
+                g.check("mm_cells_transversely_isotropic(%d,%d) %s" % (nn, nq, n))
             fe, pt, dp = G(3 * nn * ncell), G(9 * P), G(81 * P)
             u2 = sy.host_uniform(ncell, 3 * nn, 75, [-0.03] * (3 * nn), [0.03] * (3 * nn))
             assert lib.mm_cells_hyper(abi.MM_YEOH, C.byref(hp), nn, nq, I(dN), I(dO), I(u2), fe.ptr, pt.ptr, dp.ptr, ncell, None) == 0
