@@ -28,6 +28,9 @@
  * never an abort: it is counted in *n_fail and flagged per point; the host mirror raises the
  * reference's error text ("Material model not converged. Could not find material state.",
  * src/Plastic.jl:157, CrystalViscoPlastic.jl:92) when the count is non-zero.
+ * Non-finite inputs follow the reference's branches (`if Φ <= 0 … else` sends a NaN Φ to the Newton branch, ⟨Φ⟩ = (Φ+|Φ|)/2
+ * propagates it): such points end flagged as failed, their neighbours are unaffected.  Iteration counts are reported as uint8
+ * and saturate at 255 (NLsolve's default cap is 1000).
  */
 #ifndef MMB200_H
 #define MMB200_H
