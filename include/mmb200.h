@@ -161,6 +161,11 @@ int mm_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const doub
 int mm_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red,
                        double* state_out, uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
                        const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
+/* ... and around CrystalViscoPlastic{12}: deps_red is the reduced strain INCREMENT, state 42 per point; `active` as mm_crystal plus
+ * bit 13 (0x2000) = the outer Newton did not converge; inner solve = the general pivoted path (functional, not tuned) */
+int mm_wrapped_crystal(int dim_kind, const MMCrystal* p, const double* deps_red, double dt, const double* state_in, double* sig_red,
+                       double* tan_red, double* state_out, uint16_t* active, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail,
+                       const MMNewtonOpts* opts, const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
 /* the same wrappers around TransverselyIsotropic (wrappers.jl is generic in the material); a3[3] per point is the state */
 int mm_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropic* p, const double* eps_red, const double* a3,
                                       double* sig_red, double* tan_red, uint8_t* outer_iters, int32_t* n_fail,
@@ -225,6 +230,9 @@ int mmh_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const dou
 int mmh_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red,
                         double* state_out, uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
                         const MMNewtonOpts* wrapper_opts, int64_t N, int layout);
+int mmh_wrapped_crystal(int dim_kind, const MMCrystal* p, const double* deps_red, double dt, const double* state_in, double* sig_red,
+                        double* tan_red, double* state_out, uint16_t* active, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail,
+                        const MMNewtonOpts* opts, const MMNewtonOpts* wrapper_opts, int64_t N, int layout);
 int mmh_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropic* p, const double* eps_red, const double* a3,
                                        double* sig_red, double* tan_red, uint8_t* outer_iters, int32_t* n_fail,
                                        const MMNewtonOpts* wrapper_opts, int64_t N, int layout);

@@ -14,6 +14,7 @@ MM_FLAG_PLASTIC = 0x01
 MM_FLAG_FAILED = 0x80
 MM_ACTIVE_FAILED = 0x8000
 MM_FLAG_WRAPPER_FAILED = 0x40
+MM_ACTIVE_WRAPPER_FAILED = 0x2000
 MM_DIM_UNIAXIAL_STRAIN, MM_DIM_PLANE_STRAIN, MM_DIM_UNIAXIAL_STRESS, MM_DIM_PLANE_STRESS, MM_DIM_SHELL_STRESS = 1, 2, 3, 4, 5
 
 
@@ -71,10 +72,14 @@ SIGNATURES = {
     "mm_wrapped_linear_elastic": (C.c_int, [C.c_int, C.POINTER(MMLinearElastic), _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int, _P]),
     "mm_wrapped_plastic": (C.c_int, [C.c_int, C.POINTER(MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), C.POINTER(MMNewtonOpts),
                                      _I64, C.c_int, _P]),
+    "mm_wrapped_crystal": (C.c_int, [C.c_int, C.POINTER(MMCrystal), _P, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts),
+                                     C.POINTER(MMNewtonOpts), _I64, C.c_int, _P]),
     "mm_wrapped_transversely_isotropic": (C.c_int, [C.c_int, C.POINTER(MMTransverselyIsotropic), _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int, _P]),
     "mmh_wrapped_linear_elastic": (C.c_int, [C.c_int, C.POINTER(MMLinearElastic), _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int]),
     "mmh_wrapped_plastic": (C.c_int, [C.c_int, C.POINTER(MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), C.POINTER(MMNewtonOpts),
                                       _I64, C.c_int]),
+    "mmh_wrapped_crystal": (C.c_int, [C.c_int, C.POINTER(MMCrystal), _P, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts),
+                                      C.POINTER(MMNewtonOpts), _I64, C.c_int]),
     "mmh_wrapped_transversely_isotropic": (C.c_int, [C.c_int, C.POINTER(MMTransverselyIsotropic), _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int]),
     "mm_transversely_isotropic_setup": (C.c_int, [C.c_double] * 5 + [C.POINTER(MMTransverselyIsotropic)]),
     "mm_transversely_isotropic": (C.c_int, [C.POINTER(MMTransverselyIsotropic), _P, _P, _P, _P, _I64, C.c_int, _P]),

@@ -459,9 +459,9 @@ def _response_xu(m, Δ, state, layout, want_tangent):
     return T, H, state
 
 
-def _response_wrapped(dim, m, Δε, state, options, layout, want_tangent):
+def _response_wrapped(dim, m, Δε, state, options, layout, want_tangent, Δt=None):
     """material_response(dim::AbstractDim, m, Δε, state, Δt; cache, options) — reference src/wrappers.jl:29-79
-    (LinearElastic, Plastic, TransverselyIsotropic; device arrays -> mm_wrapped_*, numpy arrays -> mmh_wrapped_*)."""
+    (LinearElastic, Plastic, TransverselyIsotropic, CrystalViscoPlastic; device arrays -> mm_wrapped_*, numpy arrays -> mmh_wrapped_*)."""
     kind = dim.KIND
     lib = load()
     nc = lib.mm_wrap_ncomp(kind)
@@ -470,10 +470,12 @@ def _response_wrapped(dim, m, Δε, state, options, layout, want_tangent):
         wtol = float(options.get("plane_stress_tol", options.get(":plane_stress_tol", wtol)))
         wmax = int(options.get("plane_stress_max_iter", options.get(":plane_stress_max_iter", wmax)))
     w = _abi.MMNewtonOpts(wtol, wmax, 0)
-    if isinstance(m, (Plastic, TransverselyIsotropic)):
+    if isinstance(m, (Plastic, TransverselyIsotropic, CrystalViscoPlastic)):
         if state is None:
             raise ValueError("material_response(dim, ::%s, Δε, state): state required" % type(m).__name__)
         layout = state.layout
+    if isinstance(m, CrystalViscoPlastic) and Δt is None:
+        raise ValueError("material_response(dim, ::CrystalViscoPlastic, Δε, state, Δt): Δt required")
     Δε = _prep(Δε)
     host = _is_host(Δε)
     N = _npoints(Δε, nc, layout)
@@ -516,8 +518,24 @@ def _response_wrapped(dim, m, Δε, state, options, layout, want_tangent):
                      ctypes.byref(o), ctypes.byref(w), N, lay, *tail), "mm_wrapped_plastic")
             new = PlasticState(sout, layout)
             new.flags, new.iters, new.n_fail = flags, iters, nfail
+        elif isinstance(m, CrystalViscoPlastic):
+            if N != state.N:
+                raise ValueError("strain has %d points, state has %d" % (N, state.N))
+            sin = _prep(state.data)
+            if _is_host(sin) != host:
+                raise ValueError("strain and state must live in the same place")
+            sout = _empty(_shape(42, N, layout), Δε)
+            active = _empty((N,), Δε, np.uint16 if host else _torch().int16)
+            iters = _empty((N,), Δε, u8)
+            o = _newton_opts(m, options)
+            fn = lib.mmh_wrapped_crystal if host else lib.mm_wrapped_crystal
+            check(fn(kind, ctypes.byref(m._c), _ptr(Δε), float(Δt), _ptr(sin), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(active), _ptr(iters), _ptr(oit),
+                     _ptr(nfail), ctypes.byref(o), ctypes.byref(w), N, lay, *tail), "mm_wrapped_crystal")
+            new = CrystalViscoPlasticState(sout, layout)
+            new.flags, new.iters, new.n_fail = active, iters, nfail
+            flags = ((active >> 8) & 0x20) << 1                       # MM_ACTIVE_WRAPPER_FAILED (bit 13) -> MM_FLAG_WRAPPER_FAILED (0x40)
         else:
-            raise NotImplementedError("dimension wrappers are implemented for LinearElastic, Plastic and TransverselyIsotropic")
+            raise NotImplementedError("dimension wrappers are implemented for LinearElastic, Plastic, TransverselyIsotropic and CrystalViscoPlastic")
     if hasattr(new, "__dict__"):
         new.outer_iters = oit
         new.n_fail = nfail
@@ -542,7 +560,8 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
         m = args.pop(0)
         strain = args.pop(0)
         state = args.pop(0) if args else None
-        return _response_wrapped(dim, m, strain, state, options, layout, tangent)
+        Δt = args.pop(0) if args else None
+        return _response_wrapped(dim, m, strain, state, options, layout, tangent, Δt)
     if args and isinstance(args[0], AbstractTangent):                       # src/traits.jl:91-107
         out_tangent = args.pop(0)
         m = args.pop(0)

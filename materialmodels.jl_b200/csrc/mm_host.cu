@@ -206,6 +206,21 @@ int mmh_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red,
     });
 }
 
+int mmh_wrapped_crystal(int dim_kind, const MMCrystal* p, const double* deps_red, double dt, const double* state_in, double* sig_red, double* tan_red,
+                        double* state_out, uint16_t* active, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
+                        const MMNewtonOpts* wrapper_opts, int64_t N, int layout) {
+    const int nc = mm_wrap_ncomp(dim_kind);
+    if (nc < 0) return nc;
+    if (!p || N < 0 || (N > 0 && (!deps_red || !state_in || !sig_red || !state_out))) return set_error(MM_ERR_ARG, "mmh_wrapped_crystal: bad argument");
+    Arr a[8] = {in_arr(deps_red, nc), in_arr(state_in, 42), out_arr(sig_red, nc), out_arr(tan_red, nc * nc), out_arr(state_out, 42),
+                out_arr(active, 1, 2, false), out_arr(iters, 1, 1, false), out_arr(outer_iters, 1, 1, false)};
+    return pipeline(a, 8, N, layout, n_fail, [&](int s, int64_t n, cudaStream_t st) {
+        return mm_wrapped_crystal(dim_kind, p, (const double*)a[0].d[s], dt, (const double*)a[1].d[s], (double*)a[2].d[s], (double*)a[3].d[s],
+                                  (double*)a[4].d[s], (uint16_t*)a[5].d[s], (uint8_t*)a[6].d[s], (uint8_t*)a[7].d[s], g_ws.d_fail, opts, wrapper_opts, n,
+                                  layout, st);
+    });
+}
+
 int mmh_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropic* p, const double* eps_red, const double* a3, double* sig_red,
                                        double* tan_red, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* wrapper_opts, int64_t N, int layout) {
     const int nc = mm_wrap_ncomp(dim_kind);

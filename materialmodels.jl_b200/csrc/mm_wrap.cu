@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include "../../include/mmb200.h"
 #include "mm_kernels.cuh"
+#include "mm_crystal_math.cuh"
 #include "mm_wrap_math.cuh"
 
 namespace mm {
@@ -87,6 +88,48 @@ int launch_wrapped_transviso(const MMTransverselyIsotropic* p, const double* eps
     return launch_points<WrappedTransvIsoOp<KIND>, 128, 128>(op, ptrs, N, layout, st, "mm_wrapped_transversely_isotropic");
 }
 
+// CrystalViscoPlastic under a dimension wrapper (wrappers.jl is generic in the material): the inner model is the structured Newton
+// (crystal_point_fast, per-system vectors in the thread's shared-memory scratch column) on the register accessor, with the general
+// pivoted 12x12 path as its fallback.  Functional, not tuned: every outer update is a full inner crystal solve including its tangent.  `active` bit 13 = outer Newton failed, bit 15 = inner solve failed.
+#define MM_ACTIVE_WRAPPER_FAILED 0x2000u
+template <int KIND> struct WrappedCrystalOp {
+    static constexpr int NIN = 2, NOUT = 3, SCRATCH = MM_CRYSTAL_SCRATCH;
+    __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? wrap_nc(KIND) : 42; }
+    __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? wrap_nc(KIND) : (a == 1 ? wrap_nc(KIND) * wrap_nc(KIND) : 42); }
+    CrystalK k;
+    double tol; int max_iter;
+    uint16_t* active;
+    uint8_t* iters;
+    uint8_t* outer_iters;
+    int32_t* n_fail;
+    template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch& scr) const {
+        int oit = 0, iit = 0;
+        unsigned mask = 0;
+        const int flag = wrapped_point<KIND, 42>(
+            [&](RegIO<42>& io, int* it) {
+                bool fb = !k.h_struct;
+                if (!fb) mask = (k.b_h != 0.0) ? crystal_point_fast<true>(k, io, scr, it, &fb) : crystal_point_fast<false>(k, io, scr, it, &fb);
+                if (fb) mask = crystal_point(k, io, it);               // general pivoted path, Jacobian in local memory (rare)
+                return (mask & MM_ACTIVE_FAILED) ? 0x80 : 0;
+            },
+            acc, tol, max_iter, &oit, &iit);
+        if (flag & 0x40) mask |= MM_ACTIVE_WRAPPER_FAILED;
+        if (active) active[i] = (uint16_t)mask;
+        if (iters) iters[i] = (uint8_t)(iit > 255 ? 255 : iit);
+        if (outer_iters) outer_iters[i] = (uint8_t)oit;
+        if ((flag & 0xC0) && n_fail) atomicAdd(n_fail, 1);
+    }
+};
+template <int KIND>
+int launch_wrapped_crystal(const CrystalK& k, const double* deps, const double* sin, double* sig, double* tan, double* sout, uint16_t* active, uint8_t* iters,
+                           uint8_t* oit, int32_t* n_fail, const MMNewtonOpts* w, int64_t N, int layout, cudaStream_t st) {
+    WrappedCrystalOp<KIND> op;
+    op.k = k; op.tol = w ? w->tol : 1e-8; op.max_iter = w ? w->max_iter : 10;
+    op.active = active; op.iters = iters; op.outer_iters = oit; op.n_fail = n_fail;
+    Ptrs<2, 3> ptrs; ptrs.in[0] = deps; ptrs.in[1] = sin; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = sout;
+    return launch_points<WrappedCrystalOp<KIND>, 64, 32>(op, ptrs, N, layout, st, "mm_wrapped_crystal");
+}
+
 template <int KIND>
 int launch_wrapped_elastic(const MMLinearElastic* p, const double* eps, double* sig, double* tan, uint8_t* oit, int32_t* n_fail, const MMNewtonOpts* w,
                            int64_t N, int layout, cudaStream_t st) {
@@ -145,6 +188,27 @@ int mm_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropi
     }
 #undef MM_WT
     return set_error(MM_ERR_ARG, "mm_wrapped_transversely_isotropic: unknown dim_kind %d", dim_kind);
+}
+
+int mm_wrapped_crystal(int dim_kind, const MMCrystal* p, const double* deps_red, double dt, const double* state_in, double* sig_red, double* tan_red,
+                       double* state_out, uint16_t* active, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
+                       const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream) {
+    if (!p || N < 0 || (N > 0 && (!deps_red || !state_in || !sig_red || !state_out))) return set_error(MM_ERR_ARG, "mm_wrapped_crystal: bad argument");
+    if (p->nslip != MM_NSLIP) return set_error(MM_ERR_ARG, "mm_wrapped_crystal: nslip must be %d (got %d)", MM_NSLIP, p->nslip);
+    CrystalK k;
+    make_crystal_k(k, p->E, p->nu, p->tau_y, p->H_kin, p->alpha_inf, p->t_star, p->sigma_c, p->m, p->MS, p->H, dt, opts ? opts->tol : 1e-8,
+                   opts ? opts->max_iter : 100);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MM_WC(K) return launch_wrapped_crystal<K>(k, deps_red, state_in, sig_red, tan_red, state_out, active, iters, outer_iters, n_fail, wrapper_opts, N, layout, st)
+    switch (dim_kind) {
+        case MM_DIM_UNIAXIAL_STRAIN: MM_WC(WRAP_UNIAXIAL_STRAIN);
+        case MM_DIM_PLANE_STRAIN: MM_WC(WRAP_PLANE_STRAIN);
+        case MM_DIM_UNIAXIAL_STRESS: MM_WC(WRAP_UNIAXIAL_STRESS);
+        case MM_DIM_PLANE_STRESS: MM_WC(WRAP_PLANE_STRESS);
+        case MM_DIM_SHELL_STRESS: MM_WC(WRAP_SHELL_STRESS);
+    }
+#undef MM_WC
+    return set_error(MM_ERR_ARG, "mm_wrapped_crystal: unknown dim_kind %d", dim_kind);
 }
 
 int mm_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red, double* state_out,

@@ -314,6 +314,49 @@ int mmo_wrapped_transviso(int kind, const MMTransverselyIsotropic* p, const doub
     return 0;
 }
 
+int mmo_wrapped_crystal(int kind, const MMCrystal* p, const double* deps_red, double dt, const double* state_in, double* sig_red, double* tan_red,
+                        double* state_out, uint16_t* active, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
+                        const MMNewtonOpts* wopts, int64_t N, int layout) {
+    if (p->nslip != 12) return MM_ERR_ARG;
+    CrystalM<12> m;
+    m.E = p->E; m.nu = p->nu; m.tau_y = p->tau_y; m.H_iso = p->H_iso; m.H_kin = p->H_kin; m.q = p->q; m.alpha_inf = p->alpha_inf;
+    m.t_star = p->t_star; m.sigma_c = p->sigma_c; m.m = p->m;
+    m.Ee = elastic_tangent_3D(p->E, p->nu);
+    for (int i = 0; i < 12; ++i) for (int j = 0; j < 12; ++j) m.H[i + 12 * j] = p->H[i][j];
+    for (int s = 0; s < 12; ++s) for (int k = 0; k < 9; ++k) m.MS[s].a[k] = p->MS[s][k];
+    const double tol = opts ? opts->tol : 1e-8; const int max_iter = opts ? opts->max_iter : 100;
+    const double wtol = wopts ? wopts->tol : 1e-8; const int wmax = wopts ? wopts->max_iter : 10;
+    const int nc = wrap_ncomp(kind);
+    View ve = V(deps_red, N, nc, layout), vi = V(state_in, N, 42, layout), vs = V(sig_red, N, nc, layout), vt = V(tan_red, N, nc * nc, layout),
+         vo = V(state_out, N, 42, layout);
+    int64_t fails = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : fails)
+    for (int64_t i = 0; i < N; ++i) {
+        double e[6], s[6] = {0, 0, 0, 0, 0, 0}, t[36]; int oit = 0;
+        for (int c = 0; c < 36; ++c) t[c] = 0;
+        for (int c = 0; c < nc; ++c) e[c] = ve.at(i, c);
+        CrystalState<12> st, sn;
+        for (int c = 0; c < 6; ++c) st.sigma.a[c] = vi.at(i, c);
+        for (int k = 0; k < 12; ++k) { st.kappa[k] = vi.at(i, 6 + k); st.alpha[k] = vi.at(i, 18 + k); st.mu[k] = vi.at(i, 30 + k); }
+        sn = st;
+        unsigned act = 0; int it = 0;
+        auto inner = [&](const Sym2<double>& eps3, Sym2<double>& sig, Sym4<double>& tan) { return material_response<12>(m, eps3, st, dt, tol, max_iter, sig, tan, sn, act, it); };
+        int status = wrapped_response(kind, inner, e, wtol, wmax, s, t, oit);
+        if (status == 1) act |= MM_ACTIVE_FAILED;
+        if (status == 2) act |= 0x2000u;
+        if (status) ++fails;
+        for (int c = 0; c < nc; ++c) vs.at(i, c) = s[c];
+        if (tan_red) for (int c = 0; c < nc * nc; ++c) vt.at(i, c) = t[c];
+        for (int c = 0; c < 6; ++c) vo.at(i, c) = sn.sigma.a[c];
+        for (int k = 0; k < 12; ++k) { vo.at(i, 6 + k) = sn.kappa[k]; vo.at(i, 18 + k) = sn.alpha[k]; vo.at(i, 30 + k) = sn.mu[k]; }
+        if (active) active[i] = (uint16_t)act;
+        if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if (outer_iters) outer_iters[i] = (uint8_t)oit;
+    }
+    if (n_fail) *n_fail += (int32_t)fails;
+    return 0;
+}
+
 // ---- the caller's quadrature loop around material_response (Ferrite.jl-style assemble_cell!) --------
 //   ε = symmetric(Σ_a u_a ⊗ ∇N_a);  σ, D, state_new = material_response(m, ε, state);  fe[a] += (σ ⋅ ∇N_a) dΩ
 // model: 0 LinearElastic (params = MMLinearElastic), 1 Plastic (params = MMPlastic), 2 TransverselyIsotropic (params =

@@ -42,6 +42,8 @@ _SIG = {
     "mmo_wrapped_transviso": (C.c_int, [C.c_int, C.POINTER(abi.MMTransverselyIsotropic), _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
     "mmo_cells": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts), _I64]),
     "mmo_cells_hyper": (C.c_int, [C.c_int, C.POINTER(abi.MMHyper), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _I64]),
+    "mmo_wrapped_crystal": (C.c_int, [C.c_int, C.POINTER(abi.MMCrystal), _P, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(abi.MMNewtonOpts),
+                                      C.POINTER(abi.MMNewtonOpts), _I64, C.c_int]),
     "mmo_transviso_setup": (C.c_int, [C.c_double] * 5 + [C.POINTER(abi.MMTransverselyIsotropic)]),
     "mmo_transversely_isotropic": (C.c_int, [C.POINTER(abi.MMTransverselyIsotropic), _P, _P, _P, _P, _I64, C.c_int]),
     "mmo_strain_energy_batch": (C.c_int, [C.c_int, _P, _P, C.c_int, _P, _I64, C.c_int]),
@@ -335,3 +337,17 @@ def cells_hyper(model, params, nn, nq, dNdx, dOmega, ue, want_tangent=True):
     rc = lib().mmo_cells_hyper(model, C.byref(p), nn, nq, _ptr(dNdx), _ptr(dOmega), _ptr(ue), _ptr(fe), _ptr(Pt), _ptr(dP), ncell)
     assert rc == 0
     return dict(fe=fe, Pt=Pt, dPdF=dP)
+
+
+def wrapped_crystal(kind, p, deps_red, state, dt=1.0, layout=SOA, tol=1e-8, max_iter=100, wtol=1e-8, wmax_iter=10):
+    nc = WRAP_NCOMP[kind]
+    deps_red, N = _n(deps_red, layout)
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    sig, tan, st = _alloc(nc, N, layout), _alloc(nc * nc, N, layout), _alloc(42, N, layout)
+    active, iters, oit = np.zeros(N, np.uint16), np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+    nfail = np.zeros(1, np.int32)
+    o, w = abi.MMNewtonOpts(tol, max_iter, 0), abi.MMNewtonOpts(wtol, wmax_iter, 0)
+    rc = lib().mmo_wrapped_crystal(kind, C.byref(p), _ptr(deps_red), dt, _ptr(state), _ptr(sig), _ptr(tan), _ptr(st), _ptr(active), _ptr(iters), _ptr(oit),
+                                   _ptr(nfail), C.byref(o), C.byref(w), N, layout)
+    assert rc == 0
+    return dict(sig=sig, tan=tan, state=st, active=active, iters=iters, outer_iters=oit, n_fail=int(nfail[0]))

@@ -104,6 +104,38 @@ extern "C" int twin_wrapped_plastic(int kind, const MMPlastic* p, const double* 
     }
     return 0;
 }
+template <int KIND> static void twin_wrapped_crystal_k(const mm::CrystalK& k, const double* deps, const double* sin, double* sig, double* tan, double* sout,
+                                                       uint16_t* active, uint8_t* iters, uint8_t* oiters, double wtol, int wmax, int64_t N) {
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<2, 3> a{{deps, sin}, {sig, tan, sout}, N, i};
+        int oit = 0, iit = 0; unsigned mask = 0;
+        HostScratch scr;
+        int f = mm::wrapped_point<KIND, 42>(
+            [&](mm::RegIO<42>& io, int* it) {
+                bool fb = !k.h_struct;
+                if (!fb) mask = (k.b_h != 0.0) ? mm::crystal_point_fast<true>(k, io, scr, it, &fb) : mm::crystal_point_fast<false>(k, io, scr, it, &fb);
+                if (fb) mask = mm::crystal_point(k, io, it);
+                return (mask & 0x8000u) ? 0x80 : 0;
+            },
+            a, wtol, wmax, &oit, &iit);
+        if (f & 0x40) mask |= 0x2000u;
+        active[i] = (uint16_t)mask; iters[i] = (uint8_t)(iit > 255 ? 255 : iit); oiters[i] = (uint8_t)oit;
+    }
+}
+extern "C" int twin_wrapped_crystal(int kind, const MMCrystal* p, const double* deps, double dt, const double* sin, double* sig, double* tan, double* sout,
+                         uint16_t* active, uint8_t* iters, uint8_t* oiters, double tol, int max_iter, double wtol, int wmax, int64_t N) {
+    mm::CrystalK k;
+    mm::make_crystal_k(k, p->E, p->nu, p->tau_y, p->H_kin, p->alpha_inf, p->t_star, p->sigma_c, p->m, p->MS, p->H, dt, tol, max_iter);
+    switch (kind) {
+        case 1: twin_wrapped_crystal_k<1>(k, deps, sin, sig, tan, sout, active, iters, oiters, wtol, wmax, N); break;
+        case 2: twin_wrapped_crystal_k<2>(k, deps, sin, sig, tan, sout, active, iters, oiters, wtol, wmax, N); break;
+        case 3: twin_wrapped_crystal_k<3>(k, deps, sin, sig, tan, sout, active, iters, oiters, wtol, wmax, N); break;
+        case 4: twin_wrapped_crystal_k<4>(k, deps, sin, sig, tan, sout, active, iters, oiters, wtol, wmax, N); break;
+        case 5: twin_wrapped_crystal_k<5>(k, deps, sin, sig, tan, sout, active, iters, oiters, wtol, wmax, N); break;
+        default: return -1;
+    }
+    return 0;
+}
 template <int KIND> static void twin_wrapped_elastic_k(const mm::ElasticK& k, const double* eps, double* sig, double* tan, uint8_t* oiters, int64_t N) {
     for (int64_t i = 0; i < N; ++i) {
         HostAcc<1, 2> a{{eps}, {sig, tan}, N, i};

@@ -131,6 +131,14 @@ def test_no_entry_point_writes_out_of_bounds(mm, cuda_lib, N, lay, shift):
         assert lib.mm_crystal(C.byref(cm._c), I(de), 1.0, I(np.zeros((42, N))), s.ptr, t.ptr, so.ptr, ac.ptr, it.ptr, pn, None, N, lay, None) == 0
         for g, n in ((s, "σ"), (t, "tangent"), (so, "state"), (it, "iters"), (ac, "active")):
             g.check("mm_crystal(q=%g) %s" % (q, n))
+    # wrapped crystal (general inner path, Jacobian in the shared-memory scratch column)
+    for kind, ncr, amp in ((abi.MM_DIM_PLANE_STRESS, 3, 4e-3), (abi.MM_DIM_UNIAXIAL_STRESS, 1, 6e-3)):
+        er = sy.host_uniform(N, ncr, 33, [-amp] * ncr, [amp] * ncr)
+        s, t, so, ac, it, oi = G(ncr * N), G(ncr * ncr * N), G(42 * N), G(N, i16), G(N, u8), G(N, u8)
+        assert lib.mm_wrapped_crystal(kind, C.byref(cm._c), I(er), 1.0, I(np.zeros((42, N))), s.ptr, t.ptr, so.ptr, ac.ptr, it.ptr, oi.ptr, pn, None, None, N,
+                                      lay, None) == 0
+        for g, n in ((s, "σ"), (t, "tangent"), (so, "state"), (it, "iters"), (ac, "active"), (oi, "outer iters")):
+            g.check("mm_wrapped_crystal[%d] %s" % (kind, n))
     # fused cell kernels (SoA only): ncell chosen so that P = ncell*nq is ragged against the 128-thread blocks
     if lay == 0:
         for nn, nq in ((4, 1), (4, 4), (8, 1), (8, 8), (10, 4)):

@@ -91,6 +91,8 @@ def test_empty_batches(mm, torch):
     cm = make_crystal(mm)
     s, t, cs = mm.material_response(cm, z(6), mm.initial_material_state(cm, 0), 1.0)
     assert s.shape == (6, 0) and cs.data.shape == (42, 0)
+    s, t, cs = mm.material_response(mm.PlaneStress(), cm, z(3), mm.initial_material_state(cm, 0), 1.0)
+    assert s.shape == (3, 0) and t.shape == (9, 0) and cs.data.shape == (42, 0)
     for lay in ("soa", "aos"):
         e = torch.zeros((6, 0) if lay == "soa" else (0, 6), dtype=torch.float64, device="cuda")
         assert mm.material_response(m, e, layout=lay)[0].numel() == 0

@@ -251,3 +251,98 @@ def test_gpu_wrapped_transviso_and_host_buffer_forms(mm, cuda_lib, oracle, kind,
         assert np.array_equal(sh, sd.cpu().numpy()) and np.array_equal(th, td.cpu().numpy())
     finally:
         cuda_lib.mmh_set_chunk_points(old)
+
+
+# ---- wrappers around CrystalViscoPlastic (the last material of the generic wrappers.jl) ---------------------------------
+XTAL_AMPL = {1: 6e-3, 2: 4e-3, 3: 6e-3, 4: 4e-3, 5: 3e-3}
+
+
+def _xtal_compare(r, active, iters, oit, sig, tan, state, kind):
+    """wrapped crystal vs oracle: bit-exact masks / iteration counts and 1e-12 values away from the reference Newton's chaotic
+    trajectories (helpers.crystal_compare explains those); the outer loop multiplies inner solves, so `iters` (the LAST inner
+    solve's count) >= CHAOTIC_ITERS or any failure marks the point as chaotic."""
+    active = np.asarray(active).view(np.uint16)
+    chaotic = ((r["active"] & 0xA000) != 0) | (r["iters"] >= H.CHAOTIC_ITERS) | ((active & 0xA000) != 0) | (np.asarray(iters) >= H.CHAOTIC_ITERS)
+    ok = ~chaotic
+    assert chaotic.mean() < 0.03, chaotic.mean()
+    assert np.array_equal(active[ok], r["active"][ok])
+    assert np.array_equal(np.asarray(iters)[ok], r["iters"][ok]) and np.array_equal(np.asarray(oit)[ok], r["outer_iters"][ok])
+    assert sig_err(sig[:, ok], r["sig"][:, ok]) < H.RTOL
+    assert H.rel_err(tan[:, ok], r["tan"][:, ok]).max() < max(TAN_TOL[kind], 1e-10)
+    assert H.rel_err(state[:, ok], r["state"][:, ok]).max() < H.RTOL
+    return int(chaotic.sum())
+
+
+def test_oracle_wrapped_crystal_properties(oracle):
+    """PlaneStress / UniaxialStress around the crystal: out-of-plane stresses of the stored 3D state vanish (wrappers.jl:57-61), and a
+    UniaxialStrain step equals the 3D model at ε = (ε11, 0, …) (wrappers.jl:29-35)."""
+    p = H.crystal_c(oracle)
+    N = 300
+    for kind, oop in ((4, [2, 4, 5]), (3, [1, 2, 3, 4, 5]), (5, [5])):
+        e = sy.host_uniform(N, NC[kind], 50 + kind, -XTAL_AMPL[kind], XTAL_AMPL[kind])
+        r = oracle.wrapped_crystal(kind, p, e, np.zeros((42, N)))
+        good = (r["active"] & 0xA000) == 0
+        assert good.mean() > 0.97 and (r["active"][good] & 0xFFF).astype(bool).mean() > 0.2
+        assert np.abs(r["state"][oop][:, good]).max() < 1e-8 * 50      # tol · a stress scale
+    e = sy.host_uniform(N, 1, 60, -XTAL_AMPL[1], XTAL_AMPL[1])
+    r = oracle.wrapped_crystal(1, p, e, np.zeros((42, N)))
+    e3 = np.zeros((6, N)); e3[0] = e[0]
+    r3 = oracle.crystal(p, e3, np.zeros((42, N)))
+    assert np.array_equal(r["sig"][0], r3["sig"][0]) and np.array_equal(r["state"], r3["state"]) and np.array_equal(r["tan"][0], r3["tan"][0])
+    assert np.array_equal(r["active"], r3["active"]) and np.array_equal(r["iters"], r3["iters"])
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_twin_wrapped_crystal_matches_oracle(oracle, kind):
+    tw = H.hosttwin()
+    p = H.crystal_c(oracle)
+    N = 400
+    nc = NC[kind]
+    st = np.zeros((42, N))
+    nch = 0
+    for step in range(2):
+        e = sy.host_uniform(N, nc, 70 + 10 * kind + step, -XTAL_AMPL[kind], XTAL_AMPL[kind])
+        r = oracle.wrapped_crystal(kind, p, e, st)
+        sig, tan, so = np.zeros((nc, N)), np.zeros((nc * nc, N)), np.zeros((42, N))
+        act, it, oi = np.zeros(N, np.uint16), np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+        assert tw.twin_wrapped_crystal(kind, C.byref(p), H.P(e), C.c_double(1.0), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(act), H.P(it), H.P(oi),
+                                       C.c_double(1e-8), 100, C.c_double(1e-8), 10, C.c_int64(N)) == 0
+        nch += _xtal_compare(r, act, it, oi, sig, tan, so, kind)
+        good = (r["active"] & 0xA000) == 0
+        st = np.where(good[None, :], r["state"], st)
+    print("wrapped crystal kind %d: %d chaotic / failed of %d" % (kind, nch, 2 * N))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lname,lay", [("soa", 0), ("aos", 1)])
+@pytest.mark.parametrize("kind", KINDS)
+def test_gpu_wrapped_crystal(mm, cuda_lib, oracle, kind, lname, lay):
+    import torch
+    from test_gpu_parity import make_crystal
+    dim = {1: mm.UniaxialStrain(), 2: mm.PlaneStrain(), 3: mm.UniaxialStress(), 4: mm.PlaneStress(), 5: mm.ShellStress()}[kind]
+    m = make_crystal(mm)
+    p = H.crystal_c(oracle)
+    N = 3001
+    nc = NC[kind]
+    T = (lambda a: a) if lay == 0 else (lambda a: np.ascontiguousarray(a.T))
+    st = mm.initial_material_state(m, N, layout=lname)
+    st_ref = np.zeros((42, N))
+    for step in range(2):
+        e = sy.host_uniform(N, nc, 170 + 10 * kind + step, -XTAL_AMPL[kind], XTAL_AMPL[kind])
+        r = oracle.wrapped_crystal(kind, p, e, st_ref)
+        s, t, new = mm.material_response(dim, m, torch.from_numpy(T(e)).cuda(), st, 1.0, options={"defer_check": True})
+        g = lambda x: x.cpu().numpy() if lay == 0 else np.ascontiguousarray(x.cpu().numpy().T)
+        _xtal_compare(r, new.flags.cpu().numpy(), new.iters.cpu().numpy(), new.outer_iters.cpu().numpy(), g(s), g(t), g(new.data), kind)
+        # host-buffer form: the same kernels -> identical bits
+        sth = mm.CrystalViscoPlasticState(st.data.cpu().numpy(), lname)
+        sh, th, nh = mm.material_response(dim, m, T(e), sth, 1.0, options={"defer_check": True})
+        assert np.array_equal(sh, s.cpu().numpy()) and np.array_equal(th, t.cpu().numpy()) and np.array_equal(nh.data, new.data.cpu().numpy())
+        assert np.array_equal(nh.flags, new.flags.cpu().numpy().view(np.uint16)) and int(nh.n_fail[0]) == int(new.n_fail.item())
+        good = (r["active"] & 0xA000) == 0
+        st_ref = np.where(good[None, :], r["state"], st_ref)
+        keep = torch.from_numpy(good).cuda()
+        data = torch.where(keep[None, :] if lay == 0 else keep[:, None], new.data, st.data)
+        st = mm.CrystalViscoPlasticState(data, lname)
+        st_ref_dev = g(data)
+        assert H.rel_err(st_ref_dev[:, good], st_ref[:, good]).max() < H.RTOL
+        st_ref = st_ref_dev                                                    # keep both sides on the same state bits

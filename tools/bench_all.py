@@ -230,6 +230,19 @@ def main():
             del e
         del a3, st
         torch.cuda.empty_cache()
+    if want("wrapxtal"):
+        N = int(2e6 * S)
+        m = mm.CrystalViscoPlastic(slipsystems=mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES), **sy.CRYSTAL_PARAMS)
+        for dim, nc, amp in ((mm.PlaneStress(), 3, 4e-3), (mm.UniaxialStress(), 1, 6e-3)):
+            e = mm.synth_uniform(N, nc, 51, -amp, amp)
+            st0 = mm.initial_material_state(m, N)
+            med, mn = timeit(lambda: mm.material_response(dim, m, e, st0, 1.0, options={"defer_check": True}), max(a.reps // 3, 2), warm=1)
+            _, _, st1 = mm.material_response(dim, m, e, st0, 1.0, options={"defer_check": True})
+            report("crystal %s soa" % type(dim).__name__, N, 8 * (nc + 42 + nc + nc * nc + 42) + 4, med, mn,
+                   {"active_fraction": round(((st1.flags & 0xFFF) != 0).float().mean().item(), 3), "mean_outer_iters": round(st1.outer_iters.float().mean().item(), 2),
+                    "n_fail": int(st1.n_fail.item())})
+            del e, st0, st1
+            torch.cuda.empty_cache()
     if want("xtalvariants"):
         # crystal plasticity off the headline configuration: BCC table (the reference's, with two non-slip 'systems' -> fix-up points)
         # and cross hardening q != 0 (Sherman-Morrison path)
