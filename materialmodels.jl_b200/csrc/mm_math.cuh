@@ -345,12 +345,12 @@ template <int MODEL, int KIND, int TAN, class Acc> MM_HD void hyper_point_ex(con
         const double m01 = C[2] * C[4] - C[1] * C[5];
         const double m02 = C[1] * C[4] - C[2] * C[3];
         const double det = C[0] * m00 + C[1] * m01 + C[2] * m02;
-        const double idet = 1.0 / det;
+        const double idet = fast_rcp(det);
         A[0] = m00 * idet; A[1] = m01 * idet; A[2] = m02 * idet;
         A[3] = (C[0] * C[5] - C[2] * C[2]) * idet;
         A[4] = (C[1] * C[2] - C[0] * C[4]) * idet;
         A[5] = (C[0] * C[3] - C[1] * C[1]) * idet;
-        const double lnJ = log(sqrt(det));
+        const double lnJ = 0.5 * log(det);          // ln J = ln √det C, without the square root
         g = 0.0;
         if (MODEL == 0) {   // NeoHook: S = μ (I − C⁻¹) + λ ln J C⁻¹
             a = k.mu; b = k.lambda * lnJ - k.mu;
@@ -433,35 +433,38 @@ template <int MODEL, int KIND, class Acc> MM_HD void hyper_point(const HyperK& k
 // of the potential at :86 (the reference differentiates it with nested duals; closed forms here).
 // in<0> = Δ(dim), last component normal;  out<0> = T(dim), out<1> = dTdΔ(dim², column-major, optional)
 // =================================================================================================
-struct XuK { double Phi_n, delta_n, delta_t, q, r; };
+struct XuK { double Phi_n, delta_n, delta_t, q, r, idn, idt2, A0, B0; };
 MM_HD XuK make_xu_k(double Phi_n, double Phi_t, double delta_n, double delta_t, double Delta_n_star) {
     XuK k; k.Phi_n = Phi_n; k.delta_n = delta_n; k.delta_t = delta_t;
     k.q = Phi_t / Phi_n;              // :83
     k.r = Delta_n_star / delta_n;     // :84
+    // per-material constants of the potential, hoisted out of the per-point code (FP64 divisions cost ~40 instructions each)
+    k.idn = 1.0 / delta_n; k.idt2 = 1.0 / (delta_t * delta_t);
+    k.A0 = (1 - k.q) / (k.r - 1); k.B0 = (k.r - k.q) / (k.r - 1);
     return k;
 }
 template <int DIM, class Acc> MM_HD void xu_point(const XuK& k, Acc& acc) {
     double D[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) D[c] = acc.template in<0>(c);
-    const double a = D[DIM - 1] / k.delta_n;
+    const double a = D[DIM - 1] * k.idn;
     double t2 = 0.0;
 #pragma unroll
     for (int c = 0; c < DIM - 1; ++c) t2 += D[c] * D[c];
-    const double idt2 = 1.0 / (k.delta_t * k.delta_t);
+    const double idt2 = k.idt2;
     const double E1 = exp(-a), E2 = exp(-t2 * idt2);
-    const double A0 = (1 - k.q) / (k.r - 1), B0 = (k.r - k.q) / (k.r - 1);
+    const double A0 = k.A0, B0 = k.B0;
     const double f = (1 - k.r + a) * A0, gq = k.q + B0 * a;
     const double pe = k.Phi_n * E1;
     // gradient
-    const double Tn = pe / k.delta_n * ((A0 - f) + (gq - B0) * E2);
+    const double Tn = pe * k.idn * ((A0 - f) + (gq - B0) * E2);
     const double ct = 2.0 * pe * gq * E2 * idt2;     // T_t = ct Δ_t
 #pragma unroll
     for (int c = 0; c < DIM - 1; ++c) acc.template out<0>(c, ct * D[c]);
     acc.template out<0>(DIM - 1, Tn);
     if (acc.template has_out<1>()) {
-        const double Hnn = pe / (k.delta_n * k.delta_n) * ((f - 2.0 * A0) + (2.0 * B0 - gq) * E2);
-        const double cnt = -2.0 * pe / k.delta_n * (gq - B0) * E2 * idt2;   // H_nt = cnt Δ_t
+        const double Hnn = pe * (k.idn * k.idn) * ((f - 2.0 * A0) + (2.0 * B0 - gq) * E2);
+        const double cnt = -2.0 * pe * k.idn * (gq - B0) * E2 * idt2;   // H_nt = cnt Δ_t
 #pragma unroll
         for (int j = 0; j < DIM - 1; ++j) {
 #pragma unroll
@@ -565,7 +568,7 @@ template <int MODEL, int KIND, class Acc> MM_HD void hyper_energy_point(const Hy
         psi = 0.5 * k.lambda * (trE * trE) + k.mu * ddot6(E, E);
     } else {
         const double det = C[0] * (C[3] * C[5] - C[4] * C[4]) + C[1] * (C[2] * C[4] - C[1] * C[5]) + C[2] * (C[1] * C[4] - C[2] * C[3]);
-        const double lJ = log(sqrt(det)), i3 = tr6(C) - 3.0;
+        const double lJ = 0.5 * log(det), i3 = tr6(C) - 3.0;
         psi = k.mu / 2 * i3 - k.mu * lJ + k.lambda / 2 * (lJ * lJ);
         if (MODEL == 1) psi += k.c2 * (i3 * i3) + k.c3 * (i3 * i3 * i3);
     }

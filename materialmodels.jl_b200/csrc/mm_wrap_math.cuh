@@ -47,6 +47,7 @@ template <int NS> struct RegIO {
 // everything statically indexed so it stays in registers.  false on a zero pivot.
 template <int n, int m> MM_HD bool small_solve(double* A, double* B) {
     bool ok = true;
+    double ip[n];                                        // pivot reciprocals, reused by the back substitution (fast_rcp: no IEEE division scaffolding)
 #pragma unroll
     for (int k = 0; k < n; ++k) {
 #pragma unroll
@@ -60,10 +61,10 @@ template <int n, int m> MM_HD bool small_solve(double* A, double* B) {
         }
         const double pv = A[k * n + k];
         ok = ok & (pv != 0.0);
-        const double ip = 1.0 / pv;
+        ip[k] = fast_rcp(pv);
 #pragma unroll
         for (int i = k + 1; i < n; ++i) {
-            const double l = A[i * n + k] * ip;
+            const double l = A[i * n + k] * ip[k];
 #pragma unroll
             for (int j = k + 1; j < n; ++j) A[i * n + j] -= l * A[k * n + j];
 #pragma unroll
@@ -72,13 +73,12 @@ template <int n, int m> MM_HD bool small_solve(double* A, double* B) {
     }
 #pragma unroll
     for (int k = n - 1; k >= 0; --k) {
-        const double ip = 1.0 / A[k * n + k];
 #pragma unroll
         for (int j = 0; j < m; ++j) {
             double s = B[k * m + j];
 #pragma unroll
             for (int i = k + 1; i < n; ++i) s -= A[k * n + i] * B[i * m + j];
-            B[k * m + j] = s * ip;
+            B[k * m + j] = s * ip[k];
         }
     }
     return ok;
@@ -150,14 +150,14 @@ MM_HD int wrapped_point(Inner&& inner, Acc& acc, double tol, int max_iter, int* 
 #pragma unroll
                             for (int p = 0; p < nzero; ++p)
                                 v -= io.tan[slot_of_mandel(wrap_nz(KIND, a)) + 6 * slot_of_mandel(wrap_zero(KIND, p))] * (fa * mandel_f(wrap_zero(KIND, p))) * X[p * nnz + b];
-                            acc.template out<1>(wrap_red_of_nz(KIND, a) + nc * wrap_red_of_nz(KIND, b), v / (fa * fb));
+                            acc.template out<1>(wrap_red_of_nz(KIND, a) + nc * wrap_red_of_nz(KIND, b), v * (1.0 / (fa * fb)));   // constant folded
                         }
                 }
                 done = true;
             } else {                                                                              // :72-76 Δε_3D += frommandel(−inv(J) σ)
                 if (!small_solve<nzero, 1>(Jzz, sm)) { flag |= 0x40; break; }
 #pragma unroll
-                for (int a = 0; a < nzero; ++a) io.eps[slot_of_mandel(wrap_zero(KIND, a))] -= sm[a] / mandel_f(wrap_zero(KIND, a));
+                for (int a = 0; a < nzero; ++a) io.eps[slot_of_mandel(wrap_zero(KIND, a))] -= sm[a] * (1.0 / mandel_f(wrap_zero(KIND, a)));   // constant folded
                 oit = it;
             }
         }
