@@ -35,6 +35,13 @@ template <int NIN, int NOUT> struct SoaAcc {
 
 template <class Op> struct MinBlocks { static constexpr int value = 1, block = 32; };   // per-Op occupancy target (register cap): `value` blocks of `block` threads
 
+// SoA kernels that write the 36/81-component tangent keep 40+ output streams open per warp; with every warp slot of the SM filled
+// (32-64 resident warps) the DRAM write stream thrashes — measured (profiles/r01_soa_residency_sweep.log): LinearElastic+tangent
+// 0.944 -> 0.985 of the HBM peak and NeoHook 0.958 -> 0.980 when only 2 blocks of 256 threads are resident, while the read-dominated
+// launches (σ only, energies, XuNeedleman) want full occupancy.  `blocks` > 0: cap residency at that many blocks per SM when out[1]
+// (the tangent) is requested, by requesting unused dynamic shared memory.
+template <class Op> struct SoaTangentCap { static constexpr int blocks = 0; };
+
 // Per-thread scratch in shared memory, laid out [slot][thread] (thread-minor => bank-conflict free).
 // Ops declare how many doubles they need in Op::SCRATCH (0 for the streaming models).
 struct Scratch {
@@ -229,9 +236,14 @@ int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int
         const int64_t blocks = (N + BS_SOA - 1) / BS_SOA;
         if (blocks > 2147483647LL) return set_error(-1, "%s: N too large for one launch", what);
         constexpr size_t scratch = (size_t)Op::SCRATCH * BS_SOA * sizeof(double);
+        // residency cap for the tangent-writing streaming ops (see SoaTangentCap): unused dynamic shared memory sized so that exactly
+        // `cap` blocks fit the SM's 227 KB (+1 KB reserved per block)
+        constexpr int cap = SoaTangentCap<Op>::blocks;
+        constexpr size_t cap_bytes = cap > 0 ? (size_t)(227 * 1024 / cap - 1024 - 2048) : 0;
+        const size_t smem = (cap > 0 && Op::NOUT > 1 && p.out[1] != nullptr && cap_bytes > scratch) ? cap_bytes : scratch;
         static SmemOptIn soa_optin;
-        if (int rc = ensure_smem(soa_optin, soa_kernel<Op, BS_SOA>, scratch, what)) return rc;
-        soa_kernel<Op, BS_SOA><<<(unsigned)blocks, BS_SOA, scratch, stream>>>(op, p, N);
+        if (int rc = ensure_smem(soa_optin, soa_kernel<Op, BS_SOA>, cap_bytes > scratch ? cap_bytes : scratch, what)) return rc;
+        soa_kernel<Op, BS_SOA><<<(unsigned)blocks, BS_SOA, smem, stream>>>(op, p, N);
     } else if (layout == 1) {
         // one kernel for every AoS batch: full tiles through the copy engine (TMA bulk copies) when all array bases are
         // 16-byte aligned, the ragged last tile (or everything, if unaligned) through element-wise copies

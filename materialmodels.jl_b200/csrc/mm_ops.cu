@@ -15,6 +15,8 @@ struct ElasticOp {
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { linear_elastic_point(k, acc); }
 };
 
+template <> struct SoaTangentCap<ElasticOp> { static constexpr int blocks = 2; };
+
 struct PlasticOp {
     static constexpr int NIN = 2, NOUT = 3, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? 6 : 14; }
@@ -53,6 +55,8 @@ template <int MODEL, int KIND, int TAN> struct HyperOp {
     HyperK k;
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { hyper_point_ex<MODEL, KIND, TAN>(k, acc); }
 };
+
+template <int MODEL, int KIND, int TAN> struct SoaTangentCap<HyperOp<MODEL, KIND, TAN>> { static constexpr int blocks = TAN == 1 ? 0 : 2; };   // ∂S∂E measured slower capped (6.82 vs 6.66 ms)
 
 template <int DIM> struct XuOp {
     static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;
