@@ -42,6 +42,10 @@ template <class Op> struct MinBlocks { static constexpr int value = 1, block = 3
 // (the tangent) is requested, by requesting unused dynamic shared memory.
 template <class Op> struct SoaTangentCap { static constexpr int blocks = 0; };
 
+// the AoS tile kernel may want a different register cap than the SoA kernel of the same op (it keeps fewer warps resident anyway:
+// shared-memory images bound its residency); defaults to the SoA choice
+template <class Op> struct MinBlocksAos { static constexpr int value = MinBlocks<Op>::value, block = MinBlocks<Op>::block; };
+
 // Per-thread scratch in shared memory, laid out [slot][thread] (thread-minor => bank-conflict free).
 // Ops declare how many doubles they need in Op::SCRATCH (0 for the streaming models).
 struct Scratch {
@@ -95,21 +99,41 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // dense tile images: inputs [A][pt][c], then outputs [A][pt][c] (no aliasing: strides differ)
+// OutAlias<Op>::of(a) = index of the INPUT array whose image slot output a reuses, or -1.  A thread may overwrite its own point's
+// input slots once it holds them in registers (no other thread reads them), so an output with the same component count as an input
+// needs no image of its own: Plastic's σ(6)/state(14) go out through the ε(6)/state(14) slots and only the tangent is staged
+// separately — 608 instead of 768 bytes of shared memory per point, one more resident block per SM.  Requires: the point function
+// reads ALL inputs before its first output (program order keeps shared-memory loads ahead of the aliasing stores).
+template <class Op> struct OutAlias { __host__ __device__ static constexpr int of(int) { return -1; } };
 template <class Op> __host__ __device__ constexpr int dense_in_off(int a) { return a == 0 ? 0 : dense_in_off<Op>(a - 1) + Op::in_nc(a - 1); }
-template <class Op> __host__ __device__ constexpr int dense_out_off(int a) { return a == 0 ? dense_in_off<Op>(Op::NIN) : dense_out_off<Op>(a - 1) + Op::out_nc(a - 1); }
-template <class Op> __host__ __device__ constexpr int dense_doubles_per_point() { return dense_out_off<Op>(Op::NOUT) + Op::SCRATCH; }
-
-template <class Op> __host__ __device__ constexpr int dense_out_rel(int a) { return dense_out_off<Op>(a) - dense_in_off<Op>(Op::NIN); }   // offset inside the output image
+template <class Op> __host__ __device__ constexpr int dense_out_rel(int a) {     // offset inside the output image (aliased outputs take no room)
+    return a == 0 ? 0 : dense_out_rel<Op>(a - 1) + (OutAlias<Op>::of(a - 1) < 0 ? Op::out_nc(a - 1) : 0);
+}
+template <class Op> __host__ __device__ constexpr int dense_out_rel_noalias(int a) { return a == 0 ? 0 : dense_out_rel_noalias<Op>(a - 1) + Op::out_nc(a - 1); }
 template <class Op, int BS> struct DenseAcc {
-    const double* sm_in;      // input image  [A][pt][c]
+    double* sm_in;            // input image  [A][pt][c] (also the staging area of aliased outputs)
     double* sm_out;           // output image [A][pt][c]
     const Ptrs<Op::NIN, Op::NOUT>& p;
     int t;
-    __device__ __forceinline__ DenseAcc(const double* in_, double* out_, const Ptrs<Op::NIN, Op::NOUT>& p_, int t_) : sm_in(in_), sm_out(out_), p(p_), t(t_) {}
+    __device__ __forceinline__ DenseAcc(double* in_, double* out_, const Ptrs<Op::NIN, Op::NOUT>& p_, int t_) : sm_in(in_), sm_out(out_), p(p_), t(t_) {}
     template <int A> __device__ __forceinline__ double in(int c) const { return sm_in[dense_in_off<Op>(A) * BS + t * Op::in_nc(A) + c]; }
-    template <int A> __device__ __forceinline__ void out(int c, double v) const { sm_out[dense_out_rel<Op>(A) * BS + t * Op::out_nc(A) + c] = v; }
+    template <int A> __device__ __forceinline__ void out(int c, double v) const {
+        constexpr int al = OutAlias<Op>::of(A);
+        if constexpr (al >= 0) {
+            static_assert(Op::out_nc(A) == Op::in_nc(al), "aliased output must have the input's component count");
+            sm_in[dense_in_off<Op>(al) * BS + t * Op::out_nc(A) + c] = v;
+        } else {
+            sm_out[dense_out_rel<Op>(A) * BS + t * Op::out_nc(A) + c] = v;
+        }
+    }
     template <int A> __device__ __forceinline__ bool has_out() const { return p.out[A] != nullptr; }
 };
+// where output A is staged: in the input image (aliased) or in the output image
+template <class Op, int BS, int A> __device__ __forceinline__ double* dense_out_ptr(double* sm_in, double* sm_out) {
+    constexpr int al = OutAlias<Op>::of(A);
+    if constexpr (al >= 0) return sm_in + dense_in_off<Op>(al) * BS;
+    else return sm_out + dense_out_rel<Op>(A) * BS;
+}
 template <class Op, int BS, int A> struct BulkIO {
     static __device__ __forceinline__ uint32_t in_bytes() {
         uint32_t b = (uint32_t)(BS * Op::in_nc(A) * sizeof(double));
@@ -120,9 +144,9 @@ template <class Op, int BS, int A> struct BulkIO {
         bulk_g2s(sm_in + dense_in_off<Op>(A) * BS, p.in[A] + i0 * Op::in_nc(A), (uint32_t)(BS * Op::in_nc(A) * sizeof(double)), bar);
         if constexpr (A + 1 < Op::NIN) BulkIO<Op, BS, A + 1>::load_all(sm_in, p, i0, bar);
     }
-    static __device__ __forceinline__ void store_all(double* sm_out, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0) {
-        if (p.out[A] != nullptr) bulk_s2g(p.out[A] + i0 * Op::out_nc(A), sm_out + dense_out_rel<Op>(A) * BS, (uint32_t)(BS * Op::out_nc(A) * sizeof(double)));
-        if constexpr (A + 1 < Op::NOUT) BulkIO<Op, BS, A + 1>::store_all(sm_out, p, i0);
+    static __device__ __forceinline__ void store_all(double* sm_in, double* sm_out, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0) {
+        if (p.out[A] != nullptr) bulk_s2g(p.out[A] + i0 * Op::out_nc(A), dense_out_ptr<Op, BS, A>(sm_in, sm_out), (uint32_t)(BS * Op::out_nc(A) * sizeof(double)));
+        if constexpr (A + 1 < Op::NOUT) BulkIO<Op, BS, A + 1>::store_all(sm_in, sm_out, p, i0);
     }
 };
 
@@ -132,12 +156,13 @@ template <class Op, int BS, int A> struct DenseTailIO {     // element-wise copi
         for (int e = threadIdx.x; e < npts * Op::in_nc(A); e += BS) sm_in[dense_in_off<Op>(A) * BS + e] = __ldcs(g + e);
         if constexpr (A + 1 < Op::NIN) DenseTailIO<Op, BS, A + 1>::load_all(sm_in, p, i0, npts);
     }
-    static __device__ __forceinline__ void store_all(const double* sm_out, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, int npts) {
+    static __device__ __forceinline__ void store_all(double* sm_in, double* sm_out, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t i0, int npts) {
         if (p.out[A] != nullptr) {
             double* g = p.out[A] + i0 * Op::out_nc(A);
-            for (int e = threadIdx.x; e < npts * Op::out_nc(A); e += BS) __stcs(g + e, sm_out[dense_out_rel<Op>(A) * BS + e]);
+            const double* src = dense_out_ptr<Op, BS, A>(sm_in, sm_out);
+            for (int e = threadIdx.x; e < npts * Op::out_nc(A); e += BS) __stcs(g + e, src[e]);
         }
-        if constexpr (A + 1 < Op::NOUT) DenseTailIO<Op, BS, A + 1>::store_all(sm_out, p, i0, npts);
+        if constexpr (A + 1 < Op::NOUT) DenseTailIO<Op, BS, A + 1>::store_all(sm_in, sm_out, p, i0, npts);
     }
 };
 
@@ -152,7 +177,7 @@ template <class Op, int BS> __host__ __device__ constexpr size_t aos_smem_bytes(
     return 16 + (size_t)(MM_AOS_NBUF * dense_in_off<Op>(Op::NIN) + dense_out_rel<Op>(Op::NOUT) + Op::SCRATCH) * BS * sizeof(double);
 }
 template <class Op, int BS>
-__global__ void __launch_bounds__(BS, (MinBlocks<Op>::value * MinBlocks<Op>::block + BS - 1) / BS)
+__global__ void __launch_bounds__(BS, (MinBlocksAos<Op>::value * MinBlocksAos<Op>::block + BS - 1) / BS)
 aos_bulk_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N, const int64_t ntiles, const int bulk) {
     constexpr int NB = MM_AOS_NBUF, IN_D = dense_in_off<Op>(Op::NIN) * BS, OUT_D = dense_out_rel<Op>(Op::NOUT) * BS;
     extern __shared__ __align__(128) unsigned char sm_raw[];
@@ -195,16 +220,17 @@ aos_bulk_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N, c
         __syncthreads();                              // all outputs written, all inputs consumed
         if (full) {
             if (threadIdx.x == 0) {
-                BulkIO<Op, BS, 0>::store_all(sm_out, p, tile * BS);
+                BulkIO<Op, BS, 0>::store_all(in_img, sm_out, p, tile * BS);
                 bulk_commit();
                 if (NB == 1 && nxt < nfull) {         // single image: next tile's loads overlap this tile's store drain
+                    if (dense_out_rel<Op>(Op::NOUT) != dense_out_rel_noalias<Op>(Op::NOUT)) bulk_wait_read0();   // ... unless outputs leave from the input image
                     mbar_expect_tx(bar, BulkIO<Op, BS, 0>::in_bytes());
                     BulkIO<Op, BS, 0>::load_all(sm_in, p, nxt * BS, bar);
                 }
                 bulk_wait_read0();                    // output image may be overwritten again
             }
         } else {
-            DenseTailIO<Op, BS, 0>::store_all(sm_out, p, tile * BS, npts);
+            DenseTailIO<Op, BS, 0>::store_all(in_img, sm_out, p, tile * BS, npts);
         }
         __syncthreads();
     }

@@ -33,6 +33,7 @@ struct PlasticOp {
         if ((flag & MM_FLAG_FAILED) && n_fail) atomicAdd(n_fail, 1);
     }
 };
+template <> struct OutAlias<PlasticOp> { __host__ __device__ static constexpr int of(int a) { return a == 0 ? 0 : (a == 2 ? 1 : -1); } };   // σ <- ε slots, state <- state slots
 
 #ifndef MM_PLASTIC_SOA_BS
 #define MM_PLASTIC_SOA_BS 128
@@ -46,7 +47,14 @@ struct PlasticOp {
 #ifndef MM_PLASTIC_MINBLOCKS
 #define MM_PLASTIC_MINBLOCKS 3
 #endif
-template <> struct MinBlocks<PlasticOp> { static constexpr int value = MM_PLASTIC_MINBLOCKS, block = 128; };   // 128 threads x 3 blocks/SM -> <= 168 regs: measured best of {1,3,4,5} (tools/sweep_plastic.sh)
+#ifndef MM_PLASTIC_MINBLOCK_THREADS
+#define MM_PLASTIC_MINBLOCK_THREADS 128
+#endif
+#ifndef MM_PLASTIC_AOS_MINBLOCKS
+#define MM_PLASTIC_AOS_MINBLOCKS 2
+#endif
+template <> struct MinBlocksAos<PlasticOp> { static constexpr int value = MM_PLASTIC_AOS_MINBLOCKS, block = 128; };   // 256 threads -> 238 registers, no spills: 10.1 ms vs 11.2 ms at the SoA kernel's 168
+template <> struct MinBlocks<PlasticOp> { static constexpr int value = MM_PLASTIC_MINBLOCKS, block = MM_PLASTIC_MINBLOCK_THREADS; };   // 128 threads x 3 blocks/SM -> <= 168 regs: measured best of {1,3,4,5} (tools/sweep_plastic.sh)
 
 template <int MODEL, int KIND, int TAN> struct HyperOp {
     static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;

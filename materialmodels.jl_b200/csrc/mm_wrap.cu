@@ -44,6 +44,7 @@ template <int KIND> struct WrappedPlasticOp {
         if ((flag & 0xC0) && n_fail) atomicAdd(n_fail, 1);
     }
 };
+template <int KIND> struct OutAlias<WrappedPlasticOp<KIND>> { __host__ __device__ static constexpr int of(int a) { return a == 0 ? 0 : (a == 2 ? 1 : -1); } };
 #ifndef MM_WRAP_MINBLOCKS
 #define MM_WRAP_MINBLOCKS 3
 #endif
