@@ -44,6 +44,9 @@ template <> struct OutAlias<PlasticOp> { __host__ __device__ static constexpr in
 #ifndef MM_STREAM_AOS_BS
 #define MM_STREAM_AOS_BS 128
 #endif
+#ifndef MM_SMALL_AOS_BS
+#define MM_SMALL_AOS_BS 512       // AoS tile of the ops with <= 20 doubles per point (XuNeedleman, energies): 128-point tiles are 3-9 KB copies, sync-bound (Xu 2.08 -> 1.93 ms, energies 1.30 -> 1.15 ms)
+#endif
 #ifndef MM_PLASTIC_MINBLOCKS
 #define MM_PLASTIC_MINBLOCKS 3
 #endif
@@ -122,6 +125,10 @@ __global__ void __launch_bounds__(256) synth_kernel(double* out, int64_t N, int 
 #ifndef MM_DPDF_MINBLOCKS
 #define MM_DPDF_MINBLOCKS 3
 #endif
+#ifndef MM_DPDF_AOS_MINBLOCKS
+#define MM_DPDF_AOS_MINBLOCKS MM_DPDF_MINBLOCKS
+#endif
+template <int MODEL, int KIND> struct MinBlocksAos<HyperOp<MODEL, KIND, 2>> { static constexpr int value = MM_DPDF_AOS_MINBLOCKS, block = 128; };
 template <int MODEL, int KIND> struct MinBlocks<HyperOp<MODEL, KIND, 2>> { static constexpr int value = MM_DPDF_MINBLOCKS, block = 128; };
 
 template <int MODEL, int KIND, int TAN>
@@ -145,10 +152,10 @@ template <int MODEL> int launch_hyper(const HyperK& k, const double* strain, int
 
 template <int MODEL> int launch_hyper_energy(const HyperK& k, const double* strain, int strain_kind, double* psi, int64_t N, int layout, cudaStream_t st) {
     Ptrs<1, 1> p; p.in[0] = strain; p.out[0] = psi;
-    if (strain_kind == MM_STRAIN_F) { HyperEnergyOp<MODEL, 1> op; op.k = k; return launch_points<HyperEnergyOp<MODEL, 1>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper_energy"); }
-    if (strain_kind == MM_STRAIN_E) { HyperEnergyOp<MODEL, 2> op; op.k = k; return launch_points<HyperEnergyOp<MODEL, 2>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper_energy"); }
+    if (strain_kind == MM_STRAIN_F) { HyperEnergyOp<MODEL, 1> op; op.k = k; return launch_points<HyperEnergyOp<MODEL, 1>, 256, MM_SMALL_AOS_BS>(op, p, N, layout, st, "mm_hyper_energy"); }
+    if (strain_kind == MM_STRAIN_E) { HyperEnergyOp<MODEL, 2> op; op.k = k; return launch_points<HyperEnergyOp<MODEL, 2>, 256, MM_SMALL_AOS_BS>(op, p, N, layout, st, "mm_hyper_energy"); }
     HyperEnergyOp<MODEL, 0> op; op.k = k;
-    return launch_points<HyperEnergyOp<MODEL, 0>, 256, MM_STREAM_AOS_BS>(op, p, N, layout, st, "mm_hyper_energy");
+    return launch_points<HyperEnergyOp<MODEL, 0>, 256, MM_SMALL_AOS_BS>(op, p, N, layout, st, "mm_hyper_energy");
 }
 
 }  // namespace mm
@@ -199,8 +206,8 @@ int mm_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, doubl
     if (!p || N < 0 || (N > 0 && (!jump || !T))) return set_error(MM_ERR_ARG, "mm_xu_needleman: bad argument");
     const XuK k = make_xu_k(p->Phi_n, p->Phi_t, p->delta_n, p->delta_t, p->Delta_n_star);
     Ptrs<1, 2> ptrs; ptrs.in[0] = jump; ptrs.out[0] = T; ptrs.out[1] = dTdD;
-    if (dim == 3) { XuOp<3> op; op.k = k; return launch_points<XuOp<3>, 256, MM_STREAM_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
-    if (dim == 2) { XuOp<2> op; op.k = k; return launch_points<XuOp<2>, 256, MM_STREAM_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
+    if (dim == 3) { XuOp<3> op; op.k = k; return launch_points<XuOp<3>, 256, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
+    if (dim == 2) { XuOp<2> op; op.k = k; return launch_points<XuOp<2>, 256, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
     return set_error(MM_ERR_ARG, "mm_xu_needleman: dim must be 2 or 3 (got %d)", dim);
 }
 
@@ -226,7 +233,7 @@ int mm_linear_elastic_energy(const MMLinearElastic* p, const double* eps, double
     if (!p || N < 0 || (N > 0 && (!eps || !psi))) return set_error(MM_ERR_ARG, "mm_linear_elastic_energy: bad argument");
     ElasticEnergyOp op; op.k = make_elastic_k(p->E, p->nu);
     Ptrs<1, 1> ptrs; ptrs.in[0] = eps; ptrs.out[0] = psi;
-    return launch_points<ElasticEnergyOp, 256, MM_STREAM_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_linear_elastic_energy");
+    return launch_points<ElasticEnergyOp, 256, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_linear_elastic_energy");
 }
 
 int mm_hyper_energy(int model, const MMHyper* p, const double* strain, int strain_kind, double* psi, int64_t N, int layout, void* stream) {

@@ -48,6 +48,10 @@ template <int KIND> struct OutAlias<WrappedPlasticOp<KIND>> { __host__ __device_
 #ifndef MM_WRAP_MINBLOCKS
 #define MM_WRAP_MINBLOCKS 3
 #endif
+#ifndef MM_WRAP_AOS_MINBLOCKS
+#define MM_WRAP_AOS_MINBLOCKS MM_WRAP_MINBLOCKS
+#endif
+template <int KIND> struct MinBlocksAos<WrappedPlasticOp<KIND>> { static constexpr int value = MM_WRAP_AOS_MINBLOCKS, block = 128; };
 template <int KIND> struct MinBlocks<WrappedPlasticOp<KIND>> { static constexpr int value = MM_WRAP_MINBLOCKS, block = 128; };
 
 // wrappers.jl is generic in the material; TransverselyIsotropic (the laminate-ply model: ShellStress / PlaneStress use) carries

@@ -108,6 +108,11 @@ def main():
         report("NeoHook dSdE from F soa", N, 408, med, mn)
         del F
         torch.cuda.empty_cache()
+        F = mm.synth_uniform(N, nc, seed, lo, hi, layout="aos")
+        med, mn = timeit(lambda: mm.material_response(mm.dPdF(), m, mm.DeformationGradient(F), layout="aos"), a.reps)
+        report("NeoHook dPdF from F aos", N, 8 * (9 + 9 + 81), med, mn)
+        del F
+        torch.cuda.empty_cache()
     if want("transviso"):
         N = int(1e8 * S)
         m = mm.TransverselyIsotropic(E_L=100e3, E_T=10e3, G_LT=5e3, ν_LT=0.4, ν_TT=0.3)
@@ -217,6 +222,14 @@ def main():
                     "n_fail": int(stB.n_fail.item())})
             del eA, eB, stA, stB
             torch.cuda.empty_cache()
+        dim, nc, amp = mm.PlaneStress(), 3, 1.2e-3                       # the Julia zero-copy layout through the TMA tile kernel
+        eA = mm.synth_uniform(N, nc, 31, -amp, amp, layout="aos")
+        _, _, stA = mm.material_response(dim, m, eA, mm.initial_material_state(m, N, layout="aos"), options={"defer_check": True})
+        eB = mm.synth_uniform(N, nc, 32, -amp, amp, layout="aos")
+        med, mn = timeit(lambda: mm.material_response(dim, m, eB, stA, options={"defer_check": True}), a.reps)
+        report("plastic PlaneStress stepB aos", N, 8 * (nc + 14 + nc + nc * nc + 14) + 3, med, mn)
+        del eA, eB, stA
+        torch.cuda.empty_cache()
     if want("wrapti"):
         N = int(1e8 * S)
         m = mm.TransverselyIsotropic(E_L=100e3, E_T=10e3, G_LT=5e3, ν_LT=0.4, ν_TT=0.3)
