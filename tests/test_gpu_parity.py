@@ -466,3 +466,38 @@ def test_crystal_in_place_state_update(mm, torch, cuda_lib, q, structure):
         assert torch.equal(inplace, new.data) and torch.equal(sig, s_ref) and torch.equal(tan, t_ref)
         assert torch.equal(act, new.flags) and torch.equal(it, new.iters) and int(nf.item()) == int(new.n_fail.item())
         st = new
+
+
+def test_aos_unaligned_bases_take_the_elementwise_tiles_and_give_the_same_bits(mm, torch):
+    """AoS arrays whose base is only 8-byte aligned cannot use the bulk copy engine (16-byte rule): every tile then goes through the
+    element-wise copies of the SAME kernel instantiation — including the in-place σ / state staging — and the result is
+    bit-identical to the aligned call."""
+    N = 10007
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    nc, lo, hi, seed = sy.c2_strain(0)
+    eps = mm.synth_uniform(N, nc, seed, lo, hi, layout="aos")
+    st0 = mm.initial_material_state(m, N, layout="aos")
+    _, _, stA = mm.material_response(m, eps, st0)
+    nc, lo, hi, seed = sy.c2_strain(1)
+    eps = mm.synth_uniform(N, nc, seed, lo, hi, layout="aos")
+    s, t, new = mm.material_response(m, eps, stA)
+
+    def shifted(x):                         # same values at an address that is 8 mod 16
+        buf = torch.empty(x.numel() + 1, dtype=x.dtype, device=x.device)
+        v = buf[1:].view(x.shape)
+        v.copy_(x)
+        assert v.data_ptr() % 16 == 8
+        return v
+
+    out = {"stress": shifted(torch.zeros_like(s)), "tangent": shifted(torch.zeros_like(t)), "state": shifted(torch.zeros_like(new.data))}
+    s2, t2, new2 = mm.material_response(m, shifted(eps), mm.PlasticState(shifted(stA.data), "aos"), out=out)
+    assert s2.data_ptr() % 16 == 8 and new2.data.data_ptr() % 16 == 8
+    assert torch.equal(s2, s) and torch.equal(t2, t) and torch.equal(new2.data, new.data)
+    assert torch.equal(new2.flags, new.flags) and torch.equal(new2.iters, new.iters)
+    # hyperelastic AoS too (9-in / 6 + 36-out, no aliasing)
+    nh = mm.NeoHook(λ=1.0, μ=1.0)
+    nc, lo, hi, seed = sy.c3_defgrad()
+    F = mm.synth_uniform(N, nc, seed, lo, hi, layout="aos")
+    S, T, _ = mm.material_response(mm.dSdC(), nh, mm.DeformationGradient(F), layout="aos")
+    S2, T2, _ = mm.material_response(mm.dSdC(), nh, mm.DeformationGradient(shifted(F)), layout="aos")
+    assert torch.equal(S2, S) and torch.equal(T2, T)
