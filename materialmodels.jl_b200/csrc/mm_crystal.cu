@@ -223,7 +223,7 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint8_t* iter
 }
 
 template <bool HASQ, int LAYOUT>
-int launch_crystal_persistent(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
+int launch_crystal_by_exponent(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
     return k.m_int ? launch_crystal_two_kernel<HASQ, true, LAYOUT>(k, active, iters, n_fail, ptrs, N, st)
                    : launch_crystal_two_kernel<HASQ, false, LAYOUT>(k, active, iters, n_fail, ptrs, N, st);
 }
@@ -239,8 +239,8 @@ template <bool HASQ>
 int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
     if (N == 0) return MM_OK;
     int rc;
-    if (layout == 0)      rc = launch_crystal_persistent<HASQ, 0>(k, active, iters, n_fail, ptrs, N, st);
-    else if (layout == 1) rc = launch_crystal_persistent<HASQ, 1>(k, active, iters, n_fail, ptrs, N, st);
+    if (layout == 0)      rc = launch_crystal_by_exponent<HASQ, 0>(k, active, iters, n_fail, ptrs, N, st);
+    else if (layout == 1) rc = launch_crystal_by_exponent<HASQ, 1>(k, active, iters, n_fail, ptrs, N, st);
     else return set_error(MM_ERR_ARG, "mm_crystal: unknown layout %d", layout);
     if (rc) return rc;
     const int64_t nranges = (N + MM_FIXUP_RANGE - 1) / MM_FIXUP_RANGE;

@@ -57,7 +57,7 @@ template <> struct OutAlias<PlasticOp> { __host__ __device__ static constexpr in
 #define MM_PLASTIC_AOS_MINBLOCKS 2
 #endif
 template <> struct MinBlocksAos<PlasticOp> { static constexpr int value = MM_PLASTIC_AOS_MINBLOCKS, block = 128; };   // 256 threads -> 238 registers, no spills: 10.1 ms vs 11.2 ms at the SoA kernel's 168
-template <> struct MinBlocks<PlasticOp> { static constexpr int value = MM_PLASTIC_MINBLOCKS, block = MM_PLASTIC_MINBLOCK_THREADS; };   // 128 threads x 3 blocks/SM -> <= 168 regs: measured best of {1,3,4,5} (tools/sweep_plastic.sh)
+template <> struct MinBlocks<PlasticOp> { static constexpr int value = MM_PLASTIC_MINBLOCKS, block = MM_PLASTIC_MINBLOCK_THREADS; };   // 128 threads x 3 blocks/SM -> <= 168 regs: measured best of {1,2,3,4,5} (profiles/r01_plastic_regcap_sweep.log, r01_plastic_aos_regcap_sweep.log)
 
 template <int MODEL, int KIND, int TAN> struct HyperOp {
     static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;
