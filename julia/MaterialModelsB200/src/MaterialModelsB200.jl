@@ -250,4 +250,54 @@ function material_response(m::CrystalViscoPlastic{12}, Δε::CuMatrix{Float64}, 
     return σ, T, BatchedCrystalState(new, layout)
 end
 
+# The same wrappers around the other small-strain materials (wrappers.jl is generic in the material).
+_wrap_opts(options) = MMNewtonOpts(get(options, :plane_stress_tol, 1e-8), get(options, :plane_stress_max_iter, 10), 0)      # wrappers.jl:55-56
+function _reduced_outputs(kind::Cint, Δε::CuMatrix{Float64}, layout)
+    nc = Int(ccall((:mm_wrap_ncomp, libmmb200), Cint, (Cint,), kind))
+    N = layout == MM_LAYOUT_AOS ? size(Δε, 2) : size(Δε, 1)
+    T = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, nc * nc, N) : CUDA.zeros(Float64, N, nc * nc)
+    return N, similar(Δε), T, CUDA.zeros(UInt8, N), CUDA.zeros(Int32, 1)
+end
+function material_response(dim::MaterialModels.AbstractDim, m::LinearElastic, Δε::CuMatrix{Float64}, state = initial_material_state(m), Δt = nothing;
+                           cache = nothing, options::Dict{Symbol,Any} = Dict{Symbol,Any}(), layout = MM_LAYOUT_AOS)
+    kind = _dimkind(dim)
+    N, σ, T, outer, nfail = _reduced_outputs(kind, Δε, layout)
+    check(ccall((:mm_wrapped_linear_elastic, libmmb200), Cint,
+                (Cint, Ref{MMLinearElastic}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt8}, CuPtr{Int32}, Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
+                kind, Ref(MMLinearElastic(m.E, m.ν)), Δε, σ, T, outer, nfail, Ref(_wrap_opts(options)), N, layout, CUDA.stream().handle),
+          "mm_wrapped_linear_elastic")
+    Array(nfail)[1] == 0 || error("Not converged. Could not find plane stress state.")                             # wrappers.jl:78
+    return σ, T, state
+end
+function material_response(dim::MaterialModels.AbstractDim, m::TransverselyIsotropic, Δε::CuMatrix{Float64}, state::BatchedTransverselyIsotropicState,
+                           Δt = nothing; cache = nothing, options::Dict{Symbol,Any} = Dict{Symbol,Any}())
+    kind = _dimkind(dim); layout = state.layout
+    N, σ, T, outer, nfail = _reduced_outputs(kind, Δε, layout)
+    check(ccall((:mm_wrapped_transversely_isotropic, libmmb200), Cint,
+                (Cint, Ref{MMTransverselyIsotropic}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt8}, CuPtr{Int32},
+                 Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
+                kind, Ref(MMTransverselyIsotropic(m.L⊥, m.L₌, m.M₌, m.G⊥, m.G₌)), Δε, state.a3, σ, T, outer, nfail, Ref(_wrap_opts(options)), N, layout,
+                CUDA.stream().handle), "mm_wrapped_transversely_isotropic")
+    Array(nfail)[1] == 0 || error("Not converged. Could not find plane stress state.")
+    return σ, T, state
+end
+function material_response(dim::MaterialModels.AbstractDim, m::CrystalViscoPlastic{12}, Δε::CuMatrix{Float64}, state::BatchedCrystalState, Δt = 1.0;
+                           cache = nothing, options::Dict{Symbol,Any} = Dict{Symbol,Any}())
+    kind = _dimkind(dim); layout = state.layout
+    N, σ, T, outer, nfail = _reduced_outputs(kind, Δε, layout)
+    new = similar(state.data)
+    active = CUDA.zeros(UInt16, N); iters = CUDA.zeros(UInt8, N)
+    inner = MMNewtonOpts(get(options, :tol, 1e-8), get(options, :max_iter, 100), 0)
+    check(ccall((:mm_wrapped_crystal, libmmb200), Cint,
+                (Cint, Ref{MMCrystal}, CuPtr{Cdouble}, Cdouble, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt16}, CuPtr{UInt8},
+                 CuPtr{UInt8}, CuPtr{Int32}, Ref{MMNewtonOpts}, Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
+                kind, Ref(MMCrystal(m)), Δε, Float64(Δt), state.data, σ, T, new, active, iters, outer, nfail, Ref(inner), Ref(_wrap_opts(options)), N, layout,
+                CUDA.stream().handle), "mm_wrapped_crystal")
+    if Array(nfail)[1] != 0
+        any(Array(active) .& 0x2000 .!= 0) && error("Not converged. Could not find plane stress state.")           # wrappers.jl:78
+        error("Material model not converged. Could not find material state.")                                      # CrystalViscoPlastic.jl:92
+    end
+    return σ, T, BatchedCrystalState(new, layout)
+end
+
 end # module
