@@ -78,3 +78,46 @@ def test_xu_setup_matches_reference_formulas(mm):
     assert L.load().mm_xu_needleman_setup(400.0, 200.0, Φn, Φt, 0.01, C.byref(out)) == 0
     assert np.isclose(out.delta_n, 0.002) and np.isclose(out.delta_t, 0.002)
     assert out.delta_n == m.δₙ and out.delta_t == m.δₜ
+
+
+def test_julia_binding_ccalls_match_the_header():
+    """julia/MaterialModelsB200 cannot be executed here (no Julia in the image), so at least every `ccall` in it must name an
+    exported symbol and pass the argument kinds (int / int64 / double / pointer) the C declaration has, in order."""
+    import ctypes as C
+    import os
+    import re
+
+    import materialmodels_jl_b200._abi as abi
+
+    src = open(os.path.join(os.path.dirname(__file__), "..", "julia", "MaterialModelsB200", "src", "MaterialModelsB200.jl"), encoding="utf-8").read()
+    calls = re.findall(r"ccall\(\(:(\w+),\s*libmmb200\),\s*(\w+),\s*\(([^()]*)\)", src)
+    assert len(calls) >= 12
+
+    def jl_kind(t):
+        t = t.strip()
+        if t in ("Cint", "Int32"):
+            return "i32"
+        if t == "Int64":
+            return "i64"
+        if t == "Cdouble":
+            return "f64"
+        if re.match(r"^(CuPtr|Ptr|Ref)\{", t):
+            return "ptr"
+        raise AssertionError("unknown Julia argument type %r" % t)
+
+    def c_kind(t):
+        if t is C.c_int:
+            return "i32"
+        if t is C.c_int64:
+            return "i64"
+        if t is C.c_double:
+            return "f64"
+        return "ptr"
+
+    for sym, ret, args in calls:
+        assert sym in abi.SIGNATURES, "Julia binding calls %s, which include/mmb200.h does not declare" % sym
+        restype, argtypes = abi.SIGNATURES[sym]
+        jl = [jl_kind(t) for t in args.split(",") if t.strip()]
+        cc = [c_kind(t) for t in argtypes]
+        assert jl == cc, "%s: Julia passes %s, C expects %s" % (sym, jl, cc)
+        assert ret == ("Cint" if restype is C.c_int else ret)
