@@ -21,14 +21,15 @@ if which.startswith("plastic"):
     eB = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
     for _ in range(reps):
         s, t, st = mm.material_response(m, eB, stA, options={"defer_check": True})
-elif which == "crystal":
+elif which in ("crystal", "crystal_aos"):
+    lname = "aos" if which.endswith("aos") else "soa"
     ss = mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES)
     m = mm.CrystalViscoPlastic(slipsystems=ss, **sy.CRYSTAL_PARAMS)
     nc, lo, hi, seed = sy.c4_strain_increment(0)
-    dA = mm.synth_uniform(N, nc, seed, lo, hi)
-    _, _, stA = mm.material_response(m, dA, mm.initial_material_state(m, N), 1.0)
+    dA = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
+    _, _, stA = mm.material_response(m, dA, mm.initial_material_state(m, N, layout=lname), 1.0)
     nc, lo, hi, seed = sy.c4_strain_increment(1)
-    dB = mm.synth_uniform(N, nc, seed, lo, hi)
+    dB = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
     for _ in range(reps):
         mm.material_response(m, dB, stA, 1.0, options={"defer_check": True})
 elif which == "neohook":
