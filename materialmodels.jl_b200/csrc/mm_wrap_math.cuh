@@ -45,11 +45,10 @@ template <int NS> struct RegIO {
 
 // solve A X = B in place (A: n x n row-major, B: n x m row-major) by Gaussian elimination with partial pivoting;
 // everything statically indexed so it stays in registers.  false on a zero pivot.
-template <int n, int m> MM_HD bool small_solve(double* A, double* B) {
-    bool ok = true;
-    double ip[n];                                        // pivot reciprocals, reused by the back substitution (fast_rcp: no IEEE division scaffolding)
-#pragma unroll
-    for (int k = 0; k < n; ++k) {
+// The elimination column k is a TEMPLATE parameter: with a plain `#pragma unroll` over k nvcc left the pivot search of the 5 x 5 case
+// (UniaxialStress) as a run-time loop, which put A and B into local memory (346 LDL/STL in the kernel, 248 B of stack).
+template <int n, int m, int k> struct SmallElim {
+    static MM_HD void run(double* A, double* B, double* ip, bool& ok) {
 #pragma unroll
         for (int i = k + 1; i < n; ++i) {            // bring the largest |A[i][k]| to row k
             if (fabs(A[i * n + k]) > fabs(A[k * n + k])) {
@@ -61,7 +60,7 @@ template <int n, int m> MM_HD bool small_solve(double* A, double* B) {
         }
         const double pv = A[k * n + k];
         ok = ok & (pv != 0.0);
-        ip[k] = fast_rcp(pv);
+        ip[k] = fast_rcp(pv);                        // pivot reciprocals, reused by the back substitution (no IEEE division scaffolding)
 #pragma unroll
         for (int i = k + 1; i < n; ++i) {
             const double l = A[i * n + k] * ip[k];
@@ -70,9 +69,12 @@ template <int n, int m> MM_HD bool small_solve(double* A, double* B) {
 #pragma unroll
             for (int j = 0; j < m; ++j) B[i * m + j] -= l * B[k * m + j];
         }
+        SmallElim<n, m, k + 1>::run(A, B, ip, ok);
     }
-#pragma unroll
-    for (int k = n - 1; k >= 0; --k) {
+};
+template <int n, int m> struct SmallElim<n, m, n> { static MM_HD void run(double*, double*, double*, bool&) {} };
+template <int n, int m, int k> struct SmallBack {
+    static MM_HD void run(const double* A, double* B, const double* ip) {
 #pragma unroll
         for (int j = 0; j < m; ++j) {
             double s = B[k * m + j];
@@ -80,7 +82,15 @@ template <int n, int m> MM_HD bool small_solve(double* A, double* B) {
             for (int i = k + 1; i < n; ++i) s -= A[k * n + i] * B[i * m + j];
             B[k * m + j] = s * ip[k];
         }
+        SmallBack<n, m, k - 1>::run(A, B, ip);
     }
+};
+template <int n, int m> struct SmallBack<n, m, -1> { static MM_HD void run(const double*, double*, const double*) {} };
+template <int n, int m> MM_HD bool small_solve(double* A, double* B) {
+    bool ok = true;
+    double ip[n];
+    SmallElim<n, m, 0>::run(A, B, ip, ok);
+    SmallBack<n, m, n - 1>::run(A, B, ip);
     return ok;
 }
 
