@@ -501,3 +501,21 @@ def test_aos_unaligned_bases_take_the_elementwise_tiles_and_give_the_same_bits(m
     S, T, _ = mm.material_response(mm.dSdC(), nh, mm.DeformationGradient(F), layout="aos")
     S2, T2, _ = mm.material_response(mm.dSdC(), nh, mm.DeformationGradient(shifted(F)), layout="aos")
     assert torch.equal(S2, S) and torch.equal(T2, T)
+
+
+@pytest.mark.parametrize("lname", ["soa", "aos"])
+def test_plastic_state_updated_in_place(mm, torch, lname):
+    """`state_in` may alias `state_out` (include/mmb200.h): the AoS tile kernel prefetches the NEXT tile's inputs before it stores this
+    tile's outputs and stages σ / state in the input image, so an in-place update is the case that would expose an ordering bug."""
+    N = 50021
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    nc, lo, hi, seed = sy.c2_strain(0)
+    eA = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
+    _, _, stA = mm.material_response(m, eA, mm.initial_material_state(m, N, layout=lname))
+    nc, lo, hi, seed = sy.c2_strain(1)
+    eB = mm.synth_uniform(N, nc, seed, lo, hi, layout=lname)
+    s, t, new = mm.material_response(m, eB, stA)
+    buf = stA.data.clone()
+    s2, t2, new2 = mm.material_response(m, eB, mm.PlasticState(buf, lname), out={"state": buf})
+    assert new2.data.data_ptr() == buf.data_ptr()
+    assert torch.equal(s2, s) and torch.equal(t2, t) and torch.equal(buf, new.data)
