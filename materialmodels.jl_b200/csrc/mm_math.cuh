@@ -155,7 +155,13 @@ MM_HD PlasticK make_plastic_k(double E, double nu, double sigma_y, double H, dou
 // before it and ALL stores after it, executed by the full warp (elastic lanes carry ξ = 0, u = 0 so the one
 // tangent formula Eᵉ − 2Gξ I_dev + u⊗n degenerates to Eᵉ exactly).  A per-branch store phase would issue every
 // store twice with complementary half-empty lane masks — partially written 32 B sectors, measured 2.2x slower.
-template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* iters_out) {
+// the three ingredients of the consistent tangent  ∂σ∂ε = Eᵉ − gxi I_dev + u ⊗ n  (elastic point: gxi = 0, u = 0)
+struct PlasticTangentParts { double gxi; double u[6], n[6]; };
+MM_HD double plastic_tangent_entry(const PlasticK& k, const PlasticTangentParts& tp, int I, int J) {
+    return (iso_entry(I, J, k.lam, k.G) - tp.gxi * idev_entry(I, J)) + tp.u[I] * tp.n[J];
+}
+// plastic_point_parts: the update without the 36 tangent stores (the dimension wrappers evaluate only the entries they need per outer pass)
+template <class Acc> MM_HD int plastic_point_parts(const PlasticK& k, Acc& acc, int* iters_out, PlasticTangentParts& tp) {
     const double c1 = 1.2247448713915890491;   // sqrt(3/2)
     const double r2 = 1.4142135623730950488;   // sqrt(2) (Mandel scaling of the shear residuals)
     const double G2 = 2.0 * k.G;
@@ -289,14 +295,21 @@ template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* i
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc.template out<2>(7 + c, al[c]);
     acc.template out<2>(13, mu);
+    tp.gxi = gxi;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { tp.u[c] = u[c]; tp.n[c] = n[c]; }
+    *iters_out = iters;
+    return flag;
+}
+template <class Acc> MM_HD int plastic_point(const PlasticK& k, Acc& acc, int* iters_out) {
+    PlasticTangentParts tp;
+    const int flag = plastic_point_parts(k, acc, iters_out, tp);
     if (acc.template has_out<1>()) {
 #pragma unroll
         for (int J = 0; J < 6; ++J)
 #pragma unroll
-            for (int I = 0; I < 6; ++I)
-                acc.template out<1>(I + 6 * J, (iso_entry(I, J, k.lam, k.G) - gxi * idev_entry(I, J)) + u[I] * n[J]);
+            for (int I = 0; I < 6; ++I) acc.template out<1>(I + 6 * J, plastic_tangent_entry(k, tp, I, J));
     }
-    *iters_out = iters;
     return flag;
 }
 

@@ -24,6 +24,15 @@ template <int KIND> struct WrappedElasticOp {
     }
 };
 
+struct LazyJ2IO {
+    double eps[6], st_in[14], sig[6], st_out[14];
+    PlasticK k;
+    PlasticTangentParts tp;
+    template <int A> __device__ __forceinline__ double in(int c) const { return A == 0 ? eps[c] : st_in[c]; }
+    template <int A> __device__ __forceinline__ void out(int c, double v) { if (A == 0) sig[c] = v; else if (A == 2) st_out[c] = v; }
+    template <int A> __device__ __forceinline__ bool has_out() const { return A != 1; }
+    __device__ __forceinline__ double T(int idx) const { return plastic_tangent_entry(k, tp, idx % 6, idx / 6); }
+};
 template <int KIND> struct WrappedPlasticOp {
     static constexpr int NIN = 2, NOUT = 3, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? wrap_nc(KIND) : 14; }
@@ -36,8 +45,15 @@ template <int KIND> struct WrappedPlasticOp {
     int32_t* n_fail;
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
         int oit = 0, iit = 0;
-        const PlasticK kk = k;
-        const int flag = wrapped_point<KIND, 14>([&](RegIO<14>& io, int* it) { return plastic_point(kk, io, it); }, acc, tol, max_iter, &oit, &iit);
+        // the inner model leaves the three ingredients of its tangent (13 doubles) instead of 36 entries; the wrapper evaluates the 1-25
+        // entries of the zero-stress block per outer pass and the rest once, at the converged pass (same expression, same bits)
+        LazyJ2IO io;
+        io.k = k;
+#pragma unroll
+        for (int c = 0; c < 14; ++c) io.st_in[c] = acc.template in<1>(c);
+        const int flag = wrapped_core<KIND>([&](LazyJ2IO& o, int* it) { return plastic_point_parts(o.k, o, it, o.tp); }, acc, io, tol, max_iter, &oit, &iit);
+#pragma unroll
+        for (int c = 0; c < 14; ++c) acc.template out<2>(c, io.st_out[c]);
         if (flags) flags[i] = (uint8_t)flag;
         if (iters) iters[i] = (uint8_t)(iit > 255 ? 255 : iit);
         if (outer_iters) outer_iters[i] = (uint8_t)oit;

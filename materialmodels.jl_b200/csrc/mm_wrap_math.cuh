@@ -41,6 +41,7 @@ template <int NS> struct RegIO {
     template <int A> MM_HD double in(int c) const { return A == 0 ? eps[c] : st_in[c]; }
     template <int A> MM_HD void out(int c, double v) { if (A == 0) sig[c] = v; else if (A == 1) tan[c] = v; else st_out[c] = v; }
     template <int A> MM_HD bool has_out() const { return true; }
+    MM_HD double T(int idx) const { return tan[idx]; }          // tangent entry I + 6 J as the wrapper reads it (a lazy IO computes it on demand)
 };
 
 // solve A X = B in place (A: n x n row-major, B: n x m row-major) by Gaussian elimination with partial pivoting;
@@ -97,16 +98,15 @@ template <int n, int m> MM_HD bool small_solve(double* A, double* B) {
 // status bits returned: 0x80 inner model failed, 0x40 outer Newton not converged ("Could not find plane stress state")
 // inner(io, &inner_iters) -> inner flag bits (0x80 = failed).  acc: in<0> reduced strain, in<1> state (NS > 0),
 // out<0> reduced stress, out<1> reduced tangent (optional), out<2> new state (NS > 0).
-template <int KIND, int NS, class Inner, class Acc>
-MM_HD int wrapped_point(Inner&& inner, Acc& acc, double tol, int max_iter, int* outer_iters, int* inner_iters) {
+// wrapped_core: everything but the state traffic.  `io` is what the inner 3D model sees: eps[6] in, sig[6] out as members, T(I + 6 J)
+// the tangent entries (RegIO: the stored 36; the J2 wrapper: computed on demand from the model's tangent ingredients).
+template <int KIND, class IO, class Inner, class Acc>
+MM_HD int wrapped_core(Inner&& inner, Acc& acc, IO& io, double tol, int max_iter, int* outer_iters, int* inner_iters) {
     constexpr int d = wrap_dim(KIND), nc = wrap_nc(KIND);
-    RegIO<NS> io;
 #pragma unroll
     for (int c = 0; c < 6; ++c) io.eps[c] = 0.0;
 #pragma unroll
     for (int r = 0; r < nc; ++r) io.eps[wrap_slot(d, r)] = acc.template in<0>(r);               // increase_dim (:24-27)
-#pragma unroll
-    for (int c = 0; c < NS; ++c) io.st_in[c] = acc.template in<1>(c);
     int flag = 0, oit = 0;
     if (KIND == WRAP_UNIAXIAL_STRAIN || KIND == WRAP_PLANE_STRAIN) {                              // :29-41
         flag = inner(io, inner_iters);
@@ -116,7 +116,7 @@ MM_HD int wrapped_point(Inner&& inner, Acc& acc, double tol, int max_iter, int* 
 #pragma unroll
             for (int b = 0; b < nc; ++b)
 #pragma unroll
-                for (int a = 0; a < nc; ++a) acc.template out<1>(a + nc * b, io.tan[wrap_slot(d, a) + 6 * wrap_slot(d, b)]);
+                for (int a = 0; a < nc; ++a) acc.template out<1>(a + nc * b, io.T(wrap_slot(d, a) + 6 * wrap_slot(d, b)));
         }
     } else {
         constexpr int nzero = wrap_nzero(KIND), nnz = 6 - nzero;
@@ -132,7 +132,7 @@ MM_HD int wrapped_point(Inner&& inner, Acc& acc, double tol, int max_iter, int* 
                 nrm2 += sm[a] * sm[a];
 #pragma unroll
                 for (int b = 0; b < nzero; ++b)
-                    Jzz[a * nzero + b] = io.tan[slot_of_mandel(wrap_zero(KIND, a)) + 6 * slot_of_mandel(wrap_zero(KIND, b))] *
+                    Jzz[a * nzero + b] = io.T(slot_of_mandel(wrap_zero(KIND, a)) + 6 * slot_of_mandel(wrap_zero(KIND, b))) *
                                          (mandel_f(wrap_zero(KIND, a)) * mandel_f(wrap_zero(KIND, b)));
             }
             if (sqrt(nrm2) < tol) {                                                               // :63-70 Schur complement
@@ -141,7 +141,7 @@ MM_HD int wrapped_point(Inner&& inner, Acc& acc, double tol, int max_iter, int* 
                 for (int a = 0; a < nzero; ++a)
 #pragma unroll
                     for (int b = 0; b < nnz; ++b)
-                        X[a * nnz + b] = io.tan[slot_of_mandel(wrap_zero(KIND, a)) + 6 * slot_of_mandel(wrap_nz(KIND, b))] *
+                        X[a * nnz + b] = io.T(slot_of_mandel(wrap_zero(KIND, a)) + 6 * slot_of_mandel(wrap_nz(KIND, b))) *
                                          (mandel_f(wrap_zero(KIND, a)) * mandel_f(wrap_nz(KIND, b)));
                 if (!small_solve<nzero, nnz>(Jzz, X)) flag |= 0x40;
 #pragma unroll
@@ -156,10 +156,10 @@ MM_HD int wrapped_point(Inner&& inner, Acc& acc, double tol, int max_iter, int* 
 #pragma unroll
                         for (int b = 0; b < nnz; ++b) {
                             const double fa = mandel_f(wrap_nz(KIND, a)), fb = mandel_f(wrap_nz(KIND, b));
-                            double v = io.tan[slot_of_mandel(wrap_nz(KIND, a)) + 6 * slot_of_mandel(wrap_nz(KIND, b))] * (fa * fb);
+                            double v = io.T(slot_of_mandel(wrap_nz(KIND, a)) + 6 * slot_of_mandel(wrap_nz(KIND, b))) * (fa * fb);
 #pragma unroll
                             for (int p = 0; p < nzero; ++p)
-                                v -= io.tan[slot_of_mandel(wrap_nz(KIND, a)) + 6 * slot_of_mandel(wrap_zero(KIND, p))] * (fa * mandel_f(wrap_zero(KIND, p))) * X[p * nnz + b];
+                                v -= io.T(slot_of_mandel(wrap_nz(KIND, a)) + 6 * slot_of_mandel(wrap_zero(KIND, p))) * (fa * mandel_f(wrap_zero(KIND, p))) * X[p * nnz + b];
                             acc.template out<1>(wrap_red_of_nz(KIND, a) + nc * wrap_red_of_nz(KIND, b), v * (1.0 / (fa * fb)));   // constant folded
                         }
                 }
@@ -181,9 +181,17 @@ MM_HD int wrapped_point(Inner&& inner, Acc& acc, double tol, int max_iter, int* 
             }
         }
     }
+    *outer_iters = oit;
+    return flag;
+}
+template <int KIND, int NS, class Inner, class Acc>
+MM_HD int wrapped_point(Inner&& inner, Acc& acc, double tol, int max_iter, int* outer_iters, int* inner_iters) {
+    RegIO<NS> io;
+#pragma unroll
+    for (int c = 0; c < NS; ++c) io.st_in[c] = acc.template in<1>(c);
+    const int flag = wrapped_core<KIND>(inner, acc, io, tol, max_iter, outer_iters, inner_iters);
 #pragma unroll
     for (int c = 0; c < NS; ++c) acc.template out<2>(c, io.st_out[c]);
-    *outer_iters = oit;
     return flag;
 }
 
