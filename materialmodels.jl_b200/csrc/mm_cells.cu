@@ -260,8 +260,11 @@ struct HyperCellArgs {
     double* fe; double* Pt; double* dPdF;
     int64_t ncell;
 };
+#ifndef MM_HCELLS_MINBLOCKS
+#define MM_HCELLS_MINBLOCKS 3
+#endif
 template <int HMODEL, int NN, int NQ, int BS>
-__global__ void __launch_bounds__(BS, 3) hyper_cells_kernel(const HyperK k, const HyperCellArgs a) {
+__global__ void __launch_bounds__(BS, MM_HCELLS_MINBLOCKS) hyper_cells_kernel(const HyperK k, const HyperCellArgs a) {
     static_assert(NQ == 1 || NQ == 2 || NQ == 4 || NQ == 8, "quadrature points per cell must be a power of two <= 8");
     constexpr int NC = 3 * NN;
     extern __shared__ double sm[];
