@@ -199,22 +199,27 @@ def cpu_baseline_other_configs(n=200000):
     return out
 
 
+def workload_config(N):
+    """the static description of the workload — identical in both arms (the driver compares them)"""
+    return {"workload": "Plastic J2 (E=200e3, nu=0.3, sigma_y=200, H=50, r=0.5, kappa_inf=alpha_inf=13), %d points/GPU, step B from a non-virgin state (BASELINE.json configs[1])" % N,
+            "points_per_gpu": N, "layout": "soa",
+            "l2": "inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (160 * N / 1e9), "parallelism": "contiguous point shards, no data-path collective"}
+
+
 def run_reference(args):
     """--impl reference: Julia is not installed here and the reference has no C/C++ sources to compile, so the
-    reference arm is the oracle port (oracle/, kind "port") on all host cores; each step is a bounded sample."""
+    reference arm is the oracle port (oracle/, kind "port") on all host cores; each step is a bounded sample
+    (--ref-points points of the same synthetic workload), same K and W as the b200 arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     pts = args.ref_points
-    if pts <= 0:   # size the per-step sample so that the whole run takes ~75 s whatever K is
-        rate, _, _, _ = cpu_baseline_run(100000)
-        pts = int(min(max(rate * 75.0 / (args.steps + min(args.warmup, 1) + 1), 50000), 4 * 10**6))
-    value, cores, dt, frac = cpu_baseline_run(pts, steps=args.steps, warmup=min(args.warmup, 1))
+    value, cores, dt, frac = cpu_baseline_run(pts, steps=args.steps, warmup=args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Plastic J2, 1e8 points/GPU, ~50% plastic, step B (BASELINE.json configs[1])", "sample_points_per_step": pts,
-                   "plastic_fraction": frac},
+        "config": workload_config(args.points),
+        "workload_stats": {"sample_points_per_step": pts, "plastic_fraction": frac},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d-point slice of the same synthetic workload per step, oracle mmo_plastic, OpenMP over all host cores" % pts},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -234,8 +239,9 @@ def main():
     ap.add_argument("--e2e-points", type=int, default=2 * 10**7)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-points", type=int, default=16 * 10**6)
-    ap.add_argument("--ref-points", type=int, default=0, help="points per step of --impl reference (0 = sized for a ~75 s run)")
+    ap.add_argument("--ref-points", type=int, default=2 * 10**6, help="points per step of --impl reference (a bounded slice of the workload)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-full", dest="e2e_full", action="store_false", help="skip the one e2e call at the full 1e8-point size (N=1 only)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the informational timings of the other BASELINE configs")
     args = ap.parse_args()
@@ -268,7 +274,7 @@ def main():
     epsB = mm.synth_uniform(N, ncB, seedB + lo_pt * ncB, loB, hiB, device=dev)
     out = {"stress": torch.empty((6, N), dtype=torch.float64, device=dev), "tangent": torch.empty((36, N), dtype=torch.float64, device=dev),
            "state": torch.empty((14, N), dtype=torch.float64, device=dev), "flags": torch.empty((N,), dtype=torch.uint8, device=dev),
-           "iters": torch.empty((N,), dtype=torch.uint8, device=dev)}
+           "iters": torch.empty((N,), dtype=torch.int16, device=dev)}
     opts = {"defer_check": True}      # the convergence counter is read once after the timed region, not per step
 
     def step():
@@ -306,32 +312,9 @@ def main():
     # ---- e2e: public API, pinned host buffers, H2D + kernel + D2H inside the timed region --------------
     e2e = None
     if not args.no_e2e:
-        Ne = min(args.e2e_points, N)
         out = None
         torch.cuda.empty_cache()
-        h_eps = mm.PinnedArray((6, Ne))
-        h_st = mm.PinnedArray((14, Ne))
-        h_out = {"stress": mm.PinnedArray((6, Ne)), "tangent": mm.PinnedArray((36, Ne)), "state": mm.PinnedArray((14, Ne)),
-                 "flags": mm.PinnedArray((Ne,), np.uint8), "iters": mm.PinnedArray((Ne,), np.uint8)}
-        h_eps.array[...] = epsB[:, :Ne].cpu().numpy()
-        h_st.array[...] = stA.data[:, :Ne].cpu().numpy()
-        st_host = mm.PlasticState(h_st.array)
-        outs = {k: v.array for k, v in h_out.items()}
-        mm.material_response(m, h_eps.array, st_host, out=outs)            # warm-up (workspace allocation)
-        sharding.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            _, _, sth = mm.material_response(m, h_eps.array, st_host, out=outs)   # raises if any point failed (reads n_fail)
-        dt = time.perf_counter() - t0
-        dt = sharding.allreduce_max(dt, device=dev)
-        same = bool(np.array_equal(outs["stress"], stB_slice_host(stB, mm, m, epsB, stA, Ne)))
-        chunks = -(-Ne // (1 << 20))
-        e2e = {"value": world * Ne * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 160 * Ne, "d2h_bytes_per_step": 450 * Ne + 4,
-               "points_per_step_per_gpu": Ne, "steps": args.e2e_steps, "api": "material_response(m, numpy eps, PlasticState(numpy)) -> mmh_plastic",
-               "kernel_launches_per_step": chunks, "matches_device_path": same,
-               "timing": "host clock around the blocking call (last op is a stream sync), max over ranks"}
-        for v in [h_eps, h_st] + list(h_out.values()):
-            v.free()
+        e2e = run_e2e(args, mm, m, epsB, stA, stB, N, world, dev, sharding)
 
     out = None
     if world > 1:
@@ -347,9 +330,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Plastic J2 (E=200e3, nu=0.3, sigma_y=200, H=50, r=0.5, kappa_inf=alpha_inf=13), %d points/GPU, step B from a non-virgin state (BASELINE.json configs[1])" % N,
-                   "points_per_gpu": N, "layout": "soa", "plastic_fraction": frac, "n_not_converged": n_fail,
-                   "l2": "inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (160 * N / 1e9), "parallelism": "contiguous point shards, no data-path collective"},
+        "config": workload_config(N),
+        "workload_stats": {"plastic_fraction": frac, "n_not_converged": n_fail},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ((traffic or {}).get("dram_bytes_per_point") or 0) * N or None,
                      "kernel": "mm::soa_kernel<mm::PlasticOp,128>", "bytes_per_point": BYTES_PER_POINT, "points_per_launch": N, "kernel_ms_mean": mean_kernel_ms,
                      "kernel_ms_min": kern_ms[0], "kernel_ms_max": kern_ms[-1], "peak_source": peak_src,
@@ -358,6 +340,7 @@ def main():
         "clocks": clocks, "gpu_launches": args.steps,
     }
     if e2e:
+        line["gpu_launches"] += e2e.pop("gpu_launches", 0)
         line["e2e"] = e2e
     if world == 1 and not args.no_extra:
         del epsB, stA, stB
@@ -380,6 +363,121 @@ def main():
                 line["cpu_baseline"]["other_configs_error"] = repr(e)
     emit(line)
     return 0
+
+
+def run_e2e(args, mm, m, epsB, stA, stB, N, world, dev, sharding):
+    """The same metric through the public API with HOST buffers: material_response(m, numpy ε, state) -> mmh_* chunk pipeline, pinned
+    memory, every step uploads that step's inputs and downloads its results inside the timed region (host clock around the blocking call,
+    max over ranks).  Headline = the compact "factored" return (the reference's own return shape, Plastic.jl:134-135: elastic points share
+    Eᵉ and keep their state; yielded points get a 27-double row); the dense return, the 36-entry rows, the device-resident-state mode and
+    the cost of re-expanding to dense arrays on the host are timed beside it on the same slice."""
+    import numpy as np
+    import torch
+
+    from materialmodels_jl_b200 import _abi
+    import materialmodels_jl_b200._lib as L
+
+    lib = L.load()
+    Ne = min(args.e2e_points, N)
+    steps = args.e2e_steps
+    h_eps = mm.PinnedArray((6, Ne)).array
+    h_st = mm.PinnedArray((14, Ne)).array
+    h_eps[...] = epsB[:, :Ne].cpu().numpy()
+    h_st[...] = stA.data[:, :Ne].cpu().numpy()
+    frac = float((stB.flags[:Ne] & 1).float().mean().item())
+    cap = min(Ne, int(Ne * min(1.0, frac + 0.02)) + 1024)
+    ref_sig = stB_slice_host(stB, mm, m, epsB, stA, Ne)
+    chunk = lib.mmh_set_chunk_points(0)
+    lib.mmh_set_chunk_points(chunk)
+    chunks = -(-Ne // chunk)
+    launches = {"n": 0}
+
+    def timed(fn, n=steps):
+        fn()                                            # warm-up (workspace allocation, page faults)
+        sharding.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            r = fn()
+        dt = time.perf_counter() - t0
+        return sharding.allreduce_max(dt, device=dev), r
+
+    variants = {}
+    h_sig = mm.PinnedArray((6, Ne)).array
+    h_fl = mm.PinnedArray((Ne,), np.uint8).array
+    h_it = mm.PinnedArray((Ne,), np.uint16).array
+
+    def compact_variant(kind, resident=False, expand=False):
+        W = lib.mm_plastic_row_width({("compact", False): 0, ("factored", False): 1, ("compact", True): 2, ("factored", True): 3}[(kind, resident)])
+        rows = mm.PinnedArray((cap, W)).array
+        outs = {"stress": h_sig, "flags": h_fl, "iters": h_it, "rows": rows}
+        dense_tan = np.empty((36, Ne)) if expand else None
+        dense_st = np.empty((14, Ne)) if expand else None
+        if resident:
+            d_state = torch.empty((14, Ne), dtype=torch.float64, device=dev)
+            src = stA.data[:, :Ne]
+
+        def call():
+            if resident:
+                d_state.copy_(src)                      # every timed step starts from the same state (the in-place update would drift otherwise)
+                st = mm.PlasticState(d_state)
+            else:
+                st = mm.PlasticState(h_st)
+            sg, T, new = mm.material_response(m, h_eps, st, tangent=kind, out=outs)
+            if expand:
+                T.dense(out=dense_tan)
+                new.commit(dense_st)
+            return sg, T, new
+
+        dt, (sg, T, new) = timed(call)
+        launches["n"] += 4 * chunks * (steps + 1)
+        n_rows = T.n_rows
+        name = kind + ("_resident_state" if resident else "") + ("_expanded_on_host" if expand else "")
+        variants[name] = {"value": world * Ne * steps / dt, "h2d_bytes_per_step": (48 if resident else 160) * Ne,
+                          "d2h_bytes_per_step": 51 * Ne + 8 * W * n_rows + 8 * chunks, "row_doubles": W, "rows": n_rows,
+                          "matches_device_path": bool(np.array_equal(sg, ref_sig))}
+        return variants[name]
+
+    # dense (round-1 headline, unchanged code path: mmh_plastic)
+    h_out = {"stress": h_sig, "tangent": mm.PinnedArray((36, Ne)).array, "state": mm.PinnedArray((14, Ne)).array, "flags": h_fl, "iters": h_it}
+    dt, (sg, _, _) = timed(lambda: mm.material_response(m, h_eps, mm.PlasticState(h_st), out=h_out))
+    launches["n"] += chunks * (steps + 1)
+    variants["dense"] = {"value": world * Ne * steps / dt, "h2d_bytes_per_step": 160 * Ne, "d2h_bytes_per_step": 451 * Ne + 4,
+                         "matches_device_path": bool(np.array_equal(sg, ref_sig))}
+    h_out = None
+    compact_variant("compact")
+    head = compact_variant("factored")
+    compact_variant("factored", resident=True)
+    if world == 1:
+        compact_variant("factored", expand=True)
+    e2e = {"value": head["value"], "unit": UNIT, "h2d_bytes_per_step": head["h2d_bytes_per_step"], "d2h_bytes_per_step": head["d2h_bytes_per_step"],
+           "d2h_bytes_per_step_dense_equivalent": 451 * Ne + 4, "points_per_step_per_gpu": Ne, "steps": steps,
+           "api": "material_response(m, numpy eps, PlasticState(numpy), tangent='factored') -> mmh_plastic_compact: sigma, flags, iters for all points; "
+                  "[g_xi, u(6), n(6) | state(14)] rows for the yielded points only (elastic points: the shared E_e and their unchanged state, as Plastic.jl:134-135 returns them)",
+           "matches_device_path": head["matches_device_path"], "kernel_launches_per_step": 4 * chunks, "variants": variants,
+           "timing": "host clock around the blocking call (last op is a stream sync), max over ranks; warm-up 1 call per variant"}
+    # the headline form once at the full configuration size (single GPU only: host memory is per box, not per rank)
+    if world == 1 and args.e2e_full and N > Ne:
+        try:
+            h_eps = h_st = h_sig = h_fl = h_it = None
+            big = dict(eps=mm.PinnedArray((6, N)).array, st=mm.PinnedArray((14, N)).array, sig=mm.PinnedArray((6, N)).array, fl=mm.PinnedArray((N,), np.uint8).array,
+                       it=mm.PinnedArray((N,), np.uint16).array)
+            capN = min(N, int(N * min(1.0, frac + 0.02)) + 1024)
+            big["rows"] = mm.PinnedArray((capN, 27)).array
+            for lo in range(0, N, 1 << 24):
+                hi = min(N, lo + (1 << 24))
+                big["eps"][:, lo:hi] = epsB[:, lo:hi].cpu().numpy()
+                big["st"][:, lo:hi] = stA.data[:, lo:hi].cpu().numpy()
+            outs = {"stress": big["sig"], "flags": big["fl"], "iters": big["it"], "rows": big["rows"]}
+            t0 = time.perf_counter()
+            _, T, _ = mm.material_response(m, big["eps"], mm.PlasticState(big["st"]), tangent="factored", out=outs)
+            dt = time.perf_counter() - t0
+            launches["n"] += 4 * (-(-N // chunk))
+            e2e["full_size_run"] = {"points": N, "value": N / dt, "seconds": dt, "rows": T.n_rows, "note": "one un-warmed call at the configuration size (1e8 points, 33 GB of pinned host memory)"}
+            big = outs = T = None
+        except Exception as e:       # an informational leg must never cost the headline line
+            e2e["full_size_run"] = {"error": repr(e)}
+    e2e["gpu_launches"] = launches["n"]
+    return e2e
 
 
 def _time_kernel(torch, fn, reps=5, warm=2):

@@ -29,8 +29,8 @@
  * reference's error text ("Material model not converged. Could not find material state.",
  * src/Plastic.jl:157, CrystalViscoPlastic.jl:92) when the count is non-zero.
  * Non-finite inputs follow the reference's branches (`if Φ <= 0 … else` sends a NaN Φ to the Newton branch, ⟨Φ⟩ = (Φ+|Φ|)/2
- * propagates it): such points end flagged as failed, their neighbours are unaffected.  Iteration counts are reported as uint8
- * and saturate at 255 (NLsolve's default cap is 1000).
+ * propagates it): such points end flagged as failed, their neighbours are unaffected.  Newton iteration counts (`iters`) are
+ * uint16 (NLsolve's default cap is 1000; they saturate at 65535); the wrappers' outer counts are uint8 (default cap 10).
  */
 #ifndef MMB200_H
 #define MMB200_H
@@ -50,6 +50,7 @@ extern "C" {
 #define MM_ERR_ARG (-1)
 #define MM_ERR_CUDA (-2)
 #define MM_ERR_NOGPU (-3)
+#define MM_ERR_CAPACITY (-4) /* compact return: more points yielded than the caller's row buffer holds */
 
 /* hyperelastic models (mm_hyper `model`) */
 #define MM_NEOHOOK 0  /* src/FiniteStrain/neohook.jl:35-43  */
@@ -112,10 +113,32 @@ int mm_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig, 
 
 /* material_response(::Plastic, ε, state; cache, options) — src/Plastic.jl:126-160 (+ residuals :162-172,
  * NLsolve newton at :146-148).  eps[6] TOTAL strain, state_in/out[14] (may alias), sig[6], tan[36] (not
- * major-symmetric in general; may be NULL), flags/iters (uint8, may be NULL), *n_fail += #non-converged. */
+ * major-symmetric in general; may be NULL), flags (uint8) / iters (uint16) (may be NULL), *n_fail += #non-converged. */
 int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, double* sig, double* tan,
-               double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
+               double* state_out, uint8_t* flags, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
                int64_t N, int layout, void* stream);
+
+/* ---- compact return of the J2 update (opt-in) — reference src/Plastic.jl:134-135 --------------------------------------------
+ * The reference hands every ELASTIC point the one stored m.Eᵉ and its unchanged state object; only a point that took the Newton
+ * branch gets a tangent and a state of its own.  mm_plastic writes 36 + 14 doubles for every point all the same (400 of its 608 bytes
+ * per point).  The compact form returns σ[6], flags and iters for all N points and ONE ROW per yielded point (MM_FLAG_PLASTIC), rows in
+ * point order (row index of point i = number of yielded points before i):
+ *     MM_ROWS_TANGENT_STATE   [∂σ∂ε(36) | new state(14)]        50 doubles      MM_ROWS_TANGENT   [∂σ∂ε(36)]
+ *     MM_ROWS_FACTORED_STATE  [gξ, u(6), n(6) | new state(14)]  27 doubles      MM_ROWS_FACTORED  [gξ, u(6), n(6)]
+ * with ∂σ∂ε[I + 6J] = fma(u[I], n[J], fma(−gξ, I_dev[I,J], Eᵉ[I,J])) — 13 numbers carry the consistent tangent exactly.
+ * Elastic points: tangent = mm_elastic_tangent_3d(E, ν), state = the caller's state_in.  *n_rows (DEVICE int64 for mm_, host for mmh_)
+ * receives the number of yielded points; rows beyond rows_capacity are not written (mmh_: MM_ERR_CAPACITY, everything else complete).
+ * state_out (dense, may be NULL, may alias state_in) is written for all points when given.  `workspace`: device scratch of
+ * mm_plastic_compact_workspace(N, state_out != NULL) bytes (nothing is allocated on the hot path). */
+#define MM_ROWS_TANGENT_STATE 0
+#define MM_ROWS_FACTORED_STATE 1
+#define MM_ROWS_TANGENT 2
+#define MM_ROWS_FACTORED 3
+int mm_plastic_row_width(int row_kind);
+uint64_t mm_plastic_compact_workspace(int64_t N, int want_state_out);
+int mm_plastic_compact(const MMPlastic* p, const double* eps, const double* state_in, double* sig, uint8_t* flags, uint16_t* iters, int row_kind,
+                       double* rows, int64_t rows_capacity, int64_t* n_rows, double* state_out, int32_t* n_fail, const MMNewtonOpts* opts,
+                       void* workspace, uint64_t workspace_bytes, int64_t N, int layout, void* stream);
 
 /* material_response(::NeoHook/::Yeoh/::StVenant, C) — neohook.jl:35-43, yeoh.jl:37-54, stvenant.jl:36-48, and the
  * trait route material_response(∂S∂C(), m, DeformationGradient(F), ...) — src/traits.jl:91-130.
@@ -130,9 +153,9 @@ int mm_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_ki
 
 /* material_response(::CrystalViscoPlastic{12}, Δε, state, Δt; options) — CrystalViscoPlastic.jl:64-94
  * (+ residuals :97-115, get_state_vars :118-132, solve nonlinear_solver.jl:52-62).
- * deps[6] strain INCREMENT, state_in/out[42] (may alias), sig[6], tan[36], active (uint16 mask), iters (uint8). */
+ * deps[6] strain INCREMENT, state_in/out[42] (may alias), sig[6], tan[36], active (uint16 mask), iters (uint16). */
 int mm_crystal(const MMCrystal* p, const double* deps, double dt, const double* state_in, double* sig, double* tan,
-               double* state_out, uint16_t* active, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
+               double* state_out, uint16_t* active, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
                int64_t N, int layout, void* stream);
 
 /* material_response(::XuNeedleman, Δ::Tensor{1,dim}) — XuNeedleman.jl:75-91.  dim = 2 or 3.
@@ -159,12 +182,12 @@ int mm_wrap_ncomp(int dim_kind);
 int mm_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const double* eps_red, double* sig_red, double* tan_red,
                               uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
 int mm_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red,
-                       double* state_out, uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
+                       double* state_out, uint8_t* flags, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
                        const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
 /* ... and around CrystalViscoPlastic{12}: deps_red is the reduced strain INCREMENT, state 42 per point; `active` as mm_crystal plus
  * bit 13 (0x2000) = the outer Newton did not converge; inner solve = the general pivoted path (functional, not tuned) */
 int mm_wrapped_crystal(int dim_kind, const MMCrystal* p, const double* deps_red, double dt, const double* state_in, double* sig_red,
-                       double* tan_red, double* state_out, uint16_t* active, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail,
+                       double* tan_red, double* state_out, uint16_t* active, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail,
                        const MMNewtonOpts* opts, const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
 /* the same wrappers around TransverselyIsotropic (wrappers.jl is generic in the material); a3[3] per point is the state */
 int mm_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropic* p, const double* eps_red, const double* a3,
@@ -199,7 +222,7 @@ int mm_cells_linear_elastic(const MMLinearElastic* p, int nn, int nq, const doub
                             double* fe, double* ke, double* sig, double* tan, int64_t ncell, void* stream);
 int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue,
                      const double* state_in, double* fe, double* ke, double* sig, double* tan, double* state_out, uint8_t* flags,
-                     uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell, void* stream);
+                     uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell, void* stream);
 
 int mm_cells_transversely_isotropic(const MMTransverselyIsotropic* p, int nn, int nq, const double* dNdx, const double* dOmega,
                                     const double* ue, const double* a3 /* [3][P] unit directions */, double* fe, double* ke, double* sig,
@@ -220,18 +243,32 @@ void* mmh_alloc_pinned(uint64_t bytes);
 void mmh_free_pinned(void* p);
 int mmh_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig, double* tan_or_null, int64_t N, int layout);
 int mmh_plastic(const MMPlastic* p, const double* eps, const double* state_in, double* sig, double* tan, double* state_out,
-                uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
+                uint8_t* flags, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
+/* compact return through the chunk pipeline: per point 160 B up and 51 B + (yielded fraction) x 8 x row width down instead of 450 B.
+ * flags is required.  mmh_plastic_compact_resident keeps the state in DEVICE memory (d_state: one N-point array in `layout`, updated in
+ * place; row kind MM_ROWS_TANGENT or MM_ROWS_FACTORED): only ε goes up and only σ, flags, iters and the tangent rows come down. */
+int mmh_plastic_compact(const MMPlastic* p, const double* eps, const double* state_in, double* sig, uint8_t* flags, uint16_t* iters, int row_kind,
+                        double* rows, int64_t rows_capacity, int64_t* n_rows, double* state_out, int32_t* n_fail, const MMNewtonOpts* opts,
+                        int64_t N, int layout);
+int mmh_plastic_compact_resident(const MMPlastic* p, const double* eps, double* d_state, double* sig, uint8_t* flags, uint16_t* iters, int row_kind,
+                                 double* rows, int64_t rows_capacity, int64_t* n_rows, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
+/* dense arrays from the compact return (host threads): tan[36] and / or state_out[14] for all N points in `layout`, bit-identical to what
+ * mmh_plastic writes.  state_out needs a ..._STATE row kind and state_in; state_out == state_in updates the caller's state in place
+ * (only the yielded points are touched).  mmh_set_host_threads(n): threads used by the expander (0 = all cores, capped at 64). */
+int mmh_plastic_expand(const MMPlastic* p, int row_kind, const uint8_t* flags, const double* rows, int64_t n_rows, const double* state_in,
+                       double* tan, double* state_out, int64_t N, int layout);
+int mmh_set_host_threads(int n);
 int mmh_hyper(int model, const MMHyper* p, const double* strain, int strain_kind, double* S, double* dSdC, int64_t N, int layout);
 int mmh_crystal(const MMCrystal* p, const double* deps, double dt, const double* state_in, double* sig, double* tan,
-                double* state_out, uint16_t* active, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
+                double* state_out, uint16_t* active, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
 int mmh_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, double* dTdD, int dim, int64_t N, int layout);
 int mmh_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const double* eps_red, double* sig_red, double* tan_red,
                                uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* wrapper_opts, int64_t N, int layout);
 int mmh_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red,
-                        double* state_out, uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
+                        double* state_out, uint8_t* flags, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
                         const MMNewtonOpts* wrapper_opts, int64_t N, int layout);
 int mmh_wrapped_crystal(int dim_kind, const MMCrystal* p, const double* deps_red, double dt, const double* state_in, double* sig_red,
-                        double* tan_red, double* state_out, uint16_t* active, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail,
+                        double* tan_red, double* state_out, uint16_t* active, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail,
                         const MMNewtonOpts* opts, const MMNewtonOpts* wrapper_opts, int64_t N, int layout);
 int mmh_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropic* p, const double* eps_red, const double* a3,
                                        double* sig_red, double* tan_red, uint8_t* outer_iters, int32_t* n_fail,

@@ -45,12 +45,12 @@ function material_response(m::Plastic, ε::CuMatrix{Float64}, state::BatchedPlas
     σ   = similar(ε)
     tan = aos ? CUDA.zeros(Float64, 36, N) : CUDA.zeros(Float64, N, 36)
     new = similar(state.data)
-    flags = CUDA.zeros(UInt8, N); iters = CUDA.zeros(UInt8, N); nfail = CUDA.zeros(Int32, 1)
+    flags = CUDA.zeros(UInt8, N); iters = CUDA.zeros(UInt16, N); nfail = CUDA.zeros(Int32, 1)
     p = get(options, :nlsolve_params, Dict{Symbol,Any}())
     opts = Ref(MMNewtonOpts(get(p, :ftol, 1e-8), get(p, :iterations, 1000), 0))
     rc = ccall((:mm_plastic, libmmb200), Cint,
                (Ref{MMPlastic}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble},
-                CuPtr{UInt8}, CuPtr{UInt8}, CuPtr{Int32}, Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
+                CuPtr{UInt8}, CuPtr{UInt16}, CuPtr{Int32}, Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
                Ref(MMPlastic(m)), ε, state.data, σ, tan, new, flags, iters, nfail, opts, N, state.layout,
                CUDA.stream().handle)
     check(rc, "mm_plastic")
@@ -62,9 +62,9 @@ end
 function material_response(m::Plastic, ε::Matrix{Float64}, state::Matrix{Float64}, Δt = nothing; layout = MM_LAYOUT_AOS, kwargs...)
     N = layout == MM_LAYOUT_AOS ? size(ε, 2) : size(ε, 1)
     σ = similar(ε); tan = layout == MM_LAYOUT_AOS ? zeros(36, N) : zeros(N, 36); new = similar(state)
-    flags = zeros(UInt8, N); iters = zeros(UInt8, N); nfail = Ref{Int32}(0)
+    flags = zeros(UInt8, N); iters = zeros(UInt16, N); nfail = Ref{Int32}(0)
     rc = ccall((:mmh_plastic, libmmb200), Cint,
-               (Ref{MMPlastic}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{UInt8}, Ptr{UInt8},
+               (Ref{MMPlastic}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{UInt8}, Ptr{UInt16},
                 Ref{Int32}, Ptr{Cvoid}, Int64, Cint),
                Ref(MMPlastic(m)), ε, state, σ, tan, new, flags, iters, nfail, C_NULL, N, layout)
     check(rc, "mmh_plastic")
@@ -185,11 +185,11 @@ function material_response(dim::MaterialModels.AbstractDim, m::Plastic, Δε::Cu
     σ = similar(Δε)
     T = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, nc * nc, N) : CUDA.zeros(Float64, N, nc * nc)
     new = similar(state.data)
-    flags = CUDA.zeros(UInt8, N); iters = CUDA.zeros(UInt8, N); outer = CUDA.zeros(UInt8, N); nfail = CUDA.zeros(Int32, 1)
+    flags = CUDA.zeros(UInt8, N); iters = CUDA.zeros(UInt16, N); outer = CUDA.zeros(UInt8, N); nfail = CUDA.zeros(Int32, 1)
     inner = MMNewtonOpts(1e-8, 1000, 0)
     wrap = MMNewtonOpts(get(options, :plane_stress_tol, 1e-8), get(options, :plane_stress_max_iter, 10), 0)        # wrappers.jl:55-56
     check(ccall((:mm_wrapped_plastic, libmmb200), Cint,
-                (Cint, Ref{MMPlastic}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt8}, CuPtr{UInt8},
+                (Cint, Ref{MMPlastic}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt8}, CuPtr{UInt16},
                  CuPtr{UInt8}, CuPtr{Int32}, Ref{MMNewtonOpts}, Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
                 kind, Ref(MMPlastic(m)), Δε, state.data, σ, T, new, flags, iters, outer, nfail, Ref(inner), Ref(wrap), N, layout,
                 CUDA.stream().handle), "mm_wrapped_plastic")
@@ -209,10 +209,10 @@ function cell_internal_forces(m::Plastic, dNdx::CuMatrix{Float64}, dΩ::CuVector
     ncell, nc = size(ue); nn = nc ÷ 3; P = length(dΩ); nq = P ÷ ncell
     fe = CUDA.zeros(Float64, ncell, nc); new = similar(state.data)
     D = tangent ? CUDA.zeros(Float64, P, 36) : nothing
-    flags = CUDA.zeros(UInt8, P); iters = CUDA.zeros(UInt8, P); nfail = CUDA.zeros(Int32, 1)
+    flags = CUDA.zeros(UInt8, P); iters = CUDA.zeros(UInt16, P); nfail = CUDA.zeros(Int32, 1)
     check(ccall((:mm_cells_plastic, libmmb200), Cint,
                 (Ref{MMPlastic}, Cint, Cint, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble},
-                 CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt8}, CuPtr{UInt8}, CuPtr{Int32}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+                 CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt8}, CuPtr{UInt16}, CuPtr{Int32}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
                 Ref(MMPlastic(m)), nn, nq, dNdx, dΩ, ue, state.data, fe, CU_NULL #= ke: pass a (3nn)² x ncell array for BᵀDB =#, CU_NULL, tangent ? D : CU_NULL, new, flags, iters, nfail, C_NULL, ncell,
                 CUDA.stream().handle), "mm_cells_plastic")
     Array(nfail)[1] == 0 || error("Material model not converged. Could not find material state.")                  # Plastic.jl:157
@@ -240,10 +240,10 @@ function material_response(m::CrystalViscoPlastic{12}, Δε::CuMatrix{Float64}, 
     σ = similar(Δε)
     T = layout == MM_LAYOUT_AOS ? CUDA.zeros(Float64, 36, N) : CUDA.zeros(Float64, N, 36)
     new = similar(state.data)
-    active = CUDA.zeros(UInt16, N); iters = CUDA.zeros(UInt8, N); nfail = CUDA.zeros(Int32, 1)
+    active = CUDA.zeros(UInt16, N); iters = CUDA.zeros(UInt16, N); nfail = CUDA.zeros(Int32, 1)
     opts = MMNewtonOpts(get(options, :tol, 1e-8), get(options, :max_iter, 100), 0)                                  # nonlinear_solver.jl:52
     check(ccall((:mm_crystal, libmmb200), Cint,
-                (Ref{MMCrystal}, CuPtr{Cdouble}, Cdouble, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt16}, CuPtr{UInt8},
+                (Ref{MMCrystal}, CuPtr{Cdouble}, Cdouble, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt16}, CuPtr{UInt16},
                  CuPtr{Int32}, Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
                 Ref(MMCrystal(m)), Δε, Float64(Δt), state.data, σ, T, new, active, iters, nfail, Ref(opts), N, layout, CUDA.stream().handle), "mm_crystal")
     Array(nfail)[1] == 0 || error("Material model not converged. Could not find material state.")                  # CrystalViscoPlastic.jl:92
@@ -286,10 +286,10 @@ function material_response(dim::MaterialModels.AbstractDim, m::CrystalViscoPlast
     kind = _dimkind(dim); layout = state.layout
     N, σ, T, outer, nfail = _reduced_outputs(kind, Δε, layout)
     new = similar(state.data)
-    active = CUDA.zeros(UInt16, N); iters = CUDA.zeros(UInt8, N)
+    active = CUDA.zeros(UInt16, N); iters = CUDA.zeros(UInt16, N)
     inner = MMNewtonOpts(get(options, :tol, 1e-8), get(options, :max_iter, 100), 0)
     check(ccall((:mm_wrapped_crystal, libmmb200), Cint,
-                (Cint, Ref{MMCrystal}, CuPtr{Cdouble}, Cdouble, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt16}, CuPtr{UInt8},
+                (Cint, Ref{MMCrystal}, CuPtr{Cdouble}, Cdouble, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{UInt16}, CuPtr{UInt16},
                  CuPtr{UInt8}, CuPtr{Int32}, Ref{MMNewtonOpts}, Ref{MMNewtonOpts}, Int64, Cint, Ptr{Cvoid}),
                 kind, Ref(MMCrystal(m)), Δε, Float64(Δt), state.data, σ, T, new, active, iters, outer, nfail, Ref(inner), Ref(_wrap_opts(options)), N, layout,
                 CUDA.stream().handle), "mm_wrapped_crystal")

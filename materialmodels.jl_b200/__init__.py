@@ -11,7 +11,7 @@ from .materials import (  # noqa: F401
     xu_needleman_Φₙ, xu_needleman_Φₜ, xu_needleman_σₘₐₓ, xu_needleman_τₘₐₓ,
 )
 from .api import (  # noqa: F401
-    NOT_CONVERGED, PLANE_STRESS_NOT_CONVERGED, CrystalViscoPlasticState, PinnedArray, LinearElasticState, NeoHookState, PlasticCache, PlasticState, StVenantState,
+    NOT_CONVERGED, PLANE_STRESS_NOT_CONVERGED, CompactPlasticState, CompactTangent, CrystalViscoPlasticState, PinnedArray, LinearElasticState, NeoHookState, PlasticCache, PlasticState, StVenantState,
     TransverselyIsotropicState, XuNeedlemanState, YeohState, cell_internal_forces, elastic_strain_energy_density, elastic_tangent_3D, get_cache, initial_material_state, material_response, synth_uniform,
 )
 

@@ -5,7 +5,8 @@ import ctypes as C
 MM_LAYOUT_SOA = 0
 MM_LAYOUT_AOS = 1
 MM_NSLIP = 12
-MM_OK, MM_ERR_ARG, MM_ERR_CUDA, MM_ERR_NOGPU = 0, -1, -2, -3
+MM_OK, MM_ERR_ARG, MM_ERR_CUDA, MM_ERR_NOGPU, MM_ERR_CAPACITY = 0, -1, -2, -3, -4
+MM_ROWS_TANGENT_STATE, MM_ROWS_FACTORED_STATE, MM_ROWS_TANGENT, MM_ROWS_FACTORED = 0, 1, 2, 3
 MM_NEOHOOK, MM_YEOH, MM_STVENANT = 0, 1, 2
 MM_STRAIN_C, MM_STRAIN_F, MM_STRAIN_E = 0, 1, 2
 MM_TANGENT_DSDC, MM_TANGENT_DSDE, MM_TANGENT_DPDF = 0, 1, 2
@@ -102,6 +103,13 @@ SIGNATURES = {
     "mmh_crystal": (C.c_int, [C.POINTER(MMCrystal), _P, C.c_double, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int]),
     "mmh_xu_needleman": (C.c_int, [C.POINTER(MMXuNeedleman), _P, _P, _P, C.c_int, _I64, C.c_int]),
     "mmh_set_chunk_points": (_I64, [_I64]),
+    "mm_plastic_row_width": (C.c_int, [C.c_int]),
+    "mm_plastic_compact_workspace": (C.c_uint64, [_I64, C.c_int]),
+    "mm_plastic_compact": (C.c_int, [C.POINTER(MMPlastic), _P, _P, _P, _P, _P, C.c_int, _P, _I64, _P, _P, _P, C.POINTER(MMNewtonOpts), _P, C.c_uint64, _I64, C.c_int, _P]),
+    "mmh_plastic_compact": (C.c_int, [C.POINTER(MMPlastic), _P, _P, _P, _P, _P, C.c_int, _P, _I64, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int]),
+    "mmh_plastic_compact_resident": (C.c_int, [C.POINTER(MMPlastic), _P, _P, _P, _P, _P, C.c_int, _P, _I64, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int]),
+    "mmh_plastic_expand": (C.c_int, [C.POINTER(MMPlastic), C.c_int, _P, _P, _I64, _P, _P, _P, _I64, C.c_int]),
+    "mmh_set_host_threads": (C.c_int, [C.c_int]),
 }
 
 

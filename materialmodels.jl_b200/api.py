@@ -297,17 +297,196 @@ def _response_linear_elastic(m, ε, state, layout, want_tangent):
 
 
 def _out(out, key, shape, like, dtype=None):
-    """caller-provided output buffer (e.g. pinned host memory) or a fresh allocation"""
+    """caller-provided output buffer (e.g. pinned host memory) or a fresh allocation.  A provided buffer is written through its raw
+    pointer, so everything the native side assumes is checked here: shape, dtype, contiguity, and that it lives where the inputs live."""
     if out is not None and out.get(key) is not None:
         a = out[key]
         if tuple(a.shape) != tuple(shape):
             raise ValueError("out[%r] has shape %s, expected %s" % (key, tuple(a.shape), tuple(shape)))
         if _is_host(like) != _is_host(a):
             raise ValueError("out[%r] must live where the inputs live" % key)
-        if _is_host(a) and not a.flags["C_CONTIGUOUS"]:
-            raise ValueError("out[%r] must be C-contiguous" % key)
+        if _is_host(a):
+            want = np.dtype(dtype or np.float64)
+            if a.dtype != want:
+                raise ValueError("out[%r] has dtype %s, expected %s" % (key, a.dtype, want))
+            if not a.flags["C_CONTIGUOUS"] or not a.flags["WRITEABLE"]:
+                raise ValueError("out[%r] must be a writeable C-contiguous array" % key)
+        else:
+            torch = _torch()
+            want = dtype or torch.float64
+            if a.dtype != want:
+                raise ValueError("out[%r] has dtype %s, expected %s" % (key, a.dtype, want))
+            if not a.is_contiguous():
+                raise ValueError("out[%r] must be contiguous" % key)
+            if a.device != like.device:
+                raise ValueError("out[%r] is on %s, the inputs are on %s" % (key, a.device, like.device))
         return a
     return _empty(shape, like, dtype)
+
+
+def _same_place(strain, state_data, what):
+    """strain and state must both be host arrays or both live on the same CUDA device (a device pointer handed to mmh_* as a host
+    source, or a host pointer handed to a kernel, is an illegal address that poisons the CUDA context)"""
+    if _is_host(strain) != _is_host(state_data):
+        raise ValueError("%s: strain and state must live in the same place (strain on %s, state on %s); initial_material_state(m, N, device='cpu') "
+                         "gives a host state for numpy strains" % (what, "host" if _is_host(strain) else strain.device, "host" if _is_host(state_data) else state_data.device))
+    if not _is_host(strain) and strain.device != state_data.device:
+        raise ValueError("%s: strain is on %s, state on %s" % (what, strain.device, state_data.device))
+
+
+class CompactTangent:
+    """∂σ∂ε of a batched J2 update in the reference's own terms (src/Plastic.jl:134-135): every elastic point shares the ONE stored
+    m.Eᵉ (`elastic`, 36), every yielded point (flags & MM_FLAG_PLASTIC) owns one row of `rows`, in point order.
+    kind "compact": the row is the 36-entry tangent; "factored": the row is (gξ, u(6), n(6)) with ∂σ∂ε = Eᵉ − gξ I_dev + u⊗n.
+    `tangent[i]` gives the 36 entries of point i; `dense()` materialises the (36, N) / (N, 36) array (bit-identical to the dense path)."""
+
+    def __init__(self, m, kind, row_kind, flags, rows, n_rows, layout, state_in=None):
+        self.m, self.kind, self.row_kind, self.flags, self.rows, self.n_rows, self.layout = m, kind, row_kind, flags, rows, n_rows, layout
+        self.N = flags.shape[0]
+        self.elastic = m.Eᵉ
+        self.width = rows.shape[1] if rows.ndim == 2 else 0
+        self._state_in = state_in
+        self._row_of = None
+
+    @property
+    def row_of(self):
+        """row index per point, -1 for elastic points"""
+        if self._row_of is None:
+            y = (self.flags & _abi.MM_FLAG_PLASTIC).astype(bool)
+            r = np.cumsum(y, dtype=np.int64) - 1
+            r[~y] = -1
+            self._row_of = r
+        return self._row_of
+
+    def __getitem__(self, i):
+        k = int(self.row_of[i])
+        if k < 0:
+            return self.elastic.copy()
+        r = self.rows[k]
+        if self.kind == "compact":
+            return np.array(r[:36])
+        gxi, u, n = r[0], r[1:7], r[7:13]
+        idev = _IDEV36
+        return (self.elastic - gxi * idev + np.outer(n, u).reshape(36))      # entry I + 6J = u[I] n[J]
+
+    def dense(self, out=None):
+        shape = _shape(36, self.N, self.layout)
+        tan = np.empty(shape) if out is None else out
+        if tuple(tan.shape) != shape or tan.dtype != np.float64 or not tan.flags["C_CONTIGUOUS"]:
+            raise ValueError("dense(out=...): expected a C-contiguous float64 array of shape %s" % (shape,))
+        check(load().mmh_plastic_expand(ctypes.byref(self.m._c), self.row_kind, _ptr(self.flags), _ptr(self.rows), self.n_rows, None, _ptr(tan), None,
+                                        self.N, _LAYOUTS[self.layout]), "mmh_plastic_expand")
+        return tan
+
+
+def _idev36():
+    d = np.zeros((6, 6))
+    diag = (0, 3, 5)
+    for I in range(6):
+        for J in range(6):
+            if I in diag and J in diag:
+                d[J, I] = 2.0 / 3.0 if I == J else -1.0 / 3.0
+            elif I == J:
+                d[J, I] = 0.5
+    return d.reshape(36)
+
+
+_IDEV36 = _idev36()
+
+
+class CompactPlasticState(_ArrayState):
+    """New state of a compact J2 update: elastic points keep the caller's previous state (the reference returns the same object,
+    Plastic.jl:135), yielded points own the trailing 14 entries of their row.  `.data` materialises the dense array on first use;
+    `commit(into)` scatters the yielded rows into an existing dense state array (in place when `into` is the previous state's array)."""
+    NC = 14
+
+    def __init__(self, m, prev, row_kind, flags, rows, n_rows, layout):
+        self.m, self.prev, self.row_kind, self.rows, self.n_rows = m, prev, row_kind, rows, n_rows
+        self.layout = layout
+        self.N = flags.shape[0]
+        self.flags = flags
+        self.iters = None
+        self.n_fail = None
+        self._data = None
+
+    def commit(self, into=None):
+        prev = np.ascontiguousarray(self.prev)
+        if into is None:
+            into = np.empty_like(prev)
+        check(load().mmh_plastic_expand(ctypes.byref(self.m._c), self.row_kind, _ptr(self.flags), _ptr(self.rows), self.n_rows, _ptr(prev), None, _ptr(into),
+                                        self.N, _LAYOUTS[self.layout]), "mmh_plastic_expand")
+        self._data = into
+        return into
+
+    @property
+    def data(self):
+        if self._data is None:
+            self.commit()
+        return self._data
+
+    @data.setter
+    def data(self, v):
+        self._data = v
+
+
+_ROW_KINDS = {("compact", True): _abi.MM_ROWS_TANGENT_STATE, ("factored", True): _abi.MM_ROWS_FACTORED_STATE,
+              ("compact", False): _abi.MM_ROWS_TANGENT, ("factored", False): _abi.MM_ROWS_FACTORED}
+
+
+def _response_plastic_compact(m, ε, state, options, kind, out):
+    """material_response(m::Plastic, ε, state; tangent="compact" | "factored") for HOST strains: the compact return of
+    include/mmb200.h (mmh_plastic_compact).  state on the host: rows carry [tangent | new state]; state on a CUDA device (resident
+    mode): the device state is updated IN PLACE and only ε goes up / σ, flags, iters and tangent rows come down.
+    out: stress (6,N), flags (N,) uint8, iters (N,) uint16, rows (capacity, W) float64 [W = mm_plastic_row_width]."""
+    layout = state.layout
+    ε = _prep(ε)
+    if not _is_host(ε):
+        raise NotImplementedError("tangent=%r is the host-buffer form of the update (numpy strains); device callers use mm_plastic_compact through the C ABI" % kind)
+    N = _npoints(ε, 6, layout)
+    if N != state.N:
+        raise ValueError("strain has %d points, state has %d" % (N, state.N))
+    resident = not _is_host(state.data)
+    row_kind = _ROW_KINDS[(kind, not resident)]
+    lib = load()
+    W = lib.mm_plastic_row_width(row_kind)
+    σ = _out(out, "stress", _shape(6, N, layout), ε)
+    flags = _out(out, "flags", (N,), ε, np.uint8)
+    iters = _out(out, "iters", (N,), ε, np.uint16)
+    rows = out.get("rows") if out else None
+    if rows is None:
+        rows = np.empty((N, W))
+    if rows.ndim != 2 or rows.shape[1] != W or rows.dtype != np.float64 or not rows.flags["C_CONTIGUOUS"]:
+        raise ValueError("out['rows'] must be a C-contiguous float64 array of shape (capacity, %d)" % W)
+    nrows = ctypes.c_int64(0)
+    nfail = np.zeros(1, np.int32)
+    o = _newton_opts(m, options)
+    if resident:
+        sdev = state.data
+        if not sdev.is_contiguous() or sdev.dtype != _torch().float64:
+            raise ValueError("resident state must be a contiguous float64 CUDA tensor")
+        with _DeviceGuard(sdev):
+            _torch().cuda.current_stream(sdev.device).synchronize()       # the pipeline runs on the library's own streams
+            rc = lib.mmh_plastic_compact_resident(ctypes.byref(m._c), _ptr(ε), _ptr(sdev), _ptr(σ), _ptr(flags), _ptr(iters), row_kind, _ptr(rows), rows.shape[0],
+                                                  ctypes.byref(nrows), _ptr(nfail), ctypes.byref(o), N, _LAYOUTS[layout])
+    else:
+        sin = _prep(state.data)
+        rc = lib.mmh_plastic_compact(ctypes.byref(m._c), _ptr(ε), _ptr(sin), _ptr(σ), _ptr(flags), _ptr(iters), row_kind, _ptr(rows), rows.shape[0],
+                                     ctypes.byref(nrows), None, _ptr(nfail), ctypes.byref(o), N, _LAYOUTS[layout])
+    if rc == _abi.MM_ERR_CAPACITY:
+        raise BufferError("out['rows'] holds %d rows but %d points yielded" % (rows.shape[0], nrows.value))
+    check(rc, "mmh_plastic_compact")
+    n = int(nrows.value)
+    tan = CompactTangent(m, kind, row_kind, flags, rows[:n], n, layout)
+    if resident:
+        new = PlasticState(state.data, layout)                 # updated in place on the device
+        new.flags = flags
+    else:
+        new = CompactPlasticState(m, sin, row_kind, flags, rows[:n], n, layout)
+        if out and out.get("state") is not None:
+            new.commit(_out(out, "state", _shape(14, N, layout), ε))
+    new.iters, new.n_fail = iters, nfail
+    _finish_fail(nfail, ε, options)
+    return σ, tan, new
 
 
 def _response_plastic(m, ε, state, options, want_tangent, out=None):
@@ -317,12 +496,13 @@ def _response_plastic(m, ε, state, options, want_tangent, out=None):
     if N != state.N:
         raise ValueError("strain has %d points, state has %d" % (N, state.N))
     sin = _prep(state.data)
+    _same_place(ε, sin, "material_response(::Plastic)")
     host = _is_host(ε)
     σ = _out(out, "stress", _shape(6, N, layout), ε)
     tan = _out(out, "tangent", _shape(36, N, layout), ε) if want_tangent else None
     sout = _out(out, "state", _shape(14, N, layout), ε)
     flags = _out(out, "flags", (N,), ε, np.uint8 if host else _torch().uint8)
-    iters = _out(out, "iters", (N,), ε, np.uint8 if host else _torch().uint8)
+    iters = _out(out, "iters", (N,), ε, np.uint16 if host else _torch().int16)
     nfail = _zeros((1,), ε, np.int32 if host else _torch().int32)
     o = _newton_opts(m, options)
     lib = load()
@@ -347,12 +527,13 @@ def _response_crystal(m, Δε, state, Δt, options, want_tangent):
     if N != state.N:
         raise ValueError("strain has %d points, state has %d" % (N, state.N))
     sin = _prep(state.data)
+    _same_place(Δε, sin, "material_response(::CrystalViscoPlastic)")
     σ = _empty(_shape(6, N, layout), Δε)
     tan = _empty(_shape(36, N, layout), Δε) if want_tangent else None
     sout = _empty(_shape(42, N, layout), Δε)
     host = _is_host(Δε)
     active = _empty((N,), Δε, np.uint16 if host else _torch().int16)
-    iters = _empty((N,), Δε, np.uint8 if host else _torch().uint8)
+    iters = _empty((N,), Δε, np.uint16 if host else _torch().int16)
     nfail = _zeros((1,), Δε, np.int32 if host else _torch().int32)
     o = _newton_opts(m, options)
     lib = load()
@@ -519,7 +700,7 @@ def _response_wrapped(dim, m, Δε, state, options, layout, want_tangent, Δt=No
                 raise ValueError("strain and state must live in the same place")
             sout = _empty(_shape(14, N, layout), Δε)
             flags = _empty((N,), Δε, u8)
-            iters = _empty((N,), Δε, u8)
+            iters = _empty((N,), Δε, np.uint16 if host else _torch().int16)
             o = _newton_opts(m, options)
             fn = lib.mmh_wrapped_plastic if host else lib.mm_wrapped_plastic
             check(fn(kind, ctypes.byref(m._c), _ptr(Δε), _ptr(sin), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(flags), _ptr(iters), _ptr(oit), _ptr(nfail),
@@ -534,7 +715,7 @@ def _response_wrapped(dim, m, Δε, state, options, layout, want_tangent, Δt=No
                 raise ValueError("strain and state must live in the same place")
             sout = _empty(_shape(42, N, layout), Δε)
             active = _empty((N,), Δε, np.uint16 if host else _torch().int16)
-            iters = _empty((N,), Δε, u8)
+            iters = _empty((N,), Δε, np.uint16 if host else _torch().int16)
             o = _newton_opts(m, options)
             fn = lib.mmh_wrapped_crystal if host else lib.mm_wrapped_crystal
             check(fn(kind, ctypes.byref(m._c), _ptr(Δε), float(Δt), _ptr(sin), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(active), _ptr(iters), _ptr(oit),
@@ -561,7 +742,10 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
     Returns (stress, tangent, new_state) for all N points of `strain`.
     `layout` applies to stateless models (stateful ones use their state's layout);
     `tangent=False` skips the 36-component tangent output (returns None in its place);
-    `out` (Plastic) = dict of preallocated output buffers: stress, tangent, state, flags, iters."""
+    `tangent="compact" | "factored"` (Plastic, numpy strains): the reference's own return shape, src/Plastic.jl:134-135 — elastic points
+    share m.Eᵉ and keep their state, yielded points own one row (CompactTangent / CompactPlasticState); a state on a CUDA device
+    with numpy strains = resident mode (state updated in place on the device, only ε up and σ + rows down);
+    `out` (Plastic) = dict of preallocated output buffers: stress, tangent, state, flags, iters (and rows for the compact forms)."""
     args = list(args)
     if args and isinstance(args[0], AbstractDim):                            # src/wrappers.jl:29-79
         dim = args.pop(0)
@@ -612,6 +796,10 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
     if isinstance(m, Plastic):
         if state is None:
             raise TypeError("material_response(::Plastic, ε, state): state required")
+        if isinstance(tangent, str):
+            if tangent not in ("compact", "factored"):
+                raise ValueError("tangent must be True, False, 'compact' or 'factored'")
+            return _response_plastic_compact(m, strain, state, options, tangent, out)
         return _response_plastic(m, strain, state, options, tangent, out)
     if isinstance(m, CrystalViscoPlastic):
         if state is None:
@@ -681,9 +869,10 @@ def cell_internal_forces(m, dNdx, dΩ, ue, state=None, tangent=False, stress=Fal
         if state is None or state.N != P or _LAYOUTS[state.layout] != _abi.MM_LAYOUT_SOA:
             raise ValueError("cell_internal_forces(::Plastic): a 'soa' PlasticState over the %d quadrature points is required" % P)
         sin = _prep(state.data)
+        _same_place(ue, sin, "cell_internal_forces(::Plastic)")
         sout = _empty((14, P), ue)
         flags = _empty((P,), ue, torch.uint8)
-        iters = _empty((P,), ue, torch.uint8)
+        iters = _empty((P,), ue, torch.int16)
         nfail = _zeros((1,), ue, torch.int32)
         o = _newton_opts(m, options)
         check(lib.mm_cells_plastic(ctypes.byref(m._c), nn, nq, _ptr(dNdx), _ptr(dΩ), _ptr(ue), _ptr(sin), _ptr(fe), _ptr(ke), _ptr(σ), _ptr(tan), _ptr(sout), _ptr(flags),
@@ -706,26 +895,37 @@ def synth_uniform(N, nc, seed, lo, hi, layout="soa", device="cuda"):
     return out
 
 
-class PinnedArray:
-    """float64/uint8 numpy array backed by page-locked host memory (mmh_alloc_pinned): what a host-resident
-    caller should hand to the numpy path so the H2D/D2H copies run at PCIe speed and truly asynchronously."""
+class _PinnedBlock:
+    """owner of one mmh_alloc_pinned allocation; freed when the last numpy view that refers to it is gone"""
 
-    def __init__(self, shape, dtype=np.float64):
-        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        self._ptr = load().mmh_alloc_pinned(max(self.nbytes, 1))
-        if not self._ptr:
-            raise MemoryError("mmh_alloc_pinned(%d) failed" % self.nbytes)
-        buf = (ctypes.c_char * max(self.nbytes, 1)).from_address(self._ptr)
-        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-
-    def free(self):
-        if self._ptr:
-            self.array = None
-            load().mmh_free_pinned(ctypes.c_void_p(self._ptr))
-            self._ptr = None
+    def __init__(self, nbytes):
+        self.ptr = load().mmh_alloc_pinned(max(nbytes, 1))
+        if not self.ptr:
+            raise MemoryError("mmh_alloc_pinned(%d) failed" % nbytes)
+        self.nbytes = max(nbytes, 1)
+        self.__array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
 
     def __del__(self):
         try:
-            self.free()
+            if self.ptr:
+                load().mmh_free_pinned(ctypes.c_void_p(self.ptr))
+                self.ptr = None
         except Exception:
             pass
+
+
+class PinnedArray:
+    """float64/uint8/... numpy array backed by page-locked host memory (mmh_alloc_pinned): what a host-resident caller should hand
+    to the numpy path so the H2D/D2H copies run at PCIe speed and truly asynchronously.  `.array` and every view or slice of it keep
+    the allocation alive (the pinned block is the numpy base object), so `PinnedArray(shape).array` is safe on its own and results
+    returned by material_response(out=...) stay valid after the PinnedArray object is gone; the memory is unpinned and released when
+    the last view dies.  `free()` only drops this object's own reference."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        block = _PinnedBlock(self.nbytes)
+        raw = np.asarray(block)                      # uint8 view whose .base is the block: numpy's refcount owns the pinned memory
+        self.array = raw[: self.nbytes].view(dtype).reshape(shape)
+
+    def free(self):
+        self.array = None

@@ -7,8 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libmmb200.so")
-SOURCES = ["mm_api.cu", "mm_ops.cu", "mm_crystal.cu", "mm_wrap.cu", "mm_cells.cu", "mm_host.cu"]
-HEADERS = ["mm_math.cuh", "mm_crystal_math.cuh", "mm_wrap_math.cuh", "mm_kernels.cuh", os.path.join("..", "..", "include", "mmb200.h")]
+SOURCES = ["mm_api.cu", "mm_ops.cu", "mm_compact.cu", "mm_crystal.cu", "mm_wrap.cu", "mm_cells.cu", "mm_host.cu", "mm_expand.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -25,34 +24,84 @@ def nvcc():
     return p
 
 
+import re
+
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def deps_of(path, seen=None):
+    """the source and every header it includes by a quoted path, transitively"""
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path, encoding="utf-8") as f:
+        for inc in _INC.findall(f.read()):
+            deps_of(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
+
+
+def _obj(s):
+    return os.path.join(HERE, "build", os.path.splitext(s)[0] + ".o")
+
+
+def _src_stale(s, extra_key):
+    o = _obj(s)
+    if not os.path.exists(o):
+        return True
+    try:
+        with open(o + ".flags") as f:
+            if f.read() != extra_key:
+                return True
+    except OSError:
+        return True
+    t = os.path.getmtime(o)
+    return any(os.path.getmtime(d) > t for d in list(deps_of(os.path.join(CSRC, s))) + [os.path.abspath(__file__)])
+
+
 def stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    deps = set()
+    for s in SOURCES:
+        deps |= deps_of(os.path.join(CSRC, s))
+    return any(os.path.getmtime(d) > t for d in list(deps) + [os.path.abspath(__file__)])
 
 
 def build(force=False, verbose=False, extra=()):
+    """Recompiles only the translation units whose source, headers or flags changed (one nvcc process per unit, in parallel)."""
     extra = list(extra) + os.environ.get("MM_NVCC_EXTRA", "").split()      # e.g. -DMM_PLASTIC_MINBLOCKS=3 for tuning sweeps
-    if not force and not stale():
+    if not force and not stale() and not extra:
         return SO
+    key = " ".join(NVCC_FLAGS + extra)
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        o = _obj(s)
+        objs.append(o)
+        if not force and not _src_stale(s, key):
+            continue
         cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             print(" ".join(cmd))
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(o)
-    for s, p in procs:
+        procs.append((s, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = None
+    for s, o, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:
             sys.stdout.write(out)
         if p.returncode:
-            raise RuntimeError("nvcc failed on %s" % s)
+            failed = failed or s
+            if os.path.exists(o):
+                os.remove(o)
+        else:
+            with open(o + ".flags", "w") as f:
+                f.write(key)
+    if failed:
+        raise RuntimeError("nvcc failed on %s" % failed)
     cmd = [nvcc(), "-shared", "-o", SO] + objs + ["-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
     return SO

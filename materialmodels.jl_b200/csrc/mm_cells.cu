@@ -51,7 +51,7 @@ struct HyperCellAcc {
 struct CellArgs {
     const double* dNdx; const double* dOmega; const double* ue; const double* state_in;
     double* fe; double* ke; double* sig; double* tan; double* state_out;
-    uint8_t* flags; uint8_t* iters; int32_t* n_fail;
+    uint8_t* flags; uint16_t* iters; int32_t* n_fail;
     int64_t ncell;
 };
 
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_ke
         int it = 0;
         const int flag = plastic_point(kp, acc, &it);
         if (a.flags) a.flags[i] = (uint8_t)flag;
-        if (a.iters) a.iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if (a.iters) a.iters[i] = (uint16_t)(it > 65535 ? 65535 : it);
         if ((flag & MM_FLAG_FAILED) && a.n_fail) atomicAdd(a.n_fail, 1);
     }
     // fe[a][k] = Σ_q (σ ⋅ ∇N_a)_k dΩ
@@ -373,7 +373,7 @@ int mm_cells_linear_elastic(const MMLinearElastic* p, int nn, int nq, const doub
 }
 
 int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, const double* state_in, double* fe,
-                     double* ke_out, double* sig, double* tan, double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell,
+                     double* ke_out, double* sig, double* tan, double* state_out, uint8_t* flags, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell,
                      void* stream) {
     if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !state_in || !fe || !state_out))) return set_error(MM_ERR_ARG, "mm_cells_plastic: bad argument");
     CellArgs a{dNdx, dOmega, ue, state_in, fe, ke_out, sig, tan, state_out, flags, iters, n_fail, ncell};

@@ -20,13 +20,13 @@ struct CrystalGeneralOp {
     __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : (a == 1 ? 36 : 42); }
     CrystalK k;
     uint16_t* active;
-    uint8_t* iters;
+    uint16_t* iters;
     int32_t* n_fail;
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch& scr) const {
         int it = 0;
         const unsigned mask = crystal_point(k, acc, &it, scr.base, scr.stride);
         if (active) active[i] = (uint16_t)mask;
-        if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if (iters) iters[i] = (uint16_t)(it > 65535 ? 65535 : it);
         if ((mask & MM_ACTIVE_FAILED) && n_fail) atomicAdd(n_fail, 1);
     }
 };
@@ -52,7 +52,7 @@ template <int LAYOUT> struct DirectAcc {
 #define MM_FIXUP_BS 32
 #define MM_FIXUP_RANGE 4096
 template <int LAYOUT>
-__global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint8_t* iters, int32_t* n_fail, const int64_t N,
+__global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, int32_t* n_fail, const int64_t N,
                                                                     const int64_t nranges) {
     __shared__ uint16_t list[MM_FIXUP_RANGE];
     __shared__ int count, next;
@@ -89,12 +89,26 @@ __global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const Crysta
                 DirectAcc<LAYOUT> acc(p, N, i);
                 const unsigned mask = crystal_gen_finalize(k, acc, S);
                 active[i] = (uint16_t)mask;
-                if (iters) iters[i] = (uint8_t)(S.iters > 255 ? 255 : S.iters);
+                if (iters) iters[i] = (uint16_t)(S.iters > 65535 ? 65535 : S.iters);
                 if ((mask & MM_ACTIVE_FAILED) && n_fail) atomicAdd(n_fail, 1);
                 has = false;
             }
         }
     }
+}
+
+// tuning / A-B switches, read from the environment ONCE per process (tools/README.md) — never on the per-call path
+struct CrystalKnobs { int thresh, chunk, fixup_per_sm; bool force_general; };
+static const CrystalKnobs& crystal_knobs() {
+    static const CrystalKnobs k = [] {
+        CrystalKnobs v{0, 0, 0, false};
+        if (const char* e = getenv("MM_CRYSTAL_THRESH")) v.thresh = atoi(e);
+        if (const char* e = getenv("MM_CRYSTAL_CHUNK")) v.chunk = atoi(e);
+        if (const char* e = getenv("MM_FIXUP_PER_SM")) v.fixup_per_sm = atoi(e);
+        if (const char* e = getenv("MM_CRYSTAL_FORCE_GENERAL")) v.force_general = (e[0] == '1');
+        return v;
+    }();
+    return k;
 }
 
 #ifndef MM_CRYSTAL_BS
@@ -129,7 +143,7 @@ template <int LAYOUT> struct DirectAccRW : DirectAcc<LAYOUT> {
 
 template <bool HASQ, bool INTPOW, int LAYOUT, int BS>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_MINBLOCKS)
-crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint8_t* iters, const int64_t N, const int chunk, const int thresh) {
+crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, const int64_t N, const int chunk, const int thresh) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     const unsigned FULL = 0xffffffffu;
@@ -167,7 +181,7 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
                     for (int i = 0; i < 12; ++i) acc.template out<2>(30 + i, scr(XS + i));
                 }
                 active[my] = (uint16_t)(L.bad ? MM_ACTIVE_NEEDS_GENERAL : (L.converged ? 0u : MM_ACTIVE_FAILED));
-                if (iters) iters[my] = (uint8_t)(L.bad ? 0 : (L.iters > 255 ? 255 : L.iters));
+                if (iters) iters[my] = (uint16_t)(L.bad ? 0 : (L.iters > 65535 ? 65535 : L.iters));
                 has_work = false; finished = false;
             }
         }
@@ -198,7 +212,7 @@ crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, in
 }
 
 template <bool HASQ, bool INTPOW, int LAYOUT>
-int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
+int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
     constexpr int BS = MM_CRYSTAL_BS, FBS = MM_CRYSTAL_FINISH_BS;
     constexpr size_t smem = (size_t)MM_CRYSTAL_SCRATCH * BS * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
     static SmemOptIn optin_newton, optin_finish;
@@ -210,9 +224,9 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint8_t* iter
     if (chunk > 1024) chunk = 1024;
     if (chunk < 64) chunk = 64;
     chunk = (chunk + 31) / 32 * 32;
-    int thresh = MM_CRYSTAL_THRESH;
-    if (const char* t = getenv("MM_CRYSTAL_THRESH")) thresh = atoi(t);          // tuning knobs
-    if (const char* c = getenv("MM_CRYSTAL_CHUNK")) chunk = atoi(c);
+    const CrystalKnobs& kn = crystal_knobs();
+    const int thresh = kn.thresh > 0 ? kn.thresh : MM_CRYSTAL_THRESH;
+    if (kn.chunk > 0) chunk = kn.chunk;
     const int64_t warps = (N + chunk - 1) / chunk;
     const int64_t blocks = (warps + (BS / 32) - 1) / (BS / 32);
     crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, N, (int)chunk, thresh);
@@ -223,12 +237,12 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint8_t* iter
 }
 
 template <bool HASQ, int LAYOUT>
-int launch_crystal_by_exponent(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
+int launch_crystal_by_exponent(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
     return k.m_int ? launch_crystal_two_kernel<HASQ, true, LAYOUT>(k, active, iters, n_fail, ptrs, N, st)
                    : launch_crystal_two_kernel<HASQ, false, LAYOUT>(k, active, iters, n_fail, ptrs, N, st);
 }
 
-int launch_crystal_general(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
+int launch_crystal_general(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
     if (N == 0) return MM_OK;
     CrystalGeneralOp op;
     op.k = k; op.active = active; op.iters = iters; op.n_fail = n_fail;
@@ -236,7 +250,7 @@ int launch_crystal_general(const CrystalK& k, uint16_t* active, uint8_t* iters, 
 }
 
 template <bool HASQ>
-int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint8_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
+int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
     if (N == 0) return MM_OK;
     int rc;
     if (layout == 0)      rc = launch_crystal_by_exponent<HASQ, 0>(k, active, iters, n_fail, ptrs, N, st);
@@ -244,8 +258,7 @@ int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint8_t* iter
     else return set_error(MM_ERR_ARG, "mm_crystal: unknown layout %d", layout);
     if (rc) return rc;
     const int64_t nranges = (N + MM_FIXUP_RANGE - 1) / MM_FIXUP_RANGE;
-    int per_sm = 5;
-    if (const char* e = getenv("MM_FIXUP_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;      // tuning knob
+    const int per_sm = crystal_knobs().fixup_per_sm > 0 ? crystal_knobs().fixup_per_sm : 5;
     int64_t blocks = (int64_t)sm_count() * per_sm;
     if (blocks > nranges) blocks = nranges;
     if (layout == 0) crystal_fixup_kernel<0><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges);
@@ -258,7 +271,7 @@ int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint8_t* iter
 using namespace mm;
 
 extern "C" int mm_crystal(const MMCrystal* p, const double* deps, double dt, const double* state_in, double* sig, double* tan,
-                          double* state_out, uint16_t* active, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
+                          double* state_out, uint16_t* active, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
                           int64_t N, int layout, void* stream) {
     if (!p || N < 0 || (N > 0 && (!deps || !state_in || !sig || !state_out))) return set_error(MM_ERR_ARG, "mm_crystal: bad argument");
     if (p->nslip != MM_NSLIP) return set_error(MM_ERR_ARG, "mm_crystal: nslip must be %d (got %d)", MM_NSLIP, p->nslip);
@@ -267,8 +280,7 @@ extern "C" int mm_crystal(const MMCrystal* p, const double* deps, double dt, con
                    opts ? opts->tol : 1e-8, opts ? opts->max_iter : 100);
     Ptrs<2, 3> ptrs; ptrs.in[0] = deps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = state_out;
     cudaStream_t st = (cudaStream_t)stream;
-    const char* force = getenv("MM_CRYSTAL_FORCE_GENERAL");      // debugging / A-B timing switch
-    if (!k.h_struct || (force && force[0] == '1')) return launch_crystal_general(k, active, iters, n_fail, ptrs, N, layout, st);
+    if (!k.h_struct || crystal_knobs().force_general) return launch_crystal_general(k, active, iters, n_fail, ptrs, N, layout, st);
     // the structured path needs a per-point flag array for its fix-up pass; callers normally pass `active`,
     // otherwise a stream-ordered temporary is used (the only allocation this library ever makes on a compute call)
     uint16_t* flags = active;

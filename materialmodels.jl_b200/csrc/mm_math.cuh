@@ -157,8 +157,13 @@ MM_HD PlasticK make_plastic_k(double E, double nu, double sigma_y, double H, dou
 // store twice with complementary half-empty lane masks — partially written 32 B sectors, measured 2.2x slower.
 // the three ingredients of the consistent tangent  ∂σ∂ε = Eᵉ − gxi I_dev + u ⊗ n  (elastic point: gxi = 0, u = 0)
 struct PlasticTangentParts { double gxi; double u[6], n[6]; };
+// Spelled with explicit fma so that the device kernels and the host-side expander of the compact return (mm_expand.cpp, which
+// rebuilds the dense tangent from the stored {gxi, u, n}) round identically: both evaluate fma(u_I, n_J, fma(-gxi, I_dev, Eᵉ)).
+MM_HD double plastic_tangent_entry_lg(double lam, double G, double gxi, const double* u, const double* n, int I, int J) {
+    return fma(u[I], n[J], fma(-gxi, idev_entry(I, J), iso_entry(I, J, lam, G)));
+}
 MM_HD double plastic_tangent_entry(const PlasticK& k, const PlasticTangentParts& tp, int I, int J) {
-    return (iso_entry(I, J, k.lam, k.G) - tp.gxi * idev_entry(I, J)) + tp.u[I] * tp.n[J];
+    return plastic_tangent_entry_lg(k.lam, k.G, tp.gxi, tp.u, tp.n, I, J);
 }
 // plastic_point_parts: the update without the 36 tangent stores (the dimension wrappers evaluate only the entries they need per outer pass)
 template <class Acc> MM_HD int plastic_point_parts(const PlasticK& k, Acc& acc, int* iters_out, PlasticTangentParts& tp) {

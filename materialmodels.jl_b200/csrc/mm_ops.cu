@@ -23,13 +23,31 @@ struct PlasticOp {
     __host__ __device__ static constexpr int out_nc(int a) { return a == 0 ? 6 : (a == 1 ? 36 : 14); }
     PlasticK k;
     uint8_t* flags;
-    uint8_t* iters;
+    uint16_t* iters;
     int32_t* n_fail;
+    // parts_mode (the producer half of the compact return, mm_compact.cu): output 1 receives the tangent in its FACTORED form
+    // {gξ, u(6), n(6)} — components 0..12 of the 36 — instead of the 36 entries.  A run-time switch inside the ONE kernel rather than
+    // a second instantiation on purpose: the σ / state arithmetic (and nvcc's fma contraction choices in it) are then the very same
+    // machine code for the dense and the compact return, which is what makes the two bit-identical.
+    int parts_mode;
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
         int it = 0;
-        const int flag = plastic_point(k, acc, &it);
+        PlasticTangentParts tp;
+        const int flag = plastic_point_parts(k, acc, &it, tp);
+        if (acc.template has_out<1>()) {
+            if (parts_mode) {
+                acc.template out<1>(0, tp.gxi);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { acc.template out<1>(1 + c, tp.u[c]); acc.template out<1>(7 + c, tp.n[c]); }
+            } else {
+#pragma unroll
+                for (int J = 0; J < 6; ++J)
+#pragma unroll
+                    for (int I = 0; I < 6; ++I) acc.template out<1>(I + 6 * J, plastic_tangent_entry(k, tp, I, J));
+            }
+        }
         if (flags) flags[i] = (uint8_t)flag;
-        if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if (iters) iters[i] = (uint16_t)(it > 65535 ? 65535 : it);
         if ((flag & MM_FLAG_FAILED) && n_fail) atomicAdd(n_fail, 1);
     }
 };
@@ -158,6 +176,17 @@ template <int MODEL> int launch_hyper_energy(const HyperK& k, const double* stra
     return launch_points<HyperEnergyOp<MODEL, 0>, 256, MM_SMALL_AOS_BS>(op, p, N, layout, st, "mm_hyper_energy");
 }
 
+// internal (mm_compact.cu): the J2 update with output 1 in factored form — SoA: parts[c*N + i], c < 13; AoS: parts[i*36 + c] (the tile
+// kernel stages output 1 with its compile-time stride of 36; only the first 13 slots of a point are meaningful)
+int launch_plastic_parts(const MMPlastic* p, const MMNewtonOpts* opts, const double* eps, const double* state_in, double* sig, double* parts, double* state_out,
+                         uint8_t* flags, uint16_t* iters, int32_t* n_fail, int64_t N, int layout, cudaStream_t st) {
+    PlasticOp op;
+    op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
+    op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 1;
+    Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = parts; ptrs.out[2] = state_out;
+    return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, st, "mm_plastic_compact");
+}
+
 }  // namespace mm
 
 using namespace mm;
@@ -172,11 +201,11 @@ int mm_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig, 
 }
 
 int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, double* sig, double* tan, double* state_out,
-               uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout, void* stream) {
+               uint8_t* flags, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout, void* stream) {
     if (!p || N < 0 || (N > 0 && (!eps || !state_in || !sig || !state_out))) return set_error(MM_ERR_ARG, "mm_plastic: bad argument");
     PlasticOp op;
     op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
-    op.flags = flags; op.iters = iters; op.n_fail = n_fail;
+    op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 0;
     Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = state_out;
     return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
 }

@@ -40,7 +40,7 @@ template <int KIND> struct WrappedPlasticOp {
     PlasticK k;
     double tol; int max_iter;
     uint8_t* flags;
-    uint8_t* iters;
+    uint16_t* iters;
     uint8_t* outer_iters;
     int32_t* n_fail;
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
@@ -55,7 +55,7 @@ template <int KIND> struct WrappedPlasticOp {
 #pragma unroll
         for (int c = 0; c < 14; ++c) acc.template out<2>(c, io.st_out[c]);
         if (flags) flags[i] = (uint8_t)flag;
-        if (iters) iters[i] = (uint8_t)(iit > 255 ? 255 : iit);
+        if (iters) iters[i] = (uint16_t)(iit > 65535 ? 65535 : iit);
         if (outer_iters) outer_iters[i] = (uint8_t)oit;
         if ((flag & 0xC0) && n_fail) atomicAdd(n_fail, 1);
     }
@@ -120,7 +120,7 @@ template <int KIND> struct WrappedCrystalOp {
     CrystalK k;
     double tol; int max_iter;
     uint16_t* active;
-    uint8_t* iters;
+    uint16_t* iters;
     uint8_t* outer_iters;
     int32_t* n_fail;
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch& scr) const {
@@ -136,13 +136,13 @@ template <int KIND> struct WrappedCrystalOp {
             acc, tol, max_iter, &oit, &iit);
         if (flag & 0x40) mask |= MM_ACTIVE_WRAPPER_FAILED;
         if (active) active[i] = (uint16_t)mask;
-        if (iters) iters[i] = (uint8_t)(iit > 255 ? 255 : iit);
+        if (iters) iters[i] = (uint16_t)(iit > 65535 ? 65535 : iit);
         if (outer_iters) outer_iters[i] = (uint8_t)oit;
         if ((flag & 0xC0) && n_fail) atomicAdd(n_fail, 1);
     }
 };
 template <int KIND>
-int launch_wrapped_crystal(const CrystalK& k, const double* deps, const double* sin, double* sig, double* tan, double* sout, uint16_t* active, uint8_t* iters,
+int launch_wrapped_crystal(const CrystalK& k, const double* deps, const double* sin, double* sig, double* tan, double* sout, uint16_t* active, uint16_t* iters,
                            uint8_t* oit, int32_t* n_fail, const MMNewtonOpts* w, int64_t N, int layout, cudaStream_t st) {
     WrappedCrystalOp<KIND> op;
     op.k = k; op.tol = w ? w->tol : 1e-8; op.max_iter = w ? w->max_iter : 10;
@@ -160,7 +160,7 @@ int launch_wrapped_elastic(const MMLinearElastic* p, const double* eps, double* 
     return launch_points<WrappedElasticOp<KIND>, 256, 128>(op, ptrs, N, layout, st, "mm_wrapped_linear_elastic");
 }
 template <int KIND>
-int launch_wrapped_plastic(const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags, uint8_t* iters,
+int launch_wrapped_plastic(const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags, uint16_t* iters,
                            uint8_t* oit, int32_t* n_fail, const MMNewtonOpts* o, const MMNewtonOpts* w, int64_t N, int layout, cudaStream_t st) {
     WrappedPlasticOp<KIND> op;
     op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, o ? o->tol : 1e-8, o ? o->max_iter : 1000);
@@ -212,7 +212,7 @@ int mm_wrapped_transversely_isotropic(int dim_kind, const MMTransverselyIsotropi
 }
 
 int mm_wrapped_crystal(int dim_kind, const MMCrystal* p, const double* deps_red, double dt, const double* state_in, double* sig_red, double* tan_red,
-                       double* state_out, uint16_t* active, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
+                       double* state_out, uint16_t* active, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
                        const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream) {
     if (!p || N < 0 || (N > 0 && (!deps_red || !state_in || !sig_red || !state_out))) return set_error(MM_ERR_ARG, "mm_wrapped_crystal: bad argument");
     if (p->nslip != MM_NSLIP) return set_error(MM_ERR_ARG, "mm_wrapped_crystal: nslip must be %d (got %d)", MM_NSLIP, p->nslip);
@@ -233,7 +233,7 @@ int mm_wrapped_crystal(int dim_kind, const MMCrystal* p, const double* deps_red,
 }
 
 int mm_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red, double* state_out,
-                       uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts, const MMNewtonOpts* wrapper_opts,
+                       uint8_t* flags, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts, const MMNewtonOpts* wrapper_opts,
                        int64_t N, int layout, void* stream) {
     if (!p || N < 0 || (N > 0 && (!eps_red || !state_in || !sig_red || !state_out))) return set_error(MM_ERR_ARG, "mm_wrapped_plastic: bad argument");
     cudaStream_t st = (cudaStream_t)stream;

@@ -67,6 +67,13 @@ class Plastic(AbstractMaterial):
         self.H_α = -2 / 3 * (1 - self.r) * self.H      # Plastic.jl:32
         self._c = _abi.MMPlastic(self.E, self.ν, self.σ_y, self.H, self.r, self.κ_inf, self.α_inf)
 
+    @property
+    def Eᵉ(self):
+        """the one stored elastic tangent every elastic point returns — reference src/Plastic.jl:23, :135"""
+        from .api import elastic_tangent_3D
+
+        return elastic_tangent_3D(self.E, self.ν)
+
 
 class _Hyper(AbstractMaterial):
     MODEL = None

@@ -93,7 +93,7 @@ int mmo_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig,
 }
 
 int mmo_plastic(const MMPlastic* p, const double* eps, const double* state_in, double* sig, double* tan, double* state_out,
-                uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout) {
+                uint8_t* flags, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout) {
     PlasticM m = make_plastic(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf);
     NewtonOpts o{opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000};
     View ve = V(eps, N, 6, layout), vi = V(state_in, N, 14, layout), vs = V(sig, N, 6, layout), vt = V(tan, N, 36, layout),
@@ -117,7 +117,7 @@ int mmo_plastic(const MMPlastic* p, const double* eps, const double* state_in, d
         for (int c = 0; c < 6; ++c) vo.at(i, 7 + c) = sn.alpha.a[c];
         vo.at(i, 13) = sn.mu;
         if (flags) flags[i] = (uint8_t)flag;
-        if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if (iters) iters[i] = (uint16_t)(it > 65535 ? 65535 : it);
     }
     if (n_fail) *n_fail += (int32_t)fails;
     return 0;
@@ -152,7 +152,7 @@ int mmo_hyper_ad(int model, const MMHyper* p, const double* C6, double* psi, dou
 }
 
 int mmo_crystal(const MMCrystal* p, const double* deps, double dt, const double* state_in, double* sig, double* tan, double* state_out,
-                uint16_t* active, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout) {
+                uint16_t* active, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout) {
     if (p->nslip != 12) return MM_ERR_ARG;
     CrystalM<12> m;
     m.E = p->E; m.nu = p->nu; m.tau_y = p->tau_y; m.H_iso = p->H_iso; m.H_kin = p->H_kin; m.q = p->q; m.alpha_inf = p->alpha_inf;
@@ -178,7 +178,7 @@ int mmo_crystal(const MMCrystal* p, const double* deps, double dt, const double*
         for (int c = 0; c < 6; ++c) vo.at(i, c) = sn.sigma.a[c];
         for (int k = 0; k < 12; ++k) { vo.at(i, 6 + k) = sn.kappa[k]; vo.at(i, 18 + k) = sn.alpha[k]; vo.at(i, 30 + k) = sn.mu[k]; }
         if (active) active[i] = (uint16_t)act;
-        if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if (iters) iters[i] = (uint16_t)(it > 65535 ? 65535 : it);
     }
     if (n_fail) *n_fail += (int32_t)fails;
     return 0;
@@ -250,7 +250,7 @@ int mmo_wrapped_linear_elastic(int kind, const MMLinearElastic* p, const double*
 }
 
 int mmo_wrapped_plastic(int kind, const MMPlastic* p, const double* eps_red, const double* state_in, double* sig_red, double* tan_red,
-                        double* state_out, uint8_t* flags, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail,
+                        double* state_out, uint8_t* flags, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail,
                         const MMNewtonOpts* opts, const MMNewtonOpts* wopts, int64_t N, int layout) {
     PlasticM m = make_plastic(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf);
     NewtonOpts o{opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000};
@@ -284,7 +284,7 @@ int mmo_wrapped_plastic(int kind, const MMPlastic* p, const double* eps_red, con
         for (int c = 0; c < 6; ++c) vo.at(i, 7 + c) = sn.alpha.a[c];
         vo.at(i, 13) = sn.mu;
         if (flags) flags[i] = (uint8_t)flag;
-        if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if (iters) iters[i] = (uint16_t)(it > 65535 ? 65535 : it);
         if (outer_iters) outer_iters[i] = (uint8_t)oit;
     }
     if (n_fail) *n_fail += (int32_t)fails;
@@ -315,7 +315,7 @@ int mmo_wrapped_transviso(int kind, const MMTransverselyIsotropic* p, const doub
 }
 
 int mmo_wrapped_crystal(int kind, const MMCrystal* p, const double* deps_red, double dt, const double* state_in, double* sig_red, double* tan_red,
-                        double* state_out, uint16_t* active, uint8_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
+                        double* state_out, uint16_t* active, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
                         const MMNewtonOpts* wopts, int64_t N, int layout) {
     if (p->nslip != 12) return MM_ERR_ARG;
     CrystalM<12> m;
@@ -350,7 +350,7 @@ int mmo_wrapped_crystal(int kind, const MMCrystal* p, const double* deps_red, do
         for (int c = 0; c < 6; ++c) vo.at(i, c) = sn.sigma.a[c];
         for (int k = 0; k < 12; ++k) { vo.at(i, 6 + k) = sn.kappa[k]; vo.at(i, 18 + k) = sn.alpha[k]; vo.at(i, 30 + k) = sn.mu[k]; }
         if (active) active[i] = (uint16_t)act;
-        if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+        if (iters) iters[i] = (uint16_t)(it > 65535 ? 65535 : it);
         if (outer_iters) outer_iters[i] = (uint8_t)oit;
     }
     if (n_fail) *n_fail += (int32_t)fails;
@@ -362,7 +362,7 @@ int mmo_wrapped_crystal(int kind, const MMCrystal* p, const double* deps_red, do
 // model: 0 LinearElastic (params = MMLinearElastic), 1 Plastic (params = MMPlastic), 2 TransverselyIsotropic (params =
 // MMTransverselyIsotropic, state_in = a3[3][P]).  Arrays as include/mmb200.h mm_cells_*.
 int mmo_cells(int model, const void* params, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, const double* state_in,
-              double* fe, double* ke, double* sig_out, double* tan_out, double* state_out, uint8_t* flags, uint8_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
+              double* fe, double* ke, double* sig_out, double* tan_out, double* state_out, uint8_t* flags, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts,
               int64_t ncell) {
     const int64_t P = ncell * nq;
     LinearElasticM le{}; PlasticM pm{}; TransvIsoM tm{};
@@ -401,7 +401,7 @@ int mmo_cells(int model, const void* params, int nn, int nq, const double* dNdx,
                 for (int c = 0; c < 6; ++c) state_out[(int64_t)(7 + c) * P + i] = sn.alpha.a[c];
                 state_out[(int64_t)13 * P + i] = sn.mu;
                 if (flags) flags[i] = (uint8_t)flag;
-                if (iters) iters[i] = (uint8_t)(it > 255 ? 255 : it);
+                if (iters) iters[i] = (uint16_t)(it > 65535 ? 65535 : it);
             }
             if (sig_out) for (int c = 0; c < 6; ++c) sig_out[(int64_t)c * P + i] = sig.a[c];
             if (tan_out) for (int c = 0; c < 36; ++c) tan_out[(int64_t)c * P + i] = tan.a[c];

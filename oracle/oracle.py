@@ -139,7 +139,7 @@ def plastic(params, eps, state, layout=SOA, tol=1e-8, max_iter=1000):
     eps, N = _n(eps, layout)
     state = np.ascontiguousarray(state, dtype=np.float64)
     sig, tan, st = _alloc(6, N, layout), _alloc(36, N, layout), _alloc(14, N, layout)
-    flags, iters = np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+    flags, iters = np.zeros(N, np.uint8), np.zeros(N, np.uint16)
     nfail = np.zeros(1, np.int32)
     o = abi.MMNewtonOpts(tol, max_iter, 0)
     rc = lib().mmo_plastic(C.byref(p), _ptr(eps), _ptr(state), _ptr(sig), _ptr(tan), _ptr(st), _ptr(flags), _ptr(iters), _ptr(nfail), C.byref(o), N, layout)
@@ -174,7 +174,7 @@ def crystal(p, deps, state, dt=1.0, layout=SOA, tol=1e-8, max_iter=100):
     deps, N = _n(deps, layout)
     state = np.ascontiguousarray(state, dtype=np.float64)
     sig, tan, st = _alloc(6, N, layout), _alloc(36, N, layout), _alloc(42, N, layout)
-    active, iters = np.zeros(N, np.uint16), np.zeros(N, np.uint8)
+    active, iters = np.zeros(N, np.uint16), np.zeros(N, np.uint16)
     nfail = np.zeros(1, np.int32)
     o = abi.MMNewtonOpts(tol, max_iter, 0)
     rc = lib().mmo_crystal(C.byref(p), _ptr(deps), dt, _ptr(state), _ptr(sig), _ptr(tan), _ptr(st), _ptr(active), _ptr(iters), _ptr(nfail), C.byref(o), N, layout)
@@ -228,7 +228,7 @@ def wrapped_plastic(kind, params, eps_red, state, layout=SOA, tol=1e-8, max_iter
     eps_red, N = _n(eps_red, layout)
     state = np.ascontiguousarray(state, dtype=np.float64)
     sig, tan, st = _alloc(nc, N, layout), _alloc(nc * nc, N, layout), _alloc(14, N, layout)
-    flags, iters, oit = np.zeros(N, np.uint8), np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+    flags, iters, oit = np.zeros(N, np.uint8), np.zeros(N, np.uint16), np.zeros(N, np.uint8)
     nfail = np.zeros(1, np.int32)
     o, w = abi.MMNewtonOpts(tol, max_iter, 0), abi.MMNewtonOpts(wtol, wmax_iter, 0)
     rc = lib().mmo_wrapped_plastic(kind, C.byref(p), _ptr(eps_red), _ptr(state), _ptr(sig), _ptr(tan), _ptr(st), _ptr(flags), _ptr(iters),
@@ -317,7 +317,7 @@ def cells(model, params, nn, nq, dNdx, dOmega, ue, state=None, want_tangent=True
     else:
         p = params if isinstance(params, abi.MMPlastic) else abi.MMPlastic(*params)
         st_in = np.ascontiguousarray(state, dtype=np.float64); st_out = np.zeros((14, P))
-        flags, iters = np.zeros(P, np.uint8), np.zeros(P, np.uint8)
+        flags, iters = np.zeros(P, np.uint8), np.zeros(P, np.uint16)
     nfail = np.zeros(1, np.int32)
     o = abi.MMNewtonOpts(tol, max_iter, 0)
     rc = lib().mmo_cells(model, C.byref(p), nn, nq, _ptr(dNdx), _ptr(dOmega), _ptr(ue), _ptr(st_in), _ptr(fe), _ptr(ke), _ptr(sig), _ptr(tan), _ptr(st_out),
@@ -344,7 +344,7 @@ def wrapped_crystal(kind, p, deps_red, state, dt=1.0, layout=SOA, tol=1e-8, max_
     deps_red, N = _n(deps_red, layout)
     state = np.ascontiguousarray(state, dtype=np.float64)
     sig, tan, st = _alloc(nc, N, layout), _alloc(nc * nc, N, layout), _alloc(42, N, layout)
-    active, iters, oit = np.zeros(N, np.uint16), np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+    active, iters, oit = np.zeros(N, np.uint16), np.zeros(N, np.uint16), np.zeros(N, np.uint8)
     nfail = np.zeros(1, np.int32)
     o, w = abi.MMNewtonOpts(tol, max_iter, 0), abi.MMNewtonOpts(wtol, wmax_iter, 0)
     rc = lib().mmo_wrapped_crystal(kind, C.byref(p), _ptr(deps_red), dt, _ptr(state), _ptr(sig), _ptr(tan), _ptr(st), _ptr(active), _ptr(iters), _ptr(oit),

@@ -23,13 +23,27 @@ int twin_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig
     for (int64_t i = 0; i < N; ++i) { HostAcc<1, 2> a{{eps}, {sig, tan}, N, i}; mm::linear_elastic_point(k, a); }
     return 0;
 }
-int twin_plastic(const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags, uint8_t* iters,
+int twin_plastic(const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags, uint16_t* iters,
                  double tol, int max_iter, int64_t N) {
     mm::PlasticK k = mm::make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, tol, max_iter);
     for (int64_t i = 0; i < N; ++i) {
         HostAcc<2, 3> a{{eps, sin}, {sig, tan, sout}, N, i};
         int it = 0; int f = mm::plastic_point(k, a, &it);
-        flags[i] = (uint8_t)f; iters[i] = (uint8_t)it;
+        flags[i] = (uint8_t)f; iters[i] = (uint16_t)it;
+    }
+    return 0;
+}
+// the factored tangent {gξ, u, n} (parts[13][N]) of the same update: what the compact return ships for a yielded point
+int twin_plastic_parts(const MMPlastic* p, const double* eps, const double* sin, double* sig, double* parts, double* sout, uint8_t* flags, uint16_t* iters,
+                       double tol, int max_iter, int64_t N) {
+    mm::PlasticK k = mm::make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, tol, max_iter);
+    for (int64_t i = 0; i < N; ++i) {
+        HostAcc<2, 3> a{{eps, sin}, {sig, nullptr, sout}, N, i};
+        int it = 0; mm::PlasticTangentParts tp;
+        int f = mm::plastic_point_parts(k, a, &it, tp);
+        parts[i] = tp.gxi;
+        for (int c = 0; c < 6; ++c) { parts[(int64_t)(1 + c) * N + i] = tp.u[c]; parts[(int64_t)(7 + c) * N + i] = tp.n[c]; }
+        flags[i] = (uint8_t)f; iters[i] = (uint16_t)it;
     }
     return 0;
 }
@@ -51,7 +65,7 @@ struct HostScratch { double v[MM_CRYSTAL_SCRATCH]; double& operator()(int j) { r
 
 // mode 0: general pivoted path; mode 1: structured fast path (falls back like the kernel does)
 int twin_crystal_mode(const MMCrystal* p, const double* deps, double dt, const double* sin, double* sig, double* tan, double* sout, uint16_t* active,
-                      uint8_t* iters, double tol, int max_iter, int64_t N, int mode, int64_t* n_fallback) {
+                      uint16_t* iters, double tol, int max_iter, int64_t N, int mode, int64_t* n_fallback) {
     mm::CrystalK k;
     mm::make_crystal_k(k, p->E, p->nu, p->tau_y, p->H_kin, p->alpha_inf, p->t_star, p->sigma_c, p->m, p->MS, p->H, dt, tol, max_iter);
     int64_t nfb = 0;
@@ -64,35 +78,35 @@ int twin_crystal_mode(const MMCrystal* p, const double* deps, double dt, const d
             m = (k.b_h != 0.0) ? mm::crystal_point_fast<true>(k, a, scr, &it, &fb) : mm::crystal_point_fast<false>(k, a, scr, &it, &fb);
             if (fb) { ++nfb; m = mm::crystal_point(k, a, &it); }
         }
-        active[i] = (uint16_t)m; iters[i] = (uint8_t)it;
+        active[i] = (uint16_t)m; iters[i] = (uint16_t)it;
     }
     if (n_fallback) *n_fallback = nfb;
     return 0;
 }
 int twin_crystal(const MMCrystal* p, const double* deps, double dt, const double* sin, double* sig, double* tan, double* sout, uint16_t* active,
-                 uint8_t* iters, double tol, int max_iter, int64_t N) {
+                 uint16_t* iters, double tol, int max_iter, int64_t N) {
     mm::CrystalK k;
     mm::make_crystal_k(k, p->E, p->nu, p->tau_y, p->H_kin, p->alpha_inf, p->t_star, p->sigma_c, p->m, p->MS, p->H, dt, tol, max_iter);
     for (int64_t i = 0; i < N; ++i) {
         HostAcc<2, 3> a{{deps, sin}, {sig, tan, sout}, N, i};
         int it = 0; unsigned m = mm::crystal_point(k, a, &it);
-        active[i] = (uint16_t)m; iters[i] = (uint8_t)it;
+        active[i] = (uint16_t)m; iters[i] = (uint16_t)it;
     }
     return 0;
 }
 
 }  // extern "C"
 template <int KIND> static void twin_wrapped_plastic_k(const mm::PlasticK& k, const double* eps, const double* sin, double* sig, double* tan, double* sout,
-                                                       uint8_t* flags, uint8_t* iters, uint8_t* oiters, double wtol, int wmax, int64_t N) {
+                                                       uint8_t* flags, uint16_t* iters, uint8_t* oiters, double wtol, int wmax, int64_t N) {
     for (int64_t i = 0; i < N; ++i) {
         HostAcc<2, 3> a{{eps, sin}, {sig, tan, sout}, N, i};
         int oit = 0, iit = 0;
         int f = mm::wrapped_point<KIND, 14>([&](mm::RegIO<14>& io, int* it) { return mm::plastic_point(k, io, it); }, a, wtol, wmax, &oit, &iit);
-        flags[i] = (uint8_t)f; iters[i] = (uint8_t)iit; oiters[i] = (uint8_t)oit;
+        flags[i] = (uint8_t)f; iters[i] = (uint16_t)iit; oiters[i] = (uint8_t)oit;
     }
 }
 extern "C" int twin_wrapped_plastic(int kind, const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags,
-                         uint8_t* iters, uint8_t* oiters, double tol, int max_iter, double wtol, int wmax, int64_t N) {
+                         uint16_t* iters, uint8_t* oiters, double tol, int max_iter, double wtol, int wmax, int64_t N) {
     mm::PlasticK k = mm::make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, tol, max_iter);
     switch (kind) {
         case 1: twin_wrapped_plastic_k<1>(k, eps, sin, sig, tan, sout, flags, iters, oiters, wtol, wmax, N); break;
@@ -105,7 +119,7 @@ extern "C" int twin_wrapped_plastic(int kind, const MMPlastic* p, const double* 
     return 0;
 }
 template <int KIND> static void twin_wrapped_crystal_k(const mm::CrystalK& k, const double* deps, const double* sin, double* sig, double* tan, double* sout,
-                                                       uint16_t* active, uint8_t* iters, uint8_t* oiters, double wtol, int wmax, int64_t N) {
+                                                       uint16_t* active, uint16_t* iters, uint8_t* oiters, double wtol, int wmax, int64_t N) {
     for (int64_t i = 0; i < N; ++i) {
         HostAcc<2, 3> a{{deps, sin}, {sig, tan, sout}, N, i};
         int oit = 0, iit = 0; unsigned mask = 0;
@@ -119,11 +133,11 @@ template <int KIND> static void twin_wrapped_crystal_k(const mm::CrystalK& k, co
             },
             a, wtol, wmax, &oit, &iit);
         if (f & 0x40) mask |= 0x2000u;
-        active[i] = (uint16_t)mask; iters[i] = (uint8_t)(iit > 255 ? 255 : iit); oiters[i] = (uint8_t)oit;
+        active[i] = (uint16_t)mask; iters[i] = (uint16_t)(iit > 65535 ? 65535 : iit); oiters[i] = (uint8_t)oit;
     }
 }
 extern "C" int twin_wrapped_crystal(int kind, const MMCrystal* p, const double* deps, double dt, const double* sin, double* sig, double* tan, double* sout,
-                         uint16_t* active, uint8_t* iters, uint8_t* oiters, double tol, int max_iter, double wtol, int wmax, int64_t N) {
+                         uint16_t* active, uint16_t* iters, uint8_t* oiters, double tol, int max_iter, double wtol, int wmax, int64_t N) {
     mm::CrystalK k;
     mm::make_crystal_k(k, p->E, p->nu, p->tau_y, p->H_kin, p->alpha_inf, p->t_star, p->sigma_c, p->m, p->MS, p->H, dt, tol, max_iter);
     switch (kind) {

@@ -77,14 +77,14 @@ def test_no_entry_point_writes_out_of_bounds(mm, cuda_lib, N, lay, shift):
     pp = abi.MMPlastic(*[sy.PLASTIC_PARAMS[k] for k in ("E", "nu", "sigma_y", "H", "r", "kappa_inf", "alpha_inf")])
     nc, lo, hi, seed = sy.c2_strain(0)
     e2 = sy.host_uniform(N, nc, seed, lo, hi)
-    s, t, so, fl, it = G(6 * N), G(36 * N), G(14 * N), G(N, u8), G(N, u8)
+    s, t, so, fl, it = G(6 * N), G(36 * N), G(14 * N), G(N, u8), G(N, i16)
     assert lib.mm_plastic(C.byref(pp), I(e2), I(np.zeros((14, N))), s.ptr, t.ptr, so.ptr, fl.ptr, it.ptr, pn, None, N, lay, None) == 0
     for g, n in ((s, "σ"), (t, "tangent"), (so, "state"), (fl, "flags"), (it, "iters")):
         g.check("mm_plastic " + n)
     # wrapped Plastic: PlaneStress (nc 3) and UniaxialStress (nc 1)
     for kind, ncr, amp in ((abi.MM_DIM_PLANE_STRESS, 3, 1.2e-3), (abi.MM_DIM_UNIAXIAL_STRESS, 1, 2.5e-3), (abi.MM_DIM_PLANE_STRAIN, 3, 1e-3)):
         er = sy.host_uniform(N, ncr, 31, [-amp] * ncr, [amp] * ncr)
-        s, t, so, fl, it, oi = G(ncr * N), G(ncr * ncr * N), G(14 * N), G(N, u8), G(N, u8), G(N, u8)
+        s, t, so, fl, it, oi = G(ncr * N), G(ncr * ncr * N), G(14 * N), G(N, u8), G(N, i16), G(N, u8)
         assert lib.mm_wrapped_plastic(kind, C.byref(pp), I(er), I(np.zeros((14, N))), s.ptr, t.ptr, so.ptr, fl.ptr, it.ptr, oi.ptr, pn, None, None, N, lay, None) == 0
         for g, n in ((s, "σ"), (t, "tangent"), (so, "state"), (fl, "flags"), (it, "iters"), (oi, "outer iters")):
             g.check("mm_wrapped_plastic[%d] %s" % (kind, n))
@@ -127,14 +127,14 @@ def test_no_entry_point_writes_out_of_bounds(mm, cuda_lib, N, lay, shift):
         cm = mm.CrystalViscoPlastic(slipsystems=mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES), **prm)
         nc, lo, hi, seed = sy.c4_strain_increment(0)
         de = sy.host_uniform(N, nc, seed, lo, hi)
-        s, t, so, ac, it = G(6 * N), G(36 * N), G(42 * N), G(N, i16), G(N, u8)
+        s, t, so, ac, it = G(6 * N), G(36 * N), G(42 * N), G(N, i16), G(N, i16)
         assert lib.mm_crystal(C.byref(cm._c), I(de), 1.0, I(np.zeros((42, N))), s.ptr, t.ptr, so.ptr, ac.ptr, it.ptr, pn, None, N, lay, None) == 0
         for g, n in ((s, "σ"), (t, "tangent"), (so, "state"), (it, "iters"), (ac, "active")):
             g.check("mm_crystal(q=%g) %s" % (q, n))
     # wrapped crystal (general inner path, Jacobian in the shared-memory scratch column)
     for kind, ncr, amp in ((abi.MM_DIM_PLANE_STRESS, 3, 4e-3), (abi.MM_DIM_UNIAXIAL_STRESS, 1, 6e-3)):
         er = sy.host_uniform(N, ncr, 33, [-amp] * ncr, [amp] * ncr)
-        s, t, so, ac, it, oi = G(ncr * N), G(ncr * ncr * N), G(42 * N), G(N, i16), G(N, u8), G(N, u8)
+        s, t, so, ac, it, oi = G(ncr * N), G(ncr * ncr * N), G(42 * N), G(N, i16), G(N, i16), G(N, u8)
         assert lib.mm_wrapped_crystal(kind, C.byref(cm._c), I(er), 1.0, I(np.zeros((42, N))), s.ptr, t.ptr, so.ptr, ac.ptr, it.ptr, oi.ptr, pn, None, None, N,
                                       lay, None) == 0
         for g, n in ((s, "σ"), (t, "tangent"), (so, "state"), (it, "iters"), (ac, "active"), (oi, "outer iters")):
@@ -147,7 +147,7 @@ def test_no_entry_point_writes_out_of_bounds(mm, cuda_lib, N, lay, shift):
             dN = sy.host_uniform(P, 3 * nn, 71, [-1.0] * (3 * nn), [1.0] * (3 * nn))
             dO = sy.host_uniform(P, 1, 72, [0.5], [1.5])
             ue = sy.host_uniform(ncell, 3 * nn, 73, [-4e-4] * (3 * nn), [4e-4] * (3 * nn))
-            fe, kk, s, t, so, fl, it = G(3 * nn * ncell), G(9 * nn * nn * ncell), G(6 * P), G(36 * P), G(14 * P), G(P, u8), G(P, u8)
+            fe, kk, s, t, so, fl, it = G(3 * nn * ncell), G(9 * nn * nn * ncell), G(6 * P), G(36 * P), G(14 * P), G(P, u8), G(P, i16)
             assert lib.mm_cells_plastic(C.byref(pp), nn, nq, I(dN), I(dO), I(ue), I(np.zeros((14, P))), fe.ptr, kk.ptr, s.ptr, t.ptr, so.ptr, fl.ptr, it.ptr, pn,
                                         None, ncell, None) == 0
             for g, n in ((fe, "fe"), (kk, "ke"), (s, "σ"), (t, "tangent"), (so, "state"), (fl, "flags"), (it, "iters")):

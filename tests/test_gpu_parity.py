@@ -457,7 +457,7 @@ def test_crystal_in_place_state_update(mm, torch, cuda_lib, q, structure):
         inplace = st.data.clone()
         sig, tan = torch.empty_like(s_ref), torch.empty_like(t_ref)
         act = torch.empty(N, dtype=torch.int16, device="cuda")
-        it = torch.empty(N, dtype=torch.uint8, device="cuda")
+        it = torch.empty(N, dtype=torch.int16, device="cuda")
         nf = torch.zeros(1, dtype=torch.int32, device="cuda")
         P = lambda a: C.c_void_p(a.data_ptr())
         rc = cuda_lib.mm_crystal(C.byref(m._c), P(de), 1.0, P(inplace), P(sig), P(tan), P(inplace), P(act), P(it), P(nf), None, N, 0, None)

@@ -142,3 +142,96 @@ def test_small_batch_graph_loop_is_launch_bound_not_sync_bound(mm, torch):
     for a, b in zip(outs, ref):
         assert torch.equal(a, b)
     assert int(outs[3].item()) == 0
+
+
+def test_mixed_host_buffer_entry_points_from_two_threads(mm, torch, cuda_lib):
+    """mmh_* calls share ONE staging workspace (streams, device chunk buffers, fail counter) behind ONE lock: two host threads calling
+    DIFFERENT entry points at the same time (ctypes releases the GIL for the call) must each get the serial result, bit for bit —
+    with a small chunk size so that every call runs many pipeline chunks and the workspace is resized back and forth"""
+    N1, N2 = 50001, 30011
+    p = mm.Plastic(**sy.PLASTIC_PARAMS)
+    nc, lo, hi, seed = sy.c2_strain(0)
+    eps = sy.host_uniform(N1, nc, seed, lo, hi)
+    st0 = np.zeros((14, N1))
+    nh = mm.Yeoh(λ=1.0, μ=1.0, c2=-1.0, c3=1.0)
+    nc, lo, hi, seed = sy.c3_defgrad()
+    F = sy.host_uniform(N2, nc, seed, lo, hi)
+    old = cuda_lib.mmh_set_chunk_points(2048)
+    try:
+        s1, t1, n1 = mm.material_response(p, eps, mm.PlasticState(st0))
+        s2, t2, _ = mm.material_response(mm.dSdC(), nh, mm.DeformationGradient(F))
+        s3, T3, n3 = mm.material_response(p, eps, mm.PlasticState(st0), tangent="factored")
+        errs = []
+
+        def plastic_worker():
+            try:
+                for _ in range(50):
+                    a, b, c = mm.material_response(p, eps, mm.PlasticState(st0))
+                    assert np.array_equal(a, s1) and np.array_equal(b, t1) and np.array_equal(c.data, n1.data) and np.array_equal(c.iters, n1.iters)
+            except BaseException as e:      # noqa: BLE001
+                errs.append(e)
+
+        def hyper_worker():
+            try:
+                for _ in range(50):
+                    a, b, _ = mm.material_response(mm.dSdC(), nh, mm.DeformationGradient(F))
+                    assert np.array_equal(a, s2) and np.array_equal(b, t2)
+            except BaseException as e:      # noqa: BLE001
+                errs.append(e)
+
+        def compact_worker():
+            try:
+                for _ in range(50):
+                    a, T, c = mm.material_response(p, eps, mm.PlasticState(st0), tangent="factored")
+                    assert np.array_equal(a, s3) and np.array_equal(T.rows, T3.rows) and T.n_rows == T3.n_rows
+            except BaseException as e:      # noqa: BLE001
+                errs.append(e)
+
+        th = [threading.Thread(target=f) for f in (plastic_worker, hyper_worker, compact_worker)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errs, errs[0]
+        assert np.array_equal(T3.dense(), t1) and np.array_equal(n3.data, n1.data)
+    finally:
+        cuda_lib.mmh_set_chunk_points(old)
+
+
+def test_pinned_array_views_own_their_memory(mm, torch):
+    """a view of a PinnedArray keeps the page-locked block alive after the PinnedArray object (and the original array) are gone"""
+    import gc
+
+    a = mm.PinnedArray((6, 1000)).array           # the PinnedArray temporary dies here
+    a[...] = 3.0
+    v = a[2:4, 10:20]
+    del a
+    gc.collect()
+    junk = [mm.PinnedArray((6, 1000)).array for _ in range(8)]      # would recycle the block if it had been released
+    for j in junk:
+        j[...] = -1.0
+    assert float(v.sum()) == 60.0
+    pa = mm.PinnedArray((4,), np.uint16)
+    w = pa.array
+    pa.free()
+    w[:] = 7
+    assert int(w.sum()) == 28
+
+
+def test_strain_and_state_must_live_in_the_same_place(mm, torch):
+    """a device state with a host strain (or the reverse) is refused before any pointer reaches the library (it would be an illegal address)"""
+    N = 100
+    p = mm.Plastic(**sy.PLASTIC_PARAMS)
+    eps_h = np.zeros((6, N))
+    eps_d = torch.zeros((6, N), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError, match="same place"):
+        mm.material_response(p, eps_h, mm.initial_material_state(p, N))                    # default state lives on the GPU
+    with pytest.raises(ValueError, match="same place"):
+        mm.material_response(p, eps_d, mm.initial_material_state(p, N, device="cpu"))
+    cm = make_crystal(mm)
+    with pytest.raises(ValueError, match="same place"):
+        mm.material_response(cm, eps_h, mm.initial_material_state(cm, N), 1.0)
+    for bad in (torch.zeros((6, N), dtype=torch.float32, device="cuda"), torch.zeros((N, 6), dtype=torch.float64, device="cuda").T):
+        with pytest.raises(ValueError):
+            mm.material_response(p, eps_d, mm.initial_material_state(p, N), out={"stress": bad})
+    torch.cuda.synchronize()

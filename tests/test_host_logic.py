@@ -67,6 +67,19 @@ def test_api_argument_validation_without_gpu(mm):
         mm.material_response(mm.dSdC(), mm.NeoHook(λ=1.0, μ=1.0), mm.SmallStrain(np.zeros((6, 1))))
     with pytest.raises(TypeError):
         mm.initial_material_state(m)                                    # batched API needs N
+    # caller-provided output buffers are written through raw pointers: wrong dtype / layout is refused before the library is touched
+    with pytest.raises(ValueError, match="dtype"):
+        mm.material_response(m, np.zeros((6, 5)), st, out={"stress": np.zeros((6, 5), np.float32)})
+    with pytest.raises(ValueError, match="contiguous"):
+        mm.material_response(m, np.zeros((6, 5)), st, out={"stress": np.zeros((5, 6)).T})
+    with pytest.raises(ValueError, match="dtype"):
+        mm.material_response(m, np.zeros((6, 5)), st, out={"iters": np.zeros(5, np.uint8)})      # Newton counts are uint16
+    # NLsolve options: only method = :newton exists on the GPU path; anything else must fail loudly (Plastic.jl:146-147 forwards them)
+    for method in ("trust_region", ":anderson"):
+        with pytest.raises(NotImplementedError, match="newton"):
+            mm.material_response(m, np.zeros((6, 5)), st, options={"nlsolve_params": {"method": method}})
+    with pytest.raises(ValueError, match="tangent must be"):
+        mm.material_response(m, np.zeros((6, 5)), st, tangent="sparse")
 
 
 def test_product_has_no_cpu_fallback(mm, monkeypatch):
@@ -95,7 +108,7 @@ def test_twin_plastic_matches_oracle(oracle):
         eps = sy.host_uniform(N_TWIN, nc, seed, lo, hi)
         r = oracle.plastic(p, eps, st)
         sig, tan, so = np.zeros((6, N_TWIN)), np.zeros((36, N_TWIN)), np.zeros((14, N_TWIN))
-        fl, it = np.zeros(N_TWIN, np.uint8), np.zeros(N_TWIN, np.uint8)
+        fl, it = np.zeros(N_TWIN, np.uint8), np.zeros(N_TWIN, np.uint16)
         tw.twin_plastic(C.byref(p), H.P(eps), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(fl), H.P(it), C.c_double(1e-8), 1000, C.c_int64(N_TWIN))
         assert r["n_fail"] == 0 and 0.3 < r["flags"].mean() < 0.7           # mixed elastic / plastic load
         assert np.array_equal(fl, r["flags"])                               # yield decisions exact
@@ -151,7 +164,7 @@ def test_twin_crystal_matches_oracle(oracle):
             r = oracle.crystal(cp, de, st)
             for mode in (0, 1):
                 sig, tan, so = np.zeros((6, N)), np.zeros((36, N)), np.zeros((42, N))
-                ac, it = np.zeros(N, np.uint16), np.zeros(N, np.uint8)
+                ac, it = np.zeros(N, np.uint16), np.zeros(N, np.uint16)
                 nfb = C.c_int64(0)
                 tw.twin_crystal_mode(C.byref(cp), H.P(de), C.c_double(1.0), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(ac), H.P(it),
                                      C.c_double(1e-8), 100, C.c_int64(N), mode, C.byref(nfb))

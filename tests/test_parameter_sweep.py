@@ -43,7 +43,7 @@ def test_twin_matches_oracle_over_parameter_corners(oracle, name, prm):
         r = oracle.plastic(p, eps, st)
         assert int((r["flags"] & abi.MM_FLAG_FAILED != 0).sum()) == 0
         sig, tan, so = np.zeros((6, N)), np.zeros((36, N)), np.zeros((14, N))
-        fl, it = np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+        fl, it = np.zeros(N, np.uint8), np.zeros(N, np.uint16)
         tw.twin_plastic(C.byref(p), H.P(eps), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(fl), H.P(it), C.c_double(1e-8), 1000, C.c_int64(N))
         assert np.array_equal(fl, r["flags"]) and np.array_equal(it, r["iters"]), (name, step)
         assert H.rel_err(sig, r["sig"]).max() < tol(prm) and H.rel_err(tan, r["tan"]).max() < tol(prm), (name, step)
@@ -117,7 +117,7 @@ def test_twin_crystal_structured_path_over_parameter_corners(oracle, name, kw, r
         de = sy.host_uniform(N, nc, seed, lo, hi)
         r = oracle.crystal(p, de, st)
         sig, tan, so = np.zeros((6, N)), np.zeros((36, N)), np.zeros((42, N))
-        act, it, nfb = np.zeros(N, np.uint16), np.zeros(N, np.uint8), C.c_int64(0)
+        act, it, nfb = np.zeros(N, np.uint16), np.zeros(N, np.uint16), C.c_int64(0)
         tw.twin_crystal_mode(C.byref(p), H.P(de), C.c_double(1.0), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(act), H.P(it), C.c_double(1e-8), 100,
                              C.c_int64(N), 1, C.byref(nfb))
         ok = xtal_check(r, act, it, sig, tan, so, rtol)

@@ -100,7 +100,7 @@ def test_twin_wrapped_matches_oracle(oracle, kind):
         eps = sy.host_uniform(N, nc, 777 + kind + 10 * step, -AMPL[kind], AMPL[kind])
         r = oracle.wrapped_plastic(kind, p, eps, st)
         sig, tan, so = np.zeros((nc, N)), np.zeros((nc * nc, N)), np.zeros((14, N))
-        fl, it, oi = np.zeros(N, np.uint8), np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+        fl, it, oi = np.zeros(N, np.uint8), np.zeros(N, np.uint16), np.zeros(N, np.uint8)
         tw.twin_wrapped_plastic(kind, C.byref(p), H.P(eps), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(fl), H.P(it), H.P(oi),
                                 C.c_double(1e-8), 1000, C.c_double(1e-8), 10, C.c_int64(N))
         assert r["n_fail"] == 0 and 0.15 < (r["flags"] & 1).mean() < 0.9
@@ -304,7 +304,7 @@ def test_twin_wrapped_crystal_matches_oracle(oracle, kind):
         e = sy.host_uniform(N, nc, 70 + 10 * kind + step, -XTAL_AMPL[kind], XTAL_AMPL[kind])
         r = oracle.wrapped_crystal(kind, p, e, st)
         sig, tan, so = np.zeros((nc, N)), np.zeros((nc * nc, N)), np.zeros((42, N))
-        act, it, oi = np.zeros(N, np.uint16), np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+        act, it, oi = np.zeros(N, np.uint16), np.zeros(N, np.uint16), np.zeros(N, np.uint8)
         assert tw.twin_wrapped_crystal(kind, C.byref(p), H.P(e), C.c_double(1.0), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(act), H.P(it), H.P(oi),
                                        C.c_double(1e-8), 100, C.c_double(1e-8), 10, C.c_int64(N)) == 0
         nch += _xtal_compare(r, act, it, oi, sig, tan, so, kind)

@@ -70,7 +70,7 @@ def main():
             shp = lambda nc: (nc, N) if lname == "soa" else (N, nc)
             out = {"stress": torch.empty(shp(6), dtype=torch.float64, device="cuda"), "tangent": torch.empty(shp(36), dtype=torch.float64, device="cuda"),
                    "state": torch.empty(shp(14), dtype=torch.float64, device="cuda"), "flags": torch.empty((N,), dtype=torch.uint8, device="cuda"),
-                   "iters": torch.empty((N,), dtype=torch.uint8, device="cuda")}
+                   "iters": torch.empty((N,), dtype=torch.int16, device="cuda")}
             med, mn = timeit(lambda: mm.material_response(m, eB, stA, options={"defer_check": True}, out=out), a.reps)
             frac = out["flags"].float().mean().item()
             report("plastic stepB " + lname, N, 608, med, mn, {"plastic_fraction": round(frac, 4)})

@@ -86,7 +86,7 @@ def main():
             set_mempolicy(MPOL_DEFAULT, [])
         h_eps, h_st = mm.PinnedArray((6, Ne)), mm.PinnedArray((14, Ne))
         h_out = {"stress": mm.PinnedArray((6, Ne)), "tangent": mm.PinnedArray((36, Ne)), "state": mm.PinnedArray((14, Ne)),
-                 "flags": mm.PinnedArray((Ne,), np.uint8), "iters": mm.PinnedArray((Ne,), np.uint8)}
+                 "flags": mm.PinnedArray((Ne,), np.uint8), "iters": mm.PinnedArray((Ne,), np.uint16)}
         h_eps.array[...] = eps
         h_st.array[...] = 0.0
         outs = {k: v.array for k, v in h_out.items()}
