@@ -5,9 +5,9 @@ first use and the load FAILS LOUDLY if it is missing — there is no CPU fallbac
 """
 from . import _abi, synth  # noqa: F401
 from .materials import (  # noqa: F401
-    AbstractDim, AbstractMaterial, AbstractMaterialState, AbstractTangent, BCC, FCC, PlaneStrain, PlaneStress, ShellStress, UniaxialStrain, UniaxialStress, CrystalViscoPlastic, DeformationGradient,
+    AbstractDim, AbstractMaterial, AbstractMaterialState, AbstractTangent, BCC, Dim, FCC, PlaneStrain, PlaneStress, ShellStress, UniaxialStrain, UniaxialStress, CrystalViscoPlastic, DeformationGradient,
     GreenLagrange, LinearElastic, NeoHook, Plastic, RightCauchyGreen, SmallStrain, StVenant, StrainMeasure, TransverselyIsotropic, XuNeedleman,
-    Yeoh, dPdF, dSdC, dSdE, dsigmadeps, native_tangent_type, slipsystems,
+    Yeoh, dPdF, dSdC, dSdE, dsigmadeps, native_strain_type, native_stress_type, native_tangent_type, slipsystems,
     xu_needleman_Φₙ, xu_needleman_Φₜ, xu_needleman_σₘₐₓ, xu_needleman_τₘₐₓ,
 )
 from .api import (  # noqa: F401

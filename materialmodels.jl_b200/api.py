@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _abi
 from ._lib import check, load
-from .materials import (AbstractDim, AbstractMaterialState, AbstractTangent, CrystalViscoPlastic, DeformationGradient, GreenLagrange,
+from .materials import (AbstractDim, AbstractMaterialState, AbstractTangent, CrystalViscoPlastic, DeformationGradient, GreenLagrange, dsigmadeps,
                         LinearElastic, Plastic, RightCauchyGreen, SmallStrain, StrainMeasure, TransverselyIsotropic, XuNeedleman, _Hyper,
                         dPdF, dSdC, dSdE)
 
@@ -749,6 +749,8 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
     args = list(args)
     if args and isinstance(args[0], AbstractDim):                            # src/wrappers.jl:29-79
         dim = args.pop(0)
+        if dim.KIND == 0:                                                    # Dim{3}: the plain 3D call (wrappers.jl:22, :29-41)
+            return material_response(*args, cache=cache, options=options, layout=layout, tangent=tangent, out=out)
         m = args.pop(0)
         strain = args.pop(0)
         state = args.pop(0) if args else None
@@ -760,9 +762,20 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
         strain = args.pop(0)
         state = args.pop(0) if args else None
         if not isinstance(strain, StrainMeasure):
-            raise TypeError("trait form expects a StrainMeasure (DeformationGradient / RightCauchyGreen)")
+            raise TypeError("trait form expects a StrainMeasure (DeformationGradient / RightCauchyGreen / GreenLagrange / SmallStrain)")
         if not isinstance(m, _Hyper):
-            raise NotImplementedError("trait route is implemented for NeoHook / Yeoh / StVenant")
+            # small-strain materials: native strain SmallStrain, native tangent ∂σ∂ε (traits.jl:142-143, LinearElastic.jl:25); both
+            # transformations are the identity (traits.jl:33, :58), so this is the native 3D call with the wrapper taken off
+            if not isinstance(m, (LinearElastic, Plastic, TransverselyIsotropic, CrystalViscoPlastic)):
+                raise TypeError("material_response(tangent, m, strain, ...): unsupported material %r" % (m,))
+            if not isinstance(strain, SmallStrain):                          # traits.jl:120
+                raise RuntimeError("%s is not the native strain measure for %s:" % (type(strain).__name__, type(m).__name__))
+            if not isinstance(out_tangent, dsigmadeps):                      # no transform_stress_tangent method from ∂σ∂ε to anything else (traits.jl:58-77)
+                raise TypeError("no transformation from dsigmadeps (∂σ∂ε) to %s is defined (src/traits.jl:58-77)" % type(out_tangent).__name__)
+            rest = [state] + args if state is not None else []
+            return material_response(m, strain.value, *rest, cache=cache, options=options, layout=layout, tangent=tangent, out=out)
+        if isinstance(out_tangent, dsigmadeps):
+            raise TypeError("no transformation from dSdC (∂S∂C) to dsigmadeps is defined (src/traits.jl:58-77)")
         if isinstance(out_tangent, dSdC):
             tk = _abi.MM_TANGENT_DSDC
         elif isinstance(out_tangent, dSdE):

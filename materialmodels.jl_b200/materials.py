@@ -235,6 +235,19 @@ class ShellStress(AbstractDim):
     KIND, DIM = _abi.MM_DIM_SHELL_STRESS, 3
 
 
+class Dim(AbstractDim):
+    """Dim{d}: the generic strain-restricted state — reference src/wrappers.jl:3, dispatched together with UniaxialStrain / PlaneStrain
+    at :29-41 (pad the d-dimensional strain with zeros, cut the 3D result down).  Dim(1) == UniaxialStrain, Dim(2) == PlaneStrain storage;
+    Dim(3) is the plain 3D call (reduce_dim(A, ::AbstractDim{3}) = A, :22)."""
+
+    def __init__(self, d):
+        d = int(d)
+        if d not in (1, 2, 3):
+            raise ValueError("Dim(d): d must be 1, 2 or 3")
+        self.DIM = d
+        self.KIND = {1: _abi.MM_DIM_UNIAXIAL_STRAIN, 2: _abi.MM_DIM_PLANE_STRAIN, 3: 0}[d]
+
+
 # --------------------------------------------------------------------------------------------
 # strain measures and tangent tags (reference src/traits.jl:1-26)
 class StrainMeasure:
@@ -279,6 +292,18 @@ class dsigmadeps(AbstractTangent):  # ∂σ∂ε
 
 
 def native_tangent_type(M):
+    """native_tangent_type(::Type{M}) — reference neohook.jl:27, yeoh.jl:29, stvenant.jl:26 (∂S∂C), LinearElastic.jl:25 (∂σ∂ε).  The
+    reference defines it for LinearElastic only among the small-strain models; here every small-strain model answers ∂σ∂ε."""
     if issubclass(M, _Hyper):
         return dSdC
     return dsigmadeps
+
+
+def native_strain_type(M):
+    """native_strain_type(::Type{M}) — reference src/traits.jl:138,140-143 (test_linear_elastic.jl:32)"""
+    return RightCauchyGreen if native_tangent_type(M) is dSdC else SmallStrain
+
+
+def native_stress_type(M):
+    """native_stress_type(::Type{M}) — reference src/traits.jl:139-143: the NAME of the stress measure (no wrapper types are needed here)"""
+    return "SecondPiolaKirchhoff" if native_tangent_type(M) is dSdC else "TrueStress"

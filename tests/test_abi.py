@@ -121,3 +121,53 @@ def test_julia_binding_ccalls_match_the_header():
         cc = [c_kind(t) for t in argtypes]
         assert jl == cc, "%s: Julia passes %s, C expects %s" % (sym, jl, cc)
         assert ret == ("Cint" if restype is C.c_int else ret)
+
+
+def test_julia_binding_structs_match_the_header():
+    """the Julia `struct MM*` mirrors are passed by reference to the C side: field ORDER, field types and total size must equal the
+    header's (checked against the ctypes mirror, which test_header_and_ctypes... pins to include/mmb200.h)"""
+    import ctypes as C
+    import os
+    import re
+
+    import materialmodels_jl_b200._abi as abi
+
+    src = open(os.path.join(os.path.dirname(__file__), "..", "julia", "MaterialModelsB200", "src", "MaterialModelsB200.jl"), encoding="utf-8").read()
+    size = {"Cdouble": 8, "Int32": 4, "Cint": 4, "Int64": 8}
+    found = {}
+    for name, body in re.findall(r"^struct (MM\w+)\b;?(.*?)\bend$", src, re.M | re.S):
+        fields = []
+        for fname, ftype in re.findall(r"(\w+)::([\w{},]+)", body):
+            m = re.match(r"NTuple\{(\d+),(\w+)\}", ftype)
+            fields.append((fname, ftype, int(m.group(1)) * size[m.group(2)] if m else size[ftype]))
+        found[name] = fields
+    assert set(found) >= {"MMPlastic", "MMLinearElastic", "MMHyper", "MMXuNeedleman", "MMNewtonOpts", "MMTransverselyIsotropic", "MMCrystal"}
+    alias = {"lambda": "lambda_", "pad": "pad_"}
+    for name, fields in found.items():
+        cs = getattr(abi, name)
+        cfields = [(f[0], C.sizeof(f[1])) for f in cs._fields_]
+        assert [(alias.get(n, n), sz) for n, _, sz in fields] == cfields, "%s: Julia fields %s, C fields %s" % (name, fields, cfields)
+        assert sum(sz for _, _, sz in fields) == C.sizeof(cs)           # no padding holes on either side (all 8-byte aligned runs)
+
+
+def test_header_structs_match_the_ctypes_mirror():
+    """include/mmb200.h is the contract; _abi.py (and through it the Julia mirror above) must list the same fields in the same order"""
+    import os
+    import re
+
+    import materialmodels_jl_b200._abi as abi
+
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "mmb200.h"), encoding="utf-8").read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for name, body in re.findall(r"typedef struct (MM\w+)\s*\{(.*?)\}\s*\1;", hdr, re.S):
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            ctype, rest = decl.split(None, 1)
+            for part in rest.split(","):
+                names.append(re.match(r"\s*(\w+)", part).group(1))
+        cs = getattr(abi, name)
+        alias = {"lambda": "lambda_"}
+        assert [alias.get(n, n) for n in names] == [f[0] for f in cs._fields_], name

@@ -89,3 +89,82 @@ def test_gpu_traits_match_oracle(mm, cuda_lib, oracle, name, model, prm, lname, 
     S, T, _ = mm.material_response(mm.dSdC(), m, mm.DeformationGradient(torch.from_numpy(lay_of(F)).cuda()), layout=lname)
     SE, TE, _ = mm.material_response(mm.dSdE(), m, mm.DeformationGradient(torch.from_numpy(lay_of(F)).cuda()), layout=lname)
     assert torch.equal(S, SE) and torch.equal(2 * T, TE)
+
+
+# ---- small-strain trait route and Dim{d} (reference src/traits.jl:91-148, src/wrappers.jl:3,29-41; test_linear_elastic.jl:32-33) ----
+def test_native_types_and_small_strain_errors_without_gpu(mm):
+    assert mm.native_strain_type(mm.LinearElastic) is mm.SmallStrain                    # test_linear_elastic.jl:32
+    assert mm.native_stress_type(mm.LinearElastic) == "TrueStress"                      # test_linear_elastic.jl:33
+    assert mm.native_strain_type(mm.NeoHook) is mm.RightCauchyGreen and mm.native_stress_type(mm.Yeoh) == "SecondPiolaKirchhoff"
+    m = mm.LinearElastic(E=200e3, ν=0.3)
+    eps = np.zeros((6, 3))
+    with pytest.raises(RuntimeError, match="DeformationGradient is not the native strain measure for LinearElastic:"):   # traits.jl:120
+        mm.material_response(mm.dsigmadeps(), m, mm.DeformationGradient(np.zeros((9, 3))))
+    with pytest.raises(TypeError, match="no transformation"):                           # no transform_stress_tangent method (traits.jl:58-77)
+        mm.material_response(mm.dSdC(), m, mm.SmallStrain(eps))
+    with pytest.raises(TypeError, match="no transformation"):
+        mm.material_response(mm.dsigmadeps(), mm.NeoHook(λ=1.0, μ=1.0), mm.RightCauchyGreen(np.zeros((6, 3))))
+    with pytest.raises(ValueError):
+        mm.Dim(4)
+    assert mm.Dim(2).KIND == mm.PlaneStrain.KIND and mm.Dim(1).KIND == mm.UniaxialStrain.KIND and mm.Dim(3).KIND == 0
+
+
+@pytest.mark.gpu
+def test_small_strain_trait_route_is_the_native_call(mm, cuda_lib):
+    """material_response(∂σ∂ε(), m, SmallStrain(ε), state, Δt) == material_response(m, ε, state, Δt) for every small-strain material"""
+    import torch
+
+    N = 5000
+    eq = lambda a, b: torch.equal(a, b)
+    le = mm.LinearElastic(E=200e3, ν=0.3)
+    nc, lo, hi, seed = sy.c1_strain()
+    eps = mm.synth_uniform(N, nc, seed, lo, hi)
+    a = mm.material_response(le, eps)
+    b = mm.material_response(mm.dsigmadeps(), le, mm.SmallStrain(eps))
+    assert eq(a[0], b[0]) and eq(a[1], b[1])
+    pl = mm.Plastic(**sy.PLASTIC_PARAMS)
+    nc, lo, hi, seed = sy.c2_strain(0)
+    e2 = mm.synth_uniform(N, nc, seed, lo, hi)
+    st = mm.initial_material_state(pl, N)
+    a = mm.material_response(pl, e2, st)
+    b = mm.material_response(mm.dsigmadeps(), pl, mm.SmallStrain(e2), st, 0.0, cache=mm.get_cache(pl))
+    assert eq(a[0], b[0]) and eq(a[1], b[1]) and eq(a[2].data, b[2].data) and eq(a[2].iters, b[2].iters)
+    ti = mm.TransverselyIsotropic(E_L=140e3, E_T=10e3, G_LT=5e3, ν_LT=0.3, ν_TT=0.4)
+    ts = mm.initial_material_state(ti, (0.0, 0.6, 0.8), N)
+    a = mm.material_response(ti, eps, ts)
+    b = mm.material_response(mm.dsigmadeps(), ti, mm.SmallStrain(eps), ts)
+    assert eq(a[0], b[0]) and eq(a[1], b[1])
+    cm = mm.CrystalViscoPlastic(slipsystems=mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES), **sy.CRYSTAL_PARAMS)
+    nc, lo, hi, seed = sy.c4_strain_increment(0)
+    de = mm.synth_uniform(N, nc, seed, lo, hi)
+    cs = mm.initial_material_state(cm, N)
+    a = mm.material_response(cm, de, cs, 1.0)
+    b = mm.material_response(mm.dsigmadeps(), cm, mm.SmallStrain(de), cs, 1.0)
+    assert eq(a[0], b[0]) and eq(a[1], b[1]) and eq(a[2].data, b[2].data)
+    # numpy strains take the host-buffer entry points through the same route
+    s_h, t_h, _ = mm.material_response(mm.dsigmadeps(), le, mm.SmallStrain(eps.cpu().numpy()))
+    assert np.array_equal(s_h, a_np(mm.material_response(le, eps)[0]))
+
+
+def a_np(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.gpu
+def test_generic_dim_wrapper(mm, cuda_lib):
+    """Dim{d} (wrappers.jl:3): Dim(2) is dispatched with PlaneStrain, Dim(1) with UniaxialStrain (:29-41); Dim(3) is the 3D call (:22)"""
+    import torch
+
+    N = 4000
+    pl = mm.Plastic(**sy.PLASTIC_PARAMS)
+    st = mm.initial_material_state(pl, N)
+    for d, ref_dim, nc in ((2, mm.PlaneStrain(), 3), (1, mm.UniaxialStrain(), 1)):
+        e = mm.synth_uniform(N, nc, 77 + d, -1.5e-3, 1.5e-3)
+        a = mm.material_response(ref_dim, pl, e, st)
+        b = mm.material_response(mm.Dim(d), pl, e, st)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2].data, b[2].data)
+    nc, lo, hi, seed = sy.c2_strain(0)
+    e3 = mm.synth_uniform(N, nc, seed, lo, hi)
+    a = mm.material_response(pl, e3, st)
+    b = mm.material_response(mm.Dim(3), pl, e3, st)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2].data, b[2].data)
