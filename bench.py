@@ -468,11 +468,14 @@ def run_e2e(args, mm, m, epsB, stA, stB, N, world, dev, sharding):
                 big["eps"][:, lo:hi] = epsB[:, lo:hi].cpu().numpy()
                 big["st"][:, lo:hi] = stA.data[:, lo:hi].cpu().numpy()
             outs = {"stress": big["sig"], "flags": big["fl"], "iters": big["it"], "rows": big["rows"]}
-            t0 = time.perf_counter()
-            _, T, _ = mm.material_response(m, big["eps"], mm.PlasticState(big["st"]), tangent="factored", out=outs)
-            dt = time.perf_counter() - t0
-            launches["n"] += 4 * (-(-N // chunk))
-            e2e["full_size_run"] = {"points": N, "value": N / dt, "seconds": dt, "rows": T.n_rows, "note": "one un-warmed call at the configuration size (1e8 points, 33 GB of pinned host memory)"}
+            dts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                _, T, _ = mm.material_response(m, big["eps"], mm.PlasticState(big["st"]), tangent="factored", out=outs)
+                dts.append(time.perf_counter() - t0)
+            launches["n"] += 2 * 4 * (-(-N // chunk))
+            e2e["full_size_run"] = {"points": N, "value": N / dts[1], "seconds": dts[1], "first_call_seconds": dts[0], "rows": T.n_rows,
+                                    "note": "the headline form at the configuration size (1e8 points, 33 GB of pinned host memory): second of two calls"}
             big = outs = T = None
         except Exception as e:       # an informational leg must never cost the headline line
             e2e["full_size_run"] = {"error": repr(e)}

@@ -95,6 +95,11 @@ const char* mm_version(void);
 const char* mm_last_error(void);
 int mm_device_count(void);
 
+/* test / tuning hook: A-B switches of the crystal kernels ("crystal_force_general", "crystal_thresh", "crystal_chunk",
+ * "crystal_fixup_per_sm", "crystal_variant"); initial values come from the MM_CRYSTAL_* environment variables, read once per process.
+ * Returns the previous value, -1 for an unknown name.  Results never depend on these (tests/test_gpu_parity.py runs both paths). */
+int mm_set_tuning(const char* name, int value);
+
 /* ---- host-side parameter helpers (run once per material, like the Julia constructors) ------ */
 /* elastic_tangent_3D(E, ν) — src/LinearElastic.jl:27-35 */
 int mm_elastic_tangent_3d(double E, double nu, double* out36);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "mm_version": (C.c_char_p, []),
     "mm_last_error": (C.c_char_p, []),
     "mm_device_count": (C.c_int, []),
+    "mm_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "mm_elastic_tangent_3d": (C.c_int, [C.c_double, C.c_double, _P]),
     "mm_slipsystems": (C.c_int, [C.c_int, _P, _P, _P]),
     "mm_crystal_setup": (C.c_int, [C.POINTER(MMCrystal), _P, _P]),

@@ -1,6 +1,7 @@
 // mm_crystal — device-pointer entry point of CrystalViscoPlastic{12} (FP64-compute-bound model).
 #include <cuda_runtime.h>
 #include <stdlib.h>
+#include <string.h>
 #include "../../include/mmb200.h"
 #include "mm_kernels.cuh"
 #include "mm_crystal_math.cuh"
@@ -97,15 +98,17 @@ __global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const Crysta
     }
 }
 
-// tuning / A-B switches, read from the environment ONCE per process (tools/README.md) — never on the per-call path
-struct CrystalKnobs { int thresh, chunk, fixup_per_sm; bool force_general; };
-static const CrystalKnobs& crystal_knobs() {
-    static const CrystalKnobs k = [] {
-        CrystalKnobs v{0, 0, 0, false};
+// tuning / A-B switches: initialised from the environment ONCE per process (tools/README.md), changed afterwards only through
+// mm_set_tuning() — never a getenv on the per-call path
+struct CrystalKnobs { int thresh, chunk, fixup_per_sm, force_general, variant; };
+static CrystalKnobs& crystal_knobs() {
+    static CrystalKnobs k = [] {
+        CrystalKnobs v{0, 0, 0, 0, -1};
         if (const char* e = getenv("MM_CRYSTAL_THRESH")) v.thresh = atoi(e);
         if (const char* e = getenv("MM_CRYSTAL_CHUNK")) v.chunk = atoi(e);
         if (const char* e = getenv("MM_FIXUP_PER_SM")) v.fixup_per_sm = atoi(e);
         if (const char* e = getenv("MM_CRYSTAL_FORCE_GENERAL")) v.force_general = (e[0] == '1');
+        if (const char* e = getenv("MM_CRYSTAL_VARIANT")) v.variant = atoi(e);
         return v;
     }();
     return k;
@@ -292,4 +295,20 @@ extern "C" int mm_crystal(const MMCrystal* p, const double* deps, double dt, con
                                   : launch_crystal_structured<false>(k, flags, iters, n_fail, ptrs, N, layout, st);
     if (!active && flags) cudaFreeAsync(flags, st);
     return rc;
+}
+
+// test / tuning hook (not part of the reference-facing surface): returns the previous value, -1 for an unknown name
+extern "C" int mm_set_tuning(const char* name, int value) {
+    if (!name) return -1;
+    CrystalKnobs& k = crystal_knobs();
+    int* slot = nullptr;
+    if (!strcmp(name, "crystal_force_general")) slot = &k.force_general;
+    else if (!strcmp(name, "crystal_thresh")) slot = &k.thresh;
+    else if (!strcmp(name, "crystal_chunk")) slot = &k.chunk;
+    else if (!strcmp(name, "crystal_fixup_per_sm")) slot = &k.fixup_per_sm;
+    else if (!strcmp(name, "crystal_variant")) slot = &k.variant;
+    if (!slot) return -1;
+    const int old = *slot;
+    *slot = value;
+    return old;
 }

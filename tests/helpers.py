@@ -82,6 +82,27 @@ def plastic_state_scales(eps, sig):
     return np.where(e == 0, 1.0, e), np.where(s == 0, 1.0, s)
 
 
+def report_state_own_norm(state, state_ref, flags, what):
+    """The Plastic state is compared with a SCALED metric (plastic_state_scales: εᵖ, μ against ‖ε‖; κ, α against ‖σ‖) because a barely
+    yielding point has |state| ~ 1e-9 obtained from a cancelling yield function, so an error relative to its OWN norm is ill-posed there
+    (DESIGN.md §6).  What that waives is printed here: percentiles of the own-norm relative error over the yielded points."""
+    y = (np.asarray(flags) & 1).astype(bool)
+    if not y.any():
+        return None
+    out = {}
+    for name, sl in (("eps_p", slice(0, 6)), ("kappa", slice(6, 7)), ("alpha", slice(7, 13)), ("mu", slice(13, 14))):
+        a, b = state[sl][:, y], state_ref[sl][:, y]
+        den = np.maximum(np.linalg.norm(b, axis=0), 1e-300)
+        e = np.linalg.norm(a - b, axis=0) / den
+        out[name] = tuple(float(np.percentile(e, q)) for q in (50, 99, 99.99, 100))
+    print("own-norm relative error of the Plastic state (%s; yielded points; p50 / p99 / p99.99 / max): " % what
+          + "; ".join("%s %.1e / %.1e / %.1e / %.1e" % ((k,) + v) for k, v in out.items())
+          + "  | fraction above 1e-12: " + ", ".join("%s %.2e" % (k, float((np.linalg.norm(state[sl][:, y] - state_ref[sl][:, y], axis=0)
+                                                                           > 1e-12 * np.maximum(np.linalg.norm(state_ref[sl][:, y], axis=0), 1e-300)).mean()))
+                                                        for k, sl in (("eps_p", slice(0, 6)), ("kappa", slice(6, 7)), ("alpha", slice(7, 13)), ("mu", slice(13, 14)))))
+    return out
+
+
 _twin = None
 
 
