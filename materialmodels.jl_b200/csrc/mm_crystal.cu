@@ -144,11 +144,18 @@ template <int LAYOUT> struct DirectAccRW : DirectAcc<LAYOUT> {
     }
 };
 
-template <bool HASQ, bool INTPOW, int LAYOUT, int BS>
+// SPARSE (integer m only): the per-lane active-list pass crystal_iterate_sparse — the slip-system tables are copied into shared memory
+// ([component][system], behind the scratch columns) because every lane walks its own list of systems
+template <bool HASQ, bool INTPOW, int LAYOUT, int BS, bool SPARSE>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_MINBLOCKS)
 crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, const int64_t N, const int chunk, const int thresh) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
+    double* tab = sm_scratch + MM_CRYSTAL_SCRATCH * BS;
+    if (SPARSE) {
+        for (int e = threadIdx.x; e < MM_CRYSTAL_TAB; e += BS) crystal_fill_tab(k, tab, e);
+        __syncthreads();
+    }
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t warp_id = (int64_t)blockIdx.x * (BS / 32) + (threadIdx.x >> 5);
@@ -173,7 +180,66 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
         }
         const unsigned working = __ballot_sync(FULL, has_work);
         if (working == 0u) break;
-        if (has_work && !finished) finished = crystal_iterate<HASQ, INTPOW, false>(k, scr, L);
+        if (has_work && !finished) {
+            if (SPARSE) finished = crystal_iterate_sparse<HASQ, false>(k, tab, scr, L);
+            else        finished = crystal_iterate<HASQ, INTPOW, false>(k, scr, L);
+        }
+        const unsigned fin = __ballot_sync(FULL, has_work && finished);
+        const unsigned iterating = working & ~fin;
+        if (fin != 0u && (__popc(fin) >= thresh || iterating == 0u || next >= end)) {
+            if (has_work && finished) {
+                if (!L.bad) {
+                    DirectAcc<LAYOUT> acc(p, N, my);
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) acc.template out<2>(30 + i, scr(XS + i));
+                }
+                active[my] = (uint16_t)(L.bad ? MM_ACTIVE_NEEDS_GENERAL : (L.converged ? 0u : MM_ACTIVE_FAILED));
+                if (iters) iters[my] = (uint16_t)(L.bad ? 0 : (L.iters > 65535 ? 65535 : L.iters));
+                has_work = false; finished = false;
+            }
+        }
+    }
+}
+
+// (1') the same lane-persistent scheme around the PHASED pass (crystal_iterate_phased: integer m, q = 0 — the reference's test and
+// BASELINE configuration).  Its own kernel because its parameter block is its own: every table entry is read as a compile-time
+// constant-bank operand, so the block holds exactly the tables the pass touches (Pw, Eᵉ:MS, T, (Eᵉ)⁻¹: 3.4 KB of the 4 KB bank window).
+#ifndef MM_CRYSTAL_PHASED_MINBLOCKS
+#define MM_CRYSTAL_PHASED_MINBLOCKS 6
+#endif
+template <int LAYOUT, int BS>
+__global__ void __launch_bounds__(BS, MM_CRYSTAL_PHASED_MINBLOCKS)
+crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, const int64_t N, const int chunk, const int thresh) {
+    extern __shared__ double sm_scratch[];
+    const Scratch scr{sm_scratch + threadIdx.x, BS};
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_id = (int64_t)blockIdx.x * (BS / 32) + (threadIdx.x >> 5);
+    int64_t next = warp_id * chunk;
+    const int64_t end = (next + chunk < N) ? (next + chunk) : N;
+    CrystalLane L;
+    double sigt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    bool has_work = false, finished = false;
+    int64_t my = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !has_work);
+        if (idle != 0u && next < end) {                       // refill idle lanes with the next points of the chunk
+            if (!has_work) {
+                const int64_t cand = next + __popc(idle & ((1u << lane) - 1u));
+                if (cand < end) {
+                    my = cand;
+                    DirectAcc<LAYOUT> acc(p, N, my);
+                    crystal_init(k, acc, scr, L);
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) sigt[c] = scr(SIGT + c);
+                    has_work = true; finished = false;
+                }
+            }
+            next += __popc(idle);
+        }
+        const unsigned working = __ballot_sync(FULL, has_work);
+        if (working == 0u) break;
+        if (has_work && !finished) finished = crystal_iterate_phased<false>(k, scr, L, sigt);
         const unsigned fin = __ballot_sync(FULL, has_work && finished);
         const unsigned iterating = working & ~fin;
         if (fin != 0u && (__popc(fin) >= thresh || iterating == 0u || next >= end)) {
@@ -217,10 +283,29 @@ crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, in
 template <bool HASQ, bool INTPOW, int LAYOUT>
 int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
     constexpr int BS = MM_CRYSTAL_BS, FBS = MM_CRYSTAL_FINISH_BS;
-    constexpr size_t smem = (size_t)MM_CRYSTAL_SCRATCH * BS * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
-    static SmemOptIn optin_newton, optin_finish;
-    if (int rc = ensure_smem(optin_newton, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS>, smem, "mm_crystal")) return rc;
+    constexpr size_t smem = (size_t)(MM_CRYSTAL_SCRATCH * BS + MM_CRYSTAL_TAB) * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
+    // "crystal_variant" (mm_set_tuning / MM_CRYSTAL_VARIANT): 0 or default = dense branch-free pass, 1 = sparse per-lane pass, 2 = phased pass.
+    // Measured on configs[3] (1e7 points, step B, profiles/r02_crystal_variants.jsonl + r02_crystal_*_ncu.txt): dense 21.9 ms, sparse 21.9 ms,
+    // phased 25.6 ms — the sparse pass does HALF the thread-level work of the dense one but leaves 15 of 32 lanes active per instruction, the
+    // phased pass (unrolled, constant-bank operands) outgrows the 32 KB instruction cache (23 % no_instruction stalls).  Tests run all three.
+    const bool sparse = INTPOW && crystal_knobs().variant == 1;
+    static SmemOptIn optin_newton, optin_newton_sparse, optin_finish;
+    if (int rc = ensure_smem(optin_newton, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, false>, smem, "mm_crystal")) return rc;
+    if (INTPOW) if (int rc = ensure_smem(optin_newton_sparse, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, INTPOW>, smem, "mm_crystal")) return rc;
     if (int rc = ensure_smem(optin_finish, crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS>, fsmem, "mm_crystal")) return rc;
+    // six blocks of scratch columns need 210 KB of the SM's 228 KB: ask for the largest shared-memory carve-out (with the default heuristic
+    // ncu reported a shared-memory limit of 5 blocks, i.e. 10 instead of 12 resident warps)
+    static bool carve[64] = {};
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !carve[dev]) {
+            cudaFuncSetAttribute(crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (INTPOW) cudaFuncSetAttribute(crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, INTPOW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaGetLastError();
+            carve[dev] = true;
+        }
+    }
     // chunk of points per warp: large enough to refill many times, small enough for >= ~8 waves of warps on the chip
     const int64_t resident_warps = (int64_t)sm_count() * MM_CRYSTAL_MINBLOCKS * (BS / 32);
     int64_t chunk = N / (resident_warps * 8);
@@ -232,7 +317,22 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     if (kn.chunk > 0) chunk = kn.chunk;
     const int64_t warps = (N + chunk - 1) / chunk;
     const int64_t blocks = (warps + (BS / 32) - 1) / (BS / 32);
-    crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, N, (int)chunk, thresh);
+    if (INTPOW && !HASQ && crystal_knobs().variant == 2) {          // "crystal_variant" 2: the phased pass (integer m, q = 0) — measured slower, kept for A/B
+        constexpr size_t psmem = (size_t)MM_CRYSTAL_SCRATCH_PHASED * BS * sizeof(double);
+        static SmemOptIn optin_phased;
+        if (int rc = ensure_smem(optin_phased, crystal_newton_phased_kernel<LAYOUT, BS>, psmem, "mm_crystal")) return rc;
+        static bool carve_p[64] = {};
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !carve_p[dev]) {
+            cudaFuncSetAttribute(crystal_newton_phased_kernel<LAYOUT, BS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaGetLastError();
+            carve_p[dev] = true;
+        }
+        CrystalNK nk;
+        make_crystal_nk(nk, k);
+        crystal_newton_phased_kernel<LAYOUT, BS><<<(unsigned)blocks, BS, psmem, st>>>(nk, ptrs, active, iters, N, (int)chunk, thresh);
+    } else if (sparse) crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, INTPOW><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, N, (int)chunk, thresh);
+    else        crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, false><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, N, (int)chunk, thresh);
     int rc = check_launch("mm_crystal (Newton kernel)");
     if (rc) return rc;
     crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS><<<(unsigned)((N + FBS - 1) / FBS), FBS, fsmem, st>>>(k, ptrs, active, n_fail, N);

@@ -353,16 +353,55 @@ struct CrystalLane {
     double yp[6];          // Σ s_i (D⁻¹p̂)_i Pw_i at the last evaluation (cross hardening only)
     unsigned spos, sneg;   // frozen trial signs
     unsigned mask;         // active mask at the last evaluation
+    unsigned nz;           // systems with x_i != 0 (sparse pass: only these, and the systems that are active, cost more than a yield test)
+    unsigned cand;         // sparse pass: candidate set of the last evaluation (their g / D⁻¹r slots are the only non-zero ones)
     int it;                // loop index of nonlinear_solver.jl:53 (1-based) of the NEXT evaluation
     int iters;             // number of x updates done
     bool converged, bad;
     bool flip;             // some ACTIVE system has sgn_i != s_i at the last evaluation
 };
 
-MM_HD double crystal_sign(const CrystalLane& L, int i) { return ((L.spos >> i) & 1u) ? 1.0 : (((L.sneg >> i) & 1u) ? -1.0 : 0.0); }
+MM_HD int __ffs_(unsigned m) {      // index of the lowest set bit (m != 0)
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+// s_i = ±1.0 or 0.0 from the two frozen-sign bit masks, assembled in the integer pipe (high word 0x3FF00000 | sign bit; the FP64 select
+// chain the ternary form compiles to was 4 % of the Newton kernel's instructions)
+MM_HD double crystal_sign(const CrystalLane& L, int i) {
+#if defined(__CUDA_ARCH__)
+    const unsigned neg = (L.sneg >> i) & 1u, any = ((L.spos | L.sneg) >> i) & 1u;
+    return __hiloint2double((int)((0u - any) & (0x3FF00000u | (neg << 31))), 0);
+#else
+    return ((L.spos >> i) & 1u) ? 1.0 : (((L.sneg >> i) & 1u) ? -1.0 : 0.0);
+#endif
+}
+// sign(x) = ±1.0, 0.0 for x = 0 (Julia's sign), assembled from the sign bit in the integer pipe: one compare and one integer select
+// instead of two FP64 compares and four FSEL
+MM_HD double sign_of(double x) {
+#if defined(__CUDA_ARCH__)
+    const unsigned hi = (x == 0.0) ? 0u : (0x3FF00000u | ((unsigned)__double2hiint(x) & 0x80000000u));
+    return __hiloint2double((int)hi, 0);
+#else
+    return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : 0.0);
+#endif
+}
+// b^n, n = NPOW known at compile time (the reference's m = 10 -> x^9: three squarings and one product, no predicates)
+template <int NPOW> MM_HD double powc_(double b) {      // the multiplication sequence of powi6_ with the tests folded away
+    double r = (NPOW & 1) ? b : 1.0;
+    bool r_is_one = !(NPOW & 1);
+#pragma unroll
+    for (int bit = 1; bit < 7; ++bit) {
+        if ((NPOW >> bit) != 0) b *= b;
+        if ((NPOW >> bit) & 1) { r = r_is_one ? b : r * b; r_is_one = false; }       // 1.0 * b is exact, so skipping it changes nothing
+    }
+    return r;
+}
 
-template <class Acc, class Scr>
-MM_HD void crystal_init(const CrystalK& k, Acc& acc, Scr& scr, CrystalLane& L) {
+template <class KT, class Acc, class Scr>       // KT: CrystalK or CrystalNK (reads lam, G, Pw only)
+MM_HD void crystal_init(const KT& k, Acc& acc, Scr& scr, CrystalLane& L) {
     const double G2 = 2.0 * k.G;
     double st[6];
     {   // σ_trial = σₙ + Eᵉ ⊡ Δε                                                           :119
@@ -374,10 +413,12 @@ MM_HD void crystal_init(const CrystalK& k, Acc& acc, Scr& scr, CrystalLane& L) {
         for (int c = 0; c < 6; ++c) { st[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c])); scr(SIGT + c) = st[c]; }
     }
     L.spos = 0; L.sneg = 0;
+    unsigned nz = 0;
 #pragma unroll
     for (int i = 0; i < 12; ++i) {                                                      // :120-121
-        const double kn = acc.template in<1>(6 + i), an = acc.template in<1>(18 + i);
-        scr(i) = kn; scr(12 + i) = an; scr(XS + i) = acc.template in<1>(30 + i);
+        const double kn = acc.template in<1>(6 + i), an = acc.template in<1>(18 + i), x0 = acc.template in<1>(30 + i);
+        scr(i) = kn; scr(12 + i) = an; scr(XS + i) = x0;
+        if (x0 != 0.0) nz |= (1u << i);
         double tau = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) tau += st[c] * k.Pw[i][c];
@@ -385,7 +426,7 @@ MM_HD void crystal_init(const CrystalK& k, Acc& acc, Scr& scr, CrystalLane& L) {
         if (d > 0.0) L.spos |= (1u << i);
         if (d < 0.0) L.sneg |= (1u << i);
     }
-    L.mask = 0; L.it = 1; L.iters = 0; L.converged = false; L.bad = false; L.flip = false;
+    L.mask = 0; L.nz = nz; L.cand = 0xFFFu; L.it = 1; L.iters = 0; L.converged = false; L.bad = false; L.flip = false;
 }
 
 #ifndef MM_CRYSTAL_UNROLL
@@ -438,13 +479,13 @@ MM_HD void crystal_evaluate(const CrystalK& k, Scr& scr, CrystalLane& L, double*
 #pragma unroll
         for (int c = 0; c < 6; ++c) tau += L.sig[c] * pw[c];
         const double red = tau - al;
-        const double sgn = (red > 0.0) ? 1.0 : ((red < 0.0) ? -1.0 : 0.0);
+        const double sgn = sign_of(red);
         const double Phi = fabs(red) - k.tau_y - kap;                                    // :110
         const bool act = Phi > 0.0;                                                     // ⟨Φ⟩ = (Φ+|Φ|)/2
         double Ri, p, invD;
         if (INTPOW) {
             const double xx = act ? Phi * k.isc : Phi * 0.0;                            // ∓0 when inactive; a NaN Φ stays NaN (⟨Φ⟩ = (Φ+|Φ|)/2 in the reference)
-            const double pw1 = powi6_(xx, npow);
+            const double pw1 = (npow == 9) ? powc_<9>(xx) : powi6_(xx, npow);     // m = 10 (the reference's value): straight-line x^9
             Ri = k.dt * (pw1 * xx) - k.t_star * xi;                                     // :111  (inactive: 0 − t* μ)
             p = k.dtm_sc * pw1;
             mask |= act ? (1u << i) : 0u;
@@ -554,6 +595,329 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
         if (HASQ) d += (g * dv - k.b_h * fabs(g)) * fac;
         scr(XS + i) -= d;
     }
+    L.iters = L.it;
+    L.it += 1;
+    return false;
+}
+
+// ---- SPARSE pass (integer m) ------------------------------------------------------------------------------------------------
+// On the benchmark workload only ~1.8 of the 12 systems are active at the solution (step B; 0.9 in step A), yet the branch-free pass
+// above runs the full chain — two reciprocals, the power, the rank-1 update of M, ~68 FP64 instructions — for all 12, because with the
+// system index uniform across the warp some lane is always active.  Here the system index is PER LANE:
+//   1. σ from the systems with x_i != 0 only (a term with x_i = 0 is an exact zero);
+//   2. a uniform yield test over the 12 systems (τ_i, Φ_i with α = αₙ, κ = κₙ [+ b_h Σx]: exactly what the full formulas give for
+//      x_i = 0, since fma(a_h, 0, κₙ) = κₙ and rcp_nc(1) = 1) -> candidate set = {x_i != 0} ∪ {Φ_i > 0 or NaN};
+//   3. the full chain for the candidates only, each lane walking ITS OWN bit list (trip count = the warp's longest list, ~5 instead of 12),
+//      the Pw / Eᵉ:MS rows fetched from a shared-memory copy of the tables laid out [component][system] (lane-divergent rows without
+//      bank conflicts; the constant bank would serialise them);
+//   4. the update for the candidates only — every other system has R_i = −t*·0, g_i = 0, so x_i stays 0.
+// Everything skipped is an exact zero in the dense pass, so the iterates are the same numbers up to the flush of 1e-16-level noise
+// described at the update (tests: masks, counts and values against the oracle, exactly as for the dense pass).
+// tab: [0,72) Pw transposed (tab[c*12 + i]), [72,144) Eᵉ:MS transposed.
+constexpr int MM_CRYSTAL_TAB = 144;
+MM_HD void crystal_fill_tab(const CrystalK& k, double* tab, int e) {      // e in [0,144): one entry (kernel threads fill it cooperatively)
+    const int c = (e % 72) / 12, i = e % 12;
+    tab[e] = e < 72 ? k.Pw[i][c] : k.EM[i][c];
+}
+
+#if defined(MM_CRYSTAL_STATS) && !defined(__CUDA_ARCH__)
+void mm_crystal_stats_pass(unsigned nz, unsigned cand);       // host-twin instrumentation (tests/hosttwin)
+#endif
+template <bool HASQ, bool KEEPK, class Scr>
+MM_HD bool crystal_iterate_sparse(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L) {
+    double yr[6], nrm2 = 0.0, sumx = 0.0;
+    // 1. σ = σ_trial − Σ_{x_j != 0} x_j s_j Eᵉ:MS_j                                        :131
+#pragma unroll
+    for (int c = 0; c < 6; ++c) L.sig[c] = scr(SIGT + c);
+    for (unsigned m = L.nz; m != 0u; m &= m - 1u) {
+        const int j = __ffs_(m);
+        const double xj = scr(XS + j);
+        const double f = xj * crystal_sign(L, j);
+        if (HASQ) sumx += xj;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) L.sig[c] -= f * tab[72 + c * 12 + j];
+    }
+    // 2. uniform yield test
+    unsigned cand = L.nz;
+    const double kq = HASQ ? k.b_h * sumx : 0.0;
+#pragma unroll 4
+    for (int i = 0; i < 12; ++i) {
+        double tau = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) tau += L.sig[c] * k.Pw[i][c];
+        double kap = scr(i);
+        if (HASQ) kap += kq;
+        const double Phi = fabs(tau - scr(12 + i)) - k.tau_y - kap;
+        cand |= (!(Phi <= 0.0)) ? (1u << i) : 0u;                                       // Φ > 0, or NaN (handled by the full chain)
+    }
+    // systems that were candidates at the last evaluation and are not any more: their g / D⁻¹r slots go back to the zeros the dense pass
+    // would write (crystal_finalize reads all twelve); first pass: all slots
+    for (unsigned m = L.cand & ~cand; m != 0u; m &= m - 1u) { const int i = __ffs_(m); scr(24 + i) = 0.0; scr(36 + i) = 0.0; }
+    L.cand = cand;
+#if defined(MM_CRYSTAL_STATS) && !defined(__CUDA_ARCH__)
+    mm_crystal_stats_pass(L.nz, cand);
+#endif
+    // 3. full chain for the candidates
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) L.K[a * 6 + b] = k.Cmp[a][b];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { yr[c] = 0.0; L.yp[c] = 0.0; }
+    unsigned mask = 0;
+    bool bad = false, flip = false;
+    const int npow = k.m_int - 1;
+    for (unsigned m = cand; m != 0u; m &= m - 1u) {
+        const int i = __ffs_(m);
+        double pw[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) pw[c] = tab[c * 12 + i];
+        const double si = crystal_sign(L, i), xi = scr(XS + i);
+        double kap = scr(i) + k.a_h * xi;                                               // :127 with H = a I + b 11ᵀ
+        if (HASQ) kap += kq;
+        const double iden = rcp_nc(1.0 + k.hk_ai * xi);
+        const double al = (scr(12 + i) + k.H_kin * xi * si) * iden;                     // :128
+        double tau = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) tau += L.sig[c] * pw[c];
+        const double red = tau - al;
+        const double sgn = sign_of(red);
+        const double Phi = fabs(red) - k.tau_y - kap;                                    // :110
+        const bool act = Phi > 0.0;
+        const double xx = act ? Phi * k.isc : Phi * 0.0;
+        const double pw1 = (npow == 9) ? powc_<9>(xx) : powi6_(xx, npow);
+        const double Ri = k.dt * (pw1 * xx) - k.t_star * xi;                            // :111
+        const double p = k.dtm_sc * pw1;
+        mask |= act ? (1u << i) : 0u;
+        flip = flip | (act & (sgn != si));
+        const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
+        const double dD = k.t_star + p * (sgn * dal + k.a_h);
+        bad = bad | (act & !(dD >= 0.25 * k.t_star));
+        const double invD = act ? -rcp_nc(dD) : k.mits;
+        nrm2 += Ri * Ri;
+        const double ci = p * sgn;
+        const double rD = Ri * invD;
+        const double g = ci * invD;
+        scr(24 + i) = g; scr(36 + i) = rD;
+        const double w = -si * g;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double wa = w * pw[a];
+#pragma unroll
+            for (int b = 0; b <= a; ++b) L.K[a * 6 + b] += wa * pw[b];
+        }
+        const double srD = si * rD;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) yr[c] += srD * pw[c];
+        if (HASQ) {
+            const double spD = si * (k.b_h * p * invD);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) L.yp[c] += spD * pw[c];
+        }
+    }
+    L.mask = mask;
+    L.flip = flip;
+    L.iters = L.it - 1;
+    if (L.it > k.max_iter) return true;                                                  // nonlinear_solver.jl:61
+    if (!(nrm2 == nrm2)) return true;                                                    // NaN residual -> not converged
+    if (bad) { L.bad = true; return true; }
+    if (nrm2 < k.tol2_lo || (nrm2 <= k.tol2_hi && sqrt(nrm2) < k.tol)) { L.converged = true; return true; }
+    // x -= J \ r                                                                        nonlinear_solver.jl:59
+    double Mc[KEEPK ? 36 : 1];
+    double* M = KEEPK ? Mc : L.K;
+    if (KEEPK) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) Mc[KEEPK ? (a * 6 + b) : 0] = L.K[a * 6 + b];
+    }
+    if (!ldl6_factor(M)) { L.bad = true; return true; }
+    ldl6_solve(M, yr);
+    double fac = 0.0;
+    double ypl[6];
+    if (HASQ) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) ypl[c] = L.yp[c];
+        ldl6_solve(M, ypl);
+        double su = 0.0, sv = 0.0;
+        for (unsigned m = cand; m != 0u; m &= m - 1u) {
+            const int i = __ffs_(m);
+            const double g = scr(24 + i);
+            double du = 0.0, dv = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { du += tab[c * 12 + i] * yr[c]; dv += tab[c * 12 + i] * ypl[c]; }
+            su += scr(36 + i) + g * du;
+            sv += g * dv - k.b_h * fabs(g);
+        }
+        fac = su * fast_rcp(1.0 - sv);
+    }
+    unsigned nz = 0;
+    for (unsigned m = cand; m != 0u; m &= m - 1u) {
+        const int i = __ffs_(m);
+        const double g = scr(24 + i);
+        double d = scr(36 + i);
+        double du = 0.0, dv = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { du += tab[c * 12 + i] * yr[c]; if (HASQ) dv += tab[c * 12 + i] * ypl[c]; }
+        d += g * du;
+        if (HASQ) d += (g * dv - k.b_h * fabs(g)) * fac;
+        const double xo = scr(XS + i);
+        double xn = xo - d;
+        // An INACTIVE system's exact Newton step is x_i -> 0 (R_i = −t* x_i, J_ii = −t*); in floating point it lands on rounding noise
+        // ~1e-16 |x_i| which would keep the system on the candidate list while it decays over the next ~20 passes.  Noise of that size is
+        // flushed to the exact zero the step means (the reference's LU leaves a different 1e-16-level noise there; nothing depends on it).
+        if (!((mask >> i) & 1u) && fabs(xn) <= 1e-14 * fabs(xo)) xn = 0.0;
+        scr(XS + i) = xn;
+        if (xn != 0.0) nz |= (1u << i);
+    }
+    L.nz = nz;
+    L.iters = L.it;
+    L.it += 1;
+    return false;
+}
+
+// ---- PHASED pass (integer m, q = 0): the Newton kernel's default ----------------------------------------------------------------
+// ncu on the two passes above (profiles/r02_crystal_dense_vs_sparse_ncu.txt): the dense pass executes 87.7e9 thread-instructions per
+// 2e6 points, the sparse one 44.9e9 — half the work — but only 16 % fewer WARP instructions, because the per-lane system lists leave
+// 15 of 32 lanes active per instruction.  And in both, ~45 % of the issued instructions are not FP64 math: run-time-indexed constant
+// loads of the Pw / Eᵉ:MS rows, scratch traffic, sign extraction.  So the pass is split by the kind of work:
+//   1. σ = σ_trial − Σ x_j s_j Eᵉ:MS_j and τ_i = σ:Pw_i for all 12 systems — dense, FULLY UNROLLED, every table entry a compile-time
+//      constant-bank operand of the DFMA itself (no loads, no address arithmetic, all 32 lanes busy); the yield test with α = αₙ, κ = κₙ
+//      gives the candidate set {x_i != 0} ∪ {Φ_i > 0 or NaN} (exact for x_i = 0, see the sparse pass);
+//   2. the scalar chain (two reciprocals, the power, D_ii) — the only part that is wasted on inactive systems — for the candidates only,
+//      each lane walking its own list (~3 of 12 per pass); it needs no table at all (τ_i was parked in the D⁻¹r slot);
+//   3. M = (Eᵉ)⁻¹ + Σ w_i Pw_i Pw_iᵀ as 21 dot products with the host-built table T[ab][i] = Pw_i[a] Pw_i[b], y_r, ‖r‖² — dense, unrolled;
+//   4. LDLᵀ, and the update x_i −= (D⁻¹r)_i + g_i Pw_i·z — dense, unrolled, stores only for the candidates.
+// Scratch (72 slots): [0,12) κₙ [12,24) αₙ [24,36) g [36,48) τ -> D⁻¹r [48,60) x [60,72) R_i² (+inf = D_ii guard failed); σ_trial in registers.
+struct CrystalNK {
+    double Pw[12][6], EM[12][6], T[21][12], Cmp[21];
+    double lam, G, tau_y, H_kin, a_h, hk_ai, isc, dtm_sc, dt, t_star, mits, tol, tol2_lo, tol2_hi;
+    int max_iter, npow;
+};
+constexpr int MM_CRYSTAL_SCRATCH_PHASED = 72;
+constexpr int R2S = 60;
+MM_HD constexpr int tri21(int a, int b) { return a * (a + 1) / 2 + b; }        // b <= a
+inline void make_crystal_nk(CrystalNK& n, const CrystalK& k) {
+    for (int i = 0; i < 12; ++i)
+        for (int c = 0; c < 6; ++c) { n.Pw[i][c] = k.Pw[i][c]; n.EM[i][c] = k.EM[i][c]; }
+    for (int a = 0; a < 6; ++a)
+        for (int b = 0; b <= a; ++b) {
+            n.Cmp[tri21(a, b)] = k.Cmp[a][b];
+            for (int i = 0; i < 12; ++i) n.T[tri21(a, b)][i] = k.Pw[i][a] * k.Pw[i][b];
+        }
+    n.lam = k.lam; n.G = k.G; n.tau_y = k.tau_y; n.H_kin = k.H_kin; n.a_h = k.a_h; n.hk_ai = k.hk_ai; n.isc = k.isc; n.dtm_sc = k.dtm_sc; n.dt = k.dt; n.t_star = k.t_star;
+    n.mits = k.mits; n.tol = k.tol; n.tol2_lo = k.tol2_lo; n.tol2_hi = k.tol2_hi; n.max_iter = k.max_iter; n.npow = k.m_int - 1;
+}
+
+template <bool KEEPK, class Scr>
+MM_HD bool crystal_iterate_phased(const CrystalNK& k, Scr& scr, CrystalLane& L, const double* sigt) {
+    // ---- 1. σ, τ_i, yield test
+    double sig[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sig[c] = sigt[c];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        const double f = scr(XS + j) * crystal_sign(L, j);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sig[c] -= f * k.EM[j][c];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) L.sig[c] = sig[c];
+    unsigned cand = L.nz;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        double tau = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) tau += sig[c] * k.Pw[i][c];
+        scr(36 + i) = tau;
+        const double Phi = fabs(tau - scr(12 + i)) - k.tau_y - scr(i);
+        cand |= (!(Phi <= 0.0)) ? (1u << i) : 0u;
+    }
+    for (unsigned m = L.cand & ~cand; m != 0u; m &= m - 1u) scr(24 + __ffs_(m)) = 0.0;     // g slots of systems that left the list (finalize reads all twelve)
+    L.cand = cand;
+    // ---- 2. scalar chains of the candidates
+    unsigned mask = 0;
+    bool flip = false;
+    for (unsigned m = cand; m != 0u; m &= m - 1u) {
+        const int i = __ffs_(m);
+        const double si = crystal_sign(L, i), xi = scr(XS + i), tau = scr(36 + i);
+        const double kap = scr(i) + k.a_h * xi;                                         // :127 (q = 0)
+        const double iden = rcp_nc(1.0 + k.hk_ai * xi);
+        const double al = (scr(12 + i) + k.H_kin * xi * si) * iden;                     // :128
+        const double red = tau - al;
+        const double sgn = sign_of(red);
+        const double Phi = fabs(red) - k.tau_y - kap;                                    // :110
+        const bool act = Phi > 0.0;
+        const double xx = act ? Phi * k.isc : Phi * 0.0;
+        const double pw1 = (k.npow == 9) ? powc_<9>(xx) : powi6_(xx, k.npow);
+        const double Ri = k.dt * (pw1 * xx) - k.t_star * xi;                            // :111
+        const double p = k.dtm_sc * pw1;
+        mask |= act ? (1u << i) : 0u;
+        flip = flip | (act & (sgn != si));
+        const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
+        const double dD = k.t_star + p * (sgn * dal + k.a_h);
+        const bool bad = act & !(dD >= 0.25 * k.t_star);
+        const double invD = act ? -rcp_nc(dD) : k.mits;
+        scr(24 + i) = (p * sgn) * invD;
+        scr(36 + i) = Ri * invD;
+        scr(R2S + i) = bad ? HUGE_VAL : Ri * Ri;
+    }
+    L.mask = mask;
+    L.flip = flip;
+    // ---- 3. M, y_r, ‖r‖²
+    double K[21], yr[6], nrm2 = 0.0;
+#pragma unroll
+    for (int e = 0; e < 21; ++e) K[e] = k.Cmp[e];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) yr[c] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const bool in = (cand >> i) & 1u;
+        const double si = crystal_sign(L, i);
+        const double g = in ? scr(24 + i) : 0.0, rD = in ? scr(36 + i) : 0.0, r2 = in ? scr(R2S + i) : 0.0;
+        nrm2 += r2;
+        const double w = -si * g, srD = si * rD;
+#pragma unroll
+        for (int e = 0; e < 21; ++e) K[e] += w * k.T[e][i];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) yr[c] += srD * k.Pw[i][c];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) L.K[a * 6 + b] = K[tri21(a, b)];
+    L.iters = L.it - 1;
+    if (L.it > k.max_iter) return true;                                                  // nonlinear_solver.jl:61
+    if (!(nrm2 == nrm2)) return true;                                                    // NaN residual -> not converged
+    if (nrm2 == HUGE_VAL) { L.bad = true; return true; }                                 // a D_ii guard failed -> general path
+    if (nrm2 < k.tol2_lo || (nrm2 <= k.tol2_hi && sqrt(nrm2) < k.tol)) { L.converged = true; return true; }
+    // ---- 4. x -= J \ r                                                                nonlinear_solver.jl:59
+    double Mc[KEEPK ? 36 : 1];
+    double* M = KEEPK ? Mc : L.K;
+    if (KEEPK) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) Mc[KEEPK ? (a * 6 + b) : 0] = L.K[a * 6 + b];
+    }
+    if (!ldl6_factor(M)) { L.bad = true; return true; }
+    ldl6_solve(M, yr);
+    unsigned nz = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        if ((cand >> i) & 1u) {
+            const double g = scr(24 + i), xo = scr(XS + i);
+            double du = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) du += k.Pw[i][c] * yr[c];
+            const double d = scr(36 + i) + g * du;
+            double xn = xo - d;
+            if (g == 0.0 && fabs(xn) <= 1e-14 * fabs(xo)) xn = 0.0;                      // inactive system: the exact step is x_i -> 0 (see the sparse pass)
+            scr(XS + i) = xn;
+            if (xn != 0.0) nz |= (1u << i);
+        }
+    }
+    L.nz = nz;
     L.iters = L.it;
     L.it += 1;
     return false;
@@ -704,6 +1068,35 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
             for (int Ic = 0; Ic < 6; ++Ic) acc.template out<1>(Ic + 6 * Jc, col[Ic]);
         }
     }
+    return mask;
+}
+
+// one point start to finish through the SPARSE pass (host twin of the Newton kernel's default path; integer m only)
+template <bool HASQ, class Acc, class Scr>
+MM_HD unsigned crystal_point_sparse(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
+    double tab[MM_CRYSTAL_TAB];
+    for (int e = 0; e < MM_CRYSTAL_TAB; ++e) crystal_fill_tab(k, tab, e);
+    CrystalLane L;
+    crystal_init(k, acc, scr, L);
+    while (!crystal_iterate_sparse<HASQ, true>(k, tab, scr, L)) {}
+    const unsigned mask = crystal_finalize<HASQ>(k, acc, scr, L, fallback);
+    *iters_out = *fallback ? 0 : L.iters;
+    return mask;
+}
+
+// one point start to finish through the PHASED pass (host twin of the Newton kernel's default path; integer m, q = 0)
+template <class Acc, class Scr>
+MM_HD unsigned crystal_point_phased(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
+    CrystalNK nk;
+    make_crystal_nk(nk, k);
+    CrystalLane L;
+    crystal_init(k, acc, scr, L);
+    double sigt[6];
+    for (int c = 0; c < 6; ++c) sigt[c] = scr(SIGT + c);
+    while (!crystal_iterate_phased<true>(nk, scr, L, sigt)) {}
+    for (int c = 0; c < 6; ++c) scr(SIGT + c) = sigt[c];          // the R² slots overlap σ_trial's; crystal_finalize does not read either
+    const unsigned mask = crystal_finalize<false>(k, acc, scr, L, fallback);
+    *iters_out = *fallback ? 0 : L.iters;
     return mask;
 }
 

@@ -3,6 +3,8 @@
 // never loaded by the product; the GPU parity tests (-m gpu) are the real gate.
 #include <cstdint>
 #include <cstring>
+#define MM_CRYSTAL_STATS 1
+namespace mm { void mm_crystal_stats_pass(unsigned nz, unsigned cand); }
 #include "../../include/mmb200.h"
 #include "../../materialmodels.jl_b200/csrc/mm_math.cuh"
 #include "../../materialmodels.jl_b200/csrc/mm_crystal_math.cuh"
@@ -61,9 +63,9 @@ int twin_xu(const MMXuNeedleman* p, const double* jump, double* T, double* H, in
     for (int64_t i = 0; i < N; ++i) { HostAcc<1, 2> a{{jump}, {T, H}, N, i}; if (dim == 3) mm::xu_point<3>(k, a); else mm::xu_point<2>(k, a); }
     return 0;
 }
-struct HostScratch { double v[MM_CRYSTAL_SCRATCH]; double& operator()(int j) { return v[j]; } };
+struct HostScratch { double v[MM_CRYSTAL_SCRATCH + 8]; double& operator()(int j) { return v[j]; } };     // 72 slots for the phased pass
 
-// mode 0: general pivoted path; mode 1: structured fast path (falls back like the kernel does)
+// mode 0: general pivoted path; mode 1: structured fast path (falls back like the kernel does); mode 2: the same through the sparse pass; mode 3: through the phased pass (q = 0; else as mode 2)
 int twin_crystal_mode(const MMCrystal* p, const double* deps, double dt, const double* sin, double* sig, double* tan, double* sout, uint16_t* active,
                       uint16_t* iters, double tol, int max_iter, int64_t N, int mode, int64_t* n_fallback) {
     mm::CrystalK k;
@@ -75,7 +77,9 @@ int twin_crystal_mode(const MMCrystal* p, const double* deps, double dt, const d
         if (mode == 0 || !k.h_struct) m = mm::crystal_point(k, a, &it);
         else {
             HostScratch scr; bool fb = false;
-            m = (k.b_h != 0.0) ? mm::crystal_point_fast<true>(k, a, scr, &it, &fb) : mm::crystal_point_fast<false>(k, a, scr, &it, &fb);
+            if (mode == 3 && k.m_int && k.b_h == 0.0) m = mm::crystal_point_phased(k, a, scr, &it, &fb);
+            else if (mode >= 2 && k.m_int) m = (k.b_h != 0.0) ? mm::crystal_point_sparse<true>(k, a, scr, &it, &fb) : mm::crystal_point_sparse<false>(k, a, scr, &it, &fb);
+            else m = (k.b_h != 0.0) ? mm::crystal_point_fast<true>(k, a, scr, &it, &fb) : mm::crystal_point_fast<false>(k, a, scr, &it, &fb);
             if (fb) { ++nfb; m = mm::crystal_point(k, a, &it); }
         }
         active[i] = (uint16_t)m; iters[i] = (uint16_t)it;
@@ -235,4 +239,13 @@ extern "C" int twin_wrapped_transviso(int kind, const MMTransverselyIsotropic* p
         default: return -1;
     }
     return 0;
+}
+
+// instrumentation of the sparse crystal pass: how many systems cost a full chain per Newton pass
+static long long g_stats_passes = 0, g_stats_nz = 0, g_stats_cand = 0, g_stats_hist[13] = {0};
+namespace mm { void mm_crystal_stats_pass(unsigned nz, unsigned cand) { ++g_stats_passes; g_stats_nz += __builtin_popcount(nz); const int c = __builtin_popcount(cand); g_stats_cand += c; ++g_stats_hist[c]; } }
+extern "C" void twin_crystal_stats(long long* out16, int reset) {
+    out16[0] = g_stats_passes; out16[1] = g_stats_nz; out16[2] = g_stats_cand;
+    for (int i = 0; i < 13; ++i) out16[3 + i] = g_stats_hist[i];
+    if (reset) { g_stats_passes = g_stats_nz = g_stats_cand = 0; for (int i = 0; i < 13; ++i) g_stats_hist[i] = 0; }
 }

@@ -291,6 +291,17 @@ def _crystal_three_steps(mm, torch, oracle, lname, lay):
         st = mm.CrystalViscoPlasticState(dev(torch, st_ref), lname)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_crystal_newton_kernel_variants(mm, torch, oracle, cuda_lib, variant):
+    """The three Newton passes of the structured path — dense branch-free (default), sparse per-lane lists, phased — must all reproduce
+    the oracle's masks and iteration counts exactly and its values within 1e-12 (mm_set_tuning("crystal_variant", v))."""
+    old = cuda_lib.mm_set_tuning(b"crystal_variant", variant)
+    try:
+        _crystal_three_steps(mm, torch, oracle, "soa", 0)
+    finally:
+        cuda_lib.mm_set_tuning(b"crystal_variant", old)
+
+
 def test_crystal_golden_path(mm, torch, golden):
     g = golden["CrystalViscoPlastic1"]
     m = make_crystal(mm)
