@@ -137,18 +137,34 @@ static CrystalKnobs& crystal_knobs() {
 //     (one extra pass out of ~15) and writes σ, the tangent (six 6x6 solves) and the state.  In the one-kernel version
 //     this phase ran with 5.8 of 32 lanes active and took 16 % of the time (profiles/r01_crystal_v5_ncu_full.txt).
 // ---------------------------------------------------------------------------------------------------------
+// The Newton kernel hands its converged μ to the finish kernel through the μ slots of the state OUTPUT — unless the caller aliased
+// state_in and state_out (allowed by include/mmb200.h): then those slots still hold the PREVIOUS μ, which the fix-up pass needs as the
+// reference's initial guess x0 = state.μ (CrystalViscoPlastic.jl:73) for the points the finish kernel punts to it, so the hand-over goes
+// through a stream-ordered side buffer xbuf[12][N] instead and nothing of the old state is overwritten before the fix-up decision.
 template <int LAYOUT> struct DirectAccRW : DirectAcc<LAYOUT> {
-    __device__ __forceinline__ DirectAccRW(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_) : DirectAcc<LAYOUT>(p_, N_, i_) {}
+    const double* xbuf;
+    __device__ __forceinline__ DirectAccRW(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_, const double* xbuf_) : DirectAcc<LAYOUT>(p_, N_, i_), xbuf(xbuf_) {}
     template <int A> __device__ __forceinline__ double rd_out(int c) const {
+        if (xbuf) return xbuf[(int64_t)(c - 30) * this->N + this->i];
         return LAYOUT == 0 ? this->p.out[A][(int64_t)c * this->N + this->i] : this->p.out[A][this->i * CrystalGeneralOp::out_nc(A) + c];
     }
 };
+template <int LAYOUT, class Scr> __device__ __forceinline__ void crystal_hand_over(const Ptrs<2, 3>& p, double* xbuf, int64_t N, int64_t my, const Scr& scr) {
+    if (xbuf) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) xbuf[(int64_t)i * N + my] = scr(XS + i);
+    } else {
+        DirectAcc<LAYOUT> acc(p, N, my);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc.template out<2>(30 + i, scr(XS + i));
+    }
+}
 
 // SPARSE (integer m only): the per-lane active-list pass crystal_iterate_sparse — the slip-system tables are copied into shared memory
 // ([component][system], behind the scratch columns) because every lane walks its own list of systems
 template <bool HASQ, bool INTPOW, int LAYOUT, int BS, bool SPARSE>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_MINBLOCKS)
-crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, const int64_t N, const int chunk, const int thresh) {
+crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, const int chunk, const int thresh) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     double* tab = sm_scratch + MM_CRYSTAL_SCRATCH * BS;
@@ -188,11 +204,7 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
         const unsigned iterating = working & ~fin;
         if (fin != 0u && (__popc(fin) >= thresh || iterating == 0u || next >= end)) {
             if (has_work && finished) {
-                if (!L.bad) {
-                    DirectAcc<LAYOUT> acc(p, N, my);
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) acc.template out<2>(30 + i, scr(XS + i));
-                }
+                if (!L.bad) crystal_hand_over<LAYOUT>(p, xbuf, N, my, scr);
                 active[my] = (uint16_t)(L.bad ? MM_ACTIVE_NEEDS_GENERAL : (L.converged ? 0u : MM_ACTIVE_FAILED));
                 if (iters) iters[my] = (uint16_t)(L.bad ? 0 : (L.iters > 65535 ? 65535 : L.iters));
                 has_work = false; finished = false;
@@ -209,7 +221,7 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
 #endif
 template <int LAYOUT, int BS>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_PHASED_MINBLOCKS)
-crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, const int64_t N, const int chunk, const int thresh) {
+crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, const int chunk, const int thresh) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     const unsigned FULL = 0xffffffffu;
@@ -244,11 +256,7 @@ crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* ac
         const unsigned iterating = working & ~fin;
         if (fin != 0u && (__popc(fin) >= thresh || iterating == 0u || next >= end)) {
             if (has_work && finished) {
-                if (!L.bad) {
-                    DirectAcc<LAYOUT> acc(p, N, my);
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) acc.template out<2>(30 + i, scr(XS + i));
-                }
+                if (!L.bad) crystal_hand_over<LAYOUT>(p, xbuf, N, my, scr);
                 active[my] = (uint16_t)(L.bad ? MM_ACTIVE_NEEDS_GENERAL : (L.converged ? 0u : MM_ACTIVE_FAILED));
                 if (iters) iters[my] = (uint16_t)(L.bad ? 0 : (L.iters > 65535 ? 65535 : L.iters));
                 has_work = false; finished = false;
@@ -265,14 +273,14 @@ crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* ac
 #endif
 template <bool HASQ, bool INTPOW, int LAYOUT, int BS>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_FINISH_MINBLOCKS)
-crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, int32_t* n_fail, const int64_t N) {
+crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, int32_t* n_fail, const double* xbuf, const int64_t N) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     if (i >= N) return;
     const unsigned status = active[i];
     if (status & MM_ACTIVE_NEEDS_GENERAL) return;                     // left to the fix-up pass
-    DirectAccRW<LAYOUT> acc(p, N, i);
+    DirectAccRW<LAYOUT> acc(p, N, i, xbuf);
     bool fallback = false;
     unsigned mask = crystal_finish_from_x<HASQ, INTPOW>(k, acc, scr, (status & MM_ACTIVE_FAILED) == 0, &fallback);
     if (fallback) mask = MM_ACTIVE_NEEDS_GENERAL;
@@ -281,7 +289,7 @@ crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, in
 }
 
 template <bool HASQ, bool INTPOW, int LAYOUT>
-int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
+int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st) {
     constexpr int BS = MM_CRYSTAL_BS, FBS = MM_CRYSTAL_FINISH_BS;
     constexpr size_t smem = (size_t)(MM_CRYSTAL_SCRATCH * BS + MM_CRYSTAL_TAB) * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
     // "crystal_variant" (mm_set_tuning / MM_CRYSTAL_VARIANT): 0 or default = dense branch-free pass, 1 = sparse per-lane pass, 2 = phased pass.
@@ -330,19 +338,19 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
         }
         CrystalNK nk;
         make_crystal_nk(nk, k);
-        crystal_newton_phased_kernel<LAYOUT, BS><<<(unsigned)blocks, BS, psmem, st>>>(nk, ptrs, active, iters, N, (int)chunk, thresh);
-    } else if (sparse) crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, INTPOW><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, N, (int)chunk, thresh);
-    else        crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, false><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, N, (int)chunk, thresh);
+        crystal_newton_phased_kernel<LAYOUT, BS><<<(unsigned)blocks, BS, psmem, st>>>(nk, ptrs, active, iters, xbuf, N, (int)chunk, thresh);
+    } else if (sparse) crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, INTPOW><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh);
+    else        crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, false><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh);
     int rc = check_launch("mm_crystal (Newton kernel)");
     if (rc) return rc;
-    crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS><<<(unsigned)((N + FBS - 1) / FBS), FBS, fsmem, st>>>(k, ptrs, active, n_fail, N);
+    crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS><<<(unsigned)((N + FBS - 1) / FBS), FBS, fsmem, st>>>(k, ptrs, active, n_fail, xbuf, N);
     return check_launch("mm_crystal (finish kernel)");
 }
 
 template <bool HASQ, int LAYOUT>
-int launch_crystal_by_exponent(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, cudaStream_t st) {
-    return k.m_int ? launch_crystal_two_kernel<HASQ, true, LAYOUT>(k, active, iters, n_fail, ptrs, N, st)
-                   : launch_crystal_two_kernel<HASQ, false, LAYOUT>(k, active, iters, n_fail, ptrs, N, st);
+int launch_crystal_by_exponent(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st) {
+    return k.m_int ? launch_crystal_two_kernel<HASQ, true, LAYOUT>(k, active, iters, n_fail, ptrs, xbuf, N, st)
+                   : launch_crystal_two_kernel<HASQ, false, LAYOUT>(k, active, iters, n_fail, ptrs, xbuf, N, st);
 }
 
 int launch_crystal_general(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
@@ -353,11 +361,11 @@ int launch_crystal_general(const CrystalK& k, uint16_t* active, uint16_t* iters,
 }
 
 template <bool HASQ>
-int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
+int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, int layout, cudaStream_t st) {
     if (N == 0) return MM_OK;
     int rc;
-    if (layout == 0)      rc = launch_crystal_by_exponent<HASQ, 0>(k, active, iters, n_fail, ptrs, N, st);
-    else if (layout == 1) rc = launch_crystal_by_exponent<HASQ, 1>(k, active, iters, n_fail, ptrs, N, st);
+    if (layout == 0)      rc = launch_crystal_by_exponent<HASQ, 0>(k, active, iters, n_fail, ptrs, xbuf, N, st);
+    else if (layout == 1) rc = launch_crystal_by_exponent<HASQ, 1>(k, active, iters, n_fail, ptrs, xbuf, N, st);
     else return set_error(MM_ERR_ARG, "mm_crystal: unknown layout %d", layout);
     if (rc) return rc;
     const int64_t nranges = (N + MM_FIXUP_RANGE - 1) / MM_FIXUP_RANGE;
@@ -391,8 +399,14 @@ extern "C" int mm_crystal(const MMCrystal* p, const double* deps, double dt, con
         cudaError_t e = cudaMallocAsync((void**)&flags, (size_t)N * sizeof(uint16_t), st);
         if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_crystal: cudaMallocAsync: %s", cudaGetErrorString(e));
     }
-    const int rc = (k.b_h != 0.0) ? launch_crystal_structured<true>(k, flags, iters, n_fail, ptrs, N, layout, st)
-                                  : launch_crystal_structured<false>(k, flags, iters, n_fail, ptrs, N, layout, st);
+    double* xbuf = nullptr;
+    if (state_in == state_out && N > 0) {        // in-place update: see DirectAccRW
+        cudaError_t e = cudaMallocAsync((void**)&xbuf, (size_t)N * 12 * sizeof(double), st);
+        if (e != cudaSuccess) { if (!active && flags) cudaFreeAsync(flags, st); return set_error(MM_ERR_CUDA, "mm_crystal: cudaMallocAsync: %s", cudaGetErrorString(e)); }
+    }
+    const int rc = (k.b_h != 0.0) ? launch_crystal_structured<true>(k, flags, iters, n_fail, ptrs, xbuf, N, layout, st)
+                                  : launch_crystal_structured<false>(k, flags, iters, n_fail, ptrs, xbuf, N, layout, st);
+    if (xbuf) cudaFreeAsync(xbuf, st);
     if (!active && flags) cudaFreeAsync(flags, st);
     return rc;
 }
