@@ -237,7 +237,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=10**8, help="points per GPU (BASELINE.json configs[1]: 1e8)")
     ap.add_argument("--e2e-points", type=int, default=2 * 10**7)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-points", type=int, default=16 * 10**6)
     ap.add_argument("--ref-points", type=int, default=2 * 10**6, help="points per step of --impl reference (a bounded slice of the workload)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -392,13 +392,19 @@ def run_e2e(args, mm, m, epsB, stA, stB, N, world, dev, sharding):
     chunks = -(-Ne // chunk)
     launches = {"n": 0}
 
-    def timed(fn, n=steps):
+    step_times = {}
+
+    def timed(fn, n=steps, name=None):
         fn()                                            # warm-up (workspace allocation, page faults)
         sharding.barrier()
+        per = []
         t0 = time.perf_counter()
         for _ in range(n):
+            t1 = time.perf_counter()
             r = fn()
+            per.append(time.perf_counter() - t1)
         dt = time.perf_counter() - t0
+        step_times[name] = per
         return sharding.allreduce_max(dt, device=dev), r
 
     variants = {}
@@ -428,24 +434,24 @@ def run_e2e(args, mm, m, epsB, stA, stB, N, world, dev, sharding):
                 new.commit(dense_st)
             return sg, T, new
 
-        dt, (sg, T, new) = timed(call)
+        name = kind + ("_resident_state" if resident else "") + ("_expanded_on_host" if expand else "")
+        dt, (sg, T, new) = timed(call, name=name)
         launches["n"] += 4 * chunks * (steps + 1)
         n_rows = T.n_rows
-        name = kind + ("_resident_state" if resident else "") + ("_expanded_on_host" if expand else "")
         variants[name] = {"value": world * Ne * steps / dt, "h2d_bytes_per_step": (48 if resident else 160) * Ne,
                           "d2h_bytes_per_step": 51 * Ne + 8 * W * n_rows + 8 * chunks, "row_doubles": W, "rows": n_rows,
-                          "matches_device_path": bool(np.array_equal(sg, ref_sig))}
+                          "matches_device_path": bool(np.array_equal(sg, ref_sig)), "best_step_value": Ne / min(step_times[name])}
         return variants[name]
 
+    head = compact_variant("factored")                  # the headline form first
     # dense (round-1 headline, unchanged code path: mmh_plastic)
     h_out = {"stress": h_sig, "tangent": mm.PinnedArray((36, Ne)).array, "state": mm.PinnedArray((14, Ne)).array, "flags": h_fl, "iters": h_it}
-    dt, (sg, _, _) = timed(lambda: mm.material_response(m, h_eps, mm.PlasticState(h_st), out=h_out))
+    dt, (sg, _, _) = timed(lambda: mm.material_response(m, h_eps, mm.PlasticState(h_st), out=h_out), name="dense")
     launches["n"] += chunks * (steps + 1)
     variants["dense"] = {"value": world * Ne * steps / dt, "h2d_bytes_per_step": 160 * Ne, "d2h_bytes_per_step": 451 * Ne + 4,
                          "matches_device_path": bool(np.array_equal(sg, ref_sig))}
     h_out = None
     compact_variant("compact")
-    head = compact_variant("factored")
     compact_variant("factored", resident=True)
     if world == 1:
         compact_variant("factored", expand=True)
@@ -543,7 +549,18 @@ def other_configs(mm, torch, dev, peak):
         nc, lo, hi, seed = sy.c5_jump()
         D = mm.synth_uniform(N, nc, seed, lo, hi, device=dev)
         rec("c4_xu_needleman_3d", N, 120, _time_kernel(torch, lambda: mm.material_response(xm, D)))
-        del D
+        # the same config through the host-buffer path (pinned numpy arrays -> mmh_xu_needleman): 24 B up, 96 B down per point
+        Ne = 2 * 10**7
+        hD = mm.PinnedArray((3, Ne)).array
+        hD[...] = D[:, :Ne].cpu().numpy()
+        mm.material_response(xm, hD)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            mm.material_response(xm, hD)
+        dt = (time.perf_counter() - t0) / 3
+        out["c4_xu_needleman_3d"]["e2e"] = {"updates_per_s": Ne / dt, "points": Ne, "h2d_bytes_per_step": 24 * Ne, "d2h_bytes_per_step": 96 * Ne,
+                                            "note": "material_response(m, numpy jump) -> mmh_xu_needleman; output arrays are fresh pageable numpy arrays (allocation inside the call)"}
+        del D, hD
         torch.cuda.empty_cache()
         N = 10**7
         cm = mm.CrystalViscoPlastic(slipsystems=mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES), **sy.CRYSTAL_PARAMS)
@@ -554,6 +571,20 @@ def other_configs(mm, torch, dev, peak):
         dB = mm.synth_uniform(N, nc, seed, lo, hi, device=dev)
         ms = _time_kernel(torch, lambda: mm.material_response(cm, dB, stA, 1.0, options={"defer_check": True}), reps=3, warm=1)
         _, _, stB = mm.material_response(cm, dB, stA, 1.0, options={"defer_check": True})
+        Ne = 4 * 10**6
+        hd = mm.PinnedArray((6, Ne)).array
+        hs = mm.PinnedArray((42, Ne)).array
+        hd[...] = dB[:, :Ne].cpu().numpy()
+        hs[...] = stA.data[:, :Ne].cpu().numpy()
+        hst = mm.CrystalViscoPlasticState(hs)
+        mm.material_response(cm, hd, hst, 1.0, options={"defer_check": True})
+        t0 = time.perf_counter()
+        for _ in range(2):
+            mm.material_response(cm, hd, hst, 1.0, options={"defer_check": True})
+        dte = (time.perf_counter() - t0) / 2
+        e2e_c = {"updates_per_s": Ne / dte, "points": Ne, "h2d_bytes_per_step": 384 * Ne, "d2h_bytes_per_step": 676 * Ne,
+                 "note": "material_response(m, numpy deps, state(numpy), dt) -> mmh_crystal; output arrays are fresh pageable numpy arrays"}
+        del hd, hs, hst
         it = stB.iters.float()
         # flops of the REFERENCE algorithm per point (dense 12x12): per Newton update LU 1152 + solves 288 + Jacobian/residual 1392;
         # final evaluation 1392; tangent (inv(J), dR/dε, 12 outer products) 6100  -> DESIGN.md §4.5
@@ -561,10 +592,25 @@ def other_configs(mm, torch, dev, peak):
         f64 = fp64_peak_tflops()
         rec("c3_crystal_fcc12_stepB", N, 1056, ms, mean_newton_updates=float(it.mean().item()), frac_points_with_active_slip=float((stB.flags != 0).float().mean().item()),
             n_not_converged=int(stB.n_fail.item()), reference_algorithm_tflops=round(ref_flops / (ms * 1e-3) / 1e12, 2), fp64_fma_peak_tflops_measured=f64,
-            bound="fp64 / latency (not HBM): see profiles/r01_crystal_two_kernel_ncu_full.txt")
+            bound="fp64 issue / latency (not HBM)", roofline=crystal_roofline(N, ms, f64), e2e=e2e_c)
     except Exception as e:       # informational block must never cost the headline line
         out["error"] = repr(e)
     return out
+
+
+def crystal_roofline(N, ms, fp64_peak_tflops):
+    """FP64 roofline of the crystal update from EXECUTED instructions: thread-level DFMA / DMUL / DADD per point counted by ncu on the
+    committed capture of the same kernels (profiles/crystal_fp64_executed.json), times this run's points, over this run's time, against the
+    measured DFMA peak (tools/fp64_peak.cu).  `frac` is that ratio; `pipe_active_ncu` is ncu's own sm__pipe_fp64_cycles_active of the capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "crystal_fp64_executed.json")) as f:
+            c = json.load(f)
+        flops = (2.0 * c["dfma_per_point"] + c["dmul_per_point"] + c["dadd_per_point"]) * N
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"bound": "fp64", "achieved": ach, "peak": fp64_peak_tflops, "unit": "TFLOP/s (executed DFMA x2 + DMUL + DADD)", "frac": (ach / fp64_peak_tflops) if fp64_peak_tflops else None,
+                "pipe_active_ncu": c.get("pipe_fp64_active_pct"), "source": c.get("source")}
+    except Exception as e:
+        return {"bound": "fp64", "error": repr(e)}
 
 
 def stB_slice_host(stB, mm, m, epsB, stA, Ne):
