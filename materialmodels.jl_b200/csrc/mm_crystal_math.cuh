@@ -430,7 +430,7 @@ MM_HD void crystal_init(const KT& k, Acc& acc, Scr& scr, CrystalLane& L) {
 }
 
 #ifndef MM_CRYSTAL_UNROLL
-#define MM_CRYSTAL_UNROLL 1
+#define MM_CRYSTAL_UNROLL 2   // r02 sweep after the sign / power specialisation: 1 -> 22.0 ms, 2 -> 21.5 ms, 3 -> 21.6 ms (profiles/r02_crystal_variant_and_knob_sweep.log)
 #endif
 #ifndef MM_CRYSTAL_UNROLL_SMALL
 #define MM_CRYSTAL_UNROLL_SMALL 12

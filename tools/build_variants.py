@@ -22,7 +22,7 @@ for tag, o, p in procs:
     open(os.path.join(out, tag + ".ptxas.log"), "w").write(log)
     if p.returncode:
         sys.exit("nvcc failed for %s:\n%s" % (tag, log[-2000:]))
-    objs = [o if s == unit else os.path.join(B.HERE, "build", s.replace(".cu", ".o")) for s in B.SOURCES]
+    objs = [o if s == unit else B._obj(s) for s in B.SOURCES]
     so = os.path.join(out, "libmmb200_%s.so" % tag)
     subprocess.check_call([B.nvcc(), "-shared", "-o", so] + objs + ["-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a"])
     print(so)
