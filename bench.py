@@ -520,6 +520,8 @@ def fp64_peak_tflops():
 def other_configs(mm, torch, dev, peak):
     """Kernel-only timings of BASELINE.json configs[0], [2], [3], [4] at their stated sizes (the headline stays configs[1]).
     Informational: same CUDA-event timing, inputs resident, median of 5; each entry names its algorithmic bytes/point."""
+    import numpy as np
+
     from materialmodels_jl_b200 import synth as sy
 
     out = {}
@@ -553,14 +555,15 @@ def other_configs(mm, torch, dev, peak):
         Ne = 2 * 10**7
         hD = mm.PinnedArray((3, Ne)).array
         hD[...] = D[:, :Ne].cpu().numpy()
-        mm.material_response(xm, hD)
+        ho = {"stress": mm.PinnedArray((3, Ne)).array, "tangent": mm.PinnedArray((9, Ne)).array}
+        mm.material_response(xm, hD, out=ho)
         t0 = time.perf_counter()
         for _ in range(3):
-            mm.material_response(xm, hD)
+            mm.material_response(xm, hD, out=ho)
         dt = (time.perf_counter() - t0) / 3
         out["c4_xu_needleman_3d"]["e2e"] = {"updates_per_s": Ne / dt, "points": Ne, "h2d_bytes_per_step": 24 * Ne, "d2h_bytes_per_step": 96 * Ne,
-                                            "note": "material_response(m, numpy jump) -> mmh_xu_needleman; output arrays are fresh pageable numpy arrays (allocation inside the call)"}
-        del D, hD
+                                            "note": "material_response(m, numpy jump, out=pinned buffers) -> mmh_xu_needleman"}
+        del D, hD, ho
         torch.cuda.empty_cache()
         N = 10**7
         cm = mm.CrystalViscoPlastic(slipsystems=mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES), **sy.CRYSTAL_PARAMS)
@@ -577,14 +580,16 @@ def other_configs(mm, torch, dev, peak):
         hd[...] = dB[:, :Ne].cpu().numpy()
         hs[...] = stA.data[:, :Ne].cpu().numpy()
         hst = mm.CrystalViscoPlasticState(hs)
-        mm.material_response(cm, hd, hst, 1.0, options={"defer_check": True})
+        ho = {"stress": mm.PinnedArray((6, Ne)).array, "tangent": mm.PinnedArray((36, Ne)).array, "state": mm.PinnedArray((42, Ne)).array,
+              "flags": mm.PinnedArray((Ne,), np.uint16).array, "iters": mm.PinnedArray((Ne,), np.uint16).array}
+        mm.material_response(cm, hd, hst, 1.0, options={"defer_check": True}, out=ho)
         t0 = time.perf_counter()
         for _ in range(2):
-            mm.material_response(cm, hd, hst, 1.0, options={"defer_check": True})
+            mm.material_response(cm, hd, hst, 1.0, options={"defer_check": True}, out=ho)
         dte = (time.perf_counter() - t0) / 2
         e2e_c = {"updates_per_s": Ne / dte, "points": Ne, "h2d_bytes_per_step": 384 * Ne, "d2h_bytes_per_step": 676 * Ne,
-                 "note": "material_response(m, numpy deps, state(numpy), dt) -> mmh_crystal; output arrays are fresh pageable numpy arrays"}
-        del hd, hs, hst
+                 "note": "material_response(m, numpy deps, state(numpy), dt, out=pinned buffers) -> mmh_crystal"}
+        del hd, hs, hst, ho
         it = stB.iters.float()
         # flops of the REFERENCE algorithm per point (dense 12x12): per Newton update LU 1152 + solves 288 + Jacobian/residual 1392;
         # final evaluation 1392; tangent (inv(J), dR/dε, 12 outer products) 6100  -> DESIGN.md §4.5

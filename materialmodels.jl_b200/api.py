@@ -281,11 +281,11 @@ def _finish_fail(nfail, like, options):
         raise RuntimeError(NOT_CONVERGED)
 
 
-def _response_linear_elastic(m, ε, state, layout, want_tangent):
+def _response_linear_elastic(m, ε, state, layout, want_tangent, out=None):
     ε = _prep(ε)
     N = _npoints(ε, 6, layout)
-    σ = _empty(_shape(6, N, layout), ε)
-    tan = _empty(_shape(36, N, layout), ε) if want_tangent else None
+    σ = _out(out, "stress", _shape(6, N, layout), ε)
+    tan = _out(out, "tangent", _shape(36, N, layout), ε) if want_tangent else None
     lib = load()
     with _DeviceGuard(ε):
         if _is_host(ε):
@@ -520,7 +520,7 @@ def _response_plastic(m, ε, state, options, want_tangent, out=None):
     return σ, tan, new
 
 
-def _response_crystal(m, Δε, state, Δt, options, want_tangent):
+def _response_crystal(m, Δε, state, Δt, options, want_tangent, out=None):
     layout = state.layout
     Δε = _prep(Δε)
     N = _npoints(Δε, 6, layout)
@@ -528,12 +528,12 @@ def _response_crystal(m, Δε, state, Δt, options, want_tangent):
         raise ValueError("strain has %d points, state has %d" % (N, state.N))
     sin = _prep(state.data)
     _same_place(Δε, sin, "material_response(::CrystalViscoPlastic)")
-    σ = _empty(_shape(6, N, layout), Δε)
-    tan = _empty(_shape(36, N, layout), Δε) if want_tangent else None
-    sout = _empty(_shape(42, N, layout), Δε)
+    σ = _out(out, "stress", _shape(6, N, layout), Δε)
+    tan = _out(out, "tangent", _shape(36, N, layout), Δε) if want_tangent else None
+    sout = _out(out, "state", _shape(42, N, layout), Δε)
     host = _is_host(Δε)
-    active = _empty((N,), Δε, np.uint16 if host else _torch().int16)
-    iters = _empty((N,), Δε, np.uint16 if host else _torch().int16)
+    active = _out(out, "flags", (N,), Δε, np.uint16 if host else _torch().int16)
+    iters = _out(out, "iters", (N,), Δε, np.uint16 if host else _torch().int16)
     nfail = _zeros((1,), Δε, np.int32 if host else _torch().int32)
     o = _newton_opts(m, options)
     lib = load()
@@ -551,13 +551,13 @@ def _response_crystal(m, Δε, state, Δt, options, want_tangent):
     return σ, tan, new
 
 
-def _response_hyper(m, strain, kind, state, layout, want_tangent, tangent_kind=_abi.MM_TANGENT_DSDC):
+def _response_hyper(m, strain, kind, state, layout, want_tangent, tangent_kind=_abi.MM_TANGENT_DSDC, out=None):
     strain = _prep(strain)
     nin = 9 if kind == _abi.MM_STRAIN_F else 6
     ns, nt = (9, 81) if tangent_kind == _abi.MM_TANGENT_DPDF else (6, 36)
     N = _npoints(strain, nin, layout)
-    S = _empty(_shape(ns, N, layout), strain)
-    tan = _empty(_shape(nt, N, layout), strain) if want_tangent else None
+    S = _out(out, "stress", _shape(ns, N, layout), strain)
+    tan = _out(out, "tangent", _shape(nt, N, layout), strain) if want_tangent else None
     lib = load()
     with _DeviceGuard(strain):
         if _is_host(strain):
@@ -568,7 +568,7 @@ def _response_hyper(m, strain, kind, state, layout, want_tangent, tangent_kind=_
     return S, tan, state
 
 
-def _response_transviso(m, ε, state, want_tangent):
+def _response_transviso(m, ε, state, want_tangent, out=None):
     """material_response(m::TransverselyIsotropic, ε, state) — reference src/transverselyisotropic.jl:92-106."""
     layout = state.layout
     ε = _prep(ε)
@@ -578,8 +578,8 @@ def _response_transviso(m, ε, state, want_tangent):
     a3 = _prep(state.data)
     if _is_host(ε) != _is_host(a3):
         raise ValueError("strain and state must live in the same place")
-    σ = _empty(_shape(6, N, layout), ε)
-    tan = _empty(_shape(36, N, layout), ε) if want_tangent else None
+    σ = _out(out, "stress", _shape(6, N, layout), ε)
+    tan = _out(out, "tangent", _shape(36, N, layout), ε) if want_tangent else None
     lib = load()
     with _DeviceGuard(ε):
         if _is_host(ε):
@@ -630,14 +630,14 @@ def elastic_strain_energy_density(m, strain, layout="soa"):
     raise TypeError("elastic_strain_energy_density is defined for LinearElastic, NeoHook, Yeoh, StVenant (as in the reference)")
 
 
-def _response_xu(m, Δ, state, layout, want_tangent):
+def _response_xu(m, Δ, state, layout, want_tangent, out=None):
     Δ = _prep(Δ)
     dim = Δ.shape[0] if _LAYOUTS[layout] == 0 else Δ.shape[1]
     if dim not in (2, 3):
         raise ValueError("XuNeedleman: jump must have 2 or 3 components")
     N = _npoints(Δ, dim, layout)
-    T = _empty(_shape(dim, N, layout), Δ)
-    H = _empty(_shape(dim * dim, N, layout), Δ) if want_tangent else None
+    T = _out(out, "stress", _shape(dim, N, layout), Δ)
+    H = _out(out, "tangent", _shape(dim * dim, N, layout), Δ) if want_tangent else None
     lib = load()
     with _DeviceGuard(Δ):
         if _is_host(Δ):
@@ -745,7 +745,7 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
     `tangent="compact" | "factored"` (Plastic, numpy strains): the reference's own return shape, src/Plastic.jl:134-135 — elastic points
     share m.Eᵉ and keep their state, yielded points own one row (CompactTangent / CompactPlasticState); a state on a CUDA device
     with numpy strains = resident mode (state updated in place on the device, only ε up and σ + rows down);
-    `out` (Plastic) = dict of preallocated output buffers: stress, tangent, state, flags, iters (and rows for the compact forms)."""
+    `out` = dict of preallocated output buffers (e.g. pinned host memory): stress, tangent [, state, flags, iters for Plastic / CrystalViscoPlastic; rows for the compact forms]."""
     args = list(args)
     if args and isinstance(args[0], AbstractDim):                            # src/wrappers.jl:29-79
         dim = args.pop(0)
@@ -794,7 +794,7 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
             raise RuntimeError("%s is not the native strain measure for %s:" % (type(strain).__name__, type(m).__name__))
         if tk == _abi.MM_TANGENT_DPDF and kind != _abi.MM_STRAIN_F:
             raise TypeError("the dPdF (∂Pᵀ∂F) output needs DeformationGradient(F) as input (traits.jl:67-72)")
-        return _response_hyper(m, strain.value, kind, state if state is not None else initial_material_state(m), layout, tangent, tk)
+        return _response_hyper(m, strain.value, kind, state if state is not None else initial_material_state(m), layout, tangent, tk, out)
 
     m = args.pop(0)
     strain = args.pop(0)
@@ -805,7 +805,7 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
     if args:
         options = args.pop(0)
     if isinstance(m, LinearElastic):
-        return _response_linear_elastic(m, strain, state if state is not None else LinearElasticState(), layout, tangent)
+        return _response_linear_elastic(m, strain, state if state is not None else LinearElasticState(), layout, tangent, out)
     if isinstance(m, Plastic):
         if state is None:
             raise TypeError("material_response(::Plastic, ε, state): state required")
@@ -817,15 +817,15 @@ def material_response(*args, cache=None, options=None, layout="soa", tangent=Tru
     if isinstance(m, CrystalViscoPlastic):
         if state is None:
             raise TypeError("material_response(::CrystalViscoPlastic, Δε, state): state required")
-        return _response_crystal(m, strain, state, 1.0 if Δt is None else Δt, options, tangent)
+        return _response_crystal(m, strain, state, 1.0 if Δt is None else Δt, options, tangent, out)
     if isinstance(m, _Hyper):
-        return _response_hyper(m, strain, _abi.MM_STRAIN_C, state if state is not None else initial_material_state(m), layout, tangent)
+        return _response_hyper(m, strain, _abi.MM_STRAIN_C, state if state is not None else initial_material_state(m), layout, tangent, out=out)
     if isinstance(m, TransverselyIsotropic):
         if state is None:
             raise TypeError("material_response(::TransverselyIsotropic, ε, state): state (material direction) required")
-        return _response_transviso(m, strain, state, tangent)
+        return _response_transviso(m, strain, state, tangent, out)
     if isinstance(m, XuNeedleman):
-        return _response_xu(m, strain, state if state is not None else XuNeedlemanState(), layout, tangent)
+        return _response_xu(m, strain, state if state is not None else XuNeedlemanState(), layout, tangent, out)
     raise TypeError("material_response: unsupported material %r" % (m,))
 
 

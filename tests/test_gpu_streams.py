@@ -235,3 +235,41 @@ def test_strain_and_state_must_live_in_the_same_place(mm, torch):
         with pytest.raises(ValueError):
             mm.material_response(p, eps_d, mm.initial_material_state(p, N), out={"stress": bad})
     torch.cuda.synchronize()
+
+
+def test_out_buffers_for_every_model(mm, torch):
+    """out= (caller-provided, e.g. pinned, buffers) is honoured by every model path and gives the same bits as the allocating call"""
+    N = 3001
+    le = mm.LinearElastic(E=200e3, ν=0.3)
+    nc, lo, hi, seed = sy.c1_strain()
+    eps = sy.host_uniform(N, nc, seed, lo, hi)
+    ref = mm.material_response(le, eps)
+    o = {"stress": mm.PinnedArray((6, N)).array, "tangent": mm.PinnedArray((36, N)).array}
+    got = mm.material_response(le, eps, out=o)
+    assert got[0] is o["stress"] and np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    cm = make_crystal(mm)
+    nc, lo, hi, seed = sy.c4_strain_increment(0)
+    de = sy.host_uniform(N, nc, seed, lo, hi)
+    st = mm.initial_material_state(cm, N, device="cpu")
+    ref = mm.material_response(cm, de, st, 1.0)
+    o = {"stress": np.empty((6, N)), "tangent": np.empty((36, N)), "state": np.empty((42, N)), "flags": np.empty(N, np.uint16), "iters": np.empty(N, np.uint16)}
+    got = mm.material_response(cm, de, st, 1.0, out=o)
+    assert got[2].data is o["state"] and all(np.array_equal(a, b) for a, b in ((got[0], ref[0]), (got[1], ref[1]), (got[2].data, ref[2].data), (got[2].flags, ref[2].flags), (got[2].iters, ref[2].iters)))
+    x = sy.XU_PARAMS
+    xm = mm.XuNeedleman(σₘₐₓ=x["sigma_max"], τₘₐₓ=x["tau_max"], Φₙ=mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]),
+                        Φₜ=mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), Δₙˢ=x["Delta_n_star"])
+    nc, lo, hi, seed = sy.c5_jump()
+    D = mm.synth_uniform(N, nc, seed, lo, hi)
+    ref = mm.material_response(xm, D)
+    o = {"stress": torch.empty_like(D), "tangent": torch.empty((9, N), dtype=torch.float64, device="cuda")}
+    got = mm.material_response(xm, D, out=o)
+    assert got[0] is o["stress"] and torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+    nh = mm.NeoHook(λ=1.0, μ=1.0)
+    nc, lo, hi, seed = sy.c3_defgrad()
+    F = mm.synth_uniform(N, nc, seed, lo, hi)
+    ref = mm.material_response(mm.dPdF(), nh, mm.DeformationGradient(F))
+    o = {"stress": torch.empty((9, N), dtype=torch.float64, device="cuda"), "tangent": torch.empty((81, N), dtype=torch.float64, device="cuda")}
+    got = mm.material_response(mm.dPdF(), nh, mm.DeformationGradient(F), out=o)
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and got[1] is o["tangent"]
+    with pytest.raises(ValueError):
+        mm.material_response(xm, D, out={"stress": torch.empty((3, N + 1), dtype=torch.float64, device="cuda")})
