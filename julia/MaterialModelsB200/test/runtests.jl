@@ -32,3 +32,34 @@ end
         @test Array(S)[:, i] ≈ collect(reinterpret(Float64, [Sr.value])) rtol = 1e-12
     end
 end
+
+@testset "J2 Plastic, host arrays: compact return == dense return (src/Plastic.jl:134-135 shape)" begin
+    m = Plastic(E=200e3, ν=0.3, σ_y=200.0, H=50.0, r=0.5, κ_∞=13.0, α_∞=13.0)
+    N = 50_000
+    ε = 6.6e-4 .* (2 .* rand(6, N) .- 1)
+    st = zeros(14, N)
+    σ, D, st2 = material_response(m, ε, st)                                  # mmh_plastic (dense)
+    r = B.material_response_compact(m, ε, st; kind = :factored)              # mmh_plastic_compact
+    @test r.σ == σ
+    @test count(!iszero, r.flags .& 0x01) == size(r.rows, 2)
+    Dx, stx = B.expand(m, r, st)                                             # mmh_plastic_expand
+    @test Dx == D && stx == st2                                              # bit-identical
+    Ee = reshape(collect(reinterpret(Float64, [m.Eᵉ])), 36)
+    @test all(Dx[:, i] == Ee for i in findall(iszero, r.flags .& 0x01))      # elastic points: the one stored Eᵉ
+end
+
+@testset "small-strain trait route and Dim{d} (src/traits.jl:91-148, src/wrappers.jl:3)" begin
+    m = LinearElastic(E=200e3, ν=0.3)
+    N = 1000
+    ε = CuArray(2e-3 .* (2 .* rand(6, N) .- 1))
+    σ1, _, _ = material_response(m, ε)
+    σ2, _, _ = material_response(∂σ∂ε(), m, SmallStrain(ε))
+    @test Array(σ1) == Array(σ2)
+    @test_throws ErrorException material_response(∂σ∂ε(), m, DeformationGradient(CuArray(rand(9, N))))     # traits.jl:120
+    p = Plastic(E=200e3, ν=0.3, σ_y=200.0, H=50.0, r=0.5, κ_∞=13.0, α_∞=13.0)
+    st = initial_material_state(p, N)
+    e2 = CuArray(1.5e-3 .* (2 .* rand(3, N) .- 1))
+    a = material_response(PlaneStrain(), p, e2, st)
+    b = material_response(MaterialModels.Dim{2}(), p, e2, st)
+    @test Array(a[1]) == Array(b[1]) && Array(a[2]) == Array(b[2])
+end
