@@ -27,10 +27,10 @@ class Guarded:
         self.buf.fill_(self.sent)
         self.ptr = C.c_void_p(self.buf.data_ptr() + self.shift * self.buf.element_size())
 
-    def check(self, name):
+    def check(self, name, all_written=True):
         b = self.buf
         assert bool((b[: self.shift] == self.sent).all()) and bool((b[self.shift + self.n:] == self.sent).all()), "%s: write outside the output range" % name
-        if self.buf.dtype == self.torch.float64:
+        if all_written and self.buf.dtype == self.torch.float64:
             assert not bool((b[self.shift: self.shift + self.n] == self.sent).any()), "%s: output element left unwritten" % name
         return b[self.shift: self.shift + self.n]
 
@@ -81,6 +81,23 @@ def test_no_entry_point_writes_out_of_bounds(mm, cuda_lib, N, lay, shift):
     assert lib.mm_plastic(C.byref(pp), I(e2), I(np.zeros((14, N))), s.ptr, t.ptr, so.ptr, fl.ptr, it.ptr, pn, None, N, lay, None) == 0
     for g, n in ((s, "σ"), (t, "tangent"), (so, "state"), (fl, "flags"), (it, "iters")):
         g.check("mm_plastic " + n)
+    # compact return: rows sized EXACTLY for the yielded points (one more row would hit the sentinel), guarded count and workspace
+    n_yield = int((fl.check("flags").cpu().numpy() & 1).sum())
+    for kind in (abi.MM_ROWS_TANGENT_STATE, abi.MM_ROWS_FACTORED_STATE, abi.MM_ROWS_TANGENT, abi.MM_ROWS_FACTORED):
+        W = lib.mm_plastic_row_width(kind)
+        wsz = lib.mm_plastic_compact_workspace(N, 1)
+        s, so, fl2, it2, rows, ws = G(6 * N), G(14 * N), G(N, u8), G(N, i16), G(max(n_yield, 1) * W), G((wsz + 7) // 8)
+        cnt = torch.full((3,), -1, dtype=torch.int64, device="cuda")
+        args = (C.byref(pp), I(e2), I(np.zeros((14, N))), s.ptr, fl2.ptr, it2.ptr, kind, rows.ptr, n_yield, C.c_void_p(cnt.data_ptr() + 8), so.ptr, pn, None, ws.ptr)
+        assert lib.mm_plastic_compact(*args, wsz - 256, N, lay, None) == abi.MM_ERR_ARG          # a workspace declared too small is refused
+        assert lib.mm_plastic_compact(*args, wsz, N, lay, None) == 0
+        torch.cuda.synchronize()
+        assert cnt.tolist() == [-1, n_yield, -1]
+        for g, n in ((s, "σ"), (so, "state"), (fl2, "flags"), (it2, "iters")):
+            g.check("mm_plastic_compact " + n)
+        ws.check("mm_plastic_compact workspace", all_written=False)      # nothing outside the declared workspace range
+        if n_yield:
+            rows.check("mm_plastic_compact rows")
     # wrapped Plastic: PlaneStress (nc 3) and UniaxialStress (nc 1)
     for kind, ncr, amp in ((abi.MM_DIM_PLANE_STRESS, 3, 1.2e-3), (abi.MM_DIM_UNIAXIAL_STRESS, 1, 2.5e-3), (abi.MM_DIM_PLANE_STRAIN, 3, 1e-3)):
         er = sy.host_uniform(N, ncr, 31, [-amp] * ncr, [amp] * ncr)
