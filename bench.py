@@ -455,7 +455,31 @@ def run_e2e(args, mm, m, epsB, stA, stB, N, world, dev, sharding):
     compact_variant("factored", resident=True)
     if world == 1:
         compact_variant("factored", expand=True)
-    e2e = {"value": head["value"], "unit": UNIT, "h2d_bytes_per_step": head["h2d_bytes_per_step"], "d2h_bytes_per_step": head["d2h_bytes_per_step"],
+    # what the link gives when both directions run at once (two streams, pinned buffers): the roofline of the host-buffer path
+    link = None
+    try:
+        nlk = min(Ne * 6, 2**27)                       # <= 1 GiB each way
+        a_h, b_h = torch.from_numpy(h_sig.reshape(-1)[:nlk]), torch.from_numpy(h_eps.reshape(-1)[:nlk])
+        a_d, b_d = torch.empty(nlk, dtype=torch.float64, device=dev), torch.empty(nlk, dtype=torch.float64, device=dev)
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        best = 0.0
+        for _ in range(3):
+            torch.cuda.synchronize()
+            sharding.barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s1):
+                b_d.copy_(b_h, non_blocking=True)
+            with torch.cuda.stream(s2):
+                a_h.copy_(a_d, non_blocking=True)
+            torch.cuda.synchronize()
+            best = max(best, 8 * nlk / (time.perf_counter() - t0) / 1e9)
+        ach = min(head["h2d_bytes_per_step"], head["d2h_bytes_per_step"]) * (head["value"] / world) / Ne / 1e9
+        link = {"bound": "pcie, both directions at once", "achieved": ach, "peak": best, "unit": "GB/s per direction per GPU", "frac": ach / best,
+                "how": "peak = one %.2f GiB cudaMemcpyAsync each way on two streams, pinned memory, best of 3, measured in this run" % (8 * nlk / 2**30)}
+        del a_d, b_d
+    except Exception as e:       # informational
+        link = {"error": repr(e)}
+    e2e = {"value": head["value"], "unit": UNIT, "link_roofline": link, "h2d_bytes_per_step": head["h2d_bytes_per_step"], "d2h_bytes_per_step": head["d2h_bytes_per_step"],
            "d2h_bytes_per_step_dense_equivalent": 451 * Ne + 4, "points_per_step_per_gpu": Ne, "steps": steps,
            "api": "material_response(m, numpy eps, PlasticState(numpy), tangent='factored') -> mmh_plastic_compact: sigma, flags, iters for all points; "
                   "[g_xi, u(6), n(6) | state(14)] rows for the yielded points only (elastic points: the shared E_e and their unchanged state, as Plastic.jl:134-135 returns them)",

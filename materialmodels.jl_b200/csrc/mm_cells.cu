@@ -66,8 +66,14 @@ struct CellArgs {
 #ifndef MM_CELLS_MINBLOCKS
 #define MM_CELLS_MINBLOCKS 3
 #endif
+#ifndef MM_CELLS_KE_MINBLOCKS
+#define MM_CELLS_KE_MINBLOCKS 2      // element-stiffness instantiations: resident blocks of 128 threads (register cap)
+#endif
+#ifndef MM_CELLS_KE_CH
+#define MM_CELLS_KE_CH 8             // node columns accumulated at once per lane (3 x 3·CH accumulators)
+#endif
 template <int MODEL, int NN, int NQ, int BS, bool WITH_KE>
-__global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_kernel(const ElasticK ke, const PlasticK kp, const TransvIsoK kt, const CellArgs a) {
+__global__ void __launch_bounds__(BS, WITH_KE ? MM_CELLS_KE_MINBLOCKS : MM_CELLS_MINBLOCKS) cells_kernel(const ElasticK ke, const PlasticK kp, const TransvIsoK kt, const CellArgs a) {
     static_assert(NQ == 1 || NQ == 2 || NQ == 4 || NQ == 8, "quadrature points per cell must be a power of two <= 8");
     static_assert(BS % 32 == 0 && 32 % NQ == 0, "a cell's points must share a warp");
     constexpr int NC = 3 * NN;
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(BS, WITH_KE ? 2 : MM_CELLS_MINBLOCKS) cells_ke
             // NQ lanes per cell: lane q owns the block rows of nodes a = q, q+NQ, … and accumulates them over the cell's NQ points in
             // registers — no cross-lane reduction.  Every point parks its tangent and dΩ in shared memory ([thread][38], read back as
             // broadcast 128-bit loads by the NQ lanes of the cell); ∇N is already there.  Columns in chunks of <= 8 nodes (72 accumulators).
-            constexpr int PD = 38, CH = (NN < 8) ? NN : 8, MM_CELLS_KE_UNROLL_V = MM_CELLS_KE_UNROLL;
+            constexpr int PD = 38, CH = (NN < MM_CELLS_KE_CH) ? NN : MM_CELLS_KE_CH, MM_CELLS_KE_UNROLL_V = MM_CELLS_KE_UNROLL;
             double* sm_D = sm_f + ((NC * (BS + 1) + 1) & ~1);   // its own region (the fe image is column-per-thread, this one row-per-thread:
                                                                 // sharing the buffer would need a block-wide barrier); rounded up to 16 bytes
 #pragma unroll

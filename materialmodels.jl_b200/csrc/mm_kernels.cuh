@@ -237,6 +237,109 @@ aos_bulk_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// SoA arrays through the copy engine (opt-in per Op: SoaTiled<Op>): a tile of BS points of ONE component is a contiguous run of BS
+// doubles, so a tile is NIN_comps + NOUT_comps bulk copies into / out of a component-major shared-memory image ([comp][point]:
+// conflict-free for thread <-> point).  For the light ops with many output streams (XuNeedleman: 3 in, 12 out) the direct kernel above
+// keeps 15 DRAM streams per warp open and is bimodal in a sustained run: 1.85 ms per 1e8 points at its best (1.00 of the HBM peak) but a
+// median of 2.19-2.22 ms on every box (profiles/r02_xu_soa_tiled_sweeps.log; block size, register cap and residency cap do not matter),
+// while the tiled AoS kernel holds 0.97.  This kernel is the SoA counterpart: 256-point tiles, the copies dealt over 8 warps: 1.95-1.97 ms,
+// min = median, on the box where the direct kernel's median was 2.21 ms.  Same double-buffered input scheme as aos_bulk_kernel.
+#ifndef MM_SOA_TILE_ISSUERS
+#define MM_SOA_TILE_ISSUERS 8      // warps whose lane 0 issues the copies of a tile (component runs dealt round-robin)
+#endif
+template <class Op> struct SoaTiled { static constexpr bool value = false; static constexpr int BS = 512; };
+template <class Op, int BS> struct SoaTileAcc {
+    double* sm_in;
+    double* sm_out;
+    const Ptrs<Op::NIN, Op::NOUT>& p;
+    int t;
+    __device__ __forceinline__ SoaTileAcc(double* in_, double* out_, const Ptrs<Op::NIN, Op::NOUT>& p_, int t_) : sm_in(in_), sm_out(out_), p(p_), t(t_) {}
+    template <int A> __device__ __forceinline__ double in(int c) const { return sm_in[(dense_in_off<Op>(A) + c) * BS + t]; }
+    template <int A> __device__ __forceinline__ void out(int c, double v) const { sm_out[(dense_out_rel_noalias<Op>(A) + c) * BS + t] = v; }
+    template <int A> __device__ __forceinline__ bool has_out() const { return p.out[A] != nullptr; }
+};
+template <class Op, int BS, int A> struct SoaTileIO {
+    static __device__ __forceinline__ void load_tail(double* sm_in, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int64_t i0, int npts) {
+        for (int e = threadIdx.x; e < npts * Op::in_nc(A); e += BS) { const int c = e / npts, t = e - c * npts; sm_in[(dense_in_off<Op>(A) + c) * BS + t] = __ldcs(p.in[A] + (int64_t)c * N + i0 + t); }
+        if constexpr (A + 1 < Op::NIN) SoaTileIO<Op, BS, A + 1>::load_tail(sm_in, p, N, i0, npts);
+    }
+    static __device__ __forceinline__ void store_tail(double* sm_out, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int64_t i0, int npts) {
+        if (p.out[A] != nullptr)
+            for (int e = threadIdx.x; e < npts * Op::out_nc(A); e += BS) { const int c = e / npts, t = e - c * npts; __stcs(p.out[A] + (int64_t)c * N + i0 + t, sm_out[(dense_out_rel_noalias<Op>(A) + c) * BS + t]); }
+        if constexpr (A + 1 < Op::NOUT) SoaTileIO<Op, BS, A + 1>::store_tail(sm_out, p, N, i0, npts);
+    }
+};
+// flat component index -> global run of that component (one elected lane per warp asks, so the compare chain is cheap)
+template <class Op, int A = 0> __device__ __forceinline__ const double* soa_in_run(const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int k) {
+    if constexpr (A + 1 < Op::NIN) { if (k >= dense_in_off<Op>(A + 1)) return soa_in_run<Op, A + 1>(p, N, k); }
+    return p.in[A] + (int64_t)(k - dense_in_off<Op>(A)) * N;
+}
+template <class Op, int A = 0> __device__ __forceinline__ double* soa_out_run(const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int k) {
+    if constexpr (A + 1 < Op::NOUT) { if (k >= dense_out_rel_noalias<Op>(A + 1)) return soa_out_run<Op, A + 1>(p, N, k); }
+    return p.out[A] == nullptr ? nullptr : p.out[A] + (int64_t)(k - dense_out_rel_noalias<Op>(A)) * N;
+}
+template <class Op, int BS> __host__ __device__ constexpr size_t soa_tile_smem_bytes() {
+    return 16 + (size_t)(2 * dense_in_off<Op>(Op::NIN) + dense_out_rel_noalias<Op>(Op::NOUT) + Op::SCRATCH) * BS * sizeof(double);
+}
+template <class Op, int BS>
+__global__ void __launch_bounds__(BS, 1) soa_bulk_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N, const int64_t ntiles, const int bulk) {
+    constexpr int IN_C = dense_in_off<Op>(Op::NIN), OUT_C = dense_out_rel_noalias<Op>(Op::NOUT), IN_D = IN_C * BS, OUT_D = OUT_C * BS, NW = BS / 32;
+    constexpr uint32_t run_bytes = (uint32_t)(BS * sizeof(double));
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm_raw);
+    double* sm_in = reinterpret_cast<double*>(sm_raw + 16);
+    double* sm_out = sm_in + 2 * IN_D;
+    double* sm_scr = sm_out + OUT_D;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+    __syncthreads();
+    int64_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    const int64_t nfull = bulk ? N / BS : 0;
+    constexpr uint32_t in_bytes = (uint32_t)(IN_D * sizeof(double));
+    // the copies of a tile are spread over the warps (lane 0 of warp w moves component runs w, w + NW, ...): 15 copies issued from
+    // one thread serialise on that thread's issue slot
+    constexpr int ISSUERS = (MM_SOA_TILE_ISSUERS < NW) ? MM_SOA_TILE_ISSUERS : NW;
+    const int warp = (int)(threadIdx.x >> 5);
+    const bool leader = (threadIdx.x & 31u) == 0 && warp < ISSUERS;
+    auto issue_loads = [&](double* img, int64_t i0, uint64_t* b) {
+        if (threadIdx.x == 0) mbar_expect_tx(b, in_bytes);
+        if (leader) for (int k = warp; k < IN_C; k += ISSUERS) bulk_g2s(img + k * BS, soa_in_run<Op>(p, N, k) + i0, run_bytes, b);
+    };
+    if (tile < nfull) issue_loads(sm_in, tile * BS, bar);
+    uint32_t k = 0;
+    for (; tile < ntiles; tile += gridDim.x, ++k) {
+        const bool full = tile < nfull;
+        const int npts = (int)((N - tile * BS < BS) ? (N - tile * BS) : BS);
+        const int buf = (int)(k & 1u);
+        double* in_img = sm_in + buf * IN_D;
+        const int64_t nxt = tile + gridDim.x;
+        if (nxt < nfull) issue_loads(sm_in + (buf ^ 1) * IN_D, nxt * BS, bar + (buf ^ 1));
+        if (full) mbar_wait(bar + buf, (k >> 1) & 1u);
+        else { SoaTileIO<Op, BS, 0>::load_tail(in_img, p, N, tile * BS, npts); __syncthreads(); }
+        if ((int)threadIdx.x < npts) {
+            SoaTileAcc<Op, BS> acc(in_img, sm_out, p, (int)threadIdx.x);
+            Scratch scr{sm_scr + threadIdx.x, BS};
+            op.point(acc, tile * BS + threadIdx.x, scr);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (full) {
+            if (leader) {
+                bool any = false;
+                for (int c = warp; c < OUT_C; c += ISSUERS) {
+                    double* g = soa_out_run<Op>(p, N, c);
+                    if (g != nullptr) { bulk_s2g(g + tile * BS, sm_out + c * BS, run_bytes); any = true; }
+                }
+                if (any) { bulk_commit(); bulk_wait_read0(); }
+            }
+        } else {
+            SoaTileIO<Op, BS, 0>::store_tail(sm_out, p, N, tile * BS, npts);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 int set_error(int code, const char* fmt, ...);   // mm_api.cu
 int check_launch(const char* what);              // mm_api.cu
 int sm_count();                                  // mm_api.cu
@@ -258,6 +361,30 @@ template <class K> int ensure_smem(SmemOptIn& st, K kernel, size_t bytes, const 
 template <class Op, int BS_SOA, int BS_AOS = BS_SOA>
 int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int layout, cudaStream_t stream, const char* what) {
     if (N == 0) return 0;
+    if constexpr (SoaTiled<Op>::value) {
+      if (layout == 0) {
+        // copy-engine tiles for the ops that opt in; a run of one component must start 16-byte aligned for every component and tile:
+        // even N and 16-byte aligned bases — otherwise (and for the ragged last tile) element-wise copies inside the same kernel
+        constexpr int TBS = SoaTiled<Op>::BS;
+        bool aligned = (N % 2 == 0);
+        for (int a = 0; a < Op::NIN; ++a) aligned = aligned && ((reinterpret_cast<uintptr_t>(p.in[a]) & 15u) == 0);
+        for (int a = 0; a < Op::NOUT; ++a) aligned = aligned && ((reinterpret_cast<uintptr_t>(p.out[a]) & 15u) == 0);
+        constexpr size_t smem_b = soa_tile_smem_bytes<Op, TBS>();
+        static SmemOptIn tile_optin;
+        if (int rc = ensure_smem(tile_optin, soa_bulk_kernel<Op, TBS>, smem_b, what)) return rc;
+        const int64_t ntiles = (N + TBS - 1) / TBS;
+        static int resident = 0;                       // CTAs per SM that fit (shared-memory images bound it): one persistent wave
+        if (resident == 0) {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, soa_bulk_kernel<Op, TBS>, TBS, smem_b) != cudaSuccess || nb < 1) nb = 1;
+            resident = nb;
+        }
+        int64_t blocks = (int64_t)sm_count() * resident;
+        if (blocks > ntiles) blocks = ntiles;
+        soa_bulk_kernel<Op, TBS><<<(unsigned)blocks, TBS, smem_b, stream>>>(op, p, N, ntiles, aligned ? 1 : 0);
+        return check_launch(what);
+      }
+    }
     if (layout == 0) {
         const int64_t blocks = (N + BS_SOA - 1) / BS_SOA;
         if (blocks > 2147483647LL) return set_error(-1, "%s: N too large for one launch", what);

@@ -95,6 +95,26 @@ template <int DIM> struct XuOp {
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { xu_point<DIM>(k, acc); }
 };
 
+#ifndef MM_XU_MINBLOCKS
+#define MM_XU_MINBLOCKS 1          // occupancy target of the SoA kernel in blocks of MM_XU_SOA_BS threads (1 = no register cap)
+#endif
+#ifndef MM_XU_SOA_BS
+#define MM_XU_SOA_BS 256
+#endif
+template <int DIM> struct MinBlocks<XuOp<DIM>> { static constexpr int value = MM_XU_MINBLOCKS, block = MM_XU_SOA_BS; };
+template <int DIM> struct MinBlocksAos<XuOp<DIM>> { static constexpr int value = 1, block = 32; };
+#ifndef MM_XU_SOA_TILED
+#define MM_XU_SOA_TILED 1
+#endif
+#ifndef MM_XU_TILE_BS
+#define MM_XU_TILE_BS 256
+#endif
+template <int DIM> struct SoaTiled<XuOp<DIM>> { static constexpr bool value = MM_XU_SOA_TILED != 0; static constexpr int BS = MM_XU_TILE_BS; };
+#ifndef MM_XU_CAP
+#define MM_XU_CAP 0
+#endif
+template <int DIM> struct SoaTangentCap<XuOp<DIM>> { static constexpr int blocks = MM_XU_CAP; };
+
 struct TransvIsoOp {
     static constexpr int NIN = 2, NOUT = 2, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? 6 : 3; }
@@ -235,8 +255,8 @@ int mm_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, doubl
     if (!p || N < 0 || (N > 0 && (!jump || !T))) return set_error(MM_ERR_ARG, "mm_xu_needleman: bad argument");
     const XuK k = make_xu_k(p->Phi_n, p->Phi_t, p->delta_n, p->delta_t, p->Delta_n_star);
     Ptrs<1, 2> ptrs; ptrs.in[0] = jump; ptrs.out[0] = T; ptrs.out[1] = dTdD;
-    if (dim == 3) { XuOp<3> op; op.k = k; return launch_points<XuOp<3>, 256, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
-    if (dim == 2) { XuOp<2> op; op.k = k; return launch_points<XuOp<2>, 256, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
+    if (dim == 3) { XuOp<3> op; op.k = k; return launch_points<XuOp<3>, MM_XU_SOA_BS, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
+    if (dim == 2) { XuOp<2> op; op.k = k; return launch_points<XuOp<2>, MM_XU_SOA_BS, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
     return set_error(MM_ERR_ARG, "mm_xu_needleman: dim must be 2 or 3 (got %d)", dim);
 }
 

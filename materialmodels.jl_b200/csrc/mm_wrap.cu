@@ -4,6 +4,8 @@
 #include "mm_kernels.cuh"
 #include "mm_crystal_math.cuh"
 #include "mm_wrap_math.cuh"
+#include "mm_wrap_lp.cuh"
+#include <string.h>
 
 namespace mm {
 
@@ -159,6 +161,138 @@ int launch_wrapped_elastic(const MMLinearElastic* p, const double* eps, double* 
     Ptrs<1, 2> ptrs; ptrs.in[0] = eps; ptrs.out[0] = sig; ptrs.out[1] = tan;
     return launch_points<WrappedElasticOp<KIND>, 256, 128>(op, ptrs, N, layout, st, "mm_wrapped_linear_elastic");
 }
+// ---------------------------------------------------------------------------------------------------------
+// Lane-persistent kernel for the stress-restricted kinds around J2 (the state machine of mm_wrap_lp.cuh).  Each warp owns a contiguous
+// chunk of points; a lane carries one point through TRIAL / NEWTON / OUTER / FINAL and takes the next point of the chunk when it is
+// through, so a warp no longer runs the maximum of its lanes' 2-6 inner solves x 0-3 Newton passes.  Every section is entered on a
+// warp vote; the two sections that only some lanes need per trip (OUTER, FINAL) wait until `th_outer` / `th_final` lanes want them
+// or nothing else can advance.  Global accesses are per lane (a lane's point is wherever the queue was when it finished), but the lanes
+// of a warp stay within a window of a few dozen points, so L1/L2 see whole sectors; HBM traffic is the algorithmic figure.
+struct WrapKnobs { int variant, th_outer, th_final, chunk; };
+static WrapKnobs& wrap_knobs() {
+    static WrapKnobs k = [] {
+        WrapKnobs v{-1, 0, 0, 0};
+        if (const char* e = getenv("MM_WRAPPED_J2_VARIANT")) v.variant = atoi(e);
+        if (const char* e = getenv("MM_WRAPPED_J2_TH_OUTER")) v.th_outer = atoi(e);
+        if (const char* e = getenv("MM_WRAPPED_J2_TH_FINAL")) v.th_final = atoi(e);
+        if (const char* e = getenv("MM_WRAPPED_J2_CHUNK")) v.chunk = atoi(e);
+        return v;
+    }();
+    return k;
+}
+int* wrap_tuning_slot(const char* name) {
+    WrapKnobs& k = wrap_knobs();
+    if (!strcmp(name, "wrapped_j2_variant")) return &k.variant;          // 0 = one thread per point, 1 (default) = lane-persistent
+    if (!strcmp(name, "wrapped_j2_th_outer")) return &k.th_outer;
+    if (!strcmp(name, "wrapped_j2_th_final")) return &k.th_final;
+    if (!strcmp(name, "wrapped_j2_chunk")) return &k.chunk;
+    return nullptr;
+}
+
+template <int KIND, int LAYOUT> struct WrapLaneAcc {
+    const Ptrs<2, 3>& p;
+    int64_t N, i;
+    __device__ __forceinline__ WrapLaneAcc(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_) : p(p_), N(N_), i(i_) {}
+    template <int A> __device__ __forceinline__ double in(int c) const {
+        return LAYOUT == 0 ? p.in[A][(int64_t)c * N + i] : p.in[A][i * WrappedPlasticOp<KIND>::in_nc(A) + c];
+    }
+    template <int A> __device__ __forceinline__ void out(int c, double v) const {
+        if (LAYOUT == 0) p.out[A][(int64_t)c * N + i] = v; else p.out[A][i * WrappedPlasticOp<KIND>::out_nc(A) + c] = v;
+    }
+    template <int A> __device__ __forceinline__ bool has_out() const { return p.out[A] != nullptr; }
+};
+
+#ifndef MM_WRAPLP_BS
+#define MM_WRAPLP_BS 128
+#endif
+#ifndef MM_WRAPLP_MINBLOCKS
+#define MM_WRAPLP_MINBLOCKS 3
+#endif
+#ifndef MM_WRAPLP_TH_OUTER
+#define MM_WRAPLP_TH_OUTER 8
+#endif
+#ifndef MM_WRAPLP_TH_FINAL
+#define MM_WRAPLP_TH_FINAL 32     // PlaneStress / ShellStress; UniaxialStress (1 reduced component, 1 tangent entry: a cheap FINAL section) uses MM_WRAPLP_TH_FINAL_UNIAXIAL
+#endif
+#ifndef MM_WRAPLP_TH_FINAL_UNIAXIAL
+#define MM_WRAPLP_TH_FINAL_UNIAXIAL 4
+#endif
+template <int KIND, int LAYOUT, int BS, bool EVAL_TRIPS>
+__global__ void __launch_bounds__(BS, MM_WRAPLP_MINBLOCKS)
+wrapped_j2_lp_kernel(const PlasticK k, const double tol, const int max_iter, const Ptrs<2, 3> p, uint8_t* flags, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail,
+                     const int64_t N, const int chunk, const int th_outer, const int th_final) {
+    extern __shared__ double sm_scratch[];
+    const Scratch scr{sm_scratch + threadIdx.x, BS};
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_id = (int64_t)blockIdx.x * (BS / 32) + (threadIdx.x >> 5);
+    int64_t next = warp_id * chunk;
+    const int64_t end = (next + chunk < N) ? (next + chunk) : N;
+    J2Lane L;
+    L.phase = J2P_IDLE;
+    int64_t my = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, L.phase == J2P_IDLE);
+        if (idle != 0u && next < end) {                       // refill idle lanes with the next points of the chunk
+            if (L.phase == J2P_IDLE) {
+                const int64_t cand = next + __popc(idle & ((1u << lane) - 1u));
+                if (cand < end) {
+                    my = cand;
+                    WrapLaneAcc<KIND, LAYOUT> acc(p, N, my);
+                    j2lp_load<KIND>(acc, scr, L);
+                }
+            }
+            next += __popc(idle);
+        }
+        if (__ballot_sync(FULL, L.phase != J2P_IDLE) == 0u) break;
+        if (L.phase == J2P_TRIAL) j2lp_trial(k, scr, L);
+        if (L.phase == J2P_NEWTON) j2lp_pass(k, scr, L);
+        if (EVAL_TRIPS) {                                     // one trip = one whole inner solve: the passes of a yielded evaluation are 3 almost always
+            while (__ballot_sync(FULL, L.phase == J2P_NEWTON) != 0u) { if (L.phase == J2P_NEWTON) j2lp_pass(k, scr, L); }
+        }
+        const unsigned iterating = __ballot_sync(FULL, L.phase == J2P_NEWTON);
+        const unsigned want_outer = __ballot_sync(FULL, L.phase == J2P_OUTER);
+        if (want_outer != 0u && (__popc(want_outer) >= th_outer || iterating == 0u)) {
+            if (L.phase == J2P_OUTER) j2lp_outer<KIND>(k, scr, L, tol, max_iter);
+        }
+        const unsigned want_final = __ballot_sync(FULL, L.phase == J2P_FINAL);
+        const unsigned advancing = __ballot_sync(FULL, L.phase == J2P_TRIAL || L.phase == J2P_NEWTON || L.phase == J2P_OUTER);
+        if (want_final != 0u && (__popc(want_final) >= th_final || advancing == 0u || next >= end)) {
+            if (L.phase == J2P_FINAL) {
+                WrapLaneAcc<KIND, LAYOUT> acc(p, N, my);
+                if (!j2lp_final<KIND>(k, scr, L, acc)) L.flag |= 0x40;
+                if (flags) flags[my] = (uint8_t)L.flag;
+                if (iters) iters[my] = (uint16_t)(L.iters > 65535 ? 65535 : L.iters);
+                if (outer_iters) outer_iters[my] = (uint8_t)L.oit;
+                if ((L.flag & 0xC0) && n_fail) atomicAdd(n_fail, 1);
+                L.phase = J2P_IDLE;
+            }
+        }
+    }
+}
+template <int KIND, int LAYOUT>
+int launch_wrapped_j2_lp(const PlasticK& k, double tol, int max_iter, const Ptrs<2, 3>& ptrs, uint8_t* flags, uint16_t* iters, uint8_t* oit, int32_t* n_fail, int64_t N,
+                         cudaStream_t st) {
+    constexpr int BS = MM_WRAPLP_BS;
+    constexpr size_t smem = (size_t)J2S_SLOTS * BS * sizeof(double);
+    static_assert(smem <= 48 * 1024, "scratch columns beyond 48 KB need the shared-memory opt-in");
+    const WrapKnobs& kn = wrap_knobs();
+    // chunk of points per warp: long enough that the drain at its end (lanes running dry) is a small share, short enough for many waves
+    const int64_t resident_warps = (int64_t)sm_count() * MM_WRAPLP_MINBLOCKS * (BS / 32);
+    int64_t chunk = N / (resident_warps * 8);
+    if (chunk > 2048) chunk = 2048;
+    if (chunk < 128) chunk = 128;
+    chunk = (chunk + 31) / 32 * 32;
+    if (kn.chunk > 0) chunk = kn.chunk;
+    const int64_t warps = (N + chunk - 1) / chunk;
+    const int64_t blocks = (warps + (BS / 32) - 1) / (BS / 32);
+    if (blocks > 2147483647LL) return set_error(-1, "mm_wrapped_plastic: N too large for one launch");
+    const int th_outer = kn.th_outer > 0 ? kn.th_outer : MM_WRAPLP_TH_OUTER, th_final = kn.th_final > 0 ? kn.th_final : (KIND == WRAP_UNIAXIAL_STRESS ? MM_WRAPLP_TH_FINAL_UNIAXIAL : MM_WRAPLP_TH_FINAL);
+    if (kn.variant == 2) wrapped_j2_lp_kernel<KIND, LAYOUT, BS, false><<<(unsigned)blocks, BS, smem, st>>>(k, tol, max_iter, ptrs, flags, iters, oit, n_fail, N, (int)chunk, th_outer, th_final);
+    else                 wrapped_j2_lp_kernel<KIND, LAYOUT, BS, true><<<(unsigned)blocks, BS, smem, st>>>(k, tol, max_iter, ptrs, flags, iters, oit, n_fail, N, (int)chunk, 1, th_final);
+    return check_launch("mm_wrapped_plastic (lane-persistent kernel)");
+}
+
 template <int KIND>
 int launch_wrapped_plastic(const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags, uint16_t* iters,
                            uint8_t* oit, int32_t* n_fail, const MMNewtonOpts* o, const MMNewtonOpts* w, int64_t N, int layout, cudaStream_t st) {
@@ -167,6 +301,12 @@ int launch_wrapped_plastic(const MMPlastic* p, const double* eps, const double* 
     op.tol = w ? w->tol : 1e-8; op.max_iter = w ? w->max_iter : 10;
     op.flags = flags; op.iters = iters; op.outer_iters = oit; op.n_fail = n_fail;
     Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = sin; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = sout;
+    if constexpr (KIND == WRAP_UNIAXIAL_STRESS || KIND == WRAP_PLANE_STRESS || KIND == WRAP_SHELL_STRESS) {
+        if (wrap_knobs().variant != 0 && N > 0 && (layout == 0 || layout == 1)) {
+            return layout == 0 ? launch_wrapped_j2_lp<KIND, 0>(op.k, op.tol, op.max_iter, ptrs, flags, iters, oit, n_fail, N, st)
+                               : launch_wrapped_j2_lp<KIND, 1>(op.k, op.tol, op.max_iter, ptrs, flags, iters, oit, n_fail, N, st);
+        }
+    }
     return launch_points<WrappedPlasticOp<KIND>, 128, 64>(op, ptrs, N, layout, st, "mm_wrapped_plastic");
 }
 

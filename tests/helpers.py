@@ -112,7 +112,7 @@ def hosttwin():
     if _twin is None:
         d = os.path.join(ROOT, "tests", "hosttwin")
         so = os.path.join(d, "libhosttwin.so")
-        srcs = [os.path.join(d, "hosttwin.cpp")] + [os.path.join(ROOT, "materialmodels.jl_b200", "csrc", f) for f in ("mm_math.cuh", "mm_crystal_math.cuh", "mm_wrap_math.cuh")]
+        srcs = [os.path.join(d, "hosttwin.cpp")] + [os.path.join(ROOT, "materialmodels.jl_b200", "csrc", f) for f in ("mm_math.cuh", "mm_crystal_math.cuh", "mm_wrap_math.cuh", "mm_wrap_lp.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, srcs[0]])
         _twin = C.CDLL(so)

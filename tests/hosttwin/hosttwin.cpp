@@ -9,6 +9,7 @@ namespace mm { void mm_crystal_stats_pass(unsigned nz, unsigned cand); }
 #include "../../materialmodels.jl_b200/csrc/mm_math.cuh"
 #include "../../materialmodels.jl_b200/csrc/mm_crystal_math.cuh"
 #include "../../materialmodels.jl_b200/csrc/mm_wrap_math.cuh"
+#include "../../materialmodels.jl_b200/csrc/mm_wrap_lp.cuh"
 
 namespace {
 template <int NIN, int NOUT> struct HostAcc {   // SoA host arrays
@@ -108,6 +109,43 @@ template <int KIND> static void twin_wrapped_plastic_k(const mm::PlasticK& k, co
         int f = mm::wrapped_point<KIND, 14>([&](mm::RegIO<14>& io, int* it) { return mm::plastic_point(k, io, it); }, a, wtol, wmax, &oit, &iit);
         flags[i] = (uint8_t)f; iters[i] = (uint16_t)iit; oiters[i] = (uint8_t)oit;
     }
+}
+// the state machine of the lane-persistent kernel (mm_wrap_lp.cuh), one point at a time: sections entered in the kernel's order
+struct HostColumn { double* v; double& operator()(int j) const { return v[j]; } };
+static uint8_t* g_lp_trace = nullptr;      // optional [N][12]: Newton passes of every inner solve of a point (255 = no such evaluation), for scheduling studies
+extern "C" void twin_wrapped_plastic_lp_set_trace(uint8_t* t) { g_lp_trace = t; }
+template <int KIND> static void twin_wrapped_plastic_lp_k(const mm::PlasticK& k, const double* eps, const double* sin, double* sig, double* tan, double* sout,
+                                                          uint8_t* flags, uint16_t* iters, uint8_t* oiters, double wtol, int wmax, int64_t N) {
+    for (int64_t i = 0; i < N; ++i) {
+        int ev = -1;
+        if (g_lp_trace) memset(g_lp_trace + 12 * i, 255, 12);
+        HostAcc<2, 3> a{{eps, sin}, {sig, tan, sout}, N, i};
+        double col[mm::J2S_SLOTS];
+        HostColumn scr{col};
+        mm::J2Lane L;
+        mm::j2lp_load<KIND>(a, scr, L);
+        while (L.phase != mm::J2P_IDLE) {
+            if (L.phase == mm::J2P_TRIAL) { mm::j2lp_trial(k, scr, L); if (g_lp_trace && ++ev < 12) g_lp_trace[12 * i + ev] = 0; }
+            if (L.phase == mm::J2P_NEWTON) { mm::j2lp_pass(k, scr, L); if (g_lp_trace && ev < 12) ++g_lp_trace[12 * i + ev]; }
+            if (L.phase == mm::J2P_OUTER) mm::j2lp_outer<KIND>(k, scr, L, wtol, wmax);
+            if (L.phase == mm::J2P_FINAL) {
+                if (!mm::j2lp_final<KIND>(k, scr, L, a)) L.flag |= 0x40;
+                flags[i] = (uint8_t)L.flag; iters[i] = (uint16_t)L.iters; oiters[i] = (uint8_t)L.oit;
+                L.phase = mm::J2P_IDLE;
+            }
+        }
+    }
+}
+extern "C" int twin_wrapped_plastic_lp(int kind, const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags,
+                         uint16_t* iters, uint8_t* oiters, double tol, int max_iter, double wtol, int wmax, int64_t N) {
+    mm::PlasticK k = mm::make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, tol, max_iter);
+    switch (kind) {
+        case 3: twin_wrapped_plastic_lp_k<3>(k, eps, sin, sig, tan, sout, flags, iters, oiters, wtol, wmax, N); break;
+        case 4: twin_wrapped_plastic_lp_k<4>(k, eps, sin, sig, tan, sout, flags, iters, oiters, wtol, wmax, N); break;
+        case 5: twin_wrapped_plastic_lp_k<5>(k, eps, sin, sig, tan, sout, flags, iters, oiters, wtol, wmax, N); break;
+        default: return -1;
+    }
+    return 0;
 }
 extern "C" int twin_wrapped_plastic(int kind, const MMPlastic* p, const double* eps, const double* sin, double* sig, double* tan, double* sout, uint8_t* flags,
                          uint16_t* iters, uint8_t* oiters, double tol, int max_iter, double wtol, int wmax, int64_t N) {

@@ -107,6 +107,15 @@ def test_twin_wrapped_matches_oracle(oracle, kind):
         assert np.array_equal(fl, r["flags"]) and np.array_equal(it, r["iters"]) and np.array_equal(oi, r["outer_iters"])
         assert sig_err(sig, r["sig"]) < H.RTOL and H.rel_err(tan, r["tan"]).max() < TAN_TOL[kind]
         assert np.abs(so - r["state"]).max() < 1e-12 * max(1.0, np.abs(r["state"]).max())
+        if kind >= 3:        # the state machine the lane-persistent kernel drives (mm_wrap_lp.cuh): same counts, same flags, same values
+            sig2, tan2, so2 = np.zeros((nc, N)), np.zeros((nc * nc, N)), np.zeros((14, N))
+            fl2, it2, oi2 = np.zeros(N, np.uint8), np.zeros(N, np.uint16), np.zeros(N, np.uint8)
+            tw.twin_wrapped_plastic_lp(kind, C.byref(p), H.P(eps), H.P(st), H.P(sig2), H.P(tan2), H.P(so2), H.P(fl2), H.P(it2), H.P(oi2),
+                                       C.c_double(1e-8), 1000, C.c_double(1e-8), 10, C.c_int64(N))
+            assert np.array_equal(fl2, r["flags"]) and np.array_equal(it2, r["iters"]) and np.array_equal(oi2, r["outer_iters"])
+            assert sig_err(sig2, r["sig"]) < H.RTOL and H.rel_err(tan2, r["tan"]).max() < TAN_TOL[kind]
+            assert np.abs(so2 - r["state"]).max() < 1e-12 * max(1.0, np.abs(r["state"]).max())
+            assert np.abs(sig2 - sig).max() <= 1e-13 * np.abs(sig).max() and np.abs(so2 - so).max() <= 1e-13 * max(1.0, np.abs(so).max())
         st = r["state"]
     e = sy.host_uniform(500, nc, 5, -1e-3, 1e-3)
     rr = oracle.wrapped_linear_elastic(kind, E, NU, e)
@@ -150,6 +159,72 @@ def test_gpu_wrapped_plastic_and_elastic(mm, cuda_lib, oracle, kind, lname, lay)
     rr = oracle.wrapped_linear_elastic(kind, E, NU, e, layout=lay)
     s, t, _ = mm.material_response(dim, le, torch.from_numpy(e).cuda(), None, layout=lname)
     assert H.rel_err(soa(s.cpu().numpy()), soa(rr["sig"])).max() < H.RTOL and H.rel_err(soa(t.cpu().numpy()), soa(rr["tan"])).max() < H.RTOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lname,lay", [("soa", 0), ("aos", 1)])
+@pytest.mark.parametrize("kind", [3, 4, 5])
+def test_gpu_wrapped_plastic_lane_persistent_equals_thread_per_point(mm, cuda_lib, kind, lname, lay):
+    """The lane-persistent kernel (default for the stress-restricted kinds) against the one-thread-per-point kernel
+    (mm_set_tuning("wrapped_j2_variant", 0)): flags, inner and outer counts identical, values to rounding — whatever the section
+    thresholds and the chunk length, for ragged sizes, without a tangent, and updating the state in place."""
+    import torch
+
+    nc = NC[kind]
+    dim = getattr(mm, DIMS[kind])()
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+
+    def run(N, variant, knobs=(), tangent=True, inplace=False):
+        olds = [(b"wrapped_j2_variant", cuda_lib.mm_set_tuning(b"wrapped_j2_variant", variant))]
+        for name, v in knobs:
+            olds.append((name, cuda_lib.mm_set_tuning(name, v)))
+        try:
+            st = mm.initial_material_state(m, N, layout=lname)
+            outs = []
+            for step in range(2):
+                eps = torch.from_numpy(sy.host_uniform(N, nc, 900 + kind + 10 * step, -AMPL[kind], AMPL[kind], layout=lay)).cuda()
+                if inplace:        # state_out == state_in through the C ABI (include/mmb200.h allows it)
+                    P = lambda t_: C.c_void_p(t_.data_ptr())
+                    shp = (lambda n_: (n_, N)) if lay == 0 else (lambda n_: (N, n_))
+                    s = torch.empty(shp(nc), dtype=torch.float64, device="cuda")
+                    t = torch.empty(shp(nc * nc), dtype=torch.float64, device="cuda")
+                    fl, it_ = torch.empty(N, dtype=torch.uint8, device="cuda"), torch.empty(N, dtype=torch.int16, device="cuda")
+                    oi, nf = torch.empty(N, dtype=torch.uint8, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
+                    data = st.data.clone()
+                    rc = cuda_lib.mm_wrapped_plastic(kind, C.byref(m._c), P(eps), P(data), P(s), P(t), P(data), P(fl), P(it_), P(oi), P(nf), None, None, N, lay, None)
+                    assert rc == 0
+                    torch.cuda.synchronize()
+                    new = mm.PlasticState(data, lname)
+                    outs.append((s.cpu().numpy(), t.cpu().numpy(), data.cpu().numpy().copy(), fl.cpu().numpy(), it_.cpu().numpy().view(np.uint16), oi.cpu().numpy()))
+                    st = new
+                    continue
+                s, t, new = mm.material_response(dim, m, eps, st, tangent=tangent)
+                outs.append((s.cpu().numpy(), None if t is None else t.cpu().numpy(), new.data.cpu().numpy().copy(), new.flags.cpu().numpy(), new.iters.cpu().numpy(),
+                             new.outer_iters.cpu().numpy()))
+                st = new
+            return outs
+        finally:
+            for name, v in olds:
+                cuda_lib.mm_set_tuning(name, v)
+
+    def same(a, b):
+        for (s1, t1, d1, f1, i1, o1), (s2, t2, d2, f2, i2, o2) in zip(a, b):
+            assert np.array_equal(f1, f2) and np.array_equal(i1, i2) and np.array_equal(o1, o2)
+            assert np.abs(s1 - s2).max() <= 1e-13 * np.abs(s1).max() and np.abs(d1 - d2).max() <= 1e-13 * max(1.0, np.abs(d1).max())
+            if t1 is not None:
+                assert np.abs(t1 - t2).max() <= 1e-12 * np.abs(t1).max()
+
+    for N in (1, 31, 50021):
+        ref = run(N, 0)
+        assert (ref[1][3] & 1).mean() > 0.1 or N < 100
+        same(ref, run(N, 1))
+    N = 20011
+    ref = run(N, 0)
+    for knobs in (((b"wrapped_j2_th_outer", 1), (b"wrapped_j2_th_final", 1)), ((b"wrapped_j2_th_outer", 32), (b"wrapped_j2_th_final", 32)),
+                  ((b"wrapped_j2_chunk", 32),), ((b"wrapped_j2_chunk", 4096), (b"wrapped_j2_th_final", 3))):
+        same(ref, run(N, 1, knobs))
+    same(run(N, 0, tangent=False), run(N, 1, tangent=False))
+    same(ref, run(N, 1, inplace=True))
 
 
 @pytest.mark.gpu

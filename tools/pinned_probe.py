@@ -35,3 +35,26 @@ for b in range(nb):
         res[name] = round(8 * n / min(ts) / 1e9, 1)
     keep.append(a)
     print(json.dumps({"block": b, "GiB": gib, "is_pinned": bool(t.is_pinned()), **res}), flush=True)
+
+# both directions at once (two streams, 1 GiB copies in flight for ~1 s): what the link gives a full-duplex pipeline
+if os.environ.get("PROBE_BIDIR", "1") == "1":
+    a, b = keep[0], keep[1]
+    ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+    dev2 = torch.empty_like(dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for chunk_mib in (4, 16, 64, 256, 1024):
+        m = chunk_mib * 2**20 // 8
+        reps = max(2, int(16 * 1024 / chunk_mib) // 8)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            for r in range(reps):
+                o = (r * m) % (n - m)
+                dev[o:o + m].copy_(ta[o:o + m], non_blocking=True)
+        with torch.cuda.stream(s2):
+            for r in range(reps):
+                o = (r * m) % (n - m)
+                tb[o:o + m].copy_(dev2[o:o + m], non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(json.dumps({"bidirectional_chunk_MiB": chunk_mib, "each_direction_GBps": round(reps * m * 8 / dt / 1e9, 1)}), flush=True)

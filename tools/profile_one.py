@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Tiny driver for ncu captures: runs a few launches of ONE kernel at a size ncu can replay quickly.
-usage: profile_one.py {plastic|plastic_aos|crystal|neohook|xu|elastic} [points]"""
+usage: profile_one.py {plastic|plastic_aos|crystal|neohook|xu|elastic|wrapped_planestress|...} [points]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -65,6 +65,15 @@ elif which == "transviso":
     st = mm.TransverselyIsotropicState(a3.contiguous(), "soa")
     for _ in range(reps):
         mm.material_response(m, eps, st)
+elif which.startswith("wrapped_"):          # wrapped_planestress / wrapped_uniaxialstress / wrapped_shellstress (J2 inside)
+    dim, nc, amp = {"planestress": (mm.PlaneStress(), 3, 1.2e-3), "uniaxialstress": (mm.UniaxialStress(), 1, 2.5e-3),
+                    "shellstress": (mm.ShellStress(), 6, 0.8e-3), "planestrain": (mm.PlaneStrain(), 3, 1.0e-3)}[which.split("_", 1)[1]]
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    eA = mm.synth_uniform(N, nc, 31, -amp, amp)
+    _, _, stA = mm.material_response(dim, m, eA, mm.initial_material_state(m, N), options={"defer_check": True})
+    eB = mm.synth_uniform(N, nc, 32, -amp, amp)
+    for _ in range(reps):
+        mm.material_response(dim, m, eB, stA, options={"defer_check": True})
 elif which == "elastic":
     nc, lo, hi, seed = sy.c1_strain()
     e = mm.synth_uniform(N, nc, seed, lo, hi)
