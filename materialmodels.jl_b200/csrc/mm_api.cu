@@ -37,6 +37,32 @@ int sm_count() {
     return n;
 }
 
+// Stream-ordered workspace for the few entry points that need one (the crystal fix-up flags / aliased-state side buffer, the rounds of
+// mm_wrapped_crystal): the library's OWN memory pool per device with an unlimited release threshold, so a workspace freed by one call is
+// reused by the next instead of going back to the driver at every synchronisation (with the device's default pool and its zero
+// threshold a 2.3 GB workspace cost 12 ms of cuMemMap per call — half the call, profiles/r02_wrapped_crystal_rounds.log).
+cudaError_t ws_alloc_async(void** ptr, size_t bytes, cudaStream_t st) {
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(ptr, bytes, st);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool;
+        e = cudaMemPoolCreate(&pool, &props);
+        if (e != cudaSuccess) { cudaGetLastError(); return cudaMallocAsync(ptr, bytes, st); }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[dev] = pool;
+    }
+    return cudaMallocFromPoolAsync(ptr, bytes, pools[dev], st);
+}
+
 }  // namespace mm
 
 extern "C" {

@@ -33,12 +33,15 @@ struct CrystalGeneralOp {
 };
 
 // uncoalesced per-point accessor for the (rare) fix-up points, either layout
+// `ii` = where the point's inputs live, `i` = where its outputs go: the same index, except for the index-list batches of the dimension
+// wrappers (inputs stay where the point is, outputs are packed by list position: dense, coalesced stores whatever the list looks like)
 template <int LAYOUT> struct DirectAcc {
     const Ptrs<2, 3>& p;
-    int64_t N, i;
-    __device__ __forceinline__ DirectAcc(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_) : p(p_), N(N_), i(i_) {}
+    int64_t N, i, ii;
+    __device__ __forceinline__ DirectAcc(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_) : p(p_), N(N_), i(i_), ii(i_) {}
+    __device__ __forceinline__ DirectAcc(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_, int64_t ii_) : p(p_), N(N_), i(i_), ii(ii_) {}
     template <int A> __device__ __forceinline__ double in(int c) const {
-        return LAYOUT == 0 ? p.in[A][(int64_t)c * N + i] : p.in[A][i * CrystalGeneralOp::in_nc(A) + c];
+        return LAYOUT == 0 ? p.in[A][(int64_t)c * N + ii] : p.in[A][ii * CrystalGeneralOp::in_nc(A) + c];
     }
     template <int A> __device__ __forceinline__ void out(int c, double v) const {
         if (LAYOUT == 0) p.out[A][(int64_t)c * N + i] = v; else p.out[A][i * CrystalGeneralOp::out_nc(A) + c] = v;
@@ -54,7 +57,7 @@ template <int LAYOUT> struct DirectAcc {
 #define MM_FIXUP_RANGE 4096
 template <int LAYOUT>
 __global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, int32_t* n_fail, const int64_t N,
-                                                                    const int64_t nranges) {
+                                                                    const int64_t nranges, const int* cnt, const int* idx) {
     __shared__ uint16_t list[MM_FIXUP_RANGE];
     __shared__ int count, next;
     __shared__ double Jsm[144 * MM_FIXUP_BS];                             // every thread's 12x12 Jacobian: column t of a [144][BS] image
@@ -63,7 +66,8 @@ __global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const Crysta
         if (threadIdx.x == 0) { count = 0; next = 0; }
         __syncthreads();
         const int64_t base = r * MM_FIXUP_RANGE;
-        const int n = (int)((N - base < MM_FIXUP_RANGE) ? (N - base) : MM_FIXUP_RANGE);
+        const int64_t Nc = cnt ? (int64_t)*cnt : N;                       // points in use (cnt: device-side count; N stays the stride)
+        const int n = (int)((Nc - base < MM_FIXUP_RANGE) ? (Nc - base) : MM_FIXUP_RANGE);
         for (int j = threadIdx.x; j < n; j += MM_FIXUP_BS)
             if (active[base + j] & MM_ACTIVE_NEEDS_GENERAL) list[atomicAdd(&count, 1)] = (uint16_t)j;
         __syncthreads();
@@ -80,14 +84,14 @@ __global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const Crysta
                 const int e = atomicAdd(&next, 1);
                 if (e < m) {
                     i = base + list[e];
-                    DirectAcc<LAYOUT> acc(p, N, i);
+                    DirectAcc<LAYOUT> acc(p, N, i, idx ? (int64_t)idx[i] : i);
                     crystal_gen_init(k, acc, S, Jsm + threadIdx.x, MM_FIXUP_BS);
                     has = true;
                 }
             }
             if (!__any_sync(0xffffffffu, has)) break;
             if (has && crystal_gen_pass(k, S)) {
-                DirectAcc<LAYOUT> acc(p, N, i);
+                DirectAcc<LAYOUT> acc(p, N, i, idx ? (int64_t)idx[i] : i);
                 const unsigned mask = crystal_gen_finalize(k, acc, S);
                 active[i] = (uint16_t)mask;
                 if (iters) iters[i] = (uint16_t)(S.iters > 65535 ? 65535 : S.iters);
@@ -144,7 +148,7 @@ static CrystalKnobs& crystal_knobs() {
 // through a stream-ordered side buffer xbuf[12][N] instead and nothing of the old state is overwritten before the fix-up decision.
 template <int LAYOUT> struct DirectAccRW : DirectAcc<LAYOUT> {
     const double* xbuf;
-    __device__ __forceinline__ DirectAccRW(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_, const double* xbuf_) : DirectAcc<LAYOUT>(p_, N_, i_), xbuf(xbuf_) {}
+    __device__ __forceinline__ DirectAccRW(const Ptrs<2, 3>& p_, int64_t N_, int64_t i_, int64_t ii_, const double* xbuf_) : DirectAcc<LAYOUT>(p_, N_, i_, ii_), xbuf(xbuf_) {}
     template <int A> __device__ __forceinline__ double rd_out(int c) const {
         if (xbuf) return xbuf[(int64_t)(c - 30) * this->N + this->i];
         return LAYOUT == 0 ? this->p.out[A][(int64_t)c * this->N + this->i] : this->p.out[A][this->i * CrystalGeneralOp::out_nc(A) + c];
@@ -161,11 +165,19 @@ template <int LAYOUT, class Scr> __device__ __forceinline__ void crystal_hand_ov
     }
 }
 
+// chunk of points per warp: large enough to refill many times, small enough for >= ~8 waves of warps on the chip (rw8 = 8 x resident warps)
+__host__ __device__ inline int crystal_chunk_for(int64_t n, int rw8) {
+    int64_t c = n / (rw8 > 0 ? rw8 : 1);
+    if (c > 1024) c = 1024;
+    if (c < 64) c = 64;
+    return (int)((c + 31) / 32 * 32);
+}
+
 // SPARSE (integer m only): the per-lane active-list pass crystal_iterate_sparse — the slip-system tables are copied into shared memory
 // ([component][system], behind the scratch columns) because every lane walks its own list of systems
 template <bool HASQ, bool INTPOW, int LAYOUT, int BS, bool SPARSE>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_MINBLOCKS)
-crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, const int chunk, const int thresh) {
+crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, int chunk, const int thresh, const int* cnt, const int* idx, const int rw8) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     double* tab = sm_scratch + MM_CRYSTAL_SCRATCH * BS;
@@ -176,8 +188,10 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t warp_id = (int64_t)blockIdx.x * (BS / 32) + (threadIdx.x >> 5);
+    const int64_t Nc = cnt ? (int64_t)*cnt : N;               // points in use (N stays the SoA stride)
+    if (cnt) chunk = crystal_chunk_for(Nc, rw8);              // batch: the chunk follows the device-side count (the grid covers N / 64 warps)
     int64_t next = warp_id * chunk;
-    const int64_t end = (next + chunk < N) ? (next + chunk) : N;
+    const int64_t end = (next + chunk < Nc) ? (next + chunk) : Nc;
     CrystalLane L;
     bool has_work = false, finished = false;
     int64_t my = 0;
@@ -187,8 +201,8 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
             if (!has_work) {
                 const int64_t cand = next + __popc(idle & ((1u << lane) - 1u));
                 if (cand < end) {
-                    my = cand;
-                    DirectAcc<LAYOUT> acc(p, N, my);
+                    my = cand;                                   // output slot; the inputs of a list entry stay where the point is
+                    DirectAcc<LAYOUT> acc(p, N, my, idx ? (int64_t)idx[cand] : cand);
                     crystal_init(k, acc, scr, L);
                     has_work = true; finished = false;
                 }
@@ -222,14 +236,16 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
 #endif
 template <int LAYOUT, int BS>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_PHASED_MINBLOCKS)
-crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, const int chunk, const int thresh) {
+crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, int chunk, const int thresh, const int* cnt, const int* idx, const int rw8) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t warp_id = (int64_t)blockIdx.x * (BS / 32) + (threadIdx.x >> 5);
+    const int64_t Nc = cnt ? (int64_t)*cnt : N;
+    if (cnt) chunk = crystal_chunk_for(Nc, rw8);
     int64_t next = warp_id * chunk;
-    const int64_t end = (next + chunk < N) ? (next + chunk) : N;
+    const int64_t end = (next + chunk < Nc) ? (next + chunk) : Nc;
     CrystalLane L;
     double sigt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     bool has_work = false, finished = false;
@@ -240,8 +256,8 @@ crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* ac
             if (!has_work) {
                 const int64_t cand = next + __popc(idle & ((1u << lane) - 1u));
                 if (cand < end) {
-                    my = cand;
-                    DirectAcc<LAYOUT> acc(p, N, my);
+                    my = cand;                                   // output slot; the inputs of a list entry stay where the point is
+                    DirectAcc<LAYOUT> acc(p, N, my, idx ? (int64_t)idx[cand] : cand);
                     crystal_init(k, acc, scr, L);
 #pragma unroll
                     for (int c = 0; c < 6; ++c) sigt[c] = scr(SIGT + c);
@@ -274,14 +290,14 @@ crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* ac
 #endif
 template <bool HASQ, bool INTPOW, int LAYOUT, int BS>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_FINISH_MINBLOCKS)
-crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, int32_t* n_fail, const double* xbuf, const int64_t N) {
+crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, int32_t* n_fail, const double* xbuf, const int64_t N, const int* cnt, const int* idx) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
-    if (i >= N) return;
+    if (i >= (cnt ? (int64_t)*cnt : N)) return;
     const unsigned status = active[i];
     if (status & MM_ACTIVE_NEEDS_GENERAL) return;                     // left to the fix-up pass
-    DirectAccRW<LAYOUT> acc(p, N, i, xbuf);
+    DirectAccRW<LAYOUT> acc(p, N, i, idx ? (int64_t)idx[i] : i, xbuf);
     bool fallback = false;
     unsigned mask = crystal_finish_from_x<HASQ, INTPOW>(k, acc, scr, (status & MM_ACTIVE_FAILED) == 0, &fallback);
     if (fallback) mask = MM_ACTIVE_NEEDS_GENERAL;
@@ -290,7 +306,7 @@ crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, in
 }
 
 template <bool HASQ, bool INTPOW, int LAYOUT>
-int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st) {
+int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st, const int* cnt, const int* idx) {
     constexpr int BS = MM_CRYSTAL_BS, FBS = MM_CRYSTAL_FINISH_BS;
     constexpr size_t smem = (size_t)(MM_CRYSTAL_SCRATCH * BS + MM_CRYSTAL_TAB) * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
     // "crystal_variant" (mm_set_tuning / MM_CRYSTAL_VARIANT): 0 or default = dense branch-free pass, 1 = sparse per-lane pass, 2 = phased pass.
@@ -315,16 +331,12 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
             carve[dev] = true;
         }
     }
-    // chunk of points per warp: large enough to refill many times, small enough for >= ~8 waves of warps on the chip
-    const int64_t resident_warps = (int64_t)sm_count() * MM_CRYSTAL_MINBLOCKS * (BS / 32);
-    int64_t chunk = N / (resident_warps * 8);
-    if (chunk > 1024) chunk = 1024;
-    if (chunk < 64) chunk = 64;
-    chunk = (chunk + 31) / 32 * 32;
+    const int rw8 = sm_count() * MM_CRYSTAL_MINBLOCKS * (BS / 32) * 8;
+    int64_t chunk = crystal_chunk_for(N, rw8);
     const CrystalKnobs& kn = crystal_knobs();
     const int thresh = kn.thresh > 0 ? kn.thresh : MM_CRYSTAL_THRESH;
     if (kn.chunk > 0) chunk = kn.chunk;
-    const int64_t warps = (N + chunk - 1) / chunk;
+    const int64_t warps = cnt ? (N + 63) / 64 : (N + chunk - 1) / chunk;      // device-side count: cover the smallest chunk, surplus warps exit at once
     const int64_t blocks = (warps + (BS / 32) - 1) / (BS / 32);
     if (INTPOW && !HASQ && crystal_knobs().variant == 2) {          // "crystal_variant" 2: the phased pass (integer m, q = 0) — measured slower, kept for A/B
         constexpr size_t psmem = (size_t)MM_CRYSTAL_SCRATCH_PHASED * BS * sizeof(double);
@@ -339,19 +351,19 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
         }
         CrystalNK nk;
         make_crystal_nk(nk, k);
-        crystal_newton_phased_kernel<LAYOUT, BS><<<(unsigned)blocks, BS, psmem, st>>>(nk, ptrs, active, iters, xbuf, N, (int)chunk, thresh);
-    } else if (sparse) crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, INTPOW><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh);
-    else        crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, false><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh);
+        crystal_newton_phased_kernel<LAYOUT, BS><<<(unsigned)blocks, BS, psmem, st>>>(nk, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8);
+    } else if (sparse) crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, INTPOW><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8);
+    else        crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, false><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8);
     int rc = check_launch("mm_crystal (Newton kernel)");
     if (rc) return rc;
-    crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS><<<(unsigned)((N + FBS - 1) / FBS), FBS, fsmem, st>>>(k, ptrs, active, n_fail, xbuf, N);
+    crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS><<<(unsigned)((N + FBS - 1) / FBS), FBS, fsmem, st>>>(k, ptrs, active, n_fail, xbuf, N, cnt, idx);
     return check_launch("mm_crystal (finish kernel)");
 }
 
 template <bool HASQ, int LAYOUT>
-int launch_crystal_by_exponent(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st) {
-    return k.m_int ? launch_crystal_two_kernel<HASQ, true, LAYOUT>(k, active, iters, n_fail, ptrs, xbuf, N, st)
-                   : launch_crystal_two_kernel<HASQ, false, LAYOUT>(k, active, iters, n_fail, ptrs, xbuf, N, st);
+int launch_crystal_by_exponent(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st, const int* cnt, const int* idx) {
+    return k.m_int ? launch_crystal_two_kernel<HASQ, true, LAYOUT>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx)
+                   : launch_crystal_two_kernel<HASQ, false, LAYOUT>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx);
 }
 
 int launch_crystal_general(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
@@ -362,21 +374,31 @@ int launch_crystal_general(const CrystalK& k, uint16_t* active, uint16_t* iters,
 }
 
 template <bool HASQ>
-int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, int layout, cudaStream_t st) {
+int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, int layout, cudaStream_t st,
+                              const int* cnt = nullptr, const int* idx = nullptr) {
     if (N == 0) return MM_OK;
     int rc;
-    if (layout == 0)      rc = launch_crystal_by_exponent<HASQ, 0>(k, active, iters, n_fail, ptrs, xbuf, N, st);
-    else if (layout == 1) rc = launch_crystal_by_exponent<HASQ, 1>(k, active, iters, n_fail, ptrs, xbuf, N, st);
+    if (layout == 0)      rc = launch_crystal_by_exponent<HASQ, 0>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx);
+    else if (layout == 1) rc = launch_crystal_by_exponent<HASQ, 1>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx);
     else return set_error(MM_ERR_ARG, "mm_crystal: unknown layout %d", layout);
     if (rc) return rc;
     const int64_t nranges = (N + MM_FIXUP_RANGE - 1) / MM_FIXUP_RANGE;
     const int per_sm = crystal_knobs().fixup_per_sm > 0 ? crystal_knobs().fixup_per_sm : 5;
     int64_t blocks = (int64_t)sm_count() * per_sm;
     if (blocks > nranges) blocks = nranges;
-    if (layout == 0) crystal_fixup_kernel<0><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges);
-    else             crystal_fixup_kernel<1><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges);
+    if (layout == 0) crystal_fixup_kernel<0><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges, cnt, idx);
+    else             crystal_fixup_kernel<1><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges, cnt, idx);
     return check_launch("mm_crystal (fix-up pass)");
 }
+
+// The structured two-kernel path on a BATCH of points of SoA arrays, for the dimension wrappers (mm_wrap.cu): idx[0 .. *cnt) lists the
+// points to update (device-side list and count).  The INPUTS (strain increment, old state) are read where the point is, in[a][c*N + idx[e]];
+// the OUTPUTS (σ, ∂σ∂ε, new state, active, iters) are packed by list position e.  N = stride of every array.  Requires k.h_struct.
+int crystal_structured_batch(const CrystalK& k, uint16_t* active, uint16_t* iters, const Ptrs<2, 3>& ptrs, int64_t N, const int* cnt, const int* idx, cudaStream_t st) {
+    return (k.b_h != 0.0) ? launch_crystal_structured<true>(k, active, iters, nullptr, ptrs, nullptr, N, 0, st, cnt, idx)
+                          : launch_crystal_structured<false>(k, active, iters, nullptr, ptrs, nullptr, N, 0, st, cnt, idx);
+}
+bool crystal_force_general() { return crystal_knobs().force_general != 0; }
 
 }  // namespace mm
 
@@ -397,12 +419,12 @@ extern "C" int mm_crystal(const MMCrystal* p, const double* deps, double dt, con
     // otherwise a stream-ordered temporary is used (the only allocation this library ever makes on a compute call)
     uint16_t* flags = active;
     if (!flags && N > 0) {
-        cudaError_t e = cudaMallocAsync((void**)&flags, (size_t)N * sizeof(uint16_t), st);
+        cudaError_t e = ws_alloc_async((void**)&flags, (size_t)N * sizeof(uint16_t), st);
         if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_crystal: cudaMallocAsync: %s", cudaGetErrorString(e));
     }
     double* xbuf = nullptr;
     if (state_in == state_out && N > 0) {        // in-place update: see DirectAccRW
-        cudaError_t e = cudaMallocAsync((void**)&xbuf, (size_t)N * 12 * sizeof(double), st);
+        cudaError_t e = ws_alloc_async((void**)&xbuf, (size_t)N * 12 * sizeof(double), st);
         if (e != cudaSuccess) { if (!active && flags) cudaFreeAsync(flags, st); return set_error(MM_ERR_CUDA, "mm_crystal: cudaMallocAsync: %s", cudaGetErrorString(e)); }
     }
     const int rc = (k.b_h != 0.0) ? launch_crystal_structured<true>(k, flags, iters, n_fail, ptrs, xbuf, N, layout, st)

@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(BS, 1) soa_bulk_kernel(const Op op, const Ptrs
 int set_error(int code, const char* fmt, ...);   // mm_api.cu
 int check_launch(const char* what);              // mm_api.cu
 int sm_count();                                  // mm_api.cu
+cudaError_t ws_alloc_async(void** ptr, size_t bytes, cudaStream_t st);   // mm_api.cu: stream-ordered workspace from the library's own pool
 
 // opt-in to > 48 KB of dynamic shared memory: a per-function, PER-DEVICE attribute, so it is remembered per device
 // (`done` is one static table per kernel instantiation) — a process that drives several GPUs stays correct

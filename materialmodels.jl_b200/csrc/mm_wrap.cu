@@ -168,14 +168,16 @@ int launch_wrapped_elastic(const MMLinearElastic* p, const double* eps, double* 
 // warp vote; the two sections that only some lanes need per trip (OUTER, FINAL) wait until `th_outer` / `th_final` lanes want them
 // or nothing else can advance.  Global accesses are per lane (a lane's point is wherever the queue was when it finished), but the lanes
 // of a warp stay within a window of a few dozen points, so L1/L2 see whole sectors; HBM traffic is the algorithmic figure.
-struct WrapKnobs { int variant, th_outer, th_final, chunk; };
+struct WrapKnobs { int variant, th_outer, th_final, chunk, crystal_variant, crystal_slab; };
 static WrapKnobs& wrap_knobs() {
     static WrapKnobs k = [] {
-        WrapKnobs v{-1, 0, 0, 0};
+        WrapKnobs v{-1, 0, 0, 0, -1, 0};
         if (const char* e = getenv("MM_WRAPPED_J2_VARIANT")) v.variant = atoi(e);
         if (const char* e = getenv("MM_WRAPPED_J2_TH_OUTER")) v.th_outer = atoi(e);
         if (const char* e = getenv("MM_WRAPPED_J2_TH_FINAL")) v.th_final = atoi(e);
         if (const char* e = getenv("MM_WRAPPED_J2_CHUNK")) v.chunk = atoi(e);
+        if (const char* e = getenv("MM_WRAPPED_CRYSTAL_VARIANT")) v.crystal_variant = atoi(e);
+        if (const char* e = getenv("MM_WRAPPED_CRYSTAL_SLAB")) v.crystal_slab = atoi(e);
         return v;
     }();
     return k;
@@ -186,7 +188,190 @@ int* wrap_tuning_slot(const char* name) {
     if (!strcmp(name, "wrapped_j2_th_outer")) return &k.th_outer;
     if (!strcmp(name, "wrapped_j2_th_final")) return &k.th_final;
     if (!strcmp(name, "wrapped_j2_chunk")) return &k.chunk;
+    if (!strcmp(name, "wrapped_crystal_variant")) return &k.crystal_variant;   // 0 = one thread per point, 1 (default) = rounds of the two-kernel crystal path
+    if (!strcmp(name, "wrapped_crystal_slab")) return &k.crystal_slab;         // points per workspace slab (default 2^21)
     return nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stress-restricted kinds around CrystalViscoPlastic as ROUNDS of the tuned two-kernel crystal path (mm_crystal.cu): every outer
+// iteration of wrappers.jl:60-77 is a full inner crystal solve (5-30 Newton passes, wildly different between neighbours) plus its
+// tangent — exactly what crystal_newton_kernel (lane-persistent) + crystal_finish_kernel do well and a one-thread-per-point wrapper
+// does badly (255 registers with spills, a warp runs its slowest lane's solve on every outer iteration: 5.3-6.3e7 updates/s).  Per round r:
+//   1. the crystal kernels on the BATCH of still-unconverged points: a device-side index list idx[r][0 .. cnt[r-1]); their inputs
+//      (3D strain, old state) are workspace arrays indexed by point — nothing is moved between rounds —, their outputs (σ, ∂σ∂ε, new
+//      state) are packed by list position (scattered 8-byte stores of 84 doubles per point cost 0.6 ms per round whatever the list length);
+//   2. wrapped_crystal_outer_kernel: out-of-plane stress norm; converged -> Schur-complement tangent + all outputs of the point;
+//      otherwise one outer Newton update of the point's 3D strain in place, and the point is appended to the next round's list
+//      (warp-aggregated atomic on cnt[r]; the order of a list does not matter — points are independent).
+// max_iter rounds are always enqueued (no host synchronisation: the call stays stream-ordered and graph-capturable); a round whose
+// list is empty costs four empty launches.  Same iterates as the one-thread-per-point path: same inner solves from the same 3D
+// strains, wrap_outer_step / wrap_schur_out are the expressions of wrapped_core.  Large batches go through the workspace in slabs.
+int crystal_structured_batch(const CrystalK& k, uint16_t* active, uint16_t* iters, const Ptrs<2, 3>& ptrs, int64_t N, const int* cnt, const int* idx, cudaStream_t st);   // mm_crystal.cu
+bool crystal_force_general();                                                                                                                                         // mm_crystal.cu
+
+struct WrapXtalWs {
+    double* eps;           // [6][cap]  by point: 3D strain increment (updated in place by the outer step)
+    double* state;         // [42][cap] by point: old state (copied once from the caller's array, which may be AoS / aliased with state_out)
+    double* sig;           // [6][cap]  by list position: σ of the round's inner solve
+    double* tan;           // [36][cap] by list position: ∂σ∂ε
+    double* stout;         // [42][cap] by list position: new state
+    int* idx[2];           // [cap]     the round's list of points (ping-pong)
+    uint16_t* act;         // [cap]     by list position: inner active mask / status
+    uint16_t* its;         // [cap]     by list position: inner Newton count
+    int* cnt;              // [max_iter + 1] list lengths per round
+};
+struct WrapXtalIO {        // the caller's arrays (either layout) and the slab
+    const double* eps_red; const double* state_in;
+    double* sig_red; double* tan_red; double* state_out;
+    uint16_t* active; uint16_t* iters; uint8_t* outer_iters; int32_t* n_fail;
+    int64_t N, i0;         // all points (= SoA stride of the caller's arrays), first point of the slab
+};
+template <int LAYOUT> __device__ __forceinline__ int64_t wx_at(int64_t N, int64_t i, int nc, int c) { return LAYOUT == 0 ? (int64_t)c * N + i : i * nc + c; }
+
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(256) wrapped_crystal_init_kernel(const WrapXtalWs w, const WrapXtalIO io, const int n, const int cap) {
+    constexpr int d = wrap_dim(KIND), nc = wrap_nc(KIND);
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j == 0) w.cnt[0] = n;
+    if (j >= n) return;
+    const int64_t i = io.i0 + j;
+    double e[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < nc; ++r) e[wrap_slot(d, r)] = io.eps_red[wx_at<LAYOUT>(io.N, i, nc, r)];       // increase_dim (wrappers.jl:24-27)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) w.eps[(int64_t)c * cap + j] = e[c];
+#pragma unroll
+    for (int c0 = 0; c0 < 42; c0 += 14) {
+        double v[14];
+#pragma unroll
+        for (int c = 0; c < 14; ++c) v[c] = io.state_in[wx_at<LAYOUT>(io.N, i, 42, c0 + c)];
+#pragma unroll
+        for (int c = 0; c < 14; ++c) w.state[(int64_t)(c0 + c) * cap + j] = v[c];
+    }
+    w.idx[0][j] = j;
+}
+
+template <int KIND, int LAYOUT> struct WrapXtalOutAcc {        // reduced outputs of one point into the caller's arrays
+    const WrapXtalIO& io; int64_t i;
+    template <int A> __device__ __forceinline__ void out(int c, double v) const {
+        constexpr int nc = wrap_nc(KIND);
+        if (A == 0) io.sig_red[wx_at<LAYOUT>(io.N, i, nc, c)] = v;
+        else if (A == 1) io.tan_red[wx_at<LAYOUT>(io.N, i, nc * nc, c)] = v;
+    }
+    template <int A> __device__ __forceinline__ bool has_out() const { return A == 1 ? io.tan_red != nullptr : true; }
+};
+struct WrapXtalTangent {
+    const double* tan; int64_t cap; int j;
+    __device__ __forceinline__ double operator()(int I, int J) const { return tan[(int64_t)(I + 6 * J) * cap + j]; }
+};
+
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(128) wrapped_crystal_outer_kernel(const WrapXtalWs w, const WrapXtalIO io, const double tol, const int it, const int max_iter, const int cap) {
+    constexpr int d = wrap_dim(KIND), nc = wrap_nc(KIND);
+    const int buf = (it - 1) & 1;
+    const int n = w.cnt[it - 1];
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    bool again = false;
+    int li = 0;
+    if (j < n) {
+        li = w.idx[buf][j];
+        const int64_t i = io.i0 + li;
+        const unsigned act = w.act[j];
+        int flag = (act & MM_ACTIVE_FAILED) ? 0x80 : 0, oit = it - 1;
+        bool done = false;
+        double sig[6], eps[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { sig[c] = w.sig[(int64_t)c * cap + j]; eps[c] = w.eps[(int64_t)c * cap + li]; }
+        const WrapXtalTangent T{w.tan, cap, j};
+        if (!(flag & 0x80)) {
+            const int r = wrap_outer_step<KIND>(T, sig, eps, tol);
+            if (r == 0) done = true;
+            else if (r == 2) flag |= 0x40;
+            else { oit = it; if (it >= max_iter) flag |= 0x40; else again = true; }      // "Could not find plane stress state" (wrappers.jl:78)
+        }
+        if (again) {
+#pragma unroll
+            for (int a = 0; a < wrap_nzero(KIND); ++a) { const int c = slot_of_mandel(wrap_zero(KIND, a)); w.eps[(int64_t)c * cap + li] = eps[c]; }
+        } else {                                                                         // this point is through: all its outputs
+            WrapXtalOutAcc<KIND, LAYOUT> acc{io, i};
+#pragma unroll
+            for (int r = 0; r < nc; ++r) acc.template out<0>(r, sig[wrap_slot(d, r)]);
+            if (done) { if (!wrap_schur_out<KIND>(T, acc)) flag |= 0x40; }
+            else if (io.tan_red) {
+#pragma unroll
+                for (int c = 0; c < nc * nc; ++c) acc.template out<1>(c, 0.0);
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < 42; c0 += 14) {
+                double v[14];
+#pragma unroll
+                for (int c = 0; c < 14; ++c) v[c] = w.stout[(int64_t)(c0 + c) * cap + j];
+#pragma unroll
+                for (int c = 0; c < 14; ++c) io.state_out[wx_at<LAYOUT>(io.N, i, 42, c0 + c)] = v[c];
+            }
+            unsigned mask = act;
+            if (flag & 0x40) mask |= MM_ACTIVE_WRAPPER_FAILED;
+            if (io.active) io.active[i] = (uint16_t)mask;
+            if (io.iters) io.iters[i] = w.its[j];
+            if (io.outer_iters) io.outer_iters[i] = (uint8_t)oit;
+            if ((flag & 0xC0) && io.n_fail) atomicAdd(io.n_fail, 1);
+        }
+    }
+    // append the points that go on to the next round's list (one atomic per warp)
+    const unsigned m = __ballot_sync(0xffffffffu, again);
+    if (m != 0u) {
+        const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&w.cnt[it], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (again) w.idx[buf ^ 1][base + __popc(m & ((1u << lane) - 1u))] = li;
+    }
+}
+
+template <int KIND, int LAYOUT>
+int launch_wrapped_crystal_rounds(const CrystalK& k, const WrapXtalIO& io_all, const MMNewtonOpts* wopts, int64_t N, cudaStream_t st) {
+    const double tol = wopts ? wopts->tol : 1e-8;
+    const int max_iter = wopts ? wopts->max_iter : 10;
+    if (max_iter < 1) return -100;                                   // nothing to iterate: the caller falls back to the one-thread-per-point kernel
+    int64_t slab = wrap_knobs().crystal_slab > 0 ? wrap_knobs().crystal_slab : (1 << 21);
+    if (slab > N) slab = N;
+    const int cap = (int)((slab + 1) & ~(int64_t)1);                 // even: every component column of the workspace stays 16-byte aligned
+    const size_t nd = (size_t)(6 + 42 + 6 + 36 + 42) * cap;
+    const size_t bytes = nd * sizeof(double) + (size_t)2 * cap * sizeof(int) + (size_t)2 * cap * sizeof(uint16_t) + (size_t)(max_iter + 2) * sizeof(int) + 64;
+    char* raw = nullptr;
+    cudaError_t e = ws_alloc_async((void**)&raw, bytes, st);
+    if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_wrapped_crystal: workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+    WrapXtalWs w;
+    double* dp = reinterpret_cast<double*>(raw);
+    w.eps = dp; dp += (size_t)6 * cap;
+    w.state = dp; dp += (size_t)42 * cap;
+    w.sig = dp; dp += (size_t)6 * cap;
+    w.tan = dp; dp += (size_t)36 * cap;
+    w.stout = dp; dp += (size_t)42 * cap;
+    int* ip = reinterpret_cast<int*>(dp);
+    w.idx[0] = ip; ip += cap;
+    w.idx[1] = ip; ip += cap;
+    w.cnt = ip; ip += max_iter + 1 + ((max_iter + 1) & 1);
+    w.act = reinterpret_cast<uint16_t*>(ip);
+    w.its = w.act + cap;
+    int rc = MM_OK;
+    for (int64_t i0 = 0; i0 < N && rc == MM_OK; i0 += slab) {
+        const int n = (int)((N - i0 < slab) ? (N - i0) : slab);
+        WrapXtalIO io = io_all;
+        io.i0 = i0;
+        cudaMemsetAsync(w.cnt, 0, (size_t)(max_iter + 1) * sizeof(int), st);
+        wrapped_crystal_init_kernel<KIND, LAYOUT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, io, n, cap);
+        if ((rc = check_launch("mm_wrapped_crystal (init)")) != MM_OK) break;
+        for (int it = 1; it <= max_iter; ++it) {
+            Ptrs<2, 3> ptrs; ptrs.in[0] = w.eps; ptrs.in[1] = w.state; ptrs.out[0] = w.sig; ptrs.out[1] = w.tan; ptrs.out[2] = w.stout;
+            if ((rc = crystal_structured_batch(k, w.act, w.its, ptrs, cap, w.cnt + (it - 1), w.idx[(it - 1) & 1], st)) != MM_OK) break;
+            wrapped_crystal_outer_kernel<KIND, LAYOUT><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(w, io, tol, it, max_iter, cap);
+            if ((rc = check_launch("mm_wrapped_crystal (outer step)")) != MM_OK) break;
+        }
+    }
+    cudaFreeAsync(raw, st);
+    return rc;
 }
 
 template <int KIND, int LAYOUT> struct WrapLaneAcc {
@@ -360,6 +545,18 @@ int mm_wrapped_crystal(int dim_kind, const MMCrystal* p, const double* deps_red,
     make_crystal_k(k, p->E, p->nu, p->tau_y, p->H_kin, p->alpha_inf, p->t_star, p->sigma_c, p->m, p->MS, p->H, dt, opts ? opts->tol : 1e-8,
                    opts ? opts->max_iter : 100);
     cudaStream_t st = (cudaStream_t)stream;
+    // stress-restricted kinds with the reference constructor's hardening matrix: rounds of the tuned two-kernel crystal path
+    if (dim_kind >= MM_DIM_UNIAXIAL_STRESS && dim_kind <= MM_DIM_SHELL_STRESS && N > 0 && (layout == 0 || layout == 1) && k.h_struct && !crystal_force_general() &&
+        wrap_knobs().crystal_variant != 0) {
+        const WrapXtalIO io{deps_red, state_in, sig_red, tan_red, state_out, active, iters, outer_iters, n_fail, N, 0};
+        int rc = -100;
+#define MM_WR(K) rc = (layout == 0) ? launch_wrapped_crystal_rounds<K, 0>(k, io, wrapper_opts, N, st) : launch_wrapped_crystal_rounds<K, 1>(k, io, wrapper_opts, N, st)
+        if (dim_kind == MM_DIM_UNIAXIAL_STRESS) MM_WR(WRAP_UNIAXIAL_STRESS);
+        else if (dim_kind == MM_DIM_PLANE_STRESS) MM_WR(WRAP_PLANE_STRESS);
+        else MM_WR(WRAP_SHELL_STRESS);
+#undef MM_WR
+        if (rc != -100) return rc;
+    }
 #define MM_WC(K) return launch_wrapped_crystal<K>(k, deps_red, state_in, sig_red, tan_red, state_out, active, iters, outer_iters, n_fail, wrapper_opts, N, layout, st)
     switch (dim_kind) {
         case MM_DIM_UNIAXIAL_STRAIN: MM_WC(WRAP_UNIAXIAL_STRAIN);

@@ -176,25 +176,15 @@ template <class Scr> MM_HD double j2lp_T(const PlasticK& k, const Scr& scr, int 
 }
 
 // ---- OUTER: convergence test on the out-of-plane stresses, otherwise one outer Newton update       wrappers.jl:60-63, :72-77
+template <class Scr> struct J2LaneTangent {
+    const PlasticK& k; const Scr& scr;
+    MM_HD double operator()(int I, int J) const { return j2lp_T(k, scr, I, J); }
+};
 template <int KIND, class Scr> MM_HD void j2lp_outer(const PlasticK& k, const Scr& scr, J2Lane& L, double tol, int max_iter) {
-    constexpr int nzero = wrap_nzero(KIND);
     L.oit = L.it - 1;
-    double sm[nzero], nrm2 = 0.0, Jzz[nzero * nzero];
-#pragma unroll
-    for (int a = 0; a < nzero; ++a) {
-        sm[a] = L.sg[slot_of_mandel(wrap_zero(KIND, a))] * mandel_f(wrap_zero(KIND, a));
-        nrm2 += sm[a] * sm[a];
-    }
-    if (sqrt(nrm2) < tol) { L.done = true; L.phase = J2P_FINAL; return; }
-#pragma unroll
-    for (int a = 0; a < nzero; ++a)
-#pragma unroll
-        for (int b = 0; b < nzero; ++b)
-            Jzz[a * nzero + b] = j2lp_T(k, scr, slot_of_mandel(wrap_zero(KIND, a)), slot_of_mandel(wrap_zero(KIND, b))) *
-                                 (mandel_f(wrap_zero(KIND, a)) * mandel_f(wrap_zero(KIND, b)));
-    if (!small_solve<nzero, 1>(Jzz, sm)) { L.flag |= 0x40; L.phase = J2P_FINAL; return; }
-#pragma unroll
-    for (int a = 0; a < nzero; ++a) L.eps[slot_of_mandel(wrap_zero(KIND, a))] -= sm[a] * (1.0 / mandel_f(wrap_zero(KIND, a)));
+    const int r = wrap_outer_step<KIND>(J2LaneTangent<Scr>{k, scr}, L.sg, L.eps, tol);
+    if (r == 0) { L.done = true; L.phase = J2P_FINAL; return; }
+    if (r == 2) { L.flag |= 0x40; L.phase = J2P_FINAL; return; }
     L.oit = L.it;
     ++L.it;
     if (L.it > max_iter) { L.flag |= 0x40; L.phase = J2P_FINAL; }         // "Could not find plane stress state" (wrappers.jl:78)
@@ -204,43 +194,13 @@ template <int KIND, class Scr> MM_HD void j2lp_outer(const PlasticK& k, const Sc
 // ---- FINAL: reduced stress, Schur-complement tangent, new state                                    wrappers.jl:63-70
 // acc: out<0> reduced stress, out<1> reduced tangent (optional), out<2> new state
 template <int KIND, class Acc, class Scr> MM_HD bool j2lp_final(const PlasticK& k, const Scr& scr, const J2Lane& L, Acc& acc) {
-    constexpr int d = wrap_dim(KIND), nc = wrap_nc(KIND), nzero = wrap_nzero(KIND), nnz = 6 - nzero;
+    constexpr int d = wrap_dim(KIND), nc = wrap_nc(KIND);
     const double c1 = 1.2247448713915890491;
 #pragma unroll
     for (int r = 0; r < nc; ++r) acc.template out<0>(r, L.sg[wrap_slot(d, r)]);
     bool ok = true;
-    if (L.done) {
-        double Jzz[nzero * nzero], X[nzero * nnz];                 // X = inv(M_zz) M_z,nz
-#pragma unroll
-        for (int a = 0; a < nzero; ++a) {
-#pragma unroll
-            for (int b = 0; b < nzero; ++b)
-                Jzz[a * nzero + b] = j2lp_T(k, scr, slot_of_mandel(wrap_zero(KIND, a)), slot_of_mandel(wrap_zero(KIND, b))) *
-                                     (mandel_f(wrap_zero(KIND, a)) * mandel_f(wrap_zero(KIND, b)));
-#pragma unroll
-            for (int b = 0; b < nnz; ++b)
-                X[a * nnz + b] = j2lp_T(k, scr, slot_of_mandel(wrap_zero(KIND, a)), slot_of_mandel(wrap_nz(KIND, b))) *
-                                 (mandel_f(wrap_zero(KIND, a)) * mandel_f(wrap_nz(KIND, b)));
-        }
-        ok = small_solve<nzero, nnz>(Jzz, X);                      // a singular block sets 0x40 (as wrapped_core does)
-        if (acc.template has_out<1>()) {
-            if (KIND == WRAP_SHELL_STRESS) {
-#pragma unroll
-                for (int c = 0; c < 36; ++c) if (c % 6 == 5 || c / 6 == 5) acc.template out<1>(c, 0.0);
-            }
-#pragma unroll
-            for (int a = 0; a < nnz; ++a)
-#pragma unroll
-                for (int b = 0; b < nnz; ++b) {
-                    const double fa = mandel_f(wrap_nz(KIND, a)), fb = mandel_f(wrap_nz(KIND, b));
-                    double v = j2lp_T(k, scr, slot_of_mandel(wrap_nz(KIND, a)), slot_of_mandel(wrap_nz(KIND, b))) * (fa * fb);
-#pragma unroll
-                    for (int p = 0; p < nzero; ++p)
-                        v -= j2lp_T(k, scr, slot_of_mandel(wrap_nz(KIND, a)), slot_of_mandel(wrap_zero(KIND, p))) * (fa * mandel_f(wrap_zero(KIND, p))) * X[p * nnz + b];
-                    acc.template out<1>(wrap_red_of_nz(KIND, a) + nc * wrap_red_of_nz(KIND, b), v * (1.0 / (fa * fb)));
-                }
-        }
-    } else if (acc.template has_out<1>()) {
+    if (L.done) ok = wrap_schur_out<KIND>(J2LaneTangent<Scr>{k, scr}, acc);
+    else if (acc.template has_out<1>()) {
 #pragma unroll
         for (int c = 0; c < nc * nc; ++c) acc.template out<1>(c, 0.0);
     }

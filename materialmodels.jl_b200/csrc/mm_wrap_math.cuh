@@ -184,6 +184,64 @@ MM_HD int wrapped_core(Inner&& inner, Acc& acc, IO& io, double tol, int max_iter
     *outer_iters = oit;
     return flag;
 }
+// ---- the two halves of one outer iteration as stand-alone steps (same expressions as wrapped_core above), for the kernels that do
+// not run the outer loop inside one thread: the J2 state machine (mm_wrap_lp.cuh) and the multi-launch crystal wrapper (mm_wrap.cu).
+// T(I, J) = tangent entry ∂σ_I/∂ε_J of the last 3D evaluation in raw storage slots.
+// wrap_outer_step: 0 = out-of-plane stresses below tol (converged), 1 = eps updated by one Newton step, 2 = singular zero-stress block
+template <int KIND, class TF> MM_HD int wrap_outer_step(const TF& T, const double* sig, double* eps, double tol) {
+    constexpr int nzero = wrap_nzero(KIND);
+    double sm[nzero], nrm2 = 0.0, Jzz[nzero * nzero];
+#pragma unroll
+    for (int a = 0; a < nzero; ++a) {
+        sm[a] = sig[slot_of_mandel(wrap_zero(KIND, a))] * mandel_f(wrap_zero(KIND, a));
+        nrm2 += sm[a] * sm[a];
+    }
+    if (sqrt(nrm2) < tol) return 0;                                                           // wrappers.jl:63
+#pragma unroll
+    for (int a = 0; a < nzero; ++a)
+#pragma unroll
+        for (int b = 0; b < nzero; ++b)
+            Jzz[a * nzero + b] = T(slot_of_mandel(wrap_zero(KIND, a)), slot_of_mandel(wrap_zero(KIND, b))) * (mandel_f(wrap_zero(KIND, a)) * mandel_f(wrap_zero(KIND, b)));
+    if (!small_solve<nzero, 1>(Jzz, sm)) return 2;
+#pragma unroll
+    for (int a = 0; a < nzero; ++a) eps[slot_of_mandel(wrap_zero(KIND, a))] -= sm[a] * (1.0 / mandel_f(wrap_zero(KIND, a)));   // :72-76
+    return 1;
+}
+// wrap_schur_out: reduced tangent = Schur complement of the Mandel 6x6 (wrappers.jl:63-70) into out<1> (if requested); false on a
+// singular zero-stress block (the solve runs either way: it decides the 0x40 flag)
+template <int KIND, class TF, class Acc> MM_HD bool wrap_schur_out(const TF& T, Acc& acc) {
+    constexpr int nc = wrap_nc(KIND), nzero = wrap_nzero(KIND), nnz = 6 - nzero;
+    double Jzz[nzero * nzero], X[nzero * nnz];                     // X = inv(M_zz) M_z,nz
+#pragma unroll
+    for (int a = 0; a < nzero; ++a) {
+#pragma unroll
+        for (int b = 0; b < nzero; ++b)
+            Jzz[a * nzero + b] = T(slot_of_mandel(wrap_zero(KIND, a)), slot_of_mandel(wrap_zero(KIND, b))) * (mandel_f(wrap_zero(KIND, a)) * mandel_f(wrap_zero(KIND, b)));
+#pragma unroll
+        for (int b = 0; b < nnz; ++b)
+            X[a * nnz + b] = T(slot_of_mandel(wrap_zero(KIND, a)), slot_of_mandel(wrap_nz(KIND, b))) * (mandel_f(wrap_zero(KIND, a)) * mandel_f(wrap_nz(KIND, b)));
+    }
+    const bool ok = small_solve<nzero, nnz>(Jzz, X);
+    if (acc.template has_out<1>()) {
+        if (KIND == WRAP_SHELL_STRESS) {
+#pragma unroll
+            for (int c = 0; c < 36; ++c) if (c % 6 == 5 || c / 6 == 5) acc.template out<1>(c, 0.0);   // zero 33-row/column
+        }
+#pragma unroll
+        for (int a = 0; a < nnz; ++a)
+#pragma unroll
+            for (int b = 0; b < nnz; ++b) {
+                const double fa = mandel_f(wrap_nz(KIND, a)), fb = mandel_f(wrap_nz(KIND, b));
+                double v = T(slot_of_mandel(wrap_nz(KIND, a)), slot_of_mandel(wrap_nz(KIND, b))) * (fa * fb);
+#pragma unroll
+                for (int p = 0; p < nzero; ++p)
+                    v -= T(slot_of_mandel(wrap_nz(KIND, a)), slot_of_mandel(wrap_zero(KIND, p))) * (fa * mandel_f(wrap_zero(KIND, p))) * X[p * nnz + b];
+                acc.template out<1>(wrap_red_of_nz(KIND, a) + nc * wrap_red_of_nz(KIND, b), v * (1.0 / (fa * fb)));   // constant folded
+            }
+    }
+    return ok;
+}
+
 template <int KIND, int NS, class Inner, class Acc>
 MM_HD int wrapped_point(Inner&& inner, Acc& acc, double tol, int max_iter, int* outer_iters, int* inner_iters) {
     RegIO<NS> io;

@@ -421,3 +421,77 @@ def test_gpu_wrapped_crystal(mm, cuda_lib, oracle, kind, lname, lay):
         st_ref_dev = g(data)
         assert H.rel_err(st_ref_dev[:, good], st_ref[:, good]).max() < H.RTOL
         st_ref = st_ref_dev                                                    # keep both sides on the same state bits
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lname,lay", [("soa", 0), ("aos", 1)])
+@pytest.mark.parametrize("kind", [3, 4, 5])
+def test_gpu_wrapped_crystal_rounds_equal_thread_per_point(mm, cuda_lib, kind, lname, lay):
+    """Stress-restricted kinds around the crystal: the rounds of the two-kernel crystal path (default) against the one-thread-per-point
+    kernel (mm_set_tuning("wrapped_crystal_variant", 0)) — masks, inner and outer counts identical on every regular point, values within
+    1e-12; also through several workspace slabs, without a tangent, and with the state updated in place through the C ABI."""
+    import torch
+    from test_gpu_parity import make_crystal
+    dim = {3: mm.UniaxialStress(), 4: mm.PlaneStress(), 5: mm.ShellStress()}[kind]
+    m = make_crystal(mm)
+    N = 5003
+    nc = NC[kind]
+    T = (lambda a: a) if lay == 0 else (lambda a: np.ascontiguousarray(a.T))
+    g = lambda x: x.cpu().numpy() if lay == 0 else np.ascontiguousarray(x.cpu().numpy().T)
+
+    def run(variant, slab=0, tangent=True, inplace=False):
+        olds = [(b"wrapped_crystal_variant", cuda_lib.mm_set_tuning(b"wrapped_crystal_variant", variant)),
+                (b"wrapped_crystal_slab", cuda_lib.mm_set_tuning(b"wrapped_crystal_slab", slab))]
+        try:
+            st = mm.initial_material_state(m, N, layout=lname)
+            outs = []
+            for step in range(2):
+                e = torch.from_numpy(T(sy.host_uniform(N, nc, 270 + 10 * kind + step, -XTAL_AMPL[kind], XTAL_AMPL[kind]))).cuda()
+                if inplace:
+                    P = lambda t_: C.c_void_p(t_.data_ptr())
+                    shp = (lambda n_: (n_, N)) if lay == 0 else (lambda n_: (N, n_))
+                    s = torch.empty(shp(nc), dtype=torch.float64, device="cuda")
+                    t = torch.empty(shp(nc * nc), dtype=torch.float64, device="cuda")
+                    ac, it_ = torch.empty(N, dtype=torch.int16, device="cuda"), torch.empty(N, dtype=torch.int16, device="cuda")
+                    oi, nf = torch.empty(N, dtype=torch.uint8, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
+                    data = st.data.clone()
+                    rc = cuda_lib.mm_wrapped_crystal(kind, C.byref(m._c), P(e), C.c_double(1.0), P(data), P(s), P(t), P(data), P(ac), P(it_), P(oi), P(nf), None, None, N, lay, None)
+                    assert rc == 0
+                    torch.cuda.synchronize()
+                    outs.append((g(s), g(t), g(data), ac.cpu().numpy().view(np.uint16), it_.cpu().numpy().view(np.uint16), oi.cpu().numpy()))
+                    st = mm.CrystalViscoPlasticState(data, lname)
+                    continue
+                s, t, new = mm.material_response(dim, m, e, st, 1.0, tangent=tangent, options={"defer_check": True})
+                outs.append((g(s), None if t is None else g(t), g(new.data), new.flags.cpu().numpy().view(np.uint16), new.iters.cpu().numpy().view(np.uint16),
+                             new.outer_iters.cpu().numpy()))
+                # both variants continue from the SAME state bits: the thread-per-point result is the one carried over
+                st = new
+            return outs
+        finally:
+            for name, v in olds:
+                cuda_lib.mm_set_tuning(name, v)
+
+    def same(a, b, first_step_only=False):
+        for k_, ((s1, t1, d1, f1, i1, o1), (s2, t2, d2, f2, i2, o2)) in enumerate(zip(a, b)):
+            if first_step_only and k_ > 0:
+                break
+            ok = ((f1 & 0xA000) == 0) & (i1 < H.CHAOTIC_ITERS) & ((f2 & 0xA000) == 0) & (i2 < H.CHAOTIC_ITERS)
+            assert ok.mean() > 0.97
+            assert np.array_equal(f1[ok], f2[ok]) and np.array_equal(i1[ok], i2[ok]) and np.array_equal(o1[ok], o2[ok])
+            assert sig_err(s1[:, ok], s2[:, ok]) < H.RTOL and H.rel_err(d1[:, ok], d2[:, ok]).max() < H.RTOL
+            if t1 is not None:
+                assert H.rel_err(t1[:, ok], t2[:, ok]).max() < max(TAN_TOL[kind], 1e-10)
+
+    ref = run(0)
+    assert ((ref[0][3] & 0xFFF) != 0).mean() > 0.2
+    new = run(1)
+    same(ref, new, first_step_only=True)          # step 2 starts from each variant's own step-1 state (equal to 1e-12, not bitwise)
+    sl = run(1, slab=1000)
+    for x, y in zip(new, sl):                      # slabs only change where the batch lives: identical bits
+        assert all(np.array_equal(p_, q_) for p_, q_ in zip(x, y) if p_ is not None)
+    nt = run(1, tangent=False)
+    for x, y in zip(new, nt):
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[2], y[2]) and np.array_equal(x[3], y[3])
+    ip = run(1, inplace=True)
+    for x, y in zip(new, ip):
+        assert all(np.array_equal(p_, q_) for p_, q_ in zip(x, y))
