@@ -96,7 +96,9 @@ const char* mm_last_error(void);
 int mm_device_count(void);
 
 /* test / tuning hook: A-B switches of the crystal kernels ("crystal_force_general", "crystal_thresh", "crystal_chunk",
- * "crystal_fixup_per_sm", "crystal_variant"); initial values come from the MM_CRYSTAL_* environment variables, read once per process.
+ * "crystal_fixup_per_sm", "crystal_variant") and of the dimension wrappers ("wrapped_j2_variant" 0 = one thread per point, 1 = state
+ * machine, 2 = pass-granular trips; "wrapped_j2_th_outer", "wrapped_j2_th_final", "wrapped_j2_chunk"; "wrapped_crystal_variant" 0 = one
+ * thread per point, 1 = rounds; "wrapped_crystal_slab"); initial values come from the MM_CRYSTAL_* / MM_WRAPPED_* environment variables, read once per process.
  * Returns the previous value, -1 for an unknown name.  Results never depend on these (tests/test_gpu_parity.py runs both paths). */
 int mm_set_tuning(const char* name, int value);
 
@@ -190,7 +192,9 @@ int mm_wrapped_plastic(int dim_kind, const MMPlastic* p, const double* eps_red, 
                        double* state_out, uint8_t* flags, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* opts,
                        const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
 /* ... and around CrystalViscoPlastic{12}: deps_red is the reduced strain INCREMENT, state 42 per point; `active` as mm_crystal plus
- * bit 13 (0x2000) = the outer Newton did not converge; inner solve = the general pivoted path (functional, not tuned) */
+ * bit 13 (0x2000) = the outer Newton did not converge.  The stress-restricted kinds run as rounds of mm_crystal's kernels on the
+ * still-unconverged points (stream-ordered, no host synchronisation; workspace of ~1.1 KB per point, at most 2^21 points at a time,
+ * from the library's own stream-ordered memory pool).  state_out may alias state_in. */
 int mm_wrapped_crystal(int dim_kind, const MMCrystal* p, const double* deps_red, double dt, const double* state_in, double* sig_red,
                        double* tan_red, double* state_out, uint16_t* active, uint16_t* iters, uint8_t* outer_iters, int32_t* n_fail,
                        const MMNewtonOpts* opts, const MMNewtonOpts* wrapper_opts, int64_t N, int layout, void* stream);
