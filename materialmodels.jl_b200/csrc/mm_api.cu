@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include "../../include/mmb200.h"
 
 namespace mm {
@@ -47,6 +48,8 @@ cudaError_t ws_alloc_async(void** ptr, size_t bytes, cudaStream_t st) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaMallocAsync(ptr, bytes, st);
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);                    // pool creation only; the allocation itself is a stream-ordered call
     if (!pools[dev]) {
         cudaMemPoolProps props = {};
         props.allocType = cudaMemAllocationTypePinned;

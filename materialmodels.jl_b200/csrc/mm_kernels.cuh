@@ -237,13 +237,13 @@ aos_bulk_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// SoA arrays through the copy engine (opt-in per Op: SoaTiled<Op>): a tile of BS points of ONE component is a contiguous run of BS
-// doubles, so a tile is NIN_comps + NOUT_comps bulk copies into / out of a component-major shared-memory image ([comp][point]:
-// conflict-free for thread <-> point).  For the light ops with many output streams (XuNeedleman: 3 in, 12 out) the direct kernel above
-// keeps 15 DRAM streams per warp open and is bimodal in a sustained run: 1.85 ms per 1e8 points at its best (1.00 of the HBM peak) but a
-// median of 2.19-2.22 ms on every box (profiles/r02_xu_soa_tiled_sweeps.log; block size, register cap and residency cap do not matter),
-// while the tiled AoS kernel holds 0.97.  This kernel is the SoA counterpart: 256-point tiles, the copies dealt over 8 warps: 1.95-1.97 ms,
-// min = median, on the box where the direct kernel's median was 2.21 ms.  Same double-buffered input scheme as aos_bulk_kernel.
+// SoA arrays through the copy engine (compiled per Op through SoaTiled<Op>, selected per call): a tile of BS points of ONE component is a
+// contiguous run of BS doubles, so a tile is NIN_comps + NOUT_comps bulk copies into / out of a component-major shared-memory image
+// ([comp][point]: conflict-free for thread <-> point).  Built for the light ops with many output streams (XuNeedleman: 3 in, 12 out), whose
+// direct kernel is bimodal in a sustained run — 1.85 ms per 1e8 points (1.00 of the HBM peak) or 2.2 ms.  Measured on five boxes
+// (profiles/r02_xu_soa_tiled_sweeps.log): this kernel is bimodal as well (1.95-2.09 or 2.35-2.5 ms), i.e. no better in either
+// mode, so the direct kernel stays the default and this one is an A/B option (mm_set_tuning("xu_soa_tiled", 1)).  Same double-buffered input
+// scheme as aos_bulk_kernel.
 #ifndef MM_SOA_TILE_ISSUERS
 #define MM_SOA_TILE_ISSUERS 8      // warps whose lane 0 issues the copies of a tile (component runs dealt round-robin)
 #endif
@@ -360,10 +360,10 @@ template <class K> int ensure_smem(SmemOptIn& st, K kernel, size_t bytes, const 
 }
 
 template <class Op, int BS_SOA, int BS_AOS = BS_SOA>
-int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int layout, cudaStream_t stream, const char* what) {
+int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int layout, cudaStream_t stream, const char* what, bool soa_tiled = false) {
     if (N == 0) return 0;
     if constexpr (SoaTiled<Op>::value) {
-      if (layout == 0) {
+      if (layout == 0 && soa_tiled) {
         // copy-engine tiles for the ops that opt in; a run of one component must start 16-byte aligned for every component and tile:
         // even N and 16-byte aligned bases — otherwise (and for the ragged last tile) element-wise copies inside the same kernel
         constexpr int TBS = SoaTiled<Op>::BS;

@@ -1,6 +1,7 @@
 // Device-pointer entry points of the streaming (HBM-bound) models: LinearElastic, Plastic (J2),
 // NeoHook / Yeoh / StVenant, XuNeedleman, plus the synthetic-input generator.
 #include <cuda_runtime.h>
+#include <string.h>
 #include "../../include/mmb200.h"
 #include "mm_kernels.cuh"
 
@@ -207,6 +208,13 @@ int launch_plastic_parts(const MMPlastic* p, const MMNewtonOpts* opts, const dou
     return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, st, "mm_plastic_compact");
 }
 
+// run-time A/B switches of this translation unit (mm_set_tuning): "xu_soa_tiled" 0 (default) = direct SoA kernel, 1 = copy-engine tiles
+int* ops_tuning_slot(const char* name) {
+    static int xu_soa_tiled = [] { const char* e = getenv("MM_XU_SOA_TILED_RT"); return (e && e[0] == '1') ? 1 : 0; }();
+    if (!strcmp(name, "xu_soa_tiled")) return &xu_soa_tiled;
+    return nullptr;
+}
+
 }  // namespace mm
 
 using namespace mm;
@@ -255,8 +263,9 @@ int mm_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, doubl
     if (!p || N < 0 || (N > 0 && (!jump || !T))) return set_error(MM_ERR_ARG, "mm_xu_needleman: bad argument");
     const XuK k = make_xu_k(p->Phi_n, p->Phi_t, p->delta_n, p->delta_t, p->Delta_n_star);
     Ptrs<1, 2> ptrs; ptrs.in[0] = jump; ptrs.out[0] = T; ptrs.out[1] = dTdD;
-    if (dim == 3) { XuOp<3> op; op.k = k; return launch_points<XuOp<3>, MM_XU_SOA_BS, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
-    if (dim == 2) { XuOp<2> op; op.k = k; return launch_points<XuOp<2>, MM_XU_SOA_BS, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman"); }
+    const bool tiled = *ops_tuning_slot("xu_soa_tiled") != 0;
+    if (dim == 3) { XuOp<3> op; op.k = k; return launch_points<XuOp<3>, MM_XU_SOA_BS, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman", tiled); }
+    if (dim == 2) { XuOp<2> op; op.k = k; return launch_points<XuOp<2>, MM_XU_SOA_BS, MM_SMALL_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_xu_needleman", tiled); }
     return set_error(MM_ERR_ARG, "mm_xu_needleman: dim must be 2 or 3 (got %d)", dim);
 }
 

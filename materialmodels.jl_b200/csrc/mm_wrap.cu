@@ -333,7 +333,8 @@ template <int KIND, int LAYOUT>
 int launch_wrapped_crystal_rounds(const CrystalK& k, const WrapXtalIO& io_all, const MMNewtonOpts* wopts, int64_t N, cudaStream_t st) {
     const double tol = wopts ? wopts->tol : 1e-8;
     const int max_iter = wopts ? wopts->max_iter : 10;
-    if (max_iter < 1) return -100;                                   // nothing to iterate: the caller falls back to the one-thread-per-point kernel
+    if (max_iter < 1 || max_iter > 64) return -100;                  // nothing to iterate / an unusual cap (4 launches per round are enqueued whatever
+                                                                     // converges): the caller falls back to the one-thread-per-point kernel
     int64_t slab = wrap_knobs().crystal_slab > 0 ? wrap_knobs().crystal_slab : (1 << 21);
     if (slab > N) slab = N;
     const int cap = (int)((slab + 1) & ~(int64_t)1);                 // even: every component column of the workspace stays 16-byte aligned
