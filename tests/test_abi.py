@@ -171,3 +171,19 @@ def test_header_structs_match_the_ctypes_mirror():
         cs = getattr(abi, name)
         alias = {"lambda": "lambda_"}
         assert [alias.get(n, n) for n in names] == [f[0] for f in cs._fields_], name
+
+
+def test_tuning_switches_are_known_by_name():
+    """mm_set_tuning (host-side A/B switches; results never depend on them): every documented name is accepted and restored, an unknown
+    name is refused with -1 — no GPU needed."""
+    names = [b"crystal_force_general", b"crystal_thresh", b"crystal_chunk", b"crystal_fixup_per_sm", b"crystal_variant",
+             b"wrapped_j2_variant", b"wrapped_j2_th_outer", b"wrapped_j2_th_final", b"wrapped_j2_chunk",
+             b"wrapped_crystal_variant", b"wrapped_crystal_slab", b"xu_soa_tiled"]
+    lib = L.load()
+    for n in names:
+        old = lib.mm_set_tuning(n, 7)
+        assert lib.mm_set_tuning(n, old) == 7, n
+    assert lib.mm_set_tuning(b"no_such_switch", 1) == -1
+    hdr = open(os.path.join(H.ROOT, "include", "mmb200.h")).read()
+    for n in names:
+        assert n.decode() in hdr, "undocumented tuning switch %s" % n.decode()
