@@ -98,7 +98,8 @@ int mm_device_count(void);
 /* test / tuning hook: A-B switches of the crystal kernels ("crystal_force_general", "crystal_thresh", "crystal_chunk",
  * "crystal_fixup_per_sm", "crystal_variant") and of the dimension wrappers ("wrapped_j2_variant" 0 = one thread per point, 1 = state
  * machine, 2 = pass-granular trips; "wrapped_j2_th_outer", "wrapped_j2_th_final", "wrapped_j2_chunk"; "wrapped_crystal_variant" 0 = one
- * thread per point, 1 = rounds; "wrapped_crystal_slab"); initial values come from the MM_CRYSTAL_* / MM_WRAPPED_* environment variables, read once per process.
+ * thread per point, 1 = rounds; "wrapped_crystal_slab") and of the XuNeedleman SoA path ("xu_soa_tiled" 0 = direct kernel, 1 = copy-engine
+ * tiles); initial values come from the MM_CRYSTAL_* / MM_WRAPPED_* environment variables, read once per process.
  * Returns the previous value, -1 for an unknown name.  Results never depend on these (tests/test_gpu_parity.py runs both paths). */
 int mm_set_tuning(const char* name, int value);
 
