@@ -444,12 +444,27 @@ def run_e2e(args, mm, m, epsB, stA, stB, N, world, dev, sharding):
         return variants[name]
 
     head = compact_variant("factored")                  # the headline form first
-    # dense (round-1 headline, unchanged code path: mmh_plastic)
+    # dense: the default call (material_response(m, numpy eps, state) -> mmh_plastic, dense tangent and state in host memory).  Since round 2
+    # the library sends the factored rows over the link and rebuilds the dense tangent with the host cores while the next chunks are in
+    # flight ("dense"); "dense_plain_transfer" is the round-1 path (the 36-entry tangent of every point over PCIe), same bits either way
+    import materialmodels_jl_b200._lib as _L
     h_out = {"stress": h_sig, "tangent": mm.PinnedArray((36, Ne)).array, "state": mm.PinnedArray((14, Ne)).array, "flags": h_fl, "iters": h_it}
-    dt, (sg, _, _) = timed(lambda: mm.material_response(m, h_eps, mm.PlasticState(h_st), out=h_out), name="dense")
-    launches["n"] += chunks * (steps + 1)
-    variants["dense"] = {"value": world * Ne * steps / dt, "h2d_bytes_per_step": 160 * Ne, "d2h_bytes_per_step": 451 * Ne + 4,
-                         "matches_device_path": bool(np.array_equal(sg, ref_sig)), "best_step_value": world * Ne / min(step_times["dense"])}
+    for name, via in (("dense", 1), ("dense_plain_transfer", 0)):
+        prev = _L.load().mm_set_tuning(b"mmh_plastic_via_factored", via)
+        try:
+            dt, (sg, tg, _) = timed(lambda: mm.material_response(m, h_eps, mm.PlasticState(h_st), out=h_out), name=name)
+        finally:
+            _L.load().mm_set_tuning(b"mmh_plastic_via_factored", prev)
+        launches["n"] += (4 if via else 1) * chunks * (steps + 1)
+        nyield = int((h_fl & 1).sum())
+        variants[name] = {"value": world * Ne * steps / dt, "h2d_bytes_per_step": 160 * Ne,
+                          "d2h_bytes_per_step": (164 * Ne + 104 * nyield + 8 * chunks) if via else (451 * Ne + 4),
+                          "matches_device_path": bool(np.array_equal(sg, ref_sig)), "best_step_value": world * Ne / min(step_times[name])}
+        if via:
+            dense_tan_ref = np.array(tg, copy=True)
+        else:
+            variants[name]["same_bits_as_dense"] = bool(np.array_equal(tg, dense_tan_ref))
+            del dense_tan_ref
     h_out = None
     compact_variant("compact")
     compact_variant("factored", resident=True)

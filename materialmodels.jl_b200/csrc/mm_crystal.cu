@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const Crysta
 
 int* wrap_tuning_slot(const char* name);      // mm_wrap.cu
 int* ops_tuning_slot(const char* name);       // mm_ops.cu
+int* host_tuning_slot(const char* name);      // mm_host.cu
 // tuning / A-B switches: initialised from the environment ONCE per process (tools/README.md), changed afterwards only through
 // mm_set_tuning() — never a getenv on the per-call path
 struct CrystalKnobs { int thresh, chunk, fixup_per_sm, force_general, variant; };
@@ -447,6 +448,7 @@ extern "C" int mm_set_tuning(const char* name, int value) {
     else if (!strcmp(name, "crystal_variant")) slot = &k.variant;
     if (!slot) slot = mm::wrap_tuning_slot(name);              // "wrapped_j2_*" knobs live next to their kernel (mm_wrap.cu)
     if (!slot) slot = mm::ops_tuning_slot(name);               // "xu_soa_tiled" (mm_ops.cu)
+    if (!slot) slot = mm::host_tuning_slot(name);              // "mmh_plastic_via_factored" (mm_host.cu)
     if (!slot) return -1;
     const int old = *slot;
     *slot = value;

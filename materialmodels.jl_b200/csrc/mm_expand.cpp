@@ -10,6 +10,10 @@
 #include <string.h>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define MM_NT_STORES 1
+#endif
 #include "../../include/mmb200.h"
 #include "mm_math.cuh"
 
@@ -34,11 +38,57 @@ struct ExpandJob {
     double* tan;
     double* state_out;
     int64_t N;
+    int64_t flags_base;   // global index of flags[0] (0 for a whole-array job; i0 for a chunk whose flags sit in a staging buffer)
     double lam, G;
     double Ee[36];
 };
 
 constexpr int BLK = 256;
+
+// The expanded arrays are written once and not read here: non-temporal 8-byte stores (MOVNTI; any 8-byte alignment, full lines are
+// combined in the write-combining buffers because every stream below is written in runs of >= 2 KB) skip the read-for-ownership of a
+// normal store — the scatter is bound by host memory traffic, which this halves (tools/expand_bench.py).
+static inline void put(double* dst, double v) {
+#ifdef MM_NT_STORES
+    long long b;
+    memcpy(&b, &v, 8);
+    _mm_stream_si64(reinterpret_cast<long long*>(dst), b);
+#else
+    *dst = v;
+#endif
+}
+static inline void put_n(double* dst, const double* src, int n) { for (int i = 0; i < n; ++i) put(dst + i, src[i]); }
+static inline void store_fence() {
+#ifdef MM_NT_STORES
+    _mm_sfence();
+#endif
+}
+
+// one SoA component run of the factored tangent for a block of points: dst[t] = fma(u[t], n[t], fma(-g[t], idev, iso)) — the device
+// kernels' expression (plastic_tangent_entry_lg), so the bits are theirs; elastic points carry g = u = n = 0 and get Eᵉ exactly.
+static void tangent_run_scalar(double* dst, const double* u, const double* n, const double* g, double idev, double iso, int nb) {
+    for (int t = 0; t < nb; ++t) put(dst + t, fma(u[t], n[t], fma(-g[t], idev, iso)));
+}
+#ifdef MM_NT_STORES
+__attribute__((target("avx2,fma")))
+static void tangent_run_avx2(double* dst, const double* u, const double* n, const double* g, double idev, double iso, int nb) {
+    int t = 0;
+    for (; t < nb && (reinterpret_cast<uintptr_t>(dst + t) & 31u); ++t) put(dst + t, fma(u[t], n[t], fma(-g[t], idev, iso)));
+    const __m256d vid = _mm256_set1_pd(idev), vis = _mm256_set1_pd(iso);
+    for (; t + 4 <= nb; t += 4) {
+        const __m256d b = _mm256_fnmadd_pd(_mm256_loadu_pd(g + t), vid, vis);                       // fma(-g, idev, iso)
+        _mm256_stream_pd(dst + t, _mm256_fmadd_pd(_mm256_loadu_pd(u + t), _mm256_loadu_pd(n + t), b));
+    }
+    for (; t < nb; ++t) put(dst + t, fma(u[t], n[t], fma(-g[t], idev, iso)));
+}
+#endif
+typedef void (*tangent_run_fn)(double*, const double*, const double*, const double*, double, double, int);
+static tangent_run_fn pick_tangent_run() {
+#ifdef MM_NT_STORES
+    if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma")) return tangent_run_avx2;
+#endif
+    return tangent_run_scalar;
+}
 
 // points [lo, hi), first row index `row0`
 #if defined(__x86_64__) && defined(__GNUC__)
@@ -55,8 +105,21 @@ void expand_range(const ExpandJob& j, int64_t lo, int64_t hi, int64_t row0) {
     int64_t row = row0;
     for (int64_t b0 = lo; b0 < hi; b0 += BLK) {
         const int nb = (int)((hi - b0 < BLK) ? (hi - b0) : BLK);
-        for (int t = 0; t < nb; ++t) ridx[t] = (j.flags[b0 + t] & MM_FLAG_PLASTIC) ? row++ : -1;
-        if (j.tan) {
+        for (int t = 0; t < nb; ++t) ridx[t] = (j.flags[b0 + t - j.flags_base] & MM_FLAG_PLASTIC) ? row++ : -1;
+        if (j.tan && soa && factored) {
+            // gather the block's factored rows into component-major runs (zeros for the elastic points), then 36 straight vector loops
+            alignas(64) double gb[BLK], ub[6][BLK], nbuf[6][BLK];
+            for (int t = 0; t < nb; ++t) {
+                if (ridx[t] < 0) { gb[t] = 0.0; for (int c = 0; c < 6; ++c) { ub[c][t] = 0.0; nbuf[c][t] = 0.0; } continue; }
+                const double* r = j.rows + ridx[t] * W;
+                gb[t] = r[0];
+                for (int c = 0; c < 6; ++c) { ub[c][t] = r[1 + c]; nbuf[c][t] = r[7 + c]; }
+            }
+            static const tangent_run_fn run = pick_tangent_run();
+            for (int J = 0; J < 6; ++J)
+                for (int I = 0; I < 6; ++I)
+                    run(j.tan + (int64_t)(I + 6 * J) * N + b0, ub[I], nbuf[J], gb, idev_entry(I, J), iso_entry(I, J, j.lam, j.G), nb);
+        } else if (j.tan) {
             if (soa) {
                 for (int J = 0; J < 6; ++J)
                     for (int I = 0; I < 6; ++I) {
@@ -65,24 +128,24 @@ void expand_range(const ExpandJob& j, int64_t lo, int64_t hi, int64_t row0) {
                         const double e = j.Ee[c];
                         if (factored) {
                             for (int t = 0; t < nb; ++t) {
-                                if (ridx[t] < 0) { dst[t] = e; continue; }
+                                if (ridx[t] < 0) { put(dst + t, e); continue; }
                                 const double* r = j.rows + ridx[t] * W;
-                                dst[t] = plastic_tangent_entry_lg(j.lam, j.G, r[0], r + 1, r + 7, I, J);
+                                put(dst + t, plastic_tangent_entry_lg(j.lam, j.G, r[0], r + 1, r + 7, I, J));
                             }
                         } else {
-                            for (int t = 0; t < nb; ++t) dst[t] = ridx[t] < 0 ? e : j.rows[ridx[t] * W + c];
+                            for (int t = 0; t < nb; ++t) put(dst + t, ridx[t] < 0 ? e : j.rows[ridx[t] * W + c]);
                         }
                     }
             } else {
                 for (int t = 0; t < nb; ++t) {
                     double* dst = j.tan + (b0 + t) * 36;
-                    if (ridx[t] < 0) { memcpy(dst, j.Ee, 36 * sizeof(double)); continue; }
+                    if (ridx[t] < 0) { put_n(dst, j.Ee, 36); continue; }
                     const double* r = j.rows + ridx[t] * W;
                     if (factored) {
                         for (int J = 0; J < 6; ++J)
-                            for (int I = 0; I < 6; ++I) dst[I + 6 * J] = plastic_tangent_entry_lg(j.lam, j.G, r[0], r + 1, r + 7, I, J);
+                            for (int I = 0; I < 6; ++I) put(dst + I + 6 * J, plastic_tangent_entry_lg(j.lam, j.G, r[0], r + 1, r + 7, I, J));
                     } else {
-                        memcpy(dst, r, 36 * sizeof(double));
+                        put_n(dst, r, 36);
                     }
                 }
             }
@@ -93,21 +156,51 @@ void expand_range(const ExpandJob& j, int64_t lo, int64_t hi, int64_t row0) {
                     double* dst = j.state_out + (int64_t)c * N + b0;
                     const double* src = j.state_in + (int64_t)c * N + b0;
                     for (int t = 0; t < nb; ++t) {
-                        if (ridx[t] >= 0) dst[t] = j.rows[ridx[t] * W + TW + c];
-                        else if (!inplace) dst[t] = src[t];
+                        if (inplace) { if (ridx[t] >= 0) dst[t] = j.rows[ridx[t] * W + TW + c]; }     // sparse update of a live array: normal stores
+                        else put(dst + t, ridx[t] >= 0 ? j.rows[ridx[t] * W + TW + c] : src[t]);
                     }
                 }
             } else {
                 for (int t = 0; t < nb; ++t) {
                     double* dst = j.state_out + (b0 + t) * 14;
-                    if (ridx[t] >= 0) memcpy(dst, j.rows + ridx[t] * W + TW, 14 * sizeof(double));
-                    else if (!inplace) memcpy(dst, j.state_in + (b0 + t) * 14, 14 * sizeof(double));
+                    if (inplace) { if (ridx[t] >= 0) memcpy(dst, j.rows + ridx[t] * W + TW, 14 * sizeof(double)); }
+                    else put_n(dst, ridx[t] >= 0 ? j.rows + ridx[t] * W + TW : j.state_in + (b0 + t) * 14, 14);
                 }
             }
         }
     }
+    store_fence();
 }
 }  // namespace
+
+// Dense tangent of points [i0, i0 + n) of an N-point array from the chunk's factored rows (mm_host.cu expands every chunk of the dense
+// host-buffer call as it arrives): `fl` = the chunk's n flags, `rows` = its n_rows rows of 13 doubles.  Split over `T` host threads.
+int expand_factored_chunk(const MMPlastic* p, const uint8_t* fl, const double* rows, int64_t n_rows, double* tan, int64_t N, int64_t i0, int64_t n, int layout, int T) {
+    ExpandJob j;
+    j.row_kind = MM_ROWS_FACTORED; j.layout = layout; j.flags = fl; j.rows = rows; j.state_in = nullptr; j.tan = tan; j.state_out = nullptr; j.N = N; j.flags_base = i0;
+    const ElasticK ek = make_elastic_k(p->E, p->nu);
+    j.lam = ek.lam; j.G = ek.G;
+    const double zero[6] = {0, 0, 0, 0, 0, 0};
+    for (int J = 0; J < 6; ++J)
+        for (int I = 0; I < 6; ++I) j.Ee[I + 6 * J] = plastic_tangent_entry_lg(ek.lam, ek.G, 0.0, zero, zero, I, J);
+    if (T <= 0) T = host_threads();
+    if ((int64_t)T * 16384 > n) T = (int)(n / 16384) + 1;
+    std::vector<int64_t> lo(T + 1), row0(T + 1, 0);
+    for (int t = 0; t <= T; ++t) lo[t] = i0 + (n * t / T) / BLK * BLK;
+    lo[T] = i0 + n;
+    for (int t = 0; t < T; ++t) {                      // 1 byte per point: counting is negligible next to the 288-byte scatter
+        int64_t c = 0;
+        for (int64_t i = lo[t]; i < lo[t + 1]; ++i) c += (fl[i - i0] & MM_FLAG_PLASTIC);
+        row0[t + 1] = row0[t] + c;
+    }
+    if (row0[T] != n_rows) return set_error(MM_ERR_CUDA, "mmh_plastic: chunk at %lld: %lld flags set but %lld rows arrived", (long long)i0, (long long)row0[T], (long long)n_rows);
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back([&, t] { expand_range(j, lo[t], lo[t + 1], row0[t]); });
+    expand_range(j, lo[0], lo[1], row0[0]);
+    for (auto& x : th) x.join();
+    return MM_OK;
+}
+int expand_host_threads() { return host_threads(); }
 }  // namespace mm
 
 using namespace mm;
@@ -131,7 +224,7 @@ int mmh_plastic_expand(const MMPlastic* p, int row_kind, const uint8_t* flags, c
     if (state_out && !state_in) return set_error(MM_ERR_ARG, "mmh_plastic_expand: state_in required to fill the elastic points of state_out");
     if (N == 0 || (!tan && !state_out)) return MM_OK;
     ExpandJob j;
-    j.row_kind = row_kind; j.layout = layout; j.flags = flags; j.rows = rows; j.state_in = state_in; j.tan = tan; j.state_out = state_out; j.N = N;
+    j.row_kind = row_kind; j.layout = layout; j.flags = flags; j.rows = rows; j.state_in = state_in; j.tan = tan; j.state_out = state_out; j.N = N; j.flags_base = 0;
     const ElasticK ek = make_elastic_k(p->E, p->nu);
     j.lam = ek.lam; j.G = ek.G;
     const double zero[6] = {0, 0, 0, 0, 0, 0};

@@ -5,11 +5,16 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include <string.h>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 #include "../../include/mmb200.h"
 
 namespace mm {
 int set_error(int code, const char* fmt, ...);
+int* host_tuning_slot(const char* name);
+int expand_factored_chunk(const MMPlastic* p, const uint8_t* fl, const double* rows, int64_t n_rows, double* tan, int64_t N, int64_t i0, int64_t n, int layout, int T);   // mm_expand.cpp
 
 namespace {
 constexpr int NSLOT = 4;
@@ -32,6 +37,9 @@ struct Workspace {
     cudaEvent_t ev[NSLOT] = {};
     int64_t* h_counts = nullptr;    // pinned: per-slot row counts of the compact return
     int32_t* d_fail = nullptr;
+    cudaEvent_t ev2[NSLOT] = {};    // dense-through-factored mode: a slot's rows and flags have landed in the pinned staging
+    char* h_stage = nullptr;        // pinned staging of that mode (rows + flags per slot)
+    size_t h_stage_bytes = 0;
     bool init = false;
 };
 Workspace g_ws_dev[64];             // one workspace (streams, staging buffer, counter) per device the process has used
@@ -45,6 +53,7 @@ int ensure(size_t bytes, Workspace** out) {
         for (int s = 0; s < NSLOT; ++s) {
             if (cudaStreamCreateWithFlags(&ws.streams[s], cudaStreamNonBlocking) != cudaSuccess) return set_error(MM_ERR_CUDA, "mmh: cudaStreamCreate failed");
             if (cudaEventCreateWithFlags(&ws.ev[s], cudaEventDisableTiming) != cudaSuccess) return set_error(MM_ERR_CUDA, "mmh: cudaEventCreate failed");
+            if (cudaEventCreateWithFlags(&ws.ev2[s], cudaEventDisableTiming) != cudaSuccess) return set_error(MM_ERR_CUDA, "mmh: cudaEventCreate failed");
         }
         if (cudaMalloc(&ws.d_fail, sizeof(int32_t)) != cudaSuccess) return set_error(MM_ERR_CUDA, "mmh: cudaMalloc failed");
         if (cudaHostAlloc((void**)&ws.h_counts, NSLOT * sizeof(int64_t), cudaHostAllocDefault) != cudaSuccess) return set_error(MM_ERR_CUDA, "mmh: cudaHostAlloc failed");
@@ -61,6 +70,17 @@ int ensure(size_t bytes, Workspace** out) {
         ws.bytes = bytes;
     }
     *out = &ws;
+    return MM_OK;
+}
+
+// callers hold g_mu and have nothing in flight that touches the staging
+int ensure_stage(Workspace& ws, size_t bytes) {
+    if (bytes <= ws.h_stage_bytes) return MM_OK;
+    if (ws.h_stage) cudaFreeHost(ws.h_stage);
+    ws.h_stage = nullptr; ws.h_stage_bytes = 0;
+    cudaError_t e = cudaHostAlloc((void**)&ws.h_stage, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_error(MM_ERR_CUDA, "mmh: cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+    ws.h_stage_bytes = bytes;
     return MM_OK;
 }
 
@@ -147,9 +167,24 @@ inline Arr out_arr(void* h, int nc, int elem = 8, bool per_layout = true) { Arr 
 constexpr int LAG = 2;
 static_assert(LAG < NSLOT, "a slot's row copy must be issued before the slot is reused");
 
+// `expand_tan` (dense-through-factored mode, what mmh_plastic uses): the caller wants the DENSE tangent in host memory.  The factored rows
+// {gξ, u, n} of every chunk (104 B per yielded point instead of 288 B per point over PCIe) land in an internal pinned staging together with
+// the chunk's flags, and a helper thread expands each chunk into `expand_tan` with the host cores (mm_expand.cpp: the kernels' own fma
+// expression, so the bits are those of the dense device path) while the next chunks are still in flight.  `rows` / `cap` are unused.
+struct ExpandQueue {
+    struct Job { int64_t j; int slot; int64_t c, i0, n; };
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::deque<Job> q;
+    bool closed = false;
+    int64_t done = 0;               // chunks [0, done) are expanded: their staging slots may be refilled
+    int rc = MM_OK;
+    char msg[256] = "";
+};
+
 int compact_pipeline(const MMPlastic* p, const double* eps, const double* state_in, double* d_state, double* sig, uint8_t* flags, uint16_t* iters,
                      int row_kind, double* rows, int64_t cap, int64_t* n_rows, double* state_out, int32_t* n_fail, const MMNewtonOpts* opts,
-                     int64_t N, int layout) {
+                     int64_t N, int layout, double* expand_tan = nullptr) {
     const int W = mm_plastic_row_width(row_kind);
     if (W < 0) return W;
     *n_rows = 0;
@@ -171,8 +206,58 @@ int compact_pipeline(const MMPlastic* p, const double* eps, const double* state_
         sl[s].eps = b; b += b_eps; sl[s].st = b; b += b_st; sl[s].sig = b; b += b_sig; sl[s].fl = b; b += b_fl; sl[s].it = b; b += b_it;
         sl[s].rows = b; b += b_rows; sl[s].cnt = b; b += b_cnt; sl[s].ws = b;
     }
+    // dense-through-factored mode: pinned staging per slot = [rows: chunk x W doubles | flags: chunk bytes], expansion on a helper thread
+    char* h_rows[NSLOT] = {};
+    uint8_t* h_fl[NSLOT] = {};
+    if (expand_tan) {
+        const size_t s_rows = align256((size_t)chunk * W * 8), s_fl = align256((size_t)chunk);
+        if ((rc = ensure_stage(ws, (s_rows + s_fl) * NSLOT)) != MM_OK) return rc;
+        for (int s = 0; s < NSLOT; ++s) { h_rows[s] = ws.h_stage + s * (s_rows + s_fl); h_fl[s] = (uint8_t*)(h_rows[s] + s_rows); }
+    }
     if (cudaMemsetAsync(ws.d_fail, 0, sizeof(int32_t), ws.streams[0]) != cudaSuccess) return drain(ws, set_error(MM_ERR_CUDA, "mmh: memset failed"));
     if (cudaStreamSynchronize(ws.streams[0]) != cudaSuccess) return drain(ws, set_error(MM_ERR_CUDA, "mmh: sync failed"));
+    ExpandQueue xq;
+    std::thread helper;
+    if (expand_tan) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        helper = std::thread([&, dev] {
+            cudaSetDevice(dev);
+            for (;;) {
+                ExpandQueue::Job jb;
+                {
+                    std::unique_lock<std::mutex> lk(xq.mu);
+                    xq.cv_job.wait(lk, [&] { return !xq.q.empty() || xq.closed; });
+                    if (xq.q.empty()) return;
+                    jb = xq.q.front();
+                    xq.q.pop_front();
+                }
+                int r = MM_OK;
+                const cudaError_t e = cudaEventSynchronize(ws.ev2[jb.slot]);      // rows, flags (and everything queued before them) are in host memory
+                if (e != cudaSuccess) r = set_error(MM_ERR_CUDA, "mmh_plastic: waiting for a chunk's rows: %s", cudaGetErrorString(e));
+                else r = expand_factored_chunk(p, h_fl[jb.slot], (const double*)h_rows[jb.slot], jb.c, expand_tan, N, jb.i0, jb.n, layout, 0);
+                {
+                    std::lock_guard<std::mutex> lk(xq.mu);
+                    if (r != MM_OK && xq.rc == MM_OK) { xq.rc = r; strncpy(xq.msg, mm_last_error(), sizeof(xq.msg) - 1); }
+                    xq.done = jb.j + 1;
+                }
+                xq.cv_done.notify_all();
+            }
+        });
+    }
+    // a staging slot is refilled by chunk j only after chunk j - NSLOT has been expanded out of it
+    auto wait_expanded = [&](int64_t upto) -> int {
+        if (!expand_tan) return MM_OK;
+        std::unique_lock<std::mutex> lk(xq.mu);
+        if (upto > 0) xq.cv_done.wait(lk, [&] { return xq.done >= upto || xq.rc != MM_OK; });
+        return xq.rc;
+    };
+    auto close_helper = [&]() {
+        if (!expand_tan || !helper.joinable()) return;
+        { std::lock_guard<std::mutex> lk(xq.mu); xq.closed = true; }
+        xq.cv_job.notify_all();
+        helper.join();
+    };
     Arr a_eps = in_arr(eps, 6), a_sin = in_arr(state_in, 14), a_sig = out_arr(sig, 6), a_fl = out_arr(flags, 1, 1, false), a_it = out_arr(iters, 1, 2, false),
         a_sout = out_arr(state_out, 14);
     for (int s = 0; s < NSLOT; ++s) { a_eps.d[s] = sl[s].eps; a_sin.d[s] = sl[s].st; a_sig.d[s] = sl[s].sig; a_fl.d[s] = sl[s].fl; a_it.d[s] = sl[s].it; a_sout.d[s] = sl[s].st; }
@@ -185,6 +270,15 @@ int compact_pipeline(const MMPlastic* p, const double* eps, const double* state_
         cudaError_t e = cudaEventSynchronize(ws.ev[slot]);
         if (e != cudaSuccess) return fail("event sync", e);
         const int64_t c = ws.h_counts[slot];
+        if (expand_tan) {
+            if (c > 0 && (e = cudaMemcpyAsync(h_rows[slot], sl[slot].rows, (size_t)c * W * 8, cudaMemcpyDeviceToHost, ws.streams[slot])) != cudaSuccess) return fail("row copy", e);
+            if ((e = cudaEventRecord(ws.ev2[slot], ws.streams[slot])) != cudaSuccess) return fail("event record", e);
+            const int64_t i0 = j * chunk;
+            { std::lock_guard<std::mutex> lk(xq.mu); xq.q.push_back({j, slot, c, i0, (N - i0 < chunk) ? (N - i0) : chunk}); }
+            xq.cv_job.notify_one();
+            total += c;
+            return MM_OK;
+        }
         if (c > 0 && total + c <= cap) {
             e = cudaMemcpyAsync(rows + total * W, sl[slot].rows, (size_t)c * W * 8, cudaMemcpyDeviceToHost, ws.streams[slot]);
             if (e != cudaSuccess) return fail("row copy", e);
@@ -197,6 +291,7 @@ int compact_pipeline(const MMPlastic* p, const double* eps, const double* state_
         const int64_t i0 = k * chunk, n = (N - i0 < chunk) ? (N - i0) : chunk;
         cudaStream_t st = ws.streams[slot];
         cudaError_t e = cudaSuccess;
+        if (wait_expanded(k - NSLOT + 1) != MM_OK) break;        // the helper's error is picked up after the loop
         rc = copy_chunk(a_eps, slot, N, i0, n, layout, true, st);
         double* d_st = (double*)sl[slot].st;
         if (rc == MM_OK) {
@@ -211,6 +306,7 @@ int compact_pipeline(const MMPlastic* p, const double* eps, const double* state_
         if (rc == MM_OK && (e = cudaEventRecord(ws.ev[slot], st)) != cudaSuccess) rc = fail("event record", e);
         if (rc == MM_OK) rc = copy_chunk(a_sig, slot, N, i0, n, layout, false, st);
         if (rc == MM_OK && flags) rc = copy_chunk(a_fl, slot, N, i0, n, layout, false, st);
+        if (rc == MM_OK && expand_tan && (e = cudaMemcpyAsync(h_fl[slot], sl[slot].fl, (size_t)n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) rc = fail("flag staging", e);
         if (rc == MM_OK && iters) rc = copy_chunk(a_it, slot, N, i0, n, layout, false, st);
         if (rc == MM_OK && state_out) rc = copy_chunk(a_sout, slot, N, i0, n, layout, false, st);
         if (rc == MM_OK && d_state && layout == MM_LAYOUT_SOA &&
@@ -218,9 +314,12 @@ int compact_pipeline(const MMPlastic* p, const double* eps, const double* state_
         if (rc == MM_OK && k >= LAG) rc = finalize(k - LAG);
     }
     for (int64_t j = (nchunks > LAG ? nchunks - LAG : 0); j < nchunks && rc == MM_OK; ++j) rc = finalize(j);
+    close_helper();                        // the helper works its queue off (every queued job's event is recorded) and exits
+    if (expand_tan && rc == MM_OK && xq.rc != MM_OK) rc = set_error(xq.rc, "%s", xq.msg);      // (joined: no lock needed)
     rc = drain(ws, rc);
     if (rc != MM_OK) return rc;
     *n_rows = total;
+    if (expand_tan) cap = total;
     if (n_fail) {
         int32_t f = 0;
         if (cudaMemcpy(&f, ws.d_fail, sizeof(f), cudaMemcpyDeviceToHost) != cudaSuccess) return set_error(MM_ERR_CUDA, "mmh: n_fail readback failed");
@@ -231,6 +330,13 @@ int compact_pipeline(const MMPlastic* p, const double* eps, const double* state_
     return MM_OK;
 }
 }  // namespace
+
+// run-time switches of the host-buffer entry points (mm_set_tuning): "mmh_plastic_via_factored" 1 (default) / 0
+int* host_tuning_slot(const char* name) {
+    static int via_factored = [] { const char* e = getenv("MM_MMH_PLASTIC_VIA_FACTORED"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (!strcmp(name, "mmh_plastic_via_factored")) return &via_factored;
+    return nullptr;
+}
 }  // namespace mm
 
 using namespace mm;
@@ -256,6 +362,13 @@ int mmh_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig,
 int mmh_plastic(const MMPlastic* p, const double* eps, const double* state_in, double* sig, double* tan, double* state_out,
                 uint8_t* flags, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout) {
     if (!p || N < 0 || (N > 0 && (!eps || !state_in || !sig || !state_out))) return set_error(MM_ERR_ARG, "mmh_plastic: bad argument");
+    // dense tangent wanted: send the factored rows of the yielded points over the link and let the host cores expand them chunk by chunk
+    // while the next chunks are in flight — same bits as the dense device path (tests/test_compact.py), 217 instead of 451 bytes per
+    // point coming down ("mmh_plastic_via_factored" 0 restores the plain dense transfer)
+    if (tan && N > 0 && *host_tuning_slot("mmh_plastic_via_factored") != 0 && (layout == MM_LAYOUT_SOA || layout == MM_LAYOUT_AOS)) {
+        int64_t n_rows = 0;
+        return compact_pipeline(p, eps, state_in, nullptr, sig, flags, iters, MM_ROWS_FACTORED, nullptr, 0, &n_rows, state_out, n_fail, opts, N, layout, tan);
+    }
     Arr a[7] = {in_arr(eps, 6), in_arr(state_in, 14), out_arr(sig, 6), out_arr(tan, 36), out_arr(state_out, 14),
                 out_arr(flags, 1, 1, false), out_arr(iters, 1, 2, false)};
     return pipeline(a, 7, N, layout, n_fail, [&](int s, int64_t n, cudaStream_t st, int32_t* df) {

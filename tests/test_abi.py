@@ -178,7 +178,7 @@ def test_tuning_switches_are_known_by_name():
     name is refused with -1 — no GPU needed."""
     names = [b"crystal_force_general", b"crystal_thresh", b"crystal_chunk", b"crystal_fixup_per_sm", b"crystal_variant",
              b"wrapped_j2_variant", b"wrapped_j2_th_outer", b"wrapped_j2_th_final", b"wrapped_j2_chunk",
-             b"wrapped_crystal_variant", b"wrapped_crystal_slab", b"xu_soa_tiled"]
+             b"wrapped_crystal_variant", b"wrapped_crystal_slab", b"xu_soa_tiled", b"mmh_plastic_via_factored"]
     lib = L.load()
     for n in names:
         old = lib.mm_set_tuning(n, 7)

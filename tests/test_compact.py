@@ -284,3 +284,46 @@ def test_python_mirror_compact_forms(mm, cuda_lib):
         mm.material_response(m, eps, mm.PlasticState(sin.copy()), tangent="factored", out={"rows": np.empty((5, 27))})
     with pytest.raises(ValueError):
         mm.material_response(m, eps, mm.PlasticState(sin.copy()), tangent="sparse")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lay", [0, 1])
+@pytest.mark.parametrize("N,chunk", [(1, 1 << 20), (777, 100), (40000, 4096), (300001, 1 << 16), (2000003, 1 << 18)])
+def test_dense_host_call_through_factored_rows_is_the_dense_result(mm, cuda_lib, N, chunk, lay):
+    """mmh_plastic with a dense tangent (the default host-buffer J2 call): factored rows over the link + expansion on a helper thread while
+    the next chunks are in flight == plain dense transfer == mm_plastic, bit for bit; without flags / iters arrays, with the state updated
+    in place, for an all-elastic and an all-yielded batch (every chunk with 0 rows / n rows)."""
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    eps, sin = _two_step_inputs(mm, m, N, lay)
+    sig_d, tan_d, st_d, fl_d, it_d = _dense_reference(mm, m, eps, sin, lay)
+    lib = cuda_lib
+    old = lib.mmh_set_chunk_points(chunk)
+
+    def call(via, e, s_in, with_flags=True, inplace=False):
+        prev = lib.mm_set_tuning(b"mmh_plastic_via_factored", via)
+        try:
+            sig, T = np.full(e.shape, np.nan), np.full(tan_d.shape, np.nan)
+            S = s_in.copy() if inplace else np.full(s_in.shape, np.nan)
+            fl, it, nf = np.zeros(N, np.uint8), np.zeros(N, np.uint16), np.zeros(1, np.int32)
+            rc = lib.mmh_plastic(C.byref(m._c), H.P(e), H.P(S if inplace else s_in), H.P(sig), H.P(T), H.P(S), H.P(fl) if with_flags else None,
+                                 H.P(it) if with_flags else None, H.P(nf), None, N, lay)
+            assert rc == 0, mm._lib.last_error()
+            return sig, T, S, fl, it, int(nf[0])
+        finally:
+            lib.mm_set_tuning(b"mmh_plastic_via_factored", prev)
+
+    try:
+        for via in (1, 0):
+            sig, T, S, fl, it, nf = call(via, eps, sin)
+            assert nf == 0 and np.array_equal(sig, sig_d) and np.array_equal(T, tan_d) and np.array_equal(S, st_d) and np.array_equal(fl, fl_d) and np.array_equal(it, it_d)
+        sig, T, S, _, _, _ = call(1, eps, sin, with_flags=False)
+        assert np.array_equal(sig, sig_d) and np.array_equal(T, tan_d) and np.array_equal(S, st_d)
+        sig, T, S, _, _, _ = call(1, eps, sin, inplace=True)
+        assert np.array_equal(T, tan_d) and np.array_equal(S, st_d)
+        for scale in (1e-3, 50.0):                                  # nobody yields / everybody yields
+            e2 = eps * scale
+            a, b = call(1, e2, sin), call(0, e2, sin)
+            assert (a[3] & 1).mean() in (0.0, 1.0) or N < 10
+            assert all(np.array_equal(x, y) for x, y in zip(a[:5], b[:5])) and a[5] == b[5]
+    finally:
+        lib.mmh_set_chunk_points(old)
