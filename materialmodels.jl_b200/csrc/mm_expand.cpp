@@ -201,6 +201,28 @@ int expand_factored_chunk(const MMPlastic* p, const uint8_t* fl, const double* r
     return MM_OK;
 }
 int expand_host_threads() { return host_threads(); }
+
+// LinearElastic hands every point the ONE stored Eᵉ (src/LinearElastic.jl:59): the host-buffer call does not fetch N copies of it over the
+// link, the host cores write them (non-temporal stores) while the strains and stresses are in flight.  Ee = iso_entry, the kernel's values.
+void fill_constant_tangent(double lam, double G, double* tan, int64_t N, int layout, int T) {
+    double Ee[36];
+    for (int J = 0; J < 6; ++J)
+        for (int I = 0; I < 6; ++I) Ee[I + 6 * J] = iso_entry(I, J, lam, G);
+    if (T <= 0) T = host_threads();
+    if ((int64_t)T * 16384 > N) T = (int)(N / 16384) + 1;
+    auto work = [&](int64_t lo, int64_t hi) {
+        if (layout == MM_LAYOUT_SOA) {
+            for (int c = 0; c < 36; ++c) { double* d = tan + (int64_t)c * N; const double v = Ee[c]; for (int64_t i = lo; i < hi; ++i) put(d + i, v); }
+        } else {
+            for (int64_t i = lo; i < hi; ++i) put_n(tan + i * 36, Ee, 36);
+        }
+        store_fence();
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work, N * t / T, N * (t + 1) / T);
+    work(0, N / T);
+    for (auto& x : th) x.join();
+}
 }  // namespace mm
 
 using namespace mm;

@@ -14,6 +14,7 @@
 namespace mm {
 int set_error(int code, const char* fmt, ...);
 int* host_tuning_slot(const char* name);
+void fill_constant_tangent(double lam, double G, double* tan, int64_t N, int layout, int T);   // mm_expand.cpp
 int expand_factored_chunk(const MMPlastic* p, const uint8_t* fl, const double* rows, int64_t n_rows, double* tan, int64_t N, int64_t i0, int64_t n, int layout, int T);   // mm_expand.cpp
 
 namespace {
@@ -353,10 +354,22 @@ int64_t mmh_set_chunk_points(int64_t n) { std::lock_guard<std::mutex> lock(g_mu)
 
 int mmh_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig, double* tan_or_null, int64_t N, int layout) {
     if (!p || N < 0 || (N > 0 && (!eps || !sig))) return set_error(MM_ERR_ARG, "mmh_linear_elastic: bad argument");
-    Arr a[3] = {in_arr(eps, 6), out_arr(sig, 6), out_arr(tan_or_null, 36)};
-    return pipeline(a, 3, N, layout, nullptr, [&](int s, int64_t n, cudaStream_t st, int32_t* df) {
+    // the tangent is the one stored Eᵉ for every point (src/LinearElastic.jl:59): written by the host cores while ε and σ cross the link,
+    // instead of 288 bytes per point coming down ("mmh_plastic_via_factored" 0 also restores the plain transfer here); same values — the
+    // kernel stores iso_entry(λ, G) of the same host-computed λ, G
+    const bool host_fill = tan_or_null && N > 0 && *host_tuning_slot("mmh_plastic_via_factored") != 0 && (layout == MM_LAYOUT_SOA || layout == MM_LAYOUT_AOS);
+    std::thread filler;
+    if (host_fill) {
+        const double nu = p->nu, E = p->E;
+        const double lam = E * nu / ((1 + nu) * (1 - 2 * nu)), G = E / (2 * (1 + nu));          // make_elastic_k (mm_math.cuh)
+        filler = std::thread([=] { fill_constant_tangent(lam, G, tan_or_null, N, layout, 0); });
+    }
+    Arr a[3] = {in_arr(eps, 6), out_arr(sig, 6), out_arr(host_fill ? nullptr : tan_or_null, 36)};
+    const int rc = pipeline(a, 3, N, layout, nullptr, [&](int s, int64_t n, cudaStream_t st, int32_t* df) {
         return mm_linear_elastic(p, (const double*)a[0].d[s], (double*)a[1].d[s], (double*)a[2].d[s], n, layout, st);
     });
+    if (filler.joinable()) filler.join();
+    return rc;
 }
 
 int mmh_plastic(const MMPlastic* p, const double* eps, const double* state_in, double* sig, double* tan, double* state_out,
