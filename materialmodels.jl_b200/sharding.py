@@ -32,7 +32,26 @@ def init_process_group(backend=None):
                 dist.init_process_group(backend=backend, device_id=torch.device("cuda", local))
             else:
                 dist.init_process_group(backend=backend)
+        # the host-buffer entry points expand / fill dense arrays with the host cores: one process per GPU shares them
+        share_host_cores(int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     return rank, world, local
+
+
+def share_host_cores(processes_on_this_host):
+    """Give this process its share of the host cores for the library's host-side work (mmh_set_host_threads): `cores // processes`,
+    at least 2.  Called by init_process_group under torchrun; returns the thread count set (0 if the library is not loaded)."""
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except Exception:
+        return 0
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    n = max(2, cores // max(1, int(processes_on_this_host)))
+    lib.mmh_set_host_threads(n)
+    return n
 
 
 def allreduce_sum(value, device="cpu"):

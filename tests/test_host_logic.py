@@ -175,3 +175,18 @@ def test_twin_crystal_matches_oracle(oracle):
             ok = (r["active"] & abi.MM_ACTIVE_FAILED) == 0
             st = np.where(ok[None, :], r["state"], st)                      # failed points keep their old state
     assert n_fallback_total > 0                     # ... but the guard does fire on the harder configurations
+
+
+def test_share_host_cores_sets_the_library_thread_count():
+    """One process per GPU shares the host cores for the library's host-side expansion (sharding.share_host_cores -> mmh_set_host_threads)."""
+    import materialmodels_jl_b200._lib as L
+    from materialmodels_jl_b200 import sharding
+
+    lib = L.load()
+    try:
+        n1 = sharding.share_host_cores(1)
+        n8 = sharding.share_host_cores(8)
+        assert n1 >= n8 >= 2
+        assert lib.mmh_set_host_threads(0) == n8          # returns the previous setting
+    finally:
+        lib.mmh_set_host_threads(0)
