@@ -74,6 +74,13 @@ elif which.startswith("wrapped_"):          # wrapped_planestress / wrapped_unia
     eB = mm.synth_uniform(N, nc, 32, -amp, amp)
     for _ in range(reps):
         mm.material_response(dim, m, eB, stA, options={"defer_check": True})
+elif which.startswith("wrapxtal_"):         # wrapxtal_planestress / wrapxtal_uniaxialstress: the rounds of the two-kernel crystal path (mm_wrap.cu)
+    dim, nc, amp = {"planestress": (mm.PlaneStress(), 3, 4e-3), "uniaxialstress": (mm.UniaxialStress(), 1, 6e-3)}[which.split("_", 1)[1]]
+    m = mm.CrystalViscoPlastic(slipsystems=mm.slipsystems(mm.FCC(), sy.CRYSTAL_RODRIGUES), **sy.CRYSTAL_PARAMS)
+    e = mm.synth_uniform(N, nc, 51, -amp, amp)
+    st0 = mm.initial_material_state(m, N)
+    for _ in range(2):
+        mm.material_response(dim, m, e, st0, 1.0, options={"defer_check": True})
 elif which == "elastic":
     nc, lo, hi, seed = sy.c1_strain()
     e = mm.synth_uniform(N, nc, seed, lo, hi)
