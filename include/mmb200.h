@@ -272,6 +272,10 @@ int mmh_set_host_threads(int n);
 int mmh_hyper(int model, const MMHyper* p, const double* strain, int strain_kind, double* S, double* dSdC, int64_t N, int layout);
 int mmh_crystal(const MMCrystal* p, const double* deps, double dt, const double* state_in, double* sig, double* tan,
                 double* state_out, uint16_t* active, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
+/* ... with the state RESIDENT in device memory (one N-point array in `layout`, updated in place: what a time-stepping caller keeps between
+ * steps): only Δε goes up (48 B per point) and σ, ∂σ∂ε, active, iters come down — the 2 x 336 B of state never cross the link */
+int mmh_crystal_resident(const MMCrystal* p, const double* deps, double dt, double* d_state, double* sig, double* tan, uint16_t* active,
+                         uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout);
 int mmh_xu_needleman(const MMXuNeedleman* p, const double* jump, double* T, double* dTdD, int dim, int64_t N, int layout);
 int mmh_wrapped_linear_elastic(int dim_kind, const MMLinearElastic* p, const double* eps_red, double* sig_red, double* tan_red,
                                uint8_t* outer_iters, int32_t* n_fail, const MMNewtonOpts* wrapper_opts, int64_t N, int layout);

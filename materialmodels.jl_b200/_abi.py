@@ -102,6 +102,7 @@ SIGNATURES = {
     "mmh_plastic": (C.c_int, [C.POINTER(MMPlastic), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int]),
     "mmh_hyper": (C.c_int, [C.c_int, C.POINTER(MMHyper), _P, C.c_int, _P, _P, _I64, C.c_int]),
     "mmh_crystal": (C.c_int, [C.POINTER(MMCrystal), _P, C.c_double, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int]),
+    "mmh_crystal_resident": (C.c_int, [C.POINTER(MMCrystal), _P, C.c_double, _P, _P, _P, _P, _P, _P, C.POINTER(MMNewtonOpts), _I64, C.c_int]),
     "mmh_xu_needleman": (C.c_int, [C.POINTER(MMXuNeedleman), _P, _P, _P, C.c_int, _I64, C.c_int]),
     "mmh_set_chunk_points": (_I64, [_I64]),
     "mm_plastic_row_width": (C.c_int, [C.c_int]),

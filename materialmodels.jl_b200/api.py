@@ -527,6 +527,9 @@ def _response_crystal(m, Δε, state, Δt, options, want_tangent, out=None):
     if N != state.N:
         raise ValueError("strain has %d points, state has %d" % (N, state.N))
     sin = _prep(state.data)
+    if _is_host(Δε) and not _is_host(sin) and options and options.get("state_resident"):
+        # opt-in (options={"state_resident": True}): unlike the reference's call this updates the state array IN PLACE
+        return _response_crystal_resident(m, Δε, state, sin, Δt, options, want_tangent, out, N, layout)
     _same_place(Δε, sin, "material_response(::CrystalViscoPlastic)")
     σ = _out(out, "stress", _shape(6, N, layout), Δε)
     tan = _out(out, "tangent", _shape(36, N, layout), Δε) if want_tangent else None
@@ -546,6 +549,27 @@ def _response_crystal(m, Δε, state, Δt, options, want_tangent, out=None):
                                 _ptr(iters), _ptr(nfail), ctypes.byref(o), N, _LAYOUTS[layout], _stream(Δε))
     check(rc, "mm_crystal")
     new = CrystalViscoPlasticState(sout, layout)
+    new.flags, new.iters, new.n_fail = active, iters, nfail
+    _finish_fail(nfail, Δε, options)
+    return σ, tan, new
+
+
+def _response_crystal_resident(m, Δε, state, sdev, Δt, options, want_tangent, out, N, layout):
+    """options={"state_resident": True}: host strains, state resident on a CUDA device (what a time-stepping caller keeps between steps):
+    the state array is updated IN PLACE and handed back; only Δε crosses the link on the way up, σ / ∂σ∂ε / masks / counts on the way down (mmh_crystal_resident)."""
+    if out is not None and out.get("state") is not None:
+        raise ValueError("material_response(::CrystalViscoPlastic): the device-resident state is updated in place; out['state'] is not used")
+    σ = _out(out, "stress", _shape(6, N, layout), Δε)
+    tan = _out(out, "tangent", _shape(36, N, layout), Δε) if want_tangent else None
+    active = _out(out, "flags", (N,), Δε, np.uint16)
+    iters = _out(out, "iters", (N,), Δε, np.uint16)
+    nfail = _zeros((1,), Δε, np.int32)
+    o = _newton_opts(m, options)
+    with _DeviceGuard(sdev):
+        rc = load().mmh_crystal_resident(ctypes.byref(m._c), _ptr(Δε), float(Δt), _ptr(sdev), _ptr(σ), _ptr(tan), _ptr(active), _ptr(iters),
+                                         _ptr(nfail), ctypes.byref(o), N, _LAYOUTS[layout])
+    check(rc, "mmh_crystal_resident")
+    new = CrystalViscoPlasticState(sdev, layout)
     new.flags, new.iters, new.n_fail = active, iters, nfail
     _finish_fail(nfail, Δε, options)
     return σ, tan, new

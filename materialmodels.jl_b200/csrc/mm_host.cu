@@ -28,6 +28,8 @@ struct Arr {
     int nc;             // components per point
     int elem;           // bytes per component
     bool per_layout;    // false: one value per point, layout-independent (flags / iters / active)
+    void* d_res;        // device-RESIDENT array of all N points, read and updated in place (or NULL): an AoS chunk is used where it lies,
+                        // an SoA chunk is staged through the slot buffer with device-to-device 2-D copies
     void* d[NSLOT];     // device chunk buffers
 };
 
@@ -114,6 +116,18 @@ int copy_chunk(const Arr& a, int slot, int64_t N, int64_t i0, int64_t n, int lay
     return MM_OK;
 }
 
+// a chunk of a device-resident array: AoS -> the slot pointer is the sub-range itself (nothing moves); SoA -> gather / scatter the nc
+// component runs of the chunk into / out of the dense slot buffer
+int resident_chunk(Arr& a, int slot, int64_t N, int64_t i0, int64_t n, int layout, bool load, cudaStream_t st) {
+    char* res = (char*)a.d_res;
+    if (layout != MM_LAYOUT_SOA || a.nc == 1) { a.d[slot] = res + (size_t)i0 * a.nc * a.elem; return MM_OK; }
+    const size_t width = (size_t)n * a.elem, pitch = (size_t)N * a.elem;
+    cudaError_t e = load ? cudaMemcpy2DAsync(a.d[slot], width, res + (size_t)i0 * a.elem, pitch, width, a.nc, cudaMemcpyDeviceToDevice, st)
+                         : cudaMemcpy2DAsync(res + (size_t)i0 * a.elem, pitch, a.d[slot], width, width, a.nc, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_error(MM_ERR_CUDA, "mmh: resident-state staging failed: %s", cudaGetErrorString(e)); }
+    return MM_OK;
+}
+
 // launch(slot, n, stream, d_fail) must enqueue the device-pointer entry point on the slot's chunk buffers
 template <class Launch>
 int pipeline(Arr* arrs, int narr, int64_t N, int layout, int32_t* n_fail, Launch launch) {
@@ -121,7 +135,8 @@ int pipeline(Arr* arrs, int narr, int64_t N, int layout, int32_t* n_fail, Launch
     std::lock_guard<std::mutex> lock(g_mu);              // host threads take turns, whichever mmh_* function they call
     const int64_t chunk = (N < g_chunk) ? N : g_chunk;
     size_t per_slot = 0;
-    for (int a = 0; a < narr; ++a) if (arrs[a].h_in || arrs[a].h_out) per_slot += align256((size_t)chunk * arrs[a].nc * arrs[a].elem);
+    auto staged = [&](const Arr& a) { return a.h_in || a.h_out || (a.d_res && layout == MM_LAYOUT_SOA); };
+    for (int a = 0; a < narr; ++a) if (staged(arrs[a])) per_slot += align256((size_t)chunk * arrs[a].nc * arrs[a].elem);
     Workspace* wsp = nullptr;
     int rc = ensure(per_slot * NSLOT, &wsp);
     if (rc) return rc;
@@ -130,7 +145,7 @@ int pipeline(Arr* arrs, int narr, int64_t N, int layout, int32_t* n_fail, Launch
     for (int s = 0; s < NSLOT; ++s) {
         size_t off = 0;
         for (int a = 0; a < narr; ++a) {
-            if (arrs[a].h_in || arrs[a].h_out) { arrs[a].d[s] = base + s * per_slot + off; off += align256((size_t)chunk * arrs[a].nc * arrs[a].elem); }
+            if (staged(arrs[a])) { arrs[a].d[s] = base + s * per_slot + off; off += align256((size_t)chunk * arrs[a].nc * arrs[a].elem); }
             else arrs[a].d[s] = nullptr;
         }
     }
@@ -141,11 +156,15 @@ int pipeline(Arr* arrs, int narr, int64_t N, int layout, int32_t* n_fail, Launch
         const int slot = (int)(k % NSLOT);
         const int64_t n = (N - i0 < chunk) ? (N - i0) : chunk;
         cudaStream_t st = ws.streams[slot];
-        for (int a = 0; a < narr && rc == MM_OK; ++a)
+        for (int a = 0; a < narr && rc == MM_OK; ++a) {
             if (arrs[a].h_in) rc = copy_chunk(arrs[a], slot, N, i0, n, layout, true, st);
+            else if (arrs[a].d_res) rc = resident_chunk(arrs[a], slot, N, i0, n, layout, true, st);
+        }
         if (rc == MM_OK) rc = launch(slot, n, st, ws.d_fail);
-        for (int a = 0; a < narr && rc == MM_OK; ++a)
+        for (int a = 0; a < narr && rc == MM_OK; ++a) {
             if (arrs[a].h_out) rc = copy_chunk(arrs[a], slot, N, i0, n, layout, false, st);
+            else if (arrs[a].d_res) rc = resident_chunk(arrs[a], slot, N, i0, n, layout, false, st);
+        }
     }
     rc = drain(ws, rc);
     if (rc == MM_OK && n_fail) {
@@ -157,6 +176,7 @@ int pipeline(Arr* arrs, int narr, int64_t N, int layout, int32_t* n_fail, Launch
 }
 
 inline Arr in_arr(const void* h, int nc, int elem = 8) { Arr a; memset(&a, 0, sizeof(a)); a.h_in = h; a.nc = nc; a.elem = elem; a.per_layout = true; return a; }
+inline Arr res_arr(void* d, int nc, int elem = 8) { Arr a; memset(&a, 0, sizeof(a)); a.d_res = d; a.nc = nc; a.elem = elem; a.per_layout = true; return a; }
 inline Arr out_arr(void* h, int nc, int elem = 8, bool per_layout = true) { Arr a; memset(&a, 0, sizeof(a)); a.h_out = h; a.nc = nc; a.elem = elem; a.per_layout = per_layout; return a; }
 
 // ---- compact return of the J2 update (mm_compact.cu) behind the same chunk pipeline ----------------------------------------------
@@ -406,6 +426,17 @@ int mmh_crystal(const MMCrystal* p, const double* deps, double dt, const double*
     return pipeline(a, 7, N, layout, n_fail, [&](int s, int64_t n, cudaStream_t st, int32_t* df) {
         return mm_crystal(p, (const double*)a[0].d[s], dt, (const double*)a[1].d[s], (double*)a[2].d[s], (double*)a[3].d[s], (double*)a[4].d[s],
                           (uint16_t*)a[5].d[s], (uint16_t*)a[6].d[s], df, opts, n, layout, st);
+    });
+}
+
+int mmh_crystal_resident(const MMCrystal* p, const double* deps, double dt, double* d_state, double* sig, double* tan, uint16_t* active, uint16_t* iters,
+                         int32_t* n_fail, const MMNewtonOpts* opts, int64_t N, int layout) {
+    if (!p || N < 0 || (N > 0 && (!deps || !d_state || !sig))) return set_error(MM_ERR_ARG, "mmh_crystal_resident: bad argument");
+    if (layout != MM_LAYOUT_SOA && layout != MM_LAYOUT_AOS) return set_error(MM_ERR_ARG, "mmh_crystal_resident: unknown layout %d", layout);
+    Arr a[6] = {in_arr(deps, 6), res_arr(d_state, 42), out_arr(sig, 6), out_arr(tan, 36), out_arr(active, 1, 2, false), out_arr(iters, 1, 2, false)};
+    return pipeline(a, 6, N, layout, n_fail, [&](int s, int64_t n, cudaStream_t st, int32_t* df) {
+        return mm_crystal(p, (const double*)a[0].d[s], dt, (const double*)a[1].d[s], (double*)a[2].d[s], (double*)a[3].d[s], (double*)a[1].d[s],
+                          (uint16_t*)a[4].d[s], (uint16_t*)a[5].d[s], df, opts, n, layout, st);
     });
 }
 

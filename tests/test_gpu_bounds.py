@@ -129,6 +129,14 @@ def test_no_entry_point_writes_out_of_bounds(mm, cuda_lib, N, lay, shift):
         T, H = G(dim * N), G(dim * dim * N)
         assert lib.mm_xu_needleman(C.byref(xp), I(D), T.ptr, H.ptr, dim, N, lay, None) == 0
         T.check("mm_xu_needleman T"), H.check("mm_xu_needleman dTdΔ")
+        if lay == 0:                                   # the copy-engine tile kernel for SoA arrays (A/B option)
+            T, H = G(dim * N), G(dim * dim * N)
+            old = lib.mm_set_tuning(b"xu_soa_tiled", 1)
+            try:
+                assert lib.mm_xu_needleman(C.byref(xp), I(D), T.ptr, H.ptr, dim, N, lay, None) == 0
+            finally:
+                lib.mm_set_tuning(b"xu_soa_tiled", old)
+            T.check("mm_xu_needleman T (tiles)"), H.check("mm_xu_needleman dTdΔ (tiles)")
     # TransverselyIsotropic
     tp = abi.MMTransverselyIsotropic()
     assert lib.mm_transversely_isotropic_setup(100e3, 10e3, 5e3, 0.4, 0.3, C.byref(tp)) == 0

@@ -249,6 +249,33 @@ def test_xu_needleman(mm, torch, oracle, lname, lay, dim):
     assert np.isclose(Tk[dim - 1, 0], 400.0) and np.isclose(Tk[0, 1], 200.0)
 
 
+@pytest.mark.parametrize("dim", [3, 2])
+def test_xu_needleman_soa_tile_kernel_equals_direct_kernel(mm, torch, cuda_lib, dim):
+    """The copy-engine tile kernel for SoA arrays (mm_set_tuning("xu_soa_tiled", 1)) against the direct kernel: identical bits, for full
+    tiles, a ragged last tile, an odd point count (component runs not 16-byte aligned -> element-wise copies) and without the Hessian."""
+    x = sy.XU_PARAMS
+    m = mm.XuNeedleman(σₘₐₓ=x["sigma_max"], τₘₐₓ=x["tau_max"], Φₙ=mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]),
+                       Φₜ=mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), Δₙˢ=x["Delta_n_star"])
+    nc, lo, hi, seed = sy.c5_jump()
+    for N in (1, 255, 256, 100000, 100002, 100003, 1 << 20):
+        D = sy.host_uniform(N, nc, seed, lo, hi)
+        if dim == 2:
+            D = np.ascontiguousarray(D[1:])
+        Dd = dev(torch, D)
+        res = {}
+        for tiled in (0, 1):
+            old = cuda_lib.mm_set_tuning(b"xu_soa_tiled", tiled)
+            try:
+                T, Hh, _ = mm.material_response(m, Dd)
+                T2, none, _ = mm.material_response(m, Dd, tangent=False)
+                res[tiled] = (host(T), host(Hh), host(T2))
+                assert none is None
+            finally:
+                cuda_lib.mm_set_tuning(b"xu_soa_tiled", old)
+        for a, b in zip(res[0], res[1]):
+            assert np.array_equal(a, b)
+
+
 # ---------------------------------------------------------------------------------------------
 def make_crystal(mm, q=0.0, structure=None):
     prm = dict(sy.CRYSTAL_PARAMS)
@@ -540,3 +567,27 @@ def test_plastic_state_updated_in_place(mm, torch, lname):
     s2, t2, new2 = mm.material_response(m, eB, mm.PlasticState(buf, lname), out={"state": buf})
     assert new2.data.data_ptr() == buf.data_ptr()
     assert torch.equal(s2, s) and torch.equal(t2, t) and torch.equal(buf, new.data)
+
+
+@pytest.mark.parametrize("lname,lay", LAYOUTS)
+def test_crystal_host_call_with_device_resident_state(mm, torch, cuda_lib, lname, lay):
+    """material_response(m, numpy Δε, state on the GPU, Δt, options={"state_resident": True}) -> mmh_crystal_resident: the state array is updated in place chunk by chunk
+    (AoS: where it lies; SoA: staged with device-to-device copies); σ, ∂σ∂ε, masks, counts and the state equal the device path bit for bit."""
+    m = make_crystal(mm)
+    N = 5003
+    old = cuda_lib.mmh_set_chunk_points(1000)
+    try:
+        st_dev = mm.initial_material_state(m, N, layout=lname)
+        st_res = mm.CrystalViscoPlasticState(st_dev.data.clone(), lname)
+        for step in range(2):
+            nc, lo, hi, seed = sy.c4_strain_increment(step)
+            d = to_layout(sy.host_uniform(N, nc, seed, lo, hi), lay)
+            s1, t1, st_dev = mm.material_response(m, dev(torch, d), st_dev, 1.0, options={"defer_check": True})
+            data_before = st_res.data
+            s2, t2, st_res = mm.material_response(m, d, st_res, 1.0, options={"defer_check": True, "state_resident": True})
+            assert isinstance(s2, np.ndarray) and st_res.data is data_before          # host outputs, the device array updated in place
+            assert np.array_equal(s2, host(s1)) and np.array_equal(t2, host(t1)) and torch.equal(st_res.data, st_dev.data)
+            assert np.array_equal(st_res.flags, host(st_dev.flags).view(np.uint16)) and np.array_equal(st_res.iters, host(st_dev.iters).view(np.uint16))
+            assert int(st_res.n_fail[0]) == int(st_dev.n_fail.item())
+    finally:
+        cuda_lib.mmh_set_chunk_points(old)
