@@ -269,13 +269,15 @@ struct WrapXtalTangent {
 template <int KIND, int LAYOUT>
 __global__ void __launch_bounds__(128) wrapped_crystal_outer_kernel(const WrapXtalWs w, const WrapXtalIO io, const double tol, const int it, const int max_iter, const int cap) {
     constexpr int d = wrap_dim(KIND), nc = wrap_nc(KIND);
-    const int buf = (it - 1) & 1;
+    // (a run-time index into the kernel parameter's idx[2] would move the whole parameter block to local memory)
+    const int* idx_in = ((it - 1) & 1) ? w.idx[1] : w.idx[0];
+    int* idx_out = ((it - 1) & 1) ? w.idx[0] : w.idx[1];
     const int n = w.cnt[it - 1];
     const int j = blockIdx.x * 128 + threadIdx.x;
     bool again = false;
     int li = 0;
     if (j < n) {
-        li = w.idx[buf][j];
+        li = idx_in[j];
         const int64_t i = io.i0 + li;
         const unsigned act = w.act[j];
         int flag = (act & MM_ACTIVE_FAILED) ? 0x80 : 0, oit = it - 1;
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(128) wrapped_crystal_outer_kernel(const WrapXt
         int base = 0;
         if (lane == leader) base = atomicAdd(&w.cnt[it], __popc(m));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (again) w.idx[buf ^ 1][base + __popc(m & ((1u << lane) - 1u))] = li;
+        if (again) idx_out[base + __popc(m & ((1u << lane) - 1u))] = li;
     }
 }
 
