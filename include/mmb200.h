@@ -99,8 +99,8 @@ int mm_device_count(void);
  * "crystal_fixup_per_sm", "crystal_variant") and of the dimension wrappers ("wrapped_j2_variant" 0 = one thread per point, 1 = state
  * machine, 2 = pass-granular trips; "wrapped_j2_th_outer", "wrapped_j2_th_final", "wrapped_j2_chunk"; "wrapped_crystal_variant" 0 = one
  * thread per point, 1 = rounds; "wrapped_crystal_slab") and of the XuNeedleman SoA path ("xu_soa_tiled" 0 = direct kernel, 1 = copy-engine
- * tiles) and of the host-buffer J2 call ("mmh_plastic_via_factored" 1 = dense tangent rebuilt on the host from factored rows, 0 = plain
- * dense transfer); initial values come from the MM_CRYSTAL_* / MM_WRAPPED_* environment variables, read once per process.
+ * tiles) and of the host-buffer J2 call ("mmh_plastic_via_factored" 1 = dense tangent rebuilt on the host from factored rows for batches of >= 2^18 points,
+ * 2 = for any size, 0 = plain dense transfer); initial values come from the MM_CRYSTAL_* / MM_WRAPPED_* environment variables, read once per process.
  * Returns the previous value, -1 for an unknown name.  Results never depend on these (tests/test_gpu_parity.py runs both paths). */
 int mm_set_tuning(const char* name, int value);
 

@@ -205,13 +205,14 @@ struct ExpandQueue {
 
 int compact_pipeline(const MMPlastic* p, const double* eps, const double* state_in, double* d_state, double* sig, uint8_t* flags, uint16_t* iters,
                      int row_kind, double* rows, int64_t cap, int64_t* n_rows, double* state_out, int32_t* n_fail, const MMNewtonOpts* opts,
-                     int64_t N, int layout, double* expand_tan = nullptr) {
+                     int64_t N, int layout, double* expand_tan = nullptr, int64_t chunk_cap = 0) {
     const int W = mm_plastic_row_width(row_kind);
     if (W < 0) return W;
     *n_rows = 0;
     if (N == 0) return MM_OK;
     std::lock_guard<std::mutex> lock(g_mu);
-    const int64_t chunk = (N < g_chunk) ? N : g_chunk;
+    int64_t chunk = (N < g_chunk) ? N : g_chunk;
+    if (chunk_cap > 0 && chunk > chunk_cap) chunk = chunk_cap;
     const bool stage_state = !(d_state && layout == MM_LAYOUT_AOS);
     const size_t b_eps = align256((size_t)chunk * 48), b_st = stage_state ? align256((size_t)chunk * 112) : 0, b_sig = align256((size_t)chunk * 48),
                  b_fl = align256((size_t)chunk), b_it = align256((size_t)chunk * 2), b_rows = align256((size_t)chunk * W * 8), b_cnt = 256,
@@ -377,7 +378,7 @@ int mmh_linear_elastic(const MMLinearElastic* p, const double* eps, double* sig,
     // the tangent is the one stored Eᵉ for every point (src/LinearElastic.jl:59): written by the host cores while ε and σ cross the link,
     // instead of 288 bytes per point coming down ("mmh_plastic_via_factored" 0 also restores the plain transfer here); same values — the
     // kernel stores iso_entry(λ, G) of the same host-computed λ, G
-    const bool host_fill = tan_or_null && N > 0 && *host_tuning_slot("mmh_plastic_via_factored") != 0 && (layout == MM_LAYOUT_SOA || layout == MM_LAYOUT_AOS);
+    const bool host_fill = tan_or_null && N >= (1 << 14) && *host_tuning_slot("mmh_plastic_via_factored") != 0 && (layout == MM_LAYOUT_SOA || layout == MM_LAYOUT_AOS);
     std::thread filler;
     if (host_fill) {
         const double nu = p->nu, E = p->E;
@@ -398,9 +399,14 @@ int mmh_plastic(const MMPlastic* p, const double* eps, const double* state_in, d
     // dense tangent wanted: send the factored rows of the yielded points over the link and let the host cores expand them chunk by chunk
     // while the next chunks are in flight — same bits as the dense device path (tests/test_compact.py), 217 instead of 451 bytes per
     // point coming down ("mmh_plastic_via_factored" 0 restores the plain dense transfer)
-    if (tan && N > 0 && *host_tuning_slot("mmh_plastic_via_factored") != 0 && (layout == MM_LAYOUT_SOA || layout == MM_LAYOUT_AOS)) {
-        int64_t n_rows = 0;
-        return compact_pipeline(p, eps, state_in, nullptr, sig, flags, iters, MM_ROWS_FACTORED, nullptr, 0, &n_rows, state_out, n_fail, opts, N, layout, tan);
+    // The expansion only pays when it overlaps the transfer of later chunks: batches below 2^18 points go the plain way (measured: 111 vs 228 us
+    // at 10^3 points, 1.25 vs 2.15 ms at 10^5), medium batches are cut into >= 8 chunks (profiles/r02_host_path_dense.log).  "...via_factored" 2
+    // forces the mode for any size (tests).
+    const int via = *host_tuning_slot("mmh_plastic_via_factored");
+    if (tan && N > 0 && via != 0 && (N >= (1 << 18) || via == 2) && (layout == MM_LAYOUT_SOA || layout == MM_LAYOUT_AOS)) {
+        int64_t n_rows = 0, cap8 = N / 8;
+        if (cap8 < (1 << 16)) cap8 = 1 << 16;
+        return compact_pipeline(p, eps, state_in, nullptr, sig, flags, iters, MM_ROWS_FACTORED, nullptr, 0, &n_rows, state_out, n_fail, opts, N, layout, tan, cap8);
     }
     Arr a[7] = {in_arr(eps, 6), in_arr(state_in, 14), out_arr(sig, 6), out_arr(tan, 36), out_arr(state_out, 14),
                 out_arr(flags, 1, 1, false), out_arr(iters, 1, 2, false)};
