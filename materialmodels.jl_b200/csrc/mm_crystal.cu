@@ -57,7 +57,8 @@ template <int LAYOUT> struct DirectAcc {
 #define MM_FIXUP_RANGE 4096
 template <int LAYOUT>
 __global__ void __launch_bounds__(MM_FIXUP_BS) crystal_fixup_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, int32_t* n_fail, const int64_t N,
-                                                                    const int64_t nranges, const int* cnt, const int* idx) {
+                                                                    const int64_t nranges, const int* cnt, const int* idx, const int* n_general) {
+    if (n_general && *n_general == 0) return;                             // nothing was flagged (the usual case)
     __shared__ uint16_t list[MM_FIXUP_RANGE];
     __shared__ int count, next;
     __shared__ double Jsm[144 * MM_FIXUP_BS];                             // every thread's 12x12 Jacobian: column t of a [144][BS] image
@@ -175,15 +176,119 @@ __host__ __device__ inline int crystal_chunk_for(int64_t n, int rw8) {
     return (int)((c + 31) / 32 * 32);
 }
 
+// (0) crystal_presort_kernel — scheduling only, no effect on any result.  The sparse pass costs a warp its LONGEST per-lane candidate list,
+//     and neighbouring points have unrelated lists (configs[3]: 3.0 candidates per lane-pass on average, 7 for the longest of 32), so 15 of 32
+//     lanes are busy.  The candidate count of a point's FIRST pass predicts its mean count over all passes (correlation 0.91 on configs[3],
+//     tools/crystal_sched_sim.py), so each chunk (the unit one Newton warp owns) is re-ordered by that count, heaviest first: the lanes of a warp
+//     then walk lists of similar length (model: 0.39 -> 0.63 of the issued lane-slots useful, 26 % fewer warp-instructions), and the points that
+//     end after one evaluation come last, where they shorten the drain of the chunk.  One block per chunk; stable counting sort on 13 keys
+//     (ballot ranks inside 32-point segments, serial prefix over the <= 32 segments); order[chunk_base + position] = offset of the point in its chunk.
+#define MM_PRESORT_BS 256
+#define MM_ASET_MAX 6      // longest candidate list the active-set pass solves (crystal_iterate_aset)
+template <bool HASQ, int LAYOUT>
+__global__ void __launch_bounds__(MM_PRESORT_BS) crystal_presort_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* order, const int64_t N, const int chunk, uint16_t* hc, int* heavy_idx, int* heavy_cnt) {
+    __shared__ uint16_t segcnt[32][13];         // [segment of 32 points][key]  -> exclusive prefix over the segments
+    __shared__ uint16_t binstart[13];
+    __shared__ int hcount, hoff;                // points of this chunk with more than MM_ASET_MAX candidates, and where their indices go in the global list
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * chunk;
+    const int n = (int)((N - base < chunk) ? (N - base) : chunk);
+    for (int e = threadIdx.x; e < 32 * 13; e += MM_PRESORT_BS) (&segcnt[0][0])[e] = 0;
+    __syncthreads();
+    int key[4], rank[4];                       // chunk <= 1024 = 4 rounds of 256 threads
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int j = r * MM_PRESORT_BS + threadIdx.x;
+        key[r] = -1; rank[r] = 0;
+        if (j - lane >= n) continue;           // whole segment beyond the chunk (warp-uniform)
+        int kk = 13;                           // lanes beyond the end: a key of their own
+        if (j < n) {
+            DirectAcc<LAYOUT> acc(p, N, base + j);
+            const double G2 = 2.0 * k.G;
+            double e6[6], sg[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) e6[c] = acc.template in<0>(c);
+            const double ltr = k.lam * tr6(e6);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) sg[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e6[c] + ltr) : (G2 * e6[c]));
+            double st[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) st[c] = sg[c];
+            unsigned nz = 0;
+            double sumx = 0.0;
+            for (int i = 0; i < 12; ++i) {                         // σ(x0) = σ_trial − Σ x0_i s_i Eᵉ:MS_i, s_i from the trial state
+                const double x0 = acc.template in<1>(30 + i);
+                if (x0 != 0.0) {
+                    nz |= 1u << i;
+                    sumx += x0;
+                    double tau = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) tau += st[c] * k.Pw[i][c];
+                    const double d = tau - acc.template in<1>(18 + i);
+                    const double f = x0 * ((d > 0.0) ? 1.0 : ((d < 0.0) ? -1.0 : 0.0));
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) sg[c] -= f * k.EM[i][c];
+                }
+            }
+            unsigned cand = nz;
+            for (int i = 0; i < 12; ++i) {
+                double tau = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) tau += sg[c] * k.Pw[i][c];
+                double kap = acc.template in<1>(6 + i);
+                if (HASQ) kap += k.b_h * sumx;
+                const double Phi = fabs(tau - acc.template in<1>(18 + i)) - k.tau_y - kap;
+                cand |= (!(Phi <= 0.0)) ? (1u << i) : 0u;
+            }
+            kk = 12 - __popc(cand);                                // heaviest first
+        }
+        const unsigned same = __match_any_sync(0xffffffffu, kk);
+        key[r] = kk;
+        rank[r] = __popc(same & ((1u << lane) - 1u));
+        if (kk < 13 && rank[r] == 0) segcnt[r * (MM_PRESORT_BS / 32) + warp][kk] = (uint16_t)__popc(same);
+    }
+    __syncthreads();
+    if (threadIdx.x < 13) {                    // exclusive prefix over the segments, per key
+        int run = 0;
+        for (int sgm = 0; sgm < 32; ++sgm) { const int c = segcnt[sgm][threadIdx.x]; segcnt[sgm][threadIdx.x] = (uint16_t)run; run += c; }
+        binstart[threadIdx.x] = (uint16_t)run;                      // total of this key, for now
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int q = 0; q < 13; ++q) { const int c = binstart[q]; binstart[q] = (uint16_t)run; run += c; }
+        // the active-set launch starts each chunk behind its heavy points (more than MM_ASET_MAX candidates in the first pass: keys 0 .. 11 − MAX);
+        // their indices go to the global list the sparse launch works off
+        hcount = hc ? binstart[12 - MM_ASET_MAX] : 0;
+        if (hc) { hc[blockIdx.x] = (uint16_t)hcount; hoff = hcount ? atomicAdd(heavy_cnt, hcount) : 0; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int j = r * MM_PRESORT_BS + threadIdx.x;
+        if (key[r] >= 0 && key[r] < 13) {
+            const int pos = binstart[key[r]] + segcnt[r * (MM_PRESORT_BS / 32) + warp][key[r]] + rank[r];
+            order[base + pos] = (uint16_t)j;
+            if (pos < hcount) heavy_idx[hoff + pos] = (int)(base + j);
+        }
+    }
+}
+
+// scheduling data of one Newton launch (all optional): the chunk-local order, the per-chunk count of heavy points the launch skips, the global list
+// that collects points handed over to the sparse launch, and `scatter` = the launch works off such a list (idx / cnt) and writes each point's
+// results at the point's own index (the wrappers' batches pack them by list position instead)
+struct CrystalSched { const uint16_t* order; const uint16_t* hc; int* heavy_idx; int* heavy_cnt; int scatter; int* n_general; };
+
 // SPARSE (integer m only): the per-lane active-list pass crystal_iterate_sparse — the slip-system tables are copied into shared memory
 // ([component][system], behind the scratch columns) because every lane walks its own list of systems
-template <bool HASQ, bool INTPOW, int LAYOUT, int BS, bool SPARSE>
+template <bool HASQ, bool INTPOW, int LAYOUT, int BS, int PASS>      // PASS: 0 dense, 1 sparse, 2 active-set (q = 0)
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_MINBLOCKS)
-crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, int chunk, const int thresh, const int* cnt, const int* idx, const int rw8) {
+crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, int chunk, const int thresh, const int* cnt, const int* idx, const int rw8,
+                      const CrystalSched sched) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     double* tab = sm_scratch + MM_CRYSTAL_SCRATCH * BS;
-    if (SPARSE) {
+    if (PASS != 0) {
         for (int e = threadIdx.x; e < MM_CRYSTAL_TAB; e += BS) crystal_fill_tab(k, tab, e);
         __syncthreads();
     }
@@ -192,9 +297,12 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
     const int64_t warp_id = (int64_t)blockIdx.x * (BS / 32) + (threadIdx.x >> 5);
     const int64_t Nc = cnt ? (int64_t)*cnt : N;               // points in use (N stays the SoA stride)
     if (cnt) chunk = crystal_chunk_for(Nc, rw8);              // batch: the chunk follows the device-side count (the grid covers N / 64 warps)
-    int64_t next = warp_id * chunk;
-    const int64_t end = (next + chunk < Nc) ? (next + chunk) : Nc;
+    const int64_t nwarps = (int64_t)gridDim.x * (BS / 32);
     CrystalLane L;
+    for (int64_t cid = warp_id; cid * chunk < Nc; cid += nwarps) {   // one trip, except for a scatter launch (one resident wave walks all chunks of its list)
+    const int64_t chunk0 = cid * chunk;
+    int64_t next = chunk0 + (sched.hc ? (int64_t)sched.hc[cid] : 0);   // the chunk's heavy points (sorted first) belong to the sparse launch
+    const int64_t end = (chunk0 + chunk < Nc) ? (chunk0 + chunk) : Nc;
     bool has_work = false, finished = false;
     int64_t my = 0;
     for (;;) {
@@ -203,8 +311,9 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
             if (!has_work) {
                 const int64_t cand = next + __popc(idle & ((1u << lane) - 1u));
                 if (cand < end) {
-                    my = cand;                                   // output slot; the inputs of a list entry stay where the point is
-                    DirectAcc<LAYOUT> acc(p, N, my, idx ? (int64_t)idx[cand] : cand);
+                    // output slot; the inputs of a wrapper's list entry stay where the point is (order: the chunk's points, heaviest first)
+                    my = sched.scatter ? (int64_t)idx[cand] : (sched.order ? (chunk0 + sched.order[cand]) : cand);
+                    DirectAcc<LAYOUT> acc(p, N, my, (idx && !sched.scatter) ? (int64_t)idx[cand] : my);
                     crystal_init(k, acc, scr, L);
                     has_work = true; finished = false;
                 }
@@ -213,20 +322,29 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
         }
         const unsigned working = __ballot_sync(FULL, has_work);
         if (working == 0u) break;
-        if (has_work && !finished) {
-            if (SPARSE) finished = crystal_iterate_sparse<HASQ, false>(k, tab, scr, L);
-            else        finished = crystal_iterate<HASQ, INTPOW, false>(k, scr, L);
+        if (PASS == 2) {
+            const unsigned lanes = __ballot_sync(FULL, has_work && !finished);
+            if (has_work && !finished) finished = crystal_iterate_aset(k, tab, scr, L, lanes);
+        } else if (has_work && !finished) {
+            if (PASS == 1) finished = crystal_iterate_sparse<HASQ, false>(k, tab, scr, L);
+            else           finished = crystal_iterate<HASQ, INTPOW, false>(k, scr, L);
         }
         const unsigned fin = __ballot_sync(FULL, has_work && finished);
         const unsigned iterating = working & ~fin;
         if (fin != 0u && (__popc(fin) >= thresh || iterating == 0u || next >= end)) {
             if (has_work && finished) {
-                if (!L.bad) crystal_hand_over<LAYOUT>(p, xbuf, N, my, scr);
-                active[my] = (uint16_t)(L.bad ? MM_ACTIVE_NEEDS_GENERAL : (L.converged ? 0u : MM_ACTIVE_FAILED));
-                if (iters) iters[my] = (uint16_t)(L.bad ? 0 : (L.iters > 65535 ? 65535 : L.iters));
+                if (PASS == 2 && L.big) {
+                    sched.heavy_idx[atomicAdd(sched.heavy_cnt, 1)] = (int)my;      // redone from its first pass by the sparse launch; nothing written
+                } else {
+                    if (!L.bad) crystal_hand_over<LAYOUT>(p, xbuf, N, my, scr);
+                    else if (sched.n_general) atomicAdd(sched.n_general, 1);
+                    active[my] = (uint16_t)(L.bad ? MM_ACTIVE_NEEDS_GENERAL : (L.converged ? 0u : MM_ACTIVE_FAILED));
+                    if (iters) iters[my] = (uint16_t)(L.bad ? 0 : (L.iters > 65535 ? 65535 : L.iters));
+                }
                 has_work = false; finished = false;
             }
         }
+    }
     }
 }
 
@@ -238,7 +356,7 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
 #endif
 template <int LAYOUT, int BS>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_PHASED_MINBLOCKS)
-crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, int chunk, const int thresh, const int* cnt, const int* idx, const int rw8) {
+crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, int chunk, const int thresh, const int* cnt, const int* idx, const int rw8, int* n_general) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     const unsigned FULL = 0xffffffffu;
@@ -276,6 +394,7 @@ crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* ac
         if (fin != 0u && (__popc(fin) >= thresh || iterating == 0u || next >= end)) {
             if (has_work && finished) {
                 if (!L.bad) crystal_hand_over<LAYOUT>(p, xbuf, N, my, scr);
+                else if (n_general) atomicAdd(n_general, 1);
                 active[my] = (uint16_t)(L.bad ? MM_ACTIVE_NEEDS_GENERAL : (L.converged ? 0u : MM_ACTIVE_FAILED));
                 if (iters) iters[my] = (uint16_t)(L.bad ? 0 : (L.iters > 65535 ? 65535 : L.iters));
                 has_work = false; finished = false;
@@ -292,7 +411,7 @@ crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* ac
 #endif
 template <bool HASQ, bool INTPOW, int LAYOUT, int BS>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_FINISH_MINBLOCKS)
-crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, int32_t* n_fail, const double* xbuf, const int64_t N, const int* cnt, const int* idx) {
+crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, int32_t* n_fail, const double* xbuf, const int64_t N, const int* cnt, const int* idx, int* n_general) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
@@ -302,23 +421,30 @@ crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, in
     DirectAccRW<LAYOUT> acc(p, N, i, idx ? (int64_t)idx[i] : i, xbuf);
     bool fallback = false;
     unsigned mask = crystal_finish_from_x<HASQ, INTPOW>(k, acc, scr, (status & MM_ACTIVE_FAILED) == 0, &fallback);
-    if (fallback) mask = MM_ACTIVE_NEEDS_GENERAL;
+    if (fallback) { mask = MM_ACTIVE_NEEDS_GENERAL; if (n_general) atomicAdd(n_general, 1); }
     active[i] = (uint16_t)mask;
     if ((mask & MM_ACTIVE_FAILED) && n_fail) atomicAdd(n_fail, 1);
 }
 
 template <bool HASQ, bool INTPOW, int LAYOUT>
-int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st, const int* cnt, const int* idx) {
+int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st, const int* cnt, const int* idx, int* n_general) {
     constexpr int BS = MM_CRYSTAL_BS, FBS = MM_CRYSTAL_FINISH_BS;
     constexpr size_t smem = (size_t)(MM_CRYSTAL_SCRATCH * BS + MM_CRYSTAL_TAB) * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
     // "crystal_variant" (mm_set_tuning / MM_CRYSTAL_VARIANT): 0 or default = dense branch-free pass, 1 = sparse per-lane pass, 2 = phased pass.
     // Measured on configs[3] (1e7 points, step B, profiles/r02_crystal_variants.jsonl + r02_crystal_*_ncu.txt): dense 21.9 ms, sparse 21.9 ms,
     // phased 25.6 ms — the sparse pass does HALF the thread-level work of the dense one but leaves 15 of 32 lanes active per instruction, the
     // phased pass (unrolled, constant-bank operands) outgrows the 32 KB instruction cache (23 % no_instruction stalls).  Tests run all three.
-    const bool sparse = INTPOW && crystal_knobs().variant == 1;
-    static SmemOptIn optin_newton, optin_newton_sparse, optin_finish;
-    if (int rc = ensure_smem(optin_newton, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, false>, smem, "mm_crystal")) return rc;
-    if (INTPOW) if (int rc = ensure_smem(optin_newton_sparse, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, INTPOW>, smem, "mm_crystal")) return rc;
+    // 3 / 4 = sparse / dense pass over chunks re-ordered by first-pass candidate count (crystal_presort_kernel); 5 = active-set pass over re-ordered
+    // chunks (the DEFAULT for integer m, q = 0), 6 = active-set pass in the natural order.  With cross hardening 5 / 6 run the sparse pass.
+    const int variant = crystal_knobs().variant < 0 ? (HASQ ? 0 : 6) : crystal_knobs().variant;      // cross hardening keeps the dense pass by default
+    constexpr int SP = INTPOW ? 1 : 0, AS = (INTPOW && !HASQ) ? 2 : SP;     // instantiations that do not apply collapse onto one that does
+    // the wrappers' index-list batches (cnt / idx) keep the dense pass unless the sparse one is asked for: the active-set launch needs its hand-over list
+    const int pass = !INTPOW ? 0 : ((variant == 1 || variant == 3) ? 1 : (((variant == 5 || variant == 6) && !cnt && !idx) ? AS : 0));
+    const bool presort = INTPOW && (variant == 3 || variant == 4 || variant == 5) && !cnt && !idx;
+    static SmemOptIn optin_newton, optin_newton_sparse, optin_newton_aset, optin_finish;
+    if (int rc = ensure_smem(optin_newton, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, 0>, smem, "mm_crystal")) return rc;
+    if (int rc = ensure_smem(optin_newton_sparse, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, SP>, smem, "mm_crystal")) return rc;
+    if (int rc = ensure_smem(optin_newton_aset, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, AS>, smem, "mm_crystal")) return rc;
     if (int rc = ensure_smem(optin_finish, crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS>, fsmem, "mm_crystal")) return rc;
     // six blocks of scratch columns need 210 KB of the SM's 228 KB: ask for the largest shared-memory carve-out (with the default heuristic
     // ncu reported a shared-memory limit of 5 blocks, i.e. 10 instead of 12 resident warps)
@@ -326,8 +452,9 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     {
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !carve[dev]) {
-            cudaFuncSetAttribute(crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (INTPOW) cudaFuncSetAttribute(crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, INTPOW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, SP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, AS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaGetLastError();
             carve[dev] = true;
@@ -340,7 +467,27 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     if (kn.chunk > 0) chunk = kn.chunk;
     const int64_t warps = cnt ? (N + 63) / 64 : (N + chunk - 1) / chunk;      // device-side count: cover the smallest chunk, surplus warps exit at once
     const int64_t blocks = (warps + (BS / 32) - 1) / (BS / 32);
-    if (INTPOW && !HASQ && crystal_knobs().variant == 2) {          // "crystal_variant" 2: the phased pass (integer m, q = 0) — measured slower, kept for A/B
+    // workspace of the scheduling data (stream-ordered, freed below): order[N] u16, hc[chunks] u16, heavy_idx[N] i32, heavy_cnt i32
+    uint16_t* order = nullptr; uint16_t* hc = nullptr; int* heavy_idx = nullptr; int* heavy_cnt = nullptr;
+    char* ws = nullptr;
+    const bool split = (pass == 2) && !cnt && !idx;                 // active-set launch + sparse launch over the points it hands over
+    const bool sorted = presort && chunk <= 1024 && N > 0;
+    const int64_t nchunks = (N + chunk - 1) / chunk;
+    if (sorted || split) {
+        const size_t o_order = 0, o_hc = o_order + (((size_t)N * 2 + 15) & ~(size_t)15), o_idx = o_hc + (((size_t)nchunks * 2 + 15) & ~(size_t)15),
+                     o_cnt = o_idx + (split ? (size_t)N * 4 : 0), total = o_cnt + 16;
+        cudaError_t e = ws_alloc_async((void**)&ws, total, st);
+        if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_crystal: cudaMallocAsync: %s", cudaGetErrorString(e));
+        if (sorted) order = (uint16_t*)(ws + o_order);
+        if (sorted && split) hc = (uint16_t*)(ws + o_hc);
+        if (split) { heavy_idx = (int*)(ws + o_idx); heavy_cnt = (int*)(ws + o_cnt); cudaMemsetAsync(heavy_cnt, 0, sizeof(int), st); }
+    }
+    if (sorted) {                                                    // chunk-local re-ordering by first-pass candidate count (scheduling only)
+        crystal_presort_kernel<HASQ, LAYOUT><<<(unsigned)nchunks, MM_PRESORT_BS, 0, st>>>(k, ptrs, order, N, (int)chunk, hc, heavy_idx, heavy_cnt);
+        if (int rc = check_launch("mm_crystal (presort kernel)")) { cudaFreeAsync(ws, st); return rc; }
+    }
+    const CrystalSched sched{order, hc, heavy_idx, heavy_cnt, 0, n_general};
+    if (INTPOW && !HASQ && variant == 2) {          // "crystal_variant" 2: the phased pass (integer m, q = 0) — measured slower, kept for A/B
         constexpr size_t psmem = (size_t)MM_CRYSTAL_SCRATCH_PHASED * BS * sizeof(double);
         static SmemOptIn optin_phased;
         if (int rc = ensure_smem(optin_phased, crystal_newton_phased_kernel<LAYOUT, BS>, psmem, "mm_crystal")) return rc;
@@ -353,19 +500,29 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
         }
         CrystalNK nk;
         make_crystal_nk(nk, k);
-        crystal_newton_phased_kernel<LAYOUT, BS><<<(unsigned)blocks, BS, psmem, st>>>(nk, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8);
-    } else if (sparse) crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, INTPOW><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8);
-    else        crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, false><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8);
+        crystal_newton_phased_kernel<LAYOUT, BS><<<(unsigned)blocks, BS, psmem, st>>>(nk, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8, n_general);
+    } else if (pass == 2) crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, AS><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8, sched);
+    else if (pass == 1)   crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, SP><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8, sched);
+    else                  crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, 0><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8, sched);
     int rc = check_launch("mm_crystal (Newton kernel)");
+    if (rc == 0 && split) {
+        // the points the active-set launch did not take (heavy from the start, or grown past MM_ASET_MAX candidates): the sparse pass over the
+        // device-side list, one resident wave of warps walking its chunks, results written at each point's own index
+        const CrystalSched sc2{nullptr, nullptr, nullptr, nullptr, 1, n_general};
+        const int64_t wave = (int64_t)sm_count() * MM_CRYSTAL_MINBLOCKS;
+        crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, SP><<<(unsigned)(wave < blocks ? wave : blocks), BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, heavy_cnt, heavy_idx, rw8, sc2);
+        rc = check_launch("mm_crystal (Newton kernel, heavy points)");
+    }
+    if (ws) cudaFreeAsync(ws, st);
     if (rc) return rc;
-    crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS><<<(unsigned)((N + FBS - 1) / FBS), FBS, fsmem, st>>>(k, ptrs, active, n_fail, xbuf, N, cnt, idx);
+    crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS><<<(unsigned)((N + FBS - 1) / FBS), FBS, fsmem, st>>>(k, ptrs, active, n_fail, xbuf, N, cnt, idx, n_general);
     return check_launch("mm_crystal (finish kernel)");
 }
 
 template <bool HASQ, int LAYOUT>
-int launch_crystal_by_exponent(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st, const int* cnt, const int* idx) {
-    return k.m_int ? launch_crystal_two_kernel<HASQ, true, LAYOUT>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx)
-                   : launch_crystal_two_kernel<HASQ, false, LAYOUT>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx);
+int launch_crystal_by_exponent(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st, const int* cnt, const int* idx, int* n_general) {
+    return k.m_int ? launch_crystal_two_kernel<HASQ, true, LAYOUT>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx, n_general)
+                   : launch_crystal_two_kernel<HASQ, false, LAYOUT>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx, n_general);
 }
 
 int launch_crystal_general(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, int64_t N, int layout, cudaStream_t st) {
@@ -379,17 +536,26 @@ template <bool HASQ>
 int launch_crystal_structured(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, int layout, cudaStream_t st,
                               const int* cnt = nullptr, const int* idx = nullptr) {
     if (N == 0) return MM_OK;
+    if (layout != 0 && layout != 1) return set_error(MM_ERR_ARG, "mm_crystal: unknown layout %d", layout);
+    // how many points the Newton / finish kernels left to the fix-up pass: none on the benchmark configuration, and then the fix-up blocks exit at
+    // once instead of scanning the flag array (0.21 ms per 1e7 points)
+    int* n_general = nullptr;
+    {
+        cudaError_t e = ws_alloc_async((void**)&n_general, 16, st);
+        if (e != cudaSuccess) return set_error(MM_ERR_CUDA, "mm_crystal: cudaMallocAsync: %s", cudaGetErrorString(e));
+        cudaMemsetAsync(n_general, 0, sizeof(int), st);
+    }
     int rc;
-    if (layout == 0)      rc = launch_crystal_by_exponent<HASQ, 0>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx);
-    else if (layout == 1) rc = launch_crystal_by_exponent<HASQ, 1>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx);
-    else return set_error(MM_ERR_ARG, "mm_crystal: unknown layout %d", layout);
-    if (rc) return rc;
+    if (layout == 0) rc = launch_crystal_by_exponent<HASQ, 0>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx, n_general);
+    else             rc = launch_crystal_by_exponent<HASQ, 1>(k, active, iters, n_fail, ptrs, xbuf, N, st, cnt, idx, n_general);
+    if (rc) { cudaFreeAsync(n_general, st); return rc; }
     const int64_t nranges = (N + MM_FIXUP_RANGE - 1) / MM_FIXUP_RANGE;
     const int per_sm = crystal_knobs().fixup_per_sm > 0 ? crystal_knobs().fixup_per_sm : 5;
     int64_t blocks = (int64_t)sm_count() * per_sm;
     if (blocks > nranges) blocks = nranges;
-    if (layout == 0) crystal_fixup_kernel<0><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges, cnt, idx);
-    else             crystal_fixup_kernel<1><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges, cnt, idx);
+    if (layout == 0) crystal_fixup_kernel<0><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges, cnt, idx, n_general);
+    else             crystal_fixup_kernel<1><<<(unsigned)blocks, MM_FIXUP_BS, 0, st>>>(k, ptrs, active, iters, n_fail, N, nranges, cnt, idx, n_general);
+    cudaFreeAsync(n_general, st);
     return check_launch("mm_crystal (fix-up pass)");
 }
 

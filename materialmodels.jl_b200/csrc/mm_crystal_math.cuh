@@ -358,6 +358,7 @@ struct CrystalLane {
     int it;                // loop index of nonlinear_solver.jl:53 (1-based) of the NEXT evaluation
     int iters;             // number of x updates done
     bool converged, bad;
+    bool big;              // active-set pass: the point left the small route (list longer than 6 / zero frozen sign) -> redo it through the sparse pass
     bool flip;             // some ACTIVE system has sgn_i != s_i at the last evaluation
 };
 
@@ -426,7 +427,7 @@ MM_HD void crystal_init(const KT& k, Acc& acc, Scr& scr, CrystalLane& L) {
         if (d > 0.0) L.spos |= (1u << i);
         if (d < 0.0) L.sneg |= (1u << i);
     }
-    L.mask = 0; L.nz = nz; L.cand = 0xFFFu; L.it = 1; L.iters = 0; L.converged = false; L.bad = false; L.flip = false;
+    L.mask = 0; L.nz = nz; L.cand = 0xFFFu; L.it = 1; L.iters = 0; L.converged = false; L.bad = false; L.big = false; L.flip = false;
 }
 
 #ifndef MM_CRYSTAL_UNROLL
@@ -613,9 +614,11 @@ MM_HD bool crystal_iterate(const CrystalK& k, Scr& scr, CrystalLane& L) {
 //   4. the update for the candidates only — every other system has R_i = −t*·0, g_i = 0, so x_i stays 0.
 // Everything skipped is an exact zero in the dense pass, so the iterates are the same numbers up to the flush of 1e-16-level noise
 // described at the update (tests: masks, counts and values against the oracle, exactly as for the dense pass).
-// tab: [0,72) Pw transposed (tab[c*12 + i]), [72,144) Eᵉ:MS transposed.
-constexpr int MM_CRYSTAL_TAB = 144;
-MM_HD void crystal_fill_tab(const CrystalK& k, double* tab, int e) {      // e in [0,144): one entry (kernel threads fill it cooperatively)
+// tab: [0,72) Pw transposed (tab[c*12 + i]), [72,144) Eᵉ:MS transposed, [144,288) G[i*12 + j] = Pw_i·Eᵉ·Pw_j, symmetrised bit for bit
+// (G[i][j] = Gm[min][max]) — the active-set pass below gathers it pair by pair.
+constexpr int MM_CRYSTAL_TAB = 288, GTAB = 144;
+MM_HD void crystal_fill_tab(const CrystalK& k, double* tab, int e) {      // e in [0,288): one entry (kernel threads fill it cooperatively)
+    if (e >= GTAB) { const int i = (e - GTAB) / 12, j = (e - GTAB) % 12; tab[e] = (i <= j) ? k.Gm[i][j] : k.Gm[j][i]; return; }
     const int c = (e % 72) / 12, i = e % 12;
     tab[e] = e < 72 ? k.Pw[i][c] : k.EM[i][c];
 }
@@ -623,9 +626,10 @@ MM_HD void crystal_fill_tab(const CrystalK& k, double* tab, int e) {      // e i
 #if defined(MM_CRYSTAL_STATS) && !defined(__CUDA_ARCH__)
 void mm_crystal_stats_pass(unsigned nz, unsigned cand);       // host-twin instrumentation (tests/hosttwin)
 #endif
+template <bool HASQ, bool KEEPK, class Scr> MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L, const unsigned cand, const double kq);
 template <bool HASQ, bool KEEPK, class Scr>
 MM_HD bool crystal_iterate_sparse(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L) {
-    double yr[6], nrm2 = 0.0, sumx = 0.0;
+    double sumx = 0.0;
     // 1. σ = σ_trial − Σ_{x_j != 0} x_j s_j Eᵉ:MS_j                                        :131
 #pragma unroll
     for (int c = 0; c < 6; ++c) L.sig[c] = scr(SIGT + c);
@@ -657,7 +661,17 @@ MM_HD bool crystal_iterate_sparse(const CrystalK& k, const double* tab, Scr& scr
 #if defined(MM_CRYSTAL_STATS) && !defined(__CUDA_ARCH__)
     mm_crystal_stats_pass(L.nz, cand);
 #endif
-    // 3. full chain for the candidates
+    return crystal_sparse_tail<HASQ, KEEPK>(k, tab, scr, L, cand, kq);
+}
+
+// steps 3 and 4 of the sparse pass (6x6 SPD route): the chains of the candidates, M, the test, the update
+template <bool HASQ, bool KEEPK, class Scr>
+MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L, const unsigned cand, const double kq) {
+    double yr[6], nrm2 = 0.0;
+    // 3. full chain for the candidates — TWO list entries per trip: one chain is a ~30-level dependency ladder (reciprocal -> α -> Φ -> power ->
+    //    D -> reciprocal -> rank-1 update) and three resident warps per sub-partition cannot fill the FP64 pipe with one ladder each.  A lane whose
+    //    list has an odd length runs its last entry twice; the second copy contributes exact zeros (w = 0, s·D⁻¹r = 0, R² = 0) and rewrites the
+    //    same g / D⁻¹r, so every sum sees the same terms in the same order as one entry per trip.
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
@@ -667,52 +681,64 @@ MM_HD bool crystal_iterate_sparse(const CrystalK& k, const double* tab, Scr& scr
     unsigned mask = 0;
     bool bad = false, flip = false;
     const int npow = k.m_int - 1;
-    for (unsigned m = cand; m != 0u; m &= m - 1u) {
-        const int i = __ffs_(m);
-        double pw[6];
+    for (unsigned m = cand; m != 0u;) {
+        int ii[2];
+        ii[0] = __ffs_(m); m &= m - 1u;
+        const bool two = m != 0u;
+        ii[1] = two ? __ffs_(m) : ii[0]; m &= m - 1u;
+        double pw[2][6], w[2], srD[2], spD[2], R2[2];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) pw[c] = tab[c * 12 + i];
-        const double si = crystal_sign(L, i), xi = scr(XS + i);
-        double kap = scr(i) + k.a_h * xi;                                               // :127 with H = a I + b 11ᵀ
-        if (HASQ) kap += kq;
-        const double iden = rcp_nc(1.0 + k.hk_ai * xi);
-        const double al = (scr(12 + i) + k.H_kin * xi * si) * iden;                     // :128
-        double tau = 0.0;
+        for (int u = 0; u < 2; ++u) {
+            const int i = ii[u];
+            const bool live = (u == 0) | two;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) tau += L.sig[c] * pw[c];
-        const double red = tau - al;
-        const double sgn = sign_of(red);
-        const double Phi = fabs(red) - k.tau_y - kap;                                    // :110
-        const bool act = Phi > 0.0;
-        const double xx = act ? Phi * k.isc : Phi * 0.0;
-        const double pw1 = (npow == 9) ? powc_<9>(xx) : powi6_(xx, npow);
-        const double Ri = k.dt * (pw1 * xx) - k.t_star * xi;                            // :111
-        const double p = k.dtm_sc * pw1;
-        mask |= act ? (1u << i) : 0u;
-        flip = flip | (act & (sgn != si));
-        const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
-        const double dD = k.t_star + p * (sgn * dal + k.a_h);
-        bad = bad | (act & !(dD >= 0.25 * k.t_star));
-        const double invD = act ? -rcp_nc(dD) : k.mits;
-        nrm2 += Ri * Ri;
-        const double ci = p * sgn;
-        const double rD = Ri * invD;
-        const double g = ci * invD;
-        scr(24 + i) = g; scr(36 + i) = rD;
-        const double w = -si * g;
+            for (int c = 0; c < 6; ++c) pw[u][c] = tab[c * 12 + i];
+            const double si = crystal_sign(L, i), xi = scr(XS + i);
+            double kap = scr(i) + k.a_h * xi;                                           // :127 with H = a I + b 11ᵀ
+            if (HASQ) kap += kq;
+            const double iden = rcp_nc(1.0 + k.hk_ai * xi);
+            const double al = (scr(12 + i) + k.H_kin * xi * si) * iden;                 // :128
+            double tau = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            const double wa = w * pw[a];
-#pragma unroll
-            for (int b = 0; b <= a; ++b) L.K[a * 6 + b] += wa * pw[b];
+            for (int c = 0; c < 6; ++c) tau += L.sig[c] * pw[u][c];
+            const double red = tau - al;
+            const double sgn = sign_of(red);
+            const double Phi = fabs(red) - k.tau_y - kap;                                // :110
+            const bool act = Phi > 0.0;
+            const double xx = act ? Phi * k.isc : Phi * 0.0;
+            const double pw1 = (npow == 9) ? powc_<9>(xx) : powi6_(xx, npow);
+            const double Ri = k.dt * (pw1 * xx) - k.t_star * xi;                        // :111
+            const double p = k.dtm_sc * pw1;
+            mask |= (act & live) ? (1u << i) : 0u;
+            flip = flip | (act & (sgn != si));
+            const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
+            const double dD = k.t_star + p * (sgn * dal + k.a_h);
+            bad = bad | (act & !(dD >= 0.25 * k.t_star));
+            const double invD = act ? -rcp_nc(dD) : k.mits;
+            const double ci = p * sgn;
+            const double rD = Ri * invD;
+            const double g = ci * invD;
+            scr(24 + i) = g; scr(36 + i) = rD;
+            R2[u] = live ? Ri : 0.0;                                                    // squared at the sum below (same fma as one entry per trip)
+            w[u] = live ? -si * g : 0.0;
+            srD[u] = live ? si * rD : 0.0;
+            spD[u] = (HASQ && live) ? si * (k.b_h * p * invD) : 0.0;
         }
-        const double srD = si * rD;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) yr[c] += srD * pw[c];
-        if (HASQ) {
-            const double spD = si * (k.b_h * p * invD);
+        for (int u = 0; u < 2; ++u) {
+            nrm2 += R2[u] * R2[u];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) L.yp[c] += spD * pw[c];
+            for (int a = 0; a < 6; ++a) {
+                const double wa = w[u] * pw[u][a];
+#pragma unroll
+                for (int b = 0; b <= a; ++b) L.K[a * 6 + b] += wa * pw[u][b];
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) yr[c] += srD[u] * pw[u][c];
+            if (HASQ) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) L.yp[c] += spD[u] * pw[u][c];
+            }
         }
     }
     L.mask = mask;
@@ -752,28 +778,232 @@ MM_HD bool crystal_iterate_sparse(const CrystalK& k, const double* tab, Scr& scr
         fac = su * fast_rcp(1.0 - sv);
     }
     unsigned nz = 0;
-    for (unsigned m = cand; m != 0u; m &= m - 1u) {
-        const int i = __ffs_(m);
-        const double g = scr(24 + i);
-        double d = scr(36 + i);
-        double du = 0.0, dv = 0.0;
+    for (unsigned m = cand; m != 0u;) {                                                // two list entries per trip, as above (an odd tail entry is redone from the same x)
+        int ii[2];
+        ii[0] = __ffs_(m); m &= m - 1u;
+        ii[1] = (m != 0u) ? __ffs_(m) : ii[0]; m &= m - 1u;
+        double xn[2];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) { du += tab[c * 12 + i] * yr[c]; if (HASQ) dv += tab[c * 12 + i] * ypl[c]; }
-        d += g * du;
-        if (HASQ) d += (g * dv - k.b_h * fabs(g)) * fac;
-        const double xo = scr(XS + i);
-        double xn = xo - d;
-        // An INACTIVE system's exact Newton step is x_i -> 0 (R_i = −t* x_i, J_ii = −t*); in floating point it lands on rounding noise
-        // ~1e-16 |x_i| which would keep the system on the candidate list while it decays over the next ~20 passes.  Noise of that size is
-        // flushed to the exact zero the step means (the reference's LU leaves a different 1e-16-level noise there; nothing depends on it).
-        if (!((mask >> i) & 1u) && fabs(xn) <= 1e-14 * fabs(xo)) xn = 0.0;
-        scr(XS + i) = xn;
-        if (xn != 0.0) nz |= (1u << i);
+        for (int u = 0; u < 2; ++u) {
+            const int i = ii[u];
+            const double g = scr(24 + i);
+            double d = scr(36 + i);
+            double du = 0.0, dv = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { du += tab[c * 12 + i] * yr[c]; if (HASQ) dv += tab[c * 12 + i] * ypl[c]; }
+            d += g * du;
+            if (HASQ) d += (g * dv - k.b_h * fabs(g)) * fac;
+            const double xo = scr(XS + i);
+            xn[u] = xo - d;
+            // An INACTIVE system's exact Newton step is x_i -> 0 (R_i = −t* x_i, J_ii = −t*); in floating point it lands on rounding noise
+            // ~1e-16 |x_i| which would keep the system on the candidate list while it decays over the next ~20 passes.  Noise of that size is
+            // flushed to the exact zero the step means (the reference's LU leaves a different 1e-16-level noise there; nothing depends on it).
+            if (!((mask >> i) & 1u) && fabs(xn[u]) <= 1e-14 * fabs(xo)) xn[u] = 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            scr(XS + ii[u]) = xn[u];
+            if (xn[u] != 0.0) nz |= (1u << ii[u]);
+        }
     }
     L.nz = nz;
     L.iters = L.it;
     L.it += 1;
     return false;
+}
+
+// ---- ACTIVE-SET pass (integer m, q = 0): the Newton kernel's default ------------------------------------------------------------
+// The sparse pass still pays, per Newton pass, for the 6x6 machinery of the Woodbury split: 27 FP64 instructions per candidate to accumulate
+// M, 6 for y_r, 6 for Pw_i·z, and a 6x6 LDLᵀ + solve (≈ 160, a ladder of six dependent reciprocals) — although on configs[3] a pass has
+// 3.0 candidates on average, at most 2 in 47 %, 4 in 83 % and 6 in 96 % of all passes (tools/crystal_sched_sim.py).  Here the Newton step is
+// solved where it is small: rows of systems off the candidate list are D_ii δ_i = r_i = 0, and on the list {a_1..a_k}
+//        Σ_v (δ_uv + w_u G[a_u][a_v]) δ'_v = s_u (D⁻¹r)_u ,   δ'_v = s_v δ_v ,  w_u = −s_u c_u / D_uu ,  G = Pw Eᵉ Pwᵀ   (table)
+// — J restricted to the list, rows scaled by D⁻¹ and by the frozen signs (J_ij = D_ii δ_ij − c_i s_j G_ij, §"Register-resident fast path").
+// I + W G is a row scaling of the SPD matrix W⁻¹ + G, so elimination without pivoting is as stable as Cholesky (pivots >= 1 while every
+// w_u >= 0); a pivot that is not safely positive sends the point to the pivoted general path like the LDLᵀ guard does.  No reciprocal of w
+// is taken: a barely active system (w ~ 1e-200) is simply a row e_u.  τ_i = σ:Pw_i is parked by the yield test, so the chains need no table
+// rows at all; they leave g_i and (D⁻¹r)_i in the scratch slots of their system.  The solve is done at ONE size per warp — 2, 4 or 6, the
+// smallest that holds the longest list of the warp (a warp-uniform choice: no lane ever runs two routes) — in registers with static
+// indexing; a lane with a shorter list pads with rows e_u (w = 0, right-hand side 0: exact no-ops in the elimination, so a point's result
+// does not depend on its neighbours).  A point with a list longer than 6 in some pass (7 % of the points of configs[3]: they are known from
+// the presort and never enter this pass, bar the few whose list grows), or with a candidate whose frozen sign is 0, is done by the sparse
+// pass instead: the kernel around this pass carries no 6x6 code at all (3 360 -> 2 300 instructions; the instruction cache holds 2 000).
+// Same Newton iterates up to rounding (masks and counts against the oracle: tests).
+// `lanes`: the lanes of the warp that execute this call together (device: ballot of the caller's condition).
+template <int KM, class Scr>
+MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const unsigned cand, const unsigned mask) {
+    int a[KM];
+    double w[KM], b[KM];
+    unsigned rest = cand;
+#pragma unroll
+    for (int u = 0; u < KM; ++u) {
+        const bool live = rest != 0u;
+        a[u] = live ? __ffs_(rest) : 0;
+        rest &= rest - 1u;
+        const double si = crystal_sign(L, a[u]);
+        w[u] = live ? -si * scr(24 + a[u]) : 0.0;
+        b[u] = live ? si * scr(36 + a[u]) : 0.0;
+    }
+    double Nm[KM][KM];
+#pragma unroll
+    for (int u = 0; u < KM; ++u)
+#pragma unroll
+        for (int v = u; v < KM; ++v) Nm[u][v] = tab[GTAB + a[u] * 12 + a[v]];           // G is symmetric bit for bit (crystal_fill_tab)
+#pragma unroll
+    for (int u = 0; u < KM; ++u)
+#pragma unroll
+        for (int v = 0; v < u; ++v) Nm[u][v] = w[u] * Nm[v][u];                         // the upper triangle still holds G here
+#pragma unroll
+    for (int u = 0; u < KM; ++u)
+#pragma unroll
+        for (int v = u; v < KM; ++v) Nm[u][v] = (u == v) ? fma(w[u], Nm[u][v], 1.0) : w[u] * Nm[u][v];
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < KM; ++q) {
+        const double d = Nm[q][q];
+        ok = ok & (d > 1e-200) & (d < 1e200);
+        const double id = rcp_nc(d);
+        Nm[q][q] = id;
+#pragma unroll
+        for (int i = q + 1; i < KM; ++i) {
+            const double l = Nm[i][q] * id;
+#pragma unroll
+            for (int j = q + 1; j < KM; ++j) Nm[i][j] -= l * Nm[q][j];
+            b[i] -= l * b[q];
+        }
+    }
+    if (!ok) { L.bad = true; return true; }
+#pragma unroll
+    for (int i = KM - 1; i >= 0; --i) {
+        double t = b[i];
+#pragma unroll
+        for (int j = i + 1; j < KM; ++j) t -= Nm[i][j] * b[j];
+        b[i] = t * Nm[i][i];
+    }
+    // x -= δ on the list (δ_u = s_u δ'_u); every other system keeps x_i = 0
+    unsigned nz = 0;
+    rest = cand;
+#pragma unroll
+    for (int u = 0; u < KM; ++u) {
+        if (rest != 0u) {
+            const int i = a[u];
+            const double xo = scr(XS + i);
+            double xn = xo - crystal_sign(L, i) * b[u];
+            if (!((mask >> i) & 1u) && fabs(xn) <= 1e-14 * fabs(xo)) xn = 0.0;          // see the sparse pass
+            scr(XS + i) = xn;
+            if (xn != 0.0) nz |= (1u << i);
+        }
+        rest &= rest - 1u;
+    }
+    L.nz = nz;
+    L.iters = L.it;
+    L.it += 1;
+    return false;
+}
+
+template <class Scr>
+MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L, const unsigned lanes) {
+    // 1. σ = σ_trial − Σ_{x_j != 0} x_j s_j Eᵉ:MS_j                                        :131
+#pragma unroll
+    for (int c = 0; c < 6; ++c) L.sig[c] = scr(SIGT + c);
+    for (unsigned m = L.nz; m != 0u; m &= m - 1u) {
+        const int j = __ffs_(m);
+        const double f = scr(XS + j) * crystal_sign(L, j);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) L.sig[c] -= f * tab[72 + c * 12 + j];
+    }
+    // 2. uniform yield test; τ_i parked in the D⁻¹r slot
+    unsigned cand = L.nz;
+#pragma unroll 4
+    for (int i = 0; i < 12; ++i) {
+        double tau = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) tau += L.sig[c] * k.Pw[i][c];
+        scr(36 + i) = tau;
+        const double Phi = fabs(tau - scr(12 + i)) - k.tau_y - scr(i);
+        cand |= (!(Phi <= 0.0)) ? (1u << i) : 0u;                                       // Φ > 0, or NaN (handled by the full chain)
+    }
+    L.cand = cand;
+#if defined(MM_CRYSTAL_STATS) && !defined(__CUDA_ARCH__)
+    mm_crystal_stats_pass(L.nz, cand);
+#endif
+    // the route is a property of the POINT (its result must not depend on its neighbours in the warp): more than 6 candidates in any of its
+    // passes, or a candidate whose frozen sign is 0 -> the point is handed to the sparse pass (6x6 Woodbury route) and redone from its first
+    // pass there; the solve SIZE below is the warp's (padding is an exact no-op)
+#if defined(__CUDA_ARCH__)
+    const int kc = __popc(cand);
+#else
+    const int kc = __builtin_popcount(cand);
+#endif
+    const bool big = (kc > 6) | ((cand & ~(L.spos | L.sneg)) != 0u);
+#if defined(__CUDA_ARCH__)
+    const unsigned kmax = __reduce_max_sync(lanes, big ? 0u : (unsigned)kc);            // the longest list among the warp's small-route lanes
+#else
+    const unsigned kmax = (unsigned)kc; (void)lanes;
+#endif
+    if (big) { L.big = true; return true; }                                             // the whole point is redone by the sparse pass (second launch)
+    // 3. the chains, two list entries per trip (see the sparse pass): g_i, (D⁻¹r)_i into the scratch slots of their system
+    double nrm2 = 0.0;
+    unsigned mask = 0;
+    bool bad = false, flip = false;
+    const int npow = k.m_int - 1;
+    for (unsigned m = cand; m != 0u;) {
+        int ii[2];
+        ii[0] = __ffs_(m); m &= m - 1u;
+        const bool two = m != 0u;
+        ii[1] = two ? __ffs_(m) : ii[0]; m &= m - 1u;
+        double gg[2], rr[2], R2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = ii[u];
+            const bool live = (u == 0) | two;
+            const double si = crystal_sign(L, i), xi = scr(XS + i);
+            const double kap = scr(i) + k.a_h * xi;                                     // :127 with H = a I (q = 0)
+            const double iden = rcp_nc(1.0 + k.hk_ai * xi);
+            const double al = (scr(12 + i) + k.H_kin * xi * si) * iden;                 // :128
+            const double red = scr(36 + i) - al;
+            const double sgn = sign_of(red);
+            const double Phi = fabs(red) - k.tau_y - kap;                                // :110
+            const bool act = Phi > 0.0;
+            const double xx = act ? Phi * k.isc : Phi * 0.0;
+            const double pw1 = (npow == 9) ? powc_<9>(xx) : powi6_(xx, npow);
+            const double Ri = k.dt * (pw1 * xx) - k.t_star * xi;                        // :111
+            const double p = k.dtm_sc * pw1;
+            mask |= (act & live) ? (1u << i) : 0u;
+            flip = flip | (act & (sgn != si));
+            const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
+            const double dD = k.t_star + p * (sgn * dal + k.a_h);
+            bad = bad | (act & !(dD >= 0.25 * k.t_star));
+            const double invD = act ? -rcp_nc(dD) : k.mits;
+            rr[u] = Ri * invD;
+            gg[u] = (p * sgn) * invD;
+            R2[u] = live ? Ri : 0.0;
+        }
+        // both reads of the parked τ precede both writes: an odd tail entry is the same system twice
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { scr(24 + ii[u]) = gg[u]; scr(36 + ii[u]) = rr[u]; nrm2 += R2[u] * R2[u]; }
+    }
+    L.mask = mask;
+    L.flip = flip;
+    L.iters = L.it - 1;
+    if (L.it > k.max_iter) return true;                                                  // nonlinear_solver.jl:61
+    if (!(nrm2 == nrm2)) return true;                                                    // NaN residual -> not converged
+    if (bad) { L.bad = true; return true; }
+    if (nrm2 < k.tol2_lo || (nrm2 <= k.tol2_hi && sqrt(nrm2) < k.tol)) { L.converged = true; return true; }
+    // 4. (I + W G) δ' = s ∘ D⁻¹r on the list, elimination without pivoting                 nonlinear_solver.jl:59
+#ifndef MM_ASET_SIZES
+#define MM_ASET_SIZES 246
+#endif
+#if MM_ASET_SIZES == 246 || MM_ASET_SIZES == 26
+    if (kmax <= 2u) return crystal_aset_solve<2>(tab, scr, L, cand, mask);
+#endif
+#if MM_ASET_SIZES == 36
+    if (kmax <= 3u) return crystal_aset_solve<3>(tab, scr, L, cand, mask);
+#endif
+#if MM_ASET_SIZES == 246 || MM_ASET_SIZES == 46
+    if (kmax <= 4u) return crystal_aset_solve<4>(tab, scr, L, cand, mask);
+#endif
+    return crystal_aset_solve<6>(tab, scr, L, cand, mask);
 }
 
 // ---- PHASED pass (integer m, q = 0): the Newton kernel's default ----------------------------------------------------------------
@@ -931,8 +1161,13 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
     if (!L.converged) mask |= 0x8000u;
     // the tangent's SPD factorisation first: if it fails the point goes to the general path and NOTHING may have been written yet
     // (state_out may alias state_in, and the general path restarts from the old state)
+    // (factored for every point that writes a tangent, elastic ones included — theirs is unused: a factorisation only the plastic lanes of a warp
+    // execute, with an early return inside, left the two halves of the warp un-reconverged to the end of the kernel in one build: 3.75 instead of
+    // 2.49 ms per 1e7 points for the same thread-instruction count)
     const bool want_tan = acc.template has_out<1>() && ((mask & 0x0FFFu) != 0) && L.converged;
-    if (want_tan && !ldl6_factor(L.K)) { *fallback = true; return 0; }
+    bool factored = true;
+    if (acc.template has_out<1>()) factored = ldl6_factor(L.K);
+    if (want_tan && !factored) { *fallback = true; return 0; }
 #pragma unroll
     for (int c = 0; c < 6; ++c) { acc.template out<0>(c, L.sig[c]); acc.template out<2>(c, L.sig[c]); }
     double sumx = 0.0;
@@ -977,13 +1212,10 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
 #pragma unroll
             for (int Jc = 0; Jc < 6; ++Jc) {
                 double col[6];
-                if (!want) {
-#pragma unroll
-                    for (int Ic = 0; Ic < 6; ++Ic) col[Ic] = iso_entry(Ic, Jc, k.lam, k.G);
-                } else {
+                {
 #pragma unroll
                     for (int Ic = 0; Ic < 6; ++Ic) col[Ic] = (Ic == Jc) ? 1.0 : 0.0;
-                    ldl6_solve(L.K, col);                                       // column Jc of M⁻¹
+                    ldl6_solve(L.K, col);                                       // column Jc of M⁻¹ (every lane; an elastic point's column is replaced below)
                     if (flip) {
                         double t[6];                                            // t = S_g m
 #pragma unroll
@@ -1002,7 +1234,7 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
                     }
                 }
 #pragma unroll
-                for (int Ic = 0; Ic < 6; ++Ic) acc.template out<1>(Ic + 6 * Jc, col[Ic]);
+                for (int Ic = 0; Ic < 6; ++Ic) acc.template out<1>(Ic + 6 * Jc, want ? col[Ic] : iso_entry(Ic, Jc, k.lam, k.G));
             }
             return mask;
         }
@@ -1081,6 +1313,29 @@ MM_HD unsigned crystal_point_sparse(const CrystalK& k, Acc& acc, Scr& scr, int* 
     while (!crystal_iterate_sparse<HASQ, true>(k, tab, scr, L)) {}
     const unsigned mask = crystal_finalize<HASQ>(k, acc, scr, L, fallback);
     *iters_out = *fallback ? 0 : L.iters;
+    return mask;
+}
+
+// one point start to finish through the ACTIVE-SET pass (host twin of the Newton kernel's default path; integer m, q = 0): the Newton
+// iteration as the kernel runs it, then — like crystal_finish_kernel — one dense evaluation at the converged x for the outputs
+template <class Acc, class Scr>
+MM_HD unsigned crystal_point_aset(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
+    double tab[MM_CRYSTAL_TAB];
+    for (int e = 0; e < MM_CRYSTAL_TAB; ++e) crystal_fill_tab(k, tab, e);
+    CrystalLane L;
+    crystal_init(k, acc, scr, L);
+    while (!crystal_iterate_aset(k, tab, scr, L, 0xffffffffu)) {}
+    if (L.big) return crystal_point_sparse<false>(k, acc, scr, iters_out, fallback);          // redone from the start, as the second launch does
+    if (L.bad) { *fallback = true; *iters_out = 0; return 0; }
+    const bool converged = L.converged;
+    const int iters = L.iters;
+    double yr[6], nrm2;
+    bool bad;
+    crystal_evaluate<false, true>(k, scr, L, yr, &nrm2, &bad);
+    if (bad) { *fallback = true; *iters_out = 0; return 0; }
+    L.converged = converged;
+    const unsigned mask = crystal_finalize<false>(k, acc, scr, L, fallback);
+    *iters_out = *fallback ? 0 : iters;
     return mask;
 }
 

@@ -5,6 +5,7 @@
 #include <cstring>
 #define MM_CRYSTAL_STATS 1
 namespace mm { void mm_crystal_stats_pass(unsigned nz, unsigned cand); }
+static inline void trace_put(uint8_t v);
 #include "../../include/mmb200.h"
 #include "../../materialmodels.jl_b200/csrc/mm_math.cuh"
 #include "../../materialmodels.jl_b200/csrc/mm_crystal_math.cuh"
@@ -66,7 +67,7 @@ int twin_xu(const MMXuNeedleman* p, const double* jump, double* T, double* H, in
 }
 struct HostScratch { double v[MM_CRYSTAL_SCRATCH + 8]; double& operator()(int j) { return v[j]; } };     // 72 slots for the phased pass
 
-// mode 0: general pivoted path; mode 1: structured fast path (falls back like the kernel does); mode 2: the same through the sparse pass; mode 3: through the phased pass (q = 0; else as mode 2)
+// mode 0: general pivoted path; mode 1: structured fast path (falls back like the kernel does); mode 2: the same through the sparse pass; mode 3: through the phased pass (q = 0; else as mode 2); mode 4: through the active-set pass (q = 0; else as mode 2)
 int twin_crystal_mode(const MMCrystal* p, const double* deps, double dt, const double* sin, double* sig, double* tan, double* sout, uint16_t* active,
                       uint16_t* iters, double tol, int max_iter, int64_t N, int mode, int64_t* n_fallback) {
     mm::CrystalK k;
@@ -75,10 +76,12 @@ int twin_crystal_mode(const MMCrystal* p, const double* deps, double dt, const d
     for (int64_t i = 0; i < N; ++i) {
         HostAcc<2, 3> a{{deps, sin}, {sig, tan, sout}, N, i};
         int it = 0; unsigned m;
+        trace_put(255);
         if (mode == 0 || !k.h_struct) m = mm::crystal_point(k, a, &it);
         else {
             HostScratch scr; bool fb = false;
-            if (mode == 3 && k.m_int && k.b_h == 0.0) m = mm::crystal_point_phased(k, a, scr, &it, &fb);
+            if (mode == 4 && k.m_int && k.b_h == 0.0) m = mm::crystal_point_aset(k, a, scr, &it, &fb);
+            else if (mode == 3 && k.m_int && k.b_h == 0.0) m = mm::crystal_point_phased(k, a, scr, &it, &fb);
             else if (mode >= 2 && k.m_int) m = (k.b_h != 0.0) ? mm::crystal_point_sparse<true>(k, a, scr, &it, &fb) : mm::crystal_point_sparse<false>(k, a, scr, &it, &fb);
             else m = (k.b_h != 0.0) ? mm::crystal_point_fast<true>(k, a, scr, &it, &fb) : mm::crystal_point_fast<false>(k, a, scr, &it, &fb);
             if (fb) { ++nfb; m = mm::crystal_point(k, a, &it); }
@@ -281,7 +284,12 @@ extern "C" int twin_wrapped_transviso(int kind, const MMTransverselyIsotropic* p
 
 // instrumentation of the sparse crystal pass: how many systems cost a full chain per Newton pass
 static long long g_stats_passes = 0, g_stats_nz = 0, g_stats_cand = 0, g_stats_hist[13] = {0};
-namespace mm { void mm_crystal_stats_pass(unsigned nz, unsigned cand) { ++g_stats_passes; g_stats_nz += __builtin_popcount(nz); const int c = __builtin_popcount(cand); g_stats_cand += c; ++g_stats_hist[c]; } }
+// optional per-pass trace (tools/crystal_sched_sim.py): one byte per Newton pass = candidate count, 255 = start of a point
+static uint8_t* g_trace = nullptr; static long long g_trace_cap = 0, g_trace_len = 0;
+extern "C" void twin_crystal_trace(uint8_t* buf, long long cap) { g_trace = buf; g_trace_cap = cap; g_trace_len = 0; }
+extern "C" long long twin_crystal_trace_len() { return g_trace_len; }
+static inline void trace_put(uint8_t v) { if (g_trace && g_trace_len < g_trace_cap) g_trace[g_trace_len++] = v; }
+namespace mm { void mm_crystal_stats_pass(unsigned nz, unsigned cand) { trace_put((uint8_t)__builtin_popcount(cand)); ++g_stats_passes; g_stats_nz += __builtin_popcount(nz); const int c = __builtin_popcount(cand); g_stats_cand += c; ++g_stats_hist[c]; } }
 extern "C" void twin_crystal_stats(long long* out16, int reset) {
     out16[0] = g_stats_passes; out16[1] = g_stats_nz; out16[2] = g_stats_cand;
     for (int i = 0; i < 13; ++i) out16[3 + i] = g_stats_hist[i];

@@ -318,15 +318,46 @@ def _crystal_three_steps(mm, torch, oracle, lname, lay):
         st = mm.CrystalViscoPlasticState(dev(torch, st_ref), lname)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
-def test_crystal_newton_kernel_variants(mm, torch, oracle, cuda_lib, variant):
-    """The three Newton passes of the structured path — dense branch-free (default), sparse per-lane lists, phased — must all reproduce
-    the oracle's masks and iteration counts exactly and its values within 1e-12 (mm_set_tuning("crystal_variant", v))."""
+@pytest.mark.parametrize("variant,lname,lay", [(0, "soa", 0), (1, "soa", 0), (2, "soa", 0), (3, "soa", 0), (4, "soa", 0), (5, "soa", 0), (6, "soa", 0), (3, "aos", 1), (1, "aos", 1), (5, "aos", 1), (0, "aos", 1)])
+def test_crystal_newton_kernel_variants(mm, torch, oracle, cuda_lib, variant, lname, lay):
+    """The Newton passes of the structured path — dense branch-free, sparse per-lane lists, phased, the sparse / dense pass over chunks
+    re-ordered by first-pass candidate count (3 / 4; a pure scheduling change), and the active-set pass with / without the re-ordering
+    (5 = the default / 6) — must all reproduce the oracle's masks and iteration counts exactly and its values within 1e-12
+    (mm_set_tuning("crystal_variant", v))."""
     old = cuda_lib.mm_set_tuning(b"crystal_variant", variant)
     try:
-        _crystal_three_steps(mm, torch, oracle, "soa", 0)
+        _crystal_three_steps(mm, torch, oracle, lname, lay)
     finally:
         cuda_lib.mm_set_tuning(b"crystal_variant", old)
+
+
+@pytest.mark.parametrize("chunk", [64, 96, 1024])
+def test_crystal_presorted_chunks_visit_every_point_once(mm, torch, cuda_lib, chunk):
+    """The chunk-local re-ordering is a permutation: with it (variants 3, 5) every point gets exactly the result of the natural order
+    (variants 1, 6), bit for bit, whatever the chunk size and for a ragged last chunk."""
+    N = 50021
+    m = make_crystal(mm)
+    res = {}
+    oldc = cuda_lib.mm_set_tuning(b"crystal_chunk", chunk)
+    oldv = cuda_lib.mm_set_tuning(b"crystal_variant", 1)
+    try:
+        for variant in (1, 3, 6, 5):
+            cuda_lib.mm_set_tuning(b"crystal_variant", variant)
+            st = mm.initial_material_state(m, N)
+            for step in range(2):
+                nc, lo, hi, seed = sy.c4_strain_increment(step)
+                de = mm.synth_uniform(N, nc, seed, lo, hi)
+                s, t, st = mm.material_response(m, de, st, 1.0, options={"defer_check": True})
+            res[variant] = (s, t, st.data, st.flags, st.iters)
+    finally:
+        cuda_lib.mm_set_tuning(b"crystal_variant", oldv)
+        cuda_lib.mm_set_tuning(b"crystal_chunk", oldc)
+    for a, b in zip(res[1], res[3]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[6], res[5]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[1][3], res[5][3]) and torch.equal(res[1][4], res[5][4])       # sparse vs active-set pass: same masks, same counts
+    assert int((res[3][3] != 0).sum()) > N // 10          # the workload does yield
 
 
 def test_crystal_golden_path(mm, torch, golden):

@@ -162,7 +162,7 @@ def test_twin_crystal_matches_oracle(oracle):
             nc, lo, hi, seed = sy.c4_strain_increment(step)
             de = sy.host_uniform(N, nc, seed, lo, hi)
             r = oracle.crystal(cp, de, st)
-            for mode in (0, 1, 2, 3):             # general pivoted / structured: dense pass, sparse pass, phased pass (the Newton kernel's default)
+            for mode in (0, 1, 2, 3, 4):          # general pivoted / structured: dense pass, sparse pass, phased pass, active-set pass (the Newton kernel's default)
                 sig, tan, so = np.zeros((6, N)), np.zeros((36, N)), np.zeros((42, N))
                 ac, it = np.zeros(N, np.uint16), np.zeros(N, np.uint16)
                 nfb = C.c_int64(0)

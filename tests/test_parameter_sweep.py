@@ -116,7 +116,7 @@ def test_twin_crystal_structured_path_over_parameter_corners(oracle, name, kw, r
         nc, lo, hi, seed = sy.c4_strain_increment(step)
         de = sy.host_uniform(N, nc, seed, lo, hi)
         r = oracle.crystal(p, de, st)
-        for mode in (3, 2, 1):                     # phased pass (integer m, q = 0), sparse pass (integer m), dense pass — each falls back to the next
+        for mode in (4, 3, 2, 1):                  # active-set and phased pass (integer m, q = 0), sparse pass (integer m), dense pass — each falls back to the next
             sig, tan, so = np.zeros((6, N)), np.zeros((36, N)), np.zeros((42, N))
             act, it, nfb = np.zeros(N, np.uint16), np.zeros(N, np.uint16), C.c_int64(0)
             tw.twin_crystal_mode(C.byref(p), H.P(de), C.c_double(1.0), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(act), H.P(it), C.c_double(1e-8), 100,

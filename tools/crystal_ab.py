@@ -46,8 +46,16 @@ def run(variant):
     return res
 
 
-r0, rs, r1 = run(0), run(1), run(2)
+r0 = run(0)
+extra = {v: run(v) for v in (3, 4, 5, 6)}       # chunks re-ordered by first-pass candidate count: sparse / dense pass; active-set pass with / without re-ordering
+rs, r1 = run(1), run(2)
 for step in (0, 1):
+    o3 = extra[3][step][1]
+    print(json.dumps({"step": "AB"[step], "points": N, "layout": layout, "sparse_presorted_ms": round(extra[3][step][0], 3), "dense_presorted_ms": round(extra[4][step][0], 3),
+                      "aset_presorted_ms": round(extra[5][step][0], 3), "aset_ms": round(extra[6][step][0], 3),
+                      "aset_vs_dense_mask_or_count_differences": int((extra[5][step][1][2].flags != r0[step][1][2].flags).sum().item()) + int((extra[5][step][1][2].iters != r0[step][1][2].iters).sum().item()),
+                      "presorted_vs_sparse_bitwise_differences": int((o3[0] != rs[step][1][0]).sum().item()) + int((o3[1] != rs[step][1][1]).sum().item())
+                      + int((o3[2].data != rs[step][1][2].data).sum().item()) + int((o3[2].iters != rs[step][1][2].iters).sum().item())}), flush=True)
     (t0, o0), (t1, o1) = r0[step], r1[step]
     tsp = rs[step][0]
     ax = 0 if lay == 0 else 1
