@@ -296,8 +296,12 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
     const int lane = threadIdx.x & 31;
     const int64_t warp_id = (int64_t)blockIdx.x * (BS / 32) + (threadIdx.x >> 5);
     const int64_t Nc = cnt ? (int64_t)*cnt : N;               // points in use (N stays the SoA stride)
-    if (cnt) chunk = crystal_chunk_for(Nc, rw8);              // batch: the chunk follows the device-side count (the grid covers N / 64 warps)
     const int64_t nwarps = (int64_t)gridDim.x * (BS / 32);
+    if (cnt) chunk = crystal_chunk_for(Nc, rw8);              // batch: the chunk follows the device-side count (the grid covers N / 64 warps)
+    if (cnt && sched.scatter) {                               // one resident wave works the whole list: one chunk per warp, so that its lanes drain once
+        const int64_t share = ((Nc + nwarps - 1) / nwarps + 31) / 32 * 32;
+        if (share > chunk) chunk = (int)(share < (1 << 20) ? share : (1 << 20));
+    }
     CrystalLane L;
     for (int64_t cid = warp_id; cid * chunk < Nc; cid += nwarps) {   // one trip, except for a scatter launch (one resident wave walks all chunks of its list)
     const int64_t chunk0 = cid * chunk;
@@ -430,16 +434,17 @@ template <bool HASQ, bool INTPOW, int LAYOUT>
 int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st, const int* cnt, const int* idx, int* n_general) {
     constexpr int BS = MM_CRYSTAL_BS, FBS = MM_CRYSTAL_FINISH_BS;
     constexpr size_t smem = (size_t)(MM_CRYSTAL_SCRATCH * BS + MM_CRYSTAL_TAB) * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
-    // "crystal_variant" (mm_set_tuning / MM_CRYSTAL_VARIANT): 0 or default = dense branch-free pass, 1 = sparse per-lane pass, 2 = phased pass.
+    // "crystal_variant" (mm_set_tuning / MM_CRYSTAL_VARIANT): 0 = dense branch-free pass, 1 = sparse per-lane pass, 2 = phased pass.
     // Measured on configs[3] (1e7 points, step B, profiles/r02_crystal_variants.jsonl + r02_crystal_*_ncu.txt): dense 21.9 ms, sparse 21.9 ms,
     // phased 25.6 ms — the sparse pass does HALF the thread-level work of the dense one but leaves 15 of 32 lanes active per instruction, the
-    // phased pass (unrolled, constant-bank operands) outgrows the 32 KB instruction cache (23 % no_instruction stalls).  Tests run all three.
+    // phased pass (unrolled, constant-bank operands) outgrows the 32 KB instruction cache (23 % no_instruction stalls).  Tests run all of them.
     // 3 / 4 = sparse / dense pass over chunks re-ordered by first-pass candidate count (crystal_presort_kernel); 5 = active-set pass over re-ordered
-    // chunks (the DEFAULT for integer m, q = 0), 6 = active-set pass in the natural order.  With cross hardening 5 / 6 run the sparse pass.
+    // chunks, 6 = active-set pass in the natural order (the DEFAULT for integer m, q = 0: 18.3 ms; 5: 19.6 ms, profiles/r02_crystal_aset_*).  With cross
+    // hardening 5 / 6 run the sparse pass and the default stays the dense pass.
     const int variant = crystal_knobs().variant < 0 ? (HASQ ? 0 : 6) : crystal_knobs().variant;      // cross hardening keeps the dense pass by default
     constexpr int SP = INTPOW ? 1 : 0, AS = (INTPOW && !HASQ) ? 2 : SP;     // instantiations that do not apply collapse onto one that does
     // the wrappers' index-list batches (cnt / idx) keep the dense pass unless the sparse one is asked for: the active-set launch needs its hand-over list
-    const int pass = !INTPOW ? 0 : ((variant == 1 || variant == 3) ? 1 : (((variant == 5 || variant == 6) && !cnt && !idx) ? AS : 0));
+    const int pass = !INTPOW ? 0 : ((variant == 1 || variant == 3) ? 1 : (((variant == 5 || variant == 6) && !cnt && !idx && N < ((int64_t)1 << 31)) ? AS : 0));       // (the hand-over list holds 32-bit indices)
     const bool presort = INTPOW && (variant == 3 || variant == 4 || variant == 5) && !cnt && !idx;
     static SmemOptIn optin_newton, optin_newton_sparse, optin_newton_aset, optin_finish;
     if (int rc = ensure_smem(optin_newton, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, 0>, smem, "mm_crystal")) return rc;

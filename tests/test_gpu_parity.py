@@ -360,6 +360,33 @@ def test_crystal_presorted_chunks_visit_every_point_once(mm, torch, cuda_lib, ch
     assert int((res[3][3] != 0).sum()) > N // 10          # the workload does yield
 
 
+@pytest.mark.parametrize("variant", [0, 1, 5, 6])
+def test_crystal_zero_sign_candidates_and_idle_points(mm, torch, oracle, cuda_lib, variant):
+    """Edge inputs of the active-set launch: candidates whose frozen sign is 0 (handed to the sparse launch), points without any candidate,
+    and a NaN strain increment (ends as not converged, like the oracle's) — every Newton pass variant against the oracle."""
+    from test_host_logic import _crystal_edge_inputs
+
+    de, st = _crystal_edge_inputs(4096 + 37)
+    N = de.shape[1]
+    m = make_crystal(mm)
+    cp = H.crystal_c(oracle)
+    r = oracle.crystal(cp, de, st)
+    old = cuda_lib.mm_set_tuning(b"crystal_variant", variant)
+    try:
+        s, t, new = mm.material_response(m, dev(torch, de), mm.CrystalViscoPlasticState(dev(torch, st), "soa"), 1.0, options={"defer_check": True})
+        H.crystal_compare(r, host(new.flags), host(new.iters), host(s), host(t), host(new.data), nfail_gpu=int(new.n_fail.item()))
+        de2 = de.copy()
+        de2[2, 5] = np.nan
+        s, t, new = mm.material_response(m, dev(torch, de2), mm.CrystalViscoPlasticState(dev(torch, st), "soa"), 1.0, options={"defer_check": True})
+        fl = np.asarray(host(new.flags)).view(np.uint16)
+        assert (int(fl[5]) & abi.MM_ACTIVE_FAILED) and int(new.n_fail.item()) == 1
+        ok = np.ones(N, bool)
+        ok[5] = False
+        assert np.array_equal(fl[ok], r["active"][ok]) and np.array_equal(host(new.iters)[ok], r["iters"][ok])
+    finally:
+        cuda_lib.mm_set_tuning(b"crystal_variant", old)
+
+
 def test_crystal_golden_path(mm, torch, golden):
     g = golden["CrystalViscoPlastic1"]
     m = make_crystal(mm)

@@ -177,6 +177,34 @@ def test_twin_crystal_matches_oracle(oracle):
     assert n_fallback_total > 0                     # ... but the guard does fire on the harder configurations
 
 
+def _crystal_edge_inputs(N=64):
+    """Points the active-set pass must hand to the 6x6 route or end at once: a previous slip increment on a stress-free, back-stress-free state with a
+    zero strain increment (the trial reduced stress of that system is exactly 0: frozen sign 0 on a candidate), zero increments on a virgin state
+    (no candidate at all), ordinary loaded points in between."""
+    rng = np.random.default_rng(5)
+    de = rng.uniform(-sy.CRYSTAL_AMPL, sy.CRYSTAL_AMPL, (6, N))
+    st = np.zeros((42, N))
+    de[:, 0::4] = 0.0                           # every 4th point: no increment
+    st[30 + 3, 0::8] = 1e-3                     # every 8th: mu_3 != 0 with sigma = alpha = 0  ->  s_3 = 0 and x_3 != 0
+    st[30 + 7, 0::8] = -2e-4
+    return de, st
+
+
+def test_twin_crystal_zero_sign_candidates_and_idle_points(oracle):
+    tw = H.hosttwin()
+    cp = H.crystal_c(oracle)
+    de, st = _crystal_edge_inputs()
+    N = de.shape[1]
+    r = oracle.crystal(cp, de, st)
+    for mode in (1, 2, 4):
+        sig, tan, so = np.zeros((6, N)), np.zeros((36, N)), np.zeros((42, N))
+        ac, it = np.zeros(N, np.uint16), np.zeros(N, np.uint16)
+        nfb = C.c_int64(0)
+        tw.twin_crystal_mode(C.byref(cp), H.P(de), C.c_double(1.0), H.P(st), H.P(sig), H.P(tan), H.P(so), H.P(ac), H.P(it),
+                             C.c_double(1e-8), 100, C.c_int64(N), mode, C.byref(nfb))
+        H.crystal_compare(r, ac, it, sig, tan, so)
+
+
 def test_share_host_cores_sets_the_library_thread_count():
     """One process per GPU shares the host cores for the library's host-side expansion (sharding.share_host_cores -> mmh_set_host_threads)."""
     import materialmodels_jl_b200._lib as L
