@@ -157,14 +157,14 @@ template <int LAYOUT> struct DirectAccRW : DirectAcc<LAYOUT> {
         return LAYOUT == 0 ? this->p.out[A][(int64_t)c * this->N + this->i] : this->p.out[A][this->i * CrystalGeneralOp::out_nc(A) + c];
     }
 };
-template <int LAYOUT, class Scr> __device__ __forceinline__ void crystal_hand_over(const Ptrs<2, 3>& p, double* xbuf, int64_t N, int64_t my, const Scr& scr) {
+template <int LAYOUT, int XSLOT = XS, class Scr> __device__ __forceinline__ void crystal_hand_over(const Ptrs<2, 3>& p, double* xbuf, int64_t N, int64_t my, const Scr& scr) {
     if (xbuf) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) xbuf[(int64_t)i * N + my] = scr(XS + i);
+        for (int i = 0; i < 12; ++i) xbuf[(int64_t)i * N + my] = scr(XSLOT + i);
     } else {
         DirectAcc<LAYOUT> acc(p, N, my);
 #pragma unroll
-        for (int i = 0; i < 12; ++i) acc.template out<2>(30 + i, scr(XS + i));
+        for (int i = 0; i < 12; ++i) acc.template out<2>(30 + i, scr(XSLOT + i));
     }
 }
 
@@ -281,13 +281,17 @@ struct CrystalSched { const uint16_t* order; const uint16_t* hc; int* heavy_idx;
 
 // SPARSE (integer m only): the per-lane active-list pass crystal_iterate_sparse — the slip-system tables are copied into shared memory
 // ([component][system], behind the scratch columns) because every lane walks its own list of systems
-template <bool HASQ, bool INTPOW, int LAYOUT, int BS, int PASS>      // PASS: 0 dense, 1 sparse, 2 active-set (q = 0)
-__global__ void __launch_bounds__(BS, MM_CRYSTAL_MINBLOCKS)
+#ifndef MM_CRYSTAL_ASET_MINBLOCKS
+#define MM_CRYSTAL_ASET_MINBLOCKS 8   // 16 resident warps (128 registers, 48 scratch slots per lane): 12.40 ms per 1e7 points against 13.14 (6 blocks) / 12.74 (7), profiles/r02_crystal_aset_occupancy.log
+#endif
+template <bool HASQ, bool INTPOW, int LAYOUT, int BS, int PASS>      // PASS: 0 dense, 1 sparse, 2 active-set (q = 0; its own, smaller scratch layout)
+__global__ void __launch_bounds__(BS, PASS == 2 ? MM_CRYSTAL_ASET_MINBLOCKS : MM_CRYSTAL_MINBLOCKS)
 crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, int chunk, const int thresh, const int* cnt, const int* idx, const int rw8,
                       const CrystalSched sched) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
-    double* tab = sm_scratch + MM_CRYSTAL_SCRATCH * BS;
+    double* tab = sm_scratch + (PASS == 2 ? MM_CRYSTAL_SCRATCH_ASET : MM_CRYSTAL_SCRATCH) * BS;
+    double sigt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};          // active-set pass: σ_trial of the lane's point
     if (PASS != 0) {
         for (int e = threadIdx.x; e < MM_CRYSTAL_TAB; e += BS) crystal_fill_tab(k, tab, e);
         __syncthreads();
@@ -318,7 +322,8 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
                     // output slot; the inputs of a wrapper's list entry stay where the point is (order: the chunk's points, heaviest first)
                     my = sched.scatter ? (int64_t)idx[cand] : (sched.order ? (chunk0 + sched.order[cand]) : cand);
                     DirectAcc<LAYOUT> acc(p, N, my, (idx && !sched.scatter) ? (int64_t)idx[cand] : my);
-                    crystal_init(k, acc, scr, L);
+                    if (PASS == 2) crystal_init_t<XSA, -1>(k, acc, scr, L, sigt);
+                    else           crystal_init(k, acc, scr, L);
                     has_work = true; finished = false;
                 }
             }
@@ -328,7 +333,7 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
         if (working == 0u) break;
         if (PASS == 2) {
             const unsigned lanes = __ballot_sync(FULL, has_work && !finished);
-            if (has_work && !finished) finished = crystal_iterate_aset(k, tab, scr, L, lanes);
+            if (has_work && !finished) finished = crystal_iterate_aset(k, tab, scr, L, sigt, lanes);
         } else if (has_work && !finished) {
             if (PASS == 1) finished = crystal_iterate_sparse<HASQ, false>(k, tab, scr, L);
             else           finished = crystal_iterate<HASQ, INTPOW, false>(k, scr, L);
@@ -340,7 +345,7 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
                 if (PASS == 2 && L.big) {
                     sched.heavy_idx[atomicAdd(sched.heavy_cnt, 1)] = (int)my;      // redone from its first pass by the sparse launch; nothing written
                 } else {
-                    if (!L.bad) crystal_hand_over<LAYOUT>(p, xbuf, N, my, scr);
+                    if (!L.bad) crystal_hand_over<LAYOUT, (PASS == 2 ? XSA : XS)>(p, xbuf, N, my, scr);
                     else if (sched.n_general) atomicAdd(sched.n_general, 1);
                     active[my] = (uint16_t)(L.bad ? MM_ACTIVE_NEEDS_GENERAL : (L.converged ? 0u : MM_ACTIVE_FAILED));
                     if (iters) iters[my] = (uint16_t)(L.bad ? 0 : (L.iters > 65535 ? 65535 : L.iters));
@@ -434,6 +439,7 @@ template <bool HASQ, bool INTPOW, int LAYOUT>
 int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st, const int* cnt, const int* idx, int* n_general) {
     constexpr int BS = MM_CRYSTAL_BS, FBS = MM_CRYSTAL_FINISH_BS;
     constexpr size_t smem = (size_t)(MM_CRYSTAL_SCRATCH * BS + MM_CRYSTAL_TAB) * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
+    constexpr size_t smem_aset = (size_t)(MM_CRYSTAL_SCRATCH_ASET * BS + MM_CRYSTAL_TAB) * sizeof(double);      // (only when AS == 2)
     // "crystal_variant" (mm_set_tuning / MM_CRYSTAL_VARIANT): 0 = dense branch-free pass, 1 = sparse per-lane pass, 2 = phased pass.
     // Measured on configs[3] (1e7 points, step B, profiles/r02_crystal_variants.jsonl + r02_crystal_*_ncu.txt): dense 21.9 ms, sparse 21.9 ms,
     // phased 25.6 ms — the sparse pass does HALF the thread-level work of the dense one but leaves 15 of 32 lanes active per instruction, the
@@ -449,7 +455,7 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     static SmemOptIn optin_newton, optin_newton_sparse, optin_newton_aset, optin_finish;
     if (int rc = ensure_smem(optin_newton, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, 0>, smem, "mm_crystal")) return rc;
     if (int rc = ensure_smem(optin_newton_sparse, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, SP>, smem, "mm_crystal")) return rc;
-    if (int rc = ensure_smem(optin_newton_aset, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, AS>, smem, "mm_crystal")) return rc;
+    if (int rc = ensure_smem(optin_newton_aset, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, AS>, AS == 2 ? smem_aset : smem, "mm_crystal")) return rc;
     if (int rc = ensure_smem(optin_finish, crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS>, fsmem, "mm_crystal")) return rc;
     // six blocks of scratch columns need 210 KB of the SM's 228 KB: ask for the largest shared-memory carve-out (with the default heuristic
     // ncu reported a shared-memory limit of 5 blocks, i.e. 10 instead of 12 resident warps)
@@ -506,7 +512,7 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
         CrystalNK nk;
         make_crystal_nk(nk, k);
         crystal_newton_phased_kernel<LAYOUT, BS><<<(unsigned)blocks, BS, psmem, st>>>(nk, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8, n_general);
-    } else if (pass == 2) crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, AS><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8, sched);
+    } else if (pass == 2) crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, AS><<<(unsigned)blocks, BS, AS == 2 ? smem_aset : smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8, sched);
     else if (pass == 1)   crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, SP><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8, sched);
     else                  crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, 0><<<(unsigned)blocks, BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, cnt, idx, rw8, sched);
     int rc = check_launch("mm_crystal (Newton kernel)");

@@ -401,8 +401,9 @@ template <int NPOW> MM_HD double powc_(double b) {      // the multiplication se
     return r;
 }
 
-template <class KT, class Acc, class Scr>       // KT: CrystalK or CrystalNK (reads lam, G, Pw only)
-MM_HD void crystal_init(const KT& k, Acc& acc, Scr& scr, CrystalLane& L) {
+// XSLOT: first scratch slot of x; SIGSLOT: first slot of σ_trial, or -1 = returned in st_out only (the compact layout of the active-set kernel)
+template <int XSLOT, int SIGSLOT, class KT, class Acc, class Scr>       // KT: CrystalK or CrystalNK (reads lam, G, Pw only)
+MM_HD void crystal_init_t(const KT& k, Acc& acc, Scr& scr, CrystalLane& L, double* st_out) {
     const double G2 = 2.0 * k.G;
     double st[6];
     {   // σ_trial = σₙ + Eᵉ ⊡ Δε                                                           :119
@@ -411,14 +412,18 @@ MM_HD void crystal_init(const KT& k, Acc& acc, Scr& scr, CrystalLane& L) {
         for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c);
         const double ltr = k.lam * tr6(e);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) { st[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c])); scr(SIGT + c) = st[c]; }
+        for (int c = 0; c < 6; ++c) {
+            st[c] = acc.template in<1>(c) + (is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c]));
+            if (SIGSLOT >= 0) scr((SIGSLOT >= 0 ? SIGSLOT : 0) + c) = st[c];
+            if (st_out) st_out[c] = st[c];
+        }
     }
     L.spos = 0; L.sneg = 0;
     unsigned nz = 0;
 #pragma unroll
     for (int i = 0; i < 12; ++i) {                                                      // :120-121
         const double kn = acc.template in<1>(6 + i), an = acc.template in<1>(18 + i), x0 = acc.template in<1>(30 + i);
-        scr(i) = kn; scr(12 + i) = an; scr(XS + i) = x0;
+        scr(i) = kn; scr(12 + i) = an; scr(XSLOT + i) = x0;
         if (x0 != 0.0) nz |= (1u << i);
         double tau = 0.0;
 #pragma unroll
@@ -429,6 +434,8 @@ MM_HD void crystal_init(const KT& k, Acc& acc, Scr& scr, CrystalLane& L) {
     }
     L.mask = 0; L.nz = nz; L.cand = 0xFFFu; L.it = 1; L.iters = 0; L.converged = false; L.bad = false; L.big = false; L.flip = false;
 }
+template <class KT, class Acc, class Scr>
+MM_HD void crystal_init(const KT& k, Acc& acc, Scr& scr, CrystalLane& L) { crystal_init_t<XS, SIGT>(k, acc, scr, L, nullptr); }
 
 #ifndef MM_CRYSTAL_UNROLL
 #define MM_CRYSTAL_UNROLL 2   // r02 sweep after the sign / power specialisation: 1 -> 22.0 ms, 2 -> 21.5 ms, 3 -> 21.6 ms (profiles/r02_crystal_variant_and_knob_sweep.log)
@@ -830,6 +837,9 @@ MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, C
 // pass instead: the kernel around this pass carries no 6x6 code at all (3 360 -> 2 300 instructions; the instruction cache holds 2 000).
 // Same Newton iterates up to rounding (masks and counts against the oracle: tests).
 // `lanes`: the lanes of the warp that execute this call together (device: ballot of the caller's condition).
+// Scratch of the active-set kernel (48 slots per lane, so that 16 warps are resident): [0,12) κₙ [12,24) αₙ [24,36) x=μ, then BY LIST POSITION
+// [36,42) g [42,48) D⁻¹r; σ_trial stays in registers.
+constexpr int MM_CRYSTAL_SCRATCH_ASET = 48, XSA = 24, GPA = 36, RPA = 42;
 template <int KM, class Scr>
 MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const unsigned cand, const unsigned mask) {
     int a[KM];
@@ -841,8 +851,8 @@ MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const
         a[u] = live ? __ffs_(rest) : 0;
         rest &= rest - 1u;
         const double si = crystal_sign(L, a[u]);
-        w[u] = live ? -si * scr(24 + a[u]) : 0.0;
-        b[u] = live ? si * scr(36 + a[u]) : 0.0;
+        w[u] = live ? -si * scr(GPA + u) : 0.0;
+        b[u] = live ? si * scr(RPA + u) : 0.0;
     }
     double Nm[KM][KM];
 #pragma unroll
@@ -887,10 +897,10 @@ MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const
     for (int u = 0; u < KM; ++u) {
         if (rest != 0u) {
             const int i = a[u];
-            const double xo = scr(XS + i);
+            const double xo = scr(XSA + i);
             double xn = xo - crystal_sign(L, i) * b[u];
             if (!((mask >> i) & 1u) && fabs(xn) <= 1e-14 * fabs(xo)) xn = 0.0;          // see the sparse pass
-            scr(XS + i) = xn;
+            scr(XSA + i) = xn;
             if (xn != 0.0) nz |= (1u << i);
         }
         rest &= rest - 1u;
@@ -902,24 +912,23 @@ MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const
 }
 
 template <class Scr>
-MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L, const unsigned lanes) {
+MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L, const double* sigt, const unsigned lanes) {
     // 1. σ = σ_trial − Σ_{x_j != 0} x_j s_j Eᵉ:MS_j                                        :131
 #pragma unroll
-    for (int c = 0; c < 6; ++c) L.sig[c] = scr(SIGT + c);
+    for (int c = 0; c < 6; ++c) L.sig[c] = sigt[c];
     for (unsigned m = L.nz; m != 0u; m &= m - 1u) {
         const int j = __ffs_(m);
-        const double f = scr(XS + j) * crystal_sign(L, j);
+        const double f = scr(XSA + j) * crystal_sign(L, j);
 #pragma unroll
         for (int c = 0; c < 6; ++c) L.sig[c] -= f * tab[72 + c * 12 + j];
     }
-    // 2. uniform yield test; τ_i parked in the D⁻¹r slot
+    // 2. uniform yield test
     unsigned cand = L.nz;
 #pragma unroll 4
     for (int i = 0; i < 12; ++i) {
         double tau = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) tau += L.sig[c] * k.Pw[i][c];
-        scr(36 + i) = tau;
         const double Phi = fabs(tau - scr(12 + i)) - k.tau_y - scr(i);
         cand |= (!(Phi <= 0.0)) ? (1u << i) : 0u;                                       // Φ > 0, or NaN (handled by the full chain)
     }
@@ -947,7 +956,8 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
     unsigned mask = 0;
     bool bad = false, flip = false;
     const int npow = k.m_int - 1;
-    for (unsigned m = cand; m != 0u;) {
+    int pos = 0;
+    for (unsigned m = cand; m != 0u; pos += 2) {
         int ii[2];
         ii[0] = __ffs_(m); m &= m - 1u;
         const bool two = m != 0u;
@@ -957,11 +967,14 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
         for (int u = 0; u < 2; ++u) {
             const int i = ii[u];
             const bool live = (u == 0) | two;
-            const double si = crystal_sign(L, i), xi = scr(XS + i);
+            const double si = crystal_sign(L, i), xi = scr(XSA + i);
             const double kap = scr(i) + k.a_h * xi;                                     // :127 with H = a I (q = 0)
             const double iden = rcp_nc(1.0 + k.hk_ai * xi);
             const double al = (scr(12 + i) + k.H_kin * xi * si) * iden;                 // :128
-            const double red = scr(36 + i) - al;
+            double tau = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) tau += L.sig[c] * tab[c * 12 + i];             // the yield test's τ_i, bit for bit
+            const double red = tau - al;
             const double sgn = sign_of(red);
             const double Phi = fabs(red) - k.tau_y - kap;                                // :110
             const bool act = Phi > 0.0;
@@ -979,9 +992,9 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
             gg[u] = (p * sgn) * invD;
             R2[u] = live ? Ri : 0.0;
         }
-        // both reads of the parked τ precede both writes: an odd tail entry is the same system twice
+        // by list position (an odd tail entry fills a slot nobody reads)
 #pragma unroll
-        for (int u = 0; u < 2; ++u) { scr(24 + ii[u]) = gg[u]; scr(36 + ii[u]) = rr[u]; nrm2 += R2[u] * R2[u]; }
+        for (int u = 0; u < 2; ++u) { scr(GPA + pos + u) = gg[u]; scr(RPA + pos + u) = rr[u]; nrm2 += R2[u] * R2[u]; }
     }
     L.mask = mask;
     L.flip = flip;
@@ -1323,10 +1336,17 @@ MM_HD unsigned crystal_point_aset(const CrystalK& k, Acc& acc, Scr& scr, int* it
     double tab[MM_CRYSTAL_TAB];
     for (int e = 0; e < MM_CRYSTAL_TAB; ++e) crystal_fill_tab(k, tab, e);
     CrystalLane L;
-    crystal_init(k, acc, scr, L);
-    while (!crystal_iterate_aset(k, tab, scr, L, 0xffffffffu)) {}
+    double sigt[6];
+    crystal_init_t<XSA, -1>(k, acc, scr, L, sigt);
+    while (!crystal_iterate_aset(k, tab, scr, L, sigt, 0xffffffffu)) {}
     if (L.big) return crystal_point_sparse<false>(k, acc, scr, iters_out, fallback);          // redone from the start, as the second launch does
     if (L.bad) { *fallback = true; *iters_out = 0; return 0; }
+    {   // the dense evaluation below uses the standard layout: move x, restore σ_trial
+        double xs[12];
+        for (int i = 0; i < 12; ++i) xs[i] = scr(XSA + i);
+        for (int i = 0; i < 12; ++i) scr(XS + i) = xs[i];
+        for (int c = 0; c < 6; ++c) scr(SIGT + c) = sigt[c];
+    }
     const bool converged = L.converged;
     const int iters = L.iters;
     double yr[6], nrm2;
