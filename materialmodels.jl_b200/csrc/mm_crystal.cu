@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(MM_PRESORT_BS) crystal_presort_kernel(const Cr
 
 // scheduling data of one Newton launch (all optional): the chunk-local order, the per-chunk count of heavy points the launch skips, the global list
 // that collects points handed over to the sparse launch, and `scatter` = the launch works off such a list (idx / cnt) and writes each point's
-// results at the point's own index (the wrappers' batches pack them by list position instead)
-struct CrystalSched { const uint16_t* order; const uint16_t* hc; int* heavy_idx; int* heavy_cnt; int scatter; int* n_general; };
+// results at the listed index (a list of the wrappers' batch POSITIONS then: `in_idx` = the batch's own list says where each position's inputs are)
+struct CrystalSched { const uint16_t* order; const uint16_t* hc; int* heavy_idx; int* heavy_cnt; int scatter; int* n_general; const int* in_idx; };
 
 // SPARSE (integer m only): the per-lane active-list pass crystal_iterate_sparse — the slip-system tables are copied into shared memory
 // ([component][system], behind the scratch columns) because every lane walks its own list of systems
@@ -321,7 +321,7 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
                 if (cand < end) {
                     // output slot; the inputs of a wrapper's list entry stay where the point is (order: the chunk's points, heaviest first)
                     my = sched.scatter ? (int64_t)idx[cand] : (sched.order ? (chunk0 + sched.order[cand]) : cand);
-                    DirectAcc<LAYOUT> acc(p, N, my, (idx && !sched.scatter) ? (int64_t)idx[cand] : my);
+                    DirectAcc<LAYOUT> acc(p, N, my, sched.scatter ? (sched.in_idx ? (int64_t)sched.in_idx[my] : my) : (idx ? (int64_t)idx[cand] : my));
                     if (PASS == 2) crystal_init_t<XSA, -1>(k, acc, scr, L, sigt);
                     else           crystal_init(k, acc, scr, L);
                     has_work = true; finished = false;
@@ -449,8 +449,7 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     // hardening 5 / 6 run the sparse pass and the default stays the dense pass.
     const int variant = crystal_knobs().variant < 0 ? (HASQ ? 0 : 6) : crystal_knobs().variant;      // cross hardening keeps the dense pass by default
     constexpr int SP = INTPOW ? 1 : 0, AS = (INTPOW && !HASQ) ? 2 : SP;     // instantiations that do not apply collapse onto one that does
-    // the wrappers' index-list batches (cnt / idx) keep the dense pass unless the sparse one is asked for: the active-set launch needs its hand-over list
-    const int pass = !INTPOW ? 0 : ((variant == 1 || variant == 3) ? 1 : (((variant == 5 || variant == 6) && !cnt && !idx && N < ((int64_t)1 << 31)) ? AS : 0));       // (the hand-over list holds 32-bit indices)
+    const int pass = !INTPOW ? 0 : ((variant == 1 || variant == 3) ? 1 : (((variant == 5 || variant == 6) && N < ((int64_t)1 << 31)) ? AS : 0));       // (the hand-over list holds 32-bit indices)
     const bool presort = INTPOW && (variant == 3 || variant == 4 || variant == 5) && !cnt && !idx;
     static SmemOptIn optin_newton, optin_newton_sparse, optin_newton_aset, optin_finish;
     if (int rc = ensure_smem(optin_newton, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, 0>, smem, "mm_crystal")) return rc;
@@ -481,7 +480,7 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     // workspace of the scheduling data (stream-ordered, freed below): order[N] u16, hc[chunks] u16, heavy_idx[N] i32, heavy_cnt i32
     uint16_t* order = nullptr; uint16_t* hc = nullptr; int* heavy_idx = nullptr; int* heavy_cnt = nullptr;
     char* ws = nullptr;
-    const bool split = (pass == 2) && !cnt && !idx;                 // active-set launch + sparse launch over the points it hands over
+    const bool split = (pass == 2);                                 // active-set launch + sparse launch over the points it hands over (also for the wrappers' batches)
     const bool sorted = presort && chunk <= 1024 && N > 0;
     const int64_t nchunks = (N + chunk - 1) / chunk;
     if (sorted || split) {
@@ -497,7 +496,7 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
         crystal_presort_kernel<HASQ, LAYOUT><<<(unsigned)nchunks, MM_PRESORT_BS, 0, st>>>(k, ptrs, order, N, (int)chunk, hc, heavy_idx, heavy_cnt);
         if (int rc = check_launch("mm_crystal (presort kernel)")) { cudaFreeAsync(ws, st); return rc; }
     }
-    const CrystalSched sched{order, hc, heavy_idx, heavy_cnt, 0, n_general};
+    const CrystalSched sched{order, hc, heavy_idx, heavy_cnt, 0, n_general, nullptr};
     if (INTPOW && !HASQ && variant == 2) {          // "crystal_variant" 2: the phased pass (integer m, q = 0) — measured slower, kept for A/B
         constexpr size_t psmem = (size_t)MM_CRYSTAL_SCRATCH_PHASED * BS * sizeof(double);
         static SmemOptIn optin_phased;
@@ -519,7 +518,7 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     if (rc == 0 && split) {
         // the points the active-set launch did not take (heavy from the start, or grown past MM_ASET_MAX candidates): the sparse pass over the
         // device-side list, one resident wave of warps walking its chunks, results written at each point's own index
-        const CrystalSched sc2{nullptr, nullptr, nullptr, nullptr, 1, n_general};
+        const CrystalSched sc2{nullptr, nullptr, nullptr, nullptr, 1, n_general, idx};      // a batch: the heavy list holds batch positions, idx[position] = where the inputs are
         const int64_t wave = (int64_t)sm_count() * MM_CRYSTAL_MINBLOCKS;
         crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, SP><<<(unsigned)(wave < blocks ? wave : blocks), BS, smem, st>>>(k, ptrs, active, iters, xbuf, N, (int)chunk, thresh, heavy_cnt, heavy_idx, rw8, sc2);
         rc = check_launch("mm_crystal (Newton kernel, heavy points)");
