@@ -447,7 +447,9 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     // 3 / 4 = sparse / dense pass over chunks re-ordered by first-pass candidate count (crystal_presort_kernel); 5 = active-set pass over re-ordered
     // chunks, 6 = active-set pass in the natural order (the DEFAULT for integer m, q = 0: 18.3 ms; 5: 19.6 ms, profiles/r02_crystal_aset_*).  With cross
     // hardening 5 / 6 run the sparse pass and the default stays the dense pass.
-    const int variant = crystal_knobs().variant < 0 ? (HASQ ? 0 : 6) : crystal_knobs().variant;      // cross hardening keeps the dense pass by default
+    // default: cross hardening keeps the dense pass; q = 0: the active-set pass, over re-ordered chunks for AoS arrays (a point's rows are contiguous there, so
+    // the re-ordered refills stay coalesced: 18.6 against 20.3 ms) and in the natural order for SoA arrays (18.2 against 19.1 ms; profiles/r02_crystal_aset_ab_*.jsonl)
+    const int variant = crystal_knobs().variant < 0 ? (HASQ ? 0 : (LAYOUT == 1 ? 5 : 6)) : crystal_knobs().variant;
     constexpr int SP = INTPOW ? 1 : 0, AS = (INTPOW && !HASQ) ? 2 : SP;     // instantiations that do not apply collapse onto one that does
     const int pass = !INTPOW ? 0 : ((variant == 1 || variant == 3) ? 1 : (((variant == 5 || variant == 6) && N < ((int64_t)1 << 31)) ? AS : 0));       // (the hand-over list holds 32-bit indices)
     const bool presort = INTPOW && (variant == 3 || variant == 4 || variant == 5) && !cnt && !idx;
