@@ -667,13 +667,21 @@ def crystal_roofline(N, ms, fp64_peak_tflops):
         with open(os.path.join(ROOT, "profiles", "crystal_fp64_executed.json")) as f:
             c = json.load(f)
         flops = (2.0 * c["dfma_per_point"] + c["dmul_per_point"] + c["dadd_per_point"]) * N
+        dense_flop = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "crystal_fp64_executed_dense_pass.json")) as f:
+                dd = json.load(f)
+            dense_flop = 2.0 * dd["dfma_per_point"] + dd["dmul_per_point"] + dd["dadd_per_point"]
+        except Exception:
+            pass
         ach = flops / (ms * 1e-3) / 1e12
         return {"bound": "fp64", "achieved": ach, "peak": fp64_peak_tflops, "unit": "TFLOP/s (executed DFMA x2 + DMUL + DADD)", "frac": (ach / fp64_peak_tflops) if fp64_peak_tflops else None,
                 "pipe_active_ncu": c.get("pipe_fp64_active_pct"), "source": c.get("source"),
-                "executed_fp64_flop_per_point": flops / N,
-                "note": "the default (active-set) Newton pass executes 2.5x fewer FP64 instructions per point than the dense pass it replaced (13 860 vs 33 055 flop; "
-                        "profiles/crystal_fp64_executed_dense_pass.json: 21.5 ms at frac 0.53), so the fraction fell while the time per step improved; "
-                        "the kernels are bound by dependent-issue latency at 12 resident warps per SM, not by the FP64 pipe (DESIGN.md 4.5)"}
+                "executed_fp64_flop_per_point": flops / N, "dense_pass_flop_per_point": dense_flop,
+                "note": "the default (active-set) Newton pass executes %.1fx fewer FP64 instructions per point than the dense pass it replaced "
+                        "(profiles/crystal_fp64_executed_dense_pass.json: 21.5 ms per 1e7 points at frac 0.53), so the fraction fell while the time per step improved; "
+                        "the kernels are bound by dependent-issue latency at 16 / 12 resident warps per SM, not by the FP64 pipe (DESIGN.md 4.5)"
+                        % ((dense_flop / (flops / N)) if dense_flop else float("nan"))}
     except Exception as e:
         return {"bound": "fp64", "error": repr(e)}
 
