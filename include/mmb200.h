@@ -102,7 +102,9 @@ int mm_device_count(void);
  * thread per point, 1 = rounds; "wrapped_crystal_slab") and of the XuNeedleman SoA path ("xu_soa_tiled" 0 = direct kernel, 1 = copy-engine
  * tiles) and of the host-buffer J2 call ("mmh_plastic_via_factored" 1 = dense tangent rebuilt on the host from factored rows for batches of >= 2^18 points,
  * 2 = for any size, 0 = plain dense transfer); initial values come from the MM_CRYSTAL_* / MM_WRAPPED_* environment variables, read once per process.
- * Returns the previous value, -1 for an unknown name.  Results never depend on these (tests/test_gpu_parity.py runs both paths). */
+ * Returns the previous value, -1 for an unknown name.  Results do not depend on the scheduling switches (chunk, thresholds, re-ordering, slabs: bit for bit);
+ * the Newton pass variants of the crystal update solve the same Newton step by different algebra and agree to rounding — active masks and iteration counts
+ * identical, values within 1e-12 (tests/test_gpu_parity.py runs every variant against the oracle). */
 int mm_set_tuning(const char* name, int value);
 
 /* ---- host-side parameter helpers (run once per material, like the Julia constructors) ------ */
