@@ -613,6 +613,21 @@ def other_configs(mm, torch, dev, peak):
         dB = mm.synth_uniform(N, nc, seed, lo, hi, device=dev)
         ms = _time_kernel(torch, lambda: mm.material_response(cm, dB, stA, 1.0, options={"defer_check": True}), reps=3, warm=1)
         _, _, stB = mm.material_response(cm, dB, stA, 1.0, options={"defer_check": True})
+        # the dense branch-free Newton pass (rounds 1 / early 2) on the same inputs in the same run, beside the default active-set path
+        ms_dense = None
+        try:
+            import materialmodels_jl_b200._lib as _L
+            _lib = _L.load()
+            _old = _lib.mm_set_tuning(b"crystal_variant", 0)
+            try:
+                ms_dense = _time_kernel(torch, lambda: mm.material_response(cm, dB, stA, 1.0, options={"defer_check": True}), reps=3, warm=1)
+                _, _, stB0 = mm.material_response(cm, dB, stA, 1.0, options={"defer_check": True})
+                same_counts = bool(torch.equal(stB0.iters, stB.iters) and torch.equal(stB0.flags, stB.flags))
+                del stB0
+            finally:
+                _lib.mm_set_tuning(b"crystal_variant", _old)
+        except Exception:
+            same_counts = None
         Ne = 4 * 10**6
         hd = mm.PinnedArray((6, Ne)).array
         hs = mm.PinnedArray((42, Ne)).array
@@ -653,7 +668,8 @@ def other_configs(mm, torch, dev, peak):
         f64 = fp64_peak_tflops()
         rec("c3_crystal_fcc12_stepB", N, 1056, ms, mean_newton_updates=float(it.mean().item()), frac_points_with_active_slip=float((stB.flags != 0).float().mean().item()),
             n_not_converged=int(stB.n_fail.item()), reference_algorithm_tflops=round(ref_flops / (ms * 1e-3) / 1e12, 2), fp64_fma_peak_tflops_measured=f64,
-            bound="fp64 issue / latency (not HBM)", roofline=crystal_roofline(N, ms, f64), e2e=e2e_c)
+            bound="fp64 issue / latency (not HBM)", roofline=crystal_roofline(N, ms, f64), e2e=e2e_c,
+            dense_pass_ms_same_run=ms_dense, masks_and_newton_counts_equal_dense_pass_all_points=same_counts)
     except Exception as e:       # informational block must never cost the headline line
         out["error"] = repr(e)
     return out

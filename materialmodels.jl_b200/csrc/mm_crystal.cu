@@ -285,12 +285,12 @@ struct CrystalSched { const uint16_t* order; const uint16_t* hc; int* heavy_idx;
 #define MM_CRYSTAL_ASET_MINBLOCKS 8   // 16 resident warps (128 registers, 48 scratch slots per lane): 12.40 ms per 1e7 points against 13.14 (6 blocks) / 12.74 (7), profiles/r02_crystal_aset_occupancy.log
 #endif
 template <bool HASQ, bool INTPOW, int LAYOUT, int BS, int PASS>      // PASS: 0 dense, 1 sparse, 2 active-set (q = 0; its own, smaller scratch layout)
-__global__ void __launch_bounds__(BS, PASS == 2 ? MM_CRYSTAL_ASET_MINBLOCKS : MM_CRYSTAL_MINBLOCKS)
+__global__ void __launch_bounds__(BS, PASS == 2 ? (HASQ ? MM_CRYSTAL_ASET_MINBLOCKS - 1 : MM_CRYSTAL_ASET_MINBLOCKS) : MM_CRYSTAL_MINBLOCKS)      // (q != 0: 54 scratch slots, 7 blocks)
 crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, uint16_t* iters, double* xbuf, const int64_t N, int chunk, const int thresh, const int* cnt, const int* idx, const int rw8,
                       const CrystalSched sched) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
-    double* tab = sm_scratch + (PASS == 2 ? MM_CRYSTAL_SCRATCH_ASET : MM_CRYSTAL_SCRATCH) * BS;
+    double* tab = sm_scratch + (PASS == 2 ? (HASQ ? MM_CRYSTAL_SCRATCH_ASET_Q : MM_CRYSTAL_SCRATCH_ASET) : MM_CRYSTAL_SCRATCH) * BS;
     double sigt[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};          // active-set pass: σ_trial of the lane's point
     if (PASS != 0) {
         for (int e = threadIdx.x; e < MM_CRYSTAL_TAB; e += BS) crystal_fill_tab(k, tab, e);
@@ -333,7 +333,7 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
         if (working == 0u) break;
         if (PASS == 2) {
             const unsigned lanes = __ballot_sync(FULL, has_work && !finished);
-            if (has_work && !finished) finished = crystal_iterate_aset(k, tab, scr, L, sigt, lanes);
+            if (has_work && !finished) finished = crystal_iterate_aset<HASQ>(k, tab, scr, L, sigt, lanes);
         } else if (has_work && !finished) {
             if (PASS == 1) finished = crystal_iterate_sparse<HASQ, false>(k, tab, scr, L);
             else           finished = crystal_iterate<HASQ, INTPOW, false>(k, scr, L);
@@ -439,18 +439,18 @@ template <bool HASQ, bool INTPOW, int LAYOUT>
 int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* iters, int32_t* n_fail, const Ptrs<2, 3>& ptrs, double* xbuf, int64_t N, cudaStream_t st, const int* cnt, const int* idx, int* n_general) {
     constexpr int BS = MM_CRYSTAL_BS, FBS = MM_CRYSTAL_FINISH_BS;
     constexpr size_t smem = (size_t)(MM_CRYSTAL_SCRATCH * BS + MM_CRYSTAL_TAB) * sizeof(double), fsmem = (size_t)MM_CRYSTAL_SCRATCH * FBS * sizeof(double);
-    constexpr size_t smem_aset = (size_t)(MM_CRYSTAL_SCRATCH_ASET * BS + MM_CRYSTAL_TAB) * sizeof(double);      // (only when AS == 2)
+    constexpr size_t smem_aset = (size_t)((HASQ ? MM_CRYSTAL_SCRATCH_ASET_Q : MM_CRYSTAL_SCRATCH_ASET) * BS + MM_CRYSTAL_TAB) * sizeof(double);      // (only when AS == 2)
     // "crystal_variant" (mm_set_tuning / MM_CRYSTAL_VARIANT): 0 = dense branch-free pass, 1 = sparse per-lane pass, 2 = phased pass.
     // Measured on configs[3] (1e7 points, step B, profiles/r02_crystal_variants.jsonl + r02_crystal_*_ncu.txt): dense 21.9 ms, sparse 21.9 ms,
     // phased 25.6 ms — the sparse pass does HALF the thread-level work of the dense one but leaves 15 of 32 lanes active per instruction, the
     // phased pass (unrolled, constant-bank operands) outgrows the 32 KB instruction cache (23 % no_instruction stalls).  Tests run all of them.
     // 3 / 4 = sparse / dense pass over chunks re-ordered by first-pass candidate count (crystal_presort_kernel); 5 = active-set pass over re-ordered
-    // chunks, 6 = active-set pass in the natural order (the DEFAULT for integer m, q = 0: 18.3 ms; 5: 19.6 ms, profiles/r02_crystal_aset_*).  With cross
-    // hardening 5 / 6 run the sparse pass and the default stays the dense pass.
-    // default: cross hardening keeps the dense pass; q = 0: the active-set pass, over re-ordered chunks for AoS arrays (a point's rows are contiguous there, so
-    // the re-ordered refills stay coalesced: 18.6 against 20.3 ms) and in the natural order for SoA arrays (18.2 against 19.1 ms; profiles/r02_crystal_aset_ab_*.jsonl)
-    const int variant = crystal_knobs().variant < 0 ? (HASQ ? 0 : (LAYOUT == 1 ? 5 : 6)) : crystal_knobs().variant;
-    constexpr int SP = INTPOW ? 1 : 0, AS = (INTPOW && !HASQ) ? 2 : SP;     // instantiations that do not apply collapse onto one that does
+    // chunks, 6 = active-set pass in the natural order (18.3 ms; 5: 19.6 ms on SoA arrays, profiles/r02_crystal_aset_*).
+    // default (integer m): the active-set pass, over re-ordered chunks for AoS arrays (a point's rows are contiguous there, so the re-ordered refills
+    // stay coalesced: 18.6 against 20.3 ms) and in the natural order for SoA arrays (18.2 against 19.1 ms; profiles/r02_crystal_aset_ab_*.jsonl);
+    // with cross hardening 24.8 against 27.6 ms for the dense pass (profiles/r02_crystal_aset_cross_hardening.log)
+    const int variant = crystal_knobs().variant < 0 ? (LAYOUT == 1 ? 5 : 6) : crystal_knobs().variant;
+    constexpr int SP = INTPOW ? 1 : 0, AS = INTPOW ? 2 : SP;     // instantiations that do not apply collapse onto one that does
     const int pass = !INTPOW ? 0 : ((variant == 1 || variant == 3) ? 1 : (((variant == 5 || variant == 6) && N < ((int64_t)1 << 31)) ? AS : 0));       // (the hand-over list holds 32-bit indices)
     const bool presort = INTPOW && (variant == 3 || variant == 4 || variant == 5) && !cnt && !idx;
     static SmemOptIn optin_newton, optin_newton_sparse, optin_newton_aset, optin_finish;

@@ -839,11 +839,12 @@ MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, C
 // `lanes`: the lanes of the warp that execute this call together (device: ballot of the caller's condition).
 // Scratch of the active-set kernel (48 slots per lane, so that 16 warps are resident): [0,12) κₙ [12,24) αₙ [24,36) x=μ, then BY LIST POSITION
 // [36,42) g [42,48) D⁻¹r; σ_trial stays in registers.
-constexpr int MM_CRYSTAL_SCRATCH_ASET = 48, XSA = 24, GPA = 36, RPA = 42;
-template <int KM, class Scr>
+// With cross hardening (q != 0) six more slots [48,54) by list position: b_h p / D (the rank-1 column of the Jacobian).
+constexpr int MM_CRYSTAL_SCRATCH_ASET = 48, MM_CRYSTAL_SCRATCH_ASET_Q = 54, XSA = 24, GPA = 36, RPA = 42, HPA = 48;
+template <int KM, bool HASQ, class Scr>
 MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const unsigned cand, const unsigned mask) {
     int a[KM];
-    double w[KM], b[KM];
+    double w[KM], b[KM], hs[HASQ ? KM : 1], sgv[HASQ ? KM : 1];
     unsigned rest = cand;
 #pragma unroll
     for (int u = 0; u < KM; ++u) {
@@ -853,6 +854,7 @@ MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const
         const double si = crystal_sign(L, a[u]);
         w[u] = live ? -si * scr(GPA + u) : 0.0;
         b[u] = live ? si * scr(RPA + u) : 0.0;
+        if (HASQ) { hs[HASQ ? u : 0] = live ? si * scr(HPA + u) : 0.0; sgv[HASQ ? u : 0] = live ? si : 0.0; }     // cross hardening: row factor s_u b_h p_u / D_uu, column factor s_v
     }
     double Nm[KM][KM];
 #pragma unroll
@@ -867,6 +869,12 @@ MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const
     for (int u = 0; u < KM; ++u)
 #pragma unroll
         for (int v = u; v < KM; ++v) Nm[u][v] = (u == v) ? fma(w[u], Nm[u][v], 1.0) : w[u] * Nm[u][v];
+    if (HASQ) {                                                                         // − (s_u h_u) s_v : the cross-hardening column p̂ 1ᵀ on the list (I + W (G + b_h s sᵀ) while no sign flipped)
+#pragma unroll
+        for (int u = 0; u < KM; ++u)
+#pragma unroll
+            for (int v = 0; v < KM; ++v) Nm[u][v] -= hs[HASQ ? u : 0] * sgv[HASQ ? v : 0];
+    }
     bool ok = true;
 #pragma unroll
     for (int q = 0; q < KM; ++q) {
@@ -911,17 +919,21 @@ MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const
     return false;
 }
 
-template <class Scr>
+template <bool HASQ, class Scr>
 MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L, const double* sigt, const unsigned lanes) {
     // 1. σ = σ_trial − Σ_{x_j != 0} x_j s_j Eᵉ:MS_j                                        :131
 #pragma unroll
     for (int c = 0; c < 6; ++c) L.sig[c] = sigt[c];
+    double sumx = 0.0;
     for (unsigned m = L.nz; m != 0u; m &= m - 1u) {
         const int j = __ffs_(m);
-        const double f = scr(XSA + j) * crystal_sign(L, j);
+        const double xj = scr(XSA + j);
+        const double f = xj * crystal_sign(L, j);
+        if (HASQ) sumx += xj;
 #pragma unroll
         for (int c = 0; c < 6; ++c) L.sig[c] -= f * tab[72 + c * 12 + j];
     }
+    const double kq = HASQ ? k.b_h * sumx : 0.0;                                        // κ_i = κₙ_i + a_h x_i + b_h Σ x   (:127, H = a I + b 11ᵀ)
     // 2. uniform yield test
     unsigned cand = L.nz;
 #pragma unroll 4
@@ -929,7 +941,9 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
         double tau = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) tau += L.sig[c] * k.Pw[i][c];
-        const double Phi = fabs(tau - scr(12 + i)) - k.tau_y - scr(i);
+        double kap = scr(i);
+        if (HASQ) kap += kq;
+        const double Phi = fabs(tau - scr(12 + i)) - k.tau_y - kap;
         cand |= (!(Phi <= 0.0)) ? (1u << i) : 0u;                                       // Φ > 0, or NaN (handled by the full chain)
     }
     L.cand = cand;
@@ -962,13 +976,14 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
         ii[0] = __ffs_(m); m &= m - 1u;
         const bool two = m != 0u;
         ii[1] = two ? __ffs_(m) : ii[0]; m &= m - 1u;
-        double gg[2], rr[2], R2[2];
+        double gg[2], rr[2], R2[2], hh[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int i = ii[u];
             const bool live = (u == 0) | two;
             const double si = crystal_sign(L, i), xi = scr(XSA + i);
-            const double kap = scr(i) + k.a_h * xi;                                     // :127 with H = a I (q = 0)
+            double kap = scr(i) + k.a_h * xi;                                           // :127 with H = a I + b 11ᵀ
+            if (HASQ) kap += kq;
             const double iden = rcp_nc(1.0 + k.hk_ai * xi);
             const double al = (scr(12 + i) + k.H_kin * xi * si) * iden;                 // :128
             double tau = 0.0;
@@ -990,11 +1005,12 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
             const double invD = act ? -rcp_nc(dD) : k.mits;
             rr[u] = Ri * invD;
             gg[u] = (p * sgn) * invD;
+            hh[u] = HASQ ? k.b_h * p * invD : 0.0;
             R2[u] = live ? Ri : 0.0;
         }
         // by list position (an odd tail entry fills a slot nobody reads)
 #pragma unroll
-        for (int u = 0; u < 2; ++u) { scr(GPA + pos + u) = gg[u]; scr(RPA + pos + u) = rr[u]; nrm2 += R2[u] * R2[u]; }
+        for (int u = 0; u < 2; ++u) { scr(GPA + pos + u) = gg[u]; scr(RPA + pos + u) = rr[u]; if (HASQ) scr(HPA + pos + u) = hh[u]; nrm2 += R2[u] * R2[u]; }
     }
     L.mask = mask;
     L.flip = flip;
@@ -1008,15 +1024,15 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
 #define MM_ASET_SIZES 246
 #endif
 #if MM_ASET_SIZES == 246 || MM_ASET_SIZES == 26
-    if (kmax <= 2u) return crystal_aset_solve<2>(tab, scr, L, cand, mask);
+    if (kmax <= 2u) return crystal_aset_solve<2, HASQ>(tab, scr, L, cand, mask);
 #endif
 #if MM_ASET_SIZES == 36
-    if (kmax <= 3u) return crystal_aset_solve<3>(tab, scr, L, cand, mask);
+    if (kmax <= 3u) return crystal_aset_solve<3, HASQ>(tab, scr, L, cand, mask);
 #endif
 #if MM_ASET_SIZES == 246 || MM_ASET_SIZES == 46
-    if (kmax <= 4u) return crystal_aset_solve<4>(tab, scr, L, cand, mask);
+    if (kmax <= 4u) return crystal_aset_solve<4, HASQ>(tab, scr, L, cand, mask);
 #endif
-    return crystal_aset_solve<6>(tab, scr, L, cand, mask);
+    return crystal_aset_solve<6, HASQ>(tab, scr, L, cand, mask);
 }
 
 // ---- PHASED pass (integer m, q = 0): the Newton kernel's default ----------------------------------------------------------------
@@ -1331,15 +1347,15 @@ MM_HD unsigned crystal_point_sparse(const CrystalK& k, Acc& acc, Scr& scr, int* 
 
 // one point start to finish through the ACTIVE-SET pass (host twin of the Newton kernel's default path; integer m, q = 0): the Newton
 // iteration as the kernel runs it, then — like crystal_finish_kernel — one dense evaluation at the converged x for the outputs
-template <class Acc, class Scr>
+template <bool HASQ, class Acc, class Scr>
 MM_HD unsigned crystal_point_aset(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
     double tab[MM_CRYSTAL_TAB];
     for (int e = 0; e < MM_CRYSTAL_TAB; ++e) crystal_fill_tab(k, tab, e);
     CrystalLane L;
     double sigt[6];
     crystal_init_t<XSA, -1>(k, acc, scr, L, sigt);
-    while (!crystal_iterate_aset(k, tab, scr, L, sigt, 0xffffffffu)) {}
-    if (L.big) return crystal_point_sparse<false>(k, acc, scr, iters_out, fallback);          // redone from the start, as the second launch does
+    while (!crystal_iterate_aset<HASQ>(k, tab, scr, L, sigt, 0xffffffffu)) {}
+    if (L.big) return crystal_point_sparse<HASQ>(k, acc, scr, iters_out, fallback);          // redone from the start, as the second launch does
     if (L.bad) { *fallback = true; *iters_out = 0; return 0; }
     {   // the dense evaluation below uses the standard layout: move x, restore σ_trial
         double xs[12];
@@ -1351,10 +1367,10 @@ MM_HD unsigned crystal_point_aset(const CrystalK& k, Acc& acc, Scr& scr, int* it
     const int iters = L.iters;
     double yr[6], nrm2;
     bool bad;
-    crystal_evaluate<false, true>(k, scr, L, yr, &nrm2, &bad);
+    crystal_evaluate<HASQ, true>(k, scr, L, yr, &nrm2, &bad);
     if (bad) { *fallback = true; *iters_out = 0; return 0; }
     L.converged = converged;
-    const unsigned mask = crystal_finalize<false>(k, acc, scr, L, fallback);
+    const unsigned mask = crystal_finalize<HASQ>(k, acc, scr, L, fallback);
     *iters_out = *fallback ? 0 : iters;
     return mask;
 }

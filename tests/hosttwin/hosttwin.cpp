@@ -67,7 +67,7 @@ int twin_xu(const MMXuNeedleman* p, const double* jump, double* T, double* H, in
 }
 struct HostScratch { double v[MM_CRYSTAL_SCRATCH + 8]; double& operator()(int j) { return v[j]; } };     // 72 slots for the phased pass
 
-// mode 0: general pivoted path; mode 1: structured fast path (falls back like the kernel does); mode 2: the same through the sparse pass; mode 3: through the phased pass (q = 0; else as mode 2); mode 4: through the active-set pass (q = 0; else as mode 2)
+// mode 0: general pivoted path; mode 1: structured fast path (falls back like the kernel does); mode 2: the same through the sparse pass; mode 3: through the phased pass (q = 0; else as mode 2); mode 4: through the active-set pass
 int twin_crystal_mode(const MMCrystal* p, const double* deps, double dt, const double* sin, double* sig, double* tan, double* sout, uint16_t* active,
                       uint16_t* iters, double tol, int max_iter, int64_t N, int mode, int64_t* n_fallback) {
     mm::CrystalK k;
@@ -80,7 +80,7 @@ int twin_crystal_mode(const MMCrystal* p, const double* deps, double dt, const d
         if (mode == 0 || !k.h_struct) m = mm::crystal_point(k, a, &it);
         else {
             HostScratch scr; bool fb = false;
-            if (mode == 4 && k.m_int && k.b_h == 0.0) m = mm::crystal_point_aset(k, a, scr, &it, &fb);
+            if (mode == 4 && k.m_int) m = (k.b_h != 0.0) ? mm::crystal_point_aset<true>(k, a, scr, &it, &fb) : mm::crystal_point_aset<false>(k, a, scr, &it, &fb);
             else if (mode == 3 && k.m_int && k.b_h == 0.0) m = mm::crystal_point_phased(k, a, scr, &it, &fb);
             else if (mode >= 2 && k.m_int) m = (k.b_h != 0.0) ? mm::crystal_point_sparse<true>(k, a, scr, &it, &fb) : mm::crystal_point_sparse<false>(k, a, scr, &it, &fb);
             else m = (k.b_h != 0.0) ? mm::crystal_point_fast<true>(k, a, scr, &it, &fb) : mm::crystal_point_fast<false>(k, a, scr, &it, &fb);
