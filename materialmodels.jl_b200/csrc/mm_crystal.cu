@@ -333,9 +333,9 @@ crystal_newton_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, ui
         if (working == 0u) break;
         if (PASS == 2) {
             const unsigned lanes = __ballot_sync(FULL, has_work && !finished);
-            if (has_work && !finished) finished = crystal_iterate_aset<HASQ>(k, tab, scr, L, sigt, lanes);
+            if (has_work && !finished) finished = crystal_iterate_aset<HASQ, INTPOW>(k, tab, scr, L, sigt, lanes);
         } else if (has_work && !finished) {
-            if (PASS == 1) finished = crystal_iterate_sparse<HASQ, false>(k, tab, scr, L);
+            if (PASS == 1) finished = crystal_iterate_sparse<HASQ, false, INTPOW>(k, tab, scr, L);
             else           finished = crystal_iterate<HASQ, INTPOW, false>(k, scr, L);
         }
         const unsigned fin = __ballot_sync(FULL, has_work && finished);
@@ -446,13 +446,13 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     // phased pass (unrolled, constant-bank operands) outgrows the 32 KB instruction cache (23 % no_instruction stalls).  Tests run all of them.
     // 3 / 4 = sparse / dense pass over chunks re-ordered by first-pass candidate count (crystal_presort_kernel); 5 = active-set pass over re-ordered
     // chunks, 6 = active-set pass in the natural order (18.3 ms; 5: 19.6 ms on SoA arrays, profiles/r02_crystal_aset_*).
-    // default (integer m): the active-set pass, over re-ordered chunks for AoS arrays (a point's rows are contiguous there, so the re-ordered refills
+    // default: the active-set pass, over re-ordered chunks for AoS arrays (a point's rows are contiguous there, so the re-ordered refills
     // stay coalesced: 18.6 against 20.3 ms) and in the natural order for SoA arrays (18.2 against 19.1 ms; profiles/r02_crystal_aset_ab_*.jsonl);
     // with cross hardening 24.8 against 27.6 ms for the dense pass (profiles/r02_crystal_aset_cross_hardening.log)
     const int variant = crystal_knobs().variant < 0 ? (LAYOUT == 1 ? 5 : 6) : crystal_knobs().variant;
-    constexpr int SP = INTPOW ? 1 : 0, AS = INTPOW ? 2 : SP;     // instantiations that do not apply collapse onto one that does
-    const int pass = !INTPOW ? 0 : ((variant == 1 || variant == 3) ? 1 : (((variant == 5 || variant == 6) && N < ((int64_t)1 << 31)) ? AS : 0));       // (the hand-over list holds 32-bit indices)
-    const bool presort = INTPOW && (variant == 3 || variant == 4 || variant == 5) && !cnt && !idx;
+    constexpr int SP = 1, AS = 2;
+    const int pass = (variant == 1 || variant == 3) ? 1 : (((variant == 5 || variant == 6) && N < ((int64_t)1 << 31)) ? AS : 0);       // (the hand-over list holds 32-bit indices)
+    const bool presort = (variant == 3 || variant == 4 || variant == 5) && !cnt && !idx;
     static SmemOptIn optin_newton, optin_newton_sparse, optin_newton_aset, optin_finish;
     if (int rc = ensure_smem(optin_newton, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, 0>, smem, "mm_crystal")) return rc;
     if (int rc = ensure_smem(optin_newton_sparse, crystal_newton_kernel<HASQ, INTPOW, LAYOUT, BS, SP>, smem, "mm_crystal")) return rc;

@@ -402,6 +402,14 @@ template <int NPOW> MM_HD double powc_(double b) {      // the multiplication se
 }
 
 // XSLOT: first scratch slot of x; SIGSLOT: first slot of σ_trial, or -1 = returned in st_out only (the compact layout of the active-set kernel)
+// x^(m−1) of :111 in the per-lane-list passes (sparse, active-set).  Integer m: by multiplications (m = 10: straight-line x^9).  General m: pow() for
+// the active systems; an inactive one carries x = ∓0 (or NaN), whose power is the same zero (or NaN).  INTPOW is a template parameter: the integer
+// instantiation carries no pow() code (a run-time branch on m cost the m = 10 kernel 5 % more instructions).
+template <bool INTPOW> MM_HD double crystal_pow_m1(const CrystalK& k, double xx, bool act) {
+    if (INTPOW) { const int npow = k.m_int - 1; return (npow == 9) ? powc_<9>(xx) : powi6_(xx, npow); }
+    return act ? pow(xx, k.m - 1.0) : xx;
+}
+
 template <int XSLOT, int SIGSLOT, class KT, class Acc, class Scr>       // KT: CrystalK or CrystalNK (reads lam, G, Pw only)
 MM_HD void crystal_init_t(const KT& k, Acc& acc, Scr& scr, CrystalLane& L, double* st_out) {
     const double G2 = 2.0 * k.G;
@@ -633,8 +641,8 @@ MM_HD void crystal_fill_tab(const CrystalK& k, double* tab, int e) {      // e i
 #if defined(MM_CRYSTAL_STATS) && !defined(__CUDA_ARCH__)
 void mm_crystal_stats_pass(unsigned nz, unsigned cand);       // host-twin instrumentation (tests/hosttwin)
 #endif
-template <bool HASQ, bool KEEPK, class Scr> MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L, const unsigned cand, const double kq);
-template <bool HASQ, bool KEEPK, class Scr>
+template <bool HASQ, bool KEEPK, bool INTPOW, class Scr> MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L, const unsigned cand, const double kq);
+template <bool HASQ, bool KEEPK, bool INTPOW = true, class Scr>
 MM_HD bool crystal_iterate_sparse(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L) {
     double sumx = 0.0;
     // 1. σ = σ_trial − Σ_{x_j != 0} x_j s_j Eᵉ:MS_j                                        :131
@@ -668,11 +676,11 @@ MM_HD bool crystal_iterate_sparse(const CrystalK& k, const double* tab, Scr& scr
 #if defined(MM_CRYSTAL_STATS) && !defined(__CUDA_ARCH__)
     mm_crystal_stats_pass(L.nz, cand);
 #endif
-    return crystal_sparse_tail<HASQ, KEEPK>(k, tab, scr, L, cand, kq);
+    return crystal_sparse_tail<HASQ, KEEPK, INTPOW>(k, tab, scr, L, cand, kq);
 }
 
 // steps 3 and 4 of the sparse pass (6x6 SPD route): the chains of the candidates, M, the test, the update
-template <bool HASQ, bool KEEPK, class Scr>
+template <bool HASQ, bool KEEPK, bool INTPOW, class Scr>
 MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L, const unsigned cand, const double kq) {
     double yr[6], nrm2 = 0.0;
     // 3. full chain for the candidates — TWO list entries per trip: one chain is a ~30-level dependency ladder (reciprocal -> α -> Φ -> power ->
@@ -687,7 +695,6 @@ MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, C
     for (int c = 0; c < 6; ++c) { yr[c] = 0.0; L.yp[c] = 0.0; }
     unsigned mask = 0;
     bool bad = false, flip = false;
-    const int npow = k.m_int - 1;
     for (unsigned m = cand; m != 0u;) {
         int ii[2];
         ii[0] = __ffs_(m); m &= m - 1u;
@@ -713,7 +720,7 @@ MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, C
             const double Phi = fabs(red) - k.tau_y - kap;                                // :110
             const bool act = Phi > 0.0;
             const double xx = act ? Phi * k.isc : Phi * 0.0;
-            const double pw1 = (npow == 9) ? powc_<9>(xx) : powi6_(xx, npow);
+            const double pw1 = crystal_pow_m1<INTPOW>(k, xx, act);
             const double Ri = k.dt * (pw1 * xx) - k.t_star * xi;                        // :111
             const double p = k.dtm_sc * pw1;
             mask |= (act & live) ? (1u << i) : 0u;
@@ -919,7 +926,7 @@ MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const
     return false;
 }
 
-template <bool HASQ, class Scr>
+template <bool HASQ, bool INTPOW = true, class Scr>
 MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, CrystalLane& L, const double* sigt, const unsigned lanes) {
     // 1. σ = σ_trial − Σ_{x_j != 0} x_j s_j Eᵉ:MS_j                                        :131
 #pragma unroll
@@ -969,7 +976,6 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
     double nrm2 = 0.0;
     unsigned mask = 0;
     bool bad = false, flip = false;
-    const int npow = k.m_int - 1;
     int pos = 0;
     for (unsigned m = cand; m != 0u; pos += 2) {
         int ii[2];
@@ -994,7 +1000,7 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
             const double Phi = fabs(red) - k.tau_y - kap;                                // :110
             const bool act = Phi > 0.0;
             const double xx = act ? Phi * k.isc : Phi * 0.0;
-            const double pw1 = (npow == 9) ? powc_<9>(xx) : powi6_(xx, npow);
+            const double pw1 = crystal_pow_m1<INTPOW>(k, xx, act);
             const double Ri = k.dt * (pw1 * xx) - k.t_star * xi;                        // :111
             const double p = k.dtm_sc * pw1;
             mask |= (act & live) ? (1u << i) : 0u;
@@ -1339,7 +1345,8 @@ MM_HD unsigned crystal_point_sparse(const CrystalK& k, Acc& acc, Scr& scr, int* 
     for (int e = 0; e < MM_CRYSTAL_TAB; ++e) crystal_fill_tab(k, tab, e);
     CrystalLane L;
     crystal_init(k, acc, scr, L);
-    while (!crystal_iterate_sparse<HASQ, true>(k, tab, scr, L)) {}
+    if (k.m_int) { while (!crystal_iterate_sparse<HASQ, true, true>(k, tab, scr, L)) {} }
+    else         { while (!crystal_iterate_sparse<HASQ, true, false>(k, tab, scr, L)) {} }
     const unsigned mask = crystal_finalize<HASQ>(k, acc, scr, L, fallback);
     *iters_out = *fallback ? 0 : L.iters;
     return mask;
@@ -1354,7 +1361,8 @@ MM_HD unsigned crystal_point_aset(const CrystalK& k, Acc& acc, Scr& scr, int* it
     CrystalLane L;
     double sigt[6];
     crystal_init_t<XSA, -1>(k, acc, scr, L, sigt);
-    while (!crystal_iterate_aset<HASQ>(k, tab, scr, L, sigt, 0xffffffffu)) {}
+    if (k.m_int) { while (!crystal_iterate_aset<HASQ, true>(k, tab, scr, L, sigt, 0xffffffffu)) {} }
+    else         { while (!crystal_iterate_aset<HASQ, false>(k, tab, scr, L, sigt, 0xffffffffu)) {} }
     if (L.big) return crystal_point_sparse<HASQ>(k, acc, scr, iters_out, fallback);          // redone from the start, as the second launch does
     if (L.bad) { *fallback = true; *iters_out = 0; return 0; }
     {   // the dense evaluation below uses the standard layout: move x, restore σ_trial
@@ -1367,7 +1375,8 @@ MM_HD unsigned crystal_point_aset(const CrystalK& k, Acc& acc, Scr& scr, int* it
     const int iters = L.iters;
     double yr[6], nrm2;
     bool bad;
-    crystal_evaluate<HASQ, true>(k, scr, L, yr, &nrm2, &bad);
+    if (k.m_int) crystal_evaluate<HASQ, true>(k, scr, L, yr, &nrm2, &bad);
+    else         crystal_evaluate<HASQ, false>(k, scr, L, yr, &nrm2, &bad);
     if (bad) { *fallback = true; *iters_out = 0; return 0; }
     L.converged = converged;
     const unsigned mask = crystal_finalize<HASQ>(k, acc, scr, L, fallback);

@@ -80,9 +80,9 @@ int twin_crystal_mode(const MMCrystal* p, const double* deps, double dt, const d
         if (mode == 0 || !k.h_struct) m = mm::crystal_point(k, a, &it);
         else {
             HostScratch scr; bool fb = false;
-            if (mode == 4 && k.m_int) m = (k.b_h != 0.0) ? mm::crystal_point_aset<true>(k, a, scr, &it, &fb) : mm::crystal_point_aset<false>(k, a, scr, &it, &fb);
+            if (mode == 4) m = (k.b_h != 0.0) ? mm::crystal_point_aset<true>(k, a, scr, &it, &fb) : mm::crystal_point_aset<false>(k, a, scr, &it, &fb);
             else if (mode == 3 && k.m_int && k.b_h == 0.0) m = mm::crystal_point_phased(k, a, scr, &it, &fb);
-            else if (mode >= 2 && k.m_int) m = (k.b_h != 0.0) ? mm::crystal_point_sparse<true>(k, a, scr, &it, &fb) : mm::crystal_point_sparse<false>(k, a, scr, &it, &fb);
+            else if (mode >= 2) m = (k.b_h != 0.0) ? mm::crystal_point_sparse<true>(k, a, scr, &it, &fb) : mm::crystal_point_sparse<false>(k, a, scr, &it, &fb);
             else m = (k.b_h != 0.0) ? mm::crystal_point_fast<true>(k, a, scr, &it, &fb) : mm::crystal_point_fast<false>(k, a, scr, &it, &fb);
             if (fb) { ++nfb; m = mm::crystal_point(k, a, &it); }
         }
