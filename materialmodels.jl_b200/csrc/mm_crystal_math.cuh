@@ -826,7 +826,7 @@ MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, C
     return false;
 }
 
-// ---- ACTIVE-SET pass (integer m, q = 0): the Newton kernel's default ------------------------------------------------------------
+// ---- ACTIVE-SET pass: the Newton kernel's default ---------------------------------------------------------------------------------
 // The sparse pass still pays, per Newton pass, for the 6x6 machinery of the Woodbury split: 27 FP64 instructions per candidate to accumulate
 // M, 6 for y_r, 6 for Pw_i·z, and a 6x6 LDLᵀ + solve (≈ 160, a ladder of six dependent reciprocals) — although on configs[3] a pass has
 // 3.0 candidates on average, at most 2 in 47 %, 4 in 83 % and 6 in 96 % of all passes (tools/crystal_sched_sim.py).  Here the Newton step is
@@ -1027,7 +1027,7 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
     if (nrm2 < k.tol2_lo || (nrm2 <= k.tol2_hi && sqrt(nrm2) < k.tol)) { L.converged = true; return true; }
     // 4. (I + W G) δ' = s ∘ D⁻¹r on the list, elimination without pivoting                 nonlinear_solver.jl:59
 #ifndef MM_ASET_SIZES
-#define MM_ASET_SIZES 246
+#define MM_ASET_SIZES 246      // solve sizes compiled in (tuning macro): 246 = {2, 4, 6}; 6, 26, 36, 46 measured within 0.5 % (profiles/r02_crystal_aset_split_kernels.log)
 #endif
 #if MM_ASET_SIZES == 246 || MM_ASET_SIZES == 26
     if (kmax <= 2u) return crystal_aset_solve<2, HASQ>(tab, scr, L, cand, mask);
@@ -1041,7 +1041,7 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
     return crystal_aset_solve<6, HASQ>(tab, scr, L, cand, mask);
 }
 
-// ---- PHASED pass (integer m, q = 0): the Newton kernel's default ----------------------------------------------------------------
+// ---- PHASED pass (integer m, q = 0): measured slower, kept selectable (crystal_variant 2) ----------------------------------------------------------------
 // ncu on the two passes above (profiles/r02_crystal_dense_vs_sparse_ncu.txt): the dense pass executes 87.7e9 thread-instructions per
 // 2e6 points, the sparse one 44.9e9 — half the work — but only 16 % fewer WARP instructions, because the per-lane system lists leave
 // 15 of 32 lanes active per instruction.  And in both, ~45 % of the issued instructions are not FP64 math: run-time-indexed constant
@@ -1338,7 +1338,7 @@ MM_HD unsigned crystal_finalize(const CrystalK& k, Acc& acc, Scr& scr, CrystalLa
     return mask;
 }
 
-// one point start to finish through the SPARSE pass (host twin of the Newton kernel's default path; integer m only)
+// one point start to finish through the SPARSE pass (host twin of crystal_variant 1 and of the heavy-point launch)
 template <bool HASQ, class Acc, class Scr>
 MM_HD unsigned crystal_point_sparse(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
     double tab[MM_CRYSTAL_TAB];
@@ -1352,7 +1352,7 @@ MM_HD unsigned crystal_point_sparse(const CrystalK& k, Acc& acc, Scr& scr, int* 
     return mask;
 }
 
-// one point start to finish through the ACTIVE-SET pass (host twin of the Newton kernel's default path; integer m, q = 0): the Newton
+// one point start to finish through the ACTIVE-SET pass (host twin of the Newton kernel's default path): the Newton
 // iteration as the kernel runs it, then — like crystal_finish_kernel — one dense evaluation at the converged x for the outputs
 template <bool HASQ, class Acc, class Scr>
 MM_HD unsigned crystal_point_aset(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
@@ -1384,7 +1384,7 @@ MM_HD unsigned crystal_point_aset(const CrystalK& k, Acc& acc, Scr& scr, int* it
     return mask;
 }
 
-// one point start to finish through the PHASED pass (host twin of the Newton kernel's default path; integer m, q = 0)
+// one point start to finish through the PHASED pass (host twin of crystal_variant 2; integer m, q = 0)
 template <class Acc, class Scr>
 MM_HD unsigned crystal_point_phased(const CrystalK& k, Acc& acc, Scr& scr, int* iters_out, bool* fallback) {
     CrystalNK nk;
