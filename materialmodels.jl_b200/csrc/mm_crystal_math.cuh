@@ -389,6 +389,15 @@ MM_HD double sign_of(double x) {
     return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : 0.0);
 #endif
 }
+// s_i · v for a system whose frozen sign is ±1 (every candidate of the active-set pass: a zero sign sends the point to the sparse launch first):
+// the sign bit of v is flipped in the integer pipe instead of a DMUL with an assembled ±1.0
+MM_HD double crystal_apply_sign(const CrystalLane& L, int i, double v) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (int)(((L.sneg >> i) & 1u) << 31), __double2loint(v));
+#else
+    return ((L.sneg >> i) & 1u) ? -v : v;
+#endif
+}
 // b^n, n = NPOW known at compile time (the reference's m = 10 -> x^9: three squarings and one product, no predicates)
 template <int NPOW> MM_HD double powc_(double b) {      // the multiplication sequence of powi6_ with the tests folded away
     double r = (NPOW & 1) ? b : 1.0;
@@ -845,7 +854,7 @@ MM_HD bool crystal_sparse_tail(const CrystalK& k, const double* tab, Scr& scr, C
 // Same Newton iterates up to rounding (masks and counts against the oracle: tests).
 // `lanes`: the lanes of the warp that execute this call together (device: ballot of the caller's condition).
 // Scratch of the active-set kernel (48 slots per lane, so that 16 warps are resident): [0,12) κₙ [12,24) αₙ [24,36) x=μ, then BY LIST POSITION
-// [36,42) g [42,48) D⁻¹r; σ_trial stays in registers.
+// [36,42) w = −s g [42,48) s D⁻¹r; σ_trial stays in registers.
 // With cross hardening (q != 0) six more slots [48,54) by list position: b_h p / D (the rank-1 column of the Jacobian).
 constexpr int MM_CRYSTAL_SCRATCH_ASET = 48, MM_CRYSTAL_SCRATCH_ASET_Q = 54, XSA = 24, GPA = 36, RPA = 42, HPA = 48;
 template <int KM, bool HASQ, class Scr>
@@ -858,10 +867,9 @@ MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const
         const bool live = rest != 0u;
         a[u] = live ? __ffs_(rest) : 0;
         rest &= rest - 1u;
-        const double si = crystal_sign(L, a[u]);
-        w[u] = live ? -si * scr(GPA + u) : 0.0;
-        b[u] = live ? si * scr(RPA + u) : 0.0;
-        if (HASQ) { hs[HASQ ? u : 0] = live ? si * scr(HPA + u) : 0.0; sgv[HASQ ? u : 0] = live ? si : 0.0; }     // cross hardening: row factor s_u b_h p_u / D_uu, column factor s_v
+        w[u] = live ? scr(GPA + u) : 0.0;                                               // the chains stored w = −s g, s D⁻¹r (and s b_h p / D) by list position
+        b[u] = live ? scr(RPA + u) : 0.0;
+        if (HASQ) { hs[HASQ ? u : 0] = live ? scr(HPA + u) : 0.0; sgv[HASQ ? u : 0] = live ? crystal_sign(L, a[u]) : 0.0; }     // cross hardening: row factor s_u b_h p_u / D_uu, column factor s_v
     }
     double Nm[KM][KM];
 #pragma unroll
@@ -913,7 +921,7 @@ MM_HD bool crystal_aset_solve(const double* tab, Scr& scr, CrystalLane& L, const
         if (rest != 0u) {
             const int i = a[u];
             const double xo = scr(XSA + i);
-            double xn = xo - crystal_sign(L, i) * b[u];
+            double xn = xo - crystal_apply_sign(L, i, b[u]);
             if (!((mask >> i) & 1u) && fabs(xn) <= 1e-14 * fabs(xo)) xn = 0.0;          // see the sparse pass
             scr(XSA + i) = xn;
             if (xn != 0.0) nz |= (1u << i);
@@ -935,7 +943,7 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
     for (unsigned m = L.nz; m != 0u; m &= m - 1u) {
         const int j = __ffs_(m);
         const double xj = scr(XSA + j);
-        const double f = xj * crystal_sign(L, j);
+        const double f = crystal_apply_sign(L, j, xj);                                  // (a zero frozen sign on the list sends the point to the sparse launch below)
         if (HASQ) sumx += xj;
 #pragma unroll
         for (int c = 0; c < 6; ++c) L.sig[c] -= f * tab[72 + c * 12 + j];
@@ -987,11 +995,11 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
         for (int u = 0; u < 2; ++u) {
             const int i = ii[u];
             const bool live = (u == 0) | two;
-            const double si = crystal_sign(L, i), xi = scr(XSA + i);
+            const double xi = scr(XSA + i);                                             // s_i = ±1 on this list: products with it are sign-bit flips
             double kap = scr(i) + k.a_h * xi;                                           // :127 with H = a I + b 11ᵀ
             if (HASQ) kap += kq;
             const double iden = rcp_nc(1.0 + k.hk_ai * xi);
-            const double al = (scr(12 + i) + k.H_kin * xi * si) * iden;                 // :128
+            const double al = (scr(12 + i) + crystal_apply_sign(L, i, k.H_kin * xi)) * iden;    // :128
             double tau = 0.0;
 #pragma unroll
             for (int c = 0; c < 6; ++c) tau += L.sig[c] * tab[c * 12 + i];             // the yield test's τ_i, bit for bit
@@ -1004,14 +1012,14 @@ MM_HD bool crystal_iterate_aset(const CrystalK& k, const double* tab, Scr& scr, 
             const double Ri = k.dt * (pw1 * xx) - k.t_star * xi;                        // :111
             const double p = k.dtm_sc * pw1;
             mask |= (act & live) ? (1u << i) : 0u;
-            flip = flip | (act & (sgn != si));
-            const double dal = (k.H_kin * si - al * k.hk_ai) * iden;
+            flip = flip | (act & ((red == 0.0) | ((red < 0.0) != (((L.sneg >> i) & 1u) != 0u))));       // sgn_i != s_i
+            const double dal = (crystal_apply_sign(L, i, k.H_kin) - al * k.hk_ai) * iden;
             const double dD = k.t_star + p * (sgn * dal + k.a_h);
             bad = bad | (act & !(dD >= 0.25 * k.t_star));
             const double invD = act ? -rcp_nc(dD) : k.mits;
-            rr[u] = Ri * invD;
-            gg[u] = (p * sgn) * invD;
-            hh[u] = HASQ ? k.b_h * p * invD : 0.0;
+            rr[u] = crystal_apply_sign(L, i, Ri * invD);                                // s (D⁻¹r)_u
+            gg[u] = -crystal_apply_sign(L, i, (p * sgn) * invD);                        // w_u = −s_u g_u
+            hh[u] = HASQ ? crystal_apply_sign(L, i, k.b_h * p * invD) : 0.0;
             R2[u] = live ? Ri : 0.0;
         }
         // by list position (an odd tail entry fills a slot nobody reads)
