@@ -447,8 +447,8 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     // 3 / 4 = sparse / dense pass over chunks re-ordered by first-pass candidate count (crystal_presort_kernel); 5 = active-set pass over re-ordered
     // chunks, 6 = active-set pass in the natural order (18.3 ms; 5: 19.6 ms on SoA arrays, profiles/r02_crystal_aset_*).
     // default: the active-set pass, over re-ordered chunks for AoS arrays (a point's rows are contiguous there, so the re-ordered refills
-    // stay coalesced: 18.6 against 20.3 ms) and in the natural order for SoA arrays (18.2 against 19.1 ms; profiles/r02_crystal_aset_ab_*.jsonl);
-    // with cross hardening 24.8 against 27.6 ms for the dense pass (profiles/r02_crystal_aset_cross_hardening.log)
+    // stay coalesced: 18.0 against 19.3 ms) and in the natural order for SoA arrays (17.0 against 18.1 ms; profiles/r02_crystal_aset_ab_*.jsonl);
+    // with cross hardening 23.1 against 27.6 ms for the dense pass (profiles/r02_crystal_family_final.log)
     const int variant = crystal_knobs().variant < 0 ? (LAYOUT == 1 ? 5 : 6) : crystal_knobs().variant;
     constexpr int SP = 1, AS = 2;
     const int pass = (variant == 1 || variant == 3) ? 1 : (((variant == 5 || variant == 6) && N < ((int64_t)1 << 31)) ? AS : 0);       // (the hand-over list holds 32-bit indices)
