@@ -79,6 +79,9 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
         self.proc.terminate()
+        return self.window(t0, t1)
+
+    def window(self, t0, t1):
         sm, smax, reasons = [], None, set()
         for t, line in self.rows:
             f = [x.strip() for x in line.split(",")]
@@ -243,6 +246,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-full", dest="e2e_full", action="store_false", help="skip the one e2e call at the full 1e8-point size (N=1 only)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-copy-ref", action="store_true", help="skip the device-to-device copy yardstick timed right after the loop")
     ap.add_argument("--no-extra", action="store_true", help="skip the informational timings of the other BASELINE configs")
     args = ap.parse_args()
     claim_stdout()
@@ -302,8 +306,36 @@ def main():
     t_wall1 = time.time()
     sharding.barrier()
     total_ms = ev[0][0].elapsed_time(ev[-1][1])
-    kern_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    kern_ms_in_order = [a.elapsed_time(b) for a, b in ev]
+    kern_ms = sorted(kern_ms_in_order)
+    # the box's own HBM ceiling in the power state the loop above left it in: device-to-device copies (cudaMemcpyAsync through
+    # torch, a library call: a yardstick, not part of the product) for about as long as the timed loop, half of the tangent
+    # buffer onto the other half.  Reported beside `frac`, which stays against MEASURED_PEAKS.json's burst figure.
+    copy_ref = None
+    if rank == 0 and not args.no_copy_ref:
+        try:
+            tb = out["tangent"].view(-1)
+            half = tb.numel() // 2
+            n_copies = max(3, int(round(args.steps * BYTES_PER_POINT * N / (2.0 * 8 * half))))
+            for _ in range(3):
+                tb[half:2 * half].copy_(tb[:half])
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t_copy0 = time.time()
+            c0.record()
+            for _ in range(n_copies):
+                tb[half:2 * half].copy_(tb[:half])
+            c1.record()
+            torch.cuda.synchronize()
+            t_copy1 = time.time()
+            copy_ms = c0.elapsed_time(c1) / n_copies
+            copy_ref = {"gbs": 2.0 * 8 * half / (copy_ms * 1e-3) / 1e9, "copies": n_copies, "bytes_per_copy_read_plus_write": 2 * 8 * half,
+                        "how": "torch copy_ (cudaMemcpyAsync device to device) of one half of the tangent buffer onto the other, back to back right after the timed loop, CUDA events"}
+        except Exception as e:           # a yardstick only: never fails the bench
+            copy_ref = {"error": repr(e)}
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if copy_ref and "gbs" in copy_ref and sampler.proc:
+        copy_ref["clocks"] = sampler.window(t_copy0, t_copy1)
     total_ms_max = sharding.allreduce_max(total_ms, device=dev)
     n_fail = sharding.allreduce_sum(n_fail, device=dev)           # the only "collective" of the path: a tiny control-plane sum
     value = world * N * args.steps / (total_ms_max * 1e-3)
@@ -335,6 +367,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ((traffic or {}).get("dram_bytes_per_point") or 0) * N or None,
                      "kernel": "mm::soa_kernel<mm::PlasticOp,128>", "bytes_per_point": BYTES_PER_POINT, "points_per_launch": N, "kernel_ms_mean": mean_kernel_ms,
                      "kernel_ms_min": kern_ms[0], "kernel_ms_max": kern_ms[-1], "peak_source": peak_src,
+                     "kernel_ms_first5_mean": sum(kern_ms_in_order[:5]) / len(kern_ms_in_order[:5]), "kernel_ms_last5_mean": sum(kern_ms_in_order[-5:]) / len(kern_ms_in_order[-5:]),
+                     "copy_same_run": copy_ref, "frac_of_same_run_copy": (achieved / copy_ref["gbs"]) if copy_ref and "gbs" in copy_ref else None,
                      "traffic_source": ("ncu --set full dram__bytes_read+write = %.1f B/point on a %.0e-point capture (%s), scaled to this launch's point count"
                                         % (traffic["dram_bytes_per_point"], traffic["points_in_capture"], traffic["source"])) if traffic else None},
         "clocks": clocks, "gpu_launches": args.steps,
