@@ -165,111 +165,10 @@ MM_HD double plastic_tangent_entry_lg(double lam, double G, double gxi, const do
 MM_HD double plastic_tangent_entry(const PlasticK& k, const PlasticTangentParts& tp, int I, int J) {
     return plastic_tangent_entry_lg(k.lam, k.G, tp.gxi, tp.u, tp.n, I, J);
 }
-// plastic_newton: the Newton solve of a yielded point on register values — x0 = (σ_trial, κₙ, αₙ, μₙ), `s` / `rho` / `inv_rho` are
-// dev(σ_trial − αₙ), its norm and the reciprocal norm as the yield test left them.  Returns the flag bits (1, or 1 | 0x80 if it failed);
-// the iterate (sg, al, kap, mu) enters holding x0 and leaves holding the solution, n / u / gxi are the tangent's ingredients.  A separate
-// function so that the block-packed SoA kernel (mm_kernels.cuh: plastic_packed_kernel) can run it on ANOTHER lane than the one that owns the point.
-MM_HD int plastic_newton(const PlasticK& k, const double (&st)[6], const double (&al_n)[6], const double kap_n, double (&d6)[6], double (&s)[6], double rho, double inv_rho,
-                         double (&sg)[6], double (&al)[6], double& kap, double& mu, double (&n)[6], double (&u)[6], double& gxi, int& iters, double (&ep)[6]) {
-    const double c1 = 1.2247448713915890491;   // sqrt(3/2)
-    const double r2 = 1.4142135623730950488;   // sqrt(2) (Mandel scaling of the shear residuals)
-    const double G2 = 2.0 * k.G;
-    int flag = 1;
-    double w[6], i1psi, theta, i1eta, iden, ikk, gk;
-    for (;;) {
-        // residuals at x                                                           Plastic.jl:162-172
-        if (iters > 0) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) d6[c] = sg[c] - al[c];
-            dev6(d6, s);
-            inv_rho = fast_rsqrt(ddot6(s, s), &rho);
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) n[c] = s[c] * inv_rho;
-        dev6(al, w);
-        const double kr = kap * k.ikinf - 1.0;
-        double Rs[6], Ra[6];
-        const double gm = G2 * mu * c1, hm = mu * k.H_alpha;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            Rs[c] = (sg[c] - st[c]) + gm * n[c];
-            Ra[c] = (al[c] - al_n[c]) - hm * (k.c2 * w[c] - c1 * n[c]);
-        }
-        const double Rk = (kap - kap_n) - mu * k.H_kappa * kr;
-        const double Rm = c1 * rho - k.sigma_y - kap;
-        // NLsolve convergence test: max|F| <= ftol on the MANDEL vector (shear entries carry sqrt(2))
-        bool conv = (fabs(Rk) <= k.tol) & (fabs(Rm) <= k.tol);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const double t = is_diag_slot(c) ? k.tol : k.tol * (1.0 / r2);
-            conv = conv & (fabs(Rs[c]) <= t) & (fabs(Ra[c]) <= t);
-        }
-        // quantities shared by the step and by the tangent (two reciprocals serve four quotients)
-        const double beta = c1 * inv_rho;
-        const double a1 = 1.0 - hm * k.c2;                 // 1 − ψ
-        const double a2 = 1.0 - mu * k.hk_ikinf;           // k_κ
-        const double ia = fast_rcp(a1 * a2);
-        i1psi = a2 * ia;
-        ikk = a1 * ia;
-        theta = gm * inv_rho;                              // 2G μ β
-        const double phi = hm * beta;
-        const double eta1 = 1.0 + (theta - phi * i1psi);   // 1 + η
-        gk = -k.H_kappa * kr;
-        double gt[6], ha[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            ha[c] = k.H_alpha * (c1 * n[c] - k.c2 * w[c]);
-            gt[c] = G2 * c1 * n[c] - ha[c] * i1psi;
-        }
-        const double n_gt = ddot6(n, gt);
-        const double den = c1 * n_gt - gk * ikk;
-        const double ib = fast_rcp(den * eta1);
-        i1eta = den * ib;
-        iden = eta1 * ib;
-        if (conv) break;                                              // f_converged
-        // out of iterations, or a non-finite residual (NaN/Inf input: NLsolve raises on it; here the point is flagged as failed)
-        if (iters >= k.max_iter || !(fabs(Rm) < 1.7e308)) { flag |= 0x80; break; }
-        // ---- closed-form Newton step
-        const double trRs = tr6(Rs) * (1.0 / 3.0), trRa = tr6(Ra) * (1.0 / 3.0);
-        double rt[6], ra[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const double dl = is_diag_slot(c) ? 1.0 : 0.0;
-            ra[c] = Ra[c] - trRa * dl;
-            rt[c] = -(Rs[c] - trRs * dl) + ra[c] * i1psi;
-        }
-        const double n_rt = ddot6(n, rt);
-        const double dmu = (c1 * n_rt + Rm + Rk * ikk) * iden;
-        const double dkap = (-Rk - gk * dmu) * ikk;
-        const double ny = n_rt - n_gt * dmu;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const double dl = is_diag_slot(c) ? 1.0 : 0.0;
-            const double Pd = ((rt[c] - gt[c] * dmu) - ny * n[c]) * i1eta;
-            sg[c] += -Rs[c] - theta * Pd - G2 * c1 * n[c] * dmu;
-            al[c] += (-ra[c] - phi * Pd - ha[c] * dmu) * i1psi - trRa * dl;
-        }
-        kap += dkap;
-        mu += dmu;
-        ++iters;
-    }
-    // ---- results at the converged iterate                                        Plastic.jl:150-155
-    const double mnu = mu * c1;    // εᵖ = εᵖₙ + μ ν̂,  ν̂ = (3/(2√(3/2)|s|)) s = √(3/2) n
-#pragma unroll
-    for (int c = 0; c < 6; ++c) ep[c] += mnu * n[c];
-    // ∂σ∂ε = (J⁻¹)_σσ ⊡ Eᵉ = Eᵉ − 2Gξ I_dev + u ⊗ n                                  Plastic.jl:152-154
-    const double xi = theta * i1eta;
-    const double omega = k.H_alpha * k.c2 * i1psi;
-    const double cD = c1 * iden;
-    const double nw = ddot6(n, w);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) u[c] = G2 * (xi * n[c] + cD * (xi * omega * (w[c] - nw * n[c]) - G2 * c1 * n[c]));
-    gxi = G2 * xi;
-    return flag;
-}
 // plastic_point_parts: the update without the 36 tangent stores (the dimension wrappers evaluate only the entries they need per outer pass)
 template <class Acc> MM_HD int plastic_point_parts(const PlasticK& k, Acc& acc, int* iters_out, PlasticTangentParts& tp) {
     const double c1 = 1.2247448713915890491;   // sqrt(3/2)
+    const double r2 = 1.4142135623730950488;   // sqrt(2) (Mandel scaling of the shear residuals)
     const double G2 = 2.0 * k.G;
     double ep[6], st[6], al_n[6];
 #pragma unroll
@@ -300,7 +199,97 @@ template <class Acc> MM_HD int plastic_point_parts(const PlasticK& k, Acc& acc, 
     int iters = 0, flag = 0;
     if (!(Phi <= 0.0)) {                                                                // Plastic.jl:134 `if Φ <= 0` (a NaN Φ takes the Newton branch, as in the reference)
         // ---- Newton on x = (σ, κ, α, μ), x0 = (σ_trial, κₙ, αₙ, μₙ)                   Plastic.jl:142-148
-        flag = plastic_newton(k, st, al_n, kap_n, d6, s, rho, inv_rho, sg, al, kap, mu, n, u, gxi, iters, ep);
+        flag = 1;
+        double w[6], i1psi, theta, i1eta, iden, ikk, gk;
+        for (;;) {
+            // residuals at x                                                           Plastic.jl:162-172
+            if (iters > 0) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) d6[c] = sg[c] - al[c];
+                dev6(d6, s);
+                inv_rho = fast_rsqrt(ddot6(s, s), &rho);
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) n[c] = s[c] * inv_rho;
+            dev6(al, w);
+            const double kr = kap * k.ikinf - 1.0;
+            double Rs[6], Ra[6];
+            const double gm = G2 * mu * c1, hm = mu * k.H_alpha;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                Rs[c] = (sg[c] - st[c]) + gm * n[c];
+                Ra[c] = (al[c] - al_n[c]) - hm * (k.c2 * w[c] - c1 * n[c]);
+            }
+            const double Rk = (kap - kap_n) - mu * k.H_kappa * kr;
+            const double Rm = c1 * rho - k.sigma_y - kap;
+            // NLsolve convergence test: max|F| <= ftol on the MANDEL vector (shear entries carry sqrt(2))
+            bool conv = (fabs(Rk) <= k.tol) & (fabs(Rm) <= k.tol);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const double t = is_diag_slot(c) ? k.tol : k.tol * (1.0 / r2);
+                conv = conv & (fabs(Rs[c]) <= t) & (fabs(Ra[c]) <= t);
+            }
+            // quantities shared by the step and by the tangent (two reciprocals serve four quotients)
+            const double beta = c1 * inv_rho;
+            const double a1 = 1.0 - hm * k.c2;                 // 1 − ψ
+            const double a2 = 1.0 - mu * k.hk_ikinf;           // k_κ
+            const double ia = fast_rcp(a1 * a2);
+            i1psi = a2 * ia;
+            ikk = a1 * ia;
+            theta = gm * inv_rho;                              // 2G μ β
+            const double phi = hm * beta;
+            const double eta1 = 1.0 + (theta - phi * i1psi);   // 1 + η
+            gk = -k.H_kappa * kr;
+            double gt[6], ha[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                ha[c] = k.H_alpha * (c1 * n[c] - k.c2 * w[c]);
+                gt[c] = G2 * c1 * n[c] - ha[c] * i1psi;
+            }
+            const double n_gt = ddot6(n, gt);
+            const double den = c1 * n_gt - gk * ikk;
+            const double ib = fast_rcp(den * eta1);
+            i1eta = den * ib;
+            iden = eta1 * ib;
+            if (conv) break;                                              // f_converged
+            // out of iterations, or a non-finite residual (NaN/Inf input: NLsolve raises on it; here the point is flagged as failed)
+            if (iters >= k.max_iter || !(fabs(Rm) < 1.7e308)) { flag |= 0x80; break; }
+            // ---- closed-form Newton step
+            const double trRs = tr6(Rs) * (1.0 / 3.0), trRa = tr6(Ra) * (1.0 / 3.0);
+            double rt[6], ra[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const double dl = is_diag_slot(c) ? 1.0 : 0.0;
+                ra[c] = Ra[c] - trRa * dl;
+                rt[c] = -(Rs[c] - trRs * dl) + ra[c] * i1psi;
+            }
+            const double n_rt = ddot6(n, rt);
+            const double dmu = (c1 * n_rt + Rm + Rk * ikk) * iden;
+            const double dkap = (-Rk - gk * dmu) * ikk;
+            const double ny = n_rt - n_gt * dmu;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const double dl = is_diag_slot(c) ? 1.0 : 0.0;
+                const double Pd = ((rt[c] - gt[c] * dmu) - ny * n[c]) * i1eta;
+                sg[c] += -Rs[c] - theta * Pd - G2 * c1 * n[c] * dmu;
+                al[c] += (-ra[c] - phi * Pd - ha[c] * dmu) * i1psi - trRa * dl;
+            }
+            kap += dkap;
+            mu += dmu;
+            ++iters;
+        }
+        // ---- results at the converged iterate                                        Plastic.jl:150-155
+        const double mnu = mu * c1;    // εᵖ = εᵖₙ + μ ν̂,  ν̂ = (3/(2√(3/2)|s|)) s = √(3/2) n
+#pragma unroll
+        for (int c = 0; c < 6; ++c) ep[c] += mnu * n[c];
+        // ∂σ∂ε = (J⁻¹)_σσ ⊡ Eᵉ = Eᵉ − 2Gξ I_dev + u ⊗ n                                  Plastic.jl:152-154
+        const double xi = theta * i1eta;
+        const double omega = k.H_alpha * k.c2 * i1psi;
+        const double cD = c1 * iden;
+        const double nw = ddot6(n, w);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) u[c] = G2 * (xi * n[c] + cD * (xi * omega * (w[c] - nw * n[c]) - G2 * c1 * n[c]));
+        gxi = G2 * xi;
     }
     // ---- store phase, whole warp converged
 #pragma unroll

@@ -78,169 +78,6 @@ template <> struct OutAlias<PlasticOp> { __host__ __device__ static constexpr in
 template <> struct MinBlocksAos<PlasticOp> { static constexpr int value = MM_PLASTIC_AOS_MINBLOCKS, block = 128; };   // 256 threads -> 238 registers, no spills: 10.1 ms vs 11.2 ms at the SoA kernel's 168
 template <> struct MinBlocks<PlasticOp> { static constexpr int value = MM_PLASTIC_MINBLOCKS, block = MM_PLASTIC_MINBLOCK_THREADS; };   // 128 threads x 3 blocks/SM -> <= 168 regs: measured best of {1,2,3,4,5} (profiles/r01_plastic_regcap_sweep.log, r01_plastic_aos_regcap_sweep.log)
 
-// ---- block-packed SoA kernel of the J2 update ("plastic_soa_packed", mm_set_tuning) ------------------------------------------------
-// soa_kernel<PlasticOp> runs the Newton loop under the yield mask: on the bench workload (51 % of the points yield, scattered) every warp
-// walks the loop with half of its lanes idle, and the loop is where the kernel's instructions are.  Here the block packs its yielded
-// points first: every thread parks its point's trial values in its shared-memory column and the yielded ones append their thread index to
-// a list (warp-aggregated atomic); after one barrier threads 0 .. count-1 each solve ONE listed point with plastic_newton() — the same
-// function on the same values, whichever lane runs it, so the results are those of the per-thread kernel bit for bit — and put the
-// solution back into the owner's column; after a second barrier every thread stores its own point, whole warps, coalesced, exactly as
-// before.  Of a block's BS/32 warps only ceil(count/32) walk the loop.  Columns are [slot][thread]: a thread's own accesses are conflict
-// free, the solver lanes' accesses to their owners' columns are spread over <= 2 BS/count consecutive threads per lane.
-//   slots 0-5 σ_trial -> σ   6-11 αₙ -> α   12 κₙ -> κ   13 μₙ -> μ   14-19 εᵖₙ   20-25 n   26-31 u   32 gξ   33 (iters, flag)
-constexpr int PP_SLOTS = 34;
-template <int BS, int MINB>
-__global__ void __launch_bounds__(BS, MINB)
-plastic_packed_kernel(const PlasticOp op, const Ptrs<2, 3> p, const int64_t N) {
-    extern __shared__ double sm_pp[];
-    int* sm_owner = reinterpret_cast<int*>(sm_pp + PP_SLOTS * BS);      // [BS] thread indices of the yielded points, in arrival order
-    int* sm_count = sm_owner + BS;
-    const int t = threadIdx.x;
-    const int64_t i = (int64_t)blockIdx.x * BS + t;
-    const bool live = i < N;
-    const PlasticK& k = op.k;
-    const double c1 = 1.2247448713915890491;   // sqrt(3/2)
-    const double G2 = 2.0 * k.G;
-    double* col = sm_pp + t;
-    if (t == 0) *sm_count = 0;
-    __syncthreads();
-    bool yielded = false;
-    if (live) {
-        SoaAcc<2, 3> acc(p, N, i);
-        double ep[6], st[6], al_n[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) ep[c] = acc.template in<1>(c);
-        const double kap_n = acc.template in<1>(6);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) al_n[c] = acc.template in<1>(7 + c);
-        const double mu_n = acc.template in<1>(13);
-        {   // σ_trial = Eᵉ ⊡ (ε − εᵖ)                                                        Plastic.jl:131
-            double e[6];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) e[c] = acc.template in<0>(c) - ep[c];
-            const double ltr = k.lam * tr6(e);
-#pragma unroll
-            for (int c = 0; c < 6; ++c) st[c] = is_diag_slot(c) ? (G2 * e[c] + ltr) : (G2 * e[c]);
-        }
-        double d6[6], s[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) d6[c] = st[c] - al_n[c];
-        dev6(d6, s);
-        double rho;
-        fast_rsqrt(ddot6(s, s), &rho);
-        const double Phi = c1 * rho - k.sigma_y - kap_n;                                   // Plastic.jl:132
-        yielded = !(Phi <= 0.0);                                                           // Plastic.jl:134 (a NaN Φ takes the Newton branch)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { col[c * BS] = st[c]; col[(6 + c) * BS] = al_n[c]; col[(14 + c) * BS] = ep[c]; }
-        col[12 * BS] = kap_n;
-        col[13 * BS] = mu_n;
-    }
-    {   // append the yielded threads of this warp to the block's list: one atomic per warp
-        const unsigned m = __ballot_sync(0xffffffffu, yielded);
-        const int lane = t & 31;
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(sm_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (yielded) sm_owner[base + __popc(m & ((1u << lane) - 1u))] = t;
-    }
-    __syncthreads();
-    if (t < *sm_count) {
-        double* oc = sm_pp + sm_owner[t];
-        double st[6], al_n[6], sg[6], al[6], n[6], u[6], d6[6], s[6], ep_unused[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { st[c] = oc[c * BS]; al_n[c] = oc[(6 + c) * BS]; }
-        const double kap_n = oc[12 * BS], mu_n = oc[13 * BS];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) d6[c] = st[c] - al_n[c];
-        dev6(d6, s);
-        double rho, inv_rho;
-        inv_rho = fast_rsqrt(ddot6(s, s), &rho);
-        double kap = kap_n, mu = mu_n, gxi = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { sg[c] = st[c]; al[c] = al_n[c]; n[c] = 0.0; u[c] = 0.0; ep_unused[c] = 0.0; }
-        int iters = 0;
-        const int flag = plastic_newton(k, st, al_n, kap_n, d6, s, rho, inv_rho, sg, al, kap, mu, n, u, gxi, iters, ep_unused);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { oc[c * BS] = sg[c]; oc[(6 + c) * BS] = al[c]; oc[(20 + c) * BS] = n[c]; oc[(26 + c) * BS] = u[c]; }
-        oc[12 * BS] = kap;
-        oc[13 * BS] = mu;
-        oc[32 * BS] = gxi;
-        *reinterpret_cast<int2*>(oc + 33 * BS) = make_int2(iters, flag);
-    }
-    __syncthreads();
-    if (!live) return;
-    {   // store phase: every thread its own point
-        SoaAcc<2, 3> acc(p, N, i);
-        double sg[6], al[6], ep[6];
-        PlasticTangentParts tp;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { sg[c] = col[c * BS]; al[c] = col[(6 + c) * BS]; ep[c] = col[(14 + c) * BS]; }
-        const double kap = col[12 * BS], mu = col[13 * BS];
-        int it = 0, flag = 0;
-        tp.gxi = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { tp.n[c] = 0.0; tp.u[c] = 0.0; }
-        if (yielded) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) { tp.n[c] = col[(20 + c) * BS]; tp.u[c] = col[(26 + c) * BS]; }
-            tp.gxi = col[32 * BS];
-            const int2 itfl = *reinterpret_cast<const int2*>(col + 33 * BS);
-            it = itfl.x; flag = itfl.y;
-            const double mnu = mu * c1;    // εᵖ = εᵖₙ + μ ν̂
-#pragma unroll
-            for (int c = 0; c < 6; ++c) ep[c] += mnu * tp.n[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) acc.template out<0>(c, sg[c]);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) acc.template out<2>(c, ep[c]);
-        acc.template out<2>(6, kap);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) acc.template out<2>(7 + c, al[c]);
-        acc.template out<2>(13, mu);
-        if (acc.template has_out<1>()) {
-            if (op.parts_mode) {
-                acc.template out<1>(0, tp.gxi);
-#pragma unroll
-                for (int c = 0; c < 6; ++c) { acc.template out<1>(1 + c, tp.u[c]); acc.template out<1>(7 + c, tp.n[c]); }
-            } else {
-#pragma unroll
-                for (int J = 0; J < 6; ++J)
-#pragma unroll
-                    for (int I = 0; I < 6; ++I) acc.template out<1>(I + 6 * J, plastic_tangent_entry(k, tp, I, J));
-            }
-        }
-        if (op.flags) op.flags[i] = (uint8_t)flag;
-        if (op.iters) op.iters[i] = (uint16_t)(it > 65535 ? 65535 : it);
-        if ((flag & MM_FLAG_FAILED) && op.n_fail) atomicAdd(op.n_fail, 1);
-    }
-}
-template <int BS, int MINB> int launch_plastic_packed_bs(const PlasticOp& op, const Ptrs<2, 3>& p, int64_t N, cudaStream_t st, const char* what) {
-    const int64_t blocks = (N + BS - 1) / BS;
-    if (blocks > 2147483647LL) return set_error(-1, "%s: N too large for one launch", what);
-    constexpr size_t smem = (size_t)PP_SLOTS * BS * sizeof(double) + (size_t)(BS + 4) * sizeof(int);
-    static SmemOptIn optin;
-    if (int rc = ensure_smem(optin, plastic_packed_kernel<BS, MINB>, smem, what)) return rc;
-    plastic_packed_kernel<BS, MINB><<<(unsigned)blocks, BS, smem, st>>>(op, p, N);
-    return check_launch(what);
-}
-int* ops_tuning_slot(const char* name);
-// the SoA launch of the J2 update: "plastic_soa_packed" 0 = one thread per point all the way (soa_kernel), 128 / 192 / 384 = block-packed Newton
-// loop with that block size at 12 resident warps per SM, 1128 / 1256 / 1512 = block size 128 / 256 / 512 at 16 resident warps
-int launch_plastic(const PlasticOp& op, const Ptrs<2, 3>& p, int64_t N, int layout, cudaStream_t st, const char* what) {
-    if (layout == MM_LAYOUT_SOA && N > 0) {
-        switch (*ops_tuning_slot("plastic_soa_packed")) {
-            case 128: return launch_plastic_packed_bs<128, 3>(op, p, N, st, what);      // 12 resident warps, <= 168 registers (the per-thread kernel's residency)
-            case 192: return launch_plastic_packed_bs<192, 2>(op, p, N, st, what);
-            case 384: return launch_plastic_packed_bs<384, 1>(op, p, N, st, what);
-            case 1128: return launch_plastic_packed_bs<128, 4>(op, p, N, st, what);    // 16 resident warps, <= 128 registers
-            case 1256: return launch_plastic_packed_bs<256, 2>(op, p, N, st, what);
-            case 1512: return launch_plastic_packed_bs<512, 1>(op, p, N, st, what);
-        }
-    }
-    return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, p, N, layout, st, what);
-}
-
 template <int MODEL, int KIND, int TAN> struct HyperOp {
     static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int) { return KIND == 1 ? 9 : 6; }
@@ -368,15 +205,13 @@ int launch_plastic_parts(const MMPlastic* p, const MMNewtonOpts* opts, const dou
     op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
     op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 1;
     Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = parts; ptrs.out[2] = state_out;
-    return launch_plastic(op, ptrs, N, layout, st, "mm_plastic_compact");
+    return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, st, "mm_plastic_compact");
 }
 
 // run-time A/B switches of this translation unit (mm_set_tuning): "xu_soa_tiled" 0 (default) = direct SoA kernel, 1 = copy-engine tiles
 int* ops_tuning_slot(const char* name) {
     static int xu_soa_tiled = [] { const char* e = getenv("MM_XU_SOA_TILED_RT"); return (e && e[0] == '1') ? 1 : 0; }();
     if (!strcmp(name, "xu_soa_tiled")) return &xu_soa_tiled;
-    static int plastic_soa_packed = [] { const char* e = getenv("MM_PLASTIC_SOA_PACKED"); return e ? atoi(e) : 0; }();
-    if (!strcmp(name, "plastic_soa_packed")) return &plastic_soa_packed;
     return nullptr;
 }
 
@@ -400,7 +235,7 @@ int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, do
     op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
     op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 0;
     Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = state_out;
-    return launch_plastic(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
+    return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
 }
 
 int mm_hyper_ex(int model, const MMHyper* p, const double* strain, int strain_kind, int tangent_kind, double* stress, double* tangent,

@@ -179,61 +179,6 @@ def test_plastic_without_tangent_and_in_place_state(mm, torch, cuda_lib):
     assert torch.equal(buf, st1.data) and torch.equal(sig, s)
 
 
-@pytest.mark.parametrize("variant", [128, 192, 384, 1128, 1256, 1512])
-def test_plastic_block_packed_kernel_equals_per_thread_kernel(mm, torch, cuda_lib, variant):
-    """mm_set_tuning("plastic_soa_packed", BS): the block packs its yielded points so that whole warps walk the Newton loop (mm_ops.cu).  The
-    solve is the same function on the same values whichever lane runs it, so every output word equals the per-thread kernel's: ragged
-    last blocks, blocks with no / only yielded points, NaN strains (Newton branch, flagged as failed), a one-iteration cap (failures
-    counted), the call without a tangent, the state updated in place and the compact return (factored rows) that shares the kernel."""
-    m = mm.Plastic(**sy.PLASTIC_PARAMS)
-    nc, lo, hi, seed = sy.c2_strain(1)
-    nc0, lo0, hi0, seed0 = sy.c2_strain(0)
-
-    def run(N, scale, nan_at=(), opts=None, tangent=True):
-        eps = mm.synth_uniform(N, nc, seed, lo, hi) * scale
-        for i in nan_at:
-            eps[i % 6, i] = float("nan")
-        st0 = mm.material_response(m, mm.synth_uniform(N, nc0, seed0, lo0, hi0), mm.initial_material_state(m, N), tangent=False)[2]
-        o = dict(opts or {}, defer_check=True)
-        s, t, st = mm.material_response(m, eps, st0, options=o, tangent=tangent)
-        torch.cuda.synchronize()
-        return [x.clone() for x in (s, st.data, st.flags, st.iters, st.n_fail) + ((t,) if tangent else ())]
-
-    cases = [dict(N=1, scale=1.0), dict(N=127, scale=1.0), dict(N=128, scale=1.0), dict(N=100003, scale=1.0), dict(N=3 * 512 + 5, scale=1e-3),
-             dict(N=3 * 512 + 5, scale=3.0), dict(N=20011, scale=1.0, nan_at=(0, 77, 5000, 20010)),
-             dict(N=20011, scale=1.0, opts={"nlsolve_params": {"iterations": 1}}), dict(N=20011, scale=1.0, tangent=False)]
-    for c in cases:
-        old = cuda_lib.mm_set_tuning(b"plastic_soa_packed", 0)
-        try:
-            ref = run(**c)
-            cuda_lib.mm_set_tuning(b"plastic_soa_packed", variant)
-            got = run(**c)
-        finally:
-            cuda_lib.mm_set_tuning(b"plastic_soa_packed", old)
-        assert len(ref) == len(got)
-        for a, b in zip(ref, got):
-            if a.dtype == torch.float64:
-                assert torch.equal(a.view(torch.int64), b.view(torch.int64)), c     # bit for bit (NaN payloads included)
-            else:
-                assert torch.equal(a, b), c
-    fl = ref[2]
-    assert ref[0].shape[1] == 20011 and 0.3 < float(fl.float().mean()) < 0.7       # the last case really mixes both branches
-    # the compact return (host buffers) runs the same kernel in its factored-tangent mode
-    N = 50001
-    eps = sy.host_uniform(N, nc, seed, lo, hi)
-    sin = host(mm.material_response(m, mm.synth_uniform(N, nc0, seed0, lo0, hi0), mm.initial_material_state(m, N), tangent=False)[2].data)
-    res = {}
-    for v in (0, variant):
-        old = cuda_lib.mm_set_tuning(b"plastic_soa_packed", v)
-        try:
-            σ, T, new = mm.material_response(m, eps, mm.PlasticState(sin.copy()), tangent="factored")
-            res[v] = (σ.copy(), T.flags.copy(), T.rows.copy(), T.dense().copy())
-        finally:
-            cuda_lib.mm_set_tuning(b"plastic_soa_packed", old)
-    for a, b in zip(res[0], res[variant]):
-        assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
-
-
 def test_plastic_nonconvergence_is_flagged_and_raises(mm, torch, oracle):
     N = 5000
     m = mm.Plastic(**sy.PLASTIC_PARAMS)
