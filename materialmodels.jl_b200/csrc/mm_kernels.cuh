@@ -31,6 +31,9 @@ template <int NIN, int NOUT> struct SoaAcc {
     template <int A> __device__ __forceinline__ double in(int c) const { return __ldcs(p.in[A] + ((int64_t)c * N + i)); }
     template <int A> __device__ __forceinline__ void out(int c, double v) const { __stcs(p.out[A] + ((int64_t)c * N + i), v); }
     template <int A> __device__ __forceinline__ bool has_out() const { return p.out[A] != nullptr; }
+    // hint: bring the line that holds component c of point j of input A into L2 (no register, no scoreboard entry)
+    static constexpr bool CAN_PREFETCH = true;
+    template <int A> __device__ __forceinline__ void prefetch_l2(int c, int64_t j) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in[A] + ((int64_t)c * N + j))); }
 };
 
 template <class Op> struct MinBlocks { static constexpr int value = 1, block = 32; };   // per-Op occupancy target (register cap): `value` blocks of `block` threads
@@ -111,6 +114,7 @@ template <class Op> __host__ __device__ constexpr int dense_out_rel(int a) {    
 }
 template <class Op> __host__ __device__ constexpr int dense_out_rel_noalias(int a) { return a == 0 ? 0 : dense_out_rel_noalias<Op>(a - 1) + Op::out_nc(a - 1); }
 template <class Op, int BS> struct DenseAcc {
+    static constexpr bool CAN_PREFETCH = false;
     double* sm_in;            // input image  [A][pt][c] (also the staging area of aliased outputs)
     double* sm_out;           // output image [A][pt][c]
     const Ptrs<Op::NIN, Op::NOUT>& p;

@@ -18,6 +18,8 @@ struct ElasticOp {
 
 template <> struct SoaTangentCap<ElasticOp> { static constexpr int blocks = 2; };
 
+int* ops_tuning_slot(const char* name);
+
 struct PlasticOp {
     static constexpr int NIN = 2, NOUT = 3, SCRATCH = 0;
     __host__ __device__ static constexpr int in_nc(int a) { return a == 0 ? 6 : 14; }
@@ -31,7 +33,21 @@ struct PlasticOp {
     // a second instantiation on purpose: the σ / state arithmetic (and nvcc's fma contraction choices in it) are then the very same
     // machine code for the dense and the compact return, which is what makes the two bit-identical.
     int parts_mode;
+    // SoA kernel only ("plastic_soa_prefetch", mm_set_tuning): > 0 = lanes 0 and 16 of every warp ask L2 for the 20 input lines of the
+    // points `pf_dist` ahead (the block that will be resident a few waves later), so that those loads find their lines on the chip
+    int pf_dist;
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
+        if constexpr (Acc::CAN_PREFETCH) {
+            if (pf_dist > 0 && (threadIdx.x & 15) == 0) {
+                const int64_t j = i + pf_dist;
+                if (j < acc.N) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) acc.template prefetch_l2<0>(c, j);
+#pragma unroll
+                    for (int c = 0; c < 14; ++c) acc.template prefetch_l2<1>(c, j);
+                }
+            }
+        }
         int it = 0;
         PlasticTangentParts tp;
         const int flag = plastic_point_parts(k, acc, &it, tp);
@@ -203,15 +219,21 @@ int launch_plastic_parts(const MMPlastic* p, const MMNewtonOpts* opts, const dou
                          uint8_t* flags, uint16_t* iters, int32_t* n_fail, int64_t N, int layout, cudaStream_t st) {
     PlasticOp op;
     op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
-    op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 1;
+    op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 1; op.pf_dist = *ops_tuning_slot("plastic_soa_prefetch");
     Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = parts; ptrs.out[2] = state_out;
     return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, st, "mm_plastic_compact");
 }
 
-// run-time A/B switches of this translation unit (mm_set_tuning): "xu_soa_tiled" 0 (default) = direct SoA kernel, 1 = copy-engine tiles
+// run-time A/B switches of this translation unit (mm_set_tuning): "xu_soa_tiled" 0 (default) = direct SoA kernel, 1 = copy-engine tiles;
+// "plastic_soa_prefetch" = how many points ahead the J2 SoA kernel asks L2 for its input lines (0 = no hint, default 28 416)
 int* ops_tuning_slot(const char* name) {
     static int xu_soa_tiled = [] { const char* e = getenv("MM_XU_SOA_TILED_RT"); return (e && e[0] == '1') ? 1 : 0; }();
     if (!strcmp(name, "xu_soa_tiled")) return &xu_soa_tiled;
+    // measured on 1e8 points, alternating rounds on two boxes (profiles/r02_plastic_prefetch_ab*.jsonl): back to back 10.33-10.75 ms without the
+    // hint, 9.90-10.29 ms with it anywhere from 14 208 to 56 832 points ahead (1/4 to 1 resident wave of 148 x 3 blocks), 10.2 ms at 113 664,
+    // 10.9 ms at 227 328 (the lines are evicted again before they are used), same bits
+    static int plastic_soa_prefetch = [] { const char* e = getenv("MM_PLASTIC_SOA_PREFETCH"); return e ? atoi(e) : 28416; }();
+    if (!strcmp(name, "plastic_soa_prefetch")) return &plastic_soa_prefetch;
     return nullptr;
 }
 
@@ -233,7 +255,7 @@ int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, do
     if (!p || N < 0 || (N > 0 && (!eps || !state_in || !sig || !state_out))) return set_error(MM_ERR_ARG, "mm_plastic: bad argument");
     PlasticOp op;
     op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
-    op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 0;
+    op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 0; op.pf_dist = *ops_tuning_slot("plastic_soa_prefetch");
     Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = state_out;
     return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
 }

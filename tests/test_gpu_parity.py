@@ -179,6 +179,29 @@ def test_plastic_without_tangent_and_in_place_state(mm, torch, cuda_lib):
     assert torch.equal(buf, st1.data) and torch.equal(sig, s)
 
 
+@pytest.mark.parametrize("N", [1, 127, 4097, 28416, 28417, 100003])
+def test_plastic_l2_prefetch_hint_changes_no_bit(mm, torch, cuda_lib, N):
+    """mm_set_tuning("plastic_soa_prefetch", d): lanes 0 and 16 of every warp ask L2 for the input lines of the points d ahead (mm_ops.cu).  A
+    hint: with it (default distance, a short one that stays inside small batches, one past the end) and without it every output word is the same."""
+    m = mm.Plastic(**sy.PLASTIC_PARAMS)
+    nc, lo, hi, seed = sy.c2_strain(1)
+    nc0, lo0, hi0, seed0 = sy.c2_strain(0)
+    eps = mm.synth_uniform(N, nc, seed, lo, hi)
+    st0 = mm.material_response(m, mm.synth_uniform(N, nc0, seed0, lo0, hi0), mm.initial_material_state(m, N), tangent=False)[2]
+    res = {}
+    for d in (0, 28416, 32, N, 10**9):
+        old = cuda_lib.mm_set_tuning(b"plastic_soa_prefetch", d)
+        try:
+            s, t, st = mm.material_response(m, eps, st0)
+            torch.cuda.synchronize()
+            res[d] = [x.clone() for x in (s, t, st.data, st.flags, st.iters)]
+        finally:
+            cuda_lib.mm_set_tuning(b"plastic_soa_prefetch", old)
+    for d, got in res.items():
+        for a, b in zip(res[0], got):
+            assert torch.equal(a.view(torch.int64) if a.dtype == torch.float64 else a, b.view(torch.int64) if b.dtype == torch.float64 else b), d
+
+
 def test_plastic_nonconvergence_is_flagged_and_raises(mm, torch, oracle):
     N = 5000
     m = mm.Plastic(**sy.PLASTIC_PARAMS)
