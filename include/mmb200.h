@@ -100,8 +100,8 @@ int mm_device_count(void);
  * first-pass candidate count, 5 / 6 = active-set pass with / without that re-ordering, -1 = default: 6 (SoA) or 5 (AoS)) and of the dimension wrappers ("wrapped_j2_variant" 0 = one thread per point, 1 = state
  * machine, 2 = pass-granular trips; "wrapped_j2_th_outer", "wrapped_j2_th_final", "wrapped_j2_chunk"; "wrapped_crystal_variant" 0 = one
  * thread per point, 1 = rounds; "wrapped_crystal_slab") and of the XuNeedleman SoA path ("xu_soa_tiled" 0 = direct kernel, 1 = copy-engine
- * tiles), of the J2 SoA kernel ("plastic_soa_prefetch" = points ahead for which the input lines are requested into L2, 0 = no hint, default 28416: a hint,
- * no value changes) and of the host-buffer J2 call ("mmh_plastic_via_factored" 1 = dense tangent rebuilt on the host from factored rows for batches of >= 2^18 points,
+ * tiles), of the J2 SoA kernel ("plastic_soa_prefetch" = points ahead for which the input lines are requested into L2, 0 = no hint, default 28416; "stream_soa_prefetch" the same for the
+ * LinearElastic / hyperelastic / XuNeedleman SoA kernels, -1 = their own defaults: hints, no value changes) and of the host-buffer J2 call ("mmh_plastic_via_factored" 1 = dense tangent rebuilt on the host from factored rows for batches of >= 2^18 points,
  * 2 = for any size, 0 = plain dense transfer); initial values come from the MM_CRYSTAL_* / MM_WRAPPED_* environment variables, read once per process.
  * Returns the previous value, -1 for an unknown name.  Results do not depend on the scheduling switches (chunk, thresholds, re-ordering, slabs: bit for bit);
  * the Newton pass variants of the crystal update solve the same Newton step by different algebra and agree to rounding — active masks and iteration counts

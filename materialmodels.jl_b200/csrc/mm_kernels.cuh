@@ -31,9 +31,6 @@ template <int NIN, int NOUT> struct SoaAcc {
     template <int A> __device__ __forceinline__ double in(int c) const { return __ldcs(p.in[A] + ((int64_t)c * N + i)); }
     template <int A> __device__ __forceinline__ void out(int c, double v) const { __stcs(p.out[A] + ((int64_t)c * N + i), v); }
     template <int A> __device__ __forceinline__ bool has_out() const { return p.out[A] != nullptr; }
-    // hint: bring the line that holds component c of point j of input A into L2 (no register, no scoreboard entry)
-    static constexpr bool CAN_PREFETCH = true;
-    template <int A> __device__ __forceinline__ void prefetch_l2(int c, int64_t j) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in[A] + ((int64_t)c * N + j))); }
 };
 
 template <class Op> struct MinBlocks { static constexpr int value = 1, block = 32; };   // per-Op occupancy target (register cap): `value` blocks of `block` threads
@@ -57,11 +54,26 @@ struct Scratch {
     __device__ __forceinline__ double& operator()(int j) const { return base[j * stride]; }
 };
 
+// L2 prefetch hint of the SoA kernels.  A warp's loads of one component are two 128-byte lines; the kernels keep 8-12 warps per SM and have
+// nothing else to do while a warp's 6-20 input lines travel (long-scoreboard is their top stall).  `pf` > 0: lanes 0 and 16 of every warp ask
+// L2 for the input lines of the points `pf` further on — the block that becomes resident a fraction of a wave later — so that its loads find
+// them on the chip.  No register, no scoreboard entry, no extra DRAM traffic (each line is still fetched once), no value changes.
+// SoaPrefetch<Op>::dist(p) is the distance the launcher passes (0 = no hint); ops opt in where it was measured to pay (mm_ops.cu).
+template <class Op> struct SoaPrefetch { static int dist(const Ptrs<Op::NIN, Op::NOUT>&) { return 0; } };
+template <class Op, int A = 0> __device__ __forceinline__ void soa_prefetch_inputs(const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int64_t j) {
+    if constexpr (A < Op::NIN) {
+#pragma unroll
+        for (int c = 0; c < Op::in_nc(A); ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in[A] + ((int64_t)c * N + j)));
+        soa_prefetch_inputs<Op, A + 1>(p, N, j);
+    }
+}
+
 template <class Op, int BS>
-__global__ void __launch_bounds__(BS, (MinBlocks<Op>::value * MinBlocks<Op>::block + BS - 1) / BS) soa_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N) {
+__global__ void __launch_bounds__(BS, (MinBlocks<Op>::value * MinBlocks<Op>::block + BS - 1) / BS) soa_kernel(const Op op, const Ptrs<Op::NIN, Op::NOUT> p, const int64_t N, const int pf) {
     extern __shared__ double sm_scratch[];
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     if (i >= N) return;
+    if (pf > 0 && (threadIdx.x & 15) == 0 && i + pf < N) soa_prefetch_inputs<Op>(p, N, i + pf);
     SoaAcc<Op::NIN, Op::NOUT> acc(p, N, i);
     Scratch scr{sm_scratch + threadIdx.x, BS};
     op.point(acc, i, scr);
@@ -114,7 +126,6 @@ template <class Op> __host__ __device__ constexpr int dense_out_rel(int a) {    
 }
 template <class Op> __host__ __device__ constexpr int dense_out_rel_noalias(int a) { return a == 0 ? 0 : dense_out_rel_noalias<Op>(a - 1) + Op::out_nc(a - 1); }
 template <class Op, int BS> struct DenseAcc {
-    static constexpr bool CAN_PREFETCH = false;
     double* sm_in;            // input image  [A][pt][c] (also the staging area of aliased outputs)
     double* sm_out;           // output image [A][pt][c]
     const Ptrs<Op::NIN, Op::NOUT>& p;
@@ -401,7 +412,7 @@ int launch_points(const Op& op, const Ptrs<Op::NIN, Op::NOUT>& p, int64_t N, int
         const size_t smem = (cap > 0 && Op::NOUT > 1 && p.out[1] != nullptr && cap_bytes > scratch) ? cap_bytes : scratch;
         static SmemOptIn soa_optin;
         if (int rc = ensure_smem(soa_optin, soa_kernel<Op, BS_SOA>, cap_bytes > scratch ? cap_bytes : scratch, what)) return rc;
-        soa_kernel<Op, BS_SOA><<<(unsigned)blocks, BS_SOA, smem, stream>>>(op, p, N);
+        soa_kernel<Op, BS_SOA><<<(unsigned)blocks, BS_SOA, smem, stream>>>(op, p, N, SoaPrefetch<Op>::dist(p));
     } else if (layout == 1) {
         // one kernel for every AoS batch: full tiles through the copy engine (TMA bulk copies) when all array bases are
         // 16-byte aligned, the ragged last tile (or everything, if unaligned) through element-wise copies

@@ -7,6 +7,8 @@
 
 namespace mm {
 
+int* ops_tuning_slot(const char* name);      // run-time switches of this translation unit (below)
+
 // ---- Ops ----------------------------------------------------------------------------------------
 struct ElasticOp {
     static constexpr int NIN = 1, NOUT = 2, SCRATCH = 0;
@@ -17,8 +19,13 @@ struct ElasticOp {
 };
 
 template <> struct SoaTangentCap<ElasticOp> { static constexpr int blocks = 2; };
-
-int* ops_tuning_slot(const char* name);
+// the tangent-writing launches gain from the hint (profiles/r02_stream_prefetch_ab.jsonl, 1e8 points: LinearElastic 6.03 -> 5.91 ms, NeoHook / Yeoh
+// 6.48-6.65 -> 6.29-6.36 ms, XuNeedleman 1.83-1.95 -> 1.82-1.84 ms); the read-dominated σ-only launch loses (1.42 -> 1.46 ms) and gets none
+inline int stream_prefetch_dist(bool writes_tangent, int dflt) {
+    const int forced = *ops_tuning_slot("stream_soa_prefetch");
+    return forced >= 0 ? forced : (writes_tangent ? dflt : 0);
+}
+template <> struct SoaPrefetch<ElasticOp> { static int dist(const Ptrs<1, 2>& p) { return stream_prefetch_dist(p.out[1] != nullptr, 65536); } };
 
 struct PlasticOp {
     static constexpr int NIN = 2, NOUT = 3, SCRATCH = 0;
@@ -33,21 +40,7 @@ struct PlasticOp {
     // a second instantiation on purpose: the σ / state arithmetic (and nvcc's fma contraction choices in it) are then the very same
     // machine code for the dense and the compact return, which is what makes the two bit-identical.
     int parts_mode;
-    // SoA kernel only ("plastic_soa_prefetch", mm_set_tuning): > 0 = lanes 0 and 16 of every warp ask L2 for the 20 input lines of the
-    // points `pf_dist` ahead (the block that will be resident a few waves later), so that those loads find their lines on the chip
-    int pf_dist;
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t i, const Scratch&) const {
-        if constexpr (Acc::CAN_PREFETCH) {
-            if (pf_dist > 0 && (threadIdx.x & 15) == 0) {
-                const int64_t j = i + pf_dist;
-                if (j < acc.N) {
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) acc.template prefetch_l2<0>(c, j);
-#pragma unroll
-                    for (int c = 0; c < 14; ++c) acc.template prefetch_l2<1>(c, j);
-                }
-            }
-        }
         int it = 0;
         PlasticTangentParts tp;
         const int flag = plastic_point_parts(k, acc, &it, tp);
@@ -68,6 +61,7 @@ struct PlasticOp {
         if ((flag & MM_FLAG_FAILED) && n_fail) atomicAdd(n_fail, 1);
     }
 };
+template <> struct SoaPrefetch<PlasticOp> { static int dist(const Ptrs<2, 3>&) { return *ops_tuning_slot("plastic_soa_prefetch"); } };
 template <> struct OutAlias<PlasticOp> { __host__ __device__ static constexpr int of(int a) { return a == 0 ? 0 : (a == 2 ? 1 : -1); } };   // σ <- ε slots, state <- state slots
 
 #ifndef MM_PLASTIC_SOA_BS
@@ -102,6 +96,7 @@ template <int MODEL, int KIND, int TAN> struct HyperOp {
     template <class Acc> __device__ __forceinline__ void point(Acc& acc, int64_t, const Scratch&) const { hyper_point_ex<MODEL, KIND, TAN>(k, acc); }
 };
 
+template <int MODEL, int KIND, int TAN> struct SoaPrefetch<HyperOp<MODEL, KIND, TAN>> { static int dist(const Ptrs<1, 2>& p) { return stream_prefetch_dist(p.out[1] != nullptr, 32768); } };
 template <int MODEL, int KIND, int TAN> struct SoaTangentCap<HyperOp<MODEL, KIND, TAN>> { static constexpr int blocks = TAN == 1 ? 0 : 2; };   // ∂S∂E measured slower capped (6.82 vs 6.66 ms)
 
 template <int DIM> struct XuOp {
@@ -118,6 +113,7 @@ template <int DIM> struct XuOp {
 #ifndef MM_XU_SOA_BS
 #define MM_XU_SOA_BS 256
 #endif
+template <int DIM> struct SoaPrefetch<XuOp<DIM>> { static int dist(const Ptrs<1, 2>& p) { return stream_prefetch_dist(p.out[1] != nullptr, 65536); } };
 template <int DIM> struct MinBlocks<XuOp<DIM>> { static constexpr int value = MM_XU_MINBLOCKS, block = MM_XU_SOA_BS; };
 template <int DIM> struct MinBlocksAos<XuOp<DIM>> { static constexpr int value = 1, block = 32; };
 #ifndef MM_XU_SOA_TILED
@@ -219,13 +215,14 @@ int launch_plastic_parts(const MMPlastic* p, const MMNewtonOpts* opts, const dou
                          uint8_t* flags, uint16_t* iters, int32_t* n_fail, int64_t N, int layout, cudaStream_t st) {
     PlasticOp op;
     op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
-    op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 1; op.pf_dist = *ops_tuning_slot("plastic_soa_prefetch");
+    op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 1;
     Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = parts; ptrs.out[2] = state_out;
     return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, st, "mm_plastic_compact");
 }
 
 // run-time A/B switches of this translation unit (mm_set_tuning): "xu_soa_tiled" 0 (default) = direct SoA kernel, 1 = copy-engine tiles;
-// "plastic_soa_prefetch" = how many points ahead the J2 SoA kernel asks L2 for its input lines (0 = no hint, default 28 416)
+// "plastic_soa_prefetch" = how many points ahead the J2 SoA kernel asks L2 for its input lines (0 = no hint, default 28 416);
+// "stream_soa_prefetch" = the same for the LinearElastic / hyperelastic / XuNeedleman SoA kernels (-1 = per-op defaults for the tangent-writing launches)
 int* ops_tuning_slot(const char* name) {
     static int xu_soa_tiled = [] { const char* e = getenv("MM_XU_SOA_TILED_RT"); return (e && e[0] == '1') ? 1 : 0; }();
     if (!strcmp(name, "xu_soa_tiled")) return &xu_soa_tiled;
@@ -234,6 +231,8 @@ int* ops_tuning_slot(const char* name) {
     // 10.9 ms at 227 328 (the lines are evicted again before they are used), same bits
     static int plastic_soa_prefetch = [] { const char* e = getenv("MM_PLASTIC_SOA_PREFETCH"); return e ? atoi(e) : 28416; }();
     if (!strcmp(name, "plastic_soa_prefetch")) return &plastic_soa_prefetch;
+    static int stream_soa_prefetch = [] { const char* e = getenv("MM_STREAM_SOA_PREFETCH"); return e ? atoi(e) : -1; }();     // LinearElastic, hyperelastic, XuNeedleman SoA kernels: -1 = per-op defaults, >= 0 = that distance for all of them (0 = no hint)
+    if (!strcmp(name, "stream_soa_prefetch")) return &stream_soa_prefetch;
     return nullptr;
 }
 
@@ -255,7 +254,7 @@ int mm_plastic(const MMPlastic* p, const double* eps, const double* state_in, do
     if (!p || N < 0 || (N > 0 && (!eps || !state_in || !sig || !state_out))) return set_error(MM_ERR_ARG, "mm_plastic: bad argument");
     PlasticOp op;
     op.k = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
-    op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 0; op.pf_dist = *ops_tuning_slot("plastic_soa_prefetch");
+    op.flags = flags; op.iters = iters; op.n_fail = n_fail; op.parts_mode = 0;
     Ptrs<2, 3> ptrs; ptrs.in[0] = eps; ptrs.in[1] = state_in; ptrs.out[0] = sig; ptrs.out[1] = tan; ptrs.out[2] = state_out;
     return launch_points<PlasticOp, MM_PLASTIC_SOA_BS, MM_PLASTIC_AOS_BS>(op, ptrs, N, layout, (cudaStream_t)stream, "mm_plastic");
 }

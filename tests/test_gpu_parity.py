@@ -202,6 +202,40 @@ def test_plastic_l2_prefetch_hint_changes_no_bit(mm, torch, cuda_lib, N):
             assert torch.equal(a.view(torch.int64) if a.dtype == torch.float64 else a, b.view(torch.int64) if b.dtype == torch.float64 else b), d
 
 
+@pytest.mark.parametrize("N", [1, 255, 65537, 200003])
+def test_streaming_kernels_l2_prefetch_hint_changes_no_bit(mm, torch, cuda_lib, N):
+    """mm_set_tuning("stream_soa_prefetch", d) for the LinearElastic / hyperelastic / XuNeedleman SoA kernels: -1 = their own defaults
+    (tangent-writing launches only), 0 = no hint, d > 0 = that distance for every launch.  Same output words whatever the distance."""
+    le = mm.LinearElastic(E=200e3, ν=0.3)
+    nc, lo, hi, seed = sy.c1_strain()
+    eps = mm.synth_uniform(N, nc, seed, lo, hi)
+    nc, lo, hi, seed = sy.c3_defgrad()
+    F = mm.synth_uniform(N, nc, seed, lo, hi)
+    prm = sy.YEOH_PARAMS
+    hm = mm.Yeoh(λ=prm["lambda_"], μ=prm["mu"], c2=prm["c2"], c3=prm["c3"])
+    x = sy.XU_PARAMS
+    xm = mm.XuNeedleman(σₘₐₓ=x["sigma_max"], τₘₐₓ=x["tau_max"], Φₙ=mm.xu_needleman_Φₙ(x["sigma_max"], x["delta_n"]),
+                        Φₜ=mm.xu_needleman_Φₜ(x["tau_max"], x["delta_t"]), Δₙˢ=x["Delta_n_star"])
+    nc, lo, hi, seed = sy.c5_jump()
+    D = mm.synth_uniform(N, nc, seed, lo, hi)
+    calls = [lambda: mm.material_response(le, eps), lambda: mm.material_response(le, eps, tangent=False),
+             lambda: mm.material_response(mm.dSdC(), hm, mm.DeformationGradient(F)), lambda: mm.material_response(mm.dPdF(), hm, mm.DeformationGradient(F)),
+             lambda: mm.material_response(xm, D), lambda: mm.material_response(xm, D, tangent=False)]
+    res = {}
+    for d in (0, -1, 32, N, 10**9):
+        old = cuda_lib.mm_set_tuning(b"stream_soa_prefetch", d)
+        try:
+            res[d] = [[t.clone() for t in c() if isinstance(t, torch.Tensor)] for c in calls]
+            torch.cuda.synchronize()
+        finally:
+            cuda_lib.mm_set_tuning(b"stream_soa_prefetch", old)
+    for d, got in res.items():
+        for ra, rb in zip(res[0], got):
+            assert len(ra) == len(rb) and len(ra) >= 1
+            for a, b in zip(ra, rb):
+                assert torch.equal(a.view(torch.int64), b.view(torch.int64)), d
+
+
 def test_plastic_nonconvergence_is_flagged_and_raises(mm, torch, oracle):
     N = 5000
     m = mm.Plastic(**sy.PLASTIC_PARAMS)
