@@ -14,8 +14,6 @@
 //   per point  (P = ncell*NQ points, point index = cell*NQ + q):  dNdx[(3a+k)*P + i], dOmega[i], state[c*P + i], sig/tan
 //   per cell   (ncell cells):                                     ue[(3a+k)*ncell + cell], fe[(3a+k)*ncell + cell]
 #include <cuda_runtime.h>
-#include <stdlib.h>
-#include <string.h>
 #include "../../include/mmb200.h"
 #include "mm_kernels.cuh"
 
@@ -55,14 +53,7 @@ struct CellArgs {
     double* fe; double* ke; double* sig; double* tan; double* state_out;
     uint8_t* flags; uint16_t* iters; int32_t* n_fail;
     int64_t ncell;
-    int pf;            // > 0: L2 prefetch hint for the per-point input lines of the points `pf` further on ("cells_prefetch", see soa_kernel in mm_kernels.cuh)
 };
-__device__ __forceinline__ void l2_hint(const double* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
-int* cells_tuning_slot(const char* name) {
-    static int cells_prefetch = [] { const char* e = getenv("MM_CELLS_PREFETCH"); return e ? atoi(e) : 0; }();
-    if (!strcmp(name, "cells_prefetch")) return &cells_prefetch;
-    return nullptr;
-}
 
 // MODEL 0: LinearElastic (stateless), 1: Plastic (14 state doubles), 2: TransverselyIsotropic (state = direction a3, read-only)
 // ∇N is parked in shared memory across the material update (3·NN doubles per thread would otherwise cost 2·3·NN registers on
@@ -93,16 +84,6 @@ __global__ void __launch_bounds__(BS, WITH_KE ? MM_CELLS_KE_MINBLOCKS : MM_CELLS
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     const unsigned mask = __ballot_sync(0xffffffffu, i < P);   // cells are whole and warp-local: the survivors sync among themselves below
     if (i >= P) return;
-    if (a.pf > 0 && (threadIdx.x & 15) == 0 && i + a.pf < P) {
-        const int64_t j = i + a.pf;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) l2_hint(a.dNdx + (int64_t)c * P + j);
-        l2_hint(a.dOmega + j);
-        if (MODEL == 1) {
-#pragma unroll
-            for (int c = 0; c < 14; ++c) l2_hint(a.state_in + (int64_t)c * P + j);
-        }
-    }
     const int64_t cell = i / NQ;
     const int q = (int)(i - cell * NQ);
     const int t = threadIdx.x;
@@ -284,7 +265,6 @@ struct HyperCellArgs {
     const double* dNdx; const double* dOmega; const double* ue;
     double* fe; double* Pt; double* dPdF;
     int64_t ncell;
-    int pf;
 };
 #ifndef MM_HCELLS_MINBLOCKS
 #define MM_HCELLS_MINBLOCKS 3
@@ -300,12 +280,6 @@ __global__ void __launch_bounds__(BS, MM_HCELLS_MINBLOCKS) hyper_cells_kernel(co
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     const unsigned mask = __ballot_sync(0xffffffffu, i < P);
     if (i >= P) return;
-    if (a.pf > 0 && (threadIdx.x & 15) == 0 && i + a.pf < P) {
-        const int64_t j = i + a.pf;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) l2_hint(a.dNdx + (int64_t)c * P + j);
-        l2_hint(a.dOmega + j);
-    }
     const int64_t cell = i / NQ;
     const int q = (int)(i - cell * NQ);
     const int t = threadIdx.x;
@@ -398,7 +372,7 @@ extern "C" {
 int mm_cells_linear_elastic(const MMLinearElastic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue, double* fe, double* ke_out,
                             double* sig, double* tan, int64_t ncell, void* stream) {
     if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !fe))) return set_error(MM_ERR_ARG, "mm_cells_linear_elastic: bad argument");
-    CellArgs a{dNdx, dOmega, ue, nullptr, fe, ke_out, sig, tan, nullptr, nullptr, nullptr, nullptr, ncell, *cells_tuning_slot("cells_prefetch")};
+    CellArgs a{dNdx, dOmega, ue, nullptr, fe, ke_out, sig, tan, nullptr, nullptr, nullptr, nullptr, ncell};
     PlasticK kp{};
     TransvIsoK kt{};
     return dispatch_cells<0>(nn, nq, make_elastic_k(p->E, p->nu), kp, kt, a, (cudaStream_t)stream);
@@ -408,7 +382,7 @@ int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, con
                      double* ke_out, double* sig, double* tan, double* state_out, uint8_t* flags, uint16_t* iters, int32_t* n_fail, const MMNewtonOpts* opts, int64_t ncell,
                      void* stream) {
     if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !state_in || !fe || !state_out))) return set_error(MM_ERR_ARG, "mm_cells_plastic: bad argument");
-    CellArgs a{dNdx, dOmega, ue, state_in, fe, ke_out, sig, tan, state_out, flags, iters, n_fail, ncell, *cells_tuning_slot("cells_prefetch")};
+    CellArgs a{dNdx, dOmega, ue, state_in, fe, ke_out, sig, tan, state_out, flags, iters, n_fail, ncell};
     ElasticK ke = make_elastic_k(p->E, p->nu);
     PlasticK kp = make_plastic_k(p->E, p->nu, p->sigma_y, p->H, p->r, p->kappa_inf, p->alpha_inf, opts ? opts->tol : 1e-8, opts ? opts->max_iter : 1000);
     TransvIsoK kt{};
@@ -418,7 +392,7 @@ int mm_cells_plastic(const MMPlastic* p, int nn, int nq, const double* dNdx, con
 int mm_cells_transversely_isotropic(const MMTransverselyIsotropic* p, int nn, int nq, const double* dNdx, const double* dOmega, const double* ue,
                                     const double* a3, double* fe, double* ke_out, double* sig, double* tan, int64_t ncell, void* stream) {
     if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !a3 || !fe))) return set_error(MM_ERR_ARG, "mm_cells_transversely_isotropic: bad argument");
-    CellArgs a{dNdx, dOmega, ue, a3, fe, ke_out, sig, tan, nullptr, nullptr, nullptr, nullptr, ncell, *cells_tuning_slot("cells_prefetch")};
+    CellArgs a{dNdx, dOmega, ue, a3, fe, ke_out, sig, tan, nullptr, nullptr, nullptr, nullptr, ncell};
     ElasticK ke{};
     PlasticK kp{};
     TransvIsoK kt{p->L_perp, p->L_par, p->M_par, p->G_perp, p->G_par};
@@ -429,7 +403,7 @@ int mm_cells_hyper(int model, const MMHyper* p, int nn, int nq, const double* dN
                    double* dPdF, int64_t ncell, void* stream) {
     if (!p || ncell < 0 || (ncell > 0 && (!dNdx || !dOmega || !ue || !fe))) return set_error(MM_ERR_ARG, "mm_cells_hyper: bad argument");
     HyperK k; k.lambda = p->lambda; k.mu = p->mu; k.c2 = p->c2; k.c3 = p->c3;
-    HyperCellArgs a{dNdx, dOmega, ue, fe, Pt, dPdF, ncell, *cells_tuning_slot("cells_prefetch")};
+    HyperCellArgs a{dNdx, dOmega, ue, fe, Pt, dPdF, ncell};
     switch (model) {
         case MM_NEOHOOK: return dispatch_hyper_cells<0>(nn, nq, k, a, (cudaStream_t)stream);
         case MM_YEOH: return dispatch_hyper_cells<1>(nn, nq, k, a, (cudaStream_t)stream);
