@@ -96,7 +96,7 @@ const char* mm_last_error(void);
 int mm_device_count(void);
 
 /* test / tuning hook: A-B switches of the crystal kernels ("crystal_force_general", "crystal_thresh", "crystal_chunk",
- * "crystal_fixup_per_sm"; "crystal_variant" 0 = dense pass, 1 = sparse per-lane lists, 2 = phased, 3 / 4 = sparse / dense over chunks re-ordered by
+ * "crystal_fixup_per_sm"; "crystal_finish_prefetch" = points ahead for which the finish kernel asks L2 for its SoA input lines, 0 = no hint, default 4096; "crystal_variant" 0 = dense pass, 1 = sparse per-lane lists, 2 = phased, 3 / 4 = sparse / dense over chunks re-ordered by
  * first-pass candidate count, 5 / 6 = active-set pass with / without that re-ordering, -1 = default: 6 (SoA) or 5 (AoS)) and of the dimension wrappers ("wrapped_j2_variant" 0 = one thread per point, 1 = state
  * machine, 2 = pass-granular trips; "wrapped_j2_th_outer", "wrapped_j2_th_final", "wrapped_j2_chunk"; "wrapped_crystal_variant" 0 = one
  * thread per point, 1 = rounds; "wrapped_crystal_slab") and of the XuNeedleman SoA path ("xu_soa_tiled" 0 = direct kernel, 1 = copy-engine

@@ -108,15 +108,16 @@ int* ops_tuning_slot(const char* name);       // mm_ops.cu
 int* host_tuning_slot(const char* name);      // mm_host.cu
 // tuning / A-B switches: initialised from the environment ONCE per process (tools/README.md), changed afterwards only through
 // mm_set_tuning() — never a getenv on the per-call path
-struct CrystalKnobs { int thresh, chunk, fixup_per_sm, force_general, variant; };
+struct CrystalKnobs { int thresh, chunk, fixup_per_sm, force_general, variant, finish_pf; };
 static CrystalKnobs& crystal_knobs() {
     static CrystalKnobs k = [] {
-        CrystalKnobs v{0, 0, 0, 0, -1};
+        CrystalKnobs v{0, 0, 0, 0, -1, 4096};       // finish_pf: 17.00-17.02 -> 16.82-16.85 ms per 1e7 points at 2 048-4 096 points ahead, no gain from 16 384 on (profiles/r02_crystal_finish_prefetch*.log)
         if (const char* e = getenv("MM_CRYSTAL_THRESH")) v.thresh = atoi(e);
         if (const char* e = getenv("MM_CRYSTAL_CHUNK")) v.chunk = atoi(e);
         if (const char* e = getenv("MM_FIXUP_PER_SM")) v.fixup_per_sm = atoi(e);
         if (const char* e = getenv("MM_CRYSTAL_FORCE_GENERAL")) v.force_general = (e[0] == '1');
         if (const char* e = getenv("MM_CRYSTAL_VARIANT")) v.variant = atoi(e);
+        if (const char* e = getenv("MM_CRYSTAL_FINISH_PREFETCH")) v.finish_pf = atoi(e);
         return v;
     }();
     return k;
@@ -420,11 +421,20 @@ crystal_newton_phased_kernel(const CrystalNK k, const Ptrs<2, 3> p, uint16_t* ac
 #endif
 template <bool HASQ, bool INTPOW, int LAYOUT, int BS>
 __global__ void __launch_bounds__(BS, MM_CRYSTAL_FINISH_MINBLOCKS)
-crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, int32_t* n_fail, const double* xbuf, const int64_t N, const int* cnt, const int* idx, int* n_general) {
+crystal_finish_kernel(const CrystalK k, const Ptrs<2, 3> p, uint16_t* active, int32_t* n_fail, const double* xbuf, const int64_t N, const int* cnt, const int* idx, int* n_general, const int pf) {
     extern __shared__ double sm_scratch[];
     const Scratch scr{sm_scratch + threadIdx.x, BS};
     const int64_t i = (int64_t)blockIdx.x * BS + threadIdx.x;
     if (i >= (cnt ? (int64_t)*cnt : N)) return;
+    if (LAYOUT == 0 && pf > 0 && !idx && (threadIdx.x & 15) == 0 && i + pf < N) {      // L2 hint for the rows of the points `pf` further on ("crystal_finish_prefetch"; see soa_kernel)
+        const int64_t j = i + pf;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in[0] + (int64_t)c * N + j));
+#pragma unroll
+        for (int c = 0; c < 42; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in[1] + (int64_t)c * N + j));
+#pragma unroll
+        for (int c = 0; c < 12; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(xbuf ? xbuf + (int64_t)c * N + j : p.out[2] + (int64_t)(30 + c) * N + j));
+    }
     const unsigned status = active[i];
     if (status & MM_ACTIVE_NEEDS_GENERAL) return;                     // left to the fix-up pass
     DirectAccRW<LAYOUT> acc(p, N, i, idx ? (int64_t)idx[i] : i, xbuf);
@@ -527,7 +537,7 @@ int launch_crystal_two_kernel(const CrystalK& k, uint16_t* active, uint16_t* ite
     }
     if (ws) cudaFreeAsync(ws, st);
     if (rc) return rc;
-    crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS><<<(unsigned)((N + FBS - 1) / FBS), FBS, fsmem, st>>>(k, ptrs, active, n_fail, xbuf, N, cnt, idx, n_general);
+    crystal_finish_kernel<HASQ, INTPOW, LAYOUT, FBS><<<(unsigned)((N + FBS - 1) / FBS), FBS, fsmem, st>>>(k, ptrs, active, n_fail, xbuf, N, cnt, idx, n_general, crystal_knobs().finish_pf);
     return check_launch("mm_crystal (finish kernel)");
 }
 
@@ -624,6 +634,7 @@ extern "C" int mm_set_tuning(const char* name, int value) {
     else if (!strcmp(name, "crystal_chunk")) slot = &k.chunk;
     else if (!strcmp(name, "crystal_fixup_per_sm")) slot = &k.fixup_per_sm;
     else if (!strcmp(name, "crystal_variant")) slot = &k.variant;
+    else if (!strcmp(name, "crystal_finish_prefetch")) slot = &k.finish_pf;
     if (!slot) slot = mm::wrap_tuning_slot(name);              // "wrapped_j2_*" knobs live next to their kernel (mm_wrap.cu)
     if (!slot) slot = mm::ops_tuning_slot(name);               // "xu_soa_tiled" (mm_ops.cu)
     if (!slot) slot = mm::host_tuning_slot(name);              // "mmh_plastic_via_factored" (mm_host.cu)

@@ -444,6 +444,32 @@ def test_crystal_zero_sign_candidates_and_idle_points(mm, torch, oracle, cuda_li
         cuda_lib.mm_set_tuning(b"crystal_variant", old)
 
 
+@pytest.mark.parametrize("N", [1, 4097, 50021])
+def test_crystal_finish_l2_prefetch_hint_changes_no_bit(mm, torch, cuda_lib, N):
+    """mm_set_tuning("crystal_finish_prefetch", d): the finish kernel asks L2 for the SoA input lines of the points d ahead (mm_crystal.cu).
+    A hint: σ, tangent, state, masks and counts are the same words with it (default, a short distance, one past the end) and without it."""
+    cm = make_crystal(mm)
+    st = mm.initial_material_state(cm, N)
+    res = {}
+    for d in (0, 4096, 32, N, 10**9):
+        old = cuda_lib.mm_set_tuning(b"crystal_finish_prefetch", d)
+        try:
+            s0 = st
+            got = []
+            for step in (0, 1):
+                nc, lo, hi, seed = sy.c4_strain_increment(step)
+                de = mm.synth_uniform(N, nc, seed, lo, hi)
+                sg, tg, s0 = mm.material_response(cm, de, s0, 1.0, options={"defer_check": True})
+                torch.cuda.synchronize()
+                got += [sg.clone(), tg.clone(), s0.data.clone(), s0.flags.clone(), s0.iters.clone()]
+            res[d] = got
+        finally:
+            cuda_lib.mm_set_tuning(b"crystal_finish_prefetch", old)
+    for d, got in res.items():
+        for a, b in zip(res[0], got):
+            assert torch.equal(a.view(torch.int64) if a.dtype == torch.float64 else a, b.view(torch.int64) if b.dtype == torch.float64 else b), d
+
+
 def test_crystal_golden_path(mm, torch, golden):
     g = golden["CrystalViscoPlastic1"]
     m = make_crystal(mm)
